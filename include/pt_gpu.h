@@ -1,0 +1,235 @@
+/* pt_gpu.h -- C-ABI of libptgpu.so, the B200-native batched tree-containment + LCA engine.
+ *
+ * The reference (igel-kun/phylo_tools) is header-only C++17 with NO plugin / FFI layer; the
+ * boundary a maintainer would bind is therefore its template API.  Every entry point below names the
+ * reference interface it stands in for (file:line relative to the reference checkout).  The C++ facade in
+ * phylo_tools_b200/include/pt/ keeps the reference's names on top of this ABI; INTEGRATION.md shows the
+ * reference-side stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *   - every function returns PT_OK (0) or a negative pt_status; pt_last_error() gives the text
+ *     (thread-local).  The reference throws std::logic_error / MalformedNewick instead
+ *     (utils/storage_adj_common.hpp:103-109, utils/label_matching.hpp:51-52, io/newick.hpp:15-26);
+ *     the facade re-throws those types from the status codes.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All device work of a
+ *     call is enqueued on it.  Calls with HOST output buffers synchronise the stream before returning;
+ *     calls with DEVICE output buffers are asynchronous.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point returns
+ *     PT_ERR_NO_DEVICE.
+ *   - handles are single-owner; distinct handles may be used from distinct host threads.
+ */
+#ifndef PT_GPU_H_
+#define PT_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_GPU_ABI_VERSION 1
+
+typedef enum pt_status {
+  PT_OK = 0,
+  PT_ERR_INVALID = -1,     /* malformed arguments / structurally invalid input                        */
+  PT_ERR_CUDA = -2,        /* a CUDA runtime call failed (text in pt_last_error)                      */
+  PT_ERR_NOMEM = -3,       /* host or device allocation failed                                        */
+  PT_ERR_NO_DEVICE = -4,   /* no CUDA device: the engine has no CPU path                              */
+  PT_ERR_UNSUPPORTED = -5, /* instance exceeds an engine limit (see pt_limits)                        */
+  PT_ERR_PARSE = -6        /* MalformedNewick / MalformedEdgeVec (io/newick.hpp:15, io/edgelist.hpp:10) */
+} pt_status;
+
+typedef enum pt_mem { PT_MEM_HOST = 0, PT_MEM_DEVICE = 1 } pt_mem;
+
+const char* pt_last_error(void);
+int pt_abi_version(void);
+/* number of visible CUDA devices (0 without a GPU; never fails) */
+int pt_device_count(void);
+/* select the device used by subsequent calls of this thread (one process per GPU: call once with LOCAL_RANK) */
+int pt_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * LCA  -- replaces  Tree::LCA / naiveLCA            utils/tree.hpp:202-223
+ *                   lca<node_t>::lca(root), query   rmq/lca.hpp:79-106
+ * Input is the tree as a parent array (parent[root] < 0; exactly one root); answers are node ids and
+ * therefore unique -- bit-exact against either reference implementation.
+ * Internals: preorder positions instead of the 2n-1 Euler tour, 32-wide blocks, a sparse
+ * table over packed (depth,parent) block minima (rmq/sparse_rmq.hpp:45-90 re-designed), one 32-byte record
+ * per node so a query is two random sector reads plus two table reads that stay in L2.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_lca pt_lca;
+
+typedef struct pt_lca_info {
+  int64_t num_nodes;
+  int64_t num_levels;      /* depth of the tree + 1 (number of wavefront steps of the build)           */
+  int64_t num_blocks;      /* 32-position blocks                                                       */
+  int64_t table_levels;    /* levels of the block sparse table                                         */
+  int64_t device_bytes;    /* bytes kept resident for queries                                          */
+  float build_ms;          /* device time of the build (CUDA events)                                   */
+} pt_lca_info;
+
+int pt_lca_build(pt_lca** out, const int32_t* parent, int64_t n, pt_mem parent_mem, void* stream);
+int pt_lca_query(const pt_lca* h, const int32_t* u, const int32_t* v, int32_t* out, int64_t q,
+                 pt_mem mem, void* stream);
+int pt_lca_get_info(const pt_lca* h, pt_lca_info* info);
+/* depth[v] and preorder position of every node (DEVICE or HOST output, n entries each; either may be NULL);
+ * the order_number / dist_to_root of InducedSubtreeInfo  utils/induced_tree.hpp:11-35 */
+int pt_lca_node_info(const pt_lca* h, int32_t* depth, int32_t* preorder, pt_mem mem, void* stream);
+int pt_lca_free(pt_lca* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * RMQ -- replaces  rmq<It>::query / query_offset    rmq/rmq.hpp:63-74
+ *                  sparse_rmq                        rmq/sparse_rmq.hpp:45-90
+ * query over the half-open range [l, r), l < r; returns the index of the RIGHTMOST minimum, which is what
+ * sparse_rmq returns (ties -> right operand, sparse_rmq.hpp:63,89).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_rmq pt_rmq;
+int pt_rmq_build(pt_rmq** out, const int32_t* values, int64_t n, pt_mem mem, void* stream);
+int pt_rmq_query(const pt_rmq* h, const int64_t* l, const int64_t* r, int64_t* out_index, int64_t q,
+                 pt_mem mem, void* stream);
+int pt_rmq_free(pt_rmq* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched tree containment -- replaces
+ *     TreeInNetContainment(host, guest).displayed()   utils/containment.hpp:1179-1182,1202
+ *     TreeInTreeContainment(host, guest).displayed()  utils/containment.hpp:50-54,83
+ *     the `tc` dispatch                               examples/tc.cpp:130-144
+ * for B independent (host network, guest tree) instances at once.
+ *
+ * Flat layout (all int32 unless noted; instance i owns the slices given by the three offset tables):
+ *   host_node_off[B+1], host_arc_off[B+1], guest_node_off[B+1]   (int64 prefix sums of n_i, m_i, nt_i)
+ *   host_succ_off  : sum(n_i + 1) entries; instance i starts at host_node_off[i] + i; values are LOCAL arc
+ *                    positions 0..m_i  (the immutable CSR of utils/storage_adj_immutable.hpp:173-261)
+ *   host_succ_adj  : sum(m_i) entries at host_arc_off[i]; LOCAL node ids (children)
+ *   host_label     : sum(n_i) entries at host_node_off[i]; per-instance dense label id >= 0, or -1 = unlabelled
+ *                    ("" in the reference, utils/tree.hpp:138-148).  Host and guest of one instance share
+ *                    the dictionary; ids must be < n_i + nt_i.
+ *   guest_parent   : sum(nt_i) entries at guest_node_off[i]; LOCAL parent id, -1 for the root
+ *   guest_label    : sum(nt_i) entries
+ *   OPTIONAL (may be NULL; accepted for layout compatibility with SURVEY 8(b), not read by the kernels):
+ *   host_pred_off / host_pred_adj (same shapes as succ), guest_child_off (sum(nt_i+1)), guest_child_adj (sum(nt_i-1))
+ *
+ * Semantics (the definition the reference intends, containment.hpp:955-957,1110-1125,1061):
+ *   only labels on out-degree-0 nodes count; a label only in the guest => not displayed; a label only in
+ *   the host => that leaf is deleted; <= 2 common labels => displayed; otherwise displayed iff some
+ *   switching of the host (one in-arc kept per node), after removing unlabelled dangling nodes and
+ *   suppressing in=out=1 nodes on both sides, equals the guest.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_batch pt_batch;
+
+typedef struct pt_batch_desc {
+  int64_t num_instances;
+  pt_mem mem;                      /* where ALL arrays below live                                     */
+  const int64_t* host_node_off;
+  const int64_t* host_arc_off;
+  const int64_t* guest_node_off;
+  const int32_t* host_succ_off;
+  const int32_t* host_succ_adj;
+  const int32_t* host_label;
+  const int32_t* guest_parent;
+  const int32_t* guest_label;
+  const int32_t* host_pred_off;    /* optional */
+  const int32_t* host_pred_adj;    /* optional */
+  const int32_t* guest_child_off;  /* optional */
+  const int32_t* guest_child_adj;  /* optional */
+  /* per-batch maxima; 0 = let the library compute them (one extra pass + sync for DEVICE input) */
+  int32_t max_host_nodes, max_host_arcs, max_guest_nodes, max_labels;
+} pt_batch_desc;
+
+/* per-instance status written next to the verdict bit */
+typedef enum pt_inst_status {
+  PT_INST_OK = 0,
+  PT_INST_MULTILABEL = 1,   /* duplicate leaf label: std::logic_error in label_matching.hpp:51-52,61-62 */
+  PT_INST_BAD_GRAPH = 2,    /* index out of range, cycle, no/multiple roots (storage_adj_common.hpp:103-109) */
+  PT_INST_TOO_LARGE = 3,    /* exceeds pt_limits for the on-chip solver                                 */
+  PT_INST_POOL_OVERFLOW = 4 /* branching pool exhausted (raise pt_options.pool_slots)                   */
+} pt_inst_status;
+
+typedef struct pt_counters {
+  uint64_t instances;
+  uint64_t displayed;
+  uint64_t not_displayed;
+  uint64_t errors;               /* instances whose status != PT_INST_OK                               */
+  uint64_t resolved_by_rules;    /* decided without branching                                          */
+  uint64_t branched;             /* original instances that needed >= 1 branching                      */
+  uint64_t work_items;           /* (sub)instances solved over all rounds                              */
+  uint64_t rounds;               /* kernel launches of the reduce kernel                               */
+  uint64_t cherry_reductions;    /* true (multi-)cherries collapsed        (CherryPicker  :500-600)    */
+  uint64_t reticulated_cherries; /* reticulation parents fixed                                         */
+  uint64_t arcs_deleted;         /* arcs removed by the sibling-constraint rule                        */
+  uint64_t rule_passes;          /* rule-loop iterations summed over work items (apply_rules :1054)    */
+} pt_counters;
+
+typedef struct pt_options {
+  int32_t pool_slots;        /* capacity of the branching pool per round (0 = default)                  */
+  int32_t max_rounds;        /* safety bound on branching depth (0 = default 64)                        */
+  int32_t reserved[6];
+} pt_options;
+
+typedef struct pt_limits {
+  int32_t max_host_nodes, max_host_arcs, max_guest_nodes, max_labels; /* on-chip (shared-memory) solver */
+} pt_limits;
+int pt_get_limits(pt_limits* out);
+
+/* HOST input is copied to the device here (the h2d leg of the end-to-end path); DEVICE input is referenced,
+ * not copied, and must stay valid until pt_batch_free. */
+int pt_batch_create(pt_batch** out, const pt_batch_desc* desc, void* stream);
+/* result_bits: ceil(B/32) uint32 words, bit (i & 31) of word (i >> 5) = instance i displayed.
+ * status: B bytes (pt_inst_status), may be NULL.  counters may be NULL (always HOST memory).
+ * out_mem says where result_bits/status live. */
+int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, uint8_t* status,
+                     pt_mem out_mem, pt_counters* counters, void* stream);
+/* number of kernel launches issued by the last pt_batch_contain on this handle (for bench.py gpu_launches) */
+int64_t pt_batch_last_launches(const pt_batch* b);
+int pt_batch_free(pt_batch* b);
+
+/* ------------------------------------------------------------------------------------------------
+ * Exhaustive switching enumeration (one instance, a range of the mixed-radix switching index).
+ * The reference has no counterpart: it branches on one reticulation at a time (containment.hpp:1225-1266);
+ * the verdict semantics are identical (exists a switching).  Used for general networks that do not reduce
+ * and to shard [0, prod in-degree) across GPUs.
+ * Instance arrays as in pt_batch_desc but for ONE instance (HOST memory).
+ * n_switchings receives the size of the full index space; n_displaying the number of indices in
+ * [begin, end) whose switching displays the guest; first_index the smallest such index or UINT64_MAX.
+ * end == 0 means "to the end".
+ * ---------------------------------------------------------------------------------------------- */
+int pt_enum_switchings(int32_t n, int32_t m, const int32_t* succ_off, const int32_t* succ_adj, const int32_t* host_label,
+                       int32_t nt, const int32_t* guest_parent, const int32_t* guest_label,
+                       uint64_t begin, uint64_t end, int stop_at_first,
+                       uint64_t* n_switchings, uint64_t* n_displaying, uint64_t* first_index, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-side readers / generators (no GPU needed).  C wrappers over the C++ facade so that non-C++ callers
+ * (the ctypes tests, bench.py) reach the same code.
+ * ---------------------------------------------------------------------------------------------- */
+/* parse_newick  io/newick.hpp:274-290 : node ids = right-to-left preorder, root 0; edges in the
+ * reference's (post-order) sequence.  Two-call protocol: call with edges == NULL to get the sizes.
+ * labels: concatenated NUL-terminated strings, label_node[k] = node of the k-th string. */
+int pt_parse_newick(const char* text, int64_t* num_nodes, int64_t* num_edges, int32_t* edges /* 2*num_edges */,
+                    int64_t* num_labels, int32_t* label_node, char* label_buf, int64_t* label_buf_len);
+
+/* Opaque packer: accumulates (host newick, guest newick) pairs into the flat layout of pt_batch_desc. */
+typedef struct pt_packer pt_packer;
+int pt_packer_create(pt_packer** out);
+/* returns PT_ERR_PARSE / PT_ERR_INVALID for a malformed pair (nothing is added) */
+int pt_packer_add_newick(pt_packer* p, const char* host_newick, const char* guest_newick);
+/* adds `count` synthetic instances: the generate_random_binary_edgelist_trl process (utils/generator.hpp:175-245)
+ * with a seeded PRNG (seed + instance index), guest = tree displayed by a uniform random switching with shuffled
+ * child order; kind 0 = positive, 1 = guest with two leaf labels swapped, 2 = random guest tree on the same labels */
+int pt_packer_add_generated(pt_packer* p, int64_t count, int32_t num_leaves, int32_t num_retis, uint64_t seed, int kind);
+/* fills `desc` with pointers into the packer's HOST buffers (valid until the next add / free) */
+int pt_packer_desc(pt_packer* p, pt_batch_desc* desc);
+/* extended Newick text of instance i (host, then guest); two-call protocol on buffer lengths */
+int pt_packer_get_newick(pt_packer* p, int64_t i, char* host_buf, int64_t* host_len, char* guest_buf, int64_t* guest_len);
+int pt_packer_free(pt_packer* p);
+
+/* random rooted binary tree with `num_leaves` leaves as a parent array of 2*num_leaves-1 entries
+ * ("repeatedly join two uniformly chosen roots"), seeded */
+int pt_gen_random_tree(int64_t num_leaves, uint64_t seed, int32_t* parent_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PT_GPU_H_ */

@@ -1,0 +1,236 @@
+/* oracle/pt_oracle.c -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+ *
+ * Plain-C CPU restatement of the reference's hot path, used exclusively as the CHECKER by tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg.  Nothing in phylo_tools_b200/ (the product)
+ * links, imports or calls this file.
+ *
+ * What is restated, and from where (file:line relative to the reference checkout):
+ *   orc_tc_bruteforce   -- the containment SEMANTICS that utils/containment.hpp:955-957 (TreeInNetContainment)
+ *                          decides: "N displays T iff some switching of N, cleaned up, equals T".  Cleaning =
+ *                          NodeSuppresser::clean_up_node containment.hpp:756-824 (drop unlabelled dangling
+ *                          leaves, suppress in=out=1 nodes); label clean-up = containment.hpp:1110-1125
+ *                          (label only in T => not displayed; label only in N => leaf removed);
+ *                          <=2 common labels => displayed (containment.hpp:1061,1208).
+ *                          The reference decides this with reduction rules + branching (and is unreliable,
+ *                          SURVEY F4); the oracle enumerates all prod(in-degree) switchings, which is the
+ *                          definition.  PARITY PINNING: no golden verdicts exist in the reference
+ *                          (SURVEY 4.2); pinned instead against outputs of the reference itself run in the
+ *                          build container (tests/golden/tc_ref_verdicts.json, made by oracle/make_golden.py).
+ *   orc_lca_naive       -- Tree::naiveLCA utils/tree.hpp:202-219 (alternating parent walk with a seen set).
+ *   orc_lca_euler_*     -- rmq/lca.hpp:61-106: Euler tour (node emitted on entry and after each child),
+ *                          depth array, node -> LAST Euler index, RMQ over depths.
+ *   orc_sparse_rmq_*    -- rmq/sparse_rmq.hpp:45-90: table[d][i] = index of min of [i, i+2^d); on ties the
+ *                          RIGHT operand wins (val(x) < val(y) ? x : y), so the rightmost minimum is returned.
+ *                          Pinned by the known answers of rmq/rmq_test.hpp:51-109, rmq/pm_rmq_test.hpp:41-44
+ *                          and rmq/lca.cpp:46-49 (tests/test_oracle.py).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MAXW 16 /* up to 1024 common labels */
+
+typedef struct { uint64_t w[ORC_MAXW]; } bits_t;
+
+static int cmp_bits_W;
+static int cmp_bits(const void* a, const void* b) { return memcmp(a, b, (size_t)cmp_bits_W * 8); }
+
+/* reverse topological order of a DAG given as arc list; returns 0 on success, -1 if cyclic */
+static int topo_order(int n, int m, const int32_t* tail, const int32_t* head, int32_t* order) {
+  int32_t* indeg = (int32_t*)calloc((size_t)n, 4); int32_t* off = (int32_t*)calloc((size_t)n + 1, 4); int32_t* adj = (int32_t*)malloc((size_t)(m > 0 ? m : 1) * 4);
+  for (int e = 0; e < m; ++e) { indeg[head[e]]++; off[tail[e] + 1]++; }
+  for (int v = 0; v < n; ++v) off[v + 1] += off[v];
+  int32_t* pos = (int32_t*)malloc((size_t)n * 4); memcpy(pos, off, (size_t)n * 4);
+  for (int e = 0; e < m; ++e) adj[pos[tail[e]]++] = head[e];
+  int cnt = 0;
+  for (int v = 0; v < n; ++v) if (!indeg[v]) order[cnt++] = v;
+  for (int i = 0; i < cnt; ++i) { int v = order[i]; for (int k = off[v]; k < off[v + 1]; ++k) if (--indeg[adj[k]] == 0) order[cnt++] = adj[k]; }
+  free(indeg); free(off); free(adj); free(pos);
+  return cnt == n ? 0 : -1;
+}
+
+/* Sorted set of clusters (size>=2) of the cleaned tree obtained from a DAG in which every node has
+ * at most ONE active in-arc (act[e] != 0).  lab[v] = bit index of the leaf label, or -1. */
+static int clusters_of(int n, int m, const int32_t* tail, const int32_t* head, const uint8_t* act,
+                       const int32_t* lab, const int32_t* order, int W, bits_t* cl, int32_t* nalive, bits_t* out) {
+  for (int v = 0; v < n; ++v) { memset(&cl[v], 0, sizeof(bits_t)); nalive[v] = 0; if (lab[v] >= 0) cl[v].w[lab[v] >> 6] |= 1ull << (lab[v] & 63); }
+  /* process nodes children-first: walk the topological order backwards, pushing each node's cluster up its active in-arc */
+  int32_t* up = (int32_t*)malloc((size_t)n * 4);
+  for (int v = 0; v < n; ++v) up[v] = -1;
+  for (int e = 0; e < m; ++e) if (act[e]) up[head[e]] = tail[e];
+  int cnt = 0;
+  for (int i = n - 1; i >= 0; --i) {
+    int v = order[i]; int nz = 0;
+    for (int k = 0; k < W; ++k) nz |= cl[v].w[k] != 0;
+    if (!nz) continue;                      /* dead: unlabelled, nothing alive below */
+    if (nalive[v] >= 2) out[cnt++] = cl[v]; /* a branching node of the cleaned tree */
+    int p = up[v];
+    if (p >= 0) { for (int k = 0; k < W; ++k) cl[p].w[k] |= cl[v].w[k]; nalive[p]++; }
+  }
+  free(up);
+  cmp_bits_W = W; qsort(out, (size_t)cnt, sizeof(bits_t), cmp_bits);
+  return cnt;
+}
+
+/* Exhaustive-switching containment.
+ * Host: nh nodes, mh arcs (htail/hhead), hlab[v] = label id (any non-negative int) or -1 for unlabelled.
+ * Guest: nt nodes, mt arcs, tlab likewise; guest must be a tree.  Labels on nodes with out-degree > 0 are ignored.
+ * Returns 1 displayed, 0 not displayed, <0 error (-1 cyclic, -2 duplicate leaf label, -3 too many labels,
+ * -4 guest not a tree, -5 too many switchings (> max_switchings)).
+ * n_displaying (optional) receives the number of switchings that display the guest (only when the full
+ * enumeration runs, i.e. stop_at_first == 0). first_index (optional) receives the first displaying mixed-radix index. */
+int orc_tc_bruteforce(int nh, int mh, const int32_t* htail, const int32_t* hhead, const int32_t* hlab,
+                      int nt, int mt, const int32_t* ttail, const int32_t* thead, const int32_t* tlab,
+                      int stop_at_first, uint64_t max_switchings, uint64_t* n_displaying, uint64_t* first_index) {
+  if (n_displaying) *n_displaying = 0;
+  if (first_index) *first_index = UINT64_MAX;
+  if (mt != nt - 1 && !(nt == 0 && mt == 0)) return -4;
+  int32_t* hout = (int32_t*)calloc((size_t)nh + 1, 4); int32_t* tout = (int32_t*)calloc((size_t)nt + 1, 4); int32_t* tin = (int32_t*)calloc((size_t)nt + 1, 4);
+  for (int e = 0; e < mh; ++e) hout[htail[e]]++;
+  for (int e = 0; e < mt; ++e) { tout[ttail[e]]++; if (++tin[thead[e]] > 1) { free(hout); free(tout); free(tin); return -4; } }
+  /* dictionary of leaf labels */
+  int32_t maxlab = -1;
+  for (int v = 0; v < nh; ++v) if (hlab[v] > maxlab) maxlab = hlab[v];
+  for (int v = 0; v < nt; ++v) if (tlab[v] > maxlab) maxlab = tlab[v];
+  int32_t* in_h = (int32_t*)malloc((size_t)(maxlab + 2) * 4); int32_t* in_t = (int32_t*)malloc((size_t)(maxlab + 2) * 4);
+  for (int i = 0; i <= maxlab; ++i) in_h[i] = in_t[i] = -1;
+  int rc = 1, dup = 0;
+  for (int v = 0; v < nh; ++v) if (hlab[v] >= 0 && hout[v] == 0) { if (in_h[hlab[v]] >= 0) dup = 1; in_h[hlab[v]] = v; }
+  for (int v = 0; v < nt; ++v) if (tlab[v] >= 0 && tout[v] == 0) { if (in_t[tlab[v]] >= 0) dup = 1; in_t[tlab[v]] = v; }
+  int32_t* hl = (int32_t*)malloc((size_t)(nh > 0 ? nh : 1) * 4); int32_t* tl = (int32_t*)malloc((size_t)(nt > 0 ? nt : 1) * 4);
+  for (int v = 0; v < nh; ++v) hl[v] = -1;
+  for (int v = 0; v < nt; ++v) tl[v] = -1;
+  int ncommon = 0, t_only = 0;
+  for (int i = 0; i <= maxlab; ++i) {
+    if (in_t[i] >= 0 && in_h[i] < 0) t_only = 1;                       /* containment.hpp:1116 */
+    if (in_t[i] >= 0 && in_h[i] >= 0) { hl[in_h[i]] = ncommon; tl[in_t[i]] = ncommon; ncommon++; } /* host-only labels stay -1: :1117-1121 */
+  }
+  free(in_h); free(in_t); free(hout); free(tout); free(tin);
+  if (dup) { free(hl); free(tl); return -2; }
+  if (t_only) { free(hl); free(tl); return 0; }
+  if (ncommon <= 2) { free(hl); free(tl); if (n_displaying) *n_displaying = 0; if (first_index) *first_index = 0; return 1; } /* :1061,1208 */
+  int W = (ncommon + 63) / 64;
+  if (W > ORC_MAXW) { free(hl); free(tl); return -3; }
+  int32_t* horder = (int32_t*)malloc((size_t)nh * 4); int32_t* torder = (int32_t*)malloc((size_t)nt * 4);
+  if (topo_order(nh, mh, htail, hhead, horder) || topo_order(nt, mt, ttail, thead, torder)) { free(hl); free(tl); free(horder); free(torder); return -1; }
+  int nmax = nh > nt ? nh : nt;
+  bits_t* cl = (bits_t*)malloc((size_t)nmax * sizeof(bits_t)); int32_t* nal = (int32_t*)malloc((size_t)nmax * 4);
+  bits_t* tcl = (bits_t*)malloc((size_t)nt * sizeof(bits_t)); bits_t* hcl = (bits_t*)malloc((size_t)nh * sizeof(bits_t));
+  uint8_t* tact = (uint8_t*)malloc((size_t)(mt > 0 ? mt : 1)); memset(tact, 1, (size_t)(mt > 0 ? mt : 1));
+  int tcnt = clusters_of(nt, mt, ttail, thead, tact, tl, torder, W, cl, nal, tcl);
+  /* reticulations and their in-arcs */
+  int32_t* indeg = (int32_t*)calloc((size_t)nh, 4);
+  for (int e = 0; e < mh; ++e) indeg[hhead[e]]++;
+  int nr = 0; for (int v = 0; v < nh; ++v) if (indeg[v] >= 2) nr++;
+  int32_t* rnode = (int32_t*)malloc((size_t)(nr > 0 ? nr : 1) * 4); int32_t* ridx = (int32_t*)malloc((size_t)nh * 4);
+  nr = 0; for (int v = 0; v < nh; ++v) { ridx[v] = -1; if (indeg[v] >= 2) { ridx[v] = nr; rnode[nr++] = v; } }
+  int32_t* roff = (int32_t*)calloc((size_t)nr + 1, 4);
+  for (int i = 0; i < nr; ++i) roff[i + 1] = roff[i] + indeg[rnode[i]];
+  int32_t* rarc = (int32_t*)malloc((size_t)(roff[nr] > 0 ? roff[nr] : 1) * 4); int32_t* fill = (int32_t*)calloc((size_t)(nr > 0 ? nr : 1), 4);
+  for (int e = 0; e < mh; ++e) { int r = ridx[hhead[e]]; if (r >= 0) rarc[roff[r] + fill[r]++] = e; }
+  uint64_t total = 1; int overflow = 0;
+  for (int i = 0; i < nr; ++i) { uint64_t d = (uint64_t)indeg[rnode[i]]; if (total > max_switchings / d) { overflow = 1; break; } total *= d; }
+  uint8_t* act = (uint8_t*)malloc((size_t)(mh > 0 ? mh : 1));
+  uint64_t ndisp = 0, first = UINT64_MAX;
+  if (overflow) rc = -5;
+  else {
+    for (uint64_t s = 0; s < total; ++s) {
+      for (int e = 0; e < mh; ++e) act[e] = ridx[hhead[e]] < 0;
+      uint64_t x = s;
+      for (int i = 0; i < nr; ++i) { int d = indeg[rnode[i]]; act[rarc[roff[i] + (int)(x % (uint64_t)d)]] = 1; x /= (uint64_t)d; }
+      int hcnt = clusters_of(nh, mh, htail, hhead, act, hl, horder, W, cl, nal, hcl);
+      if (hcnt == tcnt && memcmp(hcl, tcl, (size_t)hcnt * sizeof(bits_t)) == 0) {
+        /* memcmp over whole bits_t is fine: unused words are zero on both sides */
+        if (first == UINT64_MAX) first = s;
+        ndisp++;
+        if (stop_at_first) break;
+      }
+    }
+    rc = ndisp > 0;
+  }
+  if (n_displaying) *n_displaying = ndisp;
+  if (first_index) *first_index = first;
+  free(hl); free(tl); free(horder); free(torder); free(cl); free(nal); free(tcl); free(hcl); free(tact); free(indeg);
+  free(rnode); free(ridx); free(roff); free(rarc); free(fill); free(act);
+  return rc;
+}
+
+/* ---- LCA: utils/tree.hpp:202-219 (naiveLCA): alternate parent steps from x and y, first node seen twice wins ---- */
+int32_t orc_lca_naive(const int32_t* parent, int32_t n, int32_t x, int32_t y, uint8_t* seen /* n bytes, zeroed; restored on return */) {
+  int32_t touched_cap = 64, nt = 0; int32_t* touched = (int32_t*)malloc((size_t)touched_cap * 4); int32_t res = -1;
+  (void)n;
+  while (x != y) {
+    int32_t* zs[2] = {&x, &y}; int done = 0;
+    for (int k = 0; k < 2 && !done; ++k) {
+      int32_t* z = zs[k];
+      if (parent[*z] < 0) continue;               /* update_for_LCA: root never moves (tree.hpp:214) */
+      if (seen[*z]) { res = *z; done = 1; break; }
+      seen[*z] = 1; if (nt == touched_cap) { touched_cap *= 2; touched = (int32_t*)realloc(touched, (size_t)touched_cap * 4); } touched[nt++] = *z;
+      *z = parent[*z];
+    }
+    if (done) break;
+  }
+  if (res < 0) res = x;
+  for (int i = 0; i < nt; ++i) seen[touched[i]] = 0;
+  free(touched);
+  return res;
+}
+void orc_lca_naive_batch(const int32_t* parent, int32_t n, const int32_t* u, const int32_t* v, int32_t* out, int64_t q) {
+  uint8_t* seen = (uint8_t*)calloc((size_t)n, 1);
+  for (int64_t i = 0; i < q; ++i) out[i] = orc_lca_naive(parent, n, u[i], v[i], seen);
+  free(seen);
+}
+
+/* ---- sparse_rmq: rmq/sparse_rmq.hpp:45-90 ---- */
+typedef struct { int64_t n; int levels; const int32_t* val; int64_t** arr; } orc_sparse_rmq;
+static int floor_log2_i64(int64_t x) { int l = 0; while ((x >> (l + 1)) > 0) ++l; return l; }
+orc_sparse_rmq* orc_sparse_rmq_build(const int32_t* val, int64_t n) {
+  orc_sparse_rmq* R = (orc_sparse_rmq*)malloc(sizeof(*R)); R->n = n; R->val = val;
+  int logn = n >= 2 ? floor_log2_i64(n) : 1; if (logn < 1) logn = 1;      /* max(1, floor(log2 n)) :69-70 */
+  R->levels = logn + 1; R->arr = (int64_t**)calloc((size_t)R->levels, sizeof(int64_t*));
+  R->arr[0] = (int64_t*)malloc((size_t)(n > 0 ? n : 1) * 8);
+  for (int64_t i = 0; i < n; ++i) R->arr[0][i] = i;                        /* :48 */
+  for (int d = 0; d < logn; ++d) {                                          /* :52-65 */
+    int64_t width = (int64_t)1 << d, cnt = n - 2 * width + 1 + 0;           /* |arr[d]| - width = (n-2^d+1) - 2^d */
+    int64_t len_d = n - width + 1; cnt = len_d - width; if (cnt < 0) cnt = 0;
+    R->arr[d + 1] = (int64_t*)malloc((size_t)(cnt > 0 ? cnt : 1) * 8);
+    for (int64_t i = 0; i < cnt; ++i) { int64_t x = R->arr[d][i], y = R->arr[d][i + width]; R->arr[d + 1][i] = val[x] < val[y] ? x : y; }
+  }
+  return R;
+}
+/* query over the half-open range [u, v), u < v (rmq/rmq.hpp:56-63) */
+int64_t orc_sparse_rmq_query(const orc_sparse_rmq* R, int64_t u, int64_t v) {
+  int depth = (v - u - 1) >= 1 ? floor_log2_i64(v - u - 1) : 0;             /* max(0, floor(log2(v-u-1))) :82-83 */
+  int64_t px = R->arr[depth][u], py = R->arr[depth][v - ((int64_t)1 << depth)];
+  return R->val[px] < R->val[py] ? px : py;                                 /* :89 ties -> right */
+}
+void orc_sparse_rmq_free(orc_sparse_rmq* R) { for (int d = 0; d < R->levels; ++d) free(R->arr[d]); free(R->arr); free(R); }
+
+/* ---- lca: rmq/lca.hpp:61-106 (Euler tour + depth + last index) over a sparse_rmq ---- */
+typedef struct { int64_t n, E; int32_t* euler; int32_t* depth; int64_t* last; orc_sparse_rmq* rmq; } orc_lca;
+orc_lca* orc_lca_euler_build(const int32_t* parent, int32_t n) {
+  orc_lca* L = (orc_lca*)malloc(sizeof(*L)); L->n = n; L->E = 2 * (int64_t)n - 1;
+  L->euler = (int32_t*)malloc((size_t)L->E * 4); L->depth = (int32_t*)malloc((size_t)L->E * 4); L->last = (int64_t*)malloc((size_t)n * 8);
+  int32_t* off = (int32_t*)calloc((size_t)n + 1, 4); int32_t* adj = (int32_t*)malloc((size_t)n * 4); int32_t root = -1;
+  for (int32_t v = 0; v < n; ++v) { if (parent[v] < 0) root = v; else off[parent[v] + 1]++; }
+  for (int32_t v = 0; v < n; ++v) off[v + 1] += off[v];
+  int32_t* pos = (int32_t*)malloc((size_t)n * 4); memcpy(pos, off, (size_t)n * 4);
+  for (int32_t v = 0; v < n; ++v) if (parent[v] >= 0) adj[pos[parent[v]]++] = v;
+  /* iterative version of preprocess(): emit on entry and after each child (:61-71) */
+  int32_t* stk = (int32_t*)malloc((size_t)n * 4); int32_t* it = (int32_t*)malloc((size_t)n * 4); int sp = 0; int64_t k = 0; int32_t d = 0;
+  stk[sp] = root; it[sp] = off[root]; sp++; L->euler[k] = root; L->depth[k] = 0; L->last[root] = k; k++;
+  while (sp > 0) {
+    int32_t v = stk[sp - 1];
+    if (it[sp - 1] < off[v + 1]) { int32_t c = adj[it[sp - 1]++]; d++; stk[sp] = c; it[sp] = off[c]; sp++; L->euler[k] = c; L->depth[k] = d; L->last[c] = k; k++; }
+    else { sp--; d--; if (sp > 0) { int32_t p = stk[sp - 1]; L->euler[k] = p; L->depth[k] = d; L->last[p] = k; k++; } }
+  }
+  L->rmq = orc_sparse_rmq_build(L->depth, L->E);
+  free(off); free(adj); free(pos); free(stk); free(it);
+  return L;
+}
+int32_t orc_lca_euler_query(const orc_lca* L, int32_t u, int32_t v) {
+  int64_t a = L->last[u], b = L->last[v]; if (b < a) { int64_t t = a; a = b; b = t; }    /* :95-99 */
+  return L->euler[orc_sparse_rmq_query(L->rmq, a, b + 1)];
+}
+void orc_lca_euler_batch(const orc_lca* L, const int32_t* u, const int32_t* v, int32_t* out, int64_t q) { for (int64_t i = 0; i < q; ++i) out[i] = orc_lca_euler_query(L, u[i], v[i]); }
+void orc_lca_euler_free(orc_lca* L) { orc_sparse_rmq_free(L->rmq); free(L->euler); free(L->depth); free(L->last); free(L); }

@@ -1,0 +1,111 @@
+"""oracle/pt_oracle.py -- TEST INFRASTRUCTURE ONLY: ctypes access to oracle/libptoracle.so (pt_oracle.c)
+and to the reference binaries in oracle/_ref/.  Imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never by phylo_tools_b200/."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(HERE, "libptoracle.so")
+    src = os.path.join(HERE, "pt_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", src, "-o", so])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        i32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+        L.orc_tc_bruteforce.restype = C.c_int
+        L.orc_tc_bruteforce.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int, C.c_uint64, u64p, u64p]
+        L.orc_lca_naive_batch.restype = None
+        L.orc_lca_naive_batch.argtypes = [i32p, C.c_int32, i32p, i32p, i32p, C.c_int64]
+        L.orc_lca_euler_build.restype = C.c_void_p
+        L.orc_lca_euler_build.argtypes = [i32p, C.c_int32]
+        L.orc_lca_euler_batch.restype = None
+        L.orc_lca_euler_batch.argtypes = [C.c_void_p, i32p, i32p, i32p, C.c_int64]
+        L.orc_lca_euler_free.argtypes = [C.c_void_p]
+        L.orc_sparse_rmq_build.restype = C.c_void_p
+        L.orc_sparse_rmq_build.argtypes = [i32p, C.c_int64]
+        L.orc_sparse_rmq_query.restype = C.c_int64
+        L.orc_sparse_rmq_query.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        L.orc_sparse_rmq_free.argtypes = [C.c_void_p]
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _arr(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32))
+
+
+def tc_bruteforce(h_edges, h_n, h_labels, t_edges, t_n, t_labels, stop_at_first=True, max_switchings=1 << 26):
+    """h_edges/t_edges: lists of (tail, head); *_labels: int array (label id or -1) per node.
+    returns (verdict, n_displaying, first_index); verdict 1/0 or negative error."""
+    he = _arr(h_edges).reshape(-1, 2)
+    te = _arr(t_edges).reshape(-1, 2)
+    ht, hh = _arr(he[:, 0]), _arr(he[:, 1])
+    tt, th = _arr(te[:, 0]), _arr(te[:, 1])
+    hl, tl = _arr(h_labels), _arr(t_labels)
+    nd, fi = C.c_uint64(0), C.c_uint64(0)
+    rc = lib().orc_tc_bruteforce(int(h_n), len(ht), _p(ht), _p(hh), _p(hl), int(t_n), len(tt), _p(tt), _p(th), _p(tl),
+                                 1 if stop_at_first else 0, int(max_switchings), C.byref(nd), C.byref(fi))
+    return rc, nd.value, fi.value
+
+
+def tc_bruteforce_newick(host_nw, guest_nw, **kw):
+    """tc semantics of examples/tc.cpp:110-114 on two Newick strings, through oracle/newick.py"""
+    from .newick import parse_newick
+    n0, e0, l0 = parse_newick(host_nw)
+    n1, e1, l1 = parse_newick(guest_nw)
+    if len(e0) == n0 - 1 and len(e1) != n1 - 1:
+        n0, e0, l0, n1, e1, l1 = n1, e1, l1, n0, e0, l0
+    names = {}
+    def enc(n, lab):
+        out = np.full(n, -1, dtype=np.int32)
+        for v, s in lab.items():
+            out[v] = names.setdefault(s, len(names))
+        return out
+    return tc_bruteforce(e0, n0, enc(n0, l0), e1, n1, enc(n1, l1), **kw)
+
+
+def lca_naive(parent, u, v):
+    parent, u, v = _arr(parent), _arr(u), _arr(v)
+    out = np.empty(len(u), dtype=np.int32)
+    lib().orc_lca_naive_batch(_p(parent), len(parent), _p(u), _p(v), _p(out), len(u))
+    return out
+
+
+def lca_euler(parent, u, v):
+    parent, u, v = _arr(parent), _arr(u), _arr(v)
+    h = lib().orc_lca_euler_build(_p(parent), len(parent))
+    out = np.empty(len(u), dtype=np.int32)
+    lib().orc_lca_euler_batch(h, _p(u), _p(v), _p(out), len(u))
+    lib().orc_lca_euler_free(h)
+    return out
+
+
+def sparse_rmq(values, ls, rs):
+    values = _arr(values)
+    h = lib().orc_sparse_rmq_build(_p(values), len(values))
+    out = np.array([lib().orc_sparse_rmq_query(h, int(l), int(r)) for l, r in zip(ls, rs)], dtype=np.int64)
+    lib().orc_sparse_rmq_free(h)
+    return out
+
+
+def ref_binary(name):
+    """path of a reference binary built by oracle/Makefile (None if absent: /root/reference is not on the GPU box,
+    but the prebuilt oracle/_ref/ travels with the snapshot)"""
+    p = os.path.join(HERE, "_ref", name)
+    return p if os.path.exists(p) else None

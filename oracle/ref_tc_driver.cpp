@@ -1,0 +1,118 @@
+// oracle/ref_tc_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+// In-process driver over the UNMODIFIED reference headers (included from /root/reference at build
+// time; nothing is copied).  Include order follows examples/tc.cpp:2-10 (the headers are not
+// self-contained).  The reference prints unconditionally on the hot path, so std::cout is
+// silenced with badbit; it also crashes on many inputs, so every instance runs inside a
+// forked worker and the parent records SEGV/abort.
+//
+//   ref_tc verdicts <file> : file holds instance pairs (2 lines each: host newick, guest newick).
+//        prints one char per instance on stdout: 1 displayed, 0 not displayed, E exception, S signal.
+//   ref_tc bench <file> <max_instances> : no fork, times displayed() over the first max_instances
+//        instances in-process (use only on inputs known not to crash); prints a JSON line.
+//   ref_tc parse <file> : for each line: "n m" then edges "u v" in reference edge-list order, then
+//        labels "id name" sorted by id, then "--" (golden vectors for the Newick reader).
+#include "io/io.hpp"
+#include "utils/command_line.hpp"
+#include "utils/network.hpp"
+#include "utils/generator.hpp"
+#include "utils/mul_wrapper.hpp"
+#include "utils/containment.hpp"
+
+#include <chrono>
+#include <fstream>
+#include <csignal>
+#include <sys/wait.h>
+#include <unistd.h>
+
+using namespace PT;
+using MyTree = ROTree<>;
+using MyNet = CompatibleRWNetwork<MyTree>;
+using LabelMap = typename MyTree::LabelMap;
+using ENL = EdgesAndNodeLabels<MyTree, LabelMap>;
+
+static bool parse_line(const std::string& line, ENL& out) {
+  out.num_nodes = parse_newick(line, out.edges, *out.labels);
+  return true;
+}
+
+// mirrors examples/tc.cpp:98-142 (read_net_and_tree + main dispatch)
+static int run_instance(const std::string& l0, const std::string& l1) {
+  std::vector<ENL> el(2);
+  parse_line(l0, el[0]); parse_line(l1, el[1]);
+  const bool host_net_index = (el[0].is_tree() && !el[1].is_tree());
+  const bool guest_net_index = 1 - host_net_index;
+  MyNet N(std::move(el[host_net_index].edges), std::move(el[host_net_index].labels), consecutive_tag());
+  MyTree T(std::move(el[guest_net_index].edges), std::move(el[guest_net_index].labels), consecutive_tag());
+  if (!T.is_tree()) return 2;
+  if (N.is_tree()) { TreeInTreeContainment tc(std::move(N.as_tree()), std::move(T)); return tc.displayed() ? 1 : 0; }
+  TreeInNetContainment tc(std::move(N), std::move(T));
+  return tc.displayed() ? 1 : 0;
+}
+
+static std::vector<std::string> read_lines(const char* fn) {
+  std::ifstream in(fn); std::vector<std::string> L; std::string s;
+  while (std::getline(in, s)) { if (!s.empty()) L.push_back(s); }
+  return L;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) { fprintf(stderr, "usage: ref_tc verdicts|bench|parse <file> [max]\n"); return 1; }
+  std::string mode = argv[1];
+  std::vector<std::string> L = read_lines(argv[2]);
+  if (mode == "parse") {
+    std::cout.setstate(std::ios::badbit);
+    for (auto& line : L) {
+      ENL e; 
+      try { parse_line(line, e); } catch (std::exception& ex) { printf("ERR\n--\n"); continue; }
+      printf("%zu %zu\n", e.num_nodes, e.edges.size());
+      for (auto& ed : e.edges) printf("%zu %zu\n", (size_t)ed.tail(), (size_t)ed.head());
+      std::vector<std::pair<size_t, std::string>> labs;
+      for (auto&& p : *e.labels) if (!p.second.empty()) labs.emplace_back((size_t)p.first, p.second);
+      std::sort(labs.begin(), labs.end());
+      for (auto& p : labs) printf("L %zu %s\n", p.first, p.second.c_str());
+      printf("--\n");
+    }
+    return 0;
+  }
+  const size_t ninst = L.size() / 2;
+  if (mode == "bench") {
+    size_t maxi = argc > 3 ? (size_t)atol(argv[3]) : ninst; if (maxi > ninst) maxi = ninst;
+    std::cout.setstate(std::ios::badbit);
+    size_t disp = 0, exc = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (size_t i = 0; i < maxi; ++i) {
+      try { disp += run_instance(L[2 * i], L[2 * i + 1]) == 1; } catch (std::exception&) { ++exc; }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    double s = std::chrono::duration<double>(t1 - t0).count();
+    fprintf(stderr, "{\"instances\": %zu, \"displayed\": %zu, \"exceptions\": %zu, \"seconds\": %.6f, \"inst_per_s\": %.3f}\n", maxi, disp, exc, s, maxi / s);
+    return 0;
+  }
+  // verdicts: forked worker streams one char per instance through a pipe; on a crash the parent
+  // records 'S' for the instance the worker was on and restarts after it.
+  std::string out(ninst, '?');
+  size_t next = 0;
+  while (next < ninst) {
+    int fd[2]; if (pipe(fd)) return 3;
+    pid_t pid = fork();
+    if (pid == 0) {
+      close(fd[0]);
+      std::cout.setstate(std::ios::badbit);
+      for (size_t i = next; i < ninst; ++i) {
+        char c;
+        try { int r = run_instance(L[2 * i], L[2 * i + 1]); c = r == 1 ? '1' : (r == 0 ? '0' : 'N'); }
+        catch (std::exception&) { c = 'E'; }
+        catch (...) { c = 'E'; }
+        if (write(fd[1], &c, 1) != 1) _exit(4);
+      }
+      _exit(0);
+    }
+    close(fd[1]);
+    char c; while (read(fd[0], &c, 1) == 1) out[next++] = c;
+    close(fd[0]);
+    int st = 0; waitpid(pid, &st, 0);
+    if (next < ninst && !(WIFEXITED(st) && WEXITSTATUS(st) == 0)) out[next++] = 'S';
+  }
+  fwrite(out.data(), 1, out.size(), stdout); fputc('\n', stdout);
+  return 0;
+}
