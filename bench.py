@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on B200.
+
+metric   : tree-containment instances/s  (BASELINE.json "metric"; config = configs[1]: a batch of 10^5 `gen` networks
+           l=100, r=20, each with a displayed tree)
+step     : one pass of the hot path (pt_batch_contain) over one batch of 10^5 synthetic instances per GPU
+value    : whole-job instances/s with the batch RESIDENT in HBM when the timed region starts (CUDA events, max over ranks)
+e2e      : the same through the public C-ABI call with HOST (pinned) buffers: pt_batch_create (H2D) + pt_batch_contain
+           (kernels + D2H of the result bits) + pt_batch_free, every step
+roofline : dominant kernel = tc_reduce_kernel over the original instances (round 0), timed live with CUDA events inside
+           the library; algorithmic bytes = 8124 B/instance; peak = MEASURED_PEAKS.json hbm_gbs
+cpu_baseline / --impl reference : the reference's own TreeInNetContainment::displayed() (oracle/_ref/ref_tc, unmodified
+           reference headers, std::cout silenced) on the box's host cores, one process per core over disjoint slices
+lca      : secondary leg (BASELINE config 3): 10^8 LCA queries on a 10^7-leaf tree, outside the timed region
+
+N > 1: one process per GPU (torchrun), instances sharded with no data-path collective; the only collective is the
+all-reduce of the packed result words and counters (phylo_tools_b200/shard.py), inside the timed region. Weak scaling:
+10^5 instances per GPU.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_INSTANCE = 8124  # int32 CSR host 4940 B + guest 3184 B at l=100, r=20
+LCA_BYTES_PER_QUERY = 40
+L, R = 100, 20
+SEED = 0xB200
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.t = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.strip().lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def reference_arm(args, rank, world):
+    """the reference's CPU implementation of the path on the host cores (rank 0 only)"""
+    if rank != 0:
+        return
+    import phylo_tools_b200 as pt
+    from oracle import pt_oracle as O
+    ref = O.ref_binary("ref_tc")
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    per = args.ref_instances_per_core
+    res = {"metric": "tree-containment instances/s", "unit": "instances/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "config": {"workload": "batch of 10^5 gen networks l=100 r=20 with a displayed tree each (BASELINE configs[1]); bounded sample per step",
+                      "leaves": L, "reticulations": R}}
+    if ref is None:
+        res["unavailable"] = "oracle/_ref/ref_tc was not built (needs /root/reference at build time)"
+        print(json.dumps(res))
+        return
+    p = pt.Packer()
+    p.add_generated(procs * per, L, R, SEED, 0)
+    files = []
+    for k in range(procs):
+        f = tempfile.NamedTemporaryFile("w", suffix=".nw", delete=False)
+        for i in range(k * per, (k + 1) * per):
+            h, g = p.newick(i)
+            f.write(h + "\n" + g + "\n")
+        f.close()
+        files.append(f.name)
+
+    def one_step():
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen([ref, "bench", fn, str(per)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True) for fn in files]
+        outs = [q.communicate()[1] for q in ps]
+        dt = time.perf_counter() - t0
+        disp = sum(json.loads(o.strip().split("\n")[-1])["displayed"] for o in outs)
+        return dt, disp
+    for _ in range(args.warmup):
+        one_step()
+    times, disp = [], 0
+    for _ in range(args.steps):
+        dt, disp = one_step()
+        times.append(dt)
+    for fn in files:
+        os.unlink(fn)
+    total = procs * per
+    ms = 1000.0 * sum(times) / len(times)
+    val = total / (ms / 1000.0)
+    res.update({"value": val, "ms_per_step": ms, "gpu_launches": 0,
+                "cpu_baseline": {"value": val, "unit": "instances/s", "cores": procs, "kind": "reference",
+                                 "sample": "%d instances per step (%d per core), all displayed=%s" % (total, per, disp == total)},
+                "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(res))
+
+
+def cpu_baseline_leg(pt, sample_seconds=15.0):
+    """bounded sample of the same workload through the reference on all host cores (reported, not the target)"""
+    from oracle import pt_oracle as O
+    ref = O.ref_binary("ref_tc")
+    if ref is None:
+        return {"value": None, "unit": "instances/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref/ref_tc not built"}
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    per = max(8, int(sample_seconds * 45))  # ~50 instances/s/core survey-time
+    per = min(per, 400)
+    p = pt.Packer()
+    p.add_generated(cores * per, L, R, SEED, 0)
+    files = []
+    for k in range(cores):
+        f = tempfile.NamedTemporaryFile("w", suffix=".nw", delete=False)
+        for i in range(k * per, (k + 1) * per):
+            h, g = p.newick(i)
+            f.write(h + "\n" + g + "\n")
+        f.close()
+        files.append(f.name)
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([ref, "bench", fn, str(per)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True) for fn in files]
+    outs = [q.communicate()[1] for q in ps]
+    dt = time.perf_counter() - t0
+    for fn in files:
+        os.unlink(fn)
+    disp = sum(json.loads(o.strip().split("\n")[-1])["displayed"] for o in outs)
+    single = [json.loads(o.strip().split("\n")[-1])["inst_per_s"] for o in outs]
+    return {"value": cores * per / dt, "unit": "instances/s", "cores": cores, "kind": "reference",
+            "sample": "first %d instances of the batch, %d per core, reference TreeInNetContainment::displayed() with std::cout silenced; %d/%d displayed; per-core rate %.1f inst/s"
+                      % (cores * per, per, disp, cores * per, sum(single) / len(single))}
+
+
+def lca_leg(pt, torch, leaves, queries, peak):
+    par = pt.random_tree(leaves, SEED)
+    n = len(par)
+    dpar = torch.from_numpy(par).cuda()
+    lca = pt.Lca(dpar)
+    info = lca.info()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u = torch.randint(0, n, (queries,), generator=g, device="cuda", dtype=torch.int32)
+    v = torch.randint(0, n, (queries,), generator=g, device="cuda", dtype=torch.int32)
+    out = torch.empty_like(u)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        lca.query(u, v, out=out, stream=stream)
+    torch.cuda.synchronize()
+    reps, best, tot = 5, 1e30, 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lca.query(u, v, out=out, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best, tot = min(best, ms), tot + ms
+    avg = tot / reps
+    checksum = int(out.long().sum().item())
+    lca.free()
+    qps = queries / (avg / 1000.0)
+    ach = LCA_BYTES_PER_QUERY * qps / 1e9
+    return {"workload": "batched LCA: %d queries on a %d-leaf random binary tree (BASELINE configs[2])" % (queries, leaves),
+            "queries_per_s": qps, "ms_per_batch": avg, "best_ms": best, "build_ms": info["build_ms"], "levels": info["num_levels"],
+            "resident_bytes": info["device_bytes"], "checksum": checksum,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "model": "40 B/query (SURVEY 8(d)); physical floor of this layout is 2 x 32 B random sectors + 12 B streamed = 76 B/query"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=100_000, help="instances per GPU")
+    ap.add_argument("--lca-leaves", type=int, default=10_000_000)
+    ap.add_argument("--lca-queries", type=int, default=100_000_000)
+    ap.add_argument("--no-lca", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-instances-per-core", type=int, default=100)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import phylo_tools_b200 as pt
+    from phylo_tools_b200.shard import place_words
+
+    if pt.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    pt.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peak, peak_src = measured_peak()
+    B = args.instances
+    total_B = B * world
+    # ---- synthetic batch of this rank: instances [rank*B, (rank+1)*B) of the global batch (seed = SEED + global index) ----
+    t_gen = time.perf_counter()
+    packer = pt.Packer()
+    packer.add_generated(B, L, R, SEED + rank * B, 0)
+    host = packer.arrays()
+    t_gen = time.perf_counter() - t_gen
+    pinned = {k: (torch.from_numpy(v).pin_memory() if isinstance(v, np.ndarray) else v) for k, v in host.items()}
+    dev = {k: (v.cuda(non_blocking=True) if hasattr(v, "cuda") else v) for k, v in pinned.items()}
+    torch.cuda.synchronize()
+    words = (B + 31) // 32
+    d_bits = torch.zeros(words, dtype=torch.int32, device="cuda")
+    d_stat = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    full_words = torch.zeros((total_B + 31) // 32, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    resident = pt.Batch(dev, stream=stream)
+    in_bytes_actual = sum(int(dev[k].numel()) * dev[k].element_size() for k in ("host_node_off", "host_arc_off", "guest_node_off", "host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"))
+
+    def step_resident():
+        resident.contain(result_bits=d_bits, status=d_stat, want_counters=False, stream=stream)
+        if world > 1:  # the path's only collective: packed result words (disjoint per rank -> SUM == OR)
+            full_words.zero_()
+            w0 = rank * B // 32
+            full_words[w0:w0 + words] = d_bits.to(torch.int64) & 0xFFFFFFFF
+            dist.all_reduce(full_words, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches = 0
+    k0_ms = []
+    with ClockSampler(local_rank) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+            launches += resident.last_launches()
+            k0_ms.append(resident.round_ms(0))
+        e1.record()
+        barrier()
+        elapsed_ms = e0.elapsed_time(e1)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = total_B / (ms_per_step / 1000.0)
+    # verdict sanity (outside the timed region): every instance is a positive by construction
+    n_disp = int(np.unpackbits(d_bits.cpu().numpy().view(np.uint8), bitorder="little")[:B].sum())
+    n_err = int((d_stat != 0).sum().item())
+    _, _, counters = resident.contain(result_bits=d_bits, status=d_stat, want_counters=True, stream=stream)
+    k0 = sum(k0_ms) / len(k0_ms)
+    ach = ALG_BYTES_PER_INSTANCE * B / (k0 / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "tc_reduce_kernel<int16> (round 0, %d instances)" % B, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "kernel_ms": k0, "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
+                "algorithmic_bytes_per_instance": ALG_BYTES_PER_INSTANCE, "bytes_actually_read_per_instance": in_bytes_actual / B,
+                "note": "instance-resident shared-memory solver: bound by dependent shared-memory latency and barriers, not HBM (SURVEY 8(d)); see profiles/"}
+    resident.free()
+
+    # ---- end to end: HOST (pinned) buffers -> pt_batch_create (H2D) -> pt_batch_contain (HOST result bits, D2H) -> free ----
+    h_bits = torch.zeros(max(words, 1), dtype=torch.int32).pin_memory()
+    h_stat = torch.zeros(max(B, 1), dtype=torch.uint8).pin_memory()
+    pinned_np = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in pinned.items()}
+    h2d = 0
+
+    def step_e2e():
+        nonlocal h2d
+        b = pt.Batch(pinned_np, stream=stream)
+        h2d = b.h2d_bytes()
+        opt = pt.Options(0, 0)
+        rc = pt.lib().pt_batch_contain(b._h, ctypes.byref(opt), h_bits.data_ptr(), h_stat.data_ptr(), pt.PT_MEM_HOST, None, stream)
+        assert rc == 0, pt.lib().pt_last_error()
+        b.free()
+        if world > 1:
+            fw = torch.from_numpy(place_words(h_bits.numpy().view(np.uint32)[:words], rank * B // 32 * 32, total_B)).cuda()
+            dist.all_reduce(fw, op=dist.ReduceOp.SUM)
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)  # host syncs inside the call: take the larger of device and wall time
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = total_B / (float(t.item()) / args.steps / 1000.0)
+    e2e_disp = int(np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[:B].sum())
+
+    out = {"metric": "tree-containment instances/s", "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "config": {"workload": "batch of 10^5 gen networks l=100 r=20 with a displayed tree each, per GPU (BASELINE configs[1])",
+                      "instances_per_gpu": B, "leaves": L, "reticulations": R, "host_nodes": 2 * R + 2 * L - 1, "generator_seed": SEED,
+                      "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" % (in_bytes_actual / 1e6),
+                      "parallelism": "instances sharded %d-way, one all-reduce of result words" % world if world > 1 else "single GPU"},
+           "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": words * 4 + B,
+                   "api": "pt_batch_create(HOST pinned) + pt_batch_contain(HOST outputs) + pt_batch_free", "displayed": e2e_disp},
+           "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline,
+           "verdicts": {"displayed": n_disp, "errors": n_err, "expected_displayed": B}, "counters": counters,
+           "host_generation_s": t_gen}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_leg(pt)
+    if rank == 0 and not args.no_lca:
+        try:
+            out["lca"] = lca_leg(pt, torch, args.lca_leaves, args.lca_queries, peak)
+        except Exception as ex:  # the secondary leg must not take the headline line down
+            out["lca"] = {"error": repr(ex)}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -183,6 +183,12 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
                      pt_mem out_mem, pt_counters* counters, void* stream);
 /* number of kernel launches issued by the last pt_batch_contain on this handle (for bench.py gpu_launches) */
 int64_t pt_batch_last_launches(const pt_batch* b);
+/* device time (CUDA events on `stream`) of the reduce-kernel launch of branching round `round` of the last
+ * pt_batch_contain (round 0 = the launch over the original instances: the dominant kernel); PT_ERR_INVALID if that
+ * round did not run */
+int pt_batch_round_ms(const pt_batch* b, int round, float* ms);
+/* bytes copied host->device by pt_batch_create (0 for DEVICE input) */
+int64_t pt_batch_h2d_bytes(const pt_batch* b);
 int pt_batch_free(pt_batch* b);
 
 /* ------------------------------------------------------------------------------------------------

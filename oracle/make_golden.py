@@ -1,0 +1,141 @@
+"""oracle/make_golden.py -- regenerates tests/golden/*.json IN THE BUILD CONTAINER (needs /root/reference through the
+binaries in oracle/_ref/, built by `make -C oracle`).  The GPU box has neither; the committed JSON files travel.
+
+  newick_ref.json      Newick strings -> (num_nodes, edges, labels) as produced by the REFERENCE reader
+                       (io/newick.hpp via oracle/_ref/ref_tc parse)
+  tc_ref_verdicts.json (host, guest) pairs -> the REFERENCE tc verdict ('1','0','E' exception,'S' crash) and the
+                       exhaustive-switching truth from oracle/pt_oracle.c.  Includes data/test.nw and the five reference
+                       false positives of SURVEY 4.3.
+  lca_ref.json         random trees + queries -> answers of the REFERENCE rmq/lca.hpp (oracle/_ref/ref_lca lca) and
+                       RMQ arrays -> (index, value) answers of the reference sparse_rmq / pm_rmq
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import phylo_tools_b200 as pt  # noqa: E402  (host-side generator only; no GPU needed)
+from oracle import pt_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF_TC = os.path.join(ROOT, "oracle", "_ref", "ref_tc")
+REF_LCA = os.path.join(ROOT, "oracle", "_ref", "ref_lca")
+
+FALSE_POSITIVES = [  # the reference prints "displayed", exhaustive switching says no
+    ("((((((d,e))#H6)#H3,(a,b)),#H3),(#H6,c));", "((c,(e,(a,b))),d);"),
+    ("(((((((c,d),(e,f)))#H4)#H3,(a,b)),#H3),#H4);", "(((f,(d,c)),(b,a)),e);"),
+    ("((((b,c),a),(((d,e))#H6,(f)#H8)),(#H6,#H8));", "(((d,f),(a,(c,b))),e);"),
+    ("((((c,d))#H2,((((e,f),a),(b)#H6),#H6)),#H2);", "((((e,a),b),(c,d)),f);"),
+    ("((((((a)#H10)#H9,(((f)#H14,c),b)))#H6,#H10),((((d,e),(i,j)),(#H6,(#H9,(g,h)))),#H14));", "(g,(((d,e),(j,i)),((a,h),(b,(c,f)))));"),
+]
+DATA_TEST = ("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));")  # data/test.nw
+
+
+def gen_pairs(count, l, r, seed, kind):
+    p = pt.Packer()
+    p.add_generated(count, l, r, seed, kind)
+    return [p.newick(i) for i in range(count)]
+
+
+def run_lines(binary, mode, lines):
+    with tempfile.NamedTemporaryFile("w", suffix=".nw", delete=False) as f:
+        f.write("\n".join(lines) + "\n")
+    out = subprocess.run([binary, mode, f.name], capture_output=True, text=True).stdout
+    os.unlink(f.name)
+    return out
+
+
+def make_newick():
+    lines = []
+    for (l, r) in [(5, 2), (10, 4), (16, 7), (30, 8), (100, 20)]:
+        for h, g in gen_pairs(6, l, r, 1234, 0):
+            lines += [h, g]
+    for f in ("test.nw", "nets.nw", "test_tree.nw"):
+        lines += [x.strip() for x in open("/root/reference/data/" + f) if x.strip()]
+    lines += ["(a:1.5,(b:2,c:0.1e-3)x:3)root;", " ( a , b ) ; ", "((a,b)#H1,(#H1,c));", "(a,(b,c,d),e);", "((x y,z),w);", "(A,(B)#LGT12,(#LGT12,C));",
+              "((a,b),(c,d))r;", "(((a)#H1,(#H1)#H2),#H2);"]
+    out = run_lines(REF_TC, "parse", lines)
+    blocks = [b.strip("\n").split("\n") for b in out.split("--\n")][:len(lines)]
+    items = []
+    for s, b in zip(lines, blocks):
+        assert b[0] != "ERR", s
+        n, m = map(int, b[0].split())
+        edges = [list(map(int, x.split())) for x in b[1:1 + m]]
+        labels = {}
+        for x in b[1 + m:]:
+            _, v, name = x.split(" ", 2)
+            labels[v] = name
+        items.append(dict(newick=s, num_nodes=n, edges=edges, labels=labels))
+    json.dump(dict(source="oracle/_ref/ref_tc parse (reference io/newick.hpp)", items=items), open(os.path.join(GOLD, "newick_ref.json"), "w"), indent=0)
+    print("newick_ref.json:", len(items))
+
+
+def make_tc():
+    pairs = [DATA_TEST] + FALSE_POSITIVES + [("((a,b),(c,d));", "((a,b),(c,d));"), ("((a,b),(c,d));", "((a,c),(b,d));")]
+    tags = ["data/test.nw"] + ["survey_false_positive"] * 5 + ["tree_in_tree_pos", "tree_in_tree_neg"]
+    for (l, r, cnt) in [(4, 1, 20), (6, 2, 40), (8, 3, 40), (10, 4, 40), (12, 5, 30), (16, 7, 30)]:
+        for kind in (0, 1, 2):
+            ps = gen_pairs(cnt, l, r, 7000 + 100 * l + r, kind)
+            pairs += ps
+            tags += ["gen l=%d r=%d kind=%d" % (l, r, kind)] * len(ps)
+    lines = [x for p in pairs for x in p]
+    ref = run_lines(REF_TC, "verdicts", lines).strip()
+    assert len(ref) == len(pairs), (len(ref), len(pairs))
+    items = []
+    for (h, g), tag, rv in zip(pairs, tags, ref):
+        truth, ndisp, first = O.tc_bruteforce_newick(h, g, stop_at_first=False)
+        items.append(dict(host=h, guest=g, tag=tag, reference=rv, truth=int(truth), n_displaying=int(ndisp)))
+    agree = sum(1 for it in items if it["reference"] in "01" and int(it["reference"]) == it["truth"])
+    wrong = [i for i, it in enumerate(items) if it["reference"] in "01" and int(it["reference"]) != it["truth"]]
+    crashed = sum(1 for it in items if it["reference"] in "ES")
+    json.dump(dict(source="oracle/_ref/ref_tc verdicts (reference containment.hpp) + oracle/pt_oracle.c exhaustive switching",
+                   summary=dict(instances=len(items), reference_agrees=agree, reference_wrong=wrong, reference_crashed=crashed), items=items),
+              open(os.path.join(GOLD, "tc_ref_verdicts.json"), "w"), indent=0)
+    print("tc_ref_verdicts.json:", len(items), "agree", agree, "wrong", wrong, "crashed", crashed)
+
+
+def make_lca():
+    rng = np.random.default_rng(2026)
+    trees = []
+    for n in (1, 2, 9, 33, 100, 1000, 4097):
+        par = np.full(n, -1, dtype=np.int64)
+        for v in range(1, n):
+            par[v] = rng.integers(0, v)
+        perm = rng.permutation(n)
+        newpar = np.full(n, -1, dtype=np.int64)
+        for v in range(n):
+            newpar[perm[v]] = perm[par[v]] if par[v] >= 0 else -1
+        q = 200
+        u, v = rng.integers(0, n, q), rng.integers(0, n, q)
+        inp = "%d %d\n%s\n%s\n" % (n, q, " ".join(map(str, newpar)), "\n".join("%d %d" % (a, b) for a, b in zip(u, v)))
+        out = subprocess.run([REF_LCA, "lca"], input=inp, capture_output=True, text=True).stdout.split()
+        trees.append(dict(parent=newpar.tolist(), u=u.tolist(), v=v.tolist(), lca=list(map(int, out))))
+    # the tree of rmq/lca.cpp:24-43 with its 4 known answers (ids as assigned there: c0 d1 e2 b3 h4 g5 i6 f7 a8)
+    known = dict(parent=[3, 3, 3, 8, 5, 7, 7, 8, -1], u=[8, 3, 0, 4], v=[8, 7, 2, 6], lca=[8, 8, 3, 7], source="rmq/lca.cpp:46-49")
+    rmqs = []
+    for n, mode in ((10, "rmq"), (1000, "rmq"), (5000, "rmq"), (1000, "pmrmq")):
+        if mode == "rmq":
+            a = rng.integers(0, 50, n)
+        else:
+            a = np.cumsum(np.concatenate([[0], rng.choice([-1, 1], n - 1)]))
+        q = 300
+        l = rng.integers(0, n, q)
+        r = np.minimum(n, l + 1 + rng.integers(0, 100, q))
+        inp = "%d %d\n%s\n%s\n" % (n, q, " ".join(map(str, a)), "\n".join("%d %d" % (x, y) for x, y in zip(l, r)))
+        out = subprocess.run([REF_LCA, mode], input=inp, capture_output=True, text=True).stdout.split()
+        rmqs.append(dict(mode=mode, values=a.tolist(), l=l.tolist(), r=r.tolist(), index=list(map(int, out[0::2])), value=list(map(int, out[1::2]))))
+    json.dump(dict(source="oracle/_ref/ref_lca (reference rmq/lca.hpp, sparse_rmq.hpp, pm_rmq.hpp)", trees=trees, known=known, rmq=rmqs),
+              open(os.path.join(GOLD, "lca_ref.json"), "w"), indent=0)
+    print("lca_ref.json:", len(trees), "trees,", len(rmqs), "rmq arrays")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    make_newick()
+    make_tc()
+    make_lca()

@@ -1,0 +1,284 @@
+"""phylo_tools_b200 -- B200-native batched tree containment + LCA behind the API surface of igel-kun/phylo_tools.
+
+The product is the C-ABI shared library phylo_tools_b200/libptgpu.so (include/pt_gpu.h; CUDA kernels for sm_100a in
+csrc/) plus the C++ facade in include/pt/.  This Python package is a thin ctypes layer used by the tests, bench.py and
+Python callers; it contains no algorithmic code and no CPU fallback."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import (PT_MEM_DEVICE, PT_MEM_HOST, BatchDesc, Counters, LcaInfo, Options)
+
+_L = _capi.load()
+
+
+class PtError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        super().__init__("%s failed (%d): %s" % (where, code, (_L.pt_last_error() or b"").decode(errors="replace")))
+
+
+class MalformedNewick(ValueError):
+    """io/newick.hpp:15-26"""
+
+
+def _check(rc, where):
+    if rc == _capi.PT_ERR_PARSE:
+        raise MalformedNewick((_L.pt_last_error() or b"").decode(errors="replace"))
+    if rc != 0:
+        raise PtError(rc, where)
+
+
+def lib():
+    return _L
+
+
+def device_count():
+    return _L.pt_device_count()
+
+
+def set_device(i):
+    _check(_L.pt_set_device(int(i)), "pt_set_device")
+
+
+def _ptr(x):
+    """raw address of a numpy array / torch tensor / int"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+def _is_device(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def parse_newick(text):
+    """parse_newick (io/newick.hpp:274-290) -> (num_nodes, edges[(tail, head)], {node: label})"""
+    s = text.encode()
+    n, m, nl, bl = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(0)
+    _check(_L.pt_parse_newick(s, C.byref(n), C.byref(m), None, C.byref(nl), None, None, C.byref(bl)), "pt_parse_newick")
+    edges = (C.c_int32 * max(1, 2 * m.value))()
+    nodes = (C.c_int32 * max(1, nl.value))()
+    buf = C.create_string_buffer(max(1, bl.value))
+    _check(_L.pt_parse_newick(s, C.byref(n), C.byref(m), edges, C.byref(nl), nodes, buf, C.byref(bl)), "pt_parse_newick")
+    names = buf.raw[:bl.value].split(b"\0")[:-1] if bl.value else []
+    return n.value, [(edges[2 * i], edges[2 * i + 1]) for i in range(m.value)], {nodes[i]: names[i].decode() for i in range(nl.value)}
+
+
+def random_tree(num_leaves, seed):
+    """parent array (int32, 2*num_leaves-1 entries) of a random rooted binary tree"""
+    out = np.empty(2 * num_leaves - 1, dtype=np.int32)
+    _check(_L.pt_gen_random_tree(num_leaves, seed, out.ctypes.data_as(_capi.i32p)), "pt_gen_random_tree")
+    return out
+
+
+class Packer:
+    """host-side batch builder (pt/packer.hpp): Newick pairs or generated instances -> flat arrays"""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        _check(_L.pt_packer_create(C.byref(self._h)), "pt_packer_create")
+
+    def add_newick(self, host, guest):
+        _check(_L.pt_packer_add_newick(self._h, host.encode(), guest.encode()), "pt_packer_add_newick")
+
+    def add_generated(self, count, leaves, retis, seed, kind=0):
+        _check(_L.pt_packer_add_generated(self._h, count, leaves, retis, seed, kind), "pt_packer_add_generated")
+
+    def desc(self):
+        d = BatchDesc()
+        _check(_L.pt_packer_desc(self._h, C.byref(d)), "pt_packer_desc")
+        return d
+
+    def arrays(self):
+        """numpy views (copied) of the flat arrays, keyed like pt_batch_desc"""
+        d = self.desc()
+        B = d.num_instances
+
+        def view(ptr, count, ctype, dtype):
+            if not ptr or count == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).copy()
+        hn = view(d.host_node_off, B + 1, C.c_int64, np.int64)
+        ha = view(d.host_arc_off, B + 1, C.c_int64, np.int64)
+        gn = view(d.guest_node_off, B + 1, C.c_int64, np.int64)
+        NH, MH, NG = (int(hn[-1]), int(ha[-1]), int(gn[-1])) if B else (0, 0, 0)
+        out = dict(num_instances=B, host_node_off=hn, host_arc_off=ha, guest_node_off=gn,
+                   host_succ_off=view(d.host_succ_off, NH + B, C.c_int32, np.int32), host_succ_adj=view(d.host_succ_adj, MH, C.c_int32, np.int32),
+                   host_label=view(d.host_label, NH, C.c_int32, np.int32), guest_parent=view(d.guest_parent, NG, C.c_int32, np.int32),
+                   guest_label=view(d.guest_label, NG, C.c_int32, np.int32),
+                   host_pred_off=view(d.host_pred_off, NH + B, C.c_int32, np.int32), host_pred_adj=view(d.host_pred_adj, MH, C.c_int32, np.int32),
+                   guest_child_off=view(d.guest_child_off, NG + B, C.c_int32, np.int32), guest_child_adj=view(d.guest_child_adj, max(NG - B, 0), C.c_int32, np.int32),
+                   max_host_nodes=d.max_host_nodes, max_host_arcs=d.max_host_arcs, max_guest_nodes=d.max_guest_nodes, max_labels=d.max_labels)
+        return out
+
+    def newick(self, i):
+        hl, gl = C.c_int64(0), C.c_int64(0)
+        _check(_L.pt_packer_get_newick(self._h, i, None, C.byref(hl), None, C.byref(gl)), "pt_packer_get_newick")
+        hb, gb = C.create_string_buffer(hl.value), C.create_string_buffer(gl.value)
+        _check(_L.pt_packer_get_newick(self._h, i, hb, C.byref(hl), gb, C.byref(gl)), "pt_packer_get_newick")
+        return hb.value.decode(), gb.value.decode()
+
+    def __len__(self):
+        return int(self.desc().num_instances)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _L.pt_packer_free(self._h)
+            self._h = None
+
+
+_ARRAY_KEYS = ["host_node_off", "host_arc_off", "guest_node_off", "host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"]
+_OPT_KEYS = ["host_pred_off", "host_pred_adj", "guest_child_off", "guest_child_adj"]
+
+
+def make_desc(arrays, mem):
+    d = BatchDesc()
+    d.num_instances = int(arrays["num_instances"])
+    d.mem = mem
+    for k in _ARRAY_KEYS:
+        setattr(d, k, _ptr(arrays[k]))
+    for k in _OPT_KEYS:
+        setattr(d, k, _ptr(arrays.get(k)) if arrays.get(k) is not None and (not hasattr(arrays[k], "__len__") or len(arrays[k])) else None)
+    for k in ("max_host_nodes", "max_host_arcs", "max_guest_nodes", "max_labels"):
+        setattr(d, k, int(arrays.get(k, 0)))
+    return d
+
+
+class Batch:
+    """pt_batch_* : batched TreeInNetContainment(...).displayed() (utils/containment.hpp:1179-1202)"""
+
+    def __init__(self, arrays, stream=None):
+        """arrays: dict keyed like pt_batch_desc; values numpy arrays (HOST) or torch CUDA tensors (DEVICE), all of one kind"""
+        self._keep = arrays
+        self.num_instances = int(arrays["num_instances"])
+        dev = _is_device(arrays["host_label"])
+        self._h = C.c_void_p()
+        d = make_desc(arrays, PT_MEM_DEVICE if dev else PT_MEM_HOST)
+        _check(_L.pt_batch_create(C.byref(self._h), C.byref(d), stream), "pt_batch_create")
+
+    def contain(self, result_bits=None, status=None, want_counters=True, stream=None, pool_slots=0, max_rounds=0):
+        """returns (verdicts bool[B] or None when device outputs are given, status uint8[B] or None, counters dict or None)"""
+        B = self.num_instances
+        words = (B + 31) // 32
+        dev_out = result_bits is not None and _is_device(result_bits)
+        if result_bits is None:
+            result_bits = np.zeros(max(words, 1), dtype=np.uint32)
+            status = np.zeros(max(B, 1), dtype=np.uint8)
+        opt = Options(pool_slots, max_rounds)
+        cnt = Counters() if want_counters else None
+        _check(_L.pt_batch_contain(self._h, C.byref(opt), _ptr(result_bits), _ptr(status), PT_MEM_DEVICE if dev_out else PT_MEM_HOST,
+                                   C.byref(cnt) if cnt is not None else None, stream), "pt_batch_contain")
+        if dev_out:
+            return None, None, (cnt.as_dict() if cnt is not None else None)
+        bits = np.unpackbits(result_bits[:words].view(np.uint8), bitorder="little")[:B].astype(bool)
+        return bits, (status[:B] if status is not None else None), (cnt.as_dict() if cnt is not None else None)
+
+    def last_launches(self):
+        return int(_L.pt_batch_last_launches(self._h))
+
+    def round_ms(self, rnd=0):
+        ms = C.c_float()
+        _check(_L.pt_batch_round_ms(self._h, rnd, C.byref(ms)), "pt_batch_round_ms")
+        return float(ms.value)
+
+    def h2d_bytes(self):
+        return int(_L.pt_batch_h2d_bytes(self._h))
+
+    def free(self):
+        if getattr(self, "_h", None):
+            _L.pt_batch_free(self._h)
+            self._h = None
+
+    __del__ = free
+
+
+def contain_newick(pairs):
+    """[(host_newick, guest_newick)] -> (bool verdicts, status) ; the `tc` protocol of examples/tc.cpp:110-142 for a list"""
+    p = Packer()
+    for h, g in pairs:
+        p.add_newick(h, g)
+    b = Batch(p.arrays())
+    try:
+        v, s, _ = b.contain()
+    finally:
+        b.free()
+    return v, s
+
+
+class Lca:
+    """pt_lca_* : Tree::LCA (utils/tree.hpp:202-223) / lca<>::query (rmq/lca.hpp:91-106) for batches of queries"""
+
+    def __init__(self, parent, stream=None):
+        self._h = C.c_void_p()
+        self._keep = parent
+        self.n = int(parent.shape[0]) if hasattr(parent, "shape") else len(parent)
+        if not _is_device(parent):
+            parent = np.ascontiguousarray(parent, dtype=np.int32)
+            self._keep = parent
+        _check(_L.pt_lca_build(C.byref(self._h), _ptr(parent), self.n, PT_MEM_DEVICE if _is_device(parent) else PT_MEM_HOST, stream), "pt_lca_build")
+
+    def query(self, u, v, out=None, stream=None):
+        dev = _is_device(u)
+        if not dev:
+            u = np.ascontiguousarray(u, dtype=np.int32)
+            v = np.ascontiguousarray(v, dtype=np.int32)
+            if out is None:
+                out = np.empty(len(u), dtype=np.int32)
+        q = int(u.shape[0])
+        _check(_L.pt_lca_query(self._h, _ptr(u), _ptr(v), _ptr(out), q, PT_MEM_DEVICE if dev else PT_MEM_HOST, stream), "pt_lca_query")
+        return out
+
+    def info(self):
+        i = LcaInfo()
+        _check(_L.pt_lca_get_info(self._h, C.byref(i)), "pt_lca_get_info")
+        return {k: getattr(i, k) for k, _ in i._fields_}
+
+    def node_info(self):
+        d, p = np.empty(self.n, dtype=np.int32), np.empty(self.n, dtype=np.int32)
+        _check(_L.pt_lca_node_info(self._h, d.ctypes.data, p.ctypes.data, PT_MEM_HOST, None), "pt_lca_node_info")
+        return d, p
+
+    def free(self):
+        if getattr(self, "_h", None):
+            _L.pt_lca_free(self._h)
+            self._h = None
+
+    __del__ = free
+
+
+class Rmq:
+    """pt_rmq_* : sparse_rmq (rmq/sparse_rmq.hpp:45-90): index of the rightmost minimum of [l, r)"""
+
+    def __init__(self, values):
+        values = np.ascontiguousarray(values, dtype=np.int32)
+        self._h = C.c_void_p()
+        _check(_L.pt_rmq_build(C.byref(self._h), values.ctypes.data, len(values), PT_MEM_HOST, None), "pt_rmq_build")
+
+    def query(self, l, r):
+        l = np.ascontiguousarray(l, dtype=np.int64)
+        r = np.ascontiguousarray(r, dtype=np.int64)
+        out = np.empty(len(l), dtype=np.int64)
+        _check(_L.pt_rmq_query(self._h, l.ctypes.data, r.ctypes.data, out.ctypes.data, len(l), PT_MEM_HOST, None), "pt_rmq_query")
+        return out
+
+    def free(self):
+        if getattr(self, "_h", None):
+            _L.pt_rmq_free(self._h)
+            self._h = None
+
+    __del__ = free
+
+
+def enum_switchings(succ_off, succ_adj, host_label, guest_parent, guest_label, begin=0, end=0, stop_at_first=False):
+    """pt_enum_switchings -> (n_switchings, n_displaying, first_index or None)"""
+    a = [np.ascontiguousarray(x, dtype=np.int32) for x in (succ_off, succ_adj, host_label, guest_parent, guest_label)]
+    tot, nd, fi = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _check(_L.pt_enum_switchings(len(a[2]), len(a[1]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[3]), a[3].ctypes.data, a[4].ctypes.data,
+                                 begin, end, 1 if stop_at_first else 0, C.byref(tot), C.byref(nd), C.byref(fi), None), "pt_enum_switchings")
+    return tot.value, nd.value, (None if fi.value == 2**64 - 1 else fi.value)

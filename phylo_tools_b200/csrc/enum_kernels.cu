@@ -1,0 +1,186 @@
+// csrc/enum_kernels.cu -- exhaustive switching enumeration for ONE instance over a range of the mixed-radix switching
+// index: one switching per THREAD (32 display trees in flight per warp, all lanes walking the same node order so the
+// structure reads are warp-uniform broadcasts and the per-thread accumulators are coalesced), compared with the guest
+// by a canonical 64-bit Merkle hash of unordered leaf-labelled trees.
+//
+// No counterpart in the reference: it branches on the parents of one reticulation and recurses on deep copies
+// (utils/containment.hpp:1225-1266); the verdict semantics are the same (exists a switching).  This kernel is the
+// engine for general networks that do not reduce (BASELINE config 5) and shards by index range across GPUs.
+// pt_batch_contain does NOT use it: the rule+branch path there is exact by construction; here equality is decided by
+// a 64-bit hash (collision probability ~2^-64 per comparison).
+#include <algorithm>
+#include <vector>
+#include "cuda_common.cuh"
+
+namespace ptgpu {
+
+typedef unsigned long long u64;
+
+__host__ __device__ __forceinline__ u64 mix64(u64 z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ u64 leaf_hash(int label) { u64 h = mix64(0x9E3779B97F4A7C15ull * (u64)(label + 1)); return h ? h : 1; }
+__host__ __device__ __forceinline__ u64 child_term(u64 v) { return mix64(v + 0xD6E8FEB86659FD93ull); }
+__host__ __device__ __forceinline__ u64 node_hash(u64 sum_terms) { u64 h = mix64(sum_terms ^ 0xA0761D6478BD642Full); return h ? h : 1; }
+
+// node i in children-first order
+struct EnumNode { int32_t parent;      // fixed parent position, -1 root, <= -2: multi-parent, digit = -2 - parent
+                  int32_t label; };    // leaf label or -1
+
+__global__ void __launch_bounds__(256) enum_kernel(int n, const EnumNode* __restrict__ nodes, int r, const int32_t* __restrict__ radix,
+                                                   const int32_t* __restrict__ par_off, const int32_t* __restrict__ par_pos,
+                                                   u64 begin, u64 end, u64 guest_hash, int stop_at_first,
+                                                   u64* __restrict__ S1, u64* __restrict__ S2, uint32_t* __restrict__ cnt,
+                                                   u64* __restrict__ result /* [0]=count [1]=first [2]=stop flag */) {
+  extern __shared__ int32_t sm[];
+  EnumNode* snode = reinterpret_cast<EnumNode*>(sm);
+  int32_t* sradix = sm + 2 * n; int32_t* soff = sradix + r; int32_t* spar = soff + r + 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) snode[i] = nodes[i];
+  for (int i = threadIdx.x; i < r; i += blockDim.x) sradix[i] = radix[i];
+  for (int i = threadIdx.x; i <= r; i += blockDim.x) soff[i] = par_off[i];
+  for (int i = threadIdx.x; i < par_off[r]; i += blockDim.x) spar[i] = par_pos[i];
+  __syncthreads();
+  const u64 T = (u64)gridDim.x * blockDim.x, tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = 0; i < n; ++i) { S1[(u64)i * T + tid] = 0; S2[(u64)i * T + tid] = 0; cnt[(u64)i * T + tid] = 0; }
+  u64 found = 0, first = ~0ull;
+  for (u64 s = begin + tid; s < end; s += T) {
+    if (stop_at_first && *(volatile u64*)&result[2]) break;
+    u64 val = 0;
+    for (int i = 0; i < n; ++i) {
+      const EnumNode nd = snode[i];
+      const u64 k = (u64)i * T + tid;
+      const uint32_t c = cnt[k];
+      if (nd.label >= 0) val = leaf_hash(nd.label);
+      else if (c == 0) val = 0;
+      else if (c == 1) val = S1[k];
+      else val = node_hash(S2[k]);
+      if (c) { S1[k] = 0; S2[k] = 0; cnt[k] = 0; }
+      if (val && nd.parent != -1) {
+        int p = nd.parent;
+        if (p <= -2) {
+          // digit of this multi-parent node: peel the mixed-radix index (digits are few; recomputing beats storing them)
+          const int d = -2 - p; u64 x = s;
+          for (int j = 0; j < d; ++j) x /= (u64)sradix[j];
+          p = spar[soff[d] + (int)(x % (u64)sradix[d])];
+        }
+        const u64 kp = (u64)p * T + tid;
+        S1[kp] += val; S2[kp] += child_term(val); cnt[kp] += 1;
+      }
+    }
+    if (val == guest_hash) { ++found; if (s < first) first = s; if (stop_at_first) result[2] = 1; }
+  }
+  for (int d = 16; d; d >>= 1) { found += __shfl_xor_sync(0xffffffffu, found, d); const u64 o = __shfl_xor_sync(0xffffffffu, first, d); first = o < first ? o : first; }
+  if ((threadIdx.x & 31) == 0) { if (found) atomicAdd(&result[0], found); if (first != ~0ull) atomicMin(&result[1], first); }
+}
+
+}  // namespace ptgpu
+
+using namespace ptgpu;
+
+extern "C" int pt_enum_switchings(int32_t n, int32_t m, const int32_t* succ_off, const int32_t* succ_adj, const int32_t* host_label, int32_t nt,
+                                  const int32_t* guest_parent, const int32_t* guest_label, uint64_t begin, uint64_t end, int stop_at_first,
+                                  uint64_t* n_switchings, uint64_t* n_displaying, uint64_t* first_index, void* stream) {
+  if (n <= 0 || m < 0 || nt <= 0 || !succ_off || (!succ_adj && m > 0) || !host_label || !guest_parent || !guest_label)
+    return set_error(PT_ERR_INVALID, "pt_enum_switchings: bad argument");
+  if (n_displaying) *n_displaying = 0;
+  if (first_index) *first_index = UINT64_MAX;
+  // ---- index structures (host side; O(n)) ----
+  if (succ_off[0] != 0 || succ_off[n] != m) return set_error(PT_ERR_INVALID, "pt_enum_switchings: bad CSR offsets");
+  std::vector<int32_t> indeg(n, 0), tdeg(nt, 0);
+  for (int v = 0; v < n; ++v) { if (succ_off[v + 1] < succ_off[v]) return set_error(PT_ERR_INVALID, "pt_enum_switchings: bad CSR offsets"); }
+  for (int e = 0; e < m; ++e) { if (succ_adj[e] < 0 || succ_adj[e] >= n) return set_error(PT_ERR_INVALID, "pt_enum_switchings: arc head out of range"); indeg[succ_adj[e]]++; }
+  int troot = -1;
+  for (int t = 0; t < nt; ++t) { const int p = guest_parent[t]; if (p >= nt || p == t) return set_error(PT_ERR_INVALID, "pt_enum_switchings: bad guest parent"); if (p < 0) { if (troot >= 0) return set_error(PT_ERR_INVALID, "guest has several roots"); troot = t; } else tdeg[p]++; }
+  if (troot < 0) return set_error(PT_ERR_INVALID, "guest has no root");
+  int maxlab = -1;
+  for (int v = 0; v < n; ++v) maxlab = std::max(maxlab, host_label[v]);
+  for (int t = 0; t < nt; ++t) maxlab = std::max(maxlab, guest_label[t]);
+  std::vector<int32_t> l2h(maxlab + 2, -1), l2t(maxlab + 2, -1);
+  for (int v = 0; v < n; ++v) if (host_label[v] >= 0 && succ_off[v + 1] == succ_off[v]) { if (l2h[host_label[v]] >= 0) return set_error(PT_ERR_INVALID, "single-label map for multi-labeled tree/network"); l2h[host_label[v]] = v; }
+  for (int t = 0; t < nt; ++t) if (guest_label[t] >= 0 && tdeg[t] == 0) { if (l2t[guest_label[t]] >= 0) return set_error(PT_ERR_INVALID, "single-label map for multi-labeled network/tree"); l2t[guest_label[t]] = t; }
+  int common = 0; bool t_only = false;
+  for (int l = 0; l <= maxlab; ++l) { if (l2t[l] >= 0 && l2h[l] < 0) t_only = true; if (l2t[l] >= 0 && l2h[l] >= 0) ++common; }
+  // topological order of the host (Kahn), root first
+  std::vector<int32_t> order; order.reserve(n);
+  { std::vector<int32_t> deg = indeg; for (int v = 0; v < n; ++v) if (!deg[v]) order.push_back(v);
+    if (order.size() != 1) return set_error(PT_ERR_INVALID, "cannot create tree/network with %zu roots", order.size());
+    for (size_t i = 0; i < order.size(); ++i) { const int v = order[i]; for (int e = succ_off[v]; e < succ_off[v + 1]; ++e) if (--deg[succ_adj[e]] == 0) order.push_back(succ_adj[e]); }
+    if ((int)order.size() != n) return set_error(PT_ERR_INVALID, "host network has a cycle"); }
+  std::vector<int32_t> posof(n);
+  for (int i = 0; i < n; ++i) posof[order[n - 1 - i]] = i;  // children first
+  std::vector<int32_t> retis; std::vector<int32_t> ridx(n, -1);
+  for (int v = 0; v < n; ++v) if (indeg[v] >= 2) { ridx[v] = (int)retis.size(); retis.push_back(v); }
+  const int r = (int)retis.size();
+  uint64_t total = 1;
+  for (int v : retis) { if (total > (UINT64_MAX >> 1) / (uint64_t)indeg[v]) return set_error(PT_ERR_UNSUPPORTED, "switching index space exceeds 2^63"); total *= (uint64_t)indeg[v]; }
+  if (n_switchings) *n_switchings = total;
+  if (end == 0 || end > total) end = total;
+  if (begin >= end) return PT_OK;
+  if (t_only) return PT_OK;                                   // containment.hpp:1116: never displayed
+  if (common <= 2) {                                          // containment.hpp:1061,1208: always displayed
+    if (n_displaying) *n_displaying = end - begin;
+    if (first_index) *first_index = begin;
+    return PT_OK;
+  }
+  if (int rc = require_device()) return rc;
+  std::vector<EnumNode> nodes(n); std::vector<int32_t> radix(std::max(r, 1)), par_off(r + 1, 0), par_pos;
+  for (int i = 0; i < r; ++i) { radix[i] = indeg[retis[i]]; par_off[i + 1] = par_off[i] + indeg[retis[i]]; }
+  par_pos.assign(std::max(par_off[r], 1), 0);
+  std::vector<int32_t> fill(std::max(r, 1), 0);
+  for (int v = 0; v < n; ++v) {
+    EnumNode& nd = nodes[posof[v]];
+    nd.parent = -1;
+    const int l = host_label[v];
+    nd.label = (l >= 0 && succ_off[v + 1] == succ_off[v] && l2t[l] >= 0) ? l : -1;   // host-only labels are dropped (:1117-1121)
+    if (ridx[v] >= 0) nd.parent = -2 - ridx[v];
+  }
+  for (int u = 0; u < n; ++u) for (int e = succ_off[u]; e < succ_off[u + 1]; ++e) {
+    const int v = succ_adj[e];
+    if (ridx[v] >= 0) par_pos[par_off[ridx[v]] + fill[ridx[v]]++] = posof[u];   // digit order = arc order, like oracle/pt_oracle.c
+    else nodes[posof[v]].parent = posof[u];
+  }
+  // guest canonical hash (same functions as the device)
+  std::vector<std::vector<int>> tk(nt);
+  for (int t = 0; t < nt; ++t) if (guest_parent[t] >= 0) tk[guest_parent[t]].push_back(t);
+  std::vector<u64> th(nt, 0);
+  { std::vector<int> st{troot}, post; while (!st.empty()) { int t = st.back(); st.pop_back(); post.push_back(t); for (int c : tk[t]) st.push_back(c); }
+    for (size_t i = post.size(); i-- > 0;) { const int t = post[i];
+      if (tk[t].empty()) { th[t] = guest_label[t] >= 0 ? leaf_hash(guest_label[t]) : 0; continue; }
+      int c = 0; u64 s1 = 0, s2 = 0; for (int k : tk[t]) if (th[k]) { ++c; s1 += th[k]; s2 += child_term(th[k]); }
+      th[t] = c == 0 ? 0 : (c == 1 ? s1 : node_hash(s2)); } }
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  const size_t smem = (size_t)(2 * n + r + (r + 1) + par_off[r] + 4) * 4;
+  if (smem > (size_t)dp.smem_optin) return set_error(PT_ERR_UNSUPPORTED, "instance too large for the enumerator (%zu bytes of shared memory)", smem);
+  PT_CUDA(cudaFuncSetAttribute(enum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // threads: enough to cover the range, at most 8 CTAs of 256 per SM, and at most ~2 GB of accumulators
+  uint64_t want = (end - begin + 255) / 256;
+  int grid = (int)std::min<uint64_t>(want, (uint64_t)dp.sms * 8);
+  while (grid > 1 && (uint64_t)grid * 256ull * (uint64_t)n * 20ull > (2ull << 30)) grid /= 2;
+  grid = std::max(grid, 1);
+  const size_t T = (size_t)grid * 256;
+  EnumNode* d_nodes = nullptr; int32_t *d_radix = nullptr, *d_off = nullptr, *d_par = nullptr; u64 *d_S1 = nullptr, *d_S2 = nullptr, *d_res = nullptr; uint32_t* d_cnt = nullptr;
+  auto freeall = [&]() { cudaFree(d_nodes); cudaFree(d_radix); cudaFree(d_off); cudaFree(d_par); cudaFree(d_S1); cudaFree(d_S2); cudaFree(d_cnt); cudaFree(d_res); };
+#define EN_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { freeall(); return set_error(e__ == cudaErrorMemoryAllocation ? PT_ERR_NOMEM : PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
+  EN_TRY(cudaMalloc((void**)&d_nodes, nodes.size() * sizeof(EnumNode))); EN_TRY(cudaMalloc((void**)&d_radix, radix.size() * 4));
+  EN_TRY(cudaMalloc((void**)&d_off, par_off.size() * 4)); EN_TRY(cudaMalloc((void**)&d_par, par_pos.size() * 4));
+  EN_TRY(cudaMalloc((void**)&d_S1, T * (size_t)n * 8)); EN_TRY(cudaMalloc((void**)&d_S2, T * (size_t)n * 8)); EN_TRY(cudaMalloc((void**)&d_cnt, T * (size_t)n * 4));
+  EN_TRY(cudaMalloc((void**)&d_res, 32));
+  const u64 init[4] = {0, ~0ull, 0, 0};
+  EN_TRY(cudaMemcpyAsync(d_nodes, nodes.data(), nodes.size() * sizeof(EnumNode), cudaMemcpyHostToDevice, s));
+  EN_TRY(cudaMemcpyAsync(d_radix, radix.data(), radix.size() * 4, cudaMemcpyHostToDevice, s));
+  EN_TRY(cudaMemcpyAsync(d_off, par_off.data(), par_off.size() * 4, cudaMemcpyHostToDevice, s));
+  EN_TRY(cudaMemcpyAsync(d_par, par_pos.data(), par_pos.size() * 4, cudaMemcpyHostToDevice, s));
+  EN_TRY(cudaMemcpyAsync(d_res, init, 32, cudaMemcpyHostToDevice, s));
+  enum_kernel<<<grid, 256, smem, s>>>(n, d_nodes, r, d_radix, d_off, d_par, begin, end, th[troot], stop_at_first, d_S1, d_S2, d_cnt, d_res);
+  EN_TRY(cudaGetLastError());
+  u64 res[4];
+  EN_TRY(cudaMemcpyAsync(res, d_res, 32, cudaMemcpyDeviceToHost, s));
+  EN_TRY(cudaStreamSynchronize(s));
+#undef EN_TRY
+  freeall();
+  if (n_displaying) *n_displaying = res[0];
+  if (first_index) *first_index = res[1];
+  return PT_OK;
+}

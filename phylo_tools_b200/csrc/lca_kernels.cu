@@ -1,0 +1,577 @@
+// csrc/lca_kernels.cu -- batched LCA on sm_100a.
+//
+// Entry points pt_lca_build / pt_lca_query / pt_lca_node_info / pt_lca_free (include/pt_gpu.h) stand in for
+//   Tree::LCA / naiveLCA          utils/tree.hpp:202-223   (parent walk, O(depth) per query)
+//   lca<node_t>::lca(), query()   rmq/lca.hpp:61-106       (Euler tour + depth array + RMQ)
+//   sparse_rmq                    rmq/sparse_rmq.hpp:45-90 (O(n log n) index table)
+// Answers are node ids, hence unique: bit-exact against either reference path.
+//
+// Layout.  Instead of the reference's 2n-1 Euler tour with a 26-level index table (3.9 GB at
+// n = 2*10^7, seven dependent random gathers per query) the build orders nodes by PREORDER position and uses
+//     lca(u,v) = parent( argmin depth over positions (pos[u], pos[v]] ),   pos[u] < pos[v]
+// Positions are cut into blocks of 32.  Per NODE one 32-byte record (one DRAM sector):
+//     { pos, in-block stack mask, min key over (pos, block end], min key over [block start, pos], own key }
+// with key = depth << 32 | parent.  Whole blocks between the two end blocks are answered by a sparse table over
+// packed block minima (n/32 entries per level, ~100 MB at n = 2*10^7: L2 resident on B200's 126 MB L2).
+// A query is therefore: 8 B of (u,v) streamed, TWO random 32-byte sector reads, two table reads that hit L2,
+// 4 B streamed out.
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <new>
+#include <vector>
+#include "cuda_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ptgpu {
+
+typedef unsigned long long u64;
+constexpr u64 KEY_INF = ~0ull;
+
+struct __align__(32) LcaRecord { uint32_t pos, mask; u64 suf, pre, key; };
+static_assert(sizeof(LcaRecord) == 32, "one record = one 32-byte sector");
+
+// ---- build step 1: children counts + root ---------------------------------------------------------------------
+__global__ void lca_count_kernel(const int32_t* __restrict__ parent, int64_t n, int32_t* __restrict__ deg, int32_t* __restrict__ info /*[0]=nroots [1]=root [2]=bad*/) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t p = parent[v];
+    if (p < 0) { atomicAdd(&info[0], 1); info[1] = (int32_t)v; }
+    else if (p >= n || p == v) info[2] = 1;
+    else atomicAdd(&deg[p], 1);
+  }
+}
+
+// ---- exclusive scan (three passes, tiles of 2048) ---------------------------------------------------------------
+constexpr int SCAN_TILE = 2048;
+__global__ void scan_tile_sums_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ tile_sums) {
+  __shared__ int64_t wsum[8];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int64_t s = 0;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += 256) { const int64_t k = base + i; if (k < n) s += in[k]; }
+  for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { int64_t t = 0; for (int k = 0; k < 8; ++k) t += wsum[k]; tile_sums[blockIdx.x] = t; }
+}
+__global__ void scan_tile_offsets_kernel(int64_t* __restrict__ tile_sums, int64_t ntiles) {
+  // single CTA: sequential over chunks of 1024 with a block scan inside
+  __shared__ int64_t buf[1024];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b = 0; b < ntiles; b += 1024) {
+    const int64_t k = b + threadIdx.x;
+    const int64_t v = k < ntiles ? tile_sums[k] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) { int64_t t = threadIdx.x >= d ? buf[threadIdx.x - d] : 0; __syncthreads(); buf[threadIdx.x] += t; __syncthreads(); }
+    if (k < ntiles) tile_sums[k] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+}
+__global__ void scan_apply_kernel(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ tile_off, int32_t* __restrict__ out /* n+1 */) {
+  __shared__ int32_t wtot[8];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  // each thread owns 8 consecutive elements
+  int32_t v[8]; int32_t s = 0;
+  const int64_t t0 = base + (int64_t)threadIdx.x * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { v[j] = (t0 + j < n) ? in[t0 + j] : 0; s += v[j]; }
+  int32_t incl = s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  if (lane == 31) wtot[wid] = incl;
+  __syncthreads();
+  int32_t woff = 0;
+  for (int k = 0; k < wid; ++k) woff += wtot[k];
+  int64_t acc = tile_off[blockIdx.x] + woff + incl - s;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { if (t0 + j < n) out[t0 + j] = (int32_t)acc; acc += v[j]; }
+  if (t0 <= n - 1 && n - 1 < t0 + 8) out[n] = (int32_t)acc;  // the thread holding the last element writes the total
+}
+
+// ---- build step 3: fill children lists (order inside a list is arbitrary: LCA answers do not depend on it) -------
+__global__ void lca_fill_children_kernel(const int32_t* __restrict__ parent, int64_t n, const int32_t* __restrict__ child_off, int32_t* __restrict__ cursor,
+                                         int32_t* __restrict__ child_adj) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t p = parent[v];
+    if (p >= 0) child_adj[child_off[p] + atomicAdd(&cursor[p], 1)] = (int32_t)v;
+  }
+}
+
+// ---- build step 4: three level-synchronous sweeps in ONE cooperative kernel -------------------------------------
+//   top-down   : BFS order + depth (wavefront, children appended with one atomic per parent)
+//   bottom-up  : subtree sizes
+//   top-down   : preorder positions
+// level_off[l] = first index of level l in order[]; ctr[3] rotating append counters; info[3] receives the level count,
+// info[4] the number of nodes reached.
+__global__ void __launch_bounds__(256) lca_sweeps_kernel(int64_t n, int32_t root, const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj,
+                                                         int32_t* __restrict__ order, int32_t* __restrict__ depth, int32_t* __restrict__ size,
+                                                         int32_t* __restrict__ pre, int32_t* __restrict__ level_off, int32_t* __restrict__ ctr, int32_t* __restrict__ info) {
+  cg::grid_group grid = cg::this_grid();
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+  if (gtid == 0) { order[0] = root; depth[root] = 0; pre[root] = 0; level_off[0] = 0; ctr[0] = ctr[1] = ctr[2] = 0; }
+  grid.sync();
+  int lev = 0; int64_t b = 0, e = 1;
+  while (b < e) {
+    int32_t* c = &ctr[lev % 3];
+    if (gtid == 0) { ctr[(lev + 1) % 3] = 0; level_off[lev + 1] = (int32_t)e; }
+    for (int64_t i = b + gtid; i < e; i += gsize) {
+      const int32_t v = order[i];
+      const int32_t cb = child_off[v], ce = child_off[v + 1];
+      if (ce > cb) {
+        const int64_t base = e + atomicAdd(c, ce - cb);
+        for (int32_t j = cb; j < ce; ++j) { const int32_t ch = child_adj[j]; order[base + (j - cb)] = ch; depth[ch] = lev + 1; }
+      }
+    }
+    grid.sync();
+    const int64_t cnt = *(volatile int32_t*)c;
+    b = e; e = e + cnt; ++lev;
+  }
+  const int levels = lev;  // number of non-empty levels
+  if (gtid == 0) { info[3] = levels; info[4] = (int32_t)e; }
+  if (e != n) return;      // unreachable nodes (cycle / several components): host reports the error; uniform exit
+  for (int l = levels - 1; l >= 0; --l) {
+    const int64_t lb = level_off[l], le = level_off[l + 1];
+    for (int64_t i = lb + gtid; i < le; i += gsize) {
+      const int32_t v = order[i];
+      int32_t s = 1;
+      for (int32_t j = child_off[v]; j < child_off[v + 1]; ++j) s += size[child_adj[j]];
+      size[v] = s;
+    }
+    grid.sync();
+  }
+  for (int l = 0; l < levels; ++l) {
+    const int64_t lb = level_off[l], le = level_off[l + 1];
+    for (int64_t i = lb + gtid; i < le; i += gsize) {
+      const int32_t v = order[i];
+      int32_t run = pre[v] + 1;
+      for (int32_t j = child_off[v]; j < child_off[v + 1]; ++j) { const int32_t ch = child_adj[j]; pre[ch] = run; run += size[ch]; }
+    }
+    grid.sync();
+  }
+}
+
+// ---- build step 5: keys by position ------------------------------------------------------------------------------
+__global__ void lca_keys_kernel(int64_t n, const int32_t* __restrict__ parent, const int32_t* __restrict__ depth, const int32_t* __restrict__ pre,
+                                u64* __restrict__ keypos, int32_t* __restrict__ nodeat) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t p = pre[v];
+    keypos[p] = ((u64)(uint32_t)depth[v] << 32) | (u64)(uint32_t)parent[v];
+    nodeat[p] = (int32_t)v;
+  }
+}
+
+// ---- build step 6: one warp per block of 32 positions: prefix / suffix minima, stack masks, block minimum ----------
+template <bool BY_NODE>
+__global__ void __launch_bounds__(256) lca_blocks_kernel(int64_t n, int64_t nblocks, const u64* __restrict__ keypos, const int32_t* __restrict__ nodeat,
+                                                         LcaRecord* __restrict__ rec, u64* __restrict__ table0) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t blk = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; blk < nblocks; blk += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t pos = blk * 32 + lane;
+    const bool valid = pos < n;
+    const u64 key = valid ? keypos[pos] : KEY_INF;
+    u64 pre = key;  // inclusive prefix minimum
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d && t < pre) pre = t; }
+    u64 sufi = key;  // inclusive suffix minimum
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u64 t = __shfl_down_sync(0xffffffffu, sufi, d); if (lane + d < 32 && t < sufi) sufi = t; }
+    u64 suf = __shfl_down_sync(0xffffffffu, sufi, 1);  // LCA: exclusive (pos, block end];  RMQ: inclusive [pos, block end]
+    if (lane == 31) suf = KEY_INF;
+    if (!BY_NODE) suf = sufi;
+    // mask of lane r: bit j set iff key[j] <= min(key[j+1..r]); walk j downwards with a running minimum
+    uint32_t mask = 0; u64 run = KEY_INF;
+    for (int j = 31; j >= 0; --j) {
+      const u64 kj = __shfl_sync(0xffffffffu, key, j);
+      if (j <= lane && kj <= run) { mask |= 1u << j; run = kj; }
+    }
+    if (valid) {
+      LcaRecord r; r.pos = (uint32_t)pos; r.mask = mask; r.suf = suf; r.pre = pre; r.key = key;
+      uint4* dst = reinterpret_cast<uint4*>(&rec[BY_NODE ? (int64_t)nodeat[pos] : pos]);
+      const uint4* srcv = reinterpret_cast<const uint4*>(&r);
+      dst[0] = srcv[0]; dst[1] = srcv[1];
+    }
+    const u64 bmin = __shfl_sync(0xffffffffu, pre, 31);
+    if (lane == 0) table0[blk] = bmin;
+  }
+}
+
+// ---- build step 7: one sparse-table level (sparse_rmq.hpp:52-65, on packed keys instead of indices) ----------------
+__global__ void lca_table_level_kernel(const u64* __restrict__ prev, u64* __restrict__ next, int64_t count, int64_t half) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const u64 a = prev[i], b = prev[i + half];
+    next[i] = a < b ? a : b;
+  }
+}
+
+// ---- query ------------------------------------------------------------------------------------------------------------
+template <int QPT>
+__global__ void __launch_bounds__(256) lca_query_kernel(int64_t q, int64_t n, const int32_t* __restrict__ qu, const int32_t* __restrict__ qv, int32_t* __restrict__ out,
+                                                        const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table,
+                                                        const int64_t* __restrict__ level_base /* device array: offset of level k in table */) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const u64 keep = l2_policy_evict_last();
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < q; i0 += stride * QPT) {
+    int32_t u[QPT], v[QPT];
+    // record words: w0 = pos | mask << 32, w1 = suf, w2 = pre, w3 = key
+    u64 a0[QPT], a1[QPT], a2[QPT], a3[QPT], b0[QPT], b1[QPT], b2[QPT], b3[QPT];
+    bool ok[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t i = i0 + j * stride;
+      ok[j] = i < q;
+      u[j] = ok[j] ? ld_stream(qu + i) : 0; v[j] = ok[j] ? ld_stream(qv + i) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      ok[j] = ok[j] && (uint64_t)(uint32_t)u[j] < (uint64_t)n && (uint64_t)(uint32_t)v[j] < (uint64_t)n;
+      if (ok[j]) { ld_sector_evict_first(rec + u[j], a0[j], a1[j], a2[j], a3[j]); ld_sector_evict_first(rec + v[j], b0[j], b1[j], b2[j], b3[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t i = i0 + j * stride;
+      if (i >= q) continue;
+      int32_t ans = -1;
+      if (ok[j]) {
+        if (u[j] == v[j]) ans = u[j];
+        else {
+          // left = smaller position
+          const bool swap = (uint32_t)a0[j] > (uint32_t)b0[j];
+          const u64 l0 = swap ? b0[j] : a0[j], lsuf = swap ? b1[j] : a1[j];
+          const u64 r0 = swap ? a0[j] : b0[j], rpre = swap ? a2[j] : b2[j];
+          const uint32_t lp = (uint32_t)l0, rp = (uint32_t)r0;
+          const uint32_t bl = lp >> 5, br = rp >> 5;
+          u64 best;
+          if (bl == br) {
+            const uint32_t m = (uint32_t)(r0 >> 32) >> ((lp & 31) + 1);        // stack entries strictly right of lp
+            const uint32_t jpos = (lp & 31) + 1 + (uint32_t)__ffs(m) - 1;        // m != 0: bit (rp & 31) is always set
+            best = keypos[((int64_t)bl << 5) + jpos];
+          } else {
+            best = lsuf < rpre ? lsuf : rpre;      // (lp, end of its block]  and  [start of rp's block, rp]
+            if (br - bl >= 2) {
+              const uint32_t span = br - bl - 1;   // whole blocks bl+1 .. br-1
+              const int k = 31 - __clz(span);
+              const u64* lvl = table + level_base[k];
+              const u64 t1 = ld_u64_hint(lvl + (bl + 1), keep), t2 = ld_u64_hint(lvl + (br - (1u << k)), keep);
+              const u64 t = t1 < t2 ? t1 : t2;
+              best = t < best ? t : best;
+            }
+          }
+          ans = (int32_t)(uint32_t)(best & 0xffffffffull);
+        }
+      }
+      st_stream(out + i, ans);
+    }
+  }
+}
+
+__global__ void lca_node_info_kernel(int64_t n, const LcaRecord* __restrict__ rec, int32_t* __restrict__ depth, int32_t* __restrict__ preorder) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    if (depth) depth[v] = (int32_t)(rec[v].key >> 32);
+    if (preorder) preorder[v] = (int32_t)rec[v].pos;
+  }
+}
+
+// ---- generic RMQ over int32 values (rmq/sparse_rmq.hpp semantics: index of the RIGHTMOST minimum of [l, r)) ------------
+// key = (value biased to unsigned) << 32 | (0xFFFFFFFF - index): the smallest key is the smallest value, largest index.
+__global__ void rmq_keys_kernel(int64_t n, const int32_t* __restrict__ values, u64* __restrict__ keypos) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    keypos[i] = ((u64)((uint32_t)values[i] ^ 0x80000000u) << 32) | (u64)(0xFFFFFFFFu - (uint32_t)i);
+}
+__global__ void __launch_bounds__(256) rmq_query_kernel(int64_t q, int64_t n, const int64_t* __restrict__ ql, const int64_t* __restrict__ qr, int64_t* __restrict__ out,
+                                                        const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table,
+                                                        const int64_t* __restrict__ level_base) {
+  const u64 keep = l2_policy_evict_last();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < q; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = ql[i], r = qr[i] - 1;  // inclusive [l, r]
+    int64_t ans = -1;
+    if (l >= 0 && l <= r && r < n) {
+      u64 a0, a1, a2, a3, b0, b1, b2, b3;
+      ld_sector_evict_first(rec + l, a0, a1, a2, a3);
+      ld_sector_evict_first(rec + r, b0, b1, b2, b3);
+      const uint32_t bl = (uint32_t)(l >> 5), br = (uint32_t)(r >> 5);
+      u64 best;
+      if (bl == br) {
+        const uint32_t m = (uint32_t)(b0 >> 32) >> (l & 31);          // stack entries at or right of l
+        best = keypos[((int64_t)bl << 5) + (l & 31) + __ffs(m) - 1];    // m != 0: bit (r & 31) is always set
+      } else {
+        best = a1 < b2 ? a1 : b2;                                       // [l, end of block]  and  [start of block, r]
+        if (br - bl >= 2) {
+          const uint32_t span = br - bl - 1;
+          const int k = 31 - __clz(span);
+          const u64* lvl = table + level_base[k];
+          const u64 t1 = ld_u64_hint(lvl + (bl + 1), keep), t2 = ld_u64_hint(lvl + (br - (1u << k)), keep);
+          const u64 t = t1 < t2 ? t1 : t2;
+          best = t < best ? t : best;
+        }
+      }
+      ans = (int64_t)(0xFFFFFFFFu - (uint32_t)(best & 0xffffffffull));
+    }
+    out[i] = ans;
+  }
+}
+
+// device exclusive scan of int32 -> int32 (out has n+1 entries); tmp holds ceil(n/SCAN_TILE) int64
+static int device_exclusive_scan(const int32_t* in, int64_t n, int32_t* out, int64_t* tmp, cudaStream_t s) {
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (tiles == 0) { PT_CUDA(cudaMemsetAsync(out, 0, 4, s)); return PT_OK; }
+  scan_tile_sums_kernel<<<(unsigned)tiles, 256, 0, s>>>(in, n, tmp);
+  scan_tile_offsets_kernel<<<1, 1024, 0, s>>>(tmp, tiles);
+  scan_apply_kernel<<<(unsigned)tiles, 256, 0, s>>>(in, n, tmp, out);
+  PT_CUDA(cudaGetLastError());
+  return PT_OK;
+}
+
+}  // namespace ptgpu
+
+using namespace ptgpu;
+
+struct pt_lca {
+  int64_t n = 0, nblocks = 0, levels = 0, table_levels = 0, device_bytes = 0;
+  float build_ms = 0.f;
+  LcaRecord* rec = nullptr; u64* keypos = nullptr; u64* table = nullptr; int64_t* d_level_base = nullptr;
+  int32_t *d_u = nullptr, *d_v = nullptr, *d_out = nullptr; int64_t qcap = 0;  // staging for HOST queries
+};
+
+static void lca_release(pt_lca* h) {
+  if (!h) return;
+  cudaFree(h->rec); cudaFree(h->keypos); cudaFree(h->table); cudaFree(h->d_level_base); cudaFree(h->d_u); cudaFree(h->d_v); cudaFree(h->d_out);
+  delete h;
+}
+
+extern "C" {
+
+int pt_lca_build(pt_lca** out, const int32_t* parent, int64_t n, pt_mem parent_mem, void* stream) {
+  if (!out || !parent || n <= 0 || n > (int64_t)INT32_MAX - 64) return set_error(PT_ERR_INVALID, "pt_lca_build: bad argument (n must be in [1, 2^31-65])");
+  *out = nullptr;
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  pt_lca* h = new (std::nothrow) pt_lca();
+  if (!h) return set_error(PT_ERR_NOMEM, "out of host memory");
+  h->n = n; h->nblocks = (n + 31) / 32;
+  // scratch (freed before returning)
+  int32_t *d_parent = nullptr, *deg = nullptr, *child_off = nullptr, *child_adj = nullptr, *order = nullptr, *depth = nullptr, *size = nullptr, *pre = nullptr,
+          *level_off = nullptr, *small = nullptr, *nodeat = nullptr;
+  int64_t* scan_tmp = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int rc = PT_OK;
+  auto cleanup = [&]() {
+    if (parent_mem == PT_MEM_HOST) cudaFree(d_parent);
+    cudaFree(deg); cudaFree(child_off); cudaFree(child_adj); cudaFree(order); cudaFree(depth); cudaFree(size); cudaFree(pre); cudaFree(level_off); cudaFree(small);
+    cudaFree(nodeat); cudaFree(scan_tmp);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  };
+#define LCA_TRY(call)                                                                                                     \
+  do {                                                                                                                    \
+    cudaError_t e__ = (call);                                                                                             \
+    if (e__ != cudaSuccess) {                                                                                             \
+      rc = set_error(e__ == cudaErrorMemoryAllocation ? PT_ERR_NOMEM : PT_ERR_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      cleanup(); lca_release(h); return rc;                                                                               \
+    }                                                                                                                     \
+  } while (0)
+  const size_t n4 = (size_t)n * 4;
+  if (parent_mem == PT_MEM_HOST) { LCA_TRY(cudaMalloc((void**)&d_parent, n4)); LCA_TRY(cudaMemcpyAsync(d_parent, parent, n4, cudaMemcpyHostToDevice, s)); }
+  else d_parent = (int32_t*)parent;
+  LCA_TRY(cudaEventCreate(&ev0)); LCA_TRY(cudaEventCreate(&ev1));
+  LCA_TRY(cudaMalloc((void**)&deg, n4 + 4)); LCA_TRY(cudaMalloc((void**)&child_off, n4 + 4)); LCA_TRY(cudaMalloc((void**)&child_adj, n4));
+  LCA_TRY(cudaMalloc((void**)&order, n4)); LCA_TRY(cudaMalloc((void**)&depth, n4)); LCA_TRY(cudaMalloc((void**)&size, n4)); LCA_TRY(cudaMalloc((void**)&pre, n4));
+  LCA_TRY(cudaMalloc((void**)&level_off, n4 + 8)); LCA_TRY(cudaMalloc((void**)&small, 64)); LCA_TRY(cudaMalloc((void**)&nodeat, n4));
+  LCA_TRY(cudaMalloc((void**)&scan_tmp, ((size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1) * 8));
+  LCA_TRY(cudaMalloc((void**)&h->rec, (size_t)n * sizeof(LcaRecord)));
+  LCA_TRY(cudaMalloc((void**)&h->keypos, (size_t)n * 8));
+  // table geometry: level k has nblocks - 2^k + 1 entries
+  std::vector<int64_t> level_base; int64_t total = 0;
+  for (int k = 0; ((int64_t)1 << k) <= h->nblocks; ++k) { level_base.push_back(total); total += h->nblocks - ((int64_t)1 << k) + 1; }
+  h->table_levels = (int64_t)level_base.size();
+  LCA_TRY(cudaMalloc((void**)&h->table, (size_t)total * 8));
+  LCA_TRY(cudaMalloc((void**)&h->d_level_base, level_base.size() * 8));
+  LCA_TRY(cudaMemcpyAsync(h->d_level_base, level_base.data(), level_base.size() * 8, cudaMemcpyHostToDevice, s));
+  h->device_bytes = (int64_t)n * (int64_t)sizeof(LcaRecord) + n * 8 + total * 8;
+
+  LCA_TRY(cudaEventRecord(ev0, s));
+  const int grid = dp.sms * 8;
+  LCA_TRY(cudaMemsetAsync(deg, 0, n4 + 4, s)); LCA_TRY(cudaMemsetAsync(small, 0, 64, s));
+  lca_count_kernel<<<grid, 256, 0, s>>>(d_parent, n, deg, small);
+  if ((rc = device_exclusive_scan(deg, n, child_off, scan_tmp, s)) != PT_OK) { cleanup(); lca_release(h); return rc; }
+  LCA_TRY(cudaMemsetAsync(deg, 0, n4, s));
+  lca_fill_children_kernel<<<grid, 256, 0, s>>>(d_parent, n, child_off, deg, child_adj);
+  int32_t info[8];
+  LCA_TRY(cudaMemcpyAsync(info, small, 32, cudaMemcpyDeviceToHost, s));
+  LCA_TRY(cudaStreamSynchronize(s));
+  if (info[0] != 1 || info[2]) {  // utils/storage_adj_common.hpp:103-109: exactly one root
+    rc = set_error(PT_ERR_INVALID, "pt_lca_build: parent array is not a rooted tree (%d roots%s)", info[0], info[2] ? ", parent index out of range" : "");
+    cleanup(); lca_release(h); return rc;
+  }
+  {
+    int occ = 0;
+    LCA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lca_sweeps_kernel, 256, 0));
+    const int cgrid = dp.sms * std::max(1, std::min(occ, 4));
+    int32_t root = info[1];
+    int64_t nn = n;
+    int32_t* ctr = small + 8; int32_t* inf = small;
+    void* args[] = {&nn, &root, &child_off, &child_adj, &order, &depth, &size, &pre, &level_off, &ctr, &inf};
+    LCA_TRY(cudaLaunchCooperativeKernel((void*)lca_sweeps_kernel, dim3(cgrid), dim3(256), args, 0, s));
+  }
+  LCA_TRY(cudaMemcpyAsync(info, small, 32, cudaMemcpyDeviceToHost, s));
+  LCA_TRY(cudaStreamSynchronize(s));
+  if (info[4] != (int32_t)n) {
+    rc = set_error(PT_ERR_INVALID, "pt_lca_build: parent array is not a tree (%d of %lld nodes reachable from the root: cycle)", info[4], (long long)n);
+    cleanup(); lca_release(h); return rc;
+  }
+  h->levels = info[3];
+  lca_keys_kernel<<<grid, 256, 0, s>>>(n, d_parent, depth, pre, h->keypos, nodeat);
+  lca_blocks_kernel<true><<<grid, 256, 0, s>>>(n, h->nblocks, h->keypos, nodeat, h->rec, h->table);
+  for (size_t k = 1; k < level_base.size(); ++k) {
+    const int64_t count = h->nblocks - ((int64_t)1 << k) + 1;
+    const int g = (int)std::min<int64_t>(grid, (count + 255) / 256);
+    lca_table_level_kernel<<<std::max(g, 1), 256, 0, s>>>(h->table + level_base[k - 1], h->table + level_base[k], count, (int64_t)1 << (k - 1));
+  }
+  LCA_TRY(cudaGetLastError());
+  LCA_TRY(cudaEventRecord(ev1, s));
+  LCA_TRY(cudaStreamSynchronize(s));
+  LCA_TRY(cudaEventElapsedTime(&h->build_ms, ev0, ev1));
+#undef LCA_TRY
+  cleanup();
+  *out = h;
+  return PT_OK;
+}
+
+int pt_lca_query(const pt_lca* hc, const int32_t* u, const int32_t* v, int32_t* out, int64_t q, pt_mem mem, void* stream) {
+  pt_lca* h = const_cast<pt_lca*>(hc);
+  if (!h || q < 0 || (q > 0 && (!u || !v || !out))) return set_error(PT_ERR_INVALID, "pt_lca_query: bad argument");
+  if (q == 0) return PT_OK;
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  const int32_t *du = u, *dv = v; int32_t* dout = out;
+  if (mem == PT_MEM_HOST) {
+    if (h->qcap < q) {
+      cudaFree(h->d_u); cudaFree(h->d_v); cudaFree(h->d_out); h->d_u = h->d_v = h->d_out = nullptr; h->qcap = 0;
+      PT_CUDA(cudaMalloc((void**)&h->d_u, (size_t)q * 4)); PT_CUDA(cudaMalloc((void**)&h->d_v, (size_t)q * 4)); PT_CUDA(cudaMalloc((void**)&h->d_out, (size_t)q * 4));
+      h->qcap = q;
+    }
+    PT_CUDA(cudaMemcpyAsync(h->d_u, u, (size_t)q * 4, cudaMemcpyHostToDevice, s));
+    PT_CUDA(cudaMemcpyAsync(h->d_v, v, (size_t)q * 4, cudaMemcpyHostToDevice, s));
+    du = h->d_u; dv = h->d_v; dout = h->d_out;
+  }
+  constexpr int QPT = 4;
+  const int64_t threads = (q + QPT - 1) / QPT;
+  const int grid = (int)std::min<int64_t>((threads + 255) / 256, (int64_t)dp.sms * 8);
+  lca_query_kernel<QPT><<<std::max(grid, 1), 256, 0, s>>>(q, h->n, du, dv, dout, h->rec, h->keypos, h->table, h->d_level_base);
+  PT_CUDA(cudaGetLastError());
+  if (mem == PT_MEM_HOST) {
+    PT_CUDA(cudaMemcpyAsync(out, dout, (size_t)q * 4, cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaStreamSynchronize(s));
+  }
+  return PT_OK;
+}
+
+int pt_lca_get_info(const pt_lca* h, pt_lca_info* info) {
+  if (!h || !info) return set_error(PT_ERR_INVALID, "pt_lca_get_info: null argument");
+  info->num_nodes = h->n; info->num_levels = h->levels; info->num_blocks = h->nblocks; info->table_levels = h->table_levels;
+  info->device_bytes = h->device_bytes; info->build_ms = h->build_ms;
+  return PT_OK;
+}
+
+int pt_lca_node_info(const pt_lca* h, int32_t* depth, int32_t* preorder, pt_mem mem, void* stream) {
+  if (!h) return set_error(PT_ERR_INVALID, "pt_lca_node_info: null argument");
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t *dd = depth, *dp = preorder;
+  const size_t n4 = (size_t)h->n * 4;
+  if (mem == PT_MEM_HOST) { dd = dp = nullptr; if (depth) PT_CUDA(cudaMalloc((void**)&dd, n4)); if (preorder) PT_CUDA(cudaMalloc((void**)&dp, n4)); }
+  lca_node_info_kernel<<<592, 256, 0, s>>>(h->n, h->rec, dd, dp);
+  PT_CUDA(cudaGetLastError());
+  if (mem == PT_MEM_HOST) {
+    if (depth) PT_CUDA(cudaMemcpyAsync(depth, dd, n4, cudaMemcpyDeviceToHost, s));
+    if (preorder) PT_CUDA(cudaMemcpyAsync(preorder, dp, n4, cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaStreamSynchronize(s));
+    cudaFree(dd); cudaFree(dp);
+  }
+  return PT_OK;
+}
+
+int pt_lca_free(pt_lca* h) { lca_release(h); return PT_OK; }
+
+}  // extern "C"
+
+// ---- RMQ API --------------------------------------------------------------------------------------------------------
+struct pt_rmq {
+  int64_t n = 0, nblocks = 0;
+  LcaRecord* rec = nullptr; u64* keypos = nullptr; u64* table = nullptr; int64_t* d_level_base = nullptr;
+};
+static void rmq_release(pt_rmq* h) { if (!h) return; cudaFree(h->rec); cudaFree(h->keypos); cudaFree(h->table); cudaFree(h->d_level_base); delete h; }
+
+extern "C" {
+
+int pt_rmq_build(pt_rmq** out, const int32_t* values, int64_t n, pt_mem mem, void* stream) {
+  if (!out || !values || n <= 0 || n >= ((int64_t)1 << 32) - 64) return set_error(PT_ERR_INVALID, "pt_rmq_build: bad argument");
+  *out = nullptr;
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  pt_rmq* h = new (std::nothrow) pt_rmq();
+  if (!h) return set_error(PT_ERR_NOMEM, "out of host memory");
+  h->n = n; h->nblocks = (n + 31) / 32;
+  int32_t* dvals = nullptr;
+  auto fail = [&](int code) { if (mem == PT_MEM_HOST) cudaFree(dvals); rmq_release(h); return code; };
+#define RMQ_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(set_error(e__ == cudaErrorMemoryAllocation ? PT_ERR_NOMEM : PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__))); } while (0)
+  if (mem == PT_MEM_HOST) { RMQ_TRY(cudaMalloc((void**)&dvals, (size_t)n * 4)); RMQ_TRY(cudaMemcpyAsync(dvals, values, (size_t)n * 4, cudaMemcpyHostToDevice, s)); }
+  else dvals = (int32_t*)values;
+  std::vector<int64_t> level_base; int64_t total = 0;
+  for (int k = 0; ((int64_t)1 << k) <= h->nblocks; ++k) { level_base.push_back(total); total += h->nblocks - ((int64_t)1 << k) + 1; }
+  RMQ_TRY(cudaMalloc((void**)&h->rec, (size_t)n * sizeof(LcaRecord)));
+  RMQ_TRY(cudaMalloc((void**)&h->keypos, (size_t)n * 8));
+  RMQ_TRY(cudaMalloc((void**)&h->table, (size_t)total * 8));
+  RMQ_TRY(cudaMalloc((void**)&h->d_level_base, level_base.size() * 8));
+  RMQ_TRY(cudaMemcpyAsync(h->d_level_base, level_base.data(), level_base.size() * 8, cudaMemcpyHostToDevice, s));
+  const int grid = dp.sms * 8;
+  rmq_keys_kernel<<<grid, 256, 0, s>>>(n, dvals, h->keypos);
+  lca_blocks_kernel<false><<<grid, 256, 0, s>>>(n, h->nblocks, h->keypos, nullptr, h->rec, h->table);
+  for (size_t k = 1; k < level_base.size(); ++k) {
+    const int64_t count = h->nblocks - ((int64_t)1 << k) + 1;
+    const int g = (int)std::min<int64_t>(grid, (count + 255) / 256);
+    lca_table_level_kernel<<<std::max(g, 1), 256, 0, s>>>(h->table + level_base[k - 1], h->table + level_base[k], count, (int64_t)1 << (k - 1));
+  }
+  RMQ_TRY(cudaGetLastError());
+  RMQ_TRY(cudaStreamSynchronize(s));
+#undef RMQ_TRY
+  if (mem == PT_MEM_HOST) cudaFree(dvals);
+  *out = h;
+  return PT_OK;
+}
+
+int pt_rmq_query(const pt_rmq* h, const int64_t* l, const int64_t* r, int64_t* out_index, int64_t q, pt_mem mem, void* stream) {
+  if (!h || q < 0 || (q > 0 && (!l || !r || !out_index))) return set_error(PT_ERR_INVALID, "pt_rmq_query: bad argument");
+  if (q == 0) return PT_OK;
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t *dl = l, *dr = r; int64_t* dout = out_index;
+  int64_t* buf = nullptr;
+  if (mem == PT_MEM_HOST) {
+    PT_CUDA(cudaMalloc((void**)&buf, (size_t)q * 24));
+    PT_CUDA(cudaMemcpyAsync(buf, l, (size_t)q * 8, cudaMemcpyHostToDevice, s));
+    PT_CUDA(cudaMemcpyAsync(buf + q, r, (size_t)q * 8, cudaMemcpyHostToDevice, s));
+    dl = buf; dr = buf + q; dout = buf + 2 * q;
+  }
+  const int grid = (int)std::min<int64_t>((q + 255) / 256, 148 * 16);
+  rmq_query_kernel<<<std::max(grid, 1), 256, 0, s>>>(q, h->n, dl, dr, dout, h->rec, h->keypos, h->table, h->d_level_base);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && mem == PT_MEM_HOST) { e = cudaMemcpyAsync(out_index, dout, (size_t)q * 8, cudaMemcpyDeviceToHost, s); if (e == cudaSuccess) e = cudaStreamSynchronize(s); }
+  if (mem == PT_MEM_HOST) cudaFree(buf);
+  if (e != cudaSuccess) return set_error(PT_ERR_CUDA, "pt_rmq_query: %s", cudaGetErrorString(e));
+  return PT_OK;
+}
+
+int pt_rmq_free(pt_rmq* h) { rmq_release(h); return PT_OK; }
+
+}  // extern "C"

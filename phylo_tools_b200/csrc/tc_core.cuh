@@ -1,0 +1,639 @@
+// csrc/tc_core.cuh -- the tree-containment reducer, written ONCE as barrier-separated data-parallel passes.
+//
+// Replaces the reference's sequential graph rewriting (utils/containment.hpp:380-1272: NodeSuppresser,
+// ReticulationMerger, CherryPicker, HostGuestMatch, the apply_rules loop :1054-1083 and the branching of
+// displayed() :1202-1270) with level-synchronous passes over flat arrays.  Every loop below is a
+// `PT_FOR(i, n)` = "for all i in [0,n) in parallel, in any order" followed by a barrier; the executor `Ex`
+// decides what runs it: one warp per instance with the instance in shared memory (tc_kernels.cu), or the
+// single-threaded simulator used by the CPU tests (tests/host_sim/, which also permutes the iteration order
+// to expose order dependence).  Nothing here is CPU product code: the library only instantiates the CUDA
+// executor.
+//
+// Rules (all verdict-preserving for arbitrary rooted DAG hosts; soundness arguments in DESIGN.md 4):
+//   clean      dead-end removal, in=out=1 suppression, out-degree-1 root removal, reticulation-chain merge,
+//              parallel-arc merge                                       (cf. containment.hpp:392-409,756-824)
+//   TC         true (multi-)cherry: a host node whose children are all single-parent leaves must equal a guest
+//              node whose children are exactly those leaves -> collapse both, else NOT displayed
+//                                                                       (cf. CherryPicker :538-590, match_nodes :915-950)
+//   RC         reticulated cherry: guest cherry {x,y}, host leaf x hangs on q, y (or the out-degree-1
+//              reticulation above y) has q among its parents -> keep that in-arc, delete the others
+//   SC         sibling constraint: guest cherry {x,y}, host leaf x hangs on q: everything else below q may only
+//              lead to y.  Arcs into multi-parent nodes that cannot reach y are deleted; single-parent subtrees
+//              that cannot reach y must die completely (a labelled leaf there -> NOT displayed)
+//                                                                       (generalises :564-580)
+//   branch     nothing applies: pick the lowest multi-parent node and emit one child instance per in-arc
+//              (cf. displayed() :1225-1266; the reference deep-copies the checker per branch, we append compacted
+//              instances to a pool that the next kernel launch consumes)
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define PT_HD __host__ __device__ __forceinline__
+#else
+#define PT_HD inline
+#endif
+
+namespace ptgpu {
+
+// parallel-for over [0,n): i_ is the executor's slot, i the (possibly permuted) element
+#define PT_FOR(i, n) \
+  for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
+
+enum TcCode : int { TC_NOT = 0, TC_DISPLAYED = 1, TC_BRANCH = 2, TC_ERROR = 3 };
+enum TcStatus : int { TCS_OK = 0, TCS_MULTILABEL = 1, TCS_BAD_GRAPH = 2, TCS_TOO_LARGE = 3, TCS_POOL_OVERFLOW = 4 };
+
+// one instance in the flat layout of include/pt_gpu.h (pointers already offset to the instance)
+struct TcInst {
+  int n, m, nt;
+  const int32_t* succ_off;  // n+1, local
+  const int32_t* succ_adj;  // m
+  const int32_t* hlabel;    // n
+  const int32_t* tparent;   // nt
+  const int32_t* tlabel;    // nt
+};
+// where a branch child is written (same layout, caller provides capacity n+1 / m / n / nt / nt)
+struct TcEmit {
+  int32_t* succ_off; int32_t* succ_adj; int32_t* hlabel; int32_t* tparent; int32_t* tlabel;
+  int32_t* dims;  // n, m, nt, num_labels
+};
+
+struct TcStats { unsigned cherries, retcherries, arcs_deleted, passes; };
+
+template <class I>
+struct TcWork {
+  int capN, capM, capNT, capL, W;
+  // host network
+  I *at, *ah;            // arc tail / head; at < 0 = deleted
+  I *ooff, *oarc;        // out CSR over live arcs (arc ids)
+  I *ioff, *iarc;        // in CSR
+  I *hlab;               // label of a live labelled leaf, else -1
+  I *lvl;                // height (longest path to a leaf) from the wavefront; scratch otherwise
+  int32_t *hcnt, *haux;  // atomic scratch, capN+1 each
+  uint32_t* lset;        // capN * W : labels reachable below each node
+  // guest tree
+  I *tpar, *tlab;        // tpar: -1 root, -2 deleted
+  int32_t *tdeg, *tleaf, *tmin, *tmax;  // live children, live leaf children, min / max leaf-child label
+  // labels
+  I *l2h, *l2t;
+  // scalars (shared)
+  int32_t* sc;           // [0] flag  [1] fail  [2] root  [3] troot  [4] nlabels  [5] best  [6..] scratch
+  static constexpr int kScalars = 16;
+
+  PT_HD static size_t bytes(int N, int M, int NT, int L) {
+    const int W = (L + 31) / 32;
+    size_t b = 0;
+    b += (size_t)(2 * M + (N + 1) + M + (N + 1) + M + N + (N + 1)) * sizeof(I);  // at ah ooff oarc ioff iarc hlab lvl
+    b = (b + 3) & ~(size_t)3;
+    b += (size_t)(2 * (N + 1)) * 4;                                         // hcnt haux
+    b += (size_t)N * W * 4;                                                 // lset
+    b += (size_t)(2 * NT) * sizeof(I);                                      // tpar tlab
+    b = (b + 3) & ~(size_t)3;
+    b += (size_t)(4 * (NT + 1)) * 4;                                        // tdeg tleaf tmin tmax
+    b += (size_t)(2 * L) * sizeof(I);                                       // l2h l2t
+    b = (b + 3) & ~(size_t)3;
+    b += kScalars * 4;
+    return (b + 15) & ~(size_t)15;
+  }
+  PT_HD void carve(void* base, int N, int M, int NT, int L) {
+    capN = N; capM = M; capNT = NT; capL = L; W = (L + 31) / 32;
+    char* p = (char*)base;
+    auto take = [&](size_t nbytes) { char* r = p; p += nbytes; return r; };
+    at = (I*)take((size_t)M * sizeof(I)); ah = (I*)take((size_t)M * sizeof(I));
+    ooff = (I*)take((size_t)(N + 1) * sizeof(I)); oarc = (I*)take((size_t)M * sizeof(I));
+    ioff = (I*)take((size_t)(N + 1) * sizeof(I)); iarc = (I*)take((size_t)M * sizeof(I));
+    hlab = (I*)take((size_t)N * sizeof(I)); lvl = (I*)take((size_t)(N + 1) * sizeof(I));
+    p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
+    hcnt = (int32_t*)take((size_t)(N + 1) * 4); haux = (int32_t*)take((size_t)(N + 1) * 4);
+    lset = (uint32_t*)take((size_t)N * W * 4);
+    tpar = (I*)take((size_t)NT * sizeof(I)); tlab = (I*)take((size_t)NT * sizeof(I));
+    p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
+    tdeg = (int32_t*)take((size_t)(NT + 1) * 4); tleaf = (int32_t*)take((size_t)(NT + 1) * 4);
+    tmin = (int32_t*)take((size_t)(NT + 1) * 4); tmax = (int32_t*)take((size_t)(NT + 1) * 4);
+    l2h = (I*)take((size_t)L * sizeof(I)); l2t = (I*)take((size_t)L * sizeof(I));
+    p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
+    sc = (int32_t*)take(kScalars * 4);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+template <class Ex, class I>
+struct TcSolver {
+  Ex& ex;
+  TcWork<I>& w;
+  int n, m, nt, L;  // uniform across the group
+  TcStats st;
+
+  PT_HD TcSolver(Ex& e, TcWork<I>& work) : ex(e), w(work), n(0), m(0), nt(0), L(0) { st.cherries = st.retcherries = st.arcs_deleted = st.passes = 0; }
+
+  enum { F_FLAG = 0, F_FAIL = 1, F_ROOT = 2, F_TROOT = 3, F_NLAB = 4, F_BEST = 5, F_STATUS = 6, F_TMP = 7, F_TMP2 = 8 };
+  static constexpr int TDEAD = -2;
+  static constexpr int LVL_INF = 32000;
+
+  // ---- small helpers -----------------------------------------------------------------------------------
+  PT_HD int outdeg(int v) const { return w.ooff[v + 1] - w.ooff[v]; }
+  PT_HD int indeg(int v) const { return w.ioff[v + 1] - w.ioff[v]; }
+  PT_HD int out_arc(int v, int k) const { return w.oarc[w.ooff[v] + k]; }
+  PT_HD int in_arc(int v, int k) const { return w.iarc[w.ioff[v] + k]; }
+  PT_HD bool lbit(int v, int lam) const { return (w.lset[v * w.W + (lam >> 5)] >> (lam & 31)) & 1u; }
+  // read a shared flag uniformly and reset it
+  PT_HD int take_flag(int which) {
+    ex.sync();
+    const int v = w.sc[which];
+    ex.sync();
+    if (ex.tid() == 0) w.sc[which] = 0;
+    ex.sync();
+    return v;
+  }
+  PT_HD void set_scalar(int which, int v) { if (ex.tid() == 0) w.sc[which] = v; ex.sync(); }
+
+  // ---- load + validate ---------------------------------------------------------------------------------
+  // returns TCS_* ; sets up arcs, labels, guest arrays.  Leaves w.sc[F_FAIL]=1 if a guest label is missing in the host.
+  PT_HD int load(const TcInst& in) {
+    n = in.n; m = in.m; nt = in.nt;
+    if (n > w.capN || m > w.capM || nt > w.capNT || n < 0 || m < 0 || nt < 0) return TCS_TOO_LARGE;
+    if (ex.tid() == 0) { for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
+    ex.sync();
+    // structure checks on the CSR offsets
+    PT_FOR(v, n + 1) {
+      const int o = in.succ_off[v];
+      if (o < 0 || o > m || (v < n && in.succ_off[v + 1] < o) || (v == 0 && o != 0) || (v == n && o != m)) w.sc[F_STATUS] = TCS_BAD_GRAPH;
+      w.ooff[v] = (I)(o < 0 ? 0 : (o > m ? m : o));
+    }
+    if (take_flag(F_STATUS)) return TCS_BAD_GRAPH;
+    int maxlab = -1;
+    PT_FOR(v, n) {
+      for (int e = w.ooff[v]; e < w.ooff[v + 1]; ++e) w.at[e] = (I)v;
+      const int l = in.hlabel[v];
+      w.hlab[v] = (I)l;
+      if (l >= w.capL || l < -1) w.sc[F_STATUS] = TCS_TOO_LARGE;
+      if (l > maxlab) maxlab = l;
+    }
+    PT_FOR(e, m) {
+      const int h = in.succ_adj[e];
+      if (h < 0 || h >= n) w.sc[F_STATUS] = TCS_BAD_GRAPH;
+      w.ah[e] = (I)h;
+    }
+    PT_FOR(t, nt) {
+      const int p = in.tparent[t], l = in.tlabel[t];
+      if (p < -1 || p >= nt || p == t) w.sc[F_STATUS] = TCS_BAD_GRAPH;
+      if (l >= w.capL || l < -1) w.sc[F_STATUS] = TCS_TOO_LARGE;
+      if (l > maxlab) maxlab = l;
+      w.tpar[t] = (I)p; w.tlab[t] = (I)l; w.tdeg[t] = 0;
+    }
+    ex.atomic_max(&w.sc[F_NLAB], maxlab + 1);
+    {
+      const int s = take_flag(F_STATUS);
+      if (s) return s;
+    }
+    L = w.sc[F_NLAB];
+    ex.sync();
+    PT_FOR(l, L) { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
+    // guest: child counts, exactly one root, no cycles
+    PT_FOR(t, nt) { if (w.tpar[t] >= 0) ex.atomic_add(&w.tdeg[w.tpar[t]], 1); else ex.atomic_add(&w.sc[F_TMP], 1); }
+    ex.sync();
+    if (nt > 0 && w.sc[F_TMP] != 1) return TCS_BAD_GRAPH;
+    ex.sync();
+    PT_FOR(t, nt) {
+      int x = t, steps = 0;
+      while (w.tpar[x] >= 0 && steps <= nt) { x = w.tpar[x]; ++steps; }
+      if (steps > nt) w.sc[F_STATUS] = TCS_BAD_GRAPH;
+      if (w.tpar[t] < 0) w.sc[F_TROOT] = t;
+    }
+    set_scalar(F_TMP, 0);
+    if (take_flag(F_STATUS)) return TCS_BAD_GRAPH;
+    // label tables: only out-degree-0 nodes carry labels
+    PT_FOR(v, n) {
+      const int l = w.hlab[v];
+      if (l >= 0) {
+        if (w.ooff[v + 1] == w.ooff[v]) { if (ex.atomic_cas_idx(&w.l2h[l], -1, v) != -1) w.sc[F_STATUS] = TCS_MULTILABEL; }
+        else w.hlab[v] = (I)-1;
+      }
+    }
+    PT_FOR(t, nt) {
+      const int l = w.tlab[t];
+      if (l >= 0) {
+        if (w.tdeg[t] == 0) { if (ex.atomic_cas_idx(&w.l2t[l], -1, t) != -1) w.sc[F_STATUS] = TCS_MULTILABEL; }
+        else w.tlab[t] = (I)-1;
+      }
+    }
+    if (take_flag(F_STATUS)) return TCS_MULTILABEL;
+    // containment.hpp:1110-1125: label only in the guest -> not displayed; only in the host -> leaf loses its label
+    PT_FOR(l, L) {
+      const int h = w.l2h[l], t = w.l2t[l];
+      if (t >= 0 && h < 0) w.sc[F_FAIL] = 1;
+      if (h >= 0 && t < 0) { w.hlab[h] = (I)-1; w.l2h[l] = (I)-1; }
+    }
+    ex.sync();
+    return TCS_OK;
+  }
+
+  // ---- guest clean-up: drop unlabelled leaves, suppress unary nodes --------------------------------------
+  PT_HD void clean_guest() {
+    for (;;) {
+      PT_FOR(t, nt) {
+        if (w.tpar[t] != TDEAD && w.tdeg[t] == 0 && w.tlab[t] < 0) {
+          const int p = w.tpar[t];
+          w.tpar[t] = (I)TDEAD;
+          if (p >= 0) ex.atomic_add(&w.tdeg[p], -1);
+          w.sc[F_FLAG] = 1;
+        }
+      }
+      if (!take_flag(F_FLAG)) break;
+    }
+    // new parent = nearest proper ancestor with >= 2 live children (tmin used as the double buffer)
+    PT_FOR(t, nt) {
+      int np = TDEAD;
+      if (w.tpar[t] != TDEAD && w.tdeg[t] != 1) {
+        int p = w.tpar[t];
+        while (p >= 0 && w.tdeg[p] == 1) p = w.tpar[p];
+        np = p;
+      }
+      w.tmin[t] = np;
+    }
+    ex.sync();
+    PT_FOR(t, nt) { w.tpar[t] = (I)w.tmin[t]; if (w.tmin[t] == -1) w.sc[F_TROOT] = t; }
+    ex.sync();
+  }
+
+  // ---- host CSR over live arcs ---------------------------------------------------------------------------
+  PT_HD void csr() {
+    PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = 0; }
+    ex.sync();
+    PT_FOR(e, m) { if (w.at[e] >= 0) { ex.atomic_add(&w.hcnt[w.at[e]], 1); ex.atomic_add(&w.haux[w.ah[e]], 1); } }
+    ex.sync();
+    ex.exclusive_scan(w.hcnt, w.ooff, n);
+    ex.exclusive_scan(w.haux, w.ioff, n);
+    PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = 0; }
+    ex.sync();
+    PT_FOR(e, m) {
+      if (w.at[e] >= 0) {
+        w.oarc[w.ooff[w.at[e]] + ex.atomic_add(&w.hcnt[w.at[e]], 1)] = (I)e;
+        w.iarc[w.ioff[w.ah[e]] + ex.atomic_add(&w.haux[w.ah[e]], 1)] = (I)e;
+      }
+    }
+    ex.sync();
+  }
+
+  PT_HD bool suppressible(int v) const { return indeg(v) == 1 && outdeg(v) == 1; }
+  // multi-parent node with a single child that is itself multi-parent: its parents can be handed down
+  PT_HD bool mergeable(int v) const { return indeg(v) >= 2 && outdeg(v) == 1 && indeg(w.ah[out_arc(v, 0)]) >= 2; }
+
+  // ---- host clean-up to a fix-point (sets F_FAIL when a label became unreachable) ------------------------------
+  PT_HD void clean_host() {
+    for (;;) {
+      csr();
+      // (a) dead ends: unlabelled nodes without live children lose their in-arcs
+      // (a') orphans: a non-root node that lost every in-arc (all were ruled out) is unreachable: drop its out-arcs;
+      //      an orphaned labelled leaf means its label cannot be displayed any more
+      const int root = w.sc[F_ROOT];
+      PT_FOR(v, n) {
+        if (outdeg(v) == 0) {
+          if (w.hlab[v] < 0) { if (indeg(v) > 0) { for (int k = 0; k < indeg(v); ++k) w.at[in_arc(v, k)] = (I)-1; w.sc[F_FLAG] = 1; } }
+          else if (indeg(v) == 0 && v != root) w.sc[F_FAIL] = 1;
+        } else if (indeg(v) == 0 && v != root) {
+          for (int k = 0; k < outdeg(v); ++k) w.at[out_arc(v, k)] = (I)-1;
+          w.sc[F_FLAG] = 1;
+        }
+      }
+      if (take_flag(F_FLAG)) continue;
+      if (w.sc[F_FAIL]) return;  // caller checks F_FAIL
+      // (b) out-degree-1 root: its child becomes the root
+      if (outdeg(root) == 1) {
+        ex.sync();
+        if (ex.tid() == 0) { const int e = out_arc(root, 0); w.at[e] = (I)-1; w.sc[F_ROOT] = w.ah[e]; }
+        ex.sync();
+        continue;
+      }
+      // (c) suppress in=out=1 chains.  Every arc decides for itself, so the pass is race-free: an arc whose tail is
+      // suppressible disappears; an arc entering a chain from a non-suppressible tail jumps to the end of the chain.
+      PT_FOR(e, m) {
+        const int t = w.at[e];
+        if (t >= 0) {
+          if (suppressible(t)) { w.at[e] = (I)-1; w.sc[F_FLAG] = 1; }
+          else {
+            int h = w.ah[e];
+            if (suppressible(h)) {
+              while (suppressible(h)) h = w.ah[out_arc(h, 0)];
+              w.ah[e] = (I)h;
+            }
+          }
+        }
+      }
+      if (take_flag(F_FLAG)) continue;
+      // (d) reticulation chains: hand the parents of x down to the bottom of the chain (cf. ReticulationMerger :392-409)
+      PT_FOR(v, n) {
+        int y = -1;
+        if (mergeable(v)) { y = w.ah[out_arc(v, 0)]; while (mergeable(y)) y = w.ah[out_arc(y, 0)]; }
+        w.haux[v] = y;
+      }
+      ex.sync();
+      PT_FOR(v, n) {
+        if (w.haux[v] >= 0) {
+          for (int k = 0; k < indeg(v); ++k) w.ah[in_arc(v, k)] = (I)w.haux[v];
+          w.at[out_arc(v, 0)] = (I)-1;
+          w.sc[F_FLAG] = 1;
+        }
+      }
+      if (take_flag(F_FLAG)) continue;
+      // (e) parallel arcs (can appear after (c)/(d)): keep the lowest arc id
+      PT_FOR(v, n) {
+        const int d = outdeg(v);
+        if (d >= 2 && d <= 8) {
+          for (int a = 0; a < d; ++a)
+            for (int b = 0; b < d; ++b) {
+              const int ea = out_arc(v, a), eb = out_arc(v, b);
+              if (ea < eb && w.ah[ea] == w.ah[eb]) { w.at[eb] = (I)-1; w.sc[F_FLAG] = 1; }
+            }
+        }
+      }
+      if (take_flag(F_FLAG)) continue;
+      return;
+    }
+  }
+
+  PT_HD int count_labels() {
+    PT_FOR(l, L) { if (w.l2h[l] >= 0) ex.atomic_add(&w.sc[F_TMP], 1); }
+    ex.sync();
+    const int k = w.sc[F_TMP];
+    ex.sync();
+    set_scalar(F_TMP, 0);
+    return k;
+  }
+
+  // ---- wavefront over topological levels: heights and reachable-label bitsets -----------------------------
+  // returns false if some live node was never reached (cycle)
+  PT_HD bool wavefront() {
+    const int W = w.W;
+    PT_FOR(v, n) {
+      for (int k = 0; k < W; ++k) w.lset[v * W + k] = 0;
+      w.hcnt[v] = outdeg(v);
+      w.lvl[v] = (I)((outdeg(v) == 0 && (indeg(v) > 0 || w.hlab[v] >= 0)) ? 0 : LVL_INF);
+      if (w.hlab[v] >= 0) w.lset[v * W + (w.hlab[v] >> 5)] = 1u << (w.hlab[v] & 31);
+    }
+    ex.sync();
+    for (int lev = 0;; ++lev) {
+      PT_FOR(v, n) {
+        if (w.lvl[v] == lev) {
+          w.sc[F_FLAG] = 1;
+          for (int k = 0; k < indeg(v); ++k) {
+            const int p = w.at[in_arc(v, k)];
+            for (int j = 0; j < W; ++j) { const uint32_t b = w.lset[v * W + j]; if (b) ex.atomic_or(&w.lset[p * W + j], b); }
+            if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.lvl[p] = (I)(lev + 1);
+          }
+        }
+      }
+      if (!take_flag(F_FLAG)) break;
+    }
+    PT_FOR(v, n) { if (outdeg(v) > 0 && w.lvl[v] == LVL_INF) w.sc[F_FLAG] = 1; }
+    return !take_flag(F_FLAG);
+  }
+
+  // ---- TC: true (multi-)cherries --------------------------------------------------------------------------
+  // returns 1 changed, 0 nothing, -1 NOT displayed
+  PT_HD int rule_true_cherry() {
+    PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = -1; }
+    PT_FOR(t, nt) { w.tmin[t] = 0x7fffffff; }
+    ex.sync();
+    PT_FOR(l, L) {
+      const int h = w.l2h[l];
+      if (h >= 0 && indeg(h) == 1) ex.atomic_add(&w.hcnt[w.at[in_arc(h, 0)]], 1);
+    }
+    ex.sync();
+    PT_FOR(l, L) {
+      const int h = w.l2h[l];
+      if (h >= 0 && indeg(h) == 1) {
+        const int q = w.at[in_arc(h, 0)];
+        if (w.hcnt[q] == outdeg(q) && outdeg(q) >= 2) {
+          const int p = w.tpar[w.l2t[l]];
+          if (p < 0) w.sc[F_FAIL] = 1;
+          else {
+            const int old = ex.atomic_cas(&w.haux[q], -1, p);
+            if (old != -1 && old != p) w.sc[F_FAIL] = 1;
+            ex.atomic_min(&w.tmin[p], l);
+          }
+        }
+      }
+    }
+    ex.sync();
+    PT_FOR(q, n) {
+      if (w.haux[q] >= 0 && w.tdeg[w.haux[q]] != outdeg(q)) w.sc[F_FAIL] = 1;
+    }
+    ex.sync();
+    if (w.sc[F_FAIL]) return -1;
+    PT_FOR(l, L) {
+      const int h = w.l2h[l];
+      if (h >= 0 && indeg(h) == 1) {
+        const int q = w.at[in_arc(h, 0)];
+        if (w.haux[q] >= 0) {
+          const int p = w.haux[q], t = w.l2t[l];
+          w.at[in_arc(h, 0)] = (I)-1;
+          w.hlab[h] = (I)-1;
+          w.tlab[t] = (I)-1; w.tpar[t] = (I)TDEAD;
+          if (l == w.tmin[p]) {
+            w.hlab[q] = (I)l; w.l2h[l] = (I)q;
+            w.tlab[p] = (I)l; w.l2t[l] = (I)p; w.tdeg[p] = 0;
+            ex.atomic_add(&w.sc[F_TMP2], 1);
+          } else { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
+          w.sc[F_FLAG] = 1;
+        }
+      }
+    }
+    ex.sync();
+    st.cherries += (unsigned)w.sc[F_TMP2];
+    ex.sync();
+    set_scalar(F_TMP2, 0);
+    return take_flag(F_FLAG) ? 1 : 0;
+  }
+
+  // ---- guest cherries with exactly two leaves: tmin/tmax = their labels, tleaf = 2 ---------------------------
+  PT_HD void guest_cherries() {
+    PT_FOR(t, nt) { w.tleaf[t] = 0; w.tmin[t] = 0x7fffffff; w.tmax[t] = -1; }
+    ex.sync();
+    PT_FOR(l, L) {
+      const int t = w.l2t[l];
+      if (t >= 0 && w.tpar[t] >= 0) { const int p = w.tpar[t]; ex.atomic_add(&w.tleaf[p], 1); ex.atomic_min(&w.tmin[p], l); ex.atomic_max(&w.tmax[p], l); }
+    }
+    ex.sync();
+  }
+  PT_HD bool is_bin_cherry(int p) const { return w.tpar[p] != TDEAD && w.tdeg[p] == 2 && w.tleaf[p] == 2; }
+
+  // ---- RC: reticulated cherries ---------------------------------------------------------------------------
+  PT_HD int rule_ret_cherry() {
+    PT_FOR(p, nt) {
+      if (is_bin_cherry(p)) {
+        for (int side = 0; side < 2; ++side) {
+          const int x = side ? w.tmax[p] : w.tmin[p], y = side ? w.tmin[p] : w.tmax[p];
+          const int hx = w.l2h[x], hy = w.l2h[y];
+          if (indeg(hx) != 1) continue;
+          const int q = w.at[in_arc(hx, 0)];
+          int c = -1;  // the multi-parent node whose parent gets fixed to q
+          if (indeg(hy) >= 2) c = hy;
+          else if (indeg(hy) == 1) { const int z = w.at[in_arc(hy, 0)]; if (outdeg(z) == 1 && indeg(z) >= 2) c = z; }
+          if (c < 0) continue;
+          int keep = -1;
+          for (int k = 0; k < indeg(c); ++k) if (w.at[in_arc(c, k)] == q) keep = in_arc(c, k);
+          if (keep < 0) continue;
+          for (int k = 0; k < indeg(c); ++k) { const int e = in_arc(c, k); if (e != keep) w.at[e] = (I)-1; }
+          ex.atomic_add(&w.sc[F_TMP2], 1);
+          w.sc[F_FLAG] = 1;
+          break;
+        }
+      }
+    }
+    ex.sync();
+    st.retcherries += (unsigned)w.sc[F_TMP2];
+    ex.sync();
+    set_scalar(F_TMP2, 0);
+    return take_flag(F_FLAG) ? 1 : 0;
+  }
+
+  // ---- SC: sibling constraints ----------------------------------------------------------------------------
+  // haux[v] = constraint of single-parent node v: -1 none, lam >= 0 "live leaves below v are a subset of {lam}",
+  // -2 "nothing below v may stay alive".  hcnt[v] = 1 once v has been expanded.
+  PT_HD void constrain_arc(int e, int lam) {
+    const int c = w.ah[e];
+    const bool reach = lam >= 0 && lbit(c, lam);
+    if (indeg(c) >= 2) {
+      if (!reach) { w.at[e] = (I)-1; ex.atomic_add(&w.sc[F_TMP2], 1); w.sc[F_FLAG] = 1; }
+      return;
+    }
+    if (outdeg(c) == 0) { if (!reach) w.sc[F_FAIL] = 1; return; }  // a labelled single-parent leaf that must die
+    const int want = reach ? lam : -2;
+    if (w.haux[c] != want) { w.haux[c] = want; w.sc[F_TMP] = 1; }
+  }
+  PT_HD int rule_sibling() {
+    PT_FOR(v, n + 1) { w.haux[v] = -1; w.hcnt[v] = 0; }
+    ex.sync();
+    PT_FOR(p, nt) {
+      if (is_bin_cherry(p)) {
+        for (int side = 0; side < 2; ++side) {
+          const int x = side ? w.tmax[p] : w.tmin[p], y = side ? w.tmin[p] : w.tmax[p];
+          const int hx = w.l2h[x];
+          if (indeg(hx) != 1) continue;
+          const int q = w.at[in_arc(hx, 0)];
+          for (int k = 0; k < outdeg(q); ++k) { const int e = out_arc(q, k); if (w.ah[e] != hx) constrain_arc(e, y); }
+        }
+      }
+    }
+    // propagate through single-parent nodes
+    for (;;) {
+      if (!take_flag(F_TMP)) break;
+      PT_FOR(v, n) {
+        if (w.haux[v] != -1 && !w.hcnt[v]) {
+          w.hcnt[v] = 1;
+          for (int k = 0; k < outdeg(v); ++k) constrain_arc(out_arc(v, k), w.haux[v]);
+        }
+      }
+    }
+    ex.sync();
+    if (w.sc[F_FAIL]) return -1;
+    st.arcs_deleted += (unsigned)w.sc[F_TMP2];
+    ex.sync();
+    set_scalar(F_TMP2, 0);
+    return take_flag(F_FLAG) ? 1 : 0;
+  }
+
+  // ---- branching: lowest multi-parent node ------------------------------------------------------------------
+  PT_HD int pick_branch_node() {
+    set_scalar(F_BEST, 0x7fffffff);
+    PT_FOR(v, n) { if (indeg(v) >= 2) ex.atomic_min(&w.sc[F_BEST], ((int)w.lvl[v] << 16) | v); }
+    ex.sync();
+    const int b = w.sc[F_BEST];
+    ex.sync();
+    return b == 0x7fffffff ? -1 : (b & 0xffff);
+  }
+
+  // write the current (clean) state, with only in-arc `keep` of node x kept, as a compact instance.
+  // Label ids are kept (no renumbering), so L and the bitset width stay those of the parent.
+  PT_HD void emit_child(int x, int keep, const TcEmit& out) {
+    const int root = w.sc[F_ROOT];
+    // live host nodes (root, or any live in-arc) -> new ids by a scan of the flags (lvl is free after pick_branch_node)
+    PT_FOR(v, n + 1) {
+      const int live = (v < n && (v == root || indeg(v) > 0)) ? 1 : 0;
+      int d = 0;
+      if (live) for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) ++d; }
+      w.hcnt[v] = live; w.haux[v] = d;
+    }
+    ex.sync();
+    ex.exclusive_scan(w.hcnt, w.lvl, n);   // lvl[v] = new id of v, lvl[n] = n2
+    ex.exclusive_scan(w.haux, w.ioff, n);  // ioff is rebuilt by the next csr(); from here on indeg() is invalid
+    const int n2 = w.lvl[n], m2 = w.ioff[n];
+    PT_FOR(v, n) {
+      if (w.hcnt[v]) {
+        const int id = w.lvl[v];
+        out.succ_off[id] = w.ioff[v];
+        out.hlabel[id] = w.hlab[v];
+        int pos = w.ioff[v];
+        for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) out.succ_adj[pos++] = w.lvl[w.ah[e]]; }
+      }
+    }
+    // guest
+    PT_FOR(t, nt + 1) { w.tleaf[t] = (t < nt && w.tpar[t] != TDEAD) ? 1 : 0; }
+    ex.sync();
+    ex.exclusive_scan(w.tleaf, w.tmin, nt);
+    const int nt2 = w.tmin[nt];
+    PT_FOR(t, nt) {
+      if (w.tleaf[t]) { const int id = w.tmin[t]; out.tparent[id] = w.tpar[t] >= 0 ? w.tmin[w.tpar[t]] : -1; out.tlabel[id] = w.tlab[t]; }
+    }
+    if (ex.tid() == 0) { out.succ_off[n2] = m2; out.dims[0] = n2; out.dims[1] = m2; out.dims[2] = nt2; out.dims[3] = L; }
+    ex.sync();
+  }
+
+  // Kahn peel from the leaves: every node must be reached, exactly one node has no in-arc (the reference throws
+  // std::logic_error for several roots, utils/storage_adj_common.hpp:103-109; a cycle would hang its DFS)
+  PT_HD bool check_dag(bool trusted) {
+    csr();
+    PT_FOR(v, n) { w.hcnt[v] = outdeg(v); w.lvl[v] = (I)(outdeg(v) == 0 ? 0 : LVL_INF); if (indeg(v) == 0) { ex.atomic_add(&w.sc[F_TMP], 1); w.sc[F_ROOT] = v; } }
+    ex.sync();
+    const int nroots = w.sc[F_TMP];
+    ex.sync();
+    set_scalar(F_TMP, 0);
+    if (n > 0 && nroots != 1) return false;
+    if (trusted) return true;
+    for (int lev = 0;; ++lev) {
+      PT_FOR(v, n) {
+        if (w.lvl[v] == lev) {
+          w.sc[F_FLAG] = 1;
+          for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.lvl[p] = (I)(lev + 1); }
+        }
+      }
+      if (!take_flag(F_FLAG)) break;
+      if (lev > n) return false;
+    }
+    PT_FOR(v, n) { if (w.lvl[v] == LVL_INF) w.sc[F_FLAG] = 1; }
+    return !take_flag(F_FLAG);
+  }
+
+  // ---- the rule loop (apply_rules, containment.hpp:1054-1083) -----------------------------------------------
+  // returns TcCode; on TC_ERROR *status holds the TCS_* ; on TC_BRANCH *branch_node is the node to branch on
+  PT_HD int solve(const TcInst& in, bool trusted, int* status, int* branch_node) {
+    *status = TCS_OK; *branch_node = -1;
+    int s = load(in);
+    if (s != TCS_OK) { *status = s; return TC_ERROR; }
+    if (!check_dag(trusted)) { *status = TCS_BAD_GRAPH; return TC_ERROR; }
+    if (w.sc[F_FAIL]) return TC_NOT;
+    clean_guest();
+    for (;;) {
+      ++st.passes;
+      clean_host();
+      if (w.sc[F_FAIL]) return TC_NOT;
+      if (count_labels() <= 2) return TC_DISPLAYED;  // containment.hpp:1061,1208
+      int r = rule_true_cherry();
+      if (r < 0) return TC_NOT;
+      if (r > 0) continue;
+      guest_cherries();
+      r = rule_ret_cherry();
+      if (r > 0) continue;
+      if (!wavefront()) { *status = TCS_BAD_GRAPH; return TC_ERROR; }
+      r = rule_sibling();
+      if (r < 0) return TC_NOT;
+      if (r > 0) continue;
+      const int x = pick_branch_node();
+      if (x < 0) { *status = TCS_BAD_GRAPH; return TC_ERROR; }  // a clean tree host always has a true cherry
+      *branch_node = x;
+      return TC_BRANCH;
+    }
+  }
+};
+
+}  // namespace ptgpu

@@ -1,0 +1,412 @@
+// csrc/tc_kernels.cu -- batched tree containment on sm_100a: one warp per (sub)instance, instance state in shared
+// memory, persistent warps pulling work items from an atomic ticket; branching is level-synchronous over a pool of
+// compacted child instances (one kernel launch per branching depth).
+//
+// Entry points: pt_batch_create / pt_batch_contain / pt_batch_free (include/pt_gpu.h), standing in for
+// TreeInNetContainment(...).displayed() (utils/containment.hpp:1179-1202) and TreeInTreeContainment(...).displayed() (:50-83).
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "cuda_common.cuh"
+#include "tc_core.cuh"
+
+namespace ptgpu {
+
+// ---- the warp executor: PT_FOR = lane-strided loop, barrier = __syncwarp, atomics on shared memory ---------------
+struct WarpEx {
+  int lane;
+  __device__ __forceinline__ int tid() const { return lane; }
+  __device__ __forceinline__ int nth() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ int map(int i, int) const { return i; }
+  __device__ __forceinline__ int atomic_add(int32_t* p, int v) const { return atomicAdd(p, v); }
+  __device__ __forceinline__ int atomic_min(int32_t* p, int v) const { return atomicMin(p, v); }
+  __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
+  __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
+  __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
+  __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
+    return (int)(int16_t)atomicCAS((unsigned short*)p, (unsigned short)(int16_t)c, (unsigned short)(int16_t)v);
+  }
+  // out[0..n] = exclusive prefix sums of in[0..n): each lane owns a contiguous chunk, warp shuffle scan over chunk sums
+  template <class T>
+  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) const {
+    __syncwarp();
+    const int chunk = (n + 31) >> 5;
+    const int b = lane * chunk, e = min(b + chunk, n);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += in[i];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    int acc = incl - sum;
+    for (int i = b; i < e; ++i) { const int v = in[i]; out[i] = (T)acc; acc += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) out[n] = (T)total;
+    __syncwarp();
+  }
+};
+
+// where work items come from: the caller's batch (offset tables) or a pool of fixed-stride slots
+struct TcSource {
+  int64_t count;            // batch mode: number of instances
+  const int32_t* count_ptr; // pool mode: device counter (clamped to capacity)
+  int is_pool, capacity;
+  const int64_t *hnode_off, *harc_off, *gnode_off;
+  const int32_t *succ_off, *succ_adj, *hlabel, *tparent, *tlabel;
+  const int32_t *dims, *origin;  // pool mode
+  int sN1, sM, sN, sNT;          // pool strides (elements)
+};
+struct TcSink {
+  int32_t *succ_off, *succ_adj, *hlabel, *tparent, *tlabel, *dims, *origin;
+  int32_t* count;  // atomic
+  int capacity, sN1, sM, sN, sNT;
+};
+enum { CNT_DISPLAYED = 0, CNT_ITEMS, CNT_BRANCH_ITEMS, CNT_CHERRIES, CNT_RET, CNT_ARCS, CNT_PASSES, CNT_ERRORS, CNT_N };
+
+template <class I>
+__global__ void __launch_bounds__(256) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
+                                                        uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
+                                                        uint8_t* __restrict__ branched, int32_t* __restrict__ ticket,
+                                                        unsigned long long* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpEx ex{lane};
+  TcWork<I> w;
+  w.carve(smem + (size_t)warp * warp_bytes, capN, capM, capNT, capL);
+  const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
+  unsigned long long c_disp = 0, c_items = 0, c_br = 0, c_ch = 0, c_ret = 0, c_arc = 0, c_pass = 0, c_err = 0;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(ticket, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    TcInst in;
+    int origin;
+    if (src.is_pool) {
+      origin = src.origin[item];
+      int done = 0;
+      if (lane == 0) done = (int)((*(volatile uint32_t*)&result_bits[origin >> 5] >> (origin & 31)) & 1u);
+      if (__shfl_sync(0xffffffffu, done, 0)) continue;  // a sibling branch already displayed it
+      in.n = src.dims[4 * item]; in.m = src.dims[4 * item + 1]; in.nt = src.dims[4 * item + 2];
+      in.succ_off = src.succ_off + (size_t)item * src.sN1; in.succ_adj = src.succ_adj + (size_t)item * src.sM;
+      in.hlabel = src.hlabel + (size_t)item * src.sN; in.tparent = src.tparent + (size_t)item * src.sNT; in.tlabel = src.tlabel + (size_t)item * src.sNT;
+    } else {
+      origin = item;
+      const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
+      const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
+      in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
+      if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
+      in.succ_off = src.succ_off + hb + item; in.succ_adj = src.succ_adj + ab; in.hlabel = src.hlabel + hb;
+      in.tparent = src.tparent + gb; in.tlabel = src.tlabel + gb;
+    }
+    TcSolver<WarpEx, I> sv(ex, w);
+    int st = 0, x = -1;
+    const int code = sv.solve(in, src.is_pool != 0, &st, &x);
+    ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
+    if (code == TC_DISPLAYED) {
+      if (lane == 0) { atomicOr(&result_bits[origin >> 5], 1u << (origin & 31)); }
+      ++c_disp;
+    } else if (code == TC_ERROR) {
+      if (lane == 0) status[origin] = (uint8_t)st;
+      ++c_err;
+    } else if (code == TC_BRANCH) {
+      const int d = sv.indeg(x);
+      int base = 0;
+      if (lane == 0) base = atomicAdd(sink.count, d);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base + d > sink.capacity) {
+        if (lane == 0) status[origin] = (uint8_t)TCS_POOL_OVERFLOW;
+      } else {
+        if (lane == 0) branched[origin] = 1;
+        c_br += (unsigned long long)d;
+        for (int k = 0; k < d; ++k) {
+          if (k > 0) sv.csr();  // emit_child overwrites the in-CSR offsets
+          const int keep = sv.in_arc(x, k);
+          const size_t slot = (size_t)(base + k);
+          TcEmit out{sink.succ_off + slot * sink.sN1, sink.succ_adj + slot * sink.sM, sink.hlabel + slot * sink.sN,
+                     sink.tparent + slot * sink.sNT, sink.tlabel + slot * sink.sNT, sink.dims + slot * 4};
+          sv.emit_child(x, keep, out);
+          if (lane == 0) sink.origin[slot] = origin;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    if (c_disp) atomicAdd(&counters[CNT_DISPLAYED], c_disp);
+    if (c_items) atomicAdd(&counters[CNT_ITEMS], c_items);
+    if (c_br) atomicAdd(&counters[CNT_BRANCH_ITEMS], c_br);
+    if (c_ch) atomicAdd(&counters[CNT_CHERRIES], c_ch);
+    if (c_ret) atomicAdd(&counters[CNT_RET], c_ret);
+    if (c_arc) atomicAdd(&counters[CNT_ARCS], c_arc);
+    if (c_pass) atomicAdd(&counters[CNT_PASSES], c_pass);
+    if (c_err) atomicAdd(&counters[CNT_ERRORS], c_err);
+  }
+}
+
+// per-batch maxima of n, m, nt and label id (for DEVICE input without hints)
+__global__ void tc_maxima_kernel(int64_t B, const int64_t* hnode_off, const int64_t* harc_off, const int64_t* gnode_off,
+                                 const int32_t* hlabel, const int32_t* tlabel, int32_t* out4) {
+  int mn = 0, mm = 0, mt = 0, ml = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    mn = max(mn, (int)(hnode_off[i + 1] - hnode_off[i])); mm = max(mm, (int)(harc_off[i + 1] - harc_off[i])); mt = max(mt, (int)(gnode_off[i + 1] - gnode_off[i]));
+  }
+  const int64_t NH = hnode_off[B], NG = gnode_off[B];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NH; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, hlabel[i] + 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NG; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, tlabel[i] + 1);
+  for (int d = 16; d; d >>= 1) {
+    mn = max(mn, __shfl_xor_sync(0xffffffffu, mn, d)); mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, d));
+    mt = max(mt, __shfl_xor_sync(0xffffffffu, mt, d)); ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, d));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax(&out4[0], mn); atomicMax(&out4[1], mm); atomicMax(&out4[2], mt); atomicMax(&out4[3], ml); }
+}
+
+}  // namespace ptgpu
+
+using namespace ptgpu;
+
+struct pt_batch {
+  int64_t B = 0;
+  bool owns_input = false;
+  int64_t *d_hnode_off = nullptr, *d_harc_off = nullptr, *d_gnode_off = nullptr;
+  int32_t *d_succ_off = nullptr, *d_succ_adj = nullptr, *d_hlabel = nullptr, *d_tparent = nullptr, *d_tlabel = nullptr;
+  int32_t maxN = 0, maxM = 0, maxNT = 0, maxL = 0;
+  // results + scratch
+  uint32_t* d_bits = nullptr; uint8_t* d_status = nullptr; uint8_t* d_branched = nullptr;
+  int32_t* d_ticket = nullptr;  // [0] ticket, [1] pool count A, [2] pool count B
+  unsigned long long* d_counters = nullptr;
+  // pools (ping-pong)
+  int pool_cap = 0;
+  int32_t* d_pool[2] = {nullptr, nullptr};
+  int64_t last_launches = 0;
+  int64_t h2d_bytes = 0;
+  static constexpr int kMaxTimedRounds = 16;
+  cudaEvent_t ev[2 * kMaxTimedRounds] = {};
+  int timed_rounds = 0;
+};
+
+static void batch_release(pt_batch* b) {
+  if (!b) return;
+  if (b->owns_input) {
+    cudaFree(b->d_hnode_off); cudaFree(b->d_harc_off); cudaFree(b->d_gnode_off);
+    cudaFree(b->d_succ_off); cudaFree(b->d_succ_adj); cudaFree(b->d_hlabel); cudaFree(b->d_tparent); cudaFree(b->d_tlabel);
+  }
+  cudaFree(b->d_bits); cudaFree(b->d_status); cudaFree(b->d_branched); cudaFree(b->d_ticket); cudaFree(b->d_counters);
+  cudaFree(b->d_pool[0]); cudaFree(b->d_pool[1]);
+  for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
+  delete b;
+}
+
+template <class T>
+static int upload(T** dst, const T* src, int64_t count, cudaStream_t s, int64_t* bytes) {
+  const size_t nb = (size_t)std::max<int64_t>(count, 1) * sizeof(T);
+  PT_CUDA(cudaMalloc((void**)dst, nb));
+  if (count > 0) { PT_CUDA(cudaMemcpyAsync(*dst, src, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, s)); *bytes += (int64_t)count * (int64_t)sizeof(T); }
+  return PT_OK;
+}
+
+extern "C" {
+
+int pt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int pt_set_device(int device) {
+  if (int rc = require_device()) return rc;
+  PT_CUDA(cudaSetDevice(device));
+  return PT_OK;
+}
+
+int pt_get_limits(pt_limits* out) {
+  if (!out) return set_error(PT_ERR_INVALID, "pt_get_limits: null argument");
+  // the on-chip solver keeps ids in int16 and the whole instance in the 227 KB of one CTA's shared memory
+  out->max_host_nodes = 30000; out->max_host_arcs = 30000; out->max_guest_nodes = 30000; out->max_labels = 30000;
+  return PT_OK;
+}
+
+int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
+  if (!out || !d) return set_error(PT_ERR_INVALID, "pt_batch_create: null argument");
+  *out = nullptr;
+  if (d->num_instances < 0 || d->num_instances > (int64_t)INT32_MAX - 64) return set_error(PT_ERR_INVALID, "pt_batch_create: bad num_instances");
+  if (!d->host_node_off || !d->host_arc_off || !d->guest_node_off || !d->host_succ_off || !d->host_label || !d->guest_parent || !d->guest_label ||
+      (!d->host_succ_adj && d->num_instances > 0))
+    return set_error(PT_ERR_INVALID, "pt_batch_create: a required array is null");
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  pt_batch* b = new (std::nothrow) pt_batch();
+  if (!b) return set_error(PT_ERR_NOMEM, "out of host memory");
+  const int64_t B = b->B = d->num_instances;
+  int rc = PT_OK;
+  auto fail = [&](int code) { batch_release(b); return code; };
+  b->maxN = d->max_host_nodes; b->maxM = d->max_host_arcs; b->maxNT = d->max_guest_nodes; b->maxL = d->max_labels;
+  const bool need_max = !(b->maxN > 0 && b->maxNT > 0 && b->maxL > 0) && B > 0;
+  if (d->mem == PT_MEM_HOST) {
+    // structural sanity of the offset tables before trusting them for the copy sizes
+    for (int64_t i = 0; i < B; ++i)
+      if (d->host_node_off[i + 1] < d->host_node_off[i] || d->host_arc_off[i + 1] < d->host_arc_off[i] || d->guest_node_off[i + 1] < d->guest_node_off[i])
+        return fail(set_error(PT_ERR_INVALID, "pt_batch_create: offset tables must be non-decreasing (instance %lld)", (long long)i));
+    if (d->host_node_off[0] != 0 || d->host_arc_off[0] != 0 || d->guest_node_off[0] != 0) return fail(set_error(PT_ERR_INVALID, "pt_batch_create: offset tables must start at 0"));
+    const int64_t NH = d->host_node_off[B], MH = d->host_arc_off[B], NG = d->guest_node_off[B];
+    if (need_max) {
+      for (int64_t i = 0; i < B; ++i) {
+        b->maxN = std::max<int32_t>(b->maxN, (int32_t)std::min<int64_t>(d->host_node_off[i + 1] - d->host_node_off[i], INT32_MAX));
+        b->maxM = std::max<int32_t>(b->maxM, (int32_t)std::min<int64_t>(d->host_arc_off[i + 1] - d->host_arc_off[i], INT32_MAX));
+        b->maxNT = std::max<int32_t>(b->maxNT, (int32_t)std::min<int64_t>(d->guest_node_off[i + 1] - d->guest_node_off[i], INT32_MAX));
+      }
+      int32_t ml = 0;
+      for (int64_t i = 0; i < NH; ++i) ml = std::max(ml, d->host_label[i] + 1);
+      for (int64_t i = 0; i < NG; ++i) ml = std::max(ml, d->guest_label[i] + 1);
+      b->maxL = std::max(b->maxL, ml);
+    }
+    b->owns_input = true;
+    if ((rc = upload(&b->d_hnode_off, d->host_node_off, B + 1, s, &b->h2d_bytes)) || (rc = upload(&b->d_harc_off, d->host_arc_off, B + 1, s, &b->h2d_bytes)) ||
+        (rc = upload(&b->d_gnode_off, d->guest_node_off, B + 1, s, &b->h2d_bytes)) || (rc = upload(&b->d_succ_off, d->host_succ_off, NH + B, s, &b->h2d_bytes)) ||
+        (rc = upload(&b->d_succ_adj, d->host_succ_adj, MH, s, &b->h2d_bytes)) || (rc = upload(&b->d_hlabel, d->host_label, NH, s, &b->h2d_bytes)) ||
+        (rc = upload(&b->d_tparent, d->guest_parent, NG, s, &b->h2d_bytes)) || (rc = upload(&b->d_tlabel, d->guest_label, NG, s, &b->h2d_bytes)))
+      return fail(rc);
+  } else {
+    b->d_hnode_off = (int64_t*)d->host_node_off; b->d_harc_off = (int64_t*)d->host_arc_off; b->d_gnode_off = (int64_t*)d->guest_node_off;
+    b->d_succ_off = (int32_t*)d->host_succ_off; b->d_succ_adj = (int32_t*)d->host_succ_adj; b->d_hlabel = (int32_t*)d->host_label;
+    b->d_tparent = (int32_t*)d->guest_parent; b->d_tlabel = (int32_t*)d->guest_label;
+    if (need_max) {
+      int32_t* d4 = nullptr; int32_t h4[4] = {0, 0, 0, 0};
+      if (cudaMalloc((void**)&d4, 16) != cudaSuccess) return fail(set_error(PT_ERR_NOMEM, "cudaMalloc failed"));
+      cudaMemsetAsync(d4, 0, 16, s);
+      tc_maxima_kernel<<<296, 256, 0, s>>>(B, b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_hlabel, b->d_tlabel, d4);
+      cudaError_t e = cudaMemcpyAsync(h4, d4, 16, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      cudaFree(d4);
+      if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "maxima pass failed: %s", cudaGetErrorString(e)));
+      b->maxN = std::max(b->maxN, h4[0]); b->maxM = std::max(b->maxM, h4[1]); b->maxNT = std::max(b->maxNT, h4[2]); b->maxL = std::max(b->maxL, h4[3]);
+    }
+  }
+  if (b->maxM <= 0) b->maxM = std::max(1, 2 * b->maxN);
+  b->maxN = std::max(b->maxN, 1); b->maxNT = std::max(b->maxNT, 1); b->maxL = std::max(b->maxL, 1);
+  const size_t words = (size_t)((B + 31) / 32) + 1;
+  if (cudaMalloc((void**)&b->d_bits, words * 4) != cudaSuccess || cudaMalloc((void**)&b->d_status, (size_t)B + 1) != cudaSuccess ||
+      cudaMalloc((void**)&b->d_branched, (size_t)B + 1) != cudaSuccess || cudaMalloc((void**)&b->d_ticket, 64) != cudaSuccess ||
+      cudaMalloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long)) != cudaSuccess)
+    return fail(set_error(PT_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
+  *out = b;
+  return PT_OK;
+}
+
+int64_t pt_batch_last_launches(const pt_batch* b) { return b ? b->last_launches : 0; }
+int64_t pt_batch_h2d_bytes(const pt_batch* b) { return b ? b->h2d_bytes : 0; }
+int pt_batch_round_ms(const pt_batch* b, int round, float* ms) {
+  if (!b || !ms || round < 0 || round >= b->timed_rounds) return set_error(PT_ERR_INVALID, "pt_batch_round_ms: round %d did not run (or was not timed)", round);
+  PT_CUDA(cudaEventElapsedTime(ms, b->ev[2 * round], b->ev[2 * round + 1]));
+  return PT_OK;
+}
+
+int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, uint8_t* status, pt_mem out_mem, pt_counters* counters, void* stream) {
+  if (!b || !result_bits) return set_error(PT_ERR_INVALID, "pt_batch_contain: null argument");
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  using I = int16_t;
+  const int64_t B = b->B;
+  const size_t words = (size_t)((B + 31) / 32);
+  b->last_launches = 0; b->timed_rounds = 0;
+  uint32_t* bits = out_mem == PT_MEM_DEVICE ? result_bits : b->d_bits;
+  uint8_t* stat = (out_mem == PT_MEM_DEVICE && status) ? status : b->d_status;
+  PT_CUDA(cudaMemsetAsync(bits, 0, words * 4, s));
+  PT_CUDA(cudaMemsetAsync(stat, 0, (size_t)B, s));
+  PT_CUDA(cudaMemsetAsync(b->d_branched, 0, (size_t)B, s));
+  PT_CUDA(cudaMemsetAsync(b->d_counters, 0, CNT_N * sizeof(unsigned long long), s));
+  PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 64, s));
+  uint64_t rounds = 0;
+  const bool too_large = b->maxN > 30000 || b->maxM > 30000 || b->maxNT > 30000 || b->maxL > 30000;
+  const size_t warp_bytes = TcWork<I>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL);
+  if (B > 0 && (too_large || warp_bytes > (size_t)dp.smem_optin)) {
+    // whole batch exceeds the on-chip solver: flag every instance (a global-memory executor is future work)
+    PT_CUDA(cudaMemsetAsync(stat, PT_INST_TOO_LARGE, (size_t)B, s));
+  } else if (B > 0) {
+    // occupancy: as many warps per SM as shared memory allows, in CTAs of up to 8 warps
+    int warps_per_sm = (int)std::min<size_t>(48, (size_t)dp.smem_optin / warp_bytes);
+    int wpc = std::min(8, warps_per_sm);
+    int ctas_per_sm = std::max(1, warps_per_sm / wpc);
+    while (wpc > 1 && (size_t)ctas_per_sm * ((size_t)wpc * warp_bytes + 1024) > (size_t)228 * 1024) --ctas_per_sm;
+    const size_t smem = (size_t)wpc * warp_bytes;
+    PT_CUDA(cudaFuncSetAttribute(tc_reduce_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // pool
+    int want = opt && opt->pool_slots > 0 ? opt->pool_slots : (int)std::min<int64_t>(std::max<int64_t>(8192, B), 1 << 22);
+    const int sN1 = b->maxN + 1, sM = std::max(1, (int)b->maxM), sN = b->maxN, sNT = b->maxNT;
+    const size_t slot_elems = (size_t)sN1 + sM + sN + 2 * (size_t)sNT + 4 + 1;
+    if (b->pool_cap < want) {
+      cudaFree(b->d_pool[0]); cudaFree(b->d_pool[1]); b->d_pool[0] = b->d_pool[1] = nullptr; b->pool_cap = 0;
+      for (int k = 0; k < 2; ++k) PT_CUDA(cudaMalloc((void**)&b->d_pool[k], slot_elems * (size_t)want * 4));
+      b->pool_cap = want;
+    }
+    const int cap = b->pool_cap;
+    auto sink_of = [&](int k) {
+      TcSink t; int32_t* p = b->d_pool[k];
+      t.succ_off = p; p += (size_t)sN1 * cap; t.succ_adj = p; p += (size_t)sM * cap; t.hlabel = p; p += (size_t)sN * cap;
+      t.tparent = p; p += (size_t)sNT * cap; t.tlabel = p; p += (size_t)sNT * cap; t.dims = p; p += (size_t)4 * cap; t.origin = p;
+      t.count = b->d_ticket + 1 + k; t.capacity = cap; t.sN1 = sN1; t.sM = sM; t.sN = sN; t.sNT = sNT;
+      return t;
+    };
+    const int max_rounds = opt && opt->max_rounds > 0 ? opt->max_rounds : 64;
+    TcSource src{};
+    src.count = B; src.is_pool = 0; src.hnode_off = b->d_hnode_off; src.harc_off = b->d_harc_off; src.gnode_off = b->d_gnode_off;
+    src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel;
+    int64_t items = B;
+    for (int round = 0; round < max_rounds && items > 0; ++round) {
+      const int k = round & 1;
+      TcSink sink = sink_of(k);
+      const int64_t warps_needed = items;
+      int grid = (int)std::min<int64_t>((int64_t)dp.sms * ctas_per_sm, (warps_needed + wpc - 1) / wpc);
+      grid = std::max(grid, 1);
+      const bool timed = round < pt_batch::kMaxTimedRounds;
+      if (timed) {
+        for (int j = 0; j < 2; ++j) if (!b->ev[2 * round + j]) PT_CUDA(cudaEventCreate(&b->ev[2 * round + j]));
+        PT_CUDA(cudaEventRecord(b->ev[2 * round], s));
+      }
+      tc_reduce_kernel<I><<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched,
+                                                       b->d_ticket, b->d_counters);
+      PT_CUDA(cudaGetLastError());
+      if (timed) { PT_CUDA(cudaEventRecord(b->ev[2 * round + 1], s)); b->timed_rounds = round + 1; }
+      ++b->last_launches; ++rounds;
+      int32_t h[4];
+      PT_CUDA(cudaMemcpyAsync(h, b->d_ticket, 16, cudaMemcpyDeviceToHost, s));
+      PT_CUDA(cudaStreamSynchronize(s));
+      items = std::min<int64_t>(h[1 + k], cap);
+      if (items <= 0) break;
+      // next round reads the pool just written; reset the ticket and the other pool's counter
+      TcSink just = sink;
+      src = TcSource{};
+      src.is_pool = 1; src.count_ptr = just.count; src.capacity = cap; src.succ_off = just.succ_off; src.succ_adj = just.succ_adj; src.hlabel = just.hlabel;
+      src.tparent = just.tparent; src.tlabel = just.tlabel; src.dims = just.dims; src.origin = just.origin; src.sN1 = sN1; src.sM = sM; src.sN = sN; src.sNT = sNT;
+      PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 4, s));
+      PT_CUDA(cudaMemsetAsync(b->d_ticket + 1 + (k ^ 1), 0, 4, s));
+    }
+  }
+  if (out_mem == PT_MEM_HOST) {
+    PT_CUDA(cudaMemcpyAsync(result_bits, bits, words * 4, cudaMemcpyDeviceToHost, s));
+    if (status) PT_CUDA(cudaMemcpyAsync(status, stat, (size_t)B, cudaMemcpyDeviceToHost, s));
+  }
+  if (counters) {
+    unsigned long long h[CNT_N];
+    std::vector<uint8_t> hb((size_t)B + 1), hs((size_t)B + 1);
+    PT_CUDA(cudaMemcpyAsync(h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaMemcpyAsync(hb.data(), b->d_branched, (size_t)B, cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaMemcpyAsync(hs.data(), stat, (size_t)B, cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaStreamSynchronize(s));
+    memset(counters, 0, sizeof(*counters));
+    uint64_t nbr = 0, nerr = 0;
+    for (int64_t i = 0; i < B; ++i) { nbr += hb[(size_t)i] != 0; nerr += hs[(size_t)i] != 0; }
+    counters->instances = (uint64_t)B; counters->displayed = h[CNT_DISPLAYED]; counters->errors = nerr;
+    counters->not_displayed = (uint64_t)B - h[CNT_DISPLAYED] - nerr; counters->branched = nbr; counters->resolved_by_rules = (uint64_t)B - nbr - nerr;
+    counters->work_items = h[CNT_ITEMS]; counters->rounds = rounds; counters->cherry_reductions = h[CNT_CHERRIES];
+    counters->reticulated_cherries = h[CNT_RET]; counters->arcs_deleted = h[CNT_ARCS]; counters->rule_passes = h[CNT_PASSES];
+  } else if (out_mem == PT_MEM_HOST) {
+    PT_CUDA(cudaStreamSynchronize(s));
+  }
+  return PT_OK;
+}
+
+int pt_batch_free(pt_batch* b) { batch_release(b); return PT_OK; }
+
+}  // extern "C"

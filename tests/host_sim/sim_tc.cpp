@@ -1,0 +1,114 @@
+// tests/host_sim/sim_tc.cpp -- TEST INFRASTRUCTURE ONLY.
+// Single-threaded SIMULATOR of the CUDA reducer: instantiates csrc/tc_core.cuh (the very code the kernel runs)
+// with an executor whose parallel-for runs sequentially in a permuted order.  It exists so that the rule logic
+// can be checked against the oracle on a machine without a GPU and so that order dependence between "parallel"
+// iterations shows up as a verdict that changes with the permutation seed.  It is not linked into libptgpu.so
+// and nothing in phylo_tools_b200/ calls it.
+//
+//   sim_tc gen <count> <leaves> <retis> <seed> <kind> <perm>   -> one char per instance (1 / 0 / E) on stdout,
+//                                                               a JSON line of statistics on stderr
+//   sim_tc file <path> <perm>                                  (path: pairs of Newick lines)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+#include "../../include/pt_gpu.h"
+#include "../../phylo_tools_b200/csrc/tc_core.cuh"
+#include "../../phylo_tools_b200/include/pt/packer.hpp"
+
+using namespace ptgpu;
+
+struct HostEx {
+  int perm;  // 0 identity, 1 reverse, >=2 affine permutation seeded by perm
+  int tid() const { return 0; }
+  int nth() const { return 1; }
+  void sync() const {}
+  static int gcd(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+  int map(int i, int n) const {
+    if (perm == 0 || n <= 1) return i;
+    if (perm == 1) return n - 1 - i;
+    int a = (int)((unsigned)perm * 2654435761u % (unsigned)n); if (a == 0) a = 1;
+    while (gcd(a, n) != 1) ++a;
+    const int b = (int)((unsigned)perm * 40503u % (unsigned)n);
+    return (int)(((long long)a * i + b) % n);
+  }
+  template <class T> T atomic_add(T* p, T v) const { T o = *p; *p = (T)(o + v); return o; }
+  template <class T> T atomic_min(T* p, T v) const { T o = *p; if (v < o) *p = v; return o; }
+  template <class T> T atomic_max(T* p, T v) const { T o = *p; if (v > o) *p = v; return o; }
+  template <class T> T atomic_or(T* p, T v) const { T o = *p; *p = (T)(o | v); return o; }
+  template <class T> T atomic_cas(T* p, T c, T v) const { T o = *p; if (o == c) *p = v; return o; }
+  template <class T> int atomic_cas_idx(T* p, int c, int v) const { int o = *p; if (o == c) *p = (T)v; return o; }
+  template <class T> void exclusive_scan(const int32_t* in, T* out, int n) const { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (T)acc; acc += in[i]; } out[n] = (T)acc; }
+};
+
+struct Item { std::vector<int32_t> succ_off, succ_adj, hlabel, tparent, tlabel; int n, m, nt; };
+
+struct Stats { long items = 0, branched = 0, cherries = 0, ret = 0, arcs = 0, passes = 0, max_items = 0, rules_only = 0; };
+
+static int solve_instance(const Item& root, int capN, int capM, int capNT, int capL, int perm, Stats& S, int* status) {
+  using I = int16_t;
+  std::vector<char> mem(TcWork<I>::bytes(capN, capM, capNT, capL) + 64);
+  std::vector<Item> stack{root};
+  bool first = true; long items = 0; int verdict = 0; *status = 0;
+  while (!stack.empty()) {
+    Item it = std::move(stack.back()); stack.pop_back();
+    ++items;
+    HostEx ex{perm};
+    TcWork<I> w; w.carve(mem.data(), capN, capM, capNT, capL);
+    TcSolver<HostEx, I> sv(ex, w);
+    TcInst in{it.n, it.m, it.nt, it.succ_off.data(), it.succ_adj.data(), it.hlabel.data(), it.tparent.data(), it.tlabel.data()};
+    int st = 0, x = -1;
+    const int code = sv.solve(in, !first, &st, &x);
+    first = false;
+    S.cherries += sv.st.cherries; S.ret += sv.st.retcherries; S.arcs += sv.st.arcs_deleted; S.passes += sv.st.passes;
+    if (code == TC_ERROR) { *status = st; verdict = -1; break; }
+    if (code == TC_DISPLAYED) { verdict = 1; break; }
+    if (code == TC_BRANCH) {
+      const int d = sv.indeg(x);
+      std::vector<int> arcs; for (int k = 0; k < d; ++k) arcs.push_back(sv.in_arc(x, k));
+      for (int k = 0; k < d; ++k) {
+        Item ch; ch.succ_off.resize(sv.n + 1); ch.succ_adj.resize(sv.m + 1); ch.hlabel.resize(sv.n + 1); ch.tparent.resize(sv.nt + 1); ch.tlabel.resize(sv.nt + 1);
+        int32_t dims[4];
+        TcEmit out{ch.succ_off.data(), ch.succ_adj.data(), ch.hlabel.data(), ch.tparent.data(), ch.tlabel.data(), dims};
+        if (k > 0) sv.csr();  // emit_child clobbers ioff
+        sv.emit_child(x, arcs[k], out);
+        ch.n = dims[0]; ch.m = dims[1]; ch.nt = dims[2];
+        stack.push_back(std::move(ch));
+      }
+    }
+  }
+  S.items += items; if (items > 1) S.branched++; else S.rules_only++;
+  if (items > S.max_items) S.max_items = items;
+  return verdict;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 1;
+  PT::BatchPacker P; int perm = 0;
+  if (!strcmp(argv[1], "gen") && argc >= 8) {
+    const long count = atol(argv[2]); const int l = atoi(argv[3]), r = atoi(argv[4]); const uint64_t seed = strtoull(argv[5], 0, 0); const int kind = atoi(argv[6]); perm = atoi(argv[7]);
+    for (long i = 0; i < count; ++i) P.add_generated(l, r, seed + (uint64_t)i, kind);
+  } else if (!strcmp(argv[1], "file") && argc >= 4) {
+    std::ifstream in(argv[2]); std::string a, b; perm = atoi(argv[3]);
+    while (std::getline(in, a) && std::getline(in, b)) P.add_newick(a, b);
+  } else return 1;
+  Stats S; std::string out;
+  for (size_t i = 0; i < P.size(); ++i) {
+    Item it; const int64_t hb = P.host_node_off[i], ab = P.host_arc_off[i], gb = P.guest_node_off[i];
+    it.n = (int)(P.host_node_off[i + 1] - hb); it.m = (int)(P.host_arc_off[i + 1] - ab); it.nt = (int)(P.guest_node_off[i + 1] - gb);
+    it.succ_off.assign(P.host_succ_off.begin() + hb + (int64_t)i, P.host_succ_off.begin() + hb + (int64_t)i + it.n + 1);
+    it.succ_adj.assign(P.host_succ_adj.begin() + ab, P.host_succ_adj.begin() + ab + it.m);
+    it.hlabel.assign(P.host_label.begin() + hb, P.host_label.begin() + hb + it.n);
+    it.tparent.assign(P.guest_parent.begin() + gb, P.guest_parent.begin() + gb + it.nt);
+    it.tlabel.assign(P.guest_label.begin() + gb, P.guest_label.begin() + gb + it.nt);
+    int st = 0;
+    const int v = solve_instance(it, P.max_host_nodes, P.max_host_arcs, P.max_guest_nodes, P.max_labels > 0 ? P.max_labels : 1, perm, S, &st);
+    out.push_back(v < 0 ? (char)('A' + st) : (char)('0' + v));
+  }
+  printf("%s\n", out.c_str());
+  fprintf(stderr, "{\"instances\": %zu, \"items\": %ld, \"rules_only\": %ld, \"branched\": %ld, \"max_items\": %ld, \"cherries\": %ld, \"ret_cherries\": %ld, \"arcs_deleted\": %ld, \"passes\": %ld}\n",
+          P.size(), S.items, S.rules_only, S.branched, S.max_items, S.cherries, S.ret, S.arcs, S.passes);
+  return 0;
+}

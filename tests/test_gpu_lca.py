@@ -1,0 +1,178 @@
+"""Parity of the CUDA LCA / RMQ path (through the C-ABI) with the oracle and with the reference's own answers."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _shape(rng, n, kind):
+    par = np.full(n, -1, dtype=np.int64)
+    idx = np.arange(1, n)
+    if kind == "random":
+        par[1:] = (rng.random(n - 1) * idx).astype(np.int64)
+    elif kind == "path":
+        par[1:] = idx - 1
+    elif kind == "star":
+        par[1:] = 0
+    elif kind == "cat":
+        par[1:] = np.where(idx % 2 == 1, idx - 1, np.maximum(idx - 2, 0))
+    elif kind == "bushy":  # ~8 children per node
+        par[1:] = (idx - 1) // 8
+    perm = rng.permutation(n)
+    out = np.full(n, -1, dtype=np.int32)
+    out[perm] = np.where(par >= 0, perm[np.maximum(par, 0)], -1)
+    return out
+
+
+def test_reference_answers(pt, gold_lca):
+    k = gold_lca["known"]  # rmq/lca.cpp:46-49
+    L = pt.Lca(np.array(k["parent"], dtype=np.int32))
+    assert L.query(k["u"], k["v"]).tolist() == k["lca"]
+    L.free()
+    for t in gold_lca["trees"]:
+        L = pt.Lca(np.array(t["parent"], dtype=np.int32))
+        assert L.query(t["u"], t["v"]).tolist() == t["lca"]
+        L.free()
+
+
+@pytest.mark.parametrize("kind", ["random", "path", "star", "cat", "bushy"])
+def test_shapes_and_sizes(pt, oracle, kind):
+    rng = np.random.default_rng(11)
+    sizes = [1, 2, 3, 31, 32, 33, 64, 65, 1000, 4097, 70000]
+    if kind in ("random", "bushy", "star"):
+        sizes.append(1 << 20)
+    for n in sizes:
+        if kind == "path" and n > 5000:
+            continue  # one wavefront step per level: deep trees are correct but slow
+        par = _shape(rng, n, kind)
+        L = pt.Lca(par)
+        q = 20000
+        u = rng.integers(0, n, q).astype(np.int32)
+        v = rng.integers(0, n, q).astype(np.int32)
+        # half of the queries are "near" pairs so that the in-block path is exercised
+        v[::2] = np.clip(u[::2] + rng.integers(-3, 4, len(u[::2])), 0, n - 1)
+        got = L.query(u, v)
+        exp = oracle.lca_euler(par, u, v)
+        assert (got == exp).all(), (kind, n, int((got != exp).sum()))
+        info = L.info()
+        assert info["num_nodes"] == n
+        d, p = L.node_info()
+        assert sorted(p.tolist()) == list(range(n))  # preorder positions are a permutation
+        root = int(np.where(par < 0)[0][0])
+        assert d[root] == 0 and p[root] == 0
+        nz = par >= 0
+        assert (d[nz] == d[par[nz]] + 1).all() and (p[nz] > p[par[nz]]).all()
+        L.free()
+
+
+def test_same_block_neighbours(pt, oracle):
+    """all pairs inside a few blocks of a small tree: every (l, r) offset combination of the in-block path"""
+    rng = np.random.default_rng(5)
+    par = _shape(rng, 96, "random")
+    L = pt.Lca(par)
+    u, v = np.meshgrid(np.arange(96, dtype=np.int32), np.arange(96, dtype=np.int32))
+    u, v = u.ravel(), v.ravel()
+    assert (L.query(u, v) == oracle.lca_naive(par, u, v)).all()
+    L.free()
+
+
+def test_device_memory_path(pt, oracle):
+    import torch
+    par = pt.random_tree(50000, 3)
+    dpar = torch.from_numpy(par).cuda()
+    L = pt.Lca(dpar)
+    rng = np.random.default_rng(1)
+    u = rng.integers(0, len(par), 100000).astype(np.int32)
+    v = rng.integers(0, len(par), 100000).astype(np.int32)
+    du, dv = torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda()
+    out = torch.empty_like(du)
+    L.query(du, dv, out=out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (out.cpu().numpy() == oracle.lca_euler(par, u, v)).all()
+    # out-of-range node ids answer -1 instead of reading out of bounds
+    bad = torch.tensor([-1, len(par), 5], dtype=torch.int32).cuda()
+    ok = torch.tensor([0, 0, 5], dtype=torch.int32).cuda()
+    o = torch.empty_like(bad)
+    L.query(bad, ok, out=o)
+    torch.cuda.synchronize()
+    assert o.cpu().tolist() == [-1, -1, 5]
+    L.free()
+
+
+def test_invalid_trees(pt):
+    with pytest.raises(pt.PtError):
+        pt.Lca(np.array([-1, -1, 0], dtype=np.int32))        # two roots (storage_adj_common.hpp:103-109)
+    with pytest.raises(pt.PtError):
+        pt.Lca(np.array([-1, 2, 1], dtype=np.int32))         # cycle next to the root
+    with pytest.raises(pt.PtError):
+        pt.Lca(np.array([1, 0, 0], dtype=np.int32))          # no root
+    with pytest.raises(pt.PtError):
+        pt.Lca(np.array([-1, 7], dtype=np.int32))            # parent out of range
+
+
+def test_full_size_properties(pt, oracle):
+    """BASELINE config 3 size: 10^7 leaves.  The oracle is too slow for all queries at this size, so: a sample against the
+    parent-walk oracle plus size-independent properties (idempotence, symmetry, ancestor closure)."""
+    import torch
+    leaves = 10_000_000
+    par = pt.random_tree(leaves, 0xB200)
+    n = len(par)
+    dpar = torch.from_numpy(par).cuda()
+    L = pt.Lca(dpar)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q = 4_000_000
+    u = torch.randint(0, n, (q,), generator=g, device="cuda", dtype=torch.int32)
+    v = torch.randint(0, n, (q,), generator=g, device="cuda", dtype=torch.int32)
+    a = torch.empty_like(u)
+    L.query(u, v, out=a)
+    b = torch.empty_like(u)
+    L.query(v, u, out=b)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)                                   # symmetry
+    c = torch.empty_like(u)
+    L.query(a, u, out=c)
+    torch.cuda.synchronize()
+    assert torch.equal(c, a)                                   # lca(lca(u,v), u) == lca(u,v)
+    L.query(u, u, out=c)
+    torch.cuda.synchronize()
+    assert torch.equal(c, u)                                   # lca(u,u) == u
+    pu = dpar[u.long()]
+    has = pu >= 0
+    L.query(u[has], pu[has], out=c[: int(has.sum())])
+    torch.cuda.synchronize()
+    assert torch.equal(c[: int(has.sum())], pu[has])           # lca(u, parent(u)) == parent(u)
+    k = 200_000
+    uu, vv = u[:k].cpu().numpy(), v[:k].cpu().numpy()
+    assert (a[:k].cpu().numpy() == oracle.lca_naive(par, uu, vv)).all()
+    assert L.info()["num_levels"] < 200
+    L.free()
+
+
+def test_rmq_reference_answers(pt, oracle, gold_lca):
+    for g in gold_lca["rmq"]:
+        R = pt.Rmq(g["values"])
+        got = R.query(g["l"], g["r"])
+        vals = np.asarray(g["values"])
+        assert (vals[got] == np.asarray(g["value"])).all()
+        if g["mode"] == "rmq":
+            assert (got == np.asarray(g["index"])).all()     # rightmost minimum, sparse_rmq.hpp:63,89
+        R.free()
+
+
+def test_rmq_known_answers_and_random(pt, oracle):
+    from test_oracle import PM_RMQ_TEST_HPP, RMQ_TEST_HPP
+    for arr, checks in RMQ_TEST_HPP + PM_RMQ_TEST_HPP:
+        R = pt.Rmq(arr)
+        got = R.query([c[0] for c in checks], [c[1] for c in checks])
+        for (u, v, exp), idx in zip(checks, got):
+            assert arr[idx] == arr[exp]
+        R.free()
+    rng = np.random.default_rng(9)
+    for n in (1, 2, 33, 1000, 200000):
+        a = rng.integers(-50, 50, n).astype(np.int32)
+        R = pt.Rmq(a)
+        l = rng.integers(0, n, 5000)
+        r = np.minimum(n, l + 1 + rng.integers(0, max(1, n), 5000))
+        got = R.query(l, r)
+        assert (got == oracle.sparse_rmq(a, l, r)).all()
+        R.free()

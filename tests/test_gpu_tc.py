@@ -1,0 +1,177 @@
+"""Parity of the CUDA containment path (through the C-ABI) with the oracle: exhaustive-switching truth on small
+instances, the pinned reference outputs, error statuses, and size-independent properties at BASELINE config 2 size."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(pt, packer, **kw):
+    b = pt.Batch(packer.arrays())
+    try:
+        return b.contain(**kw)
+    finally:
+        b.free()
+
+
+def test_golden_instances(pt, gold_tc):
+    items = gold_tc["items"]
+    p = pt.Packer()
+    for it in items:
+        p.add_newick(it["host"], it["guest"])
+    v, s, c = _solve(pt, p)
+    assert (s == 0).all()
+    bad = [(i, it["tag"]) for i, it in enumerate(items) if int(v[i]) != it["truth"]]
+    assert not bad, bad[:5]
+    assert c["instances"] == len(items) and c["displayed"] == int(v.sum()) and c["errors"] == 0
+    # data/test.nw (BASELINE config 1): not displayed; the reference itself crashes here
+    assert items[0]["tag"] == "data/test.nw" and not v[0]
+    # agreement with the reference wherever it terminates correctly
+    wrong = set(gold_tc["summary"]["reference_wrong"])
+    for i, it in enumerate(items):
+        if it["reference"] in "01" and i not in wrong:
+            assert int(v[i]) == int(it["reference"])
+
+
+@pytest.mark.parametrize("l,r", [(5, 2), (8, 3), (11, 5), (15, 7), (20, 9)])
+def test_generated_vs_bruteforce(pt, oracle, l, r):
+    p = pt.Packer()
+    for kind in (0, 1, 2):
+        p.add_generated(120, l, r, 31337 + 17 * l + kind, kind)
+    v, s, c = _solve(pt, p)
+    assert (s == 0).all()
+    truth = np.array([oracle.tc_bruteforce_newick(*p.newick(i))[0] for i in range(len(p))])
+    assert (v.astype(int) == truth).all(), np.where(v.astype(int) != truth)[0][:10]
+    assert v[:120].all()  # kind 0 is displayed by construction
+
+
+def test_tree_in_tree_and_degenerate(pt, oracle):
+    pairs = [("((a,b),(c,d));", "((a,b),(c,d));"), ("((a,b),(c,d));", "((a,c),(b,d));"), ("(a,b);", "(b,a);"), ("(a,(b,c));", "((a,b),c);"),
+             ("(a,b,c);", "(a,b,c);"), ("(a,b,c);", "((a,b),c);"), ("((a,b),c,(d,e,f));", "((e,d,f),c,(b,a));"),
+             ("((a,b),(c,d));", "((a,b),(c,e));"),            # label only in the guest: not displayed (containment.hpp:1116)
+             ("((a,b),(c,(d,e)));", "((a,b),(c,d));"),         # label only in the host: leaf removed (containment.hpp:1117-1121)
+             ("((a)#H1,(#H1,b));", "(a,b);"),                  # <= 2 labels: displayed (containment.hpp:1061)
+             ("(((a,b))x,((c,d))y);", "(((a,b)),((d,c)));"),   # unary nodes on both sides are suppressed
+             ("((a,(b)#H1),(#H1,c));", "(a,(b,c));"), ("((a,(b)#H1),(#H1,c));", "((a,b),c);"), ("((a,(b)#H1),(#H1,c));", "((a,c),b);")]
+    p = pt.Packer()
+    for h, g in pairs:
+        p.add_newick(h, g)
+    v, s, _ = _solve(pt, p)
+    assert (s == 0).all()
+    truth = [oracle.tc_bruteforce_newick(h, g)[0] for h, g in pairs]
+    assert v.astype(int).tolist() == truth
+    assert truth == [1, 0, 1, 0, 1, 0, 1, 0, 1, 1, 1, 1, 1, 0]
+
+
+def test_error_statuses_do_not_poison_the_batch(pt):
+    p = pt.Packer()
+    p.add_generated(3, 8, 2, 5, 0)
+    a = p.arrays()
+    # instance 1: duplicate leaf label in the host (std::logic_error in label_matching.hpp:51-52)
+    hb = int(a["host_node_off"][1])
+    lab = a["host_label"][hb: hb + 19]
+    leaves = np.where(lab >= 0)[0]
+    a["host_label"][hb + leaves[0]] = lab[leaves[1]]
+    # instance 2: an arc that closes a cycle (root's first child points back at the root)
+    ab = int(a["host_arc_off"][2])
+    a["host_succ_adj"][ab + 5] = 0
+    b = pt.Batch(a)
+    v, s, c = b.contain()
+    b.free()
+    assert s.tolist()[0] == 0 and v[0]
+    assert s[1] == 1        # PT_INST_MULTILABEL
+    assert s[2] == 2        # PT_INST_BAD_GRAPH
+    assert c["errors"] == 2
+
+
+def test_pool_overflow_is_reported(pt, oracle):
+    p = pt.Packer()
+    p.add_generated(400, 16, 7, 777, 0)
+    b = pt.Batch(p.arrays())
+    v, s, c = b.contain()
+    assert (s == 0).all() and v.all() and c["branched"] > 4
+    v2, s2, c2 = b.contain(pool_slots=2)
+    b.free()
+    assert ((s2 == 0) | (s2 == 4)).all() and (s2 == 4).sum() >= 1   # PT_INST_POOL_OVERFLOW, never a wrong verdict
+    assert v2[s2 == 0].all()
+
+
+def test_config2_full_size(pt):
+    """BASELINE config 2: 10^5 gen networks l=100 r=20, each with a displayed tree -> all displayed; the HOST-input and
+    DEVICE-input paths agree bit for bit; verdicts are reproducible."""
+    import torch
+    B = 100_000
+    p = pt.Packer()
+    p.add_generated(B, 100, 20, 0xB200, 0)
+    a = p.arrays()
+    b = pt.Batch(a)
+    v, s, c = b.contain()
+    b.free()
+    assert (s == 0).all() and v.all()
+    assert c["displayed"] == B and c["work_items"] >= B and c["resolved_by_rules"] + c["branched"] == B
+    dev = {k: (torch.from_numpy(x).cuda() if isinstance(x, np.ndarray) else x) for k, x in a.items()}
+    bits = torch.zeros((B + 31) // 32, dtype=torch.int32, device="cuda")
+    stat = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    bd = pt.Batch(dev)
+    bd.contain(result_bits=bits, status=stat, want_counters=False)
+    torch.cuda.synchronize()
+    first = bits.clone()
+    bd.contain(result_bits=bits, status=stat, want_counters=False)
+    torch.cuda.synchronize()
+    bd.free()
+    assert torch.equal(first, bits) and int(stat.sum()) == 0
+    words = np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little")[:B]
+    assert words.all()
+
+
+def test_config2_negatives_against_pinned_truth(pt, gold_tc):
+    """l=100, r=20 instances with two guest labels swapped; truth from the exhaustive oracle (2^20 switchings each),
+    computed in the build container and pinned in tests/golden/tc_l100_r20.json"""
+    from conftest import load_golden
+    g = load_golden("tc_l100_r20.json")
+    p = pt.Packer()
+    p.add_generated(g["count"], 100, 20, g["seed"], g["kind"])
+    v, s, _ = _solve(pt, p)
+    assert (s == 0).all()
+    for i, t in zip(g["index"], g["truth"]):
+        assert int(v[i]) == t, i
+
+
+def test_enum_switchings_matches_oracle_counts(pt, oracle, gold_tc):
+    """the exhaustive enumerator: number of displaying switchings and first displaying index equal the oracle's"""
+    from oracle.newick import parse_newick
+    checked = 0
+    for it in gold_tc["items"]:
+        if not it["tag"].startswith("gen") and it["tag"] != "data/test.nw":
+            continue
+        if checked >= 120:
+            break
+        n, e, lab = parse_newick(it["host"])
+        nt, te, tlab = parse_newick(it["guest"])
+        if len(te) != nt - 1:
+            continue
+        names = {}
+        hl = np.full(n, -1, dtype=np.int32)
+        tl = np.full(nt, -1, dtype=np.int32)
+        for x, sname in lab.items():
+            hl[x] = names.setdefault(sname, len(names))
+        for x, sname in tlab.items():
+            tl[x] = names.setdefault(sname, len(names))
+        e = sorted(e)  # CSR order = arc order of the oracle
+        off = np.zeros(n + 1, dtype=np.int32)
+        for a, _ in e:
+            off[a + 1] += 1
+        off = np.cumsum(off).astype(np.int32)
+        adj = np.array([b for _, b in e], dtype=np.int32)
+        tp = np.full(nt, -1, dtype=np.int32)
+        for a, b in te:
+            tp[b] = a
+        exp_v, exp_n, exp_first = oracle.tc_bruteforce(e, n, hl, te, nt, tl, stop_at_first=False)
+        tot, nd, first = pt.enum_switchings(off, adj, hl, tp, tl)
+        assert nd == exp_n and (first if first is not None else 2**64 - 1) == exp_first, it["tag"]
+        # sharding the index range (what the multi-GPU path does) gives the same total
+        if tot >= 4:
+            parts = [pt.enum_switchings(off, adj, hl, tp, tl, begin=tot * k // 4, end=tot * (k + 1) // 4)[1] for k in range(4)]
+            assert sum(parts) == exp_n
+        checked += 1
+    assert checked >= 100

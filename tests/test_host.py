@@ -1,0 +1,126 @@
+"""Host-side logic and the C-ABI surface (no GPU): the product's C++ Newick reader against the reference reader's output,
+the packer, the generator, and that libptgpu.so exports every symbol include/pt_gpu.h declares."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_every_declared_symbol(pt):
+    hdr = open(os.path.join(ROOT, "include", "pt_gpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(pt_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 24
+    lib = C.CDLL(os.path.join(ROOT, "phylo_tools_b200", "libptgpu.so"))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert pt.lib().pt_abi_version() == 1
+
+
+def test_cpp_newick_reader_matches_reference(pt, gold_newick):
+    for it in gold_newick["items"]:
+        n, edges, labels = pt.parse_newick(it["newick"])
+        assert n == it["num_nodes"]
+        assert [list(e) for e in edges] == it["edges"]
+        assert {str(k): v for k, v in labels.items()} == it["labels"]
+
+
+def test_malformed_newick(pt):
+    for bad in ["((a,b),(c,d))", "(a,b)x#H;", "((a)#H1,(#H1,#H1));", "(a,b));"]:
+        with pytest.raises(pt.MalformedNewick):
+            pt.parse_newick(bad)
+    # like the reference, the reader stops once the root's subtree is complete: an unmatched '(' on the left is ignored
+    assert pt.parse_newick("((a,b),(c,d);") == (3, [(0, 1), (0, 2)], {1: "d", 2: "c"})
+
+
+def test_packer_layout_and_roundtrip(pt, oracle):
+    p = pt.Packer()
+    p.add_generated(5, 10, 3, 99, 0)
+    p.add_newick("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));")
+    p.add_newick("((a,b),(c,d));", "(((a)#H1,b),(#H1,c));")  # tree first, network second: the network becomes the host (tc.cpp:110-111)
+    a = p.arrays()
+    B = a["num_instances"]
+    assert B == 7
+    for i in range(B):
+        hb, he = a["host_node_off"][i], a["host_node_off"][i + 1]
+        n, m = he - hb, a["host_arc_off"][i + 1] - a["host_arc_off"][i]
+        off = a["host_succ_off"][hb + i: hb + i + n + 1]
+        assert off[0] == 0 and off[-1] == m and (np.diff(off) >= 0).all()
+        adj = a["host_succ_adj"][a["host_arc_off"][i]: a["host_arc_off"][i + 1]]
+        assert ((adj >= 0) & (adj < n)).all()
+        gb, ge = a["guest_node_off"][i], a["guest_node_off"][i + 1]
+        par = a["guest_parent"][gb:ge]
+        assert (par == -1).sum() == 1 and (par < ge - gb).all()
+        # pred arrays are the transpose of succ
+        poff = a["host_pred_off"][hb + i: hb + i + n + 1]
+        assert poff[-1] == m
+        # the Newick text rebuilt from the flat arrays describes the same instance: same oracle verdict as the arrays
+        h, g = p.newick(i)
+        tails = np.repeat(np.arange(n), np.diff(off))
+        edges = list(zip(tails.tolist(), adj.tolist()))
+        gedges = [(int(par[t]), t) for t in range(ge - gb) if par[t] >= 0]
+        v1 = oracle.tc_bruteforce(edges, n, a["host_label"][hb:he], gedges, ge - gb, a["guest_label"][gb:ge])[0]
+        v2 = oracle.tc_bruteforce_newick(h, g)[0]
+        assert v1 == v2
+    assert a["max_host_nodes"] == max(np.diff(a["host_node_off"]))
+    # instance 6: host must be the network (4 leaves a b c + ... ) although it came second
+    assert a["host_arc_off"][7] - a["host_arc_off"][6] == 7
+
+
+def test_generator_shapes(pt):
+    # utils/generator.hpp:19-23: n = 2r + 2l - 1, m = n - 1 + r; binary; positives are displayed by construction
+    p = pt.Packer()
+    p.add_generated(20, 100, 20, 0xB200, 0)
+    a = p.arrays()
+    assert (np.diff(a["host_node_off"]) == 239).all() and (np.diff(a["host_arc_off"]) == 258).all()
+    assert (np.diff(a["guest_node_off"]) == 199).all()
+    for i in range(20):
+        hb = a["host_node_off"][i]
+        off = a["host_succ_off"][hb + i: hb + i + 240]
+        deg = np.diff(off)
+        assert set(deg.tolist()) <= {0, 1, 2} and (deg == 0).sum() == 100 and (deg == 1).sum() == 20
+        lab = a["host_label"][hb:hb + 239]
+        assert sorted(lab[lab >= 0].tolist()) == list(range(100))
+    # same seed -> same batch
+    q = pt.Packer()
+    q.add_generated(20, 100, 20, 0xB200, 0)
+    b = q.arrays()
+    assert all((a[k] == b[k]).all() for k in ("host_succ_adj", "guest_parent", "guest_label"))
+    h, g = p.newick(0)
+    assert h.count("#H") == 40 and g.count(",") == 99
+
+
+def test_sequential_taxon_names(pt):
+    # utils/generator.hpp:31-46: a..z, ba, bb, ...
+    p = pt.Packer()
+    p.add_generated(1, 30, 0, 1, 0)
+    h, _ = p.newick(0)
+    names = set(re.findall(r"[a-z]+", h))
+    assert {"a", "z", "ba", "bd"} <= names and "aa" not in names
+
+
+def test_random_tree(pt):
+    par = pt.random_tree(1000, 7)
+    assert len(par) == 1999 and (par == -1).sum() == 1
+    deg = np.bincount(par[par >= 0], minlength=1999)
+    assert set(deg.tolist()) == {0, 2} and (deg[:1000] == 0).all()
+
+
+def test_no_cpu_fallback(pt):
+    """without a GPU every compute entry point must fail loudly with PT_ERR_NO_DEVICE"""
+    if pt.device_count() > 0:
+        pytest.skip("a GPU is present")
+    p = pt.Packer()
+    p.add_generated(2, 5, 1, 1, 0)
+    with pytest.raises(pt.PtError) as e:
+        pt.Batch(p.arrays())
+    assert e.value.code == -4
+    with pytest.raises(pt.PtError) as e:
+        pt.Lca(np.array([-1, 0, 0], dtype=np.int32))
+    assert e.value.code == -4
+    with pytest.raises(pt.PtError) as e:
+        pt.Rmq([3, 1, 2])
+    assert e.value.code == -4

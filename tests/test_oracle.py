@@ -1,0 +1,79 @@
+"""The oracle (oracle/pt_oracle.c, oracle/newick.py) against every golden vector the reference's own tests hold for
+the path and against outputs of the reference itself (tests/golden/*.json, made by oracle/make_golden.py)."""
+import numpy as np
+
+from oracle.newick import parse_newick
+
+# rmq/rmq_test.hpp:33-109 -- EXPECT_RMQ(u, v, expect) compares VALUES (input[ret] == input[expect])
+RMQ_TEST_HPP = [
+    ([1, 1, 1, 1, 1, 1], [(0, 3, 2), (0, 2, 1), (2, 6, 5), (3, 6, 5)]),
+    ([3, 1, 2, 1, 4, 5], [(0, 3, 1), (0, 2, 1), (2, 6, 3), (3, 6, 3)]),
+    ([3, 1, 1, 1, 4, 5], [(0, 3, 2)]),
+    ([10, 8, 9, 2, 4, 5, 1, 16, 4, 7], [(0, 3, 1), (0, 6, 3), (3, 8, 6), (0, 10, 6)]),
+]
+# rmq/pm_rmq_test.hpp:29-44
+PM_RMQ_TEST_HPP = [([1, 2, 1, 2, 1, 0], [(0, 3, 2), (0, 2, 0), (2, 6, 5), (3, 6, 5)])]
+
+
+def test_sparse_rmq_known_answers(oracle):
+    for arr, checks in RMQ_TEST_HPP + PM_RMQ_TEST_HPP:
+        got = oracle.sparse_rmq(arr, [c[0] for c in checks], [c[1] for c in checks])
+        for (u, v, exp), idx in zip(checks, got):
+            assert u <= idx < v
+            assert arr[idx] == arr[exp]
+
+
+def test_sparse_rmq_random_vs_min_element(oracle):
+    # rmq_test.hpp:115-143 (vector_test): random ints % 1000, windows shorter than 100, value must equal min_element
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 1000, 20000).astype(np.int32)
+    l = rng.integers(0, len(a) - 100, 3000)
+    r = l + np.maximum(1, rng.integers(0, 100, 3000))
+    got = oracle.sparse_rmq(a, l, r)
+    for x, y, i in zip(l, r, got):
+        assert a[i] == a[x:y].min()
+        assert i == x + (y - x - 1) - int(np.argmin(a[x:y][::-1]))  # sparse_rmq.hpp:63,89: ties -> right
+
+
+def test_sparse_rmq_matches_reference_indices(oracle, gold_lca):
+    for g in gold_lca["rmq"]:
+        got = oracle.sparse_rmq(g["values"], g["l"], g["r"])
+        vals = np.asarray(g["values"])
+        assert (vals[got] == np.asarray(g["value"])).all()
+        if g["mode"] == "rmq":  # sparse_rmq index tie-break is pinned; pm_rmq's is mixed
+            assert (got == np.asarray(g["index"])).all()
+
+
+def test_lca_known_answers(oracle, gold_lca):
+    k = gold_lca["known"]  # rmq/lca.cpp:46-49
+    assert oracle.lca_naive(k["parent"], k["u"], k["v"]).tolist() == k["lca"]
+    assert oracle.lca_euler(k["parent"], k["u"], k["v"]).tolist() == k["lca"]
+
+
+def test_lca_matches_reference(oracle, gold_lca):
+    for t in gold_lca["trees"]:
+        assert oracle.lca_naive(t["parent"], t["u"], t["v"]).tolist() == t["lca"]
+        assert oracle.lca_euler(t["parent"], t["u"], t["v"]).tolist() == t["lca"]
+
+
+def test_newick_restatement_matches_reference(gold_newick):
+    for it in gold_newick["items"]:
+        n, edges, labels = parse_newick(it["newick"])
+        assert n == it["num_nodes"]
+        assert [list(e) for e in edges] == it["edges"]
+        assert {str(k): v for k, v in labels.items()} == it["labels"]
+
+
+def test_tc_bruteforce_matches_stored_truth_and_reference(oracle, gold_tc):
+    """exhaustive switching is deterministic: it must reproduce the stored truth; wherever the reference terminates with a
+    verdict it must agree with it, except on the pinned reference false positives"""
+    wrong = set(gold_tc["summary"]["reference_wrong"])
+    for i, it in enumerate(gold_tc["items"]):
+        v, nd, _ = oracle.tc_bruteforce_newick(it["host"], it["guest"], stop_at_first=False)
+        assert v == it["truth"] and nd == it["n_displaying"], it["tag"]
+        if it["reference"] in "01":
+            if i in wrong:
+                assert it["reference"] == "1" and it["truth"] == 0  # the reference only errs towards "displayed"
+            else:
+                assert int(it["reference"]) == it["truth"], it["tag"]
+    assert gold_tc["items"][0]["tag"] == "data/test.nw" and gold_tc["items"][0]["truth"] == 0 and gold_tc["items"][0]["reference"] == "S"
