@@ -81,6 +81,17 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
+def _ref_json(stderr_text):
+    for line in reversed((stderr_text or "").strip().split("\n")):
+        line = line.strip()
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except Exception:
+                pass
+    return {}
+
+
 def reference_arm(args, rank, world):
     """the reference's CPU implementation of the path on the host cores (rank 0 only)"""
     if rank != 0:
@@ -115,22 +126,22 @@ def reference_arm(args, rank, world):
         ps = [subprocess.Popen([ref, "bench", fn, str(per)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True) for fn in files]
         outs = [q.communicate()[1] for q in ps]
         dt = time.perf_counter() - t0
-        disp = sum(json.loads(o.strip().split("\n")[-1])["displayed"] for o in outs)
-        return dt, disp
+        js = [_ref_json(o) for o in outs]
+        return dt, sum(j.get("displayed", 0) for j in js), sum(j.get("displayed", 0) + j.get("not_displayed", 0) for j in js)
     for _ in range(args.warmup):
         one_step()
-    times, disp = [], 0
+    times, disp, done = [], 0, 0
     for _ in range(args.steps):
-        dt, disp = one_step()
+        dt, disp, done = one_step()
         times.append(dt)
     for fn in files:
         os.unlink(fn)
     total = procs * per
     ms = 1000.0 * sum(times) / len(times)
-    val = total / (ms / 1000.0)
+    val = done / (ms / 1000.0)  # instances on which the reference terminated with a verdict
     res.update({"value": val, "ms_per_step": ms, "gpu_launches": 0,
                 "cpu_baseline": {"value": val, "unit": "instances/s", "cores": procs, "kind": "reference",
-                                 "sample": "%d instances per step (%d per core), all displayed=%s" % (total, per, disp == total)},
+                                 "sample": "%d instances per step (%d per core); reference gave a verdict on %d (%d displayed), crashed/threw on %d" % (total, per, done, disp, total - done)},
                 "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(res))
 
@@ -160,9 +171,12 @@ def cpu_baseline_leg(pt, sample_seconds=15.0):
     dt = time.perf_counter() - t0
     for fn in files:
         os.unlink(fn)
-    disp = sum(json.loads(o.strip().split("\n")[-1])["displayed"] for o in outs)
-    single = [json.loads(o.strip().split("\n")[-1])["inst_per_s"] for o in outs]
-    return {"value": cores * per / dt, "unit": "instances/s", "cores": cores, "kind": "reference",
+    js = [_ref_json(o) for o in outs]
+    disp = sum(j.get("displayed", 0) for j in js)
+    done = sum(j.get("displayed", 0) + j.get("not_displayed", 0) for j in js)
+    crashed = cores * per - done
+    single = [j.get("inst_per_s", 0.0) for j in js]
+    return {"value": done / dt, "reference_crashes_or_exceptions": crashed, "unit": "instances/s", "cores": cores, "kind": "reference",
             "sample": "first %d instances of the batch, %d per core, reference TreeInNetContainment::displayed() with std::cout silenced; %d/%d displayed; per-core rate %.1f inst/s"
                       % (cores * per, per, disp, cores * per, sum(single) / len(single))}
 

@@ -390,15 +390,18 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   if (counters) {
     unsigned long long h[CNT_N];
     std::vector<uint8_t> hb((size_t)B + 1), hs((size_t)B + 1);
+    std::vector<uint32_t> hw(words + 1);
+    PT_CUDA(cudaMemcpyAsync(hw.data(), bits, words * 4, cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaMemcpyAsync(h, b->d_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaMemcpyAsync(hb.data(), b->d_branched, (size_t)B, cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaMemcpyAsync(hs.data(), stat, (size_t)B, cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaStreamSynchronize(s));
     memset(counters, 0, sizeof(*counters));
     uint64_t nbr = 0, nerr = 0;
-    for (int64_t i = 0; i < B; ++i) { nbr += hb[(size_t)i] != 0; nerr += hs[(size_t)i] != 0; }
-    counters->instances = (uint64_t)B; counters->displayed = h[CNT_DISPLAYED]; counters->errors = nerr;
-    counters->not_displayed = (uint64_t)B - h[CNT_DISPLAYED] - nerr; counters->branched = nbr; counters->resolved_by_rules = (uint64_t)B - nbr - nerr;
+    uint64_t ndisp = 0;  // per ORIGINAL instance (several branch children of one instance may each report "displayed")
+    for (int64_t i = 0; i < B; ++i) { nbr += hb[(size_t)i] != 0; nerr += hs[(size_t)i] != 0; ndisp += (hw[(size_t)(i >> 5)] >> (i & 31)) & 1u; }
+    counters->instances = (uint64_t)B; counters->displayed = ndisp; counters->errors = nerr;
+    counters->not_displayed = (uint64_t)B - ndisp - nerr; counters->branched = nbr; counters->resolved_by_rules = (uint64_t)B - nbr - nerr;
     counters->work_items = h[CNT_ITEMS]; counters->rounds = rounds; counters->cherry_reductions = h[CNT_CHERRIES];
     counters->reticulated_cherries = h[CNT_RET]; counters->arcs_deleted = h[CNT_ARCS]; counters->rule_passes = h[CNT_PASSES];
   } else if (out_mem == PT_MEM_HOST) {
