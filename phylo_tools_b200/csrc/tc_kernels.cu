@@ -340,7 +340,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       for (int k = 0; k < 2; ++k) PT_CUDA(cudaMalloc((void**)&b->d_pool[k], slot_elems * (size_t)want * 4));
       b->pool_cap = want;
     }
-    const int cap = b->pool_cap;
+    const int cap = std::min(b->pool_cap, want);  // an explicit pt_options.pool_slots also caps an already larger pool
     auto sink_of = [&](int k) {
       TcSink t; int32_t* p = b->d_pool[k];
       t.succ_off = p; p += (size_t)sN1 * cap; t.succ_adj = p; p += (size_t)sM * cap; t.hlabel = p; p += (size_t)sN * cap;
