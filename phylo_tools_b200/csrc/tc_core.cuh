@@ -29,8 +29,12 @@
 
 #ifdef __CUDACC__
 #define PT_HD __host__ __device__ __forceinline__
+// the passes are real functions (shared code): fully inlined, the kernel was 156 KB of SASS and 40 % of its stall samples
+// were instruction-cache misses (profiles/ncu_tc_r01_baseline.txt)
+#define PT_NI __host__ __device__ __noinline__
 #else
 #define PT_HD inline
+#define PT_NI
 #endif
 
 namespace ptgpu {
@@ -148,7 +152,7 @@ struct TcSolver {
 
   // ---- load + validate ---------------------------------------------------------------------------------
   // returns TCS_* ; sets up arcs, labels, guest arrays.  Leaves w.sc[F_FAIL]=1 if a guest label is missing in the host.
-  PT_HD int load(const TcInst& in) {
+  PT_NI int load(const TcInst& in) {
     n = in.n; m = in.m; nt = in.nt;
     if (n > w.capN || m > w.capM || nt > w.capNT || n < 0 || m < 0 || nt < 0) return TCS_TOO_LARGE;
     if (ex.tid() == 0) { for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
@@ -228,7 +232,7 @@ struct TcSolver {
   }
 
   // ---- guest clean-up: drop unlabelled leaves, suppress unary nodes --------------------------------------
-  PT_HD void clean_guest() {
+  PT_NI void clean_guest() {
     for (;;) {
       PT_FOR(t, nt) {
         if (w.tpar[t] != TDEAD && w.tdeg[t] == 0 && w.tlab[t] < 0) {
@@ -256,7 +260,7 @@ struct TcSolver {
   }
 
   // ---- host CSR over live arcs ---------------------------------------------------------------------------
-  PT_HD void csr() {
+  PT_NI void csr() {
     PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = 0; }
     ex.sync();
     PT_FOR(e, m) { if (w.at[e] >= 0) { ex.atomic_add(&w.hcnt[w.at[e]], 1); ex.atomic_add(&w.haux[w.ah[e]], 1); } }
@@ -279,24 +283,41 @@ struct TcSolver {
   PT_HD bool mergeable(int v) const { return indeg(v) >= 2 && outdeg(v) == 1 && indeg(w.ah[out_arc(v, 0)]) >= 2; }
 
   // ---- host clean-up to a fix-point (sets F_FAIL when a label became unreachable) ------------------------------
-  PT_HD void clean_host() {
+  // One detection pass per CSR snapshot decides which rewriting pass is needed (usually none); only one kind of
+  // rewriting runs per snapshot, then the CSR is rebuilt.
+  enum { NEED_DEAD = 1, NEED_SUPPRESS = 2, NEED_MERGE = 4, NEED_PARALLEL = 8, NEED_FAIL = 16 };
+  PT_NI void clean_host() {
     for (;;) {
       csr();
-      // (a) dead ends: unlabelled nodes without live children lose their in-arcs
-      // (a') orphans: a non-root node that lost every in-arc (all were ruled out) is unreachable: drop its out-arcs;
-      //      an orphaned labelled leaf means its label cannot be displayed any more
       const int root = w.sc[F_ROOT];
+      int need = 0;
       PT_FOR(v, n) {
-        if (outdeg(v) == 0) {
-          if (w.hlab[v] < 0) { if (indeg(v) > 0) { for (int k = 0; k < indeg(v); ++k) w.at[in_arc(v, k)] = (I)-1; w.sc[F_FLAG] = 1; } }
-          else if (indeg(v) == 0 && v != root) w.sc[F_FAIL] = 1;
-        } else if (indeg(v) == 0 && v != root) {
-          for (int k = 0; k < outdeg(v); ++k) w.at[out_arc(v, k)] = (I)-1;
-          w.sc[F_FLAG] = 1;
+        const int od = outdeg(v), id = indeg(v);
+        if (od == 0) {
+          if (w.hlab[v] < 0) { if (id > 0) need |= NEED_DEAD; }          // (a) unlabelled dead end
+          else if (id == 0 && v != root) need |= NEED_FAIL;              // a labelled leaf lost every in-arc
+        } else {
+          if (id == 0 && v != root) need |= NEED_DEAD;                   // (a') orphan: unreachable, drop its out-arcs
+          if (od == 1) {
+            if (id == 1) need |= NEED_SUPPRESS;                          // (c)
+            else if (id >= 2 && indeg(w.ah[out_arc(v, 0)]) >= 2) need |= NEED_MERGE;  // (d)
+          } else if (od <= 8) {                                          // (e) parallel arcs
+            for (int a = 1; a < od; ++a)
+              for (int b = 0; b < a; ++b)
+                if (w.ah[out_arc(v, a)] == w.ah[out_arc(v, b)]) need |= NEED_PARALLEL;
+          }
         }
       }
-      if (take_flag(F_FLAG)) continue;
-      if (w.sc[F_FAIL]) return;  // caller checks F_FAIL
+      need = ex.reduce_or(need);
+      if (need & NEED_FAIL) { set_scalar(F_FAIL, 1); return; }
+      if (need & NEED_DEAD) {
+        PT_FOR(v, n) {
+          if (outdeg(v) == 0) { if (w.hlab[v] < 0) for (int k = 0; k < indeg(v); ++k) w.at[in_arc(v, k)] = (I)-1; }
+          else if (indeg(v) == 0 && v != root) for (int k = 0; k < outdeg(v); ++k) w.at[out_arc(v, k)] = (I)-1;
+        }
+        ex.sync();
+        continue;
+      }
       // (b) out-degree-1 root: its child becomes the root
       if (outdeg(root) == 1) {
         ex.sync();
@@ -304,65 +325,59 @@ struct TcSolver {
         ex.sync();
         continue;
       }
-      // (c) suppress in=out=1 chains.  Every arc decides for itself, so the pass is race-free: an arc whose tail is
-      // suppressible disappears; an arc entering a chain from a non-suppressible tail jumps to the end of the chain.
-      PT_FOR(e, m) {
-        const int t = w.at[e];
-        if (t >= 0) {
-          if (suppressible(t)) { w.at[e] = (I)-1; w.sc[F_FLAG] = 1; }
-          else {
-            int h = w.ah[e];
-            if (suppressible(h)) {
-              while (suppressible(h)) h = w.ah[out_arc(h, 0)];
-              w.ah[e] = (I)h;
+      if (need & NEED_SUPPRESS) {
+        // every arc decides for itself, so the pass is race-free: an arc whose tail is suppressible disappears; an arc
+        // entering a chain from a non-suppressible tail jumps to the end of the chain
+        PT_FOR(e, m) {
+          const int t = w.at[e];
+          if (t >= 0) {
+            if (suppressible(t)) w.at[e] = (I)-1;
+            else {
+              int h = w.ah[e];
+              if (suppressible(h)) { while (suppressible(h)) h = w.ah[out_arc(h, 0)]; w.ah[e] = (I)h; }
             }
           }
         }
+        ex.sync();
+        continue;
       }
-      if (take_flag(F_FLAG)) continue;
-      // (d) reticulation chains: hand the parents of x down to the bottom of the chain (cf. ReticulationMerger :392-409)
-      PT_FOR(v, n) {
-        int y = -1;
-        if (mergeable(v)) { y = w.ah[out_arc(v, 0)]; while (mergeable(y)) y = w.ah[out_arc(y, 0)]; }
-        w.haux[v] = y;
-      }
-      ex.sync();
-      PT_FOR(v, n) {
-        if (w.haux[v] >= 0) {
-          for (int k = 0; k < indeg(v); ++k) w.ah[in_arc(v, k)] = (I)w.haux[v];
-          w.at[out_arc(v, 0)] = (I)-1;
-          w.sc[F_FLAG] = 1;
+      if (need & NEED_MERGE) {
+        // reticulation chains: hand the parents of x down to the bottom of the chain (cf. ReticulationMerger :392-409)
+        PT_FOR(v, n) {
+          int y = -1;
+          if (mergeable(v)) { y = w.ah[out_arc(v, 0)]; while (mergeable(y)) y = w.ah[out_arc(y, 0)]; }
+          w.haux[v] = y;
         }
-      }
-      if (take_flag(F_FLAG)) continue;
-      // (e) parallel arcs (can appear after (c)/(d)): keep the lowest arc id
-      PT_FOR(v, n) {
-        const int d = outdeg(v);
-        if (d >= 2 && d <= 8) {
-          for (int a = 0; a < d; ++a)
-            for (int b = 0; b < d; ++b) {
-              const int ea = out_arc(v, a), eb = out_arc(v, b);
-              if (ea < eb && w.ah[ea] == w.ah[eb]) { w.at[eb] = (I)-1; w.sc[F_FLAG] = 1; }
-            }
+        ex.sync();
+        PT_FOR(v, n) {
+          if (w.haux[v] >= 0) { for (int k = 0; k < indeg(v); ++k) w.ah[in_arc(v, k)] = (I)w.haux[v]; w.at[out_arc(v, 0)] = (I)-1; }
         }
+        ex.sync();
+        continue;
       }
-      if (take_flag(F_FLAG)) continue;
+      if (need & NEED_PARALLEL) {
+        PT_FOR(v, n) {
+          const int d = outdeg(v);
+          if (d >= 2 && d <= 8)
+            for (int a = 0; a < d; ++a)
+              for (int b = 0; b < d; ++b) { const int ea = out_arc(v, a), eb = out_arc(v, b); if (ea < eb && w.ah[ea] == w.ah[eb]) w.at[eb] = (I)-1; }
+        }
+        ex.sync();
+        continue;
+      }
       return;
     }
   }
 
   PT_HD int count_labels() {
-    PT_FOR(l, L) { if (w.l2h[l] >= 0) ex.atomic_add(&w.sc[F_TMP], 1); }
-    ex.sync();
-    const int k = w.sc[F_TMP];
-    ex.sync();
-    set_scalar(F_TMP, 0);
-    return k;
+    int c = 0;
+    PT_FOR(l, L) { c += (w.l2h[l] >= 0); }
+    return ex.reduce_add(c);
   }
 
   // ---- wavefront over topological levels: heights and reachable-label bitsets -----------------------------
   // returns false if some live node was never reached (cycle)
-  PT_HD bool wavefront() {
+  PT_NI bool wavefront() {
     const int W = w.W;
     PT_FOR(v, n) {
       for (int k = 0; k < W; ++k) w.lset[v * W + k] = 0;
@@ -389,8 +404,10 @@ struct TcSolver {
   }
 
   // ---- TC: true (multi-)cherries --------------------------------------------------------------------------
-  // returns 1 changed, 0 nothing, -1 NOT displayed
-  PT_HD int rule_true_cherry() {
+  // returns 1 changed, 0 nothing, -1 NOT displayed.  Reads only in-lists of labelled leaves and out-DEGREES of their
+  // parents, none of which a collapse changes for nodes that are still internal, so it may be repeated without
+  // rebuilding the CSR (solve() loops it until nothing collapses).
+  PT_NI int rule_true_cherry() {
     PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = -1; }
     PT_FOR(t, nt) { w.tmin[t] = 0x7fffffff; }
     ex.sync();
@@ -399,27 +416,27 @@ struct TcSolver {
       if (h >= 0 && indeg(h) == 1) ex.atomic_add(&w.hcnt[w.at[in_arc(h, 0)]], 1);
     }
     ex.sync();
+    int fail = 0, any = 0;
     PT_FOR(l, L) {
       const int h = w.l2h[l];
       if (h >= 0 && indeg(h) == 1) {
         const int q = w.at[in_arc(h, 0)];
         if (w.hcnt[q] == outdeg(q) && outdeg(q) >= 2) {
           const int p = w.tpar[w.l2t[l]];
-          if (p < 0) w.sc[F_FAIL] = 1;
+          any = 1;
+          if (p < 0) fail = 1;
           else {
             const int old = ex.atomic_cas(&w.haux[q], -1, p);
-            if (old != -1 && old != p) w.sc[F_FAIL] = 1;
+            if (old != -1 && old != p) fail = 1;
             ex.atomic_min(&w.tmin[p], l);
           }
         }
       }
     }
-    ex.sync();
-    PT_FOR(q, n) {
-      if (w.haux[q] >= 0 && w.tdeg[w.haux[q]] != outdeg(q)) w.sc[F_FAIL] = 1;
-    }
-    ex.sync();
-    if (w.sc[F_FAIL]) return -1;
+    if (!ex.reduce_or(any)) return 0;
+    PT_FOR(q, n) { if (w.haux[q] >= 0 && w.tdeg[w.haux[q]] != outdeg(q)) fail = 1; }
+    if (ex.reduce_or(fail)) { set_scalar(F_FAIL, 1); return -1; }
+    int collapsed = 0;
     PT_FOR(l, L) {
       const int h = w.l2h[l];
       if (h >= 0 && indeg(h) == 1) {
@@ -432,21 +449,17 @@ struct TcSolver {
           if (l == w.tmin[p]) {
             w.hlab[q] = (I)l; w.l2h[l] = (I)q;
             w.tlab[p] = (I)l; w.l2t[l] = (I)p; w.tdeg[p] = 0;
-            ex.atomic_add(&w.sc[F_TMP2], 1);
+            ++collapsed;
           } else { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
-          w.sc[F_FLAG] = 1;
         }
       }
     }
-    ex.sync();
-    st.cherries += (unsigned)w.sc[F_TMP2];
-    ex.sync();
-    set_scalar(F_TMP2, 0);
-    return take_flag(F_FLAG) ? 1 : 0;
+    st.cherries += (unsigned)ex.reduce_add(collapsed);
+    return 1;
   }
 
   // ---- guest cherries with exactly two leaves: tmin/tmax = their labels, tleaf = 2 ---------------------------
-  PT_HD void guest_cherries() {
+  PT_NI void guest_cherries() {
     PT_FOR(t, nt) { w.tleaf[t] = 0; w.tmin[t] = 0x7fffffff; w.tmax[t] = -1; }
     ex.sync();
     PT_FOR(l, L) {
@@ -458,7 +471,7 @@ struct TcSolver {
   PT_HD bool is_bin_cherry(int p) const { return w.tpar[p] != TDEAD && w.tdeg[p] == 2 && w.tleaf[p] == 2; }
 
   // ---- RC: reticulated cherries ---------------------------------------------------------------------------
-  PT_HD int rule_ret_cherry() {
+  PT_NI int rule_ret_cherry() {
     PT_FOR(p, nt) {
       if (is_bin_cherry(p)) {
         for (int side = 0; side < 2; ++side) {
@@ -501,7 +514,7 @@ struct TcSolver {
     const int want = reach ? lam : -2;
     if (w.haux[c] != want) { w.haux[c] = want; w.sc[F_TMP] = 1; }
   }
-  PT_HD int rule_sibling() {
+  PT_NI int rule_sibling() {
     PT_FOR(v, n + 1) { w.haux[v] = -1; w.hcnt[v] = 0; }
     ex.sync();
     PT_FOR(p, nt) {
@@ -534,7 +547,7 @@ struct TcSolver {
   }
 
   // ---- branching: lowest multi-parent node ------------------------------------------------------------------
-  PT_HD int pick_branch_node() {
+  PT_NI int pick_branch_node() {
     set_scalar(F_BEST, 0x7fffffff);
     PT_FOR(v, n) { if (indeg(v) >= 2) ex.atomic_min(&w.sc[F_BEST], ((int)w.lvl[v] << 16) | v); }
     ex.sync();
@@ -545,7 +558,7 @@ struct TcSolver {
 
   // write the current (clean) state, with only in-arc `keep` of node x kept, as a compact instance.
   // Label ids are kept (no renumbering), so L and the bitset width stay those of the parent.
-  PT_HD void emit_child(int x, int keep, const TcEmit& out) {
+  PT_NI void emit_child(int x, int keep, const TcEmit& out) {
     const int root = w.sc[F_ROOT];
     // live host nodes (root, or any live in-arc) -> new ids by a scan of the flags (lvl is free after pick_branch_node)
     PT_FOR(v, n + 1) {
@@ -581,7 +594,7 @@ struct TcSolver {
 
   // Kahn peel from the leaves: every node must be reached, exactly one node has no in-arc (the reference throws
   // std::logic_error for several roots, utils/storage_adj_common.hpp:103-109; a cycle would hang its DFS)
-  PT_HD bool check_dag(bool trusted) {
+  PT_NI bool check_dag(bool trusted) {
     csr();
     PT_FOR(v, n) { w.hcnt[v] = outdeg(v); w.lvl[v] = (I)(outdeg(v) == 0 ? 0 : LVL_INF); if (indeg(v) == 0) { ex.atomic_add(&w.sc[F_TMP], 1); w.sc[F_ROOT] = v; } }
     ex.sync();
@@ -618,9 +631,10 @@ struct TcSolver {
       clean_host();
       if (w.sc[F_FAIL]) return TC_NOT;
       if (count_labels() <= 2) return TC_DISPLAYED;  // containment.hpp:1061,1208
-      int r = rule_true_cherry();
+      int r = rule_true_cherry(), collapsed = 0;
+      while (r > 0) { collapsed = 1; r = rule_true_cherry(); }   // pendant subtrees collapse level by level, no CSR rebuild
       if (r < 0) return TC_NOT;
-      if (r > 0) continue;
+      if (collapsed) continue;
       guest_cherries();
       r = rule_ret_cherry();
       if (r > 0) continue;

@@ -20,6 +20,8 @@ struct WarpEx {
   __device__ __forceinline__ int nth() const { return 32; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ int map(int i, int) const { return i; }
+  __device__ __forceinline__ int reduce_or(int v) const { return (int)__reduce_or_sync(0xffffffffu, (unsigned)v); }
+  __device__ __forceinline__ int reduce_add(int v) const { return __reduce_add_sync(0xffffffffu, v); }
   __device__ __forceinline__ int atomic_add(int32_t* p, int v) const { return atomicAdd(p, v); }
   __device__ __forceinline__ int atomic_min(int32_t* p, int v) const { return atomicMin(p, v); }
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
