@@ -29,19 +29,26 @@
 
 #ifdef __CUDACC__
 #define PT_HD __host__ __device__ __forceinline__
-// the passes are real functions (shared code): fully inlined, the kernel was 156 KB of SASS and 40 % of its stall samples
-// were instruction-cache misses (profiles/ncu_tc_r01_baseline.txt)
-#define PT_NI __host__ __device__ __noinline__
+// Code size matters here: the first version was 156 KB of SASS and 40 % of its stall samples were instruction-cache misses
+// (profiles/).  Real (noinline) calls were worse: the workspace pointers then live in local memory.  So: everything inline,
+// every pass has ONE call site, and no loop is unrolled (PT_NOUNROLL): the kernel is latency bound, not issue bound.
+#define PT_NI __host__ __device__ __forceinline__
+#if defined(__CUDA_ARCH__)
+#define PT_NOUNROLL _Pragma("unroll 1")
+#else
+#define PT_NOUNROLL
+#endif
 #else
 #define PT_HD inline
 #define PT_NI
+#define PT_NOUNROLL
 #endif
 
 namespace ptgpu {
 
 // parallel-for over [0,n): i_ is the executor's slot, i the (possibly permuted) element
 #define PT_FOR(i, n) \
-  for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
+  PT_NOUNROLL for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
 
 enum TcCode : int { TC_NOT = 0, TC_DISPLAYED = 1, TC_BRANCH = 2, TC_ERROR = 3 };
 enum TcStatus : int { TCS_OK = 0, TCS_MULTILABEL = 1, TCS_BAD_GRAPH = 2, TCS_TOO_LARGE = 3, TCS_POOL_OVERFLOW = 4 };
@@ -72,7 +79,7 @@ struct TcWork {
   I *ioff, *iarc;        // in CSR
   I *hlab;               // label of a live labelled leaf, else -1
   I *lvl;                // height (longest path to a leaf) from the wavefront; scratch otherwise
-  int32_t *hcnt, *haux;  // atomic scratch, capN+1 each
+  int32_t *hcnt, *haux, *hscr;  // atomic / scan scratch, capN+1 each
   uint32_t* lset;        // capN * W : labels reachable below each node
   // guest tree
   I *tpar, *tlab;        // tpar: -1 root, -2 deleted
@@ -88,7 +95,7 @@ struct TcWork {
     size_t b = 0;
     b += (size_t)(2 * M + (N + 1) + M + (N + 1) + M + N + (N + 1)) * sizeof(I);  // at ah ooff oarc ioff iarc hlab lvl
     b = (b + 3) & ~(size_t)3;
-    b += (size_t)(2 * (N + 1)) * 4;                                         // hcnt haux
+    b += (size_t)(3 * (N + 1)) * 4;                                         // hcnt haux hscr
     b += (size_t)N * W * 4;                                                 // lset
     b += (size_t)(2 * NT) * sizeof(I);                                      // tpar tlab
     b = (b + 3) & ~(size_t)3;
@@ -107,7 +114,7 @@ struct TcWork {
     ioff = (I*)take((size_t)(N + 1) * sizeof(I)); iarc = (I*)take((size_t)M * sizeof(I));
     hlab = (I*)take((size_t)N * sizeof(I)); lvl = (I*)take((size_t)(N + 1) * sizeof(I));
     p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
-    hcnt = (int32_t*)take((size_t)(N + 1) * 4); haux = (int32_t*)take((size_t)(N + 1) * 4);
+    hcnt = (int32_t*)take((size_t)(N + 1) * 4); haux = (int32_t*)take((size_t)(N + 1) * 4); hscr = (int32_t*)take((size_t)(N + 1) * 4);
     lset = (uint32_t*)take((size_t)N * W * 4);
     tpar = (I*)take((size_t)NT * sizeof(I)); tlab = (I*)take((size_t)NT * sizeof(I));
     p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
@@ -155,7 +162,7 @@ struct TcSolver {
   PT_NI int load(const TcInst& in) {
     n = in.n; m = in.m; nt = in.nt;
     if (n > w.capN || m > w.capM || nt > w.capNT || n < 0 || m < 0 || nt < 0) return TCS_TOO_LARGE;
-    if (ex.tid() == 0) { for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
+    if (ex.tid() == 0) { PT_NOUNROLL for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
     ex.sync();
     // structure checks on the CSR offsets
     PT_FOR(v, n + 1) {
@@ -166,7 +173,7 @@ struct TcSolver {
     if (take_flag(F_STATUS)) return TCS_BAD_GRAPH;
     int maxlab = -1;
     PT_FOR(v, n) {
-      for (int e = w.ooff[v]; e < w.ooff[v + 1]; ++e) w.at[e] = (I)v;
+      PT_NOUNROLL for (int e = w.ooff[v]; e < w.ooff[v + 1]; ++e) w.at[e] = (I)v;
       const int l = in.hlabel[v];
       w.hlab[v] = (I)l;
       if (l >= w.capL || l < -1) w.sc[F_STATUS] = TCS_TOO_LARGE;
@@ -286,9 +293,15 @@ struct TcSolver {
   // One detection pass per CSR snapshot decides which rewriting pass is needed (usually none); only one kind of
   // rewriting runs per snapshot, then the CSR is rebuilt.
   enum { NEED_DEAD = 1, NEED_SUPPRESS = 2, NEED_MERGE = 4, NEED_PARALLEL = 8, NEED_FAIL = 16 };
-  PT_NI void clean_host() {
+  // dag_state: 0 = input not validated yet (untrusted), 1 = validated, 2 = trusted (only the root is looked up)
+  PT_NI void clean_host(int& dag_state, int* status) {
     for (;;) {
       csr();
+      if (dag_state != 1) {
+        const bool ok = check_dag(dag_state == 2);
+        dag_state = 1;
+        if (!ok) { *status = TCS_BAD_GRAPH; return; }
+      }
       const int root = w.sc[F_ROOT];
       int need = 0;
       PT_FOR(v, n) {
@@ -302,8 +315,8 @@ struct TcSolver {
             if (id == 1) need |= NEED_SUPPRESS;                          // (c)
             else if (id >= 2 && indeg(w.ah[out_arc(v, 0)]) >= 2) need |= NEED_MERGE;  // (d)
           } else if (od <= 8) {                                          // (e) parallel arcs
-            for (int a = 1; a < od; ++a)
-              for (int b = 0; b < a; ++b)
+            PT_NOUNROLL for (int a = 1; a < od; ++a)
+              PT_NOUNROLL for (int b = 0; b < a; ++b)
                 if (w.ah[out_arc(v, a)] == w.ah[out_arc(v, b)]) need |= NEED_PARALLEL;
           }
         }
@@ -312,8 +325,8 @@ struct TcSolver {
       if (need & NEED_FAIL) { set_scalar(F_FAIL, 1); return; }
       if (need & NEED_DEAD) {
         PT_FOR(v, n) {
-          if (outdeg(v) == 0) { if (w.hlab[v] < 0) for (int k = 0; k < indeg(v); ++k) w.at[in_arc(v, k)] = (I)-1; }
-          else if (indeg(v) == 0 && v != root) for (int k = 0; k < outdeg(v); ++k) w.at[out_arc(v, k)] = (I)-1;
+          if (outdeg(v) == 0) { if (w.hlab[v] < 0) PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) w.at[in_arc(v, k)] = (I)-1; }
+          else if (indeg(v) == 0 && v != root) PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) w.at[out_arc(v, k)] = (I)-1;
         }
         ex.sync();
         continue;
@@ -350,7 +363,7 @@ struct TcSolver {
         }
         ex.sync();
         PT_FOR(v, n) {
-          if (w.haux[v] >= 0) { for (int k = 0; k < indeg(v); ++k) w.ah[in_arc(v, k)] = (I)w.haux[v]; w.at[out_arc(v, 0)] = (I)-1; }
+          if (w.haux[v] >= 0) { PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) w.ah[in_arc(v, k)] = (I)w.haux[v]; w.at[out_arc(v, 0)] = (I)-1; }
         }
         ex.sync();
         continue;
@@ -359,8 +372,8 @@ struct TcSolver {
         PT_FOR(v, n) {
           const int d = outdeg(v);
           if (d >= 2 && d <= 8)
-            for (int a = 0; a < d; ++a)
-              for (int b = 0; b < d; ++b) { const int ea = out_arc(v, a), eb = out_arc(v, b); if (ea < eb && w.ah[ea] == w.ah[eb]) w.at[eb] = (I)-1; }
+            PT_NOUNROLL for (int a = 0; a < d; ++a)
+              PT_NOUNROLL for (int b = 0; b < d; ++b) { const int ea = out_arc(v, a), eb = out_arc(v, b); if (ea < eb && w.ah[ea] == w.ah[eb]) w.at[eb] = (I)-1; }
         }
         ex.sync();
         continue;
@@ -380,7 +393,7 @@ struct TcSolver {
   PT_NI bool wavefront() {
     const int W = w.W;
     PT_FOR(v, n) {
-      for (int k = 0; k < W; ++k) w.lset[v * W + k] = 0;
+      PT_NOUNROLL for (int k = 0; k < W; ++k) w.lset[v * W + k] = 0;
       w.hcnt[v] = outdeg(v);
       w.lvl[v] = (I)((outdeg(v) == 0 && (indeg(v) > 0 || w.hlab[v] >= 0)) ? 0 : LVL_INF);
       if (w.hlab[v] >= 0) w.lset[v * W + (w.hlab[v] >> 5)] = 1u << (w.hlab[v] & 31);
@@ -390,9 +403,9 @@ struct TcSolver {
       PT_FOR(v, n) {
         if (w.lvl[v] == lev) {
           w.sc[F_FLAG] = 1;
-          for (int k = 0; k < indeg(v); ++k) {
+          PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) {
             const int p = w.at[in_arc(v, k)];
-            for (int j = 0; j < W; ++j) { const uint32_t b = w.lset[v * W + j]; if (b) ex.atomic_or(&w.lset[p * W + j], b); }
+            PT_NOUNROLL for (int j = 0; j < W; ++j) { const uint32_t b = w.lset[v * W + j]; if (b) ex.atomic_or(&w.lset[p * W + j], b); }
             if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.lvl[p] = (I)(lev + 1);
           }
         }
@@ -474,7 +487,7 @@ struct TcSolver {
   PT_NI int rule_ret_cherry() {
     PT_FOR(p, nt) {
       if (is_bin_cherry(p)) {
-        for (int side = 0; side < 2; ++side) {
+        PT_NOUNROLL for (int side = 0; side < 2; ++side) {
           const int x = side ? w.tmax[p] : w.tmin[p], y = side ? w.tmin[p] : w.tmax[p];
           const int hx = w.l2h[x], hy = w.l2h[y];
           if (indeg(hx) != 1) continue;
@@ -484,9 +497,9 @@ struct TcSolver {
           else if (indeg(hy) == 1) { const int z = w.at[in_arc(hy, 0)]; if (outdeg(z) == 1 && indeg(z) >= 2) c = z; }
           if (c < 0) continue;
           int keep = -1;
-          for (int k = 0; k < indeg(c); ++k) if (w.at[in_arc(c, k)] == q) keep = in_arc(c, k);
+          PT_NOUNROLL for (int k = 0; k < indeg(c); ++k) if (w.at[in_arc(c, k)] == q) keep = in_arc(c, k);
           if (keep < 0) continue;
-          for (int k = 0; k < indeg(c); ++k) { const int e = in_arc(c, k); if (e != keep) w.at[e] = (I)-1; }
+          PT_NOUNROLL for (int k = 0; k < indeg(c); ++k) { const int e = in_arc(c, k); if (e != keep) w.at[e] = (I)-1; }
           ex.atomic_add(&w.sc[F_TMP2], 1);
           w.sc[F_FLAG] = 1;
           break;
@@ -519,12 +532,12 @@ struct TcSolver {
     ex.sync();
     PT_FOR(p, nt) {
       if (is_bin_cherry(p)) {
-        for (int side = 0; side < 2; ++side) {
+        PT_NOUNROLL for (int side = 0; side < 2; ++side) {
           const int x = side ? w.tmax[p] : w.tmin[p], y = side ? w.tmin[p] : w.tmax[p];
           const int hx = w.l2h[x];
           if (indeg(hx) != 1) continue;
           const int q = w.at[in_arc(hx, 0)];
-          for (int k = 0; k < outdeg(q); ++k) { const int e = out_arc(q, k); if (w.ah[e] != hx) constrain_arc(e, y); }
+          PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) { const int e = out_arc(q, k); if (w.ah[e] != hx) constrain_arc(e, y); }
         }
       }
     }
@@ -534,7 +547,7 @@ struct TcSolver {
       PT_FOR(v, n) {
         if (w.haux[v] != -1 && !w.hcnt[v]) {
           w.hcnt[v] = 1;
-          for (int k = 0; k < outdeg(v); ++k) constrain_arc(out_arc(v, k), w.haux[v]);
+          PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) constrain_arc(out_arc(v, k), w.haux[v]);
         }
       }
     }
@@ -564,20 +577,20 @@ struct TcSolver {
     PT_FOR(v, n + 1) {
       const int live = (v < n && (v == root || indeg(v) > 0)) ? 1 : 0;
       int d = 0;
-      if (live) for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) ++d; }
+      if (live) PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) ++d; }
       w.hcnt[v] = live; w.haux[v] = d;
     }
     ex.sync();
     ex.exclusive_scan(w.hcnt, w.lvl, n);   // lvl[v] = new id of v, lvl[n] = n2
-    ex.exclusive_scan(w.haux, w.ioff, n);  // ioff is rebuilt by the next csr(); from here on indeg() is invalid
-    const int n2 = w.lvl[n], m2 = w.ioff[n];
+    ex.exclusive_scan(w.haux, w.hscr, n);  // hscr[v] = first arc position of v in the child
+    const int n2 = w.lvl[n], m2 = w.hscr[n];
     PT_FOR(v, n) {
       if (w.hcnt[v]) {
         const int id = w.lvl[v];
-        out.succ_off[id] = w.ioff[v];
+        out.succ_off[id] = w.hscr[v];
         out.hlabel[id] = w.hlab[v];
-        int pos = w.ioff[v];
-        for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) out.succ_adj[pos++] = w.lvl[w.ah[e]]; }
+        int pos = w.hscr[v];
+        PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) out.succ_adj[pos++] = w.lvl[w.ah[e]]; }
       }
     }
     // guest
@@ -595,7 +608,6 @@ struct TcSolver {
   // Kahn peel from the leaves: every node must be reached, exactly one node has no in-arc (the reference throws
   // std::logic_error for several roots, utils/storage_adj_common.hpp:103-109; a cycle would hang its DFS)
   PT_NI bool check_dag(bool trusted) {
-    csr();
     PT_FOR(v, n) { w.hcnt[v] = outdeg(v); w.lvl[v] = (I)(outdeg(v) == 0 ? 0 : LVL_INF); if (indeg(v) == 0) { ex.atomic_add(&w.sc[F_TMP], 1); w.sc[F_ROOT] = v; } }
     ex.sync();
     const int nroots = w.sc[F_TMP];
@@ -607,7 +619,7 @@ struct TcSolver {
       PT_FOR(v, n) {
         if (w.lvl[v] == lev) {
           w.sc[F_FLAG] = 1;
-          for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.lvl[p] = (I)(lev + 1); }
+          PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.lvl[p] = (I)(lev + 1); }
         }
       }
       if (!take_flag(F_FLAG)) break;
@@ -623,16 +635,17 @@ struct TcSolver {
     *status = TCS_OK; *branch_node = -1;
     int s = load(in);
     if (s != TCS_OK) { *status = s; return TC_ERROR; }
-    if (!check_dag(trusted)) { *status = TCS_BAD_GRAPH; return TC_ERROR; }
-    if (w.sc[F_FAIL]) return TC_NOT;
+    const int missing = w.sc[F_FAIL];  // a guest label without a host leaf; reported after the input has been validated
     clean_guest();
+    int dag_state = trusted ? 2 : 0;
     for (;;) {
       ++st.passes;
-      clean_host();
-      if (w.sc[F_FAIL]) return TC_NOT;
+      clean_host(dag_state, status);
+      if (*status != TCS_OK) return TC_ERROR;
+      if (missing || w.sc[F_FAIL]) return TC_NOT;
       if (count_labels() <= 2) return TC_DISPLAYED;  // containment.hpp:1061,1208
-      int r = rule_true_cherry(), collapsed = 0;
-      while (r > 0) { collapsed = 1; r = rule_true_cherry(); }   // pendant subtrees collapse level by level, no CSR rebuild
+      int r, collapsed = 0;
+      for (;;) { r = rule_true_cherry(); if (r <= 0) break; collapsed = 1; }  // pendant subtrees collapse level by level, no CSR rebuild
       if (r < 0) return TC_NOT;
       if (collapsed) continue;
       guest_cherries();

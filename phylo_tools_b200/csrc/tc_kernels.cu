@@ -122,9 +122,11 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(TcSource src, TcSink sin
       } else {
         if (lane == 0) branched[origin] = 1;
         c_br += (unsigned long long)d;
+        int32_t* arcs = reinterpret_cast<int32_t*>(w.lset);  // the label sets are dead by now; d <= n <= capN * W words
+        for (int k = lane; k < d; k += 32) arcs[k] = sv.in_arc(x, k);
+        __syncwarp();
         for (int k = 0; k < d; ++k) {
-          if (k > 0) sv.csr();  // emit_child overwrites the in-CSR offsets
-          const int keep = sv.in_arc(x, k);
+          const int keep = arcs[k];
           const size_t slot = (size_t)(base + k);
           TcEmit out{sink.succ_off + slot * sink.sN1, sink.succ_adj + slot * sink.sM, sink.hlabel + slot * sink.sN,
                      sink.tparent + slot * sink.sNT, sink.tlabel + slot * sink.sNT, sink.dims + slot * 4};

@@ -74,7 +74,6 @@ static int solve_instance(const Item& root, int capN, int capM, int capNT, int c
         Item ch; ch.succ_off.resize(sv.n + 1); ch.succ_adj.resize(sv.m + 1); ch.hlabel.resize(sv.n + 1); ch.tparent.resize(sv.nt + 1); ch.tlabel.resize(sv.nt + 1);
         int32_t dims[4];
         TcEmit out{ch.succ_off.data(), ch.succ_adj.data(), ch.hlabel.data(), ch.tparent.data(), ch.tlabel.data(), dims};
-        if (k > 0) sv.csr();  // emit_child clobbers ioff
         sv.emit_child(x, arcs[k], out);
         ch.n = dims[0]; ch.m = dims[1]; ch.nt = dims[2];
         stack.push_back(std::move(ch));
