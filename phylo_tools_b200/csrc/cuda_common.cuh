@@ -36,6 +36,12 @@ inline int device_props(DeviceProps* p) {
   return PT_OK;
 }
 
+// Caching device allocator: pt_batch_create / pt_batch_free sit on the end-to-end path (one handle per batch), and
+// cudaMalloc / cudaFree of the ~1 GB a 10^5-instance batch needs cost more than the kernels.  Freed blocks are kept
+// (up to kCacheLimit bytes) and handed out again for requests of the same size class.
+int dev_alloc(void** p, size_t bytes);
+void dev_free(void* p);
+
 // streaming loads/stores: data touched once should not displace the L2-resident tables
 __device__ __forceinline__ int4 ld_stream_v4(const int4* p) {
   int4 r;

@@ -11,7 +11,55 @@
 #include "cuda_common.cuh"
 #include "tc_core.cuh"
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 namespace ptgpu {
+
+// ---- caching device allocator (see cuda_common.cuh) -----------------------------------------------------------------
+namespace {
+std::mutex g_alloc_mu;
+std::multimap<size_t, void*> g_free_blocks;          // (device << 48 | size) -> block
+std::unordered_map<void*, size_t> g_block_size;      // every live or cached block we own -> its key
+size_t g_cached_bytes = 0;
+constexpr size_t kCacheLimit = (size_t)16 << 30;
+size_t size_class(size_t b) { const size_t g = b < ((size_t)1 << 20) ? 4096 : ((size_t)1 << 20); return (b + g - 1) / g * g; }
+}  // namespace
+int dev_alloc(void** p, size_t bytes) {
+  const size_t sz = size_class(bytes ? bytes : 1);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t key = ((size_t)dev << 48) | sz;
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    auto it = g_free_blocks.find(key);
+    if (it != g_free_blocks.end()) { *p = it->second; g_free_blocks.erase(it); g_cached_bytes -= sz; return PT_OK; }
+  }
+  cudaError_t e = cudaMalloc(p, sz);
+  if (e != cudaSuccess) {  // release the cache and retry once
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lk(g_alloc_mu);
+      for (auto& kv : g_free_blocks) { cudaFree(kv.second); g_block_size.erase(kv.second); }
+      g_free_blocks.clear(); g_cached_bytes = 0;
+    }
+    e = cudaMalloc(p, sz);
+    if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return set_error(PT_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", sz, cudaGetErrorString(e)); }
+  }
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  g_block_size[*p] = key;
+  return PT_OK;
+}
+void dev_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  auto it = g_block_size.find(p);
+  if (it == g_block_size.end()) { cudaFree(p); return; }
+  const size_t sz = it->second & (((size_t)1 << 48) - 1);
+  if (g_cached_bytes + sz > kCacheLimit) { cudaFree(p); g_block_size.erase(it); return; }
+  g_free_blocks.emplace(it->second, p); g_cached_bytes += sz;
+}
 
 // ---- the warp executor: PT_FOR = lane-strided loop, barrier = __syncwarp, atomics on shared memory ---------------
 struct WarpEx {
@@ -187,16 +235,18 @@ struct pt_batch {
   static constexpr int kMaxTimedRounds = 16;
   cudaEvent_t ev[2 * kMaxTimedRounds] = {};
   int timed_rounds = 0;
+  cudaStream_t used_stream = nullptr; bool used_stream_valid = false;
 };
 
 static void batch_release(pt_batch* b) {
   if (!b) return;
+  if (b->used_stream_valid) cudaStreamSynchronize(b->used_stream);  // cached blocks may be handed to another handle at once
   if (b->owns_input) {
-    cudaFree(b->d_hnode_off); cudaFree(b->d_harc_off); cudaFree(b->d_gnode_off);
-    cudaFree(b->d_succ_off); cudaFree(b->d_succ_adj); cudaFree(b->d_hlabel); cudaFree(b->d_tparent); cudaFree(b->d_tlabel);
+    dev_free(b->d_hnode_off); dev_free(b->d_harc_off); dev_free(b->d_gnode_off);
+    dev_free(b->d_succ_off); dev_free(b->d_succ_adj); dev_free(b->d_hlabel); dev_free(b->d_tparent); dev_free(b->d_tlabel);
   }
-  cudaFree(b->d_bits); cudaFree(b->d_status); cudaFree(b->d_branched); cudaFree(b->d_ticket); cudaFree(b->d_counters);
-  cudaFree(b->d_pool[0]); cudaFree(b->d_pool[1]);
+  dev_free(b->d_bits); dev_free(b->d_status); dev_free(b->d_branched); dev_free(b->d_ticket); dev_free(b->d_counters);
+  dev_free(b->d_pool[0]); dev_free(b->d_pool[1]);
   for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
   delete b;
 }
@@ -204,7 +254,7 @@ static void batch_release(pt_batch* b) {
 template <class T>
 static int upload(T** dst, const T* src, int64_t count, cudaStream_t s, int64_t* bytes) {
   const size_t nb = (size_t)std::max<int64_t>(count, 1) * sizeof(T);
-  PT_CUDA(cudaMalloc((void**)dst, nb));
+  if (int rc = dev_alloc((void**)dst, nb)) return rc;
   if (count > 0) { PT_CUDA(cudaMemcpyAsync(*dst, src, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, s)); *bytes += (int64_t)count * (int64_t)sizeof(T); }
   return PT_OK;
 }
@@ -241,6 +291,7 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   pt_batch* b = new (std::nothrow) pt_batch();
   if (!b) return set_error(PT_ERR_NOMEM, "out of host memory");
   const int64_t B = b->B = d->num_instances;
+  b->used_stream = s; b->used_stream_valid = true;
   int rc = PT_OK;
   auto fail = [&](int code) { batch_release(b); return code; };
   b->maxN = d->max_host_nodes; b->maxM = d->max_host_arcs; b->maxNT = d->max_guest_nodes; b->maxL = d->max_labels;
@@ -288,10 +339,10 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   if (b->maxM <= 0) b->maxM = std::max(1, 2 * b->maxN);
   b->maxN = std::max(b->maxN, 1); b->maxNT = std::max(b->maxNT, 1); b->maxL = std::max(b->maxL, 1);
   const size_t words = (size_t)((B + 31) / 32) + 1;
-  if (cudaMalloc((void**)&b->d_bits, words * 4) != cudaSuccess || cudaMalloc((void**)&b->d_status, (size_t)B + 1) != cudaSuccess ||
-      cudaMalloc((void**)&b->d_branched, (size_t)B + 1) != cudaSuccess || cudaMalloc((void**)&b->d_ticket, 64) != cudaSuccess ||
-      cudaMalloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long)) != cudaSuccess)
-    return fail(set_error(PT_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
+  if ((rc = dev_alloc((void**)&b->d_bits, words * 4)) || (rc = dev_alloc((void**)&b->d_status, (size_t)B + 1)) ||
+      (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 64)) ||
+      (rc = dev_alloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long))))
+    return fail(rc);
   *out = b;
   return PT_OK;
 }
@@ -314,6 +365,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   const int64_t B = b->B;
   const size_t words = (size_t)((B + 31) / 32);
   b->last_launches = 0; b->timed_rounds = 0;
+  b->used_stream = s; b->used_stream_valid = true;
   uint32_t* bits = out_mem == PT_MEM_DEVICE ? result_bits : b->d_bits;
   uint8_t* stat = (out_mem == PT_MEM_DEVICE && status) ? status : b->d_status;
   PT_CUDA(cudaMemsetAsync(bits, 0, words * 4, s));
@@ -340,8 +392,8 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     const int sN1 = b->maxN + 1, sM = std::max(1, (int)b->maxM), sN = b->maxN, sNT = b->maxNT;
     const size_t slot_elems = (size_t)sN1 + sM + sN + 2 * (size_t)sNT + 4 + 1;
     if (b->pool_cap < want) {
-      cudaFree(b->d_pool[0]); cudaFree(b->d_pool[1]); b->d_pool[0] = b->d_pool[1] = nullptr; b->pool_cap = 0;
-      for (int k = 0; k < 2; ++k) PT_CUDA(cudaMalloc((void**)&b->d_pool[k], slot_elems * (size_t)want * 4));
+      dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); b->d_pool[0] = b->d_pool[1] = nullptr; b->pool_cap = 0;
+      for (int k = 0; k < 2; ++k) if (int rc2 = dev_alloc((void**)&b->d_pool[k], slot_elems * (size_t)want * 4)) return rc2;
       b->pool_cap = want;
     }
     const int cap = std::min(b->pool_cap, want);  // an explicit pt_options.pool_slots also caps an already larger pool

@@ -1,0 +1,119 @@
+// pt/containment.hpp -- the containment entry points of the reference, over the CUDA engine.
+//
+// Drop-in names for utils/containment.hpp:
+//   TreeInNetContainment<Host,Guest>(host, guest)   ctor overloads :1179-1182 (copy or move; we only read)
+//       .displayed()                                 :1202
+//       .force_parent(u, v)                          :1186-1199 (keep only the in-arc v->u of u)
+//   TreeInTreeContainment<Host,Guest>(host, guest)  :50-54, .displayed() :83
+// plus BatchContainment, the batched form the reference lacks: the engine's unit of work is a BATCH of instances
+// (one warp per instance), so single-instance calls are batches of one.
+// Not provided yet: who_displays(Node) (:72-81) -- SURVEY 8(f) rank 2.
+//
+// Errors follow the reference: duplicate labels and malformed graphs throw std::logic_error
+// (utils/label_matching.hpp:51-52, utils/storage_adj_common.hpp:103-109); engine failures throw std::runtime_error.
+// There is no CPU fallback: without a CUDA device displayed() throws.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+#include "../../../include/pt_gpu.h"
+#include "network.hpp"
+#include "packer.hpp"
+
+namespace PT {
+
+struct EngineError : public std::runtime_error { int code; EngineError(int c, const std::string& what) : std::runtime_error(what), code(c) {} };
+
+inline void throw_status(int rc, const char* where) {
+  if (rc == PT_OK) return;
+  const std::string msg = std::string(where) + ": " + pt_last_error();
+  if (rc == PT_ERR_INVALID) throw std::logic_error(msg);
+  throw EngineError(rc, msg);
+}
+
+// many (host, guest) pairs at once
+class BatchContainment {
+  BatchPacker packer_;
+  std::vector<uint8_t> status_;
+  std::vector<bool> verdict_;
+  pt_counters counters_{};
+  bool done_ = false;
+
+ public:
+  template <class Host, class Guest>
+  size_t add(const Host& N, const Guest& T) { done_ = false; packer_.add(N, T); return packer_.size() - 1; }
+  size_t add_newick(const std::string& first, const std::string& second) { done_ = false; packer_.add_newick(first, second); return packer_.size() - 1; }
+  size_t size() const { return packer_.size(); }
+  const BatchPacker& packer() const { return packer_; }
+
+  void run(void* stream = nullptr) {
+    const size_t B = packer_.size();
+    std::vector<uint32_t> bits((B + 31) / 32 + 1, 0);
+    status_.assign(B + 1, 0);
+    const pt_batch_desc d = packer_.desc();
+    pt_batch* h = nullptr;
+    throw_status(pt_batch_create(&h, &d, stream), "pt_batch_create");
+    const int rc = pt_batch_contain(h, nullptr, bits.data(), status_.data(), PT_MEM_HOST, &counters_, stream);
+    pt_batch_free(h);
+    throw_status(rc, "pt_batch_contain");
+    verdict_.resize(B);
+    for (size_t i = 0; i < B; ++i) verdict_[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+    done_ = true;
+  }
+  // verdict of instance i; throws like the reference would for a malformed instance
+  bool displayed(size_t i) {
+    if (!done_) run();
+    switch (status_.at(i)) {
+      case PT_INST_OK: return verdict_[i];
+      case PT_INST_MULTILABEL: throw std::logic_error("single-label map for multi-labeled tree/network");
+      case PT_INST_BAD_GRAPH: throw std::logic_error("cannot create tree/network: not a rooted DAG with a single root");
+      case PT_INST_TOO_LARGE: throw EngineError(PT_ERR_UNSUPPORTED, "instance exceeds the limits of the on-chip solver (pt_get_limits)");
+      default: throw EngineError(PT_ERR_UNSUPPORTED, "branching pool exhausted; raise pt_options.pool_slots");
+    }
+  }
+  uint8_t status(size_t i) { if (!done_) run(); return status_.at(i); }
+  const pt_counters& counters() { if (!done_) run(); return counters_; }
+};
+
+template <class Host, class Guest>
+class TreeInNetContainment {
+  Host host_;
+  Guest guest_;
+  bool have_ = false, result_ = false;
+
+ public:
+  TreeInNetContainment(const Host& N, const Guest& T) : host_(N), guest_(T) {}
+  TreeInNetContainment(Host&& N, const Guest& T) : host_(std::move(N)), guest_(T) {}
+  TreeInNetContainment(const Host& N, Guest&& T) : host_(N), guest_(std::move(T)) {}
+  TreeInNetContainment(Host&& N, Guest&& T) : host_(std::move(N)), guest_(std::move(T)) {}
+
+  bool displayed() {
+    if (!have_) { BatchContainment b; b.add(host_, guest_); result_ = b.displayed(0); have_ = true; }
+    return result_;
+  }
+  // utils/containment.hpp:1186-1199: make v the only parent of u
+  void force_parent(const Node u, const Node v) {
+    EdgeVec e;
+    bool found = false;
+    for (const auto& uv : host_.edges()) { if (uv.head() == u) { if (uv.tail() == v) { found = true; e.push_back(uv); } } else e.push_back(uv); }
+    if (!found) throw std::logic_error("force_parent: " + std::to_string(v) + " is not a parent of " + std::to_string(u));
+    host_ = Host(e, host_.labels_ptr(), consecutive_tag(), host_.num_nodes());
+    have_ = false;
+  }
+  const Host& host() const { return host_; }
+  const Guest& guest() const { return guest_; }
+};
+template <class Host, class Guest> TreeInNetContainment(const Host&, const Guest&) -> TreeInNetContainment<Host, Guest>;
+template <class Host, class Guest> TreeInNetContainment(Host&&, Guest&&) -> TreeInNetContainment<std::decay_t<Host>, std::decay_t<Guest>>;
+
+// a tree host is a network without reticulations: same engine (the true-cherry rule alone decides it)
+template <class Host, class Guest>
+class TreeInTreeContainment : public TreeInNetContainment<Host, Guest> {
+ public:
+  using TreeInNetContainment<Host, Guest>::TreeInNetContainment;
+};
+template <class Host, class Guest> TreeInTreeContainment(const Host&, const Guest&) -> TreeInTreeContainment<Host, Guest>;
+template <class Host, class Guest> TreeInTreeContainment(Host&&, Guest&&) -> TreeInTreeContainment<std::decay_t<Host>, std::decay_t<Guest>>;
+
+}  // namespace PT

@@ -98,6 +98,55 @@ void generate_random_binary_edgelist_rl(EdgeContainer& edges, NameContainer& nam
   generate_random_binary_edgelist_trl(edges, names, n - num_retis - num_leaves, num_retis, num_leaves, rng);
 }
 
+
+// utils/generator.hpp:50-92: random (not necessarily binary) tree; leaves are 0..l-1 and named, the root is the LAST node
+template <class EdgeContainer, class NameContainer>
+void generate_random_tree(EdgeContainer& edges, NameContainer& names, uint32_t num_internal, uint32_t num_leaves, SplitMix64& rng) {
+  if (num_leaves == 0) throw std::logic_error("cannot construct tree without leaves");
+  if (num_internal == 0) throw std::logic_error("cannot construct tree without internal nodes");
+  const uint32_t num_nodes = num_leaves + num_internal;
+  if (num_leaves + num_internal - 1 < 2 * num_internal)
+    throw std::logic_error("there is no tree with " + std::to_string(num_internal) + " internal nodes and " + std::to_string(num_leaves) + " leaves");
+  std::vector<uint32_t> free_nodes;
+  for (uint32_t u = 0; u < num_leaves; ++u) { free_nodes.push_back(u); names.emplace((Node)u, sequential_taxon_name::to_string(u)); }
+  for (uint32_t u = num_leaves; u < num_nodes; ++u) {
+    const uint32_t nodes_left = num_nodes - u;
+    const uint32_t max_degree = (uint32_t)free_nodes.size() - (nodes_left - 1);
+    const uint32_t min_degree = (u == num_nodes - 1) ? max_degree : 2;
+    const uint32_t degree = min_degree + rng.die(max_degree - min_degree + 1);
+    for (uint32_t i = 0; i < degree; ++i) {
+      const size_t k = rng.die((uint32_t)free_nodes.size());
+      edges.emplace_back((Node)u, (Node)free_nodes[k]);
+      free_nodes[k] = free_nodes.back(); free_nodes.pop_back();
+    }
+    free_nodes.push_back(u);
+  }
+}
+
+// utils/generator.hpp:97-171 for the case tc -r uses (new_tree_nodes == new_reticulations == num_edges): every new arc joins
+// two fresh nodes that subdivide two distinct random arcs, oriented so that no cycle appears.  n grows by 2 per arc.
+template <class EdgeContainer>
+void add_random_edges(EdgeContainer& edges, size_t& n, uint32_t num_edges, SplitMix64& rng) {
+  if (num_edges == 0) return;
+  if (edges.size() < 2) throw std::logic_error("cannot add edges to a tree/network with less than 2 edges");
+  auto has_path = [&](Node from, Node to) {
+    std::vector<std::vector<Node>> adj(n);
+    for (const auto& e : edges) adj[e.first].push_back(e.second);
+    std::vector<char> seen(n, 0); std::vector<Node> st{from}; seen[from] = 1;
+    while (!st.empty()) { const Node v = st.back(); st.pop_back(); if (v == to) return true; for (Node c : adj[v]) if (!seen[c]) { seen[c] = 1; st.push_back(c); } }
+    return false;
+  };
+  for (uint32_t k = 0; k < num_edges; ++k) {
+    const size_t i = rng.die((uint32_t)edges.size()); size_t j = rng.die((uint32_t)edges.size() - 1); if (j >= i) ++j;
+    const Node u = edges[i].first, v = edges[i].second, x = edges[j].first, y = edges[j].second;
+    Node s = n++, t = n++;
+    edges[i] = {u, s}; edges.emplace_back(s, v);   // subdivide (u,v) with s
+    edges[j] = {x, t}; edges.emplace_back(t, y);   // subdivide (x,y) with t
+    if (has_path(y, u) || y == u) std::swap(s, t);
+    edges.emplace_back(s, t);
+  }
+}
+
 // Tree displayed by a uniform random switching of the network given as an edge list over nodes 0..n-1:
 // keep one in-arc per node, drop unlabelled dangling nodes, suppress in=out=1 nodes, drop an out-degree-1 root.
 // Output: edges of the tree with nodes renumbered 0..nt-1 in preorder (root 0), children shuffled; labels carried over.

@@ -1,0 +1,62 @@
+// tests/cpp/test_facade.cpp -- exercises the C++ facade (phylo_tools_b200/include/pt/) the way code written against the
+// reference's headers would: parse two Newick strings, build MyNet / MyTree like examples/tc.cpp:50-51,110-114, ask
+// TreeInNetContainment / TreeInTreeContainment / LCA.  Needs a GPU; exits 0 on success.
+#include <cassert>
+#include <iostream>
+#include <sstream>
+#include "../../phylo_tools_b200/include/pt/containment.hpp"
+#include "../../phylo_tools_b200/include/pt/io.hpp"
+#include "../../phylo_tools_b200/include/pt/lca.hpp"
+
+using namespace PT;
+using MyTree = ROTree<>;
+using MyNet = CompatibleRWNetwork<MyTree>;
+
+static bool tc(const std::string& host, const std::string& guest) {
+  EdgeVec he, ge; auto hl = std::make_shared<LabelMapDefault>(); auto gl = std::make_shared<LabelMapDefault>();
+  const size_t hn = parse_newick(host, he, hl), gn = parse_newick(guest, ge, gl);
+  MyNet N(he, hl, consecutive_tag(), hn); MyTree T(ge, gl, consecutive_tag(), gn);
+  if (N.is_tree()) { TreeInTreeContainment c(N, T); return c.displayed(); }
+  TreeInNetContainment c(std::move(N), std::move(T));
+  return c.displayed();
+}
+
+int main() {
+  // data/test.nw of the reference: ground truth "not displayed" (the reference itself crashes on it)
+  assert(!tc("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));"));
+  assert(tc("((a,(b)#H1),(#H1,c));", "(a,(b,c));"));
+  assert(tc("((a,(b)#H1),(#H1,c));", "((a,b),c);"));
+  assert(!tc("((a,(b)#H1),(#H1,c));", "((a,c),b);"));
+  assert(tc("((a,b),(c,d));", "((d,c),(b,a));"));
+  assert(!tc("((a,b),(c,d));", "((a,c),(b,d));"));
+  // force_parent (containment.hpp:1186): H1 = node 4 in reader numbering of "((a,(b)#H1),(#H1,c));": edges (1,2)(1,3)... check via parents()
+  {
+    EdgeVec he, ge; LabelMapDefault hl, gl;
+    const size_t hn = parse_newick(std::string("((a,(b)#H1),(#H1,c));"), he, hl), gn = parse_newick(std::string("((a,b),c);"), ge, gl);
+    MyNet N(he, hl, consecutive_tag(), hn); MyTree T(ge, gl, consecutive_tag(), gn);
+    Node reti = NoNode;
+    for (Node v = 0; v < N.num_nodes(); ++v) if (N.is_reti(v)) reti = v;
+    assert(reti != NoNode && N.in_degree(reti) == 2);
+    int shown = 0;
+    for (size_t k = 0; k < 2; ++k) { TreeInNetContainment c(N, T); c.force_parent(reti, N.parents(reti)[k]); shown += c.displayed(); }
+    assert(shown == 1);  // exactly one of the two switchings displays ((a,b),c)
+  }
+  // duplicate labels throw std::logic_error like label_matching.hpp:51-52
+  bool threw = false;
+  try { tc("((a,a),(c,d));", "((a,b),(c,d));"); } catch (const std::logic_error&) { threw = true; }
+  assert(threw);
+  // batch form
+  BatchContainment b;
+  b.add_newick("((a,b),(c,d));", "((a,b),(c,d));");
+  b.add_newick("((a,b),(c,d));", "(((a)#H1,b),(#H1,(c,d)));");  // tree first, network second -> network is the host
+  b.run();
+  assert(b.displayed(0) && b.displayed(1) && b.counters().instances == 2);
+  // LCA: the tree of rmq/lca.cpp:24-43 and its four known answers
+  LCAOracle L(std::vector<int32_t>{3, 3, 3, 8, 5, 7, 7, 8, -1});
+  assert(L.query(8, 8) == 8 && L.query(3, 7) == 8 && L.query(0, 2) == 3 && L.query(4, 6) == 7);
+  MyTree T2 = [] { EdgeVec e; LabelMapDefault l; const size_t n = parse_newick(std::string("((a,b),(c,(d,e)));"), e, l); return MyTree(e, l, consecutive_tag(), n); }();
+  LCAOracle L2(T2);
+  for (Node u = 0; u < T2.num_nodes(); ++u) assert(L2.LCA(u, T2.root()) == T2.root());
+  std::cout << "facade ok\n";
+  return 0;
+}

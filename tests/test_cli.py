@@ -1,0 +1,64 @@
+"""The `tc` / `gen` command-line replacements and the C++ facade: they build on CPU (link test), and on the GPU box the
+CLI protocol of examples/tc.cpp is checked (verdict = last line of stdout, exit codes)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "phylo_tools_b200", "bin")
+FACADE = os.path.join(ROOT, "tests", "cpp", "build", "test_facade")
+
+
+@pytest.fixture(scope="module")
+def tools(pt):
+    if not os.path.exists(os.path.join(BIN, "tc")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "phylo_tools_b200", "csrc"), "tools"])
+    os.makedirs(os.path.dirname(FACADE), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "cpp", "test_facade.cpp")
+    if not os.path.exists(FACADE) or os.path.getmtime(FACADE) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", src, "-o", FACADE, "-L" + os.path.join(ROOT, "phylo_tools_b200"), "-lptgpu",
+                               "-Wl,-rpath," + os.path.join(ROOT, "phylo_tools_b200")])
+    return BIN
+
+
+def test_tools_build_and_usage_errors(tools, tmp_path):
+    r = subprocess.run([os.path.join(tools, "tc"), str(tmp_path / "missing.nw")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot be opened for reading" in r.stderr       # examples/tc.cpp:41-44
+    r = subprocess.run([os.path.join(tools, "tc"), "-r", "0", "5", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot construct tree" in r.stderr               # examples/tc.cpp:31-34
+    r = subprocess.run([os.path.join(tools, "gen"), "-l", "5", "-r", "2", "--with-tree"], capture_output=True, text=True)
+    lines = r.stdout.strip().split("\n")
+    assert r.returncode == 0 and len(lines) == 2 and lines[0].count("#H") == 4 and lines[1].count(",") == 4
+    assert os.path.exists(FACADE)
+
+
+@pytest.mark.gpu
+def test_tc_cli_protocol(tools, tmp_path):
+    tc = os.path.join(tools, "tc")
+    f = tmp_path / "test.nw"
+    f.write_text("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);\n((a,b),(c,d));\n")    # data/test.nw
+    r = subprocess.run([tc, str(f)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().split("\n")[-1] == "not displayed"
+    f.write_text("((a,b),(c,d));\n((a,(b)#H1),(#H1,(c,d)));\n")                # tree first: the network becomes the host
+    r = subprocess.run([tc, "-v", str(f)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().split("\n")[-1] == "displayed"
+    f.write_text("((a,(b)#H1),(#H1,c));\n((a,(b)#H1),(#H1,c));\n")
+    r = subprocess.run([tc, str(f)], capture_output=True, text=True)
+    assert r.stdout.strip().split("\n")[-1] == "sorry, can't check network-network containment yet..."
+    r = subprocess.run([tc, "-r", "30", "60", "10"], capture_output=True, text=True)  # self-test mode: always displayed
+    assert r.returncode == 0 and r.stdout.strip().split("\n")[-1] == "displayed"
+    g = subprocess.run([os.path.join(tools, "gen"), "-l", "40", "-r", "8", "--with-tree", "--seed", "5", str(tmp_path / "g.nw")], capture_output=True, text=True)
+    assert g.returncode == 0
+    r = subprocess.run([tc, str(tmp_path / "g.nw")], capture_output=True, text=True)
+    assert r.stdout.strip().split("\n")[-1] == "displayed"
+    b = tmp_path / "batch.nw"
+    b.write_text("((a,b),(c,d));\n((a,b),(c,d));\n((a,b),(c,d));\n((a,c),(b,d));\n")
+    r = subprocess.run([tc, "--batch", str(b)], capture_output=True, text=True)
+    assert r.stdout.strip().split("\n") == ["displayed", "not displayed"]
+
+
+@pytest.mark.gpu
+def test_cpp_facade(tools):
+    r = subprocess.run([FACADE], capture_output=True, text=True)
+    assert r.returncode == 0 and "facade ok" in r.stdout, r.stderr[-2000:]
