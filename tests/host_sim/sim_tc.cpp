@@ -94,6 +94,25 @@ int main(int argc, char** argv) {
   } else if (!strcmp(argv[1], "file") && argc >= 4) {
     std::ifstream in(argv[2]); std::string a, b; perm = atoi(argv[3]);
     while (std::getline(in, a) && std::getline(in, b)) P.add_newick(a, b);
+  } else if (!strcmp(argv[1], "arrays") && argc >= 4) {
+    // text format, one instance per block: "n m nt" / m lines "tail head" (sorted by tail) / n host labels / nt guest parents / nt guest labels
+    std::ifstream in(argv[2]); perm = atoi(argv[3]);
+    long n, m, nt; Stats S2; std::string out2;
+    while (in >> n >> m >> nt) {
+      Item it; it.n = (int)n; it.m = (int)m; it.nt = (int)nt;
+      it.succ_off.assign(n + 1, 0); it.succ_adj.resize(m); it.hlabel.resize(n); it.tparent.resize(nt); it.tlabel.resize(nt);
+      for (long e = 0; e < m; ++e) { long a, b; in >> a >> b; it.succ_off[a + 1]++; it.succ_adj[e] = (int32_t)b; }
+      for (long v = 0; v < n; ++v) it.succ_off[v + 1] += it.succ_off[v];
+      int maxl = 0;
+      for (auto& x : it.hlabel) { in >> x; maxl = std::max(maxl, x + 1); }
+      for (auto& x : it.tparent) in >> x;
+      for (auto& x : it.tlabel) { in >> x; maxl = std::max(maxl, x + 1); }
+      int st = 0;
+      const int v = solve_instance(it, (int)n, (int)std::max<long>(m, 1), (int)nt, std::max(maxl, 1), perm, S2, &st);
+      out2.push_back(v < 0 ? (char)('A' + st) : (char)('0' + v));
+    }
+    printf("%s\n", out2.c_str());
+    return 0;
   } else return 1;
   Stats S; std::string out;
   for (size_t i = 0; i < P.size(); ++i) {

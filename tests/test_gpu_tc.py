@@ -175,3 +175,30 @@ def test_enum_switchings_matches_oracle_counts(pt, oracle, gold_tc):
             assert sum(parts) == exp_n
         checked += 1
     assert checked >= 100
+
+
+def test_general_dag_hosts(pt, oracle):
+    """junctions, non-binary nodes, multi-parent leaves, unlabelled leaves, labels on internal nodes, unary guest nodes:
+    raw arrays straight through the C-ABI against the exhaustive oracle"""
+    from test_sim import _fuzz_instance
+    rng = np.random.default_rng(77)
+    insts = [_fuzz_instance(rng) for _ in range(3000)]
+    hn, ha, gn = [0], [0], [0]
+    so, sa, hl, gp, gl, truth = [], [], [], [], [], []
+    for n, edges, hlab, tp, tl in insts:
+        off = np.zeros(n + 1, dtype=np.int32)
+        for a, _ in edges:
+            off[a + 1] += 1
+        so.append(np.cumsum(off).astype(np.int32)); sa.append(np.array([b for _, b in edges], dtype=np.int32).reshape(-1))
+        hl.append(hlab); gp.append(tp); gl.append(tl)
+        hn.append(hn[-1] + n); ha.append(ha[-1] + len(edges)); gn.append(gn[-1] + len(tp))
+        te = [(int(tp[i]), i) for i in range(len(tp)) if tp[i] >= 0]
+        truth.append(oracle.tc_bruteforce(edges, n, hlab, te, len(tp), tl)[0])
+    arrays = dict(num_instances=len(insts), host_node_off=np.array(hn, dtype=np.int64), host_arc_off=np.array(ha, dtype=np.int64),
+                  guest_node_off=np.array(gn, dtype=np.int64), host_succ_off=np.concatenate(so), host_succ_adj=np.concatenate(sa),
+                  host_label=np.concatenate(hl).astype(np.int32), guest_parent=np.concatenate(gp).astype(np.int32), guest_label=np.concatenate(gl).astype(np.int32))
+    b = pt.Batch(arrays)   # no maxima hints: the library computes them
+    v, s, c = b.contain()
+    b.free()
+    assert (s == 0).all()
+    assert v.astype(int).tolist() == truth

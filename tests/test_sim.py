@@ -56,3 +56,95 @@ def test_simulated_config2_positives(sim):
     # BASELINE config 2 shape: l=100, r=20; positives are displayed by construction
     got = subprocess.run([sim, "gen", "40", "100", "20", "45568", "0", "0"], capture_output=True, text=True, check=True).stdout.strip()
     assert got == "1" * 40
+
+
+# ---- general DAG hosts: junctions, non-binary nodes, multi-parent leaves, unlabelled leaves, labels on internal nodes -------
+def _fuzz_instance(rng):
+    import numpy as np
+    n = int(rng.integers(2, 15))
+    edges = set()
+    for v in range(1, n):
+        edges.add((int(rng.integers(0, v)), v))
+    for _ in range(int(rng.integers(0, 6))):
+        v = int(rng.integers(1, n)); u = int(rng.integers(0, v))
+        edges.add((u, v))
+    edges = sorted(edges)
+    out = np.zeros(n, dtype=int)
+    for a, _ in edges:
+        out[a] += 1
+    hl = np.full(n, -1, dtype=np.int32)
+    nxt = 0
+    for v in range(n):
+        if out[v] == 0 and rng.random() < 0.85:
+            hl[v] = nxt; nxt += 1
+        elif out[v] > 0 and rng.random() < 0.05:
+            hl[v] = 100 + v                      # label on an internal node: must be ignored
+    # guest: tree displayed by a random switching (plain python), then perturbed
+    par = {}
+    for v in range(1, n):
+        ps = [a for a, b in edges if b == v]
+        par[v] = ps[int(rng.integers(0, len(ps)))]
+    kids = {v: [] for v in range(n)}
+    for v, p in par.items():
+        kids[p].append(v)
+    def build(v):
+        if out[v] == 0:
+            return ("L", int(hl[v])) if hl[v] >= 0 else None
+        ch = [c for c in (build(k) for k in kids[v]) if c is not None]
+        if not ch:
+            return None
+        return ch[0] if len(ch) == 1 else ("N", ch)
+    t = build(0)
+    labels = [int(x) for x in hl if 0 <= x < 100]
+    mode = int(rng.integers(0, 6))
+    tp, tl = [], []
+    def emit(node, parent):
+        i = len(tp); tp.append(parent)
+        if node[0] == "L":
+            tl.append(node[1])
+        else:
+            tl.append(-1)
+            order = list(node[1]); rng.shuffle(order)
+            for c in order:
+                emit(c, i)
+        return i
+    if t is None:
+        tp, tl = [-1], [-1]
+    else:
+        if mode == 5 and rng.random() < 0.5:     # unary root on top + an unlabelled dangling leaf: both must be cleaned away
+            tp.append(-1); tl.append(-1); emit(t, 0); tp.append(0); tl.append(-1)
+        else:
+            emit(t, -1)
+    tl = np.array(tl, dtype=np.int32); tp = np.array(tp, dtype=np.int32)
+    leaves = [i for i in range(len(tl)) if tl[i] >= 0]
+    if mode == 1 and len(leaves) >= 2:           # swap two labels
+        a, b = rng.choice(leaves, 2, replace=False); tl[a], tl[b] = tl[b], tl[a]
+    elif mode == 2 and leaves:                   # guest-only label
+        tl[leaves[0]] = 99
+    elif mode == 3 and len(leaves) >= 3:         # a label only the host has: drop one guest leaf (leaves a unary node behind)
+        tl[leaves[-1]] = -1
+    elif mode == 4 and len(leaves) >= 4:         # rotate three labels
+        a, b, c = rng.choice(leaves, 3, replace=False); tl[a], tl[b], tl[c] = tl[b], tl[c], tl[a]
+    return n, edges, hl, tp, tl
+
+
+def test_simulated_kernel_logic_general_dags(sim, oracle):
+    import numpy as np
+    rng = np.random.default_rng(20261019)
+    insts = [_fuzz_instance(rng) for _ in range(1500)]
+    truth = []
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        for n, edges, hl, tp, tl in insts:
+            te = [(int(tp[i]), i) for i in range(len(tp)) if tp[i] >= 0]
+            truth.append(oracle.tc_bruteforce(edges, n, hl, te, len(tp), tl)[0])
+            f.write("%d %d %d\n" % (n, len(edges), len(tp)))
+            f.write("".join("%d %d\n" % e for e in edges))
+            f.write(" ".join(map(str, hl.tolist())) + "\n" + " ".join(map(str, tp.tolist())) + "\n" + " ".join(map(str, tl.tolist())) + "\n")
+    try:
+        assert min(truth) >= 0 and 0.15 < sum(truth) / len(truth) < 0.9
+        for perm in (0, 1, 9):
+            got = subprocess.run([sim, "arrays", f.name, str(perm)], capture_output=True, text=True, check=True).stdout.strip()
+            bad = [(i, got[i], truth[i]) for i in range(len(truth)) if got[i] != str(truth[i])]
+            assert not bad, (perm, bad[:5], insts[bad[0][0]])
+    finally:
+        os.unlink(f.name)
