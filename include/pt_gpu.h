@@ -143,7 +143,7 @@ typedef enum pt_inst_status {
   PT_INST_OK = 0,
   PT_INST_MULTILABEL = 1,   /* duplicate leaf label: std::logic_error in label_matching.hpp:51-52,61-62 */
   PT_INST_BAD_GRAPH = 2,    /* index out of range, cycle, no/multiple roots (storage_adj_common.hpp:103-109) */
-  PT_INST_TOO_LARGE = 3,    /* exceeds pt_limits for the on-chip solver                                 */
+  PT_INST_TOO_LARGE = 3,    /* pt_options.path = 1 was forced and the instance exceeds pt_limits          */
   PT_INST_POOL_OVERFLOW = 4 /* branching pool exhausted (raise pt_options.pool_slots)                   */
 } pt_inst_status;
 
@@ -165,11 +165,13 @@ typedef struct pt_counters {
 typedef struct pt_options {
   int32_t pool_slots;        /* capacity of the branching pool per round (0 = default)                  */
   int32_t max_rounds;        /* safety bound on branching depth (0 = default 64)                        */
-  int32_t reserved[6];
+  int32_t path;              /* 0 auto; 1 force the shared-memory executor (one warp per instance, int16 ids);
+                                2 force the global-memory executor (one CTA per instance, int32 ids)         */
+  int32_t reserved[5];
 } pt_options;
 
 typedef struct pt_limits {
-  int32_t max_host_nodes, max_host_arcs, max_guest_nodes, max_labels; /* on-chip (shared-memory) solver */
+  int32_t max_host_nodes, max_host_arcs, max_guest_nodes, max_labels; /* shared-memory executor; beyond: global-memory executor */
 } pt_limits;
 int pt_get_limits(pt_limits* out);
 

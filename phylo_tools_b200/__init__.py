@@ -162,7 +162,7 @@ class Batch:
         d = make_desc(arrays, PT_MEM_DEVICE if dev else PT_MEM_HOST)
         _check(_L.pt_batch_create(C.byref(self._h), C.byref(d), stream), "pt_batch_create")
 
-    def contain(self, result_bits=None, status=None, want_counters=True, stream=None, pool_slots=0, max_rounds=0):
+    def contain(self, result_bits=None, status=None, want_counters=True, stream=None, pool_slots=0, max_rounds=0, path=0):
         """returns (verdicts bool[B] or None when device outputs are given, status uint8[B] or None, counters dict or None)"""
         B = self.num_instances
         words = (B + 31) // 32
@@ -170,7 +170,7 @@ class Batch:
         if result_bits is None:
             result_bits = np.zeros(max(words, 1), dtype=np.uint32)
             status = np.zeros(max(B, 1), dtype=np.uint8)
-        opt = Options(pool_slots, max_rounds)
+        opt = Options(pool_slots, max_rounds, path)
         cnt = Counters() if want_counters else None
         _check(_L.pt_batch_contain(self._h, C.byref(opt), _ptr(result_bits), _ptr(status), PT_MEM_DEVICE if dev_out else PT_MEM_HOST,
                                    C.byref(cnt) if cnt is not None else None, stream), "pt_batch_contain")

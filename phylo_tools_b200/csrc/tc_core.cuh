@@ -72,7 +72,7 @@ struct TcStats { unsigned cherries, retcherries, arcs_deleted, passes; };
 
 template <class I>
 struct TcWork {
-  int capN, capM, capNT, capL, W;
+  int capN, capM, capNT, capL, W;  // W = words of the reachable-label signature per node (exact when 32 W >= labels)
   // host network
   I *at, *ah;            // arc tail / head; at < 0 = deleted
   I *ooff, *oarc;        // out CSR over live arcs (arc ids)
@@ -90,8 +90,15 @@ struct TcWork {
   int32_t* sc;           // [0] flag  [1] fail  [2] root  [3] troot  [4] nlabels  [5] best  [6..] scratch
   static constexpr int kScalars = 16;
 
+  // signature words: exact label sets up to kMaxExactWords * 32 labels, hashed (label mod bits) beyond: a hashed set is a
+  // SUPERSET, so "cannot reach" stays certain and the sibling rule stays sound, it only fires less often.  Measured in the
+  // simulator (gen instances l=100..1000): 32-, 64- and 512-bit signatures give the same number of branchings to within
+  // 3 %, because the rule only ever needs to separate a handful of nearby leaves; 64 bits keep the working set small
+  // (shared-memory occupancy) and make the rule independent of the instance size (n = 10^6 needs 8 MB, not 62 GB).
+  static constexpr int kMaxExactWords = 2;
+  PT_HD static int sig_words(int L) { const int w = (L + 31) / 32; return w < 1 ? 1 : (w > kMaxExactWords ? kMaxExactWords : w); }
   PT_HD static size_t bytes(int N, int M, int NT, int L) {
-    const int W = (L + 31) / 32;
+    const int W = sig_words(L);
     size_t b = 0;
     b += (size_t)(2 * M + (N + 1) + M + (N + 1) + M + N + (N + 1)) * sizeof(I);  // at ah ooff oarc ioff iarc hlab lvl
     b = (b + 3) & ~(size_t)3;
@@ -106,7 +113,7 @@ struct TcWork {
     return (b + 15) & ~(size_t)15;
   }
   PT_HD void carve(void* base, int N, int M, int NT, int L) {
-    capN = N; capM = M; capNT = NT; capL = L; W = (L + 31) / 32;
+    capN = N; capM = M; capNT = NT; capL = L; W = sig_words(L);
     char* p = (char*)base;
     auto take = [&](size_t nbytes) { char* r = p; p += nbytes; return r; };
     at = (I*)take((size_t)M * sizeof(I)); ah = (I*)take((size_t)M * sizeof(I));
@@ -138,14 +145,14 @@ struct TcSolver {
 
   enum { F_FLAG = 0, F_FAIL = 1, F_ROOT = 2, F_TROOT = 3, F_NLAB = 4, F_BEST = 5, F_STATUS = 6, F_TMP = 7, F_TMP2 = 8 };
   static constexpr int TDEAD = -2;
-  static constexpr int LVL_INF = 32000;
+  static constexpr int LVL_INF = sizeof(I) == 2 ? 32000 : 0x3fffffff;
 
   // ---- small helpers -----------------------------------------------------------------------------------
   PT_HD int outdeg(int v) const { return w.ooff[v + 1] - w.ooff[v]; }
   PT_HD int indeg(int v) const { return w.ioff[v + 1] - w.ioff[v]; }
   PT_HD int out_arc(int v, int k) const { return w.oarc[w.ooff[v] + k]; }
   PT_HD int in_arc(int v, int k) const { return w.iarc[w.ioff[v] + k]; }
-  PT_HD bool lbit(int v, int lam) const { return (w.lset[v * w.W + (lam >> 5)] >> (lam & 31)) & 1u; }
+  PT_HD bool lbit(int v, int lam) const { const int b = lam % (w.W * 32); return (w.lset[v * w.W + (b >> 5)] >> (b & 31)) & 1u; }
   // read a shared flag uniformly and reset it
   PT_HD int take_flag(int which) {
     ex.sync();
@@ -396,7 +403,7 @@ struct TcSolver {
       PT_NOUNROLL for (int k = 0; k < W; ++k) w.lset[v * W + k] = 0;
       w.hcnt[v] = outdeg(v);
       w.lvl[v] = (I)((outdeg(v) == 0 && (indeg(v) > 0 || w.hlab[v] >= 0)) ? 0 : LVL_INF);
-      if (w.hlab[v] >= 0) w.lset[v * W + (w.hlab[v] >> 5)] = 1u << (w.hlab[v] & 31);
+      if (w.hlab[v] >= 0) { const int b = w.hlab[v] % (W * 32); w.lset[v * W + (b >> 5)] = 1u << (b & 31); }
     }
     ex.sync();
     for (int lev = 0;; ++lev) {
@@ -562,11 +569,17 @@ struct TcSolver {
   // ---- branching: lowest multi-parent node ------------------------------------------------------------------
   PT_NI int pick_branch_node() {
     set_scalar(F_BEST, 0x7fffffff);
-    PT_FOR(v, n) { if (indeg(v) >= 2) ex.atomic_min(&w.sc[F_BEST], ((int)w.lvl[v] << 16) | v); }
+    PT_FOR(v, n) { if (indeg(v) >= 2) ex.atomic_min(&w.sc[F_BEST], (int)w.lvl[v]); }
+    ex.sync();
+    const int lo = w.sc[F_BEST];
+    ex.sync();
+    if (lo == 0x7fffffff) return -1;
+    set_scalar(F_BEST, 0x7fffffff);
+    PT_FOR(v, n) { if (indeg(v) >= 2 && (int)w.lvl[v] == lo) ex.atomic_min(&w.sc[F_BEST], v); }
     ex.sync();
     const int b = w.sc[F_BEST];
     ex.sync();
-    return b == 0x7fffffff ? -1 : (b & 0xffff);
+    return b;
   }
 
   // write the current (clean) state, with only in-arc `keep` of node x kept, as a compact instance.

@@ -97,6 +97,63 @@ struct WarpEx {
   }
 };
 
+// ---- the CTA executor: one thread block per instance, workspace in GLOBAL memory (int32 ids), barrier = __syncthreads ----
+// For instances that do not fit one CTA's shared memory (BASELINE config 4: n = 10^6).  Same solver code, other executor.
+struct CtaEx {
+  int* red;  // 40 ints of shared memory
+  __device__ __forceinline__ int tid() const { return threadIdx.x; }
+  __device__ __forceinline__ int nth() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ int map(int i, int) const { return i; }
+  __device__ __forceinline__ int reduce_or(int v) const {
+    v = (int)__reduce_or_sync(0xffffffffu, (unsigned)v);
+    __syncthreads();
+    if (threadIdx.x == 0) red[32] = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && v) atomicOr(&red[32], v);
+    __syncthreads();
+    return red[32];
+  }
+  __device__ __forceinline__ int reduce_add(int v) const {
+    v = __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if (threadIdx.x == 0) red[33] = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&red[33], v);
+    __syncthreads();
+    return red[33];
+  }
+  __device__ __forceinline__ int atomic_add(int32_t* p, int v) const { return atomicAdd(p, v); }
+  __device__ __forceinline__ int atomic_min(int32_t* p, int v) const { return atomicMin(p, v); }
+  __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
+  __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
+  __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
+  __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
+  // tile-by-tile block scan with a running carry: coalesced, two barriers per tile of blockDim.x elements
+  template <class T>
+  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) const {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    int carry = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      const int v = i < n ? in[i] : 0;
+      int incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      if (lane == 31) red[wid] = incl;
+      __syncthreads();
+      int woff = 0, total = 0;
+      for (int k = 0; k < nw; ++k) { const int t = red[k]; if (k < wid) woff += t; total += t; }
+      if (i < n) out[i] = (T)(carry + woff + incl - v);
+      carry += total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = (T)carry;
+    __syncthreads();
+  }
+};
+
 // where work items come from: the caller's batch (offset tables) or a pool of fixed-stride slots
 struct TcSource {
   int64_t count;            // batch mode: number of instances
@@ -115,7 +172,7 @@ struct TcSink {
 enum { CNT_DISPLAYED = 0, CNT_ITEMS, CNT_BRANCH_ITEMS, CNT_CHERRIES, CNT_RET, CNT_ARCS, CNT_PASSES, CNT_ERRORS, CNT_N };
 
 template <class I>
-__global__ void __launch_bounds__(256) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
+__global__ void __launch_bounds__(512) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
                                                         uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                         uint8_t* __restrict__ branched, int32_t* __restrict__ ticket,
                                                         unsigned long long* __restrict__ counters) {
@@ -196,6 +253,88 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(TcSource src, TcSink sin
   }
 }
 
+// one CTA per work item, workspace in global memory
+__global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, size_t ws_bytes,
+                                                            unsigned char* __restrict__ ws, uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
+                                                            uint8_t* __restrict__ branched, int32_t* __restrict__ ticket, unsigned long long* __restrict__ counters) {
+  using I = int32_t;
+  __shared__ int s_red[40];
+  CtaEx ex{s_red};
+  TcWork<I> w;
+  w.carve(ws + (size_t)blockIdx.x * ws_bytes, capN, capM, capNT, capL);
+  const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
+  unsigned long long c_disp = 0, c_items = 0, c_br = 0, c_ch = 0, c_ret = 0, c_arc = 0, c_pass = 0, c_err = 0;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_red[36] = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int item = s_red[36];
+    if (item >= total) break;
+    TcInst in;
+    int origin;
+    if (src.is_pool) {
+      origin = src.origin[item];
+      if (threadIdx.x == 0) s_red[37] = (int)((*(volatile uint32_t*)&result_bits[origin >> 5] >> (origin & 31)) & 1u);
+      __syncthreads();
+      if (s_red[37]) continue;
+      in.n = src.dims[4 * item]; in.m = src.dims[4 * item + 1]; in.nt = src.dims[4 * item + 2];
+      in.succ_off = src.succ_off + (size_t)item * src.sN1; in.succ_adj = src.succ_adj + (size_t)item * src.sM;
+      in.hlabel = src.hlabel + (size_t)item * src.sN; in.tparent = src.tparent + (size_t)item * src.sNT; in.tlabel = src.tlabel + (size_t)item * src.sNT;
+    } else {
+      origin = item;
+      const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
+      const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
+      in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
+      if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
+      in.succ_off = src.succ_off + hb + item; in.succ_adj = src.succ_adj + ab; in.hlabel = src.hlabel + hb;
+      in.tparent = src.tparent + gb; in.tlabel = src.tlabel + gb;
+    }
+    TcSolver<CtaEx, I> sv(ex, w);
+    int st = 0, x = -1;
+    const int code = sv.solve(in, src.is_pool != 0, &st, &x);
+    ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
+    if (code == TC_DISPLAYED) {
+      if (threadIdx.x == 0) atomicOr(&result_bits[origin >> 5], 1u << (origin & 31));
+      ++c_disp;
+    } else if (code == TC_ERROR) {
+      if (threadIdx.x == 0) status[origin] = (uint8_t)st;
+      ++c_err;
+    } else if (code == TC_BRANCH) {
+      const int d = sv.indeg(x);
+      if (threadIdx.x == 0) s_red[38] = atomicAdd(sink.count, d);
+      __syncthreads();
+      const int base = s_red[38];
+      if (base + d > sink.capacity) {
+        if (threadIdx.x == 0) status[origin] = (uint8_t)TCS_POOL_OVERFLOW;
+      } else {
+        if (threadIdx.x == 0) branched[origin] = 1;
+        c_br += (unsigned long long)d;
+        int32_t* arcs = reinterpret_cast<int32_t*>(w.lset);  // signatures are dead by now; d <= n <= capN * W words
+        for (int k = threadIdx.x; k < d; k += blockDim.x) arcs[k] = sv.in_arc(x, k);
+        __syncthreads();
+        for (int k = 0; k < d; ++k) {
+          const int keep = arcs[k];
+          const size_t slot = (size_t)(base + k);
+          TcEmit out{sink.succ_off + slot * sink.sN1, sink.succ_adj + slot * sink.sM, sink.hlabel + slot * sink.sN,
+                     sink.tparent + slot * sink.sNT, sink.tlabel + slot * sink.sNT, sink.dims + slot * 4};
+          sv.emit_child(x, keep, out);
+          if (threadIdx.x == 0) sink.origin[slot] = origin;
+        }
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (c_disp) atomicAdd(&counters[CNT_DISPLAYED], c_disp);
+    if (c_items) atomicAdd(&counters[CNT_ITEMS], c_items);
+    if (c_br) atomicAdd(&counters[CNT_BRANCH_ITEMS], c_br);
+    if (c_ch) atomicAdd(&counters[CNT_CHERRIES], c_ch);
+    if (c_ret) atomicAdd(&counters[CNT_RET], c_ret);
+    if (c_arc) atomicAdd(&counters[CNT_ARCS], c_arc);
+    if (c_pass) atomicAdd(&counters[CNT_PASSES], c_pass);
+    if (c_err) atomicAdd(&counters[CNT_ERRORS], c_err);
+  }
+}
+
 // per-batch maxima of n, m, nt and label id (for DEVICE input without hints)
 __global__ void tc_maxima_kernel(int64_t B, const int64_t* hnode_off, const int64_t* harc_off, const int64_t* gnode_off,
                                  const int32_t* hlabel, const int32_t* tlabel, int32_t* out4) {
@@ -230,6 +369,7 @@ struct pt_batch {
   // pools (ping-pong)
   int pool_cap = 0;
   int32_t* d_pool[2] = {nullptr, nullptr};
+  unsigned char* d_ws = nullptr; size_t ws_cap = 0;  // global-memory workspaces of the CTA executor
   int64_t last_launches = 0;
   int64_t h2d_bytes = 0;
   static constexpr int kMaxTimedRounds = 16;
@@ -246,7 +386,7 @@ static void batch_release(pt_batch* b) {
     dev_free(b->d_succ_off); dev_free(b->d_succ_adj); dev_free(b->d_hlabel); dev_free(b->d_tparent); dev_free(b->d_tlabel);
   }
   dev_free(b->d_bits); dev_free(b->d_status); dev_free(b->d_branched); dev_free(b->d_ticket); dev_free(b->d_counters);
-  dev_free(b->d_pool[0]); dev_free(b->d_pool[1]);
+  dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); dev_free(b->d_ws);
   for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
   delete b;
 }
@@ -274,7 +414,8 @@ int pt_set_device(int device) {
 
 int pt_get_limits(pt_limits* out) {
   if (!out) return set_error(PT_ERR_INVALID, "pt_get_limits: null argument");
-  // the on-chip solver keeps ids in int16 and the whole instance in the 227 KB of one CTA's shared memory
+  // limits of the shared-memory (warp) executor: ids in int16, whole instance in the 227 KB of one CTA's shared memory.
+  // Larger instances run on the global-memory (CTA) executor with int32 ids, bounded by device memory only.
   out->max_host_nodes = 30000; out->max_host_arcs = 30000; out->max_guest_nodes = 30000; out->max_labels = 30000;
   return PT_OK;
 }
@@ -374,23 +515,43 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   PT_CUDA(cudaMemsetAsync(b->d_counters, 0, CNT_N * sizeof(unsigned long long), s));
   PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 64, s));
   uint64_t rounds = 0;
-  const bool too_large = b->maxN > 30000 || b->maxM > 30000 || b->maxNT > 30000 || b->maxL > 30000;
+  // two executors over the same solver: warps with the instance in shared memory (int16 ids), or one CTA per instance with
+  // the workspace in global memory (int32 ids) when an instance does not fit one CTA's shared memory
+  const int force = opt ? opt->path : 0;
+  const bool fits16 = b->maxN <= 30000 && b->maxM <= 30000 && b->maxNT <= 30000 && b->maxL <= 30000;
   const size_t warp_bytes = TcWork<I>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL);
-  if (B > 0 && (too_large || warp_bytes > (size_t)dp.smem_optin)) {
-    // whole batch exceeds the on-chip solver: flag every instance (a global-memory executor is future work)
-    PT_CUDA(cudaMemsetAsync(stat, PT_INST_TOO_LARGE, (size_t)B, s));
+  const bool use_cta = force == 2 || !fits16 || warp_bytes > (size_t)dp.smem_optin;
+  if (force == 1 && use_cta && B > 0) {
+    PT_CUDA(cudaMemsetAsync(stat, PT_INST_TOO_LARGE, (size_t)B, s));  // caller insisted on the shared-memory path
   } else if (B > 0) {
-    // occupancy: as many warps per SM as shared memory allows, in CTAs of up to 8 warps
-    int warps_per_sm = (int)std::min<size_t>(48, (size_t)dp.smem_optin / warp_bytes);
-    int wpc = std::min(8, warps_per_sm);
-    int ctas_per_sm = std::max(1, warps_per_sm / wpc);
-    while (wpc > 1 && (size_t)ctas_per_sm * ((size_t)wpc * warp_bytes + 1024) > (size_t)228 * 1024) --ctas_per_sm;
-    const size_t smem = (size_t)wpc * warp_bytes;
-    PT_CUDA(cudaFuncSetAttribute(tc_reduce_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int wpc = 1, ctas_per_sm = 1;
+    size_t smem = 0, ws_bytes = 0;
+    int cta_grid_cap = 0;
+    if (!use_cta) {
+      // occupancy: as many warps per SM as shared memory (warp_bytes each) and the register file (launch bound 512 threads
+      // -> at most 128 registers/thread -> 16 warps) allow, in one CTA per SM
+      int warps_per_sm = (int)std::min<size_t>(16, ((size_t)dp.smem_optin) / warp_bytes);
+      wpc = std::max(warps_per_sm, 1);
+      smem = (size_t)wpc * warp_bytes;
+      PT_CUDA(cudaFuncSetAttribute(tc_reduce_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+      ws_bytes = (TcWork<int32_t>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL) + 255) & ~(size_t)255;
+      size_t free_b = 0, total_b = 0;
+      PT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const size_t budget = free_b / 3;
+      cta_grid_cap = (int)std::min<size_t>((size_t)dp.sms * 2, std::max<size_t>(1, budget / ws_bytes));
+      cta_grid_cap = (int)std::min<int64_t>(cta_grid_cap, B);
+      if (b->ws_cap < (size_t)cta_grid_cap * ws_bytes) {
+        dev_free(b->d_ws); b->d_ws = nullptr; b->ws_cap = 0;
+        if (int rc2 = dev_alloc((void**)&b->d_ws, (size_t)cta_grid_cap * ws_bytes)) return rc2;
+        b->ws_cap = (size_t)cta_grid_cap * ws_bytes;
+      }
+    }
     // pool
-    int want = opt && opt->pool_slots > 0 ? opt->pool_slots : (int)std::min<int64_t>(std::max<int64_t>(8192, B), 1 << 22);
     const int sN1 = b->maxN + 1, sM = std::max(1, (int)b->maxM), sN = b->maxN, sNT = b->maxNT;
     const size_t slot_elems = (size_t)sN1 + sM + sN + 2 * (size_t)sNT + 4 + 1;
+    int want = opt && opt->pool_slots > 0 ? opt->pool_slots : (int)std::min<int64_t>(std::max<int64_t>(8192, B), 1 << 22);
+    if (!(opt && opt->pool_slots > 0)) want = (int)std::max<size_t>(16, std::min<size_t>((size_t)want, ((size_t)4 << 30) / (slot_elems * 4)));  // <= 4 GB per pool
     if (b->pool_cap < want) {
       dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); b->d_pool[0] = b->d_pool[1] = nullptr; b->pool_cap = 0;
       for (int k = 0; k < 2; ++k) if (int rc2 = dev_alloc((void**)&b->d_pool[k], slot_elems * (size_t)want * 4)) return rc2;
@@ -412,16 +573,19 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     for (int round = 0; round < max_rounds && items > 0; ++round) {
       const int k = round & 1;
       TcSink sink = sink_of(k);
-      const int64_t warps_needed = items;
-      int grid = (int)std::min<int64_t>((int64_t)dp.sms * ctas_per_sm, (warps_needed + wpc - 1) / wpc);
+      int grid = use_cta ? (int)std::min<int64_t>(cta_grid_cap, items) : (int)std::min<int64_t>((int64_t)dp.sms * ctas_per_sm, (items + wpc - 1) / wpc);
       grid = std::max(grid, 1);
       const bool timed = round < pt_batch::kMaxTimedRounds;
       if (timed) {
         for (int j = 0; j < 2; ++j) if (!b->ev[2 * round + j]) PT_CUDA(cudaEventCreate(&b->ev[2 * round + j]));
         PT_CUDA(cudaEventRecord(b->ev[2 * round], s));
       }
-      tc_reduce_kernel<I><<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched,
-                                                       b->d_ticket, b->d_counters);
+      if (use_cta)
+        tc_reduce_cta_kernel<<<grid, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits, stat, b->d_branched, b->d_ticket,
+                                                  b->d_counters);
+      else
+        tc_reduce_kernel<I><<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched,
+                                                         b->d_ticket, b->d_counters);
       PT_CUDA(cudaGetLastError());
       if (timed) { PT_CUDA(cudaEventRecord(b->ev[2 * round + 1], s)); b->timed_rounds = round + 1; }
       ++b->last_launches; ++rounds;

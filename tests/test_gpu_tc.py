@@ -202,3 +202,49 @@ def test_general_dag_hosts(pt, oracle):
     b.free()
     assert (s == 0).all()
     assert v.astype(int).tolist() == truth
+
+
+def test_global_memory_executor_on_golden_instances(pt, gold_tc):
+    """the CTA / global-memory executor (int32 ids, used for instances beyond shared memory) forced onto the pinned small
+    instances: same solver code, other executor, same verdicts"""
+    items = gold_tc["items"]
+    p = pt.Packer()
+    for it in items:
+        p.add_newick(it["host"], it["guest"])
+    b = pt.Batch(p.arrays())
+    v, s, c = b.contain(path=2)
+    b.free()
+    assert (s == 0).all()
+    assert [int(x) for x in v] == [it["truth"] for it in items]
+
+
+def test_executors_agree_on_mid_size(pt):
+    p = pt.Packer()
+    for kind in (0, 1, 2):
+        p.add_generated(300, 300, 60, 4000 + kind, kind)
+    b = pt.Batch(p.arrays())
+    v1, s1, c1 = b.contain(path=1)
+    v2, s2, c2 = b.contain(path=2)
+    b.free()
+    assert (s1 == 0).all() and (s2 == 0).all()
+    assert (v1 == v2).all() and v1[:300].all()
+    assert c1["work_items"] == c2["work_items"] and c1["cherry_reductions"] == c2["cherry_reductions"]
+
+
+def test_instances_beyond_shared_memory(pt):
+    """n = 6 599 host nodes (l=3000, r=300) does not fit a CTA's shared memory: the global-memory executor takes over
+    automatically; positives are displayed by construction, a guest with a foreign label is not"""
+    p = pt.Packer()
+    p.add_generated(24, 3000, 300, 99, 0)
+    a = p.arrays()
+    gl = a["guest_label"]
+    last = int(a["guest_node_off"][23])
+    leaf = last + int(np.where(gl[last:] >= 0)[0][0])
+    gl[leaf] = int(a["max_labels"])        # instance 23: a label the host does not have
+    b = pt.Batch(a)
+    v, s, c = b.contain()
+    b.free()
+    assert (s == 0).all()
+    assert v[:23].all() and not v[23]
+    with pytest.raises(AssertionError):
+        assert (pt.Batch(a).contain(path=1)[1] == 0).all()   # forcing the shared-memory path reports PT_INST_TOO_LARGE
