@@ -241,6 +241,7 @@ def test_instances_beyond_shared_memory(pt):
     last = int(a["guest_node_off"][23])
     leaf = last + int(np.where(gl[last:] >= 0)[0][0])
     gl[leaf] = int(a["max_labels"])        # instance 23: a label the host does not have
+    a["max_labels"] += 1
     b = pt.Batch(a)
     v, s, c = b.contain()
     b.free()
