@@ -128,7 +128,7 @@ class Packer:
         return int(self.desc().num_instances)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _L is not None:
             _L.pt_packer_free(self._h)
             self._h = None
 
@@ -191,7 +191,7 @@ class Batch:
         return int(_L.pt_batch_h2d_bytes(self._h))
 
     def free(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _L is not None:
             _L.pt_batch_free(self._h)
             self._h = None
 
@@ -245,7 +245,7 @@ class Lca:
         return d, p
 
     def free(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _L is not None:
             _L.pt_lca_free(self._h)
             self._h = None
 
@@ -268,7 +268,7 @@ class Rmq:
         return out
 
     def free(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _L is not None:
             _L.pt_rmq_free(self._h)
             self._h = None
 
