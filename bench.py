@@ -216,6 +216,51 @@ def lca_leg(pt, torch, leaves, queries, peak):
                          "model": "40 B/query (SURVEY 8(d)); physical floor of this layout is 2 x 32 B random sectors + 12 B streamed = 76 B/query"}}
 
 
+def config4_leg(pt, torch, count):
+    """BASELINE configs[3]: large networks n = 10^6, r = 10^3 (global-memory executor, one CTA per instance)"""
+    import numpy as np
+    leaves, retis = 499_001, 1000
+    t0 = time.perf_counter()
+    p = pt.Packer()
+    p.add_generated(count, leaves, retis, SEED + 4, 0)
+    a = p.arrays()
+    gen_s = time.perf_counter() - t0
+    dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+    bits = torch.zeros((count + 31) // 32, dtype=torch.int32, device="cuda")
+    stat = torch.zeros(count, dtype=torch.uint8, device="cuda")
+    b = pt.Batch(dev)
+    b.contain(result_bits=bits, status=stat, want_counters=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, _, c = b.contain(result_bits=bits, status=stat, want_counters=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    b.free()
+    nbytes = sum(int(dev[k].numel()) * dev[k].element_size() for k in ("host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"))
+    return {"workload": "%d gen networks n=%d r=%d with a displayed tree each (BASELINE configs[3], one GPU's share)" % (count, 2 * retis + 2 * leaves - 1, retis),
+            "instances_per_s": count / (ms / 1000.0), "ms": ms, "displayed": c["displayed"], "errors": c["errors"], "work_items": c["work_items"],
+            "rule_passes": c["rule_passes"], "input_bytes": nbytes, "host_generation_s": gen_s,
+            "note": "one CTA per instance, workspace in global memory; the reference cannot run this size (extrapolated 3e5 s per instance, BASELINE.md)"}
+
+
+def config5_leg(pt, retis=22, leaves=28):
+    """BASELINE configs[4]: exhaustive 2^r switching enumeration of one general network (guest = random tree: not displayed,
+    so the whole index space is visited)"""
+    p = pt.Packer()
+    p.add_generated(1, leaves, retis, SEED + 5, 2)
+    a = p.arrays()
+    args = (a["host_succ_off"], a["host_succ_adj"], a["host_label"], a["guest_parent"], a["guest_label"])
+    pt.enum_switchings(*args, begin=0, end=1 << 16)  # warm-up
+    t0 = time.perf_counter()
+    tot, nd, first = pt.enum_switchings(*args)
+    dt = time.perf_counter() - t0
+    return {"workload": "exhaustive switching enumeration, gen network l=%d r=%d, random guest tree (BASELINE configs[4])" % (leaves, retis),
+            "switchings": tot, "displaying": nd, "seconds": dt, "switchings_per_s": tot / dt, "host_nodes": int(a["host_node_off"][1]),
+            "note": "wall time of pt_enum_switchings incl. upload; bound by integer ALU + L1-resident accumulators, not HBM"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,6 +271,9 @@ def main():
     ap.add_argument("--lca-leaves", type=int, default=10_000_000)
     ap.add_argument("--lca-queries", type=int, default=100_000_000)
     ap.add_argument("--no-lca", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--config4-instances", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-instances-per-core", type=int, default=100)
     args = ap.parse_args()
@@ -373,6 +421,16 @@ def main():
             out["lca"] = lca_leg(pt, torch, args.lca_leaves, args.lca_queries, peak)
         except Exception as ex:  # the secondary leg must not take the headline line down
             out["lca"] = {"error": repr(ex)}
+    if rank == 0 and not args.no_config4:
+        try:
+            out["config4"] = config4_leg(pt, torch, args.config4_instances)
+        except Exception as ex:
+            out["config4"] = {"error": repr(ex)}
+    if rank == 0 and not args.no_config5:
+        try:
+            out["config5"] = config5_leg(pt)
+        except Exception as ex:
+            out["config5"] = {"error": repr(ex)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
