@@ -399,28 +399,38 @@ struct TcSolver {
   // returns false if some live node was never reached (cycle)
   PT_NI bool wavefront() {
     const int W = w.W;
+    // Kahn order from the leaves with a FIFO in hscr: total work O(n + m) instead of one scan of all nodes per level.
+    // Nodes enter the queue in non-decreasing height, so the child that releases a parent is one of its tallest children.
+    set_scalar(F_TMP, 0);  // queue tail
     PT_FOR(v, n) {
       PT_NOUNROLL for (int k = 0; k < W; ++k) w.lset[v * W + k] = 0;
       w.hcnt[v] = outdeg(v);
-      w.lvl[v] = (I)((outdeg(v) == 0 && (indeg(v) > 0 || w.hlab[v] >= 0)) ? 0 : LVL_INF);
+      w.lvl[v] = (I)LVL_INF;
       if (w.hlab[v] >= 0) { const int b = w.hlab[v] % (W * 32); w.lset[v * W + (b >> 5)] = 1u << (b & 31); }
+      if (outdeg(v) == 0 && (indeg(v) > 0 || w.hlab[v] >= 0)) { w.lvl[v] = (I)0; w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = v; }
     }
     ex.sync();
-    for (int lev = 0;; ++lev) {
-      PT_FOR(v, n) {
-        if (w.lvl[v] == lev) {
-          w.sc[F_FLAG] = 1;
-          PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) {
-            const int p = w.at[in_arc(v, k)];
-            PT_NOUNROLL for (int j = 0; j < W; ++j) { const uint32_t b = w.lset[v * W + j]; if (b) ex.atomic_or(&w.lset[p * W + j], b); }
-            if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.lvl[p] = (I)(lev + 1);
-          }
+    int head = 0;
+    for (;;) {
+      const int tail = w.sc[F_TMP];
+      ex.sync();  // everybody has read the tail before anybody appends
+      if (head >= tail) break;
+      const int cnt = tail - head;
+      PT_FOR(i, cnt) {
+        const int v = w.hscr[head + i], lv = w.lvl[v];
+        PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) {
+          const int p = w.at[in_arc(v, k)];
+          PT_NOUNROLL for (int j = 0; j < W; ++j) { const uint32_t b = w.lset[v * W + j]; if (b) ex.atomic_or(&w.lset[p * W + j], b); }
+          if (ex.atomic_add(&w.hcnt[p], -1) == 1) { w.lvl[p] = (I)(lv + 1); w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = p; }
         }
       }
-      if (!take_flag(F_FLAG)) break;
+      head = tail;
+      ex.sync();
     }
-    PT_FOR(v, n) { if (outdeg(v) > 0 && w.lvl[v] == LVL_INF) w.sc[F_FLAG] = 1; }
-    return !take_flag(F_FLAG);
+    set_scalar(F_TMP, 0);
+    int bad = 0;
+    PT_FOR(v, n) { if (outdeg(v) > 0 && w.lvl[v] == LVL_INF) bad = 1; }
+    return !ex.reduce_or(bad);
   }
 
   // ---- TC: true (multi-)cherries --------------------------------------------------------------------------
@@ -428,8 +438,15 @@ struct TcSolver {
   // parents, none of which a collapse changes for nodes that are still internal, so it may be repeated without
   // rebuilding the CSR (solve() loops it until nothing collapses).
   PT_NI int rule_true_cherry() {
-    PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = -1; }
-    PT_FOR(t, nt) { w.tmin[t] = 0x7fffffff; }
+    // every pass runs over the LABELS (live leaves) only; per-node scratch is reset just for the parents of leaves
+    PT_FOR(l, L) {
+      const int h = w.l2h[l];
+      if (h >= 0) {
+        if (indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; w.hcnt[q] = 0; w.haux[q] = -1; }
+        const int p = w.tpar[w.l2t[l]];
+        if (p >= 0) w.tmin[p] = 0x7fffffff;
+      }
+    }
     ex.sync();
     PT_FOR(l, L) {
       const int h = w.l2h[l];
@@ -454,7 +471,10 @@ struct TcSolver {
       }
     }
     if (!ex.reduce_or(any)) return 0;
-    PT_FOR(q, n) { if (w.haux[q] >= 0 && w.tdeg[w.haux[q]] != outdeg(q)) fail = 1; }
+    PT_FOR(l, L) {
+      const int h = w.l2h[l];
+      if (h >= 0 && indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (w.haux[q] >= 0 && w.tdeg[w.haux[q]] != outdeg(q)) fail = 1; }
+    }
     if (ex.reduce_or(fail)) { set_scalar(F_FAIL, 1); return -1; }
     int collapsed = 0;
     PT_FOR(l, L) {
@@ -621,25 +641,31 @@ struct TcSolver {
   // Kahn peel from the leaves: every node must be reached, exactly one node has no in-arc (the reference throws
   // std::logic_error for several roots, utils/storage_adj_common.hpp:103-109; a cycle would hang its DFS)
   PT_NI bool check_dag(bool trusted) {
-    PT_FOR(v, n) { w.hcnt[v] = outdeg(v); w.lvl[v] = (I)(outdeg(v) == 0 ? 0 : LVL_INF); if (indeg(v) == 0) { ex.atomic_add(&w.sc[F_TMP], 1); w.sc[F_ROOT] = v; } }
-    ex.sync();
-    const int nroots = w.sc[F_TMP];
-    ex.sync();
+    int roots = 0;
     set_scalar(F_TMP, 0);
-    if (n > 0 && nroots != 1) return false;
-    if (trusted) return true;
-    for (int lev = 0;; ++lev) {
-      PT_FOR(v, n) {
-        if (w.lvl[v] == lev) {
-          w.sc[F_FLAG] = 1;
-          PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.lvl[p] = (I)(lev + 1); }
-        }
-      }
-      if (!take_flag(F_FLAG)) break;
-      if (lev > n) return false;
+    PT_FOR(v, n) {
+      w.hcnt[v] = outdeg(v);
+      if (indeg(v) == 0) { ++roots; w.sc[F_ROOT] = v; }
+      if (!trusted && outdeg(v) == 0) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = v;
     }
-    PT_FOR(v, n) { if (w.lvl[v] == LVL_INF) w.sc[F_FLAG] = 1; }
-    return !take_flag(F_FLAG);
+    const int nroots = ex.reduce_add(roots);
+    if (n > 0 && nroots != 1) { set_scalar(F_TMP, 0); return false; }
+    if (trusted) { set_scalar(F_TMP, 0); return true; }
+    int head = 0;
+    for (;;) {
+      const int tail = w.sc[F_TMP];
+      ex.sync();
+      if (head >= tail) break;
+      const int cnt = tail - head;
+      PT_FOR(i, cnt) {
+        const int v = w.hscr[head + i];
+        PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = p; }
+      }
+      head = tail;
+      ex.sync();
+    }
+    set_scalar(F_TMP, 0);
+    return head == n;  // every node was released exactly once <=> no cycle
   }
 
   // ---- the rule loop (apply_rules, containment.hpp:1054-1083) -----------------------------------------------
