@@ -154,10 +154,11 @@ struct TcSolver {
   PT_HD int in_arc(int v, int k) const { return w.iarc[w.ioff[v] + k]; }
   PT_HD bool lbit(int v, int lam) const { const int b = lam % (w.W * 32); return (w.lset[v * w.W + (b >> 5)] >> (b & 31)) & 1u; }
   // read a shared flag uniformly and reset it
+  // A loop / branch decision must be the SAME value in every thread of the group.  ex.uniform() has one thread read the
+  // scalar and broadcasts it (shuffle / shared memory), so the decision cannot diverge even where the workspace lives in
+  // global memory and threads could otherwise observe it through differently aged cache lines.
   PT_HD int take_flag(int which) {
-    ex.sync();
-    const int v = w.sc[which];
-    ex.sync();
+    const int v = ex.uniform(&w.sc[which]);
     if (ex.tid() == 0) w.sc[which] = 0;
     ex.sync();
     return v;
@@ -203,14 +204,11 @@ struct TcSolver {
       const int s = take_flag(F_STATUS);
       if (s) return s;
     }
-    L = w.sc[F_NLAB];
-    ex.sync();
+    L = ex.uniform(&w.sc[F_NLAB]);
     PT_FOR(l, L) { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
     // guest: child counts, exactly one root, no cycles
     PT_FOR(t, nt) { if (w.tpar[t] >= 0) ex.atomic_add(&w.tdeg[w.tpar[t]], 1); else ex.atomic_add(&w.sc[F_TMP], 1); }
-    ex.sync();
-    if (nt > 0 && w.sc[F_TMP] != 1) return TCS_BAD_GRAPH;
-    ex.sync();
+    if (nt > 0 && ex.uniform(&w.sc[F_TMP]) != 1) return TCS_BAD_GRAPH;
     PT_FOR(t, nt) {
       int x = t, steps = 0;
       while (w.tpar[x] >= 0 && steps <= nt) { x = w.tpar[x]; ++steps; }
@@ -309,7 +307,7 @@ struct TcSolver {
         dag_state = 1;
         if (!ok) { *status = TCS_BAD_GRAPH; return; }
       }
-      const int root = w.sc[F_ROOT];
+      const int root = ex.uniform(&w.sc[F_ROOT]);
       int need = 0;
       PT_FOR(v, n) {
         const int od = outdeg(v), id = indeg(v);
@@ -412,8 +410,7 @@ struct TcSolver {
     ex.sync();
     int head = 0;
     for (;;) {
-      const int tail = w.sc[F_TMP];
-      ex.sync();  // everybody has read the tail before anybody appends
+      const int tail = ex.uniform(&w.sc[F_TMP]);  // (ends with a barrier: everybody has the tail before anybody appends)
       if (head >= tail) break;
       const int cnt = tail - head;
       PT_FOR(i, cnt) {
@@ -578,8 +575,7 @@ struct TcSolver {
         }
       }
     }
-    ex.sync();
-    if (w.sc[F_FAIL]) return -1;
+    if (ex.uniform(&w.sc[F_FAIL])) return -1;
     st.arcs_deleted += (unsigned)w.sc[F_TMP2];
     ex.sync();
     set_scalar(F_TMP2, 0);
@@ -590,22 +586,18 @@ struct TcSolver {
   PT_NI int pick_branch_node() {
     set_scalar(F_BEST, 0x7fffffff);
     PT_FOR(v, n) { if (indeg(v) >= 2) ex.atomic_min(&w.sc[F_BEST], (int)w.lvl[v]); }
-    ex.sync();
-    const int lo = w.sc[F_BEST];
-    ex.sync();
+    const int lo = ex.uniform(&w.sc[F_BEST]);
     if (lo == 0x7fffffff) return -1;
     set_scalar(F_BEST, 0x7fffffff);
     PT_FOR(v, n) { if (indeg(v) >= 2 && (int)w.lvl[v] == lo) ex.atomic_min(&w.sc[F_BEST], v); }
-    ex.sync();
-    const int b = w.sc[F_BEST];
-    ex.sync();
+    const int b = ex.uniform(&w.sc[F_BEST]);
     return b;
   }
 
   // write the current (clean) state, with only in-arc `keep` of node x kept, as a compact instance.
   // Label ids are kept (no renumbering), so L and the bitset width stay those of the parent.
   PT_NI void emit_child(int x, int keep, const TcEmit& out) {
-    const int root = w.sc[F_ROOT];
+    const int root = ex.uniform(&w.sc[F_ROOT]);
     // live host nodes (root, or any live in-arc) -> new ids by a scan of the flags (lvl is free after pick_branch_node)
     PT_FOR(v, n + 1) {
       const int live = (v < n && (v == root || indeg(v) > 0)) ? 1 : 0;
@@ -653,8 +645,7 @@ struct TcSolver {
     if (trusted) { set_scalar(F_TMP, 0); return true; }
     int head = 0;
     for (;;) {
-      const int tail = w.sc[F_TMP];
-      ex.sync();
+      const int tail = ex.uniform(&w.sc[F_TMP]);
       if (head >= tail) break;
       const int cnt = tail - head;
       PT_FOR(i, cnt) {
@@ -674,14 +665,14 @@ struct TcSolver {
     *status = TCS_OK; *branch_node = -1;
     int s = load(in);
     if (s != TCS_OK) { *status = s; return TC_ERROR; }
-    const int missing = w.sc[F_FAIL];  // a guest label without a host leaf; reported after the input has been validated
+    const int missing = ex.uniform(&w.sc[F_FAIL]);  // a guest label without a host leaf; reported after the input has been validated
     clean_guest();
     int dag_state = trusted ? 2 : 0;
     for (;;) {
       ++st.passes;
       clean_host(dag_state, status);
       if (*status != TCS_OK) return TC_ERROR;
-      if (missing || w.sc[F_FAIL]) return TC_NOT;
+      if (missing || ex.uniform(&w.sc[F_FAIL])) return TC_NOT;
       if (count_labels() <= 2) return TC_DISPLAYED;  // containment.hpp:1061,1208
       int r, collapsed = 0;
       for (;;) { r = rule_true_cherry(); if (r <= 0) break; collapsed = 1; }  // pendant subtrees collapse level by level, no CSR rebuild

@@ -68,6 +68,7 @@ struct WarpEx {
   __device__ __forceinline__ int nth() const { return 32; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ int map(int i, int) const { return i; }
+  __device__ __forceinline__ int uniform(const int32_t* p) const { __syncwarp(); int v = 0; if (lane == 0) v = *(const volatile int32_t*)p; v = __shfl_sync(0xffffffffu, v, 0); __syncwarp(); return v; }
   __device__ __forceinline__ int reduce_or(int v) const { return (int)__reduce_or_sync(0xffffffffu, (unsigned)v); }
   __device__ __forceinline__ int reduce_add(int v) const { return __reduce_add_sync(0xffffffffu, v); }
   __device__ __forceinline__ int atomic_add(int32_t* p, int v) const { return atomicAdd(p, v); }
@@ -105,6 +106,14 @@ struct CtaEx {
   __device__ __forceinline__ int nth() const { return blockDim.x; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
   __device__ __forceinline__ int map(int i, int) const { return i; }
+  __device__ __forceinline__ int uniform(const int32_t* p) const {
+    __syncthreads();
+    if (threadIdx.x == 0) red[34] = *(const volatile int32_t*)p;
+    __syncthreads();
+    const int v = red[34];
+    __syncthreads();
+    return v;
+  }
   __device__ __forceinline__ int reduce_or(int v) const {
     v = (int)__reduce_or_sync(0xffffffffu, (unsigned)v);
     __syncthreads();

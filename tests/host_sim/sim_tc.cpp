@@ -34,6 +34,7 @@ struct HostEx {
     const int b = (int)((unsigned)perm * 40503u % (unsigned)n);
     return (int)(((long long)a * i + b) % n);
   }
+  int uniform(const int32_t* p) const { return *p; }
   int reduce_or(int v) const { return v; }
   int reduce_add(int v) const { return v; }
   template <class T> T atomic_add(T* p, T v) const { T o = *p; *p = (T)(o + v); return o; }

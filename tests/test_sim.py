@@ -148,3 +148,34 @@ def test_simulated_kernel_logic_general_dags(sim, oracle):
             assert not bad, (perm, bad[:5], insts[bad[0][0]])
     finally:
         os.unlink(f.name)
+
+
+# ---- multi-threaded simulator: real barriers and atomics (what the warp / CTA executors do) -------------------------------
+SIM_MT_SRC = os.path.join(ROOT, "tests", "host_sim", "sim_tc_mt.cpp")
+SIM_MT_BIN = os.path.join(ROOT, "tests", "host_sim", "build", "sim_tc_mt")
+
+
+@pytest.fixture(scope="module")
+def sim_mt():
+    os.makedirs(os.path.dirname(SIM_MT_BIN), exist_ok=True)
+    deps = [SIM_MT_SRC, os.path.join(ROOT, "phylo_tools_b200", "csrc", "tc_core.cuh")]
+    if not os.path.exists(SIM_MT_BIN) or any(os.path.getmtime(d) > os.path.getmtime(SIM_MT_BIN) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-pthread", SIM_MT_SRC, "-o", SIM_MT_BIN])
+    return SIM_MT_BIN
+
+
+@pytest.mark.parametrize("threads,int32", [(3, 0), (8, 1)])
+def test_group_execution_with_real_barriers(sim_mt, gold_tc, threads, int32):
+    """T threads run the solver SPMD over one shared workspace; a barrier not reached by every thread deadlocks (the
+    simulator aborts after 20 s), non-uniform return codes abort, verdicts must equal the pinned truth"""
+    items = gold_tc["items"][:300]
+    with tempfile.NamedTemporaryFile("w", suffix=".nw", delete=False) as f:
+        for it in items:
+            f.write(it["host"] + "\n" + it["guest"] + "\n")
+    try:
+        r = subprocess.run([sim_mt, "file", f.name, str(threads), str(int32)], capture_output=True, text=True, timeout=600)
+    finally:
+        os.unlink(f.name)
+    assert r.returncode == 0, r.stderr[-500:]
+    out = r.stdout.strip()
+    assert [c for c in out] == [str(it["truth"]) for it in items]
