@@ -168,6 +168,7 @@ struct TcSolver {
   // ---- load + validate ---------------------------------------------------------------------------------
   // returns TCS_* ; sets up arcs, labels, guest arrays.  Leaves w.sc[F_FAIL]=1 if a guest label is missing in the host.
   PT_NI int load(const TcInst& in) {
+    ex.phase = 1;
     n = in.n; m = in.m; nt = in.nt;
     if (n > w.capN || m > w.capM || nt > w.capNT || n < 0 || m < 0 || nt < 0) return TCS_TOO_LARGE;
     if (ex.tid() == 0) { PT_NOUNROLL for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
@@ -245,6 +246,7 @@ struct TcSolver {
 
   // ---- guest clean-up: drop unlabelled leaves, suppress unary nodes --------------------------------------
   PT_NI void clean_guest() {
+    ex.phase = 2;
     for (;;) {
       PT_FOR(t, nt) {
         if (w.tpar[t] != TDEAD && w.tdeg[t] == 0 && w.tlab[t] < 0) {
@@ -273,6 +275,7 @@ struct TcSolver {
 
   // ---- host CSR over live arcs ---------------------------------------------------------------------------
   PT_NI void csr() {
+    ex.phase = 3;
     PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = 0; }
     ex.sync();
     PT_FOR(e, m) { if (w.at[e] >= 0) { ex.atomic_add(&w.hcnt[w.at[e]], 1); ex.atomic_add(&w.haux[w.ah[e]], 1); } }
@@ -396,6 +399,7 @@ struct TcSolver {
   // ---- wavefront over topological levels: heights and reachable-label bitsets -----------------------------
   // returns false if some live node was never reached (cycle)
   PT_NI bool wavefront() {
+    ex.phase = 6;
     const int W = w.W;
     // Kahn order from the leaves with a FIFO in hscr: total work O(n + m) instead of one scan of all nodes per level.
     // Nodes enter the queue in non-decreasing height, so the child that releases a parent is one of its tallest children.
@@ -435,6 +439,7 @@ struct TcSolver {
   // parents, none of which a collapse changes for nodes that are still internal, so it may be repeated without
   // rebuilding the CSR (solve() loops it until nothing collapses).
   PT_NI int rule_true_cherry() {
+    ex.phase = 7;
     // every pass runs over the LABELS (live leaves) only; per-node scratch is reset just for the parents of leaves
     PT_FOR(l, L) {
       const int h = w.l2h[l];
@@ -497,6 +502,7 @@ struct TcSolver {
 
   // ---- guest cherries with exactly two leaves: tmin/tmax = their labels, tleaf = 2 ---------------------------
   PT_NI void guest_cherries() {
+    ex.phase = 8;
     PT_FOR(t, nt) { w.tleaf[t] = 0; w.tmin[t] = 0x7fffffff; w.tmax[t] = -1; }
     ex.sync();
     PT_FOR(l, L) {
@@ -509,6 +515,7 @@ struct TcSolver {
 
   // ---- RC: reticulated cherries ---------------------------------------------------------------------------
   PT_NI int rule_ret_cherry() {
+    ex.phase = 9;
     PT_FOR(p, nt) {
       if (is_bin_cherry(p)) {
         PT_NOUNROLL for (int side = 0; side < 2; ++side) {
@@ -552,6 +559,7 @@ struct TcSolver {
     if (w.haux[c] != want) { w.haux[c] = want; w.sc[F_TMP] = 1; }
   }
   PT_NI int rule_sibling() {
+    ex.phase = 10;
     PT_FOR(v, n + 1) { w.haux[v] = -1; w.hcnt[v] = 0; }
     ex.sync();
     PT_FOR(p, nt) {
@@ -584,6 +592,7 @@ struct TcSolver {
 
   // ---- branching: lowest multi-parent node ------------------------------------------------------------------
   PT_NI int pick_branch_node() {
+    ex.phase = 11;
     set_scalar(F_BEST, 0x7fffffff);
     PT_FOR(v, n) { if (indeg(v) >= 2) ex.atomic_min(&w.sc[F_BEST], (int)w.lvl[v]); }
     const int lo = ex.uniform(&w.sc[F_BEST]);
@@ -597,6 +606,7 @@ struct TcSolver {
   // write the current (clean) state, with only in-arc `keep` of node x kept, as a compact instance.
   // Label ids are kept (no renumbering), so L and the bitset width stay those of the parent.
   PT_NI void emit_child(int x, int keep, const TcEmit& out) {
+    ex.phase = 12;
     const int root = ex.uniform(&w.sc[F_ROOT]);
     // live host nodes (root, or any live in-arc) -> new ids by a scan of the flags (lvl is free after pick_branch_node)
     PT_FOR(v, n + 1) {
@@ -633,6 +643,7 @@ struct TcSolver {
   // Kahn peel from the leaves: every node must be reached, exactly one node has no in-arc (the reference throws
   // std::logic_error for several roots, utils/storage_adj_common.hpp:103-109; a cycle would hang its DFS)
   PT_NI bool check_dag(bool trusted) {
+    ex.phase = 5;
     int roots = 0;
     set_scalar(F_TMP, 0);
     PT_FOR(v, n) {

@@ -64,6 +64,7 @@ void dev_free(void* p) {
 // ---- the warp executor: PT_FOR = lane-strided loop, barrier = __syncwarp, atomics on shared memory ---------------
 struct WarpEx {
   int lane;
+  int phase;  // last pass entered (debug aid, see CtaEx)
   __device__ __forceinline__ int tid() const { return lane; }
   __device__ __forceinline__ int nth() const { return 32; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
@@ -100,36 +101,46 @@ struct WarpEx {
 
 // ---- the CTA executor: one thread block per instance, workspace in GLOBAL memory (int32 ids), barrier = __syncthreads ----
 // For instances that do not fit one CTA's shared memory (BASELINE config 4: n = 10^6).  Same solver code, other executor.
+// debug trace (host-mapped memory, see pt_debug_trace): first and last thread of block 0 publish how many barriers they have
+// passed and which pass they are in, so that a hang can be located from the host while the kernel is still stuck
+__device__ volatile int* g_trace = nullptr;
 struct CtaEx {
   int* red;  // 40 ints of shared memory
+  int phase;
+  int nsync;
   __device__ __forceinline__ int tid() const { return threadIdx.x; }
   __device__ __forceinline__ int nth() const { return blockDim.x; }
-  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ void sync() {
+    ++nsync;
+    volatile int* t = g_trace;
+    if (t && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 1)) { const int o = threadIdx.x ? 4 : 0; t[o] = nsync; t[o + 1] = phase; }
+    __syncthreads();
+  }
   __device__ __forceinline__ int map(int i, int) const { return i; }
-  __device__ __forceinline__ int uniform(const int32_t* p) const {
-    __syncthreads();
+  __device__ __forceinline__ int uniform(const int32_t* p) {
+    sync();
     if (threadIdx.x == 0) red[34] = *(const volatile int32_t*)p;
-    __syncthreads();
+    sync();
     const int v = red[34];
-    __syncthreads();
+    sync();
     return v;
   }
-  __device__ __forceinline__ int reduce_or(int v) const {
+  __device__ __forceinline__ int reduce_or(int v) {
     v = (int)__reduce_or_sync(0xffffffffu, (unsigned)v);
-    __syncthreads();
+    sync();
     if (threadIdx.x == 0) red[32] = 0;
-    __syncthreads();
+    sync();
     if ((threadIdx.x & 31) == 0 && v) atomicOr(&red[32], v);
-    __syncthreads();
+    sync();
     return red[32];
   }
-  __device__ __forceinline__ int reduce_add(int v) const {
+  __device__ __forceinline__ int reduce_add(int v) {
     v = __reduce_add_sync(0xffffffffu, v);
-    __syncthreads();
+    sync();
     if (threadIdx.x == 0) red[33] = 0;
-    __syncthreads();
+    sync();
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&red[33], v);
-    __syncthreads();
+    sync();
     return red[33];
   }
   __device__ __forceinline__ int atomic_add(int32_t* p, int v) const { return atomicAdd(p, v); }
@@ -140,9 +151,9 @@ struct CtaEx {
   __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   // tile-by-tile block scan with a running carry: coalesced, two barriers per tile of blockDim.x elements
   template <class T>
-  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) const {
+  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __syncthreads();
+    sync();
     int carry = 0;
     for (int base = 0; base < n; base += blockDim.x) {
       const int i = base + threadIdx.x;
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(512) tc_reduce_kernel(TcSource src, TcSink sin
                                                         unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpEx ex{lane};
+  WarpEx ex{lane, 0};
   TcWork<I> w;
   w.carve(smem + (size_t)warp * warp_bytes, capN, capM, capNT, capL);
   const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
                                                             uint8_t* __restrict__ branched, int32_t* __restrict__ ticket, unsigned long long* __restrict__ counters) {
   using I = int32_t;
   __shared__ int s_red[40];
-  CtaEx ex{s_red};
+  CtaEx ex{s_red, 0, 0};
   TcWork<I> w;
   w.carve(ws + (size_t)blockIdx.x * ws_bytes, capN, capM, capNT, capL);
   const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
@@ -278,6 +289,7 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
     if (threadIdx.x == 0) s_red[36] = atomicAdd(ticket, 1);
     __syncthreads();
     const int item = s_red[36];
+    if (g_trace && blockIdx.x == 0 && threadIdx.x == 0) g_trace[8] = item;
     if (item >= total) break;
     TcInst in;
     int origin;
@@ -409,6 +421,20 @@ static int upload(T** dst, const T* src, int64_t count, cudaStream_t s, int64_t*
 }
 
 extern "C" {
+
+// debug only (not part of include/pt_gpu.h): returns a host pointer to 16 ints that the CTA executor updates while running
+int* pt_debug_trace(void) {
+  static int* host = nullptr;
+  if (!host) {
+    if (cudaHostAlloc((void**)&host, 64, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(host, 0, 64);
+    int* dev = nullptr;
+    if (cudaHostGetDevicePointer((void**)&dev, host, 0) != cudaSuccess) return nullptr;
+    volatile int* d = dev;
+    cudaMemcpyToSymbol(ptgpu::g_trace, &d, sizeof(d));
+  }
+  return host;
+}
 
 int pt_device_count(void) {
   int n = 0;

@@ -21,7 +21,8 @@
 using namespace ptgpu;
 
 struct HostEx {
-  int perm;  // 0 identity, 1 reverse, >=2 affine permutation seeded by perm
+  int perm;
+  int phase = 0;  // 0 identity, 1 reverse, >=2 affine permutation seeded by perm
   int tid() const { return 0; }
   int nth() const { return 1; }
   void sync() const {}

@@ -34,7 +34,7 @@ struct Barrier {
 struct Shared { Barrier bar; std::vector<int> scratch; std::atomic<int> red_or{0}, red_add{0}; explicit Shared(int t) : bar(t), scratch(t + 1) {} };
 
 struct GroupEx {
-  int t, T; Shared* sh; long nsync = 0;
+  int t, T; Shared* sh; long nsync = 0; int phase = 0;
   int tid() const { return t; }
   int nth() const { return T; }
   void sync() { ++nsync; sh->bar.wait(); }
