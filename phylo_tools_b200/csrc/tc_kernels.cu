@@ -113,7 +113,7 @@ struct CtaEx {
   __device__ __forceinline__ void sync() {
     ++nsync;
     volatile int* t = g_trace;
-    if (t && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 1)) { const int o = threadIdx.x ? 4 : 0; t[o] = nsync; t[o + 1] = phase; }
+    if (t && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 1)) { const int o = blockIdx.x * 16 + (threadIdx.x ? 4 : 0); t[o] = nsync; t[o + 1] = phase; }
     __syncthreads();
   }
   __device__ __forceinline__ int map(int i, int) const { return i; }
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
     if (threadIdx.x == 0) s_red[36] = atomicAdd(ticket, 1);
     __syncthreads();
     const int item = s_red[36];
-    if (g_trace && blockIdx.x == 0 && threadIdx.x == 0) g_trace[8] = item;
+    if (g_trace && threadIdx.x == 0) g_trace[blockIdx.x * 16 + 8] = item;
     if (item >= total) break;
     TcInst in;
     int origin;
@@ -422,12 +422,13 @@ static int upload(T** dst, const T* src, int64_t count, cudaStream_t s, int64_t*
 
 extern "C" {
 
-// debug only (not part of include/pt_gpu.h): returns a host pointer to 16 ints that the CTA executor updates while running
+// debug only (not part of include/pt_gpu.h): returns a host pointer to 16 ints per block (1024 blocks) that the CTA
+// executor updates while running
 int* pt_debug_trace(void) {
   static int* host = nullptr;
   if (!host) {
-    if (cudaHostAlloc((void**)&host, 64, cudaHostAllocMapped) != cudaSuccess) return nullptr;
-    memset(host, 0, 64);
+    if (cudaHostAlloc((void**)&host, 1024 * 64, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(host, 0, 1024 * 64);
     int* dev = nullptr;
     if (cudaHostGetDevicePointer((void**)&dev, host, 0) != cudaSuccess) return nullptr;
     volatile int* d = dev;
