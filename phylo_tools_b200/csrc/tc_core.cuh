@@ -305,6 +305,7 @@ struct TcSolver {
   PT_NI void clean_host(int& dag_state, int* status) {
     for (;;) {
       csr();
+      ex.phase = 40;
       if (dag_state != 1) {
         const bool ok = check_dag(dag_state == 2);
         dag_state = 1;
@@ -332,6 +333,7 @@ struct TcSolver {
       need = ex.reduce_or(need);
       if (need & NEED_FAIL) { set_scalar(F_FAIL, 1); return; }
       if (need & NEED_DEAD) {
+        ex.phase = 41;
         PT_FOR(v, n) {
           if (outdeg(v) == 0) { if (w.hlab[v] < 0) PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) w.at[in_arc(v, k)] = (I)-1; }
           else if (indeg(v) == 0 && v != root) PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) w.at[out_arc(v, k)] = (I)-1;
@@ -347,6 +349,7 @@ struct TcSolver {
         continue;
       }
       if (need & NEED_SUPPRESS) {
+        ex.phase = 43;
         // every arc decides for itself, so the pass is race-free: an arc whose tail is suppressible disappears; an arc
         // entering a chain from a non-suppressible tail jumps to the end of the chain
         PT_FOR(e, m) {
@@ -355,21 +358,22 @@ struct TcSolver {
             if (suppressible(t)) w.at[e] = (I)-1;
             else {
               int h = w.ah[e];
-              if (suppressible(h)) { while (suppressible(h)) h = w.ah[out_arc(h, 0)]; w.ah[e] = (I)h; }
+              if (suppressible(h)) { int guard = 0; while (suppressible(h) && ++guard <= n) h = w.ah[out_arc(h, 0)]; w.ah[e] = (I)h; if (guard > n) w.sc[F_STATUS] = TCS_BAD_GRAPH; }
             }
           }
         }
-        ex.sync();
+        if (take_flag(F_STATUS)) { *status = TCS_BAD_GRAPH; return; }  // a chain longer than n: cyclic structure
         continue;
       }
       if (need & NEED_MERGE) {
+        ex.phase = 44;
         // reticulation chains: hand the parents of x down to the bottom of the chain (cf. ReticulationMerger :392-409)
         PT_FOR(v, n) {
           int y = -1;
-          if (mergeable(v)) { y = w.ah[out_arc(v, 0)]; while (mergeable(y)) y = w.ah[out_arc(y, 0)]; }
+          if (mergeable(v)) { int guard = 0; y = w.ah[out_arc(v, 0)]; while (mergeable(y) && ++guard <= n) y = w.ah[out_arc(y, 0)]; if (guard > n) w.sc[F_STATUS] = TCS_BAD_GRAPH; }
           w.haux[v] = y;
         }
-        ex.sync();
+        if (take_flag(F_STATUS)) { *status = TCS_BAD_GRAPH; return; }
         PT_FOR(v, n) {
           if (w.haux[v] >= 0) { PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) w.ah[in_arc(v, k)] = (I)w.haux[v]; w.at[out_arc(v, 0)] = (I)-1; }
         }
@@ -377,6 +381,7 @@ struct TcSolver {
         continue;
       }
       if (need & NEED_PARALLEL) {
+        ex.phase = 46;
         PT_FOR(v, n) {
           const int d = outdeg(v);
           if (d >= 2 && d <= 8)
