@@ -114,6 +114,9 @@ struct CtaEx {
     ++nsync;
     volatile int* t = g_trace;
     if (t && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 1)) { const int o = blockIdx.x * 16 + (threadIdx.x ? 4 : 0); t[o] = nsync; t[o + 1] = phase; }
+    // The workspace is in GLOBAL memory and the passes mix plain stores with atomics (which execute in L2) on the same
+    // words.  A CTA barrier alone orders them only as far as the SM's L1; the fence pushes this thread's stores to L2 first.
+    __threadfence();
     __syncthreads();
   }
   __device__ __forceinline__ int map(int i, int) const { return i; }
