@@ -245,7 +245,7 @@ def config4_leg(pt, torch, count):
             "note": "one CTA per instance, workspace in global memory; the reference cannot run this size (extrapolated 3e5 s per instance, BASELINE.md)"}
 
 
-def config5_leg(pt, retis=22, leaves=28):
+def config5_leg(pt, retis=24, leaves=30):
     """BASELINE configs[4]: exhaustive 2^r switching enumeration of one general network (guest = random tree: not displayed,
     so the whole index space is visited)"""
     p = pt.Packer()
