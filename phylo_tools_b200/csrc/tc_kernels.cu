@@ -179,7 +179,7 @@ struct CtaEx {
 
 // where work items come from: the caller's batch (offset tables) or a pool of fixed-stride slots
 struct TcSource {
-  int64_t count;            // batch mode: number of instances
+  int64_t first, count;     // batch mode: this launch covers instances [first, count)
   const int32_t* count_ptr; // pool mode: device counter (clamped to capacity)
   int is_pool, capacity;
   const int64_t *hnode_off, *harc_off, *gnode_off;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(512) tc_reduce_kernel(TcSource src, TcSink sin
   unsigned long long c_disp = 0, c_items = 0, c_br = 0, c_ch = 0, c_ret = 0, c_arc = 0, c_pass = 0, c_err = 0;
   for (;;) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(ticket, 1);
+    if (lane == 0) item = (int)src.first + atomicAdd(ticket, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= total) break;
     TcInst in;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
   unsigned long long c_disp = 0, c_items = 0, c_br = 0, c_ch = 0, c_ret = 0, c_arc = 0, c_pass = 0, c_err = 0;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_red[36] = atomicAdd(ticket, 1);
+    if (threadIdx.x == 0) s_red[36] = (int)src.first + atomicAdd(ticket, 1);
     __syncthreads();
     const int item = s_red[36];
     if (g_trace && threadIdx.x == 0) g_trace[blockIdx.x * 16 + 8] = item;
@@ -394,6 +394,11 @@ struct pt_batch {
   int pool_cap = 0;
   int32_t* d_pool[2] = {nullptr, nullptr};
   unsigned char* d_ws = nullptr; size_t ws_cap = 0;  // global-memory workspaces of the CTA executor
+  // HOST input is uploaded in chunks of instances on a private copy stream; round 0 launches one kernel per chunk as soon as
+  // its bytes have landed, so the upload overlaps the solve (end-to-end path)
+  static constexpr int kMaxChunks = 8;
+  cudaStream_t copy_stream = nullptr;
+  int nchunks = 1; int64_t chunk_end[kMaxChunks] = {}; cudaEvent_t chunk_ev[kMaxChunks] = {};
   int64_t last_launches = 0;
   int64_t h2d_bytes = 0;
   static constexpr int kMaxTimedRounds = 16;
@@ -412,6 +417,8 @@ static void batch_release(pt_batch* b) {
   dev_free(b->d_bits); dev_free(b->d_status); dev_free(b->d_branched); dev_free(b->d_ticket); dev_free(b->d_counters);
   dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); dev_free(b->d_ws);
   for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : b->chunk_ev) if (e) cudaEventDestroy(e);
+  if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
   delete b;
 }
 
@@ -495,11 +502,34 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       b->maxL = std::max(b->maxL, ml);
     }
     b->owns_input = true;
+    // offset tables first (small), then the five data arrays chunk by chunk on the copy stream
     if ((rc = upload(&b->d_hnode_off, d->host_node_off, B + 1, s, &b->h2d_bytes)) || (rc = upload(&b->d_harc_off, d->host_arc_off, B + 1, s, &b->h2d_bytes)) ||
-        (rc = upload(&b->d_gnode_off, d->guest_node_off, B + 1, s, &b->h2d_bytes)) || (rc = upload(&b->d_succ_off, d->host_succ_off, NH + B, s, &b->h2d_bytes)) ||
-        (rc = upload(&b->d_succ_adj, d->host_succ_adj, MH, s, &b->h2d_bytes)) || (rc = upload(&b->d_hlabel, d->host_label, NH, s, &b->h2d_bytes)) ||
-        (rc = upload(&b->d_tparent, d->guest_parent, NG, s, &b->h2d_bytes)) || (rc = upload(&b->d_tlabel, d->guest_label, NG, s, &b->h2d_bytes)))
+        (rc = upload(&b->d_gnode_off, d->guest_node_off, B + 1, s, &b->h2d_bytes)))
       return fail(rc);
+    if ((rc = dev_alloc((void**)&b->d_succ_off, (size_t)std::max<int64_t>(NH + B, 1) * 4)) || (rc = dev_alloc((void**)&b->d_succ_adj, (size_t)std::max<int64_t>(MH, 1) * 4)) ||
+        (rc = dev_alloc((void**)&b->d_hlabel, (size_t)std::max<int64_t>(NH, 1) * 4)) || (rc = dev_alloc((void**)&b->d_tparent, (size_t)std::max<int64_t>(NG, 1) * 4)) ||
+        (rc = dev_alloc((void**)&b->d_tlabel, (size_t)std::max<int64_t>(NG, 1) * 4)))
+      return fail(rc);
+    b->nchunks = B >= 8192 ? pt_batch::kMaxChunks : 1;
+    if (b->nchunks > 1 && cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); b->nchunks = 1; }
+    cudaStream_t cs = b->nchunks > 1 ? b->copy_stream : s;
+    for (int c = 0; c < b->nchunks; ++c) {
+      const int64_t i0 = B * c / b->nchunks / 32 * 32, i1 = (c + 1 == b->nchunks) ? B : B * (c + 1) / b->nchunks / 32 * 32;
+      b->chunk_end[c] = i1;
+      const int64_t h0 = d->host_node_off[i0], h1 = d->host_node_off[i1], a0 = d->host_arc_off[i0], a1 = d->host_arc_off[i1], g0 = d->guest_node_off[i0], g1 = d->guest_node_off[i1];
+      auto cp = [&](int32_t* dst, const int32_t* src, int64_t from, int64_t to) -> cudaError_t {
+        if (to <= from) return cudaSuccess;
+        b->h2d_bytes += (to - from) * 4;
+        return cudaMemcpyAsync(dst + from, src + from, (size_t)(to - from) * 4, cudaMemcpyHostToDevice, cs);
+      };
+      cudaError_t e = cp(b->d_succ_off, d->host_succ_off, h0 + i0, h1 + i1);
+      if (e == cudaSuccess) e = cp(b->d_succ_adj, d->host_succ_adj, a0, a1);
+      if (e == cudaSuccess) e = cp(b->d_hlabel, d->host_label, h0, h1);
+      if (e == cudaSuccess) e = cp(b->d_tparent, d->guest_parent, g0, g1);
+      if (e == cudaSuccess) e = cp(b->d_tlabel, d->guest_label, g0, g1);
+      if (e == cudaSuccess && b->nchunks > 1) { e = cudaEventCreateWithFlags(&b->chunk_ev[c], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventRecord(b->chunk_ev[c], cs); }
+      if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: upload failed: %s", cudaGetErrorString(e)));
+    }
   } else {
     b->d_hnode_off = (int64_t*)d->host_node_off; b->d_harc_off = (int64_t*)d->host_arc_off; b->d_gnode_off = (int64_t*)d->guest_node_off;
     b->d_succ_off = (int32_t*)d->host_succ_off; b->d_succ_adj = (int32_t*)d->host_succ_adj; b->d_hlabel = (int32_t*)d->host_label;
@@ -619,15 +649,31 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
         for (int j = 0; j < 2; ++j) if (!b->ev[2 * round + j]) PT_CUDA(cudaEventCreate(&b->ev[2 * round + j]));
         PT_CUDA(cudaEventRecord(b->ev[2 * round], s));
       }
-      if (use_cta)
-        tc_reduce_cta_kernel<<<grid, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits, stat, b->d_branched, b->d_ticket,
-                                                  b->d_counters);
-      else
-        tc_reduce_kernel<I><<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched,
-                                                         b->d_ticket, b->d_counters);
+      // round 0 of a HOST batch: one launch per upload chunk, each waiting only for its own bytes
+      const int launches = (round == 0) ? b->nchunks : 1;
+      for (int c = 0; c < launches; ++c) {
+        int32_t* ticket = b->d_ticket;
+        if (round == 0) {
+          src.first = c == 0 ? 0 : b->chunk_end[c - 1];
+          src.count = launches > 1 ? b->chunk_end[c] : B;
+          ticket = b->d_ticket + 4 + c;
+          if (b->chunk_ev[c]) PT_CUDA(cudaStreamWaitEvent(s, b->chunk_ev[c], 0));
+          const int64_t cnt = src.count - src.first;
+          if (cnt <= 0) continue;
+          grid = use_cta ? (int)std::min<int64_t>(cta_grid_cap, cnt) : (int)std::min<int64_t>((int64_t)dp.sms * ctas_per_sm, (cnt + wpc - 1) / wpc);
+          grid = std::max(grid, 1);
+        }
+        if (use_cta)
+          tc_reduce_cta_kernel<<<grid, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits, stat, b->d_branched, ticket,
+                                                    b->d_counters);
+        else
+          tc_reduce_kernel<I><<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched, ticket,
+                                                           b->d_counters);
+        ++b->last_launches;
+      }
       PT_CUDA(cudaGetLastError());
       if (timed) { PT_CUDA(cudaEventRecord(b->ev[2 * round + 1], s)); b->timed_rounds = round + 1; }
-      ++b->last_launches; ++rounds;
+      ++rounds;
       int32_t h[4];
       PT_CUDA(cudaMemcpyAsync(h, b->d_ticket, 16, cudaMemcpyDeviceToHost, s));
       PT_CUDA(cudaStreamSynchronize(s));
