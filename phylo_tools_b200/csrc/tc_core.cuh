@@ -449,7 +449,7 @@ struct TcSolver {
     PT_FOR(l, L) {
       const int h = w.l2h[l];
       if (h >= 0) {
-        if (indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; w.hcnt[q] = 0; w.haux[q] = -1; }
+        if (indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (q >= 0) { w.hcnt[q] = 0; w.haux[q] = -1; } }
         const int p = w.tpar[w.l2t[l]];
         if (p >= 0) w.tmin[p] = 0x7fffffff;
       }
@@ -457,7 +457,7 @@ struct TcSolver {
     ex.sync();
     PT_FOR(l, L) {
       const int h = w.l2h[l];
-      if (h >= 0 && indeg(h) == 1) ex.atomic_add(&w.hcnt[w.at[in_arc(h, 0)]], 1);
+      if (h >= 0 && indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (q >= 0) ex.atomic_add(&w.hcnt[q], 1); }
     }
     ex.sync();
     int fail = 0, any = 0;
@@ -465,7 +465,7 @@ struct TcSolver {
       const int h = w.l2h[l];
       if (h >= 0 && indeg(h) == 1) {
         const int q = w.at[in_arc(h, 0)];
-        if (w.hcnt[q] == outdeg(q) && outdeg(q) >= 2) {
+        if (q >= 0 && w.hcnt[q] == outdeg(q) && outdeg(q) >= 2) {
           const int p = w.tpar[w.l2t[l]];
           any = 1;
           if (p < 0) fail = 1;
@@ -480,7 +480,7 @@ struct TcSolver {
     if (!ex.reduce_or(any)) return 0;
     PT_FOR(l, L) {
       const int h = w.l2h[l];
-      if (h >= 0 && indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (w.haux[q] >= 0 && w.tdeg[w.haux[q]] != outdeg(q)) fail = 1; }
+      if (h >= 0 && indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (q >= 0 && w.haux[q] >= 0 && w.tdeg[w.haux[q]] != outdeg(q)) fail = 1; }
     }
     if (ex.reduce_or(fail)) { set_scalar(F_FAIL, 1); return -1; }
     int collapsed = 0;
@@ -488,7 +488,7 @@ struct TcSolver {
       const int h = w.l2h[l];
       if (h >= 0 && indeg(h) == 1) {
         const int q = w.at[in_arc(h, 0)];
-        if (w.haux[q] >= 0) {
+        if (q >= 0 && w.haux[q] >= 0) {
           const int p = w.haux[q], t = w.l2t[l];
           w.at[in_arc(h, 0)] = (I)-1;
           w.hlab[h] = (I)-1;
@@ -519,34 +519,54 @@ struct TcSolver {
   PT_HD bool is_bin_cherry(int p) const { return w.tpar[p] != TDEAD && w.tdeg[p] == 2 && w.tleaf[p] == 2; }
 
   // ---- RC: reticulated cherries ---------------------------------------------------------------------------
+  // returns bit 0: some multi-parent node got its parent fixed (needs a clean-up pass), bit 1: some reticulated cherry was
+  // collapsed on the spot (q had exactly the two children: the true-cherry rule can go on without a CSR rebuild).
+  // Tolerates a CSR that is stale by arc deletions: a dead arc has at = -1 and never matches q, degrees only over-count.
   PT_NI int rule_ret_cherry() {
     ex.phase = 9;
+    int fixed = 0, collapsed = 0;
     PT_FOR(p, nt) {
       if (is_bin_cherry(p)) {
         PT_NOUNROLL for (int side = 0; side < 2; ++side) {
           const int x = side ? w.tmax[p] : w.tmin[p], y = side ? w.tmin[p] : w.tmax[p];
           const int hx = w.l2h[x], hy = w.l2h[y];
           if (indeg(hx) != 1) continue;
-          const int q = w.at[in_arc(hx, 0)];
+          const int ex_arc = in_arc(hx, 0);
+          const int q = w.at[ex_arc];
+          if (q < 0) continue;
           int c = -1;  // the multi-parent node whose parent gets fixed to q
           if (indeg(hy) >= 2) c = hy;
-          else if (indeg(hy) == 1) { const int z = w.at[in_arc(hy, 0)]; if (outdeg(z) == 1 && indeg(z) >= 2) c = z; }
+          else if (indeg(hy) == 1) { const int z = w.at[in_arc(hy, 0)]; if (z >= 0 && outdeg(z) == 1 && indeg(z) >= 2) c = z; }
           if (c < 0) continue;
           int keep = -1;
           PT_NOUNROLL for (int k = 0; k < indeg(c); ++k) if (w.at[in_arc(c, k)] == q) keep = in_arc(c, k);
           if (keep < 0) continue;
           PT_NOUNROLL for (int k = 0; k < indeg(c); ++k) { const int e = in_arc(c, k); if (e != keep) w.at[e] = (I)-1; }
-          ex.atomic_add(&w.sc[F_TMP2], 1);
-          w.sc[F_FLAG] = 1;
+          bool both = false;  // q's children are exactly hx and c (both arcs alive)
+          if (outdeg(q) == 2) {
+            const int e0 = out_arc(q, 0), e1 = out_arc(q, 1);
+            both = (e0 == ex_arc && e1 == keep) || (e1 == ex_arc && e0 == keep);
+          }
+          if (both) {
+            // collapse q -> leaf carrying the smaller label; p -> leaf carrying the same label
+            const int s_lab = w.tmin[p], t_lab = w.tmax[p];
+            w.at[ex_arc] = (I)-1; w.at[keep] = (I)-1;
+            if (c != hy) w.at[in_arc(hy, 0)] = (I)-1;
+            w.hlab[hx] = (I)-1; w.hlab[hy] = (I)-1;
+            const int ts = w.l2t[s_lab], tt = w.l2t[t_lab];
+            w.tlab[ts] = (I)-1; w.tpar[ts] = (I)TDEAD; w.tlab[tt] = (I)-1; w.tpar[tt] = (I)TDEAD;
+            w.hlab[q] = (I)s_lab; w.l2h[s_lab] = (I)q; w.l2h[t_lab] = (I)-1;
+            w.tlab[p] = (I)s_lab; w.l2t[s_lab] = (I)p; w.l2t[t_lab] = (I)-1; w.tdeg[p] = 0;
+            ++collapsed;
+          } else ++fixed;
           break;
         }
       }
     }
-    ex.sync();
-    st.retcherries += (unsigned)w.sc[F_TMP2];
-    ex.sync();
-    set_scalar(F_TMP2, 0);
-    return take_flag(F_FLAG) ? 1 : 0;
+    const int nc = ex.reduce_add(collapsed), nf = ex.reduce_add(fixed);
+    st.retcherries += (unsigned)(nc + nf);
+    st.cherries += (unsigned)nc;
+    return (nf ? 1 : 0) | (nc ? 2 : 0);
   }
 
   // ---- SC: sibling constraints ----------------------------------------------------------------------------
@@ -690,13 +710,19 @@ struct TcSolver {
       if (*status != TCS_OK) return TC_ERROR;
       if (missing || ex.uniform(&w.sc[F_FAIL])) return TC_NOT;
       if (count_labels() <= 2) return TC_DISPLAYED;  // containment.hpp:1061,1208
-      int r, collapsed = 0;
-      for (;;) { r = rule_true_cherry(); if (r <= 0) break; collapsed = 1; }  // pendant subtrees collapse level by level, no CSR rebuild
+      // true cherries and on-the-spot reticulated cherries alternate without rebuilding the CSR: pendant subtrees that match
+      // collapse level by level; only a fixed-but-not-collapsed reticulation (or nothing at all) sends us back to clean-up
+      int r, progress = 0;
+      for (;;) {
+        for (;;) { r = rule_true_cherry(); if (r <= 0) break; progress = 1; }
+        if (r < 0) break;
+        guest_cherries();
+        r = rule_ret_cherry();
+        if (r) progress = 1;
+        if (!(r & 2)) break;
+      }
       if (r < 0) return TC_NOT;
-      if (collapsed) continue;
-      guest_cherries();
-      r = rule_ret_cherry();
-      if (r > 0) continue;
+      if (progress) continue;
       if (!wavefront()) { *status = TCS_BAD_GRAPH; return TC_ERROR; }
       r = rule_sibling();
       if (r < 0) return TC_NOT;
