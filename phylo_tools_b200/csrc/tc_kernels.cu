@@ -80,21 +80,23 @@ struct WarpEx {
   __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
     return (int)(int16_t)atomicCAS((unsigned short*)p, (unsigned short)(int16_t)c, (unsigned short)(int16_t)v);
   }
-  // out[0..n] = exclusive prefix sums of in[0..n): each lane owns a contiguous chunk, warp shuffle scan over chunk sums
+  // out[0..n] = exclusive prefix sums of in[0..n): tiles of 32 consecutive elements (bank-conflict free), one shuffle scan
+  // per tile with a running carry.  (The first version gave every lane a contiguous chunk: 8-way bank conflicts, 7 % of all
+  // stall samples of the kernel.)
   template <class T>
   __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) const {
     __syncwarp();
-    const int chunk = (n + 31) >> 5;
-    const int b = lane * chunk, e = min(b + chunk, n);
-    int sum = 0;
-    for (int i = b; i < e; ++i) sum += in[i];
-    int incl = sum;
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const int v = i < n ? in[i] : 0;
+      int incl = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    int acc = incl - sum;
-    for (int i = b; i < e; ++i) { const int v = in[i]; out[i] = (T)acc; acc += v; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (lane == 0) out[n] = (T)total;
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      if (i < n) out[i] = (T)(carry + incl - v);
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) out[n] = (T)carry;
     __syncwarp();
   }
 };
