@@ -80,6 +80,18 @@ int pt_lca_node_info(const pt_lca* h, int32_t* depth, int32_t* preorder, pt_mem 
 int pt_lca_free(pt_lca* h);
 
 /* ------------------------------------------------------------------------------------------------
+ * who_displays -- replaces  TreeInTreeContainment<Host,Guest>::who_displays(u)   utils/containment.hpp:72-177
+ * for a SINGLE-LABELLED TREE host: out_host_node[u] = the host node that minimally displays the guest subtree below u
+ * (the one entry of the reference's list), or -1 if none does.  The guest is displayed iff out_host_node[guest root] >= 0
+ * (containment.hpp:83).  Internally the induced-subtree step of the reference (k-1 LCAs of consecutive candidates,
+ * utils/induced_tree.hpp:128-138) runs as one wavefront over the guest's levels on top of pt_lca.
+ * Labels: dense ids < n + nt shared by both trees, -1 = unlabelled; only labels on leaves count.  Multi-labelled hosts
+ * (the reference's MUL-trees) return PT_ERR_INVALID; more than 64 children on one guest node PT_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------------------------------- */
+int pt_tree_who_displays(const int32_t* host_parent, const int32_t* host_label, int64_t n, const int32_t* guest_parent,
+                         const int32_t* guest_label, int64_t nt, int32_t* out_host_node, pt_mem mem, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * RMQ -- replaces  rmq<It>::query / query_offset    rmq/rmq.hpp:63-74
  *                  sparse_rmq                        rmq/sparse_rmq.hpp:45-90
  * query over the half-open range [l, r), l < r; returns the index of the RIGHTMOST minimum, which is what

@@ -134,8 +134,71 @@ def make_lca():
     print("lca_ref.json:", len(trees), "trees,", len(rmqs), "rmq arrays")
 
 
+def _rand_tree_newick(rng, labels, max_deg):
+    """random rooted tree on the given leaf labels, inner nodes with 2..max_deg children"""
+    nodes = list(labels)
+    rng.shuffle(nodes)
+    while len(nodes) > 1:
+        k = int(min(len(nodes), rng.integers(2, max_deg + 1)))
+        idx = sorted(rng.choice(len(nodes), k, replace=False).tolist(), reverse=True)
+        kids = [nodes.pop(i) for i in idx]
+        nodes.insert(int(rng.integers(0, len(nodes) + 1)), "(" + ",".join(kids) + ")")
+    return nodes[0] + ";"
+
+
+def make_who():
+    """tree/tree pairs -> who_displays(u) of the REFERENCE for every guest node (oracle/_ref/ref_tc who)"""
+    rng = np.random.default_rng(4711)
+    pairs = [("((a,b),(c,d));", "((a,b),(c,d));"), ("((a,b),(c,d));", "((a,c),(b,d));"), ("(((a,b),c),(d,e));", "((a,b),((d,e),c));")]
+    names = [pt_name(i) for i in range(40)]
+    for trial in range(160):
+        l = int(rng.integers(3, 14))
+        labs = names[:l]
+        max_deg = 2 if trial % 3 else 4
+        host = _rand_tree_newick(rng, labs, max_deg)
+        mode = trial % 5
+        if mode == 0:
+            guest = host                                     # identical
+        elif mode == 1:
+            guest = _rand_tree_newick(rng, labs, max_deg)    # random tree on the same labels
+        elif mode == 2:
+            guest = _rand_tree_newick(rng, labs[: max(2, l - 2)], max_deg)   # host has extra labels
+        elif mode == 3:
+            guest = _rand_tree_newick(rng, labs + ["zz"], max_deg)           # guest has a label the host lacks
+        else:                                                # host with one subtree re-hung: partly displayed
+            guest = _rand_tree_newick(rng, labs, 2)
+            host = guest.replace("(" + labs[0] + ",", "(" + labs[1] + ",", 1) if False else host
+        pairs.append((host, guest))
+    out = run_lines(REF_TC, "who", [x for p in pairs for x in p])
+    blocks = [b.strip("\n").split("\n") for b in out.split("--\n")][:len(pairs)]
+    items = []
+    for (h, g), b in zip(pairs, blocks):
+        if b and b[0] in ("CRASH", "EXC"):
+            items.append(dict(host=h, guest=g, reference=b[0]))
+            continue
+        who = []
+        for line in b:
+            u, rest = line.split(":")
+            who.append([int(x) for x in rest.split()])
+        items.append(dict(host=h, guest=g, reference=who))
+    crashed = sum(1 for it in items if not isinstance(it["reference"], list))
+    json.dump(dict(source="oracle/_ref/ref_tc who (reference TreeInTreeContainment::who_displays, containment.hpp:72)", crashed=crashed, items=items),
+              open(os.path.join(GOLD, "who_ref.json"), "w"), indent=0)
+    print("who_ref.json:", len(items), "pairs,", crashed, "reference crashes")
+
+
+def pt_name(i):
+    s = ""
+    while True:
+        s = chr(ord("a") + i % 26) + s
+        if i < 26:
+            return s
+        i //= 26
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     make_newick()
     make_tc()
     make_lca()
+    make_who()

@@ -234,3 +234,62 @@ int32_t orc_lca_euler_query(const orc_lca* L, int32_t u, int32_t v) {
 }
 void orc_lca_euler_batch(const orc_lca* L, const int32_t* u, const int32_t* v, int32_t* out, int64_t q) { for (int64_t i = 0; i < q; ++i) out[i] = orc_lca_euler_query(L, u[i], v[i]); }
 void orc_lca_euler_free(orc_lca* L) { orc_sparse_rmq_free(L->rmq); free(L->euler); free(L->depth); free(L->last); free(L); }
+
+/* ---- who_displays for a single-labelled tree host: TreeInTreeContainment::who_displays utils/containment.hpp:72-177 ----
+ * The reference's DP says: host node v displays guest node u iff the host subtree below v, RESTRICTED to the labels below u
+ * and cleaned, equals the guest subtree below u, and v is the lowest such node (compute_possibilities :128-171 builds the
+ * subtree induced by the children's images and matches children to distinct branches).  Restated from that definition with
+ * label bitsets, independently of the LCA machinery the product uses: for every guest node u, intersect every host
+ * cluster with X_u = labels(T_u), take the deepest host node whose restricted cluster is X_u, and compare the two sets of
+ * branching clusters.  out[u] = that host node or -1.  Pinned against the reference itself (tests/golden/who_ref.json). */
+int orc_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, int nt, const int32_t* tparent, const int32_t* tlabel, int32_t* out) {
+  int32_t* hdeg = (int32_t*)calloc((size_t)n, 4); int32_t* tdeg = (int32_t*)calloc((size_t)nt, 4);
+  for (int v = 0; v < n; ++v) if (hparent[v] >= 0) hdeg[hparent[v]]++;
+  for (int t = 0; t < nt; ++t) if (tparent[t] >= 0) tdeg[tparent[t]]++;
+  int32_t maxlab = -1;
+  for (int v = 0; v < n; ++v) if (hlabel[v] > maxlab) maxlab = hlabel[v];
+  for (int t = 0; t < nt; ++t) if (tlabel[t] > maxlab) maxlab = tlabel[t];
+  int32_t* l2h = (int32_t*)malloc((size_t)(maxlab + 2) * 4);
+  for (int i = 0; i <= maxlab; ++i) l2h[i] = -1;
+  for (int v = 0; v < n; ++v) if (hlabel[v] >= 0 && hdeg[v] == 0) { if (l2h[hlabel[v]] >= 0) { free(hdeg); free(tdeg); free(l2h); return -2; } l2h[hlabel[v]] = v; }
+  const int W = (maxlab + 64) / 64 > 0 ? (maxlab + 64) / 64 : 1;
+  if (W > ORC_MAXW) { free(hdeg); free(tdeg); free(l2h); return -3; }
+  /* children-first orders by depth */
+  int32_t* hdepth = (int32_t*)calloc((size_t)n, 4); int32_t* tdepth = (int32_t*)calloc((size_t)nt, 4);
+  for (int v = 0; v < n; ++v) { int d = 0, x = v; while (hparent[x] >= 0) { x = hparent[x]; ++d; } hdepth[v] = d; }
+  for (int t = 0; t < nt; ++t) { int d = 0, x = t; while (tparent[x] >= 0) { x = tparent[x]; ++d; } tdepth[t] = d; }
+  int maxhd = 0, maxtd = 0;
+  for (int v = 0; v < n; ++v) if (hdepth[v] > maxhd) maxhd = hdepth[v];
+  for (int t = 0; t < nt; ++t) if (tdepth[t] > maxtd) maxtd = tdepth[t];
+  bits_t* X = (bits_t*)calloc((size_t)nt, sizeof(bits_t)); uint8_t* bad = (uint8_t*)calloc((size_t)nt, 1); int32_t* talive = (int32_t*)calloc((size_t)nt, 4);
+  for (int d = maxtd; d >= 0; --d) for (int t = 0; t < nt; ++t) if (tdepth[t] == d) {
+    if (tdeg[t] == 0 && tlabel[t] >= 0) { X[t].w[tlabel[t] >> 6] |= 1ull << (tlabel[t] & 63); if (l2h[tlabel[t]] < 0) bad[t] = 1; }
+    int nz = 0; for (int k = 0; k < W; ++k) nz |= X[t].w[k] != 0;
+    if (nz && tparent[t] >= 0) { for (int k = 0; k < W; ++k) X[tparent[t]].w[k] |= X[t].w[k]; talive[tparent[t]]++; bad[tparent[t]] |= bad[t]; }
+  }
+  bits_t* C = (bits_t*)malloc((size_t)n * sizeof(bits_t)); int32_t* calive = (int32_t*)malloc((size_t)n * 4);
+  bits_t* tset = (bits_t*)malloc((size_t)nt * sizeof(bits_t)); bits_t* hset = (bits_t*)malloc((size_t)n * sizeof(bits_t));
+  for (int u = 0; u < nt; ++u) {
+    out[u] = -1;
+    int nz = 0; for (int k = 0; k < W; ++k) nz |= X[u].w[k] != 0;
+    if (!nz || bad[u]) continue;
+    /* host clusters restricted to X_u */
+    for (int v = 0; v < n; ++v) { memset(&C[v], 0, sizeof(bits_t)); calive[v] = 0; if (hdeg[v] == 0 && hlabel[v] >= 0) { const int l = hlabel[v]; if ((X[u].w[l >> 6] >> (l & 63)) & 1ull) C[v].w[l >> 6] |= 1ull << (l & 63); } }
+    for (int d = maxhd; d >= 0; --d) for (int v = 0; v < n; ++v) if (hdepth[v] == d) {
+      int z = 0; for (int k = 0; k < W; ++k) z |= C[v].w[k] != 0;
+      if (z && hparent[v] >= 0) { for (int k = 0; k < W; ++k) C[hparent[v]].w[k] |= C[v].w[k]; calive[hparent[v]]++; }
+    }
+    int best = -1;
+    for (int v = 0; v < n; ++v) if (memcmp(&C[v], &X[u], sizeof(bits_t)) == 0 && (best < 0 || hdepth[v] > hdepth[best])) best = v;
+    if (best < 0) continue;
+    /* branching clusters of T_u and of the restricted host subtree below `best` */
+    int tc = 0, hc = 0;
+    for (int t = 0; t < nt; ++t) if (talive[t] >= 2) { int in = 1; for (int k = 0; k < W; ++k) if (X[t].w[k] & ~X[u].w[k]) in = 0; int x = t; while (x != u && x >= 0) x = tparent[x]; if (in && x == u) tset[tc++] = X[t]; }
+    for (int v = 0; v < n; ++v) if (calive[v] >= 2) { int x = v; while (x != best && x >= 0) x = hparent[x]; if (x == best) hset[hc++] = C[v]; }
+    if (tc != hc) continue;
+    cmp_bits_W = ORC_MAXW; qsort(tset, (size_t)tc, sizeof(bits_t), cmp_bits); qsort(hset, (size_t)hc, sizeof(bits_t), cmp_bits);
+    if (memcmp(tset, hset, (size_t)tc * sizeof(bits_t)) == 0) out[u] = best;
+  }
+  free(hdeg); free(tdeg); free(l2h); free(hdepth); free(tdepth); free(X); free(bad); free(talive); free(C); free(calive); free(tset); free(hset);
+  return 0;
+}

@@ -39,6 +39,8 @@ def lib():
         L.orc_sparse_rmq_query.restype = C.c_int64
         L.orc_sparse_rmq_query.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
         L.orc_sparse_rmq_free.argtypes = [C.c_void_p]
+        L.orc_who_displays.restype = C.c_int
+        L.orc_who_displays.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p, i32p, i32p]
     return _LIB
 
 
@@ -102,6 +104,33 @@ def sparse_rmq(values, ls, rs):
     out = np.array([lib().orc_sparse_rmq_query(h, int(l), int(r)) for l, r in zip(ls, rs)], dtype=np.int64)
     lib().orc_sparse_rmq_free(h)
     return out
+
+
+def who_displays(host_parent, host_label, guest_parent, guest_label):
+    hp, hl, gp, gl = _arr(host_parent), _arr(host_label), _arr(guest_parent), _arr(guest_label)
+    out = np.empty(len(gp), dtype=np.int32)
+    rc = lib().orc_who_displays(len(hp), _p(hp), _p(hl), len(gp), _p(gp), _p(gl), _p(out))
+    if rc != 0:
+        raise ValueError("orc_who_displays failed: %d" % rc)
+    return out
+
+
+def tree_arrays_from_newick(host_nw, guest_nw):
+    """two TREE Newick strings -> (host_parent, host_label, guest_parent, guest_label) with a shared dense label dictionary,
+    node ids as the reference reader assigns them (oracle/newick.py)"""
+    from .newick import parse_newick
+    names = {}
+    res = []
+    for s in (host_nw, guest_nw):
+        n, e, lab = parse_newick(s)
+        par = np.full(n, -1, dtype=np.int32)
+        for a, b in e:
+            par[b] = a
+        l = np.full(n, -1, dtype=np.int32)
+        for v, name in lab.items():
+            l[v] = names.setdefault(name, len(names))
+        res += [par, l]
+    return tuple(res)
 
 
 def ref_binary(name):

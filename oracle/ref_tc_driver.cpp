@@ -9,6 +9,7 @@
 //        prints one char per instance on stdout: 1 displayed, 0 not displayed, E exception, S signal.
 //   ref_tc bench <file> <max_instances> : same fork-isolated loop, timed; prints a JSON line on stderr
 //        (rate = instances with a verdict / wall seconds; crashes and exceptions are counted separately).
+//   ref_tc who <file> : tree/tree pairs; prints who_displays(u) of the reference for every guest node
 //   ref_tc parse <file> : for each line: "n m" then edges "u v" in reference edge-list order, then
 //        labels "id name" sorted by id, then "--" (golden vectors for the Newick reader).
 #include "io/io.hpp"
@@ -49,6 +50,23 @@ static int run_instance(const std::string& l0, const std::string& l1) {
   return tc.displayed() ? 1 : 0;
 }
 
+// who_displays of the reference for a tree host: one line per guest node "u: v1 v2 ..." (utils/containment.hpp:72-81)
+static void run_who(const std::string& l0, const std::string& l1) {
+  std::vector<ENL> el(2);
+  parse_line(l0, el[0]); parse_line(l1, el[1]);
+  const size_t nt = el[1].num_nodes;
+  MyNet N(std::move(el[0].edges), std::move(el[0].labels), consecutive_tag());
+  MyTree T(std::move(el[1].edges), std::move(el[1].labels), consecutive_tag());
+  TreeInTreeContainment tc(std::move(N.as_tree()), std::move(T));
+  std::string out;
+  for (size_t u = 0; u < nt; ++u) {
+    out += std::to_string(u) + ":";
+    for (const auto v : tc.who_displays(u)) out += " " + std::to_string((size_t)v);
+    out += "\n";
+  }
+  fputs(out.c_str(), stdout);
+}
+
 static std::vector<std::string> read_lines(const char* fn) {
   std::ifstream in(fn); std::vector<std::string> L; std::string s;
   while (std::getline(in, s)) { if (!s.empty()) L.push_back(s); }
@@ -70,6 +88,18 @@ int main(int argc, char** argv) {
       for (auto&& p : *e.labels) if (!p.second.empty()) labs.emplace_back((size_t)p.first, p.second);
       std::sort(labs.begin(), labs.end());
       for (auto& p : labs) printf("L %zu %s\n", p.first, p.second.c_str());
+      printf("--\n");
+    }
+    return 0;
+  }
+  if (mode == "who") {
+    // fork per pair: the reference may crash; a crashed pair prints "CRASH"
+    for (size_t i = 0; i + 1 < L.size(); i += 2) {
+      fflush(stdout);
+      pid_t pid = fork();
+      if (pid == 0) { std::cout.setstate(std::ios::badbit); try { run_who(L[i], L[i + 1]); } catch (...) { printf("EXC\n"); } fflush(stdout); _exit(0); }
+      int st = 0; waitpid(pid, &st, 0);
+      if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) printf("CRASH\n");
       printf("--\n");
     }
     return 0;

@@ -252,6 +252,16 @@ class Lca:
     __del__ = free
 
 
+def who_displays(host_parent, host_label, guest_parent, guest_label):
+    """pt_tree_who_displays: int32[nt], the host node minimally displaying each guest subtree or -1
+    (TreeInTreeContainment::who_displays, utils/containment.hpp:72, for a single-labelled tree host)"""
+    a = [np.ascontiguousarray(x, dtype=np.int32) for x in (host_parent, host_label, guest_parent, guest_label)]
+    out = np.empty(len(a[2]), dtype=np.int32)
+    _check(_L.pt_tree_who_displays(a[0].ctypes.data, a[1].ctypes.data, len(a[0]), a[2].ctypes.data, a[3].ctypes.data, len(a[2]), out.ctypes.data, PT_MEM_HOST, None),
+           "pt_tree_who_displays")
+    return out
+
+
 class Rmq:
     """pt_rmq_* : sparse_rmq (rmq/sparse_rmq.hpp:45-90): index of the rightmost minimum of [l, r)"""
 

@@ -315,6 +315,97 @@ __global__ void __launch_bounds__(256) rmq_query_kernel(int64_t q, int64_t n, co
   }
 }
 
+// ---- one LCA query from device code (same arithmetic as lca_query_kernel) ------------------------------------------------
+__device__ __forceinline__ int32_t lca_one(const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table,
+                                           const int64_t* __restrict__ level_base, int32_t u, int32_t v) {
+  if (u == v) return u;
+  LcaRecord a = rec[u], b = rec[v];
+  if (a.pos > b.pos) { const LcaRecord t = a; a = b; b = t; }
+  const uint32_t lp = a.pos, rp = b.pos, bl = lp >> 5, br = rp >> 5;
+  u64 best;
+  if (bl == br) {
+    const uint32_t m = b.mask >> ((lp & 31) + 1);
+    best = keypos[((int64_t)bl << 5) + (lp & 31) + 1 + __ffs(m) - 1];
+  } else {
+    best = a.suf < b.pre ? a.suf : b.pre;
+    if (br - bl >= 2) {
+      const uint32_t span = br - bl - 1;
+      const int k = 31 - __clz(span);
+      const u64* lvl = table + level_base[k];
+      const u64 t1 = lvl[bl + 1], t2 = lvl[br - (1u << k)];
+      const u64 t = t1 < t2 ? t1 : t2;
+      best = t < best ? t : best;
+    }
+  }
+  return (int32_t)(uint32_t)(best & 0xffffffffull);
+}
+
+// ---- who_displays for a single-labelled tree host (TreeInTreeContainment::who_displays, utils/containment.hpp:72-177) ------
+// The reference computes, per guest node u, the host nodes that minimally display the guest subtree below u: children
+// possibilities are merged in host preorder, the induced subtree is built from the LCAs of consecutive candidates
+// (utils/induced_tree.hpp:128-138) and a bipartite matching assigns children to distinct branches.  With a single-labelled
+// host every list has at most one entry, the induced subtree of k candidates needs exactly the k-1 consecutive LCAs, and
+// the matching degenerates to "all consecutive LCAs are the same node v and no candidate is v itself".  One wavefront over
+// the guest's levels, deepest first; each guest node = (small sort of its children's images by host preorder) + k-1 LCA queries.
+constexpr int WD_MAX_CHILDREN = 64;
+__global__ void __launch_bounds__(256) who_displays_kernel(int64_t nt, int levels, const int32_t* __restrict__ level_off, const int32_t* __restrict__ order,
+                                                           const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj,
+                                                           const int32_t* __restrict__ tlabel, const int32_t* __restrict__ l2h, int64_t nlab,
+                                                           const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table,
+                                                           const int64_t* __restrict__ level_base, int32_t* __restrict__ disp /* -2 dead, -1 not displayed, >= 0 host node */,
+                                                           int32_t* __restrict__ flags /* [0] too many children */) {
+  cg::grid_group grid = cg::this_grid();
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
+  for (int l = levels - 1; l >= 0; --l) {
+    for (int64_t i = level_off[l] + gtid; i < level_off[l + 1]; i += gsize) {
+      const int32_t u = order[i];
+      const int32_t cb = child_off[u], ce = child_off[u + 1];
+      int32_t d;
+      if (cb == ce) {  // guest leaf: base case construct_base_cases :115-126
+        const int32_t lab = tlabel[u];
+        d = lab < 0 ? -2 : ((int64_t)lab < nlab ? l2h[lab] : -1);
+      } else {
+        int32_t img[WD_MAX_CHILDREN]; uint32_t ps[WD_MAX_CHILDREN];
+        int k = 0; bool missing = false, overflow = false;
+        for (int32_t j = cb; j < ce; ++j) {
+          const int32_t c = disp[child_adj[j]];
+          if (c == -2) continue;               // unlabelled dangling subtree: cleaned away
+          if (c == -1) { missing = true; break; }  // merge_child_poss :180-230: an empty child list empties the parent
+          if (k == WD_MAX_CHILDREN) { overflow = true; break; }
+          // insertion sort by host preorder position (sort_by_order :108-111)
+          const uint32_t p = rec[c].pos;
+          int a = k++;
+          while (a > 0 && ps[a - 1] > p) { ps[a] = ps[a - 1]; img[a] = img[a - 1]; --a; }
+          ps[a] = p; img[a] = c;
+        }
+        if (overflow) { flags[0] = 1; d = -1; }
+        else if (missing) d = -1;
+        else if (k == 0) d = -2;
+        else if (k == 1) d = img[0];             // :167: a node with one child maps where the child maps
+        else {
+          const int32_t v = lca_one(rec, keypos, table, level_base, img[0], img[k - 1]);
+          bool ok = true;
+          for (int a = 0; a < k && ok; ++a) ok = img[a] != v;
+          for (int a = 0; a + 1 < k && ok; ++a) ok = lca_one(rec, keypos, table, level_base, img[a], img[a + 1]) == v;
+          d = ok ? v : -1;
+        }
+      }
+      disp[u] = d;
+    }
+    grid.sync();
+  }
+}
+
+__global__ void wd_label_map_kernel(int64_t n, const int32_t* __restrict__ deg, const int32_t* __restrict__ hlabel, int64_t nlab, int32_t* __restrict__ l2h, int32_t* __restrict__ flags) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t lab = hlabel[v];
+    if (lab >= 0 && deg[v] == 0) { if (lab >= nlab) flags[2] = 1; else if (atomicCAS(&l2h[lab], -1, (int32_t)v) != -1) flags[1] = 1; }
+  }
+}
+__global__ void wd_finish_kernel(int64_t nt, int32_t* __restrict__ disp) {
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < nt; u += (int64_t)gridDim.x * blockDim.x) if (disp[u] < 0) disp[u] = -1;
+}
+
 // device exclusive scan of int32 -> int32 (out has n+1 entries); tmp holds ceil(n/SCAN_TILE) int64
 static int device_exclusive_scan(const int32_t* in, int64_t n, int32_t* out, int64_t* tmp, cudaStream_t s) {
   const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
@@ -575,3 +666,82 @@ int pt_rmq_query(const pt_rmq* h, const int64_t* l, const int64_t* r, int64_t* o
 int pt_rmq_free(pt_rmq* h) { rmq_release(h); return PT_OK; }
 
 }  // extern "C"
+
+// ---- who_displays API ------------------------------------------------------------------------------------------------
+extern "C" int pt_tree_who_displays(const int32_t* host_parent, const int32_t* host_label, int64_t n, const int32_t* guest_parent,
+                                    const int32_t* guest_label, int64_t nt, int32_t* out_host_node, pt_mem mem, void* stream) {
+  if (!host_parent || !host_label || !guest_parent || !guest_label || !out_host_node || n <= 0 || nt <= 0 || n > INT32_MAX / 2 || nt > INT32_MAX / 2)
+    return set_error(PT_ERR_INVALID, "pt_tree_who_displays: bad argument");
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  std::vector<void*> owned;
+  pt_lca* H = nullptr;
+  auto cleanup = [&]() { for (void* p : owned) cudaFree(p); if (H) pt_lca_free(H); };
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
+#define WD_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return set_error(PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
+#define WD_PTR(p) do { if (!(p)) { cleanup(); return set_error(PT_ERR_NOMEM, "pt_tree_who_displays: out of device memory"); } } while (0)
+  const int32_t *hp = host_parent, *hl = host_label, *gp = guest_parent, *gl = guest_label;
+  if (mem == PT_MEM_HOST) {
+    int32_t* a = (int32_t*)dalloc((size_t)n * 4); int32_t* b = (int32_t*)dalloc((size_t)n * 4); int32_t* c = (int32_t*)dalloc((size_t)nt * 4); int32_t* d = (int32_t*)dalloc((size_t)nt * 4);
+    WD_PTR(a); WD_PTR(b); WD_PTR(c); WD_PTR(d);
+    WD_TRY(cudaMemcpyAsync(a, host_parent, (size_t)n * 4, cudaMemcpyHostToDevice, s)); WD_TRY(cudaMemcpyAsync(b, host_label, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    WD_TRY(cudaMemcpyAsync(c, guest_parent, (size_t)nt * 4, cudaMemcpyHostToDevice, s)); WD_TRY(cudaMemcpyAsync(d, guest_label, (size_t)nt * 4, cudaMemcpyHostToDevice, s));
+    hp = a; hl = b; gp = c; gl = d;
+  }
+  if (int rc = pt_lca_build(&H, hp, n, PT_MEM_DEVICE, stream)) { cleanup(); return rc; }
+  const int grid = dp.sms * 8;
+  const int64_t nlab = n + nt;
+  int32_t* hdeg = (int32_t*)dalloc((size_t)n * 4 + 4); int32_t* small = (int32_t*)dalloc(128); int32_t* l2h = (int32_t*)dalloc((size_t)nlab * 4);
+  int32_t* tdeg = (int32_t*)dalloc((size_t)nt * 4 + 4); int32_t* toff = (int32_t*)dalloc((size_t)nt * 4 + 4); int32_t* tadj = (int32_t*)dalloc((size_t)nt * 4);
+  int32_t* order = (int32_t*)dalloc((size_t)nt * 4); int32_t* depth = (int32_t*)dalloc((size_t)nt * 4); int32_t* size = (int32_t*)dalloc((size_t)nt * 4);
+  int32_t* pre = (int32_t*)dalloc((size_t)nt * 4); int32_t* level_off = (int32_t*)dalloc((size_t)nt * 4 + 8); int32_t* disp = (int32_t*)dalloc((size_t)nt * 4);
+  int64_t* scan_tmp = (int64_t*)dalloc(((size_t)((std::max(n, nt) + SCAN_TILE - 1) / SCAN_TILE) + 1) * 8);
+  WD_PTR(hdeg); WD_PTR(small); WD_PTR(l2h); WD_PTR(tdeg); WD_PTR(toff); WD_PTR(tadj); WD_PTR(order); WD_PTR(depth); WD_PTR(size); WD_PTR(pre); WD_PTR(level_off); WD_PTR(disp); WD_PTR(scan_tmp);
+  WD_TRY(cudaMemsetAsync(hdeg, 0, (size_t)n * 4 + 4, s)); WD_TRY(cudaMemsetAsync(tdeg, 0, (size_t)nt * 4 + 4, s)); WD_TRY(cudaMemsetAsync(small, 0, 128, s));
+  WD_TRY(cudaMemsetAsync(l2h, 0xff, (size_t)nlab * 4, s));
+  lca_count_kernel<<<grid, 256, 0, s>>>(hp, n, hdeg, small);           // host out-degrees (leaf test); host validity was checked by pt_lca_build
+  lca_count_kernel<<<grid, 256, 0, s>>>(gp, nt, tdeg, small + 8);      // guest children counts + root
+  wd_label_map_kernel<<<grid, 256, 0, s>>>(n, hdeg, hl, nlab, l2h, small + 16);
+  if (int rc = device_exclusive_scan(tdeg, nt, toff, scan_tmp, s)) { cleanup(); return rc; }
+  WD_TRY(cudaMemsetAsync(tdeg, 0, (size_t)nt * 4, s));
+  lca_fill_children_kernel<<<grid, 256, 0, s>>>(gp, nt, toff, tdeg, tadj);
+  int32_t info[32];
+  WD_TRY(cudaMemcpyAsync(info, small, 128, cudaMemcpyDeviceToHost, s));
+  WD_TRY(cudaStreamSynchronize(s));
+  if (info[8] != 1 || info[10]) { cleanup(); return set_error(PT_ERR_INVALID, "pt_tree_who_displays: guest is not a rooted tree (%d roots)", info[8]); }
+  if (info[17]) { cleanup(); return set_error(PT_ERR_INVALID, "single-label map for multi-labeled tree/network"); }  // label_matching.hpp:51-52
+  if (info[18]) { cleanup(); return set_error(PT_ERR_INVALID, "pt_tree_who_displays: label id out of range (must be < n + nt)"); }
+  int occ = 0;
+  WD_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lca_sweeps_kernel, 256, 0));
+  {
+    const int cgrid = dp.sms * std::max(1, std::min(occ, 4));
+    int32_t root = info[9]; int64_t nn = nt; int32_t* ctr = small + 24; int32_t* inf = small + 8;
+    void* args[] = {&nn, &root, &toff, &tadj, &order, &depth, &size, &pre, &level_off, &ctr, &inf};
+    WD_TRY(cudaLaunchCooperativeKernel((void*)lca_sweeps_kernel, dim3(cgrid), dim3(256), args, 0, s));
+  }
+  WD_TRY(cudaMemcpyAsync(info, small, 128, cudaMemcpyDeviceToHost, s));
+  WD_TRY(cudaStreamSynchronize(s));
+  if (info[12] != (int32_t)nt) { cleanup(); return set_error(PT_ERR_INVALID, "pt_tree_who_displays: guest parent array has a cycle"); }
+  {
+    int levels = info[11];
+    WD_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, who_displays_kernel, 256, 0));
+    const int cgrid = (int)std::min<int64_t>((int64_t)dp.sms * std::max(1, std::min(occ, 4)), (nt + 255) / 256);
+    int64_t nn = nt, nl = nlab; int32_t* flags = small + 16;
+    const LcaRecord* rec = H->rec; const u64* keypos = H->keypos; const u64* table = H->table; const int64_t* lb = H->d_level_base;
+    const int32_t* gl2 = gl; const int32_t* l2hc = l2h; const int32_t* lo = level_off; const int32_t* ord = order; const int32_t* co = toff; const int32_t* ca = tadj;
+    void* args[] = {&nn, &levels, &lo, &ord, &co, &ca, &gl2, &l2hc, &nl, &rec, &keypos, &table, &lb, &disp, &flags};
+    WD_TRY(cudaLaunchCooperativeKernel((void*)who_displays_kernel, dim3(std::max(cgrid, 1)), dim3(256), args, 0, s));
+  }
+  wd_finish_kernel<<<grid, 256, 0, s>>>(nt, disp);
+  WD_TRY(cudaMemcpyAsync(info, small, 128, cudaMemcpyDeviceToHost, s));
+  if (mem == PT_MEM_HOST) WD_TRY(cudaMemcpyAsync(out_host_node, disp, (size_t)nt * 4, cudaMemcpyDeviceToHost, s));
+  else WD_TRY(cudaMemcpyAsync(out_host_node, disp, (size_t)nt * 4, cudaMemcpyDeviceToDevice, s));
+  WD_TRY(cudaStreamSynchronize(s));
+#undef WD_TRY
+#undef WD_PTR
+  cleanup();
+  if (info[16]) return set_error(PT_ERR_UNSUPPORTED, "pt_tree_who_displays: a guest node has more than %d children", WD_MAX_CHILDREN);
+  return PT_OK;
+}

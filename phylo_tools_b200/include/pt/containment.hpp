@@ -7,7 +7,7 @@
 //   TreeInTreeContainment<Host,Guest>(host, guest)  :50-54, .displayed() :83
 // plus BatchContainment, the batched form the reference lacks: the engine's unit of work is a BATCH of instances
 // (one warp per instance), so single-instance calls are batches of one.
-// Not provided yet: who_displays(Node) (:72-81) -- SURVEY 8(f) rank 2.
+//   TreeInTreeContainment::who_displays(u)          :72-81 (single-labelled tree hosts; all guest nodes in one GPU pass)
 //
 // Errors follow the reference: duplicate labels and malformed graphs throw std::logic_error
 // (utils/label_matching.hpp:51-52, utils/storage_adj_common.hpp:103-109); engine failures throw std::runtime_error.
@@ -15,6 +15,7 @@
 #pragma once
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 #include "../../../include/pt_gpu.h"
@@ -107,11 +108,32 @@ class TreeInNetContainment {
 template <class Host, class Guest> TreeInNetContainment(const Host&, const Guest&) -> TreeInNetContainment<Host, Guest>;
 template <class Host, class Guest> TreeInNetContainment(Host&&, Guest&&) -> TreeInNetContainment<std::decay_t<Host>, std::decay_t<Guest>>;
 
-// a tree host is a network without reticulations: same engine (the true-cherry rule alone decides it)
+// a tree host is a network without reticulations: same engine (the true-cherry rule alone decides it).
+// who_displays(u) (containment.hpp:72-81): host nodes that minimally display the guest subtree below u, sorted by host
+// preorder -- for a single-labelled host at most one node.  Computed for all guest nodes at once (pt_tree_who_displays).
 template <class Host, class Guest>
 class TreeInTreeContainment : public TreeInNetContainment<Host, Guest> {
+  std::vector<int32_t> table_;
+  void fill_table() {
+    const Host& H = this->host(); const Guest& G = this->guest();
+    std::unordered_map<std::string, int32_t> dict;
+    auto id_of = [&](const std::string& s) -> int32_t { if (s.empty()) return -1; auto it = dict.find(s); if (it != dict.end()) return it->second; const int32_t id = (int32_t)dict.size(); dict.emplace(s, id); return id; };
+    std::vector<int32_t> hp = H.parent_array(), gp = G.parent_array(), hl(H.num_nodes()), gl(G.num_nodes());
+    for (Node v = 0; v < H.num_nodes(); ++v) hl[v] = id_of(H.label(v));
+    for (Node v = 0; v < G.num_nodes(); ++v) gl[v] = id_of(G.label(v));
+    table_.assign(G.num_nodes(), -1);
+    throw_status(pt_tree_who_displays(hp.data(), hl.data(), (int64_t)hp.size(), gp.data(), gl.data(), (int64_t)gp.size(), table_.data(), PT_MEM_HOST, nullptr),
+                 "pt_tree_who_displays");
+  }
+
  public:
   using TreeInNetContainment<Host, Guest>::TreeInNetContainment;
+  std::vector<Node> who_displays(const Node u) {
+    if (table_.empty()) fill_table();
+    std::vector<Node> r;
+    if (table_.at(u) >= 0) r.push_back((Node)table_[u]);
+    return r;
+  }
 };
 template <class Host, class Guest> TreeInTreeContainment(const Host&, const Guest&) -> TreeInTreeContainment<Host, Guest>;
 template <class Host, class Guest> TreeInTreeContainment(Host&&, Guest&&) -> TreeInTreeContainment<std::decay_t<Host>, std::decay_t<Guest>>;

@@ -57,6 +57,16 @@ int main() {
   MyTree T2 = [] { EdgeVec e; LabelMapDefault l; const size_t n = parse_newick(std::string("((a,b),(c,(d,e)));"), e, l); return MyTree(e, l, consecutive_tag(), n); }();
   LCAOracle L2(T2);
   for (Node u = 0; u < T2.num_nodes(); ++u) assert(L2.LCA(u, T2.root()) == T2.root());
+  // who_displays (containment.hpp:72): the pairs printed by the reference itself, see tests/golden/who_ref.json items 1-2
+  {
+    EdgeVec he, ge; LabelMapDefault hl, gl;
+    const size_t hn = parse_newick(std::string("((a,b),(c,d));"), he, hl), gn = parse_newick(std::string("((a,c),(b,d));"), ge, gl);
+    MyTree H(he, hl, consecutive_tag(), hn), G(ge, gl, consecutive_tag(), gn);
+    TreeInTreeContainment c(H, G);
+    const int exp[7] = {-1, 0, 2, 5, 0, 3, 6};
+    for (Node u = 0; u < 7; ++u) { const auto w = c.who_displays(u); assert(exp[u] < 0 ? w.empty() : (w.size() == 1 && w[0] == (Node)exp[u])); }
+    assert(!c.displayed());
+  }
   std::cout << "facade ok\n";
   return 0;
 }

@@ -176,3 +176,43 @@ def test_rmq_known_answers_and_random(pt, oracle):
         got = R.query(l, r)
         assert (got == oracle.sparse_rmq(a, l, r)).all()
         R.free()
+
+
+def test_who_displays_matches_reference_and_oracle(pt, oracle):
+    """pt_tree_who_displays (wavefront over guest levels + device LCA) against the reference's who_displays lists
+    (tests/golden/who_ref.json) and, where the reference crashed, against the oracle"""
+    from conftest import load_golden
+    g = load_golden("who_ref.json")
+    for it in g["items"]:
+        arrays = oracle.tree_arrays_from_newick(it["host"], it["guest"])
+        got = pt.who_displays(*arrays).tolist()
+        if isinstance(it["reference"], list):
+            assert got == [(x[0] if x else -1) for x in it["reference"]], (it["host"], it["guest"])
+        assert got == oracle.who_displays(*arrays).tolist(), (it["host"], it["guest"])
+
+
+def test_who_displays_larger_trees(pt, oracle):
+    rng = np.random.default_rng(8)
+    for leaves, kind in [(40, 0), (150, 0), (150, 1), (400, 2)]:
+        par = pt.random_tree(leaves, 100 + leaves)
+        n = len(par)
+        hl = np.full(n, -1, dtype=np.int32)
+        hl[:leaves] = rng.permutation(leaves)
+        if kind == 0:        # guest = the same tree with node ids permuted: every subtree is displayed by its own image
+            perm = rng.permutation(n).astype(np.int32)
+            gp = np.full(n, -1, dtype=np.int32)
+            gp[perm] = np.where(par >= 0, perm[np.maximum(par, 0)], -1)
+            gl = np.full(n, -1, dtype=np.int32)
+            gl[perm] = hl
+        else:                # another random tree on (a subset of) the labels
+            gleaves = leaves if kind == 1 else leaves // 2
+            gp = pt.random_tree(gleaves, 7 + leaves)
+            gl = np.full(len(gp), -1, dtype=np.int32)
+            gl[:gleaves] = rng.permutation(leaves)[:gleaves]
+        got = pt.who_displays(par, hl, gp, gl)
+        exp = oracle.who_displays(par, hl, gp, gl)
+        assert (got == exp).all(), (leaves, kind, np.where(got != exp)[0][:5])
+        if kind == 0:
+            assert (got >= 0).all()
+    with pytest.raises(pt.PtError):
+        pt.who_displays([-1, 0, 0], [-1, 5, 5], [-1, 0, 0], [-1, 5, 6])   # multi-labelled host

@@ -77,3 +77,18 @@ def test_tc_bruteforce_matches_stored_truth_and_reference(oracle, gold_tc):
             else:
                 assert int(it["reference"]) == it["truth"], it["tag"]
     assert gold_tc["items"][0]["tag"] == "data/test.nw" and gold_tc["items"][0]["truth"] == 0 and gold_tc["items"][0]["reference"] == "S"
+
+
+def test_who_displays_restatement_matches_reference(oracle):
+    """TreeInTreeContainment::who_displays (containment.hpp:72) run here through oracle/_ref/ref_tc who -> who_ref.json"""
+    from conftest import load_golden
+    g = load_golden("who_ref.json")
+    checked = 0
+    for it in g["items"]:
+        if not isinstance(it["reference"], list):
+            continue  # the reference crashed on this pair (guest label missing in the host)
+        exp = [(x[0] if x else -1) for x in it["reference"]]
+        got = oracle.who_displays(*oracle.tree_arrays_from_newick(it["host"], it["guest"])).tolist()
+        assert got == exp, (it["host"], it["guest"])
+        checked += 1
+    assert checked > 100
