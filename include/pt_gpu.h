@@ -92,6 +92,17 @@ int pt_tree_who_displays(const int32_t* host_parent, const int32_t* host_label, 
                          const int32_t* guest_label, int64_t nt, int32_t* out_host_node, pt_mem mem, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Bridges -- replaces  BridgeFinder / list_bridges(N, root)   utils/bridges.hpp:42-128
+ *            (Network::get_bridges utils/network.hpp:85-88; consumer: the bridge-separated components that
+ *             utils/biconnected_comps.hpp:15-120 iterates)
+ * Host network as the same CSR as pt_batch_desc (succ_off[n+1], succ_adj[m]).  is_bridge[e] = 1 iff removing arc e
+ * (CSR position e) disconnects the underlying undirected graph; component[v] (optional) = id of the bridge-free
+ * component of v, named by its topmost node (v's nearest ancestor-or-self that is the root or is entered by a bridge).
+ * ---------------------------------------------------------------------------------------------- */
+int pt_net_bridges(int64_t n, int64_t m, const int32_t* succ_off, const int32_t* succ_adj, uint8_t* is_bridge,
+                   int32_t* component, pt_mem mem, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * RMQ -- replaces  rmq<It>::query / query_offset    rmq/rmq.hpp:63-74
  *                  sparse_rmq                        rmq/sparse_rmq.hpp:45-90
  * query over the half-open range [l, r), l < r; returns the index of the RIGHTMOST minimum, which is what

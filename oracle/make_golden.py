@@ -187,6 +187,25 @@ def make_who():
     print("who_ref.json:", len(items), "pairs,", crashed, "reference crashes")
 
 
+def make_bridges():
+    """networks -> the bridge set of the REFERENCE BridgeFinder (oracle/_ref/ref_tc bridges)"""
+    lines = ["((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));", "((a,(b)#H1),(#H1,c));"]
+    for (l, r, cnt) in [(5, 2, 15), (10, 4, 15), (20, 8, 10), (50, 10, 10), (100, 20, 6)]:
+        lines += [h for h, _ in gen_pairs(cnt, l, r, 9100 + l, 0)]
+    out = run_lines(REF_TC, "bridges", lines)
+    blocks = [b.strip("\n").split("\n") for b in out.split("--\n")][:len(lines)]
+    items = []
+    for s, b in zip(lines, blocks):
+        if b and b[0] in ("CRASH", "EXC"):
+            items.append(dict(newick=s, reference=b[0]))
+        else:
+            items.append(dict(newick=s, reference=[list(map(int, x.split())) for x in b if x.strip()]))
+    crashed = sum(1 for it in items if not isinstance(it["reference"], list))
+    json.dump(dict(source="oracle/_ref/ref_tc bridges (reference utils/bridges.hpp BridgeFinder)", crashed=crashed, items=items),
+              open(os.path.join(GOLD, "bridges_ref.json"), "w"), indent=0)
+    print("bridges_ref.json:", len(items), "networks,", crashed, "reference crashes")
+
+
 def pt_name(i):
     s = ""
     while True:
@@ -202,3 +221,4 @@ if __name__ == "__main__":
     make_tc()
     make_lca()
     make_who()
+    make_bridges()

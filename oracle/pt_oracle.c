@@ -293,3 +293,28 @@ int orc_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, int n
   free(hdeg); free(tdeg); free(l2h); free(hdepth); free(tdepth); free(X); free(bad); free(talive); free(C); free(calive); free(tset); free(hset);
   return 0;
 }
+
+/* ---- bridges: utils/bridges.hpp:42-118 (BridgeFinder) -------------------------------------------------------------------
+ * The reference finds the arcs whose removal disconnects the underlying undirected graph with two DFS passes over DFS
+ * intervals (is_bridge_head :27-30).  Restated from the DEFINITION (remove the arc, test connectivity), which is
+ * independent of both the reference's interval trick and the product's LCA + difference-counting method.
+ * is_bridge[e] for arcs given as (tail[e], head[e]); returns the number of bridges.  Pinned against the reference itself
+ * (tests/golden/bridges_ref.json). */
+int orc_bridges(int n, int m, const int32_t* tail, const int32_t* head, uint8_t* is_bridge) {
+  int32_t* off = (int32_t*)calloc((size_t)n + 1, 4); int32_t* adj = (int32_t*)malloc((size_t)(2 * m + 1) * 4); int32_t* aid = (int32_t*)malloc((size_t)(2 * m + 1) * 4);
+  for (int e = 0; e < m; ++e) { off[tail[e] + 1]++; off[head[e] + 1]++; }
+  for (int v = 0; v < n; ++v) off[v + 1] += off[v];
+  int32_t* pos = (int32_t*)malloc((size_t)(n + 1) * 4); memcpy(pos, off, (size_t)(n + 1) * 4);
+  for (int e = 0; e < m; ++e) { adj[pos[tail[e]]] = head[e]; aid[pos[tail[e]]++] = e; adj[pos[head[e]]] = tail[e]; aid[pos[head[e]]++] = e; }
+  uint8_t* seen = (uint8_t*)malloc((size_t)n); int32_t* stk = (int32_t*)malloc((size_t)n * 4);
+  int count = 0;
+  for (int e = 0; e < m; ++e) {
+    memset(seen, 0, (size_t)n);
+    int sp = 0; stk[sp++] = tail[e]; seen[tail[e]] = 1;
+    while (sp) { const int v = stk[--sp]; for (int k = off[v]; k < off[v + 1]; ++k) if (aid[k] != e && !seen[adj[k]]) { seen[adj[k]] = 1; stk[sp++] = adj[k]; } }
+    is_bridge[e] = !seen[head[e]];
+    count += is_bridge[e];
+  }
+  free(off); free(adj); free(aid); free(pos); free(seen); free(stk);
+  return count;
+}

@@ -39,6 +39,8 @@ def lib():
         L.orc_sparse_rmq_query.restype = C.c_int64
         L.orc_sparse_rmq_query.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
         L.orc_sparse_rmq_free.argtypes = [C.c_void_p]
+        L.orc_bridges.restype = C.c_int
+        L.orc_bridges.argtypes = [C.c_int, C.c_int, i32p, i32p, C.POINTER(C.c_uint8)]
         L.orc_who_displays.restype = C.c_int
         L.orc_who_displays.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p, i32p, i32p]
     return _LIB
@@ -104,6 +106,15 @@ def sparse_rmq(values, ls, rs):
     out = np.array([lib().orc_sparse_rmq_query(h, int(l), int(r)) for l, r in zip(ls, rs)], dtype=np.int64)
     lib().orc_sparse_rmq_free(h)
     return out
+
+
+def bridges(n, edges):
+    """bool per arc: is the arc a bridge of the underlying undirected graph (utils/bridges.hpp)"""
+    e = _arr(edges).reshape(-1, 2)
+    t, h = _arr(e[:, 0]), _arr(e[:, 1])
+    out = np.zeros(max(len(t), 1), dtype=np.uint8)
+    lib().orc_bridges(int(n), len(t), _p(t), _p(h), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out[:len(t)].astype(bool)
 
 
 def who_displays(host_parent, host_label, guest_parent, guest_label):

@@ -18,6 +18,7 @@
 #include "utils/generator.hpp"
 #include "utils/mul_wrapper.hpp"
 #include "utils/containment.hpp"
+#include "utils/bridges.hpp"
 
 #include <chrono>
 #include <fstream>
@@ -88,6 +89,31 @@ int main(int argc, char** argv) {
       for (auto&& p : *e.labels) if (!p.second.empty()) labs.emplace_back((size_t)p.first, p.second);
       std::sort(labs.begin(), labs.end());
       for (auto& p : labs) printf("L %zu %s\n", p.first, p.second.c_str());
+      printf("--\n");
+    }
+    return 0;
+  }
+  if (mode == "bridges") {
+    // list_bridges of the reference (utils/bridges.hpp:42-118) per line: "tail head" pairs, sorted, then "--"
+    std::cout.setstate(std::ios::badbit);
+    for (auto& line : L) {
+      fflush(stdout);
+      pid_t pid = fork();
+      if (pid == 0) {
+        try {
+          ENL e; parse_line(line, e);
+          RONetwork<> N(e.edges, *e.labels, consecutive_tag());
+          std::vector<typename RONetwork<>::Edge> out;
+          BridgeFinder<RONetwork<>, std::vector<typename RONetwork<>::Edge>> bf(N, out);
+          std::vector<std::pair<size_t, size_t>> br;
+          for (auto& uv : out) br.emplace_back((size_t)uv.tail(), (size_t)uv.head());
+          std::sort(br.begin(), br.end());
+          for (auto& p : br) printf("%zu %zu\n", p.first, p.second);
+        } catch (...) { printf("EXC\n"); }
+        fflush(stdout); _exit(0);
+      }
+      int st = 0; waitpid(pid, &st, 0);
+      if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) printf("CRASH\n");
       printf("--\n");
     }
     return 0;

@@ -262,6 +262,17 @@ def who_displays(host_parent, host_label, guest_parent, guest_label):
     return out
 
 
+def net_bridges(succ_off, succ_adj):
+    """pt_net_bridges -> (bool[m] is_bridge per CSR arc, int32[n] component id); utils/bridges.hpp"""
+    so = np.ascontiguousarray(succ_off, dtype=np.int32)
+    sa = np.ascontiguousarray(succ_adj, dtype=np.int32)
+    n, m = len(so) - 1, len(sa)
+    br = np.zeros(max(m, 1), dtype=np.uint8)
+    comp = np.empty(n, dtype=np.int32)
+    _check(_L.pt_net_bridges(n, m, so.ctypes.data, sa.ctypes.data, br.ctypes.data, comp.ctypes.data, PT_MEM_HOST, None), "pt_net_bridges")
+    return br[:m].astype(bool), comp
+
+
 class Rmq:
     """pt_rmq_* : sparse_rmq (rmq/sparse_rmq.hpp:45-90): index of the rightmost minimum of [l, r)"""
 

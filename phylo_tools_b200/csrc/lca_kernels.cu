@@ -425,18 +425,19 @@ struct pt_lca {
   int64_t n = 0, nblocks = 0, levels = 0, table_levels = 0, device_bytes = 0;
   float build_ms = 0.f;
   LcaRecord* rec = nullptr; u64* keypos = nullptr; u64* table = nullptr; int64_t* d_level_base = nullptr;
+  int32_t* size = nullptr;  // subtree sizes (kept only when requested: bridges need preorder intervals)
   int32_t *d_u = nullptr, *d_v = nullptr, *d_out = nullptr; int64_t qcap = 0;  // staging for HOST queries
 };
 
 static void lca_release(pt_lca* h) {
   if (!h) return;
-  cudaFree(h->rec); cudaFree(h->keypos); cudaFree(h->table); cudaFree(h->d_level_base); cudaFree(h->d_u); cudaFree(h->d_v); cudaFree(h->d_out);
+  cudaFree(h->rec); cudaFree(h->keypos); cudaFree(h->table); cudaFree(h->d_level_base); cudaFree(h->d_u); cudaFree(h->d_v); cudaFree(h->d_out); cudaFree(h->size);
   delete h;
 }
 
 extern "C" {
 
-int pt_lca_build(pt_lca** out, const int32_t* parent, int64_t n, pt_mem parent_mem, void* stream) {
+static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem parent_mem, void* stream, bool keep_size) {
   if (!out || !parent || n <= 0 || n > (int64_t)INT32_MAX - 64) return set_error(PT_ERR_INVALID, "pt_lca_build: bad argument (n must be in [1, 2^31-65])");
   *out = nullptr;
   if (int rc = require_device()) return rc;
@@ -454,7 +455,7 @@ int pt_lca_build(pt_lca** out, const int32_t* parent, int64_t n, pt_mem parent_m
   int rc = PT_OK;
   auto cleanup = [&]() {
     if (parent_mem == PT_MEM_HOST) cudaFree(d_parent);
-    cudaFree(deg); cudaFree(child_off); cudaFree(child_adj); cudaFree(order); cudaFree(depth); cudaFree(size); cudaFree(pre); cudaFree(level_off); cudaFree(small);
+    cudaFree(deg); cudaFree(child_off); cudaFree(child_adj); cudaFree(order); cudaFree(depth); if (size != h->size) cudaFree(size); cudaFree(pre); cudaFree(level_off); cudaFree(small);
     cudaFree(nodeat); cudaFree(scan_tmp);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -529,10 +530,13 @@ int pt_lca_build(pt_lca** out, const int32_t* parent, int64_t n, pt_mem parent_m
   LCA_TRY(cudaStreamSynchronize(s));
   LCA_TRY(cudaEventElapsedTime(&h->build_ms, ev0, ev1));
 #undef LCA_TRY
+  if (keep_size) h->size = size;
   cleanup();
   *out = h;
   return PT_OK;
 }
+
+int pt_lca_build(pt_lca** out, const int32_t* parent, int64_t n, pt_mem parent_mem, void* stream) { return lca_build_impl(out, parent, n, parent_mem, stream, false); }
 
 int pt_lca_query(const pt_lca* hc, const int32_t* u, const int32_t* v, int32_t* out, int64_t q, pt_mem mem, void* stream) {
   pt_lca* h = const_cast<pt_lca*>(hc);
@@ -743,5 +747,102 @@ extern "C" int pt_tree_who_displays(const int32_t* host_parent, const int32_t* h
 #undef WD_PTR
   cleanup();
   if (info[16]) return set_error(PT_ERR_UNSUPPORTED, "pt_tree_who_displays: a guest node has more than %d children", WD_MAX_CHILDREN);
+  return PT_OK;
+}
+
+// ---- bridges / 2-edge-connected components of a rooted network -------------------------------------------------------------
+// BridgeFinder utils/bridges.hpp:42-118 (two recursive DFS passes over DFS intervals) re-designed as data-parallel steps:
+//   1. spanning tree: every node keeps its first in-arc (a rooted DAG with one root gives a rooted tree)
+//   2. pt_lca on that tree (preorder positions, subtree sizes)
+//   3. every other arc (u,v) closes a cycle through a = lca(u,v): cnt[u]++, cnt[v]++, cnt[a] -= 2 (one batched LCA pass)
+//   4. prefix sums of cnt in preorder: the tree arc into w is covered iff the sum over w's preorder interval is > 0
+//   5. a tree arc that no cycle covers is a bridge; components = pointer jumping to the nearest ancestor entered by a bridge
+namespace ptgpu {
+__global__ void br_first_parent_kernel(int64_t n, int64_t m, const int32_t* __restrict__ succ_off, const int32_t* __restrict__ succ_adj, int32_t* __restrict__ tree_arc) {
+  // tree_arc[v] = smallest arc id entering v
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x)
+    for (int32_t e = succ_off[u]; e < succ_off[u + 1]; ++e) atomicMin(&tree_arc[succ_adj[e]], e);
+}
+__global__ void br_tree_parent_kernel(int64_t n, const int32_t* __restrict__ succ_off, const int32_t* __restrict__ succ_adj, const int32_t* __restrict__ tree_arc,
+                                      int32_t* __restrict__ arc_tail, int32_t* __restrict__ parent) {
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+    for (int32_t e = succ_off[u]; e < succ_off[u + 1]; ++e) { arc_tail[e] = (int32_t)u; if (tree_arc[succ_adj[e]] == e) parent[succ_adj[e]] = (int32_t)u; }
+  }
+}
+__global__ void br_cover_kernel(int64_t m, const int32_t* __restrict__ arc_tail, const int32_t* __restrict__ succ_adj, const int32_t* __restrict__ tree_arc,
+                                const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table, const int64_t* __restrict__ level_base,
+                                int32_t* __restrict__ cntpos) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < m; e += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t u = arc_tail[e], v = succ_adj[e];
+    if (tree_arc[v] == (int32_t)e) continue;
+    const int32_t a = lca_one(rec, keypos, table, level_base, u, v);
+    atomicAdd(&cntpos[rec[u].pos], 1); atomicAdd(&cntpos[rec[v].pos], 1); atomicAdd(&cntpos[rec[a].pos], -2);
+  }
+}
+__global__ void br_mark_kernel(int64_t n, const int32_t* __restrict__ parent, const int32_t* __restrict__ tree_arc, const LcaRecord* __restrict__ rec,
+                               const int32_t* __restrict__ size, const int32_t* __restrict__ prefix, uint8_t* __restrict__ is_bridge, int32_t* __restrict__ up) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    if (parent[v] < 0) { up[v] = (int32_t)v; continue; }
+    const uint32_t p = rec[v].pos;
+    const bool covered = prefix[p + size[v]] - prefix[p] > 0;
+    if (!covered) is_bridge[tree_arc[v]] = 1;
+    up[v] = covered ? parent[v] : (int32_t)v;
+  }
+}
+__global__ void br_jump_kernel(int64_t n, int32_t* __restrict__ up, int32_t* __restrict__ changed) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t a = up[v], b = up[a];
+    if (a != b) { up[v] = b; *changed = 1; }
+  }
+}
+}  // namespace ptgpu
+
+extern "C" int pt_net_bridges(int64_t n, int64_t m, const int32_t* succ_off, const int32_t* succ_adj, uint8_t* is_bridge, int32_t* component, pt_mem mem, void* stream) {
+  if (n <= 0 || m < 0 || !succ_off || (!succ_adj && m > 0) || !is_bridge || n > INT32_MAX / 2 || m > INT32_MAX / 2) return set_error(PT_ERR_INVALID, "pt_net_bridges: bad argument");
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  std::vector<void*> owned; pt_lca* H = nullptr;
+  auto cleanup = [&]() { for (void* p : owned) cudaFree(p); if (H) pt_lca_free(H); };
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
+#define BR_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return set_error(PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
+#define BR_PTR(p) do { if (!(p)) { cleanup(); return set_error(PT_ERR_NOMEM, "pt_net_bridges: out of device memory"); } } while (0)
+  const int32_t *so = succ_off, *sa = succ_adj;
+  if (mem == PT_MEM_HOST) {
+    int32_t* a = (int32_t*)dalloc((size_t)(n + 1) * 4); int32_t* b = (int32_t*)dalloc((size_t)m * 4); BR_PTR(a); BR_PTR(b);
+    BR_TRY(cudaMemcpyAsync(a, succ_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s)); if (m) BR_TRY(cudaMemcpyAsync(b, succ_adj, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+    so = a; sa = b;
+  }
+  const int grid = dp.sms * 8;
+  int32_t* tree_arc = (int32_t*)dalloc((size_t)n * 4); int32_t* arc_tail = (int32_t*)dalloc((size_t)m * 4); int32_t* parent = (int32_t*)dalloc((size_t)n * 4);
+  int32_t* cntpos = (int32_t*)dalloc((size_t)(n + 1) * 4); int32_t* prefix = (int32_t*)dalloc((size_t)(n + 1) * 4); int32_t* up = (int32_t*)dalloc((size_t)n * 4);
+  uint8_t* d_br = (uint8_t*)dalloc((size_t)m + 1); int32_t* flag = (int32_t*)dalloc(16);
+  int64_t* scan_tmp = (int64_t*)dalloc(((size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1) * 8);
+  BR_PTR(tree_arc); BR_PTR(arc_tail); BR_PTR(parent); BR_PTR(cntpos); BR_PTR(prefix); BR_PTR(up); BR_PTR(d_br); BR_PTR(flag); BR_PTR(scan_tmp);
+  BR_TRY(cudaMemsetAsync(tree_arc, 0x7f, (size_t)n * 4, s)); BR_TRY(cudaMemsetAsync(parent, 0xff, (size_t)n * 4, s)); BR_TRY(cudaMemsetAsync(cntpos, 0, (size_t)(n + 1) * 4, s));
+  BR_TRY(cudaMemsetAsync(d_br, 0, (size_t)m + 1, s));
+  br_first_parent_kernel<<<grid, 256, 0, s>>>(n, m, so, sa, tree_arc);
+  br_tree_parent_kernel<<<grid, 256, 0, s>>>(n, so, sa, tree_arc, arc_tail, parent);
+  BR_TRY(cudaGetLastError());
+  if (int rc = lca_build_impl(&H, parent, n, PT_MEM_DEVICE, stream, true)) { cleanup(); return rc; }  // also validates: one root, no cycle
+  br_cover_kernel<<<grid, 256, 0, s>>>(m, arc_tail, sa, tree_arc, H->rec, H->keypos, H->table, H->d_level_base, cntpos);
+  if (int rc = device_exclusive_scan(cntpos, n, prefix, scan_tmp, s)) { cleanup(); return rc; }
+  br_mark_kernel<<<grid, 256, 0, s>>>(n, parent, tree_arc, H->rec, H->size, prefix, d_br, up);
+  for (int it = 0; it < 40; ++it) {
+    int32_t h = 0;
+    BR_TRY(cudaMemsetAsync(flag, 0, 4, s));
+    br_jump_kernel<<<grid, 256, 0, s>>>(n, up, flag);
+    BR_TRY(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, s));
+    BR_TRY(cudaStreamSynchronize(s));
+    if (!h) break;
+  }
+  const cudaMemcpyKind kind = mem == PT_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (m) BR_TRY(cudaMemcpyAsync(is_bridge, d_br, (size_t)m, kind, s));
+  if (component) BR_TRY(cudaMemcpyAsync(component, up, (size_t)n * 4, kind, s));
+  BR_TRY(cudaStreamSynchronize(s));
+#undef BR_TRY
+#undef BR_PTR
+  cleanup();
   return PT_OK;
 }

@@ -216,3 +216,49 @@ def test_who_displays_larger_trees(pt, oracle):
             assert (got >= 0).all()
     with pytest.raises(pt.PtError):
         pt.who_displays([-1, 0, 0], [-1, 5, 5], [-1, 0, 0], [-1, 5, 6])   # multi-labelled host
+
+
+def _csr(n, edges):
+    edges = sorted(edges)
+    off = np.zeros(n + 1, dtype=np.int32)
+    for a, _ in edges:
+        off[a + 1] += 1
+    return np.cumsum(off).astype(np.int32), np.array([b for _, b in edges], dtype=np.int32).reshape(-1), edges
+
+
+def test_bridges_match_reference_and_oracle(pt, oracle):
+    """pt_net_bridges (spanning tree + batched LCA + difference counting) against the reference BridgeFinder's bridge
+    sets (tests/golden/bridges_ref.json) and the remove-and-test oracle; components = union of non-bridge arcs"""
+    from conftest import load_golden
+    from oracle.newick import parse_newick
+    g = load_golden("bridges_ref.json")
+    for it in g["items"]:
+        n, e, _ = parse_newick(it["newick"])
+        off, adj, es = _csr(n, e)
+        br, comp = pt.net_bridges(off, adj)
+        assert sorted([list(x) for x, b in zip(es, br) if b]) == it["reference"], it["newick"][:60]
+        # components: two nodes share an id iff they are joined by non-bridge arcs
+        uf = list(range(n))
+        def find(x):
+            while uf[x] != x:
+                uf[x] = uf[uf[x]]; x = uf[x]
+            return x
+        for (a, b), isb in zip(es, br):
+            if not isb:
+                uf[find(a)] = find(b)
+        groups = {}
+        for v in range(n):
+            groups.setdefault(find(v), set()).add(int(comp[v]))
+        assert all(len(s) == 1 for s in groups.values()) and len({next(iter(s)) for s in groups.values()}) == len(groups)
+    # a larger network against the oracle
+    p = pt.Packer()
+    p.add_generated(3, 400, 60, 5, 0)
+    a = p.arrays()
+    for i in range(3):
+        hb, he = int(a["host_node_off"][i]), int(a["host_node_off"][i + 1])
+        n = he - hb
+        off = a["host_succ_off"][hb + i: hb + i + n + 1]
+        adj = a["host_succ_adj"][int(a["host_arc_off"][i]): int(a["host_arc_off"][i + 1])]
+        br, comp = pt.net_bridges(off, adj)
+        edges = [(int(t), int(h)) for t, h in zip(np.repeat(np.arange(n), np.diff(off)), adj)]
+        assert (br == oracle.bridges(n, edges)).all()

@@ -92,3 +92,13 @@ def test_who_displays_restatement_matches_reference(oracle):
         assert got == exp, (it["host"], it["guest"])
         checked += 1
     assert checked > 100
+
+
+def test_bridges_restatement_matches_reference(oracle):
+    """BridgeFinder (utils/bridges.hpp) run here through oracle/_ref/ref_tc bridges -> bridges_ref.json"""
+    from conftest import load_golden
+    g = load_golden("bridges_ref.json")
+    for it in g["items"]:
+        n, e, _ = parse_newick(it["newick"])
+        br = oracle.bridges(n, e)
+        assert sorted([list(x) for x, b in zip(e, br) if b]) == it["reference"]
