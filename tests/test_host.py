@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_exports_every_declared_symbol(pt):
     hdr = open(os.path.join(ROOT, "include", "pt_gpu.h")).read()
-    declared = sorted(set(re.findall(r"\b(pt_[a-z0-9_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"^(?:const char\*|int64_t|int)\s+(pt_[a-z0-9_]+)\s*\(", hdr, flags=re.M)))
     assert len(declared) >= 24
     lib = C.CDLL(os.path.join(ROOT, "phylo_tools_b200", "libptgpu.so"))
     for name in declared:
