@@ -79,7 +79,8 @@ struct TcWork {
   I *ioff, *iarc;        // in CSR
   I *hlab;               // label of a live labelled leaf, else -1
   I *lvl;                // height (longest path to a leaf) from the wavefront; scratch otherwise
-  int32_t *hcnt, *haux, *hscr;  // atomic / scan scratch, capN+1 each
+  int32_t *hcnt, *haux;  // atomic scratch, capN+1 each
+  I* hscr;               // FIFO of the wavefront / scan target of emit_child, capN+1
   uint32_t* lset;        // capN * W : labels reachable below each node
   // guest tree
   I *tpar, *tlab;        // tpar: -1 root, -2 deleted
@@ -93,16 +94,16 @@ struct TcWork {
   // signature words: exact label sets up to kMaxExactWords * 32 labels, hashed (label mod bits) beyond: a hashed set is a
   // SUPERSET, so "cannot reach" stays certain and the sibling rule stays sound, it only fires less often.  Measured in the
   // simulator (gen instances l=100..1000): 32-, 64- and 512-bit signatures give the same number of branchings to within
-  // 3 %, because the rule only ever needs to separate a handful of nearby leaves; 64 bits keep the working set small
+  // 3 %, because the rule only ever needs to separate a handful of nearby leaves; 32 bits keep the working set small
   // (shared-memory occupancy) and make the rule independent of the instance size (n = 10^6 needs 8 MB, not 62 GB).
-  static constexpr int kMaxExactWords = 2;
+  static constexpr int kMaxExactWords = 1;
   PT_HD static int sig_words(int L) { const int w = (L + 31) / 32; return w < 1 ? 1 : (w > kMaxExactWords ? kMaxExactWords : w); }
   PT_HD static size_t bytes(int N, int M, int NT, int L) {
     const int W = sig_words(L);
     size_t b = 0;
-    b += (size_t)(2 * M + (N + 1) + M + (N + 1) + M + N + (N + 1)) * sizeof(I);  // at ah ooff oarc ioff iarc hlab lvl
+    b += (size_t)(2 * M + (N + 1) + M + (N + 1) + M + N + 2 * (N + 1)) * sizeof(I);  // at ah ooff oarc ioff iarc hlab lvl hscr
     b = (b + 3) & ~(size_t)3;
-    b += (size_t)(3 * (N + 1)) * 4;                                         // hcnt haux hscr
+    b += (size_t)(2 * (N + 1)) * 4;                                         // hcnt haux
     b += (size_t)N * W * 4;                                                 // lset
     b += (size_t)(2 * NT) * sizeof(I);                                      // tpar tlab
     b = (b + 3) & ~(size_t)3;
@@ -119,9 +120,9 @@ struct TcWork {
     at = (I*)take((size_t)M * sizeof(I)); ah = (I*)take((size_t)M * sizeof(I));
     ooff = (I*)take((size_t)(N + 1) * sizeof(I)); oarc = (I*)take((size_t)M * sizeof(I));
     ioff = (I*)take((size_t)(N + 1) * sizeof(I)); iarc = (I*)take((size_t)M * sizeof(I));
-    hlab = (I*)take((size_t)N * sizeof(I)); lvl = (I*)take((size_t)(N + 1) * sizeof(I));
+    hlab = (I*)take((size_t)N * sizeof(I)); lvl = (I*)take((size_t)(N + 1) * sizeof(I)); hscr = (I*)take((size_t)(N + 1) * sizeof(I));
     p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
-    hcnt = (int32_t*)take((size_t)(N + 1) * 4); haux = (int32_t*)take((size_t)(N + 1) * 4); hscr = (int32_t*)take((size_t)(N + 1) * 4);
+    hcnt = (int32_t*)take((size_t)(N + 1) * 4); haux = (int32_t*)take((size_t)(N + 1) * 4);
     lset = (uint32_t*)take((size_t)N * W * 4);
     tpar = (I*)take((size_t)NT * sizeof(I)); tlab = (I*)take((size_t)NT * sizeof(I));
     p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
@@ -414,7 +415,7 @@ struct TcSolver {
       w.hcnt[v] = outdeg(v);
       w.lvl[v] = (I)LVL_INF;
       if (w.hlab[v] >= 0) { const int b = w.hlab[v] % (W * 32); w.lset[v * W + (b >> 5)] = 1u << (b & 31); }
-      if (outdeg(v) == 0 && (indeg(v) > 0 || w.hlab[v] >= 0)) { w.lvl[v] = (I)0; w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = v; }
+      if (outdeg(v) == 0 && (indeg(v) > 0 || w.hlab[v] >= 0)) { w.lvl[v] = (I)0; w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)v; }
     }
     ex.sync();
     int head = 0;
@@ -427,7 +428,7 @@ struct TcSolver {
         PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) {
           const int p = w.at[in_arc(v, k)];
           PT_NOUNROLL for (int j = 0; j < W; ++j) { const uint32_t b = w.lset[v * W + j]; if (b) ex.atomic_or(&w.lset[p * W + j], b); }
-          if (ex.atomic_add(&w.hcnt[p], -1) == 1) { w.lvl[p] = (I)(lv + 1); w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = p; }
+          if (ex.atomic_add(&w.hcnt[p], -1) == 1) { w.lvl[p] = (I)(lv + 1); w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)p; }
         }
       }
       head = tail;
@@ -674,7 +675,7 @@ struct TcSolver {
     PT_FOR(v, n) {
       w.hcnt[v] = outdeg(v);
       if (indeg(v) == 0) { ++roots; w.sc[F_ROOT] = v; }
-      if (!trusted && outdeg(v) == 0) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = v;
+      if (!trusted && outdeg(v) == 0) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)v;
     }
     const int nroots = ex.reduce_add(roots);
     if (n > 0 && nroots != 1) { set_scalar(F_TMP, 0); return false; }
@@ -686,7 +687,7 @@ struct TcSolver {
       const int cnt = tail - head;
       PT_FOR(i, cnt) {
         const int v = w.hscr[head + i];
-        PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = p; }
+        PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)p; }
       }
       head = tail;
       ex.sync();

@@ -197,7 +197,7 @@ struct TcSink {
 enum { CNT_DISPLAYED = 0, CNT_ITEMS, CNT_BRANCH_ITEMS, CNT_CHERRIES, CNT_RET, CNT_ARCS, CNT_PASSES, CNT_ERRORS, CNT_N };
 
 template <class I>
-__global__ void __launch_bounds__(512) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
+__global__ void __launch_bounds__(640) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
                                                         uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                         uint8_t* __restrict__ branched, int32_t* __restrict__ ticket,
                                                         unsigned long long* __restrict__ counters) {
@@ -599,9 +599,9 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     size_t smem = 0, ws_bytes = 0;
     int cta_grid_cap = 0;
     if (!use_cta) {
-      // occupancy: as many warps per SM as shared memory (warp_bytes each) and the register file (launch bound 512 threads
-      // -> at most 128 registers/thread -> 16 warps) allow, in one CTA per SM
-      int warps_per_sm = (int)std::min<size_t>(16, ((size_t)dp.smem_optin) / warp_bytes);
+      // occupancy: as many warps per SM as shared memory (warp_bytes each) and the register file (launch bound 640 threads
+      // -> at most 102 registers/thread -> 20 warps) allow, in one CTA per SM
+      int warps_per_sm = (int)std::min<size_t>(20, ((size_t)dp.smem_optin) / warp_bytes);
       wpc = std::max(warps_per_sm, 1);
       smem = (size_t)wpc * warp_bytes;
       PT_CUDA(cudaFuncSetAttribute(tc_reduce_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
