@@ -249,3 +249,25 @@ def test_instances_beyond_shared_memory(pt):
     assert v[:23].all() and not v[23]
     with pytest.raises(AssertionError):
         assert (pt.Batch(a).contain(path=1)[1] == 0).all()   # forcing the shared-memory path reports PT_INST_TOO_LARGE
+
+
+def test_edge_cases(pt, oracle):
+    """empty batch, one-node trees, one and two labels, unlabelled hosts, ragged batch (tiny next to large instances)"""
+    b = pt.Batch(dict(num_instances=0, host_node_off=np.zeros(1, np.int64), host_arc_off=np.zeros(1, np.int64), guest_node_off=np.zeros(1, np.int64),
+                      host_succ_off=np.zeros(1, np.int32), host_succ_adj=np.zeros(1, np.int32), host_label=np.zeros(1, np.int32),
+                      guest_parent=np.zeros(1, np.int32), guest_label=np.zeros(1, np.int32)))
+    v, s, c = b.contain()
+    b.free()
+    assert len(v) == 0 and c["instances"] == 0
+    pairs = [("a;", "a;"), ("a;", "b;"), ("(a,b);", "(a,b);"), ("(a,b);", "a;"), ("((a,b),c);", "(a,b);"), ("((a)#H1,(#H1,b));", "(a,b);"),
+             ("(a,(b,c));", "(c,(b,a));"), ("(,);", "(a,b);"), ("(a,b);", "(,);"), ("((a,b),(c,d));", "(((a,b)),((c,d)));")]
+    p = pt.Packer()
+    for h, g in pairs:
+        p.add_newick(h, g)
+    p.add_generated(3, 100, 20, 5, 0)       # ragged: 239-node instances next to 1-node ones
+    p.add_newick("(a,(b,c));", "((a,b),c);")
+    v, s, _ = _solve(pt, p)
+    assert (s == 0).all()
+    truth = [oracle.tc_bruteforce_newick(*p.newick(i))[0] for i in range(len(p))]
+    assert v.astype(int).tolist() == truth
+    assert truth[:10] == [1, 0, 1, 1, 1, 1, 0, 0, 1, 1] and truth[10:13] == [1, 1, 1] and truth[13] == 0
