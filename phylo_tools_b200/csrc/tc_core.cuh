@@ -84,7 +84,7 @@ struct TcWork {
   uint32_t* lset;        // capN * W : labels reachable below each node
   // guest tree
   I *tpar, *tlab;        // tpar: -1 root, -2 deleted
-  I *tdeg, *tleaf, *tmin, *tmax;  // live children, live leaf children, min / max leaf-child label (16-bit atomics on the warp path)
+  int32_t *tdeg, *tleaf, *tmin, *tmax;  // live children, live leaf children, min / max leaf-child label
   // labels
   I *l2h, *l2t;
   // scalars (shared)
@@ -105,8 +105,9 @@ struct TcWork {
     b = (b + 3) & ~(size_t)3;
     b += (size_t)(2 * (N + 1)) * 4;                                         // hcnt haux
     b += (size_t)N * W * 4;                                                 // lset
-    b += (size_t)(2 * NT + 4 * (NT + 1)) * sizeof(I);                       // tpar tlab tdeg tleaf tmin tmax
+    b += (size_t)(2 * NT) * sizeof(I);                                      // tpar tlab
     b = (b + 3) & ~(size_t)3;
+    b += (size_t)(4 * (NT + 1)) * 4;                                        // tdeg tleaf tmin tmax
     b += (size_t)(2 * L) * sizeof(I);                                       // l2h l2t
     b = (b + 3) & ~(size_t)3;
     b += kScalars * 4;
@@ -124,9 +125,9 @@ struct TcWork {
     hcnt = (int32_t*)take((size_t)(N + 1) * 4); haux = (int32_t*)take((size_t)(N + 1) * 4);
     lset = (uint32_t*)take((size_t)N * W * 4);
     tpar = (I*)take((size_t)NT * sizeof(I)); tlab = (I*)take((size_t)NT * sizeof(I));
-    tdeg = (I*)take((size_t)(NT + 1) * sizeof(I)); tleaf = (I*)take((size_t)(NT + 1) * sizeof(I));
-    tmin = (I*)take((size_t)(NT + 1) * sizeof(I)); tmax = (I*)take((size_t)(NT + 1) * sizeof(I));
     p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
+    tdeg = (int32_t*)take((size_t)(NT + 1) * 4); tleaf = (int32_t*)take((size_t)(NT + 1) * 4);
+    tmin = (int32_t*)take((size_t)(NT + 1) * 4); tmax = (int32_t*)take((size_t)(NT + 1) * 4);
     l2h = (I*)take((size_t)L * sizeof(I)); l2t = (I*)take((size_t)L * sizeof(I));
     p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
     sc = (int32_t*)take(kScalars * 4);
@@ -146,7 +147,6 @@ struct TcSolver {
   enum { F_FLAG = 0, F_FAIL = 1, F_ROOT = 2, F_TROOT = 3, F_NLAB = 4, F_BEST = 5, F_STATUS = 6, F_TMP = 7, F_TMP2 = 8 };
   static constexpr int TDEAD = -2;
   static constexpr int LVL_INF = sizeof(I) == 2 ? 32000 : 0x3fffffff;
-  static constexpr int LAB_INF = sizeof(I) == 2 ? 0x7fff : 0x7fffffff;  // 'no label yet' in tmin
 
   // ---- small helpers -----------------------------------------------------------------------------------
   PT_HD int outdeg(int v) const { return w.ooff[v + 1] - w.ooff[v]; }
@@ -267,7 +267,7 @@ struct TcSolver {
         while (p >= 0 && w.tdeg[p] == 1) p = w.tpar[p];
         np = p;
       }
-      w.tmin[t] = (I)np;
+      w.tmin[t] = np;
     }
     ex.sync();
     PT_FOR(t, nt) { w.tpar[t] = (I)w.tmin[t]; if (w.tmin[t] == -1) w.sc[F_TROOT] = t; }
@@ -452,7 +452,7 @@ struct TcSolver {
       if (h >= 0) {
         if (indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (q >= 0) { w.hcnt[q] = 0; w.haux[q] = -1; } }
         const int p = w.tpar[w.l2t[l]];
-        if (p >= 0) w.tmin[p] = (I)LAB_INF;
+        if (p >= 0) w.tmin[p] = 0x7fffffff;
       }
     }
     ex.sync();
@@ -509,7 +509,7 @@ struct TcSolver {
   // ---- guest cherries with exactly two leaves: tmin/tmax = their labels, tleaf = 2 ---------------------------
   PT_NI void guest_cherries() {
     ex.phase = 8;
-    PT_FOR(t, nt) { w.tleaf[t] = 0; w.tmin[t] = (I)LAB_INF; w.tmax[t] = (I)-1; }
+    PT_FOR(t, nt) { w.tleaf[t] = 0; w.tmin[t] = 0x7fffffff; w.tmax[t] = -1; }
     ex.sync();
     PT_FOR(l, L) {
       const int t = w.l2t[l];
@@ -655,7 +655,7 @@ struct TcSolver {
       }
     }
     // guest
-    PT_FOR(t, nt + 1) { w.tleaf[t] = (I)((t < nt && w.tpar[t] != TDEAD) ? 1 : 0); }
+    PT_FOR(t, nt + 1) { w.tleaf[t] = (t < nt && w.tpar[t] != TDEAD) ? 1 : 0; }
     ex.sync();
     ex.exclusive_scan(w.tleaf, w.tmin, nt);
     const int nt2 = w.tmin[nt];

@@ -75,18 +75,6 @@ struct WarpEx {
   __device__ __forceinline__ int atomic_add(int32_t* p, int v) const { return atomicAdd(p, v); }
   __device__ __forceinline__ int atomic_min(int32_t* p, int v) const { return atomicMin(p, v); }
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
-  // the guest-side counters are 16-bit to keep the per-instance working set small (occupancy); shared memory has a native
-  // 16-bit compare-and-swap, the rest is a CAS loop (these are cold: a handful per rule pass)
-  template <class F>
-  __device__ __forceinline__ int rmw16(int16_t* p, F f) const {
-    unsigned short* q = reinterpret_cast<unsigned short*>(p);
-    unsigned short old = *(volatile unsigned short*)q, assumed;
-    do { assumed = old; old = atomicCAS(q, assumed, (unsigned short)(int16_t)f((int)(int16_t)assumed)); } while (old != assumed);
-    return (int)(int16_t)old;
-  }
-  __device__ __forceinline__ int atomic_add(int16_t* p, int v) const { return rmw16(p, [v](int x) { return x + v; }); }
-  __device__ __forceinline__ int atomic_min(int16_t* p, int v) const { return rmw16(p, [v](int x) { return x < v ? x : v; }); }
-  __device__ __forceinline__ int atomic_max(int16_t* p, int v) const { return rmw16(p, [v](int x) { return x > v ? x : v; }); }
   __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
@@ -95,8 +83,8 @@ struct WarpEx {
   // out[0..n] = exclusive prefix sums of in[0..n): tiles of 32 consecutive elements (bank-conflict free), one shuffle scan
   // per tile with a running carry.  (The first version gave every lane a contiguous chunk: 8-way bank conflicts, 7 % of all
   // stall samples of the kernel.)
-  template <class S, class T>
-  __device__ __forceinline__ void exclusive_scan(const S* in, T* out, int n) const {
+  template <class T>
+  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) const {
     __syncwarp();
     int carry = 0;
     for (int base = 0; base < n; base += 32) {
@@ -167,8 +155,8 @@ struct CtaEx {
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   // tile-by-tile block scan with a running carry: coalesced, two barriers per tile of blockDim.x elements
-  template <class S, class T>
-  __device__ __forceinline__ void exclusive_scan(const S* in, T* out, int n) {
+  template <class T>
+  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     sync();
     int carry = 0;
@@ -209,7 +197,7 @@ struct TcSink {
 enum { CNT_DISPLAYED = 0, CNT_ITEMS, CNT_BRANCH_ITEMS, CNT_CHERRIES, CNT_RET, CNT_ARCS, CNT_PASSES, CNT_ERRORS, CNT_N };
 
 template <class I>
-__global__ void __launch_bounds__(704) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
+__global__ void __launch_bounds__(640) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
                                                         uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                         uint8_t* __restrict__ branched, int32_t* __restrict__ ticket,
                                                         unsigned long long* __restrict__ counters) {
@@ -611,9 +599,9 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     size_t smem = 0, ws_bytes = 0;
     int cta_grid_cap = 0;
     if (!use_cta) {
-      // occupancy: as many warps per SM as shared memory (warp_bytes each) and the register file (launch bound 704 threads
-      // -> at most 93 registers/thread -> 22 warps) allow, in one CTA per SM
-      int warps_per_sm = (int)std::min<size_t>(22, ((size_t)dp.smem_optin) / warp_bytes);
+      // occupancy: as many warps per SM as shared memory (warp_bytes each) and the register file (launch bound 640 threads
+      // -> at most 102 registers/thread -> 20 warps) allow, in one CTA per SM
+      int warps_per_sm = (int)std::min<size_t>(20, ((size_t)dp.smem_optin) / warp_bytes);
       wpc = std::max(warps_per_sm, 1);
       smem = (size_t)wpc * warp_bytes;
       PT_CUDA(cudaFuncSetAttribute(tc_reduce_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -38,13 +38,13 @@ struct HostEx {
   int uniform(const int32_t* p) const { return *p; }
   int reduce_or(int v) const { return v; }
   int reduce_add(int v) const { return v; }
-  template <class T> int atomic_add(T* p, int v) const { T o = *p; *p = (T)(o + v); return (int)o; }
-  template <class T> int atomic_min(T* p, int v) const { T o = *p; if (v < (int)o) *p = (T)v; return (int)o; }
-  template <class T> int atomic_max(T* p, int v) const { T o = *p; if (v > (int)o) *p = (T)v; return (int)o; }
+  template <class T> T atomic_add(T* p, T v) const { T o = *p; *p = (T)(o + v); return o; }
+  template <class T> T atomic_min(T* p, T v) const { T o = *p; if (v < o) *p = v; return o; }
+  template <class T> T atomic_max(T* p, T v) const { T o = *p; if (v > o) *p = v; return o; }
   template <class T> T atomic_or(T* p, T v) const { T o = *p; *p = (T)(o | v); return o; }
   template <class T> T atomic_cas(T* p, T c, T v) const { T o = *p; if (o == c) *p = v; return o; }
   template <class T> int atomic_cas_idx(T* p, int c, int v) const { int o = *p; if (o == c) *p = (T)v; return o; }
-  template <class S, class T> void exclusive_scan(const S* in, T* out, int n) const { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (T)acc; acc += in[i]; } out[n] = (T)acc; }
+  template <class T> void exclusive_scan(const int32_t* in, T* out, int n) const { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (T)acc; acc += in[i]; } out[n] = (T)acc; }
 };
 
 struct Item { std::vector<int32_t> succ_off, succ_adj, hlabel, tparent, tlabel; int n, m, nt; };

@@ -42,13 +42,13 @@ struct GroupEx {
   int uniform(const int32_t* p) { sync(); if (t == 0) sh->scratch[0] = __atomic_load_n(p, __ATOMIC_SEQ_CST); sync(); const int v = sh->scratch[0]; sync(); return v; }
   int reduce_or(int v) { sync(); if (t == 0) sh->red_or = 0; sync(); if (v) sh->red_or.fetch_or(v); sync(); return sh->red_or.load(); }
   int reduce_add(int v) { sync(); if (t == 0) sh->red_add = 0; sync(); if (v) sh->red_add.fetch_add(v); sync(); return sh->red_add.load(); }
-  template <class X> int atomic_add(X* p, int v) const { return (int)__atomic_fetch_add(p, (X)v, __ATOMIC_SEQ_CST); }
-  template <class X> int atomic_min(X* p, int v) const { X o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < (int)o && !__atomic_compare_exchange_n(p, &o, (X)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return (int)o; }
-  template <class X> int atomic_max(X* p, int v) const { X o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > (int)o && !__atomic_compare_exchange_n(p, &o, (X)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return (int)o; }
+  template <class X> X atomic_add(X* p, X v) const { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+  template <class X> X atomic_min(X* p, X v) const { X o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+  template <class X> X atomic_max(X* p, X v) const { X o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
   template <class X> X atomic_or(X* p, X v) const { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
   template <class X> X atomic_cas(X* p, X c, X v) const { __atomic_compare_exchange_n(p, &c, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return c; }
   template <class X> int atomic_cas_idx(X* p, int c, int v) const { X e = (X)c; __atomic_compare_exchange_n(p, &e, (X)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return (int)e; }
-  template <class S, class X> void exclusive_scan(const S* in, X* out, int n) { sync(); if (t == 0) { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (X)acc; acc += in[i]; } out[n] = (X)acc; } sync(); }
+  template <class X> void exclusive_scan(const int32_t* in, X* out, int n) { sync(); if (t == 0) { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (X)acc; acc += in[i]; } out[n] = (X)acc; } sync(); }
 };
 
 struct Item { std::vector<int32_t> succ_off, succ_adj, hlabel, tparent, tlabel; int n, m, nt; };
