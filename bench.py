@@ -261,6 +261,23 @@ def config5_leg(pt, retis=24, leaves=30):
             "note": "wall time of pt_enum_switchings incl. upload; bound by integer ALU + L1-resident accumulators, not HBM"}
 
 
+def ingest_leg(pt, pairs=20000):
+    """text -> flat arrays: the parallel batch reader on the first `pairs` instances of the workload"""
+    p = pt.Packer()
+    p.add_generated(pairs, L, R, SEED, 0)
+    text = ("\n".join(h + "\n" + g for h, g in (p.newick(i) for i in range(pairs))) + "\n").encode()
+    q = pt.Packer()
+    t0 = time.perf_counter()
+    k = q.add_newick_text(text)
+    dt = time.perf_counter() - t0
+    r = pt.Packer()
+    t1 = time.perf_counter()
+    r.add_newick_text(text, threads=1)
+    dt1 = time.perf_counter() - t1
+    return {"workload": "extended-Newick text of %d instances (l=%d, r=%d) -> flat arrays" % (k, L, R), "pairs_per_s": k / dt, "MB_per_s": len(text) / dt / 1e6,
+            "threads": os.cpu_count(), "pairs_per_s_one_thread": k / dt1, "bytes": len(text)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -421,6 +438,11 @@ def main():
             out["lca"] = lca_leg(pt, torch, args.lca_leaves, args.lca_queries, peak)
         except Exception as ex:  # the secondary leg must not take the headline line down
             out["lca"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out["newick_ingest"] = ingest_leg(pt)
+        except Exception as ex:
+            out["newick_ingest"] = {"error": repr(ex)}
     if rank == 0 and not args.no_config4:
         try:
             out["config4"] = config4_leg(pt, torch, args.config4_instances)

@@ -246,6 +246,11 @@ typedef struct pt_packer pt_packer;
 int pt_packer_create(pt_packer** out);
 /* returns PT_ERR_PARSE / PT_ERR_INVALID for a malformed pair (nothing is added) */
 int pt_packer_add_newick(pt_packer* p, const char* host_newick, const char* guest_newick);
+/* batch reader: every two non-blank lines of text[0, len) are one instance (host line, guest line; the network is the host,
+ * or the first line if both are trees, examples/tc.cpp:110-111).  Parsed on num_threads host threads (0 = all cores)
+ * straight into the flat arrays; same node numbering and label ids as pt_packer_add_newick.  On a malformed pair nothing
+ * is added and PT_ERR_PARSE / PT_ERR_INVALID names the pair. */
+int pt_packer_add_newick_text(pt_packer* p, const char* text, int64_t len, int num_threads, int64_t* num_added);
 /* adds `count` synthetic instances: the generate_random_binary_edgelist_trl process (utils/generator.hpp:175-245)
  * with a seeded PRNG (seed + instance index), guest = tree displayed by a uniform random switching with shuffled
  * child order; kind 0 = positive, 1 = guest with two leaf labels swapped, 2 = random guest tree on the same labels */

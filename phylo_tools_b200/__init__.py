@@ -87,6 +87,13 @@ class Packer:
     def add_newick(self, host, guest):
         _check(_L.pt_packer_add_newick(self._h, host.encode(), guest.encode()), "pt_packer_add_newick")
 
+    def add_newick_text(self, text, threads=0):
+        """batch reader (pt/fast_newick.hpp): two lines per instance, parsed in parallel; returns the number added"""
+        data = text if isinstance(text, (bytes, bytearray)) else text.encode()
+        k = C.c_int64(0)
+        _check(_L.pt_packer_add_newick_text(self._h, bytes(data), len(data), threads, C.byref(k)), "pt_packer_add_newick_text")
+        return k.value
+
     def add_generated(self, count, leaves, retis, seed, kind=0):
         _check(_L.pt_packer_add_generated(self._h, count, leaves, retis, seed, kind), "pt_packer_add_generated")
 

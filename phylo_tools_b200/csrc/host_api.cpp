@@ -8,6 +8,7 @@
 #include "../../include/pt_gpu.h"
 #include "../include/pt/generator.hpp"
 #include "../include/pt/newick.hpp"
+#include "../include/pt/fast_newick.hpp"
 #include "../include/pt/packer.hpp"
 #include "pt_error.h"
 
@@ -57,6 +58,13 @@ int pt_packer_add_newick(pt_packer* p, const char* host_newick, const char* gues
   if (!p || !host_newick || !guest_newick) return set_error(PT_ERR_INVALID, "pt_packer_add_newick: null argument");
   try { p->p.add_newick(host_newick, guest_newick); return PT_OK; }
   catch (const PT::MalformedNewick& e) { return set_error(PT_ERR_PARSE, "MalformedNewick: %s", e.what()); }
+  catch (const std::bad_alloc&) { return set_error(PT_ERR_NOMEM, "out of host memory"); }
+  catch (const std::exception& e) { return set_error(PT_ERR_INVALID, "%s", e.what()); }
+}
+int pt_packer_add_newick_text(pt_packer* p, const char* text, int64_t len, int num_threads, int64_t* num_added) {
+  if (!p || !text || len < 0) return set_error(PT_ERR_INVALID, "pt_packer_add_newick_text: bad argument");
+  try { const size_t k = PT::add_newick_text(p->p, text, (size_t)len, num_threads); if (num_added) *num_added = (int64_t)k; return PT_OK; }
+  catch (const PT::MalformedNewick& e) { return set_error(PT_ERR_PARSE, "%s", e.what()); }
   catch (const std::bad_alloc&) { return set_error(PT_ERR_NOMEM, "out of host memory"); }
   catch (const std::exception& e) { return set_error(PT_ERR_INVALID, "%s", e.what()); }
 }

@@ -21,6 +21,7 @@
 #include "../../../include/pt_gpu.h"
 #include "network.hpp"
 #include "packer.hpp"
+#include "fast_newick.hpp"
 
 namespace PT {
 
@@ -45,6 +46,8 @@ class BatchContainment {
   template <class Host, class Guest>
   size_t add(const Host& N, const Guest& T) { done_ = false; packer_.add(N, T); return packer_.size() - 1; }
   size_t add_newick(const std::string& first, const std::string& second) { done_ = false; packer_.add_newick(first, second); return packer_.size() - 1; }
+  // two lines per instance, parsed in parallel (pt/fast_newick.hpp); returns the number of instances added
+  size_t add_newick_text(const std::string& text, int threads = 0) { done_ = false; return PT::add_newick_text(packer_, text.data(), text.size(), threads); }
   size_t size() const { return packer_.size(); }
   const BatchPacker& packer() const { return packer_; }
 

@@ -104,6 +104,7 @@ class BatchPacker {
 
   // extended Newick (host, guest) of instance i, rebuilt from the flat arrays
   std::pair<std::string, std::string> newick_of(size_t i) const {
+    if (dict_names[i].empty() && max_labels > 0) { bool any = false; for (int64_t v = host_node_off[i]; v < host_node_off[i + 1]; ++v) any |= host_label[(size_t)v] >= 0; if (any) throw std::logic_error("label strings were not kept for this instance (batch reader)"); }
     const int64_t hb = host_node_off[i], hn = host_node_off[i + 1] - hb, ab = host_arc_off[i];
     const int64_t gb = guest_node_off[i], gn = guest_node_off[i + 1] - gb;
     EdgeVec he, ge; LabelMapDefault hl, gl;

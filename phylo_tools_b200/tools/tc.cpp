@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <string>
 #include <vector>
 #include "../include/pt/containment.hpp"
@@ -42,8 +43,9 @@ int main(int argc, char** argv) {
   try {
     if (!batch.empty()) {
       if (!file_exists(batch)) { std::cerr << batch << " cannot be opened for reading" << std::endl; return EXIT_FAILURE; }
-      std::ifstream in(batch); std::string a, b; BatchContainment bc;
-      while (std::getline(in, a)) { if (a.empty()) continue; if (!std::getline(in, b)) break; bc.add_newick(a, b); }
+      std::ifstream in(batch, std::ios::binary); std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+      BatchContainment bc;
+      bc.add_newick_text(text);   // parallel batch reader (pt/fast_newick.hpp)
       bc.run();
       for (size_t i = 0; i < bc.size(); ++i) std::cout << (bc.status(i) ? "error" : (bc.displayed(i) ? "displayed" : "not displayed")) << "\n";
       return EXIT_SUCCESS;

@@ -124,3 +124,32 @@ def test_no_cpu_fallback(pt):
     with pytest.raises(pt.PtError) as e:
         pt.Rmq([3, 1, 2])
     assert e.value.code == -4
+
+
+def test_batch_reader_is_bit_identical_to_the_per_instance_reader(pt, gold_tc, gold_newick):
+    """pt_packer_add_newick_text (parallel, straight into flat arrays) against pt_packer_add_newick on the same lines:
+    every array equal, for the pinned instances, generated ones, length annotations and white space"""
+    pairs = [(it["host"], it["guest"]) for it in gold_tc["items"]]
+    p = pt.Packer()
+    p.add_generated(300, 40, 9, 77, 0)
+    pairs += [p.newick(i) for i in range(300)]
+    pairs += [("((a:1.5,b:2)x:3,(c,d)y);", "((a,b),(c,d));"), (" ( a , b ) ; ", "(b,a);"), ("((a,b),(c,d));", "(((a)#H1,b),(#H1,(c,d)));")]
+    slow, fast = pt.Packer(), pt.Packer()
+    for h, g in pairs:
+        slow.add_newick(h, g)
+    text = "\n\n".join(h + "\r\n" + g for h, g in pairs) + "\n"
+    assert fast.add_newick_text(text, threads=3) == len(pairs)
+    a, b = slow.arrays(), fast.arrays()
+    for k in a:
+        assert (a[k] == b[k]).all() if isinstance(a[k], np.ndarray) else a[k] == b[k], k
+    one = pt.Packer()
+    assert one.add_newick_text(text, threads=1) == len(pairs)
+    c = one.arrays()
+    assert all((a[k] == c[k]).all() for k in a if isinstance(a[k], np.ndarray))
+    # a malformed pair is reported by index and nothing is added
+    bad = pt.Packer()
+    with pytest.raises(pt.MalformedNewick) as e:
+        bad.add_newick_text("(a,b);\n(a,b);\n(a,b));\n(a,b);\n")
+    assert "pair 1" in str(e.value) and len(bad) == 0
+    with pytest.raises(pt.PtError):
+        bad.add_newick_text("(a,b);\n((a)#H1,(#H1,b));\n((a)#H1,(#H1,b));\n((a)#H1,(#H1,b));\n")   # second pair: guest is not a tree
