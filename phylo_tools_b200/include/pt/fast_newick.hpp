@@ -28,62 +28,63 @@ struct Parsed {  // one network, storage reused between calls
   std::vector<Span> label;               // per node (len 0 = unlabelled)
   std::vector<std::pair<long, int32_t>> hybrids;
   std::vector<int32_t> open;
-  int32_t n = 0;
+  int32_t n = 0, narcs = 0;  // valid prefix of label / tail,head
   bool has_hybrid = false;
-  void reset() { tail.clear(); head.clear(); label.clear(); hybrids.clear(); open.clear(); n = 0; has_hybrid = false; }
 };
 
-// parses line [b, e) ; returns nullptr on success or a static error text
+// parses line s[0, len) ; returns nullptr on success or a static error text.  One backward pass; the per-node and per-arc
+// outputs are written through raw pointers into buffers sized once per line (a node costs at least one character).
 inline const char* parse_line(const char* s, long len, Parsed& P) {
-  P.reset();
+  P.hybrids.clear(); P.open.clear(); P.n = 0; P.has_hybrid = false;
+  const size_t cap = (size_t)len + 2;
+  if (P.label.size() < cap) { P.label.resize(cap); P.tail.resize(cap); P.head.resize(cap); }
+  Span* lab = P.label.data(); int32_t* tl = P.tail.data(); int32_t* hd = P.head.data();
+  int32_t n = 0, m = 0;
+  auto finish = [&](const char* err) { P.n = n; P.narcs = m; return err; };
   long back = len - 1;
-  auto skip_ws = [&]() { while (back >= 0 && (s[back] == ' ' || (unsigned)(s[back] - 9) < 5u)) --back; };
-  auto skip_length = [&]() {
-    long i = back;
-    while (i >= 0) { const char c = s[i]; if ((c >= '0' && c <= '9') || c == '.' || c == '-' || c == '+' || c == 'E' || c == 'e') --i; else break; }
-    if (i >= 0 && s[i] == ':') back = i - 1;
-  };
-  skip_ws();
-  if (back < 0) return nullptr;
-  if (s[back] != ';') return "expected ';'";
+#define FNW_SKIP_WS() while (back >= 0 && (s[back] == ' ' || (unsigned)(s[back] - 9) < 5u)) --back
+#define FNW_SKIP_LEN() do { long i_ = back; while (i_ >= 0) { const char c_ = s[i_]; if ((c_ >= '0' && c_ <= '9') || c_ == '.' || c_ == '-' || c_ == '+' || c_ == 'E' || c_ == 'e') --i_; else break; } if (i_ >= 0 && s[i_] == ':') back = i_ - 1; } while (0)
+  FNW_SKIP_WS();
+  if (back < 0) return finish(nullptr);
+  if (s[back] != ';') return finish("expected ';'");
   --back;
   bool want_subtree = true;
   int32_t done = 0;
   for (;;) {
     if (want_subtree) {
-      skip_ws();
-      long i = back;
-      while (i >= 0) { const char c = s[i]; if (c == '(' || c == ')' || c == ',') break; --i; }
+      FNW_SKIP_WS();
+      long i = back, sharp = -1;
+      while (i >= 0) { const char c = s[i]; if (c == '(' || c == ')' || c == ',') break; if (c == '#' && sharp < 0) sharp = i; --i; }
       const long nb = i + 1, nl = back - i;  // name = s[nb, nb+nl)
       back = i;
       int32_t id;
-      long sharp = -1;
-      for (long k = nb + nl - 1; k >= nb; --k) if (s[k] == '#') { sharp = k; break; }
       if (sharp >= 0) {
         long d = sharp;
         while (d < nb + nl && !(s[d] >= '0' && s[d] <= '9')) ++d;
-        if (d == nb + nl) return "found '#' but no hybrid number";
+        if (d == nb + nl) return finish("found '#' but no hybrid number");
         long key = 0;
         while (d < nb + nl && s[d] >= '0' && s[d] <= '9') { key = key * 10 + (s[d] - '0'); ++d; }
         id = -1;
         for (auto& h : P.hybrids) if (h.first == key) { id = h.second; break; }
-        if (id < 0) { id = P.n++; P.hybrids.emplace_back(key, id); P.label.push_back(Span{(uint32_t)nb, (uint32_t)(sharp - nb)}); }
+        if (id < 0) { id = n; P.hybrids.emplace_back(key, id); lab[n++] = Span{(uint32_t)nb, (uint32_t)(sharp - nb)}; }
         P.has_hybrid = true;
-      } else { id = P.n++; P.label.push_back(Span{(uint32_t)nb, (uint32_t)nl}); }
-      if (back > 0 && s[back] == ')') { --back; P.open.push_back(id); skip_length(); continue; }
+      } else { id = n; lab[n++] = Span{(uint32_t)nb, (uint32_t)nl}; }
+      if (back > 0 && s[back] == ')') { --back; P.open.push_back(id); FNW_SKIP_LEN(); continue; }
       done = id; want_subtree = false;
     }
-    skip_ws();
+    FNW_SKIP_WS();
     if (P.open.empty()) break;
     const int32_t parent = P.open.back();
-    P.tail.push_back(parent); P.head.push_back(done);
-    if (back < 0) return "unexpected start of string";
+    tl[m] = parent; hd[m++] = done;
+    if (back < 0) return finish("unexpected start of string");
     const char c = s[back];
-    if (c == ',') { --back; skip_length(); want_subtree = true; }
+    if (c == ',') { --back; FNW_SKIP_LEN(); want_subtree = true; }
     else if (c == '(') { --back; P.open.pop_back(); done = parent; }
-    else return "expected ',' or '('";
+    else return finish("expected ',' or '('");
   }
-  return nullptr;
+#undef FNW_SKIP_WS
+#undef FNW_SKIP_LEN
+  return finish(nullptr);
 }
 
 struct Chunk {  // flat output of one thread
@@ -95,7 +96,7 @@ struct Chunk {  // flat output of one thread
 
 // CSR of one network appended to off/adj (children in reverse arc order like Phylogeny::build); returns false on a double edge
 inline bool append_csr(const Parsed& P, std::vector<int32_t>& off, std::vector<int32_t>& adj, std::vector<int32_t>& scratch, bool by_head) {
-  const int32_t n = P.n, m = (int32_t)P.tail.size();
+  const int32_t n = P.n, m = P.narcs;
   const size_t o0 = off.size(), a0 = adj.size();
   off.resize(o0 + n + 1, 0); adj.resize(a0 + m);
   int32_t* O = off.data() + o0; int32_t* A = adj.data() + a0;
@@ -151,11 +152,11 @@ inline size_t add_newick_text(BatchPacker& pk, const char* text, size_t len, int
       if (!err) err = parse_line(l1, (long)lines[2 * pi + 1].second, B);
       if (err) { C.error = std::string("MalformedNewick: ") + err; C.error_pair = (int64_t)pi; return; }
       // examples/tc.cpp:110-111: the network is the host, or the first line if both are trees
-      const bool t0 = (int32_t)A.tail.size() + 1 == A.n, t1 = (int32_t)B.tail.size() + 1 == B.n;
+      const bool t0 = A.narcs + 1 == A.n, t1 = B.narcs + 1 == B.n;
       const bool swap = t0 && !t1;
       const Parsed& H = swap ? B : A; const Parsed& G = swap ? A : B;
       const char* hbase = swap ? l1 : l0; const char* gbase = swap ? l0 : l1;
-      if ((int32_t)G.tail.size() + 1 != G.n || G.has_hybrid) { C.error = "guest must be a tree"; C.error_pair = (int64_t)pi; return; }
+      if (G.narcs + 1 != G.n || G.has_hybrid) { C.error = "guest must be a tree"; C.error_pair = (int64_t)pi; return; }
       // one root each (utils/storage_adj_common.hpp:103-109): node 0 is the root by construction; every other node has an in-arc
       // label dictionary: open addressing over (hash, span)
       const int32_t nl_max = H.n + G.n;
@@ -179,11 +180,11 @@ inline size_t add_newick_text(BatchPacker& pk, const char* text, size_t len, int
       for (int32_t v = 0; v < H.n; ++v) C.hlabel.push_back(id_of(hbase, H.label[v]));
       const size_t gp0 = C.gparent.size();
       C.gparent.resize(gp0 + G.n, -1);
-      for (size_t e = 0; e < G.tail.size(); ++e) C.gparent[gp0 + G.head[e]] = G.tail[e];
+      for (int32_t e = 0; e < G.narcs; ++e) C.gparent[gp0 + G.head[e]] = G.tail[e];
       if (!append_csr(G, C.gchild_off, C.gchild_adj, scratch, false)) { C.error = "MalformedNewick: read double edge"; C.error_pair = (int64_t)pi; return; }
       for (int32_t v = 0; v < G.n; ++v) C.glabel.push_back(id_of(gbase, G.label[v]));
-      C.hn.push_back(H.n); C.hm.push_back((int64_t)H.tail.size()); C.gn.push_back(G.n);
-      C.max_hn = std::max(C.max_hn, H.n); C.max_hm = std::max(C.max_hm, (int32_t)H.tail.size()); C.max_gn = std::max(C.max_gn, G.n);
+      C.hn.push_back(H.n); C.hm.push_back((int64_t)H.narcs); C.gn.push_back(G.n);
+      C.max_hn = std::max(C.max_hn, H.n); C.max_hm = std::max(C.max_hm, H.narcs); C.max_gn = std::max(C.max_gn, G.n);
       C.max_l = std::max(C.max_l, (int32_t)table.size());
     }
   };
