@@ -36,6 +36,16 @@ L, R = 100, 20
 SEED = 0xB200
 
 
+def measured_traffic(kernel, units):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r01.json), only when the
+    launch here processes the same number of units as the captured one; else None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))[kernel]
+        return t["dram_bytes_per_launch"] if t["units_per_launch"] == units else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -212,8 +222,8 @@ def lca_leg(pt, torch, leaves, queries, peak):
     return {"workload": "batched LCA: %d queries on a %d-leaf random binary tree (BASELINE configs[2])" % (queries, leaves),
             "queries_per_s": qps, "ms_per_batch": avg, "best_ms": best, "build_ms": info["build_ms"], "levels": info["num_levels"],
             "resident_bytes": info["device_bytes"], "checksum": checksum,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "model": "40 B/query (SURVEY 8(d)); physical floor of this layout is 2 x 32 B random sectors + 12 B streamed = 76 B/query"}}
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("lca_query_kernel", queries),
+                         "model": "40 B/query (SURVEY 8(d)); this layout needs 2 random records per query and B200 moves a 128-byte line per random read (profiles/micro_gather.cu): 254 B/query measured, ceiling ~25 G queries/s"}}
 
 
 def config4_leg(pt, torch, count):
@@ -379,7 +389,7 @@ def main():
     k0 = sum(k0_ms) / len(k0_ms)
     ach = ALG_BYTES_PER_INSTANCE * B / (k0 / 1000.0) / 1e9
     roofline = {"bound": "hbm", "kernel": "tc_reduce_kernel<int16> (round 0, %d instances)" % B, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "kernel_ms": k0, "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
+                "traffic": measured_traffic("tc_reduce_kernel", B), "kernel_ms": k0, "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
                 "algorithmic_bytes_per_instance": ALG_BYTES_PER_INSTANCE, "bytes_actually_read_per_instance": in_bytes_actual / B,
                 "note": "instance-resident shared-memory solver: bound by dependent shared-memory latency and barriers, not HBM (SURVEY 8(d)); see profiles/"}
     resident.free()
