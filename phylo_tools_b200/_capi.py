@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptgpu.so")
+LIB_PATH = os.environ.get("PT_GPU_LIB") or os.path.join(_HERE, "libptgpu.so")  # PT_GPU_LIB: profiling builds only
 
 PT_OK, PT_ERR_INVALID, PT_ERR_CUDA, PT_ERR_NOMEM, PT_ERR_NO_DEVICE, PT_ERR_UNSUPPORTED, PT_ERR_PARSE = 0, -1, -2, -3, -4, -5, -6
 PT_MEM_HOST, PT_MEM_DEVICE = 0, 1

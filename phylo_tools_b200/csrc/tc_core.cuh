@@ -49,6 +49,14 @@ namespace ptgpu {
 // parallel-for over [0,n): i_ is the executor's slot, i the (possibly permuted) element
 #define PT_FOR(i, n) \
   PT_NOUNROLL for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
+// the same for the passes that read the caller's arrays from global memory (ex.ldg): four iterations in flight, so that
+// four load latencies overlap instead of one load -> store round trip per iteration
+#if defined(__CUDA_ARCH__)
+#define PT_FOR_LD(i, n) \
+  _Pragma("unroll 4") for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
+#else
+#define PT_FOR_LD(i, n) PT_FOR(i, n)
+#endif
 
 enum TcCode : int { TC_NOT = 0, TC_DISPLAYED = 1, TC_BRANCH = 2, TC_ERROR = 3 };
 enum TcStatus : int { TCS_OK = 0, TCS_MULTILABEL = 1, TCS_BAD_GRAPH = 2, TCS_TOO_LARGE = 3, TCS_POOL_OVERFLOW = 4 };
@@ -74,9 +82,9 @@ template <class I>
 struct TcWork {
   int capN, capM, capNT, capL, W;  // W = words of the reachable-label signature per node (exact when 32 W >= labels)
   // host network
-  I *at, *ah;            // arc tail / head; at < 0 = deleted
-  I *ooff, *oarc;        // out CSR over live arcs (arc ids)
-  I *ioff, *iarc;        // in CSR
+  I *at, *ah;            // arc tail / head; at < 0 = deleted.  Arcs stay SORTED BY TAIL: rewriting only deletes arcs or moves heads
+  I *ooff;               // out CSR: the out-arcs of v are the arc ids [ooff[v], ooff[v+1]) (csr() compacts the arc arrays)
+  I *ioff, *iarc;        // in CSR (arc ids)
   I *hlab;               // label of a live labelled leaf, else -1
   I *lvl;                // height (longest path to a leaf) from the wavefront; scratch otherwise
   int32_t *hcnt, *haux;  // atomic scratch, capN+1 each
@@ -84,7 +92,7 @@ struct TcWork {
   uint32_t* lset;        // capN * W : labels reachable below each node
   // guest tree
   I *tpar, *tlab;        // tpar: -1 root, -2 deleted
-  int32_t *tdeg, *tleaf, *tmin, *tmax;  // live children, live leaf children, min / max leaf-child label
+  int32_t *tdeg, *tleaf, *tmin, *tmax;  // tdeg: live children; tmax: XOR of the children's ids; tleaf, tmin: scratch
   // labels
   I *l2h, *l2t;
   // scalars (shared)
@@ -101,7 +109,7 @@ struct TcWork {
   PT_HD static size_t bytes(int N, int M, int NT, int L) {
     const int W = sig_words(L);
     size_t b = 0;
-    b += (size_t)(2 * M + (N + 1) + M + (N + 1) + M + N + 2 * (N + 1)) * sizeof(I);  // at ah ooff oarc ioff iarc hlab lvl hscr
+    b += (size_t)(2 * M + (N + 1) + (N + 1) + M + N + 2 * (N + 1)) * sizeof(I);  // at ah ooff ioff iarc hlab lvl hscr
     b = (b + 3) & ~(size_t)3;
     b += (size_t)(2 * (N + 1)) * 4;                                         // hcnt haux
     b += (size_t)N * W * 4;                                                 // lset
@@ -118,7 +126,7 @@ struct TcWork {
     char* p = (char*)base;
     auto take = [&](size_t nbytes) { char* r = p; p += nbytes; return r; };
     at = (I*)take((size_t)M * sizeof(I)); ah = (I*)take((size_t)M * sizeof(I));
-    ooff = (I*)take((size_t)(N + 1) * sizeof(I)); oarc = (I*)take((size_t)M * sizeof(I));
+    ooff = (I*)take((size_t)(N + 1) * sizeof(I));
     ioff = (I*)take((size_t)(N + 1) * sizeof(I)); iarc = (I*)take((size_t)M * sizeof(I));
     hlab = (I*)take((size_t)N * sizeof(I)); lvl = (I*)take((size_t)(N + 1) * sizeof(I)); hscr = (I*)take((size_t)(N + 1) * sizeof(I));
     p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
@@ -144,14 +152,14 @@ struct TcSolver {
 
   PT_HD TcSolver(Ex& e, TcWork<I>& work) : ex(e), w(work), n(0), m(0), nt(0), L(0) { st.cherries = st.retcherries = st.arcs_deleted = st.passes = 0; }
 
-  enum { F_FLAG = 0, F_FAIL = 1, F_ROOT = 2, F_TROOT = 3, F_NLAB = 4, F_BEST = 5, F_STATUS = 6, F_TMP = 7, F_TMP2 = 8 };
+  enum { F_FLAG = 0, F_FAIL = 1, F_ROOT = 2, F_TROOT = 3, F_NLAB = 4, F_BEST = 5, F_STATUS = 6, F_TMP = 7, F_TMP2 = 8, F_QTAIL = 9 };
   static constexpr int TDEAD = -2;
   static constexpr int LVL_INF = sizeof(I) == 2 ? 32000 : 0x3fffffff;
 
   // ---- small helpers -----------------------------------------------------------------------------------
   PT_HD int outdeg(int v) const { return w.ooff[v + 1] - w.ooff[v]; }
   PT_HD int indeg(int v) const { return w.ioff[v + 1] - w.ioff[v]; }
-  PT_HD int out_arc(int v, int k) const { return w.oarc[w.ooff[v] + k]; }
+  PT_HD int out_arc(int v, int k) const { return w.ooff[v] + k; }
   PT_HD int in_arc(int v, int k) const { return w.iarc[w.ioff[v] + k]; }
   PT_HD bool lbit(int v, int lam) const { const int b = lam % (w.W * 32); return (w.lset[v * w.W + (b >> 5)] >> (b & 31)) & 1u; }
   // read a shared flag uniformly and reset it
@@ -174,40 +182,43 @@ struct TcSolver {
     if (n > w.capN || m > w.capM || nt > w.capNT || n < 0 || m < 0 || nt < 0) return TCS_TOO_LARGE;
     if (ex.tid() == 0) { PT_NOUNROLL for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
     ex.sync();
-    // structure checks on the CSR offsets
-    PT_FOR(v, n + 1) {
-      const int o = in.succ_off[v];
-      if (o < 0 || o > m || (v < n && in.succ_off[v + 1] < o) || (v == 0 && o != 0) || (v == n && o != m)) w.sc[F_STATUS] = TCS_BAD_GRAPH;
+    // structure checks on the CSR offsets (branch-free bodies: the loads of consecutive iterations overlap)
+    int bad = 0, big = 0, maxlab = -1;
+    PT_FOR_LD(v, n + 1) {
+      const int o = ex.ldg(&in.succ_off[v]);
+      bad |= (o < 0) | (o > m) | (v == 0 && o != 0) | (v == n && o != m);
       w.ooff[v] = (I)(o < 0 ? 0 : (o > m ? m : o));
     }
-    if (take_flag(F_STATUS)) return TCS_BAD_GRAPH;
-    int maxlab = -1;
-    PT_FOR(v, n) {
-      PT_NOUNROLL for (int e = w.ooff[v]; e < w.ooff[v + 1]; ++e) w.at[e] = (I)v;
-      const int l = in.hlabel[v];
+    PT_FOR_LD(v, n) {
+      const int l = ex.ldg(&in.hlabel[v]);
       w.hlab[v] = (I)l;
-      if (l >= w.capL || l < -1) w.sc[F_STATUS] = TCS_TOO_LARGE;
-      if (l > maxlab) maxlab = l;
+      big |= (l >= w.capL) | (l < -1);
+      maxlab = l > maxlab ? l : maxlab;
     }
-    PT_FOR(e, m) {
-      const int h = in.succ_adj[e];
-      if (h < 0 || h >= n) w.sc[F_STATUS] = TCS_BAD_GRAPH;
+    PT_FOR_LD(e, m) {
+      const int h = ex.ldg(&in.succ_adj[e]);
+      bad |= (h < 0) | (h >= n);
       w.ah[e] = (I)h;
     }
-    PT_FOR(t, nt) {
-      const int p = in.tparent[t], l = in.tlabel[t];
-      if (p < -1 || p >= nt || p == t) w.sc[F_STATUS] = TCS_BAD_GRAPH;
-      if (l >= w.capL || l < -1) w.sc[F_STATUS] = TCS_TOO_LARGE;
-      if (l > maxlab) maxlab = l;
+    PT_FOR_LD(t, nt) {
+      const int p = ex.ldg(&in.tparent[t]), l = ex.ldg(&in.tlabel[t]);
+      bad |= (p < -1) | (p >= nt) | (p == t);
+      big |= (l >= w.capL) | (l < -1);
+      maxlab = l > maxlab ? l : maxlab;
       w.tpar[t] = (I)p; w.tlab[t] = (I)l; w.tdeg[t] = 0;
     }
-    ex.atomic_max(&w.sc[F_NLAB], maxlab + 1);
-    {
-      const int s = take_flag(F_STATUS);
-      if (s) return s;
+    if (bad) w.sc[F_STATUS] = TCS_BAD_GRAPH; else if (big) w.sc[F_TMP2] = 1;
+    ex.sync();
+    PT_FOR(v, n) {
+      if (w.ooff[v + 1] < w.ooff[v]) w.sc[F_STATUS] = TCS_BAD_GRAPH;
+      PT_NOUNROLL for (int e = w.ooff[v]; e < w.ooff[v + 1]; ++e) w.at[e] = (I)v;
     }
+    ex.atomic_max(&w.sc[F_NLAB], maxlab + 1);
+    if (take_flag(F_STATUS)) return TCS_BAD_GRAPH;
+    if (take_flag(F_TMP2)) return TCS_TOO_LARGE;
     L = ex.uniform(&w.sc[F_NLAB]);
     PT_FOR(l, L) { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
+    ex.phase = 15;
     // guest: child counts, exactly one root, no cycles
     PT_FOR(t, nt) { if (w.tpar[t] >= 0) ex.atomic_add(&w.tdeg[w.tpar[t]], 1); else ex.atomic_add(&w.sc[F_TMP], 1); }
     if (nt > 0 && ex.uniform(&w.sc[F_TMP]) != 1) return TCS_BAD_GRAPH;
@@ -219,6 +230,7 @@ struct TcSolver {
     }
     set_scalar(F_TMP, 0);
     if (take_flag(F_STATUS)) return TCS_BAD_GRAPH;
+    ex.phase = 16;
     // label tables: only out-degree-0 nodes carry labels
     PT_FOR(v, n) {
       const int l = w.hlab[v];
@@ -270,27 +282,37 @@ struct TcSolver {
       w.tmin[t] = np;
     }
     ex.sync();
-    PT_FOR(t, nt) { w.tpar[t] = (I)w.tmin[t]; if (w.tmin[t] == -1) w.sc[F_TROOT] = t; }
+    PT_FOR(t, nt) { w.tpar[t] = (I)w.tmin[t]; if (w.tmin[t] == -1) w.sc[F_TROOT] = t; w.tmax[t] = 0; }
     ex.sync();
+    // tmax[p] = XOR of the ids of p's children: the sibling of t below a binary p is tmax[p] ^ t.  Child SETS never change
+    // afterwards (a collapse turns p into a leaf as a whole), so this is computed once per work item.
+    PT_FOR(t, nt) { if (w.tpar[t] >= 0) ex.atomic_xor(&w.tmax[w.tpar[t]], t); }
+    ex.sync();
+  }
+  // label of the other leaf of a binary guest cherry containing the leaf labelled l, else -1
+  PT_HD int cherry_mate(int l) const {
+    const int t = w.l2t[l];
+    if (t < 0) return -1;
+    const int p = w.tpar[t];
+    if (p < 0 || w.tdeg[p] != 2) return -1;
+    return w.tlab[w.tmax[p] ^ t];
   }
 
   // ---- host CSR over live arcs ---------------------------------------------------------------------------
+  // Arcs are sorted by tail from the input on and no rule ever changes a tail, so the out-CSR is a stable compaction of the
+  // arc arrays (ballot / popc, no atomics) plus the positions where the tail changes; only the in-CSR needs counting.
   PT_NI void csr() {
     ex.phase = 3;
-    PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = 0; }
+    if (ex.tid() == 0) w.sc[F_QTAIL] = 0;
+    PT_FOR(v, n + 1) { w.haux[v] = 0; w.lvl[v] = (I)0; }  // lvl = "queued as a true cherry in this snapshot"
     ex.sync();
-    PT_FOR(e, m) { if (w.at[e] >= 0) { ex.atomic_add(&w.hcnt[w.at[e]], 1); ex.atomic_add(&w.haux[w.ah[e]], 1); } }
-    ex.sync();
-    ex.exclusive_scan(w.hcnt, w.ooff, n);
-    ex.exclusive_scan(w.haux, w.ioff, n);
-    PT_FOR(v, n + 1) { w.hcnt[v] = 0; w.haux[v] = 0; }
-    ex.sync();
-    PT_FOR(e, m) {
-      if (w.at[e] >= 0) {
-        w.oarc[w.ooff[w.at[e]] + ex.atomic_add(&w.hcnt[w.at[e]], 1)] = (I)e;
-        w.iarc[w.ioff[w.ah[e]] + ex.atomic_add(&w.haux[w.ah[e]], 1)] = (I)e;
-      }
+    m = ex.compact_arcs(w.at, w.ah, m, w.haux);  // drops dead arcs, haux[h] = live in-degree of h
+    PT_FOR(e, m + 1) {
+      const int lo = e > 0 ? w.at[e - 1] + 1 : 0, hi = e < m ? (int)w.at[e] : n;
+      PT_NOUNROLL for (int v = lo; v <= hi; ++v) w.ooff[v] = (I)e;
     }
+    ex.exclusive_scan(w.haux, w.ioff, n);
+    PT_FOR(e, m) { const int h = w.ah[e]; w.iarc[w.ioff[h] + ex.atomic_add(&w.haux[h], -1) - 1] = (I)e; }
     ex.sync();
   }
 
@@ -311,6 +333,7 @@ struct TcSolver {
         const bool ok = check_dag(dag_state == 2);
         dag_state = 1;
         if (!ok) { *status = TCS_BAD_GRAPH; return; }
+        ex.phase = 40;
       }
       const int root = ex.uniform(&w.sc[F_ROOT]);
       int need = 0;
@@ -324,10 +347,14 @@ struct TcSolver {
           if (od == 1) {
             if (id == 1) need |= NEED_SUPPRESS;                          // (c)
             else if (id >= 2 && indeg(w.ah[out_arc(v, 0)]) >= 2) need |= NEED_MERGE;  // (d)
-          } else if (od <= 8) {                                          // (e) parallel arcs
-            PT_NOUNROLL for (int a = 1; a < od; ++a)
-              PT_NOUNROLL for (int b = 0; b < a; ++b)
-                if (w.ah[out_arc(v, a)] == w.ah[out_arc(v, b)]) need |= NEED_PARALLEL;
+          } else {
+            if (od <= 8) {                                               // (e) parallel arcs
+              PT_NOUNROLL for (int a = 1; a < od; ++a)
+                PT_NOUNROLL for (int b = 0; b < a; ++b)
+                  if (w.ah[out_arc(v, a)] == w.ah[out_arc(v, b)]) need |= NEED_PARALLEL;
+            }
+            // true-cherry candidates of this snapshot (only used when the snapshot turns out to be clean)
+            if (is_host_cherry(v)) { w.lvl[v] = (I)1; w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)v; }
           }
         }
       }
@@ -440,129 +467,124 @@ struct TcSolver {
     return !ex.reduce_or(bad);
   }
 
-  // ---- TC: true (multi-)cherries --------------------------------------------------------------------------
-  // returns 1 changed, 0 nothing, -1 NOT displayed.  Reads only in-lists of labelled leaves and out-DEGREES of their
-  // parents, none of which a collapse changes for nodes that are still internal, so it may be repeated without
-  // rebuilding the CSR (solve() loops it until nothing collapses).
-  PT_NI int rule_true_cherry() {
+  // ---- TC: true (multi-)cherries, as a worklist --------------------------------------------------------------
+  // q is a true cherry: >= 2 live children, every one a labelled leaf with a single parent.  Tolerates a CSR that is stale by
+  // arc DELETIONS (dead arcs have at = -1 and are skipped; in-degrees only over-count, so the test can only say "no" too often).
+  PT_HD bool is_host_cherry(int q) const {
+    int cnt = 0;
+    PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) {
+      const int e = out_arc(q, k);
+      if (w.at[e] < 0) continue;
+      const int c = w.ah[e];
+      if (w.hlab[c] < 0 || indeg(c) != 1) return false;
+      ++cnt;
+    }
+    return cnt >= 2;
+  }
+  // The queue hscr[head, F_QTAIL) holds host nodes: candidates found by the detection pass of clean_host or by the parent
+  // check below (hlab < 0), and nodes that rule_ret_cherry collapsed on the spot (hlab >= 0: only their parent is checked).
+  // Each round: (1) every candidate is matched against the guest and collapsed (a candidate whose leaves are not exactly
+  // the children of one guest node -> NOT displayed), (2) the parent of every fresh leaf is tested and queued once
+  // (lvl = queued flag, reset by csr()).  Total work is proportional to the cherries found, not to rounds x labels.
+  // returns 1 something collapsed, 0 nothing, -1 NOT displayed
+  PT_NI int rule_true_cherry(int& head) {
     ex.phase = 7;
-    // every pass runs over the LABELS (live leaves) only; per-node scratch is reset just for the parents of leaves
-    PT_FOR(l, L) {
-      const int h = w.l2h[l];
-      if (h >= 0) {
-        if (indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (q >= 0) { w.hcnt[q] = 0; w.haux[q] = -1; } }
-        const int p = w.tpar[w.l2t[l]];
-        if (p >= 0) w.tmin[p] = 0x7fffffff;
-      }
-    }
-    ex.sync();
-    PT_FOR(l, L) {
-      const int h = w.l2h[l];
-      if (h >= 0 && indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (q >= 0) ex.atomic_add(&w.hcnt[q], 1); }
-    }
-    ex.sync();
-    int fail = 0, any = 0;
-    PT_FOR(l, L) {
-      const int h = w.l2h[l];
-      if (h >= 0 && indeg(h) == 1) {
-        const int q = w.at[in_arc(h, 0)];
-        if (q >= 0 && w.hcnt[q] == outdeg(q) && outdeg(q) >= 2) {
-          const int p = w.tpar[w.l2t[l]];
-          any = 1;
-          if (p < 0) fail = 1;
-          else {
-            const int old = ex.atomic_cas(&w.haux[q], -1, p);
-            if (old != -1 && old != p) fail = 1;
-            ex.atomic_min(&w.tmin[p], l);
-          }
+    int collapsed = 0, rounds = 0;
+    for (;;) {
+      const int tail = ex.uniform(&w.sc[F_QTAIL]);
+      if (head >= tail) break;
+      const int cnt = tail - head;
+      ++rounds;
+      PT_FOR(i, cnt) {
+        const int q = w.hscr[head + i];
+        if (w.hlab[q] >= 0) continue;  // collapsed by the reticulated-cherry rule
+        int p = -1, num = 0, minl = 0x7fffffff;
+        bool ok = true, cherry = true;
+        PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) {
+          const int e = out_arc(q, k);
+          if (w.at[e] < 0) continue;
+          const int c = w.ah[e], l = w.hlab[c];
+          if (l < 0 || indeg(c) != 1) { cherry = false; break; }
+          const int pp = w.tpar[w.l2t[l]];
+          if (num == 0) p = pp; else if (pp != p) ok = false;
+          ++num;
+          if (l < minl) minl = l;
         }
-      }
-    }
-    if (!ex.reduce_or(any)) return 0;
-    PT_FOR(l, L) {
-      const int h = w.l2h[l];
-      if (h >= 0 && indeg(h) == 1) { const int q = w.at[in_arc(h, 0)]; if (q >= 0 && w.haux[q] >= 0 && w.tdeg[w.haux[q]] != outdeg(q)) fail = 1; }
-    }
-    if (ex.reduce_or(fail)) { set_scalar(F_FAIL, 1); return -1; }
-    int collapsed = 0;
-    PT_FOR(l, L) {
-      const int h = w.l2h[l];
-      if (h >= 0 && indeg(h) == 1) {
-        const int q = w.at[in_arc(h, 0)];
-        if (q >= 0 && w.haux[q] >= 0) {
-          const int p = w.haux[q], t = w.l2t[l];
-          w.at[in_arc(h, 0)] = (I)-1;
-          w.hlab[h] = (I)-1;
+        if (!cherry || num < 2) continue;
+        if (!ok || p < 0 || w.tdeg[p] != num) { w.sc[F_FAIL] = 1; continue; }
+        PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) {
+          const int e = out_arc(q, k);
+          if (w.at[e] < 0) continue;
+          const int c = w.ah[e], l = w.hlab[c], t = w.l2t[l];
+          w.at[e] = (I)-1; w.hlab[c] = (I)-1;
           w.tlab[t] = (I)-1; w.tpar[t] = (I)TDEAD;
-          if (l == w.tmin[p]) {
-            w.hlab[q] = (I)l; w.l2h[l] = (I)q;
-            w.tlab[p] = (I)l; w.l2t[l] = (I)p; w.tdeg[p] = 0;
-            ++collapsed;
-          } else { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
+          if (l != minl) { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
+        }
+        w.hlab[q] = (I)minl; w.l2h[minl] = (I)q;
+        w.tlab[p] = (I)minl; w.l2t[minl] = (I)p; w.tdeg[p] = 0;
+        ++collapsed;
+      }
+      ex.sync();
+      PT_FOR(i, cnt) {
+        const int q = w.hscr[head + i];
+        if (w.hlab[q] >= 0 && indeg(q) == 1) {
+          const int g = w.at[in_arc(q, 0)];
+          if (g >= 0 && is_host_cherry(g) && ex.atomic_cas_idx(&w.lvl[g], 0, 1) == 0) w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)g;
         }
       }
+      head = tail;
     }
+    if (!rounds) return 0;
+    if (ex.uniform(&w.sc[F_FAIL])) return -1;
     st.cherries += (unsigned)ex.reduce_add(collapsed);
     return 1;
   }
 
-  // ---- guest cherries with exactly two leaves: tmin/tmax = their labels, tleaf = 2 ---------------------------
-  PT_NI void guest_cherries() {
-    ex.phase = 8;
-    PT_FOR(t, nt) { w.tleaf[t] = 0; w.tmin[t] = 0x7fffffff; w.tmax[t] = -1; }
-    ex.sync();
-    PT_FOR(l, L) {
-      const int t = w.l2t[l];
-      if (t >= 0 && w.tpar[t] >= 0) { const int p = w.tpar[t]; ex.atomic_add(&w.tleaf[p], 1); ex.atomic_min(&w.tmin[p], l); ex.atomic_max(&w.tmax[p], l); }
-    }
-    ex.sync();
-  }
-  PT_HD bool is_bin_cherry(int p) const { return w.tpar[p] != TDEAD && w.tdeg[p] == 2 && w.tleaf[p] == 2; }
-
   // ---- RC: reticulated cherries ---------------------------------------------------------------------------
+  // One thread per label x whose guest leaf sits in a binary cherry {x, y}: host leaf x hangs on q, and y (or the
+  // out-degree-1 reticulation above y) has q among its parents -> keep that in-arc, delete the others.  (The mirrored case
+  // is handled by the thread of y; both cannot apply at once: it would need q above z and z above q.)
   // returns bit 0: some multi-parent node got its parent fixed (needs a clean-up pass), bit 1: some reticulated cherry was
-  // collapsed on the spot (q had exactly the two children: the true-cherry rule can go on without a CSR rebuild).
+  // collapsed on the spot (q had exactly the two children; q is appended to the true-cherry queue).
   // Tolerates a CSR that is stale by arc deletions: a dead arc has at = -1 and never matches q, degrees only over-count.
   PT_NI int rule_ret_cherry() {
     ex.phase = 9;
     int fixed = 0, collapsed = 0;
-    PT_FOR(p, nt) {
-      if (is_bin_cherry(p)) {
-        PT_NOUNROLL for (int side = 0; side < 2; ++side) {
-          const int x = side ? w.tmax[p] : w.tmin[p], y = side ? w.tmin[p] : w.tmax[p];
-          const int hx = w.l2h[x], hy = w.l2h[y];
-          if (indeg(hx) != 1) continue;
-          const int ex_arc = in_arc(hx, 0);
-          const int q = w.at[ex_arc];
-          if (q < 0) continue;
-          int c = -1;  // the multi-parent node whose parent gets fixed to q
-          if (indeg(hy) >= 2) c = hy;
-          else if (indeg(hy) == 1) { const int z = w.at[in_arc(hy, 0)]; if (z >= 0 && outdeg(z) == 1 && indeg(z) >= 2) c = z; }
-          if (c < 0) continue;
-          int keep = -1;
-          PT_NOUNROLL for (int k = 0; k < indeg(c); ++k) if (w.at[in_arc(c, k)] == q) keep = in_arc(c, k);
-          if (keep < 0) continue;
-          PT_NOUNROLL for (int k = 0; k < indeg(c); ++k) { const int e = in_arc(c, k); if (e != keep) w.at[e] = (I)-1; }
-          bool both = false;  // q's children are exactly hx and c (both arcs alive)
-          if (outdeg(q) == 2) {
-            const int e0 = out_arc(q, 0), e1 = out_arc(q, 1);
-            both = (e0 == ex_arc && e1 == keep) || (e1 == ex_arc && e0 == keep);
-          }
-          if (both) {
-            // collapse q -> leaf carrying the smaller label; p -> leaf carrying the same label
-            const int s_lab = w.tmin[p], t_lab = w.tmax[p];
-            w.at[ex_arc] = (I)-1; w.at[keep] = (I)-1;
-            if (c != hy) w.at[in_arc(hy, 0)] = (I)-1;
-            w.hlab[hx] = (I)-1; w.hlab[hy] = (I)-1;
-            const int ts = w.l2t[s_lab], tt = w.l2t[t_lab];
-            w.tlab[ts] = (I)-1; w.tpar[ts] = (I)TDEAD; w.tlab[tt] = (I)-1; w.tpar[tt] = (I)TDEAD;
-            w.hlab[q] = (I)s_lab; w.l2h[s_lab] = (I)q; w.l2h[t_lab] = (I)-1;
-            w.tlab[p] = (I)s_lab; w.l2t[s_lab] = (I)p; w.l2t[t_lab] = (I)-1; w.tdeg[p] = 0;
-            ++collapsed;
-          } else ++fixed;
-          break;
-        }
+    PT_FOR(x, L) {
+      const int hx = w.l2h[x];
+      if (hx < 0 || indeg(hx) != 1) continue;
+      const int y = cherry_mate(x);
+      if (y < 0) continue;
+      const int hy = w.l2h[y];
+      const int ex_arc = in_arc(hx, 0);
+      const int q = w.at[ex_arc];
+      if (q < 0 || hy < 0) continue;
+      int c = -1;  // the multi-parent node whose parent gets fixed to q
+      if (indeg(hy) >= 2) c = hy;
+      else if (indeg(hy) == 1) { const int z = w.at[in_arc(hy, 0)]; if (z >= 0 && outdeg(z) == 1 && indeg(z) >= 2) c = z; }
+      if (c < 0) continue;
+      int keep = -1;
+      PT_NOUNROLL for (int k = 0; k < indeg(c); ++k) if (w.at[in_arc(c, k)] == q) keep = in_arc(c, k);
+      if (keep < 0) continue;
+      PT_NOUNROLL for (int k = 0; k < indeg(c); ++k) { const int e = in_arc(c, k); if (e != keep) w.at[e] = (I)-1; }
+      bool both = false;  // q's children are exactly hx and c (both arcs alive)
+      if (outdeg(q) == 2) {
+        const int e0 = out_arc(q, 0), e1 = out_arc(q, 1);
+        both = (e0 == ex_arc && e1 == keep) || (e1 == ex_arc && e0 == keep);
       }
+      if (both) {
+        // collapse q -> leaf carrying the smaller label; the guest cherry -> leaf carrying the same label
+        const int s_lab = x < y ? x : y, t_lab = x < y ? y : x;
+        const int ts = w.l2t[s_lab], tt = w.l2t[t_lab], p = w.tpar[ts];
+        w.at[ex_arc] = (I)-1; w.at[keep] = (I)-1;
+        if (c != hy) w.at[in_arc(hy, 0)] = (I)-1;
+        w.hlab[hx] = (I)-1; w.hlab[hy] = (I)-1;
+        w.tlab[ts] = (I)-1; w.tpar[ts] = (I)TDEAD; w.tlab[tt] = (I)-1; w.tpar[tt] = (I)TDEAD;
+        w.hlab[q] = (I)s_lab; w.l2h[s_lab] = (I)q; w.l2h[t_lab] = (I)-1;
+        w.tlab[p] = (I)s_lab; w.l2t[s_lab] = (I)p; w.l2t[t_lab] = (I)-1; w.tdeg[p] = 0;
+        w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)q;
+        ++collapsed;
+      } else ++fixed;
     }
     const int nc = ex.reduce_add(collapsed), nf = ex.reduce_add(fixed);
     st.retcherries += (unsigned)(nc + nf);
@@ -588,16 +610,13 @@ struct TcSolver {
     ex.phase = 10;
     PT_FOR(v, n + 1) { w.haux[v] = -1; w.hcnt[v] = 0; }
     ex.sync();
-    PT_FOR(p, nt) {
-      if (is_bin_cherry(p)) {
-        PT_NOUNROLL for (int side = 0; side < 2; ++side) {
-          const int x = side ? w.tmax[p] : w.tmin[p], y = side ? w.tmin[p] : w.tmax[p];
-          const int hx = w.l2h[x];
-          if (indeg(hx) != 1) continue;
-          const int q = w.at[in_arc(hx, 0)];
-          PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) { const int e = out_arc(q, k); if (w.ah[e] != hx) constrain_arc(e, y); }
-        }
-      }
+    PT_FOR(x, L) {
+      const int hx = w.l2h[x];
+      if (hx < 0 || indeg(hx) != 1) continue;
+      const int y = cherry_mate(x);
+      if (y < 0) continue;
+      const int q = w.at[in_arc(hx, 0)];
+      PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) { const int e = out_arc(q, k); if (w.ah[e] != hx) constrain_arc(e, y); }
     }
     // propagate through single-parent nodes
     for (;;) {
@@ -710,14 +729,15 @@ struct TcSolver {
       clean_host(dag_state, status);
       if (*status != TCS_OK) return TC_ERROR;
       if (missing || ex.uniform(&w.sc[F_FAIL])) return TC_NOT;
+      ex.phase = 14;
       if (count_labels() <= 2) return TC_DISPLAYED;  // containment.hpp:1061,1208
       // true cherries and on-the-spot reticulated cherries alternate without rebuilding the CSR: pendant subtrees that match
       // collapse level by level; only a fixed-but-not-collapsed reticulation (or nothing at all) sends us back to clean-up
-      int r, progress = 0;
+      int r, progress = 0, head = 0;
       for (;;) {
-        for (;;) { r = rule_true_cherry(); if (r <= 0) break; progress = 1; }
+        r = rule_true_cherry(head);
         if (r < 0) break;
-        guest_cherries();
+        if (r > 0) progress = 1;
         r = rule_ret_cherry();
         if (r) progress = 1;
         if (!(r & 2)) break;

@@ -62,9 +62,25 @@ void dev_free(void* p) {
 }
 
 // ---- the warp executor: PT_FOR = lane-strided loop, barrier = __syncwarp, atomics on shared memory ---------------
+#ifdef PT_PROFILE
+// profiling build (make prof -> libptgpu_prof.so, never shipped): cycles per solver pass, summed over warps
+__device__ unsigned long long g_prof[2][64];  // [0] cycles  [1] entries
+struct PhaseProbe {
+  int cur; long long t0;
+  __device__ __forceinline__ void operator=(int p) {
+    const long long t = clock64();
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&g_prof[0][cur & 63], (unsigned long long)(t - t0)); atomicAdd(&g_prof[1][p & 63], 1ull); }
+    cur = p; t0 = clock64();
+  }
+};
+#define PT_PHASE_INIT {0, clock64()}
+#else
+typedef int PhaseProbe;
+#define PT_PHASE_INIT 0
+#endif
 struct WarpEx {
   int lane;
-  int phase;  // last pass entered (debug aid, see CtaEx)
+  PhaseProbe phase;  // last pass entered (debug aid, see CtaEx)
   __device__ __forceinline__ int tid() const { return lane; }
   __device__ __forceinline__ int nth() const { return 32; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
@@ -76,9 +92,29 @@ struct WarpEx {
   __device__ __forceinline__ int atomic_min(int32_t* p, int v) const { return atomicMin(p, v); }
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
   __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
+  __device__ __forceinline__ int atomic_xor(int32_t* p, int v) const { return atomicXor(p, v); }
+  __device__ __forceinline__ int ldg(const int32_t* p) const { return __ldg(p); }  // caller's arrays: read-only during the launch
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
     return (int)(int16_t)atomicCAS((unsigned short*)p, (unsigned short)(int16_t)c, (unsigned short)(int16_t)v);
+  }
+  // stable in-place compaction of the arc arrays (keeps at >= 0), counting the heads of the survivors; returns the new count.
+  // A tile's loads complete before its ballot does and its stores go to positions <= the ones just read.
+  template <class I>
+  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m, int32_t* headcnt) const {
+    int carry = 0;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int base = 0; base < m; base += 32) {
+      const int i = base + lane;
+      int t = -1, h = 0;
+      if (i < m) { t = at[i]; h = ah[i]; }
+      const unsigned mask = __ballot_sync(0xffffffffu, t >= 0);
+      if (t >= 0) { const int pos = carry + __popc(mask & lt); at[pos] = (I)t; ah[pos] = (I)h; atomicAdd(&headcnt[h], 1); }
+      carry += __popc(mask);
+    }
+    __syncwarp();
+    return carry;
   }
   // out[0..n] = exclusive prefix sums of in[0..n): tiles of 32 consecutive elements (bank-conflict free), one shuffle scan
   // per tile with a running carry.  (The first version gave every lane a contiguous chunk: 8-way bank conflicts, 7 % of all
@@ -152,8 +188,32 @@ struct CtaEx {
   __device__ __forceinline__ int atomic_min(int32_t* p, int v) const { return atomicMin(p, v); }
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
   __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
+  __device__ __forceinline__ int atomic_xor(int32_t* p, int v) const { return atomicXor(p, v); }
+  __device__ __forceinline__ int ldg(const int32_t* p) const { return __ldg(p); }  // caller's arrays: read-only during the launch
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
+  template <class I>
+  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m, int32_t* headcnt) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    sync();
+    int carry = 0;
+    for (int base = 0; base < m; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      int t = -1, h = 0;
+      if (i < m) { t = at[i]; h = ah[i]; }
+      const unsigned mask = __ballot_sync(0xffffffffu, t >= 0);
+      if (lane == 0) red[wid] = __popc(mask);
+      __syncthreads();  // every thread has read its element of this tile
+      int woff = 0, total = 0;
+      for (int k = 0; k < nw; ++k) { const int c = red[k]; if (k < wid) woff += c; total += c; }
+      if (t >= 0) { const int pos = carry + woff + __popc(mask & lt); at[pos] = (I)t; ah[pos] = (I)h; atomicAdd(&headcnt[h], 1); }
+      carry += total;
+      __syncthreads();
+    }
+    sync();
+    return carry;
+  }
   // tile-by-tile block scan with a running carry: coalesced, two barriers per tile of blockDim.x elements
   template <class T>
   __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) {
@@ -203,7 +263,7 @@ __global__ void __launch_bounds__(640) tc_reduce_kernel(TcSource src, TcSink sin
                                                         unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpEx ex{lane, 0};
+  WarpEx ex{lane, PT_PHASE_INIT};
   TcWork<I> w;
   w.carve(smem + (size_t)warp * warp_bytes, capN, capM, capNT, capL);
   const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
@@ -235,6 +295,7 @@ __global__ void __launch_bounds__(640) tc_reduce_kernel(TcSource src, TcSink sin
     TcSolver<WarpEx, I> sv(ex, w);
     int st = 0, x = -1;
     const int code = sv.solve(in, src.is_pool != 0, &st, &x);
+    ex.phase = 13;
     ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
     if (code == TC_DISPLAYED) {
       if (lane == 0) { atomicOr(&result_bits[origin >> 5], 1u << (origin & 31)); }
@@ -381,6 +442,14 @@ __global__ void tc_maxima_kernel(int64_t B, const int64_t* hnode_off, const int6
 }  // namespace ptgpu
 
 using namespace ptgpu;
+
+#ifdef PT_PROFILE
+extern "C" int pt_debug_profile(unsigned long long* out128) {
+  unsigned long long z[128] = {};
+  if (cudaMemcpyFromSymbol(out128, g_prof, sizeof(z)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(g_prof, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 struct pt_batch {
   int64_t B = 0;

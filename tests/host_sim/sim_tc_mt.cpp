@@ -39,6 +39,7 @@ struct GroupEx {
   int nth() const { return T; }
   void sync() { ++nsync; sh->bar.wait(); }
   int map(int i, int) const { return i; }
+  int ldg(const int32_t* p) const { return *p; }
   int uniform(const int32_t* p) { sync(); if (t == 0) sh->scratch[0] = __atomic_load_n(p, __ATOMIC_SEQ_CST); sync(); const int v = sh->scratch[0]; sync(); return v; }
   int reduce_or(int v) { sync(); if (t == 0) sh->red_or = 0; sync(); if (v) sh->red_or.fetch_or(v); sync(); return sh->red_or.load(); }
   int reduce_add(int v) { sync(); if (t == 0) sh->red_add = 0; sync(); if (v) sh->red_add.fetch_add(v); sync(); return sh->red_add.load(); }
@@ -46,8 +47,17 @@ struct GroupEx {
   template <class X> X atomic_min(X* p, X v) const { X o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
   template <class X> X atomic_max(X* p, X v) const { X o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
   template <class X> X atomic_or(X* p, X v) const { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+  template <class X> X atomic_xor(X* p, X v) const { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
   template <class X> X atomic_cas(X* p, X c, X v) const { __atomic_compare_exchange_n(p, &c, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return c; }
   template <class X> int atomic_cas_idx(X* p, int c, int v) const { X e = (X)c; __atomic_compare_exchange_n(p, &e, (X)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return (int)e; }
+  template <class X> int compact_arcs(X* at, X* ah, int m, int32_t* headcnt) {
+    sync();
+    if (t == 0) { int k = 0; for (int e = 0; e < m; ++e) if (at[e] >= 0) { at[k] = at[e]; ah[k] = ah[e]; ++headcnt[ah[k]]; ++k; } sh->scratch[0] = k; }
+    sync();
+    const int k = sh->scratch[0];
+    sync();
+    return k;
+  }
   template <class X> void exclusive_scan(const int32_t* in, X* out, int n) { sync(); if (t == 0) { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (X)acc; acc += in[i]; } out[n] = (X)acc; } sync(); }
 };
 

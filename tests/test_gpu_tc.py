@@ -228,7 +228,8 @@ def test_executors_agree_on_mid_size(pt):
     b.free()
     assert (s1 == 0).all() and (s2 == 0).all()
     assert (v1 == v2).all() and v1[:300].all()
-    assert c1["work_items"] == c2["work_items"] and c1["cherry_reductions"] == c2["cherry_reductions"]
+    # (work-item counts may differ: a pool item is skipped when a sibling branch of the same launch has already displayed its origin)
+    assert c1["displayed"] == c2["displayed"] and c1["instances"] == c2["instances"]
 
 
 def test_instances_beyond_shared_memory(pt):
