@@ -45,6 +45,9 @@
 #endif
 
 namespace ptgpu {
+#ifdef PT_SIM_STATS
+static long g_sim_csr_calls, g_sim_live_nodes, g_sim_nodes, g_sim_live_arcs;
+#endif
 
 // parallel-for over [0,n): i_ is the executor's slot, i the (possibly permuted) element
 #define PT_FOR(i, n) \
@@ -85,7 +88,7 @@ struct TcWork {
   I *at, *ah;            // arc tail / head; at < 0 = deleted.  Arcs stay SORTED BY TAIL: rewriting only deletes arcs or moves heads
   I *ooff;               // out CSR: the out-arcs of v are the arc ids [ooff[v], ooff[v+1]) (csr() compacts the arc arrays)
   I *ioff, *iarc;        // in CSR (arc ids)
-  I *hlab;               // label of a live labelled leaf, else -1
+  I *hlab;               // label of a live labelled leaf, else -1 (capN+1: csr() swaps it with lvl when it renumbers the nodes)
   I *lvl;                // height (longest path to a leaf) from the wavefront; scratch otherwise
   int32_t *hcnt, *haux;  // atomic scratch, capN+1 each
   I* hscr;               // FIFO of the wavefront / scan target of emit_child, capN+1
@@ -109,7 +112,7 @@ struct TcWork {
   PT_HD static size_t bytes(int N, int M, int NT, int L) {
     const int W = sig_words(L);
     size_t b = 0;
-    b += (size_t)(2 * M + (N + 1) + (N + 1) + M + N + 2 * (N + 1)) * sizeof(I);  // at ah ooff ioff iarc hlab lvl hscr
+    b += (size_t)(2 * M + (N + 1) + (N + 1) + M + 3 * (N + 1)) * sizeof(I);  // at ah ooff ioff iarc hlab lvl hscr
     b = (b + 3) & ~(size_t)3;
     b += (size_t)(2 * (N + 1)) * 4;                                         // hcnt haux
     b += (size_t)N * W * 4;                                                 // lset
@@ -121,24 +124,28 @@ struct TcWork {
     b += kScalars * 4;
     return (b + 15) & ~(size_t)15;
   }
-  PT_HD void carve(void* base, int N, int M, int NT, int L) {
+  // All pointers are formed as base + offset (no pointer -> integer -> pointer round trip): the CUDA compiler then keeps the
+  // address space of `base`, and the warp executor gets LDS / STS / ATOMS instead of generic LD / ST / ATOM.
+  PT_HD void carve(char* base, int N, int M, int NT, int L) {
     capN = N; capM = M; capNT = NT; capL = L; W = sig_words(L);
-    char* p = (char*)base;
-    auto take = [&](size_t nbytes) { char* r = p; p += nbytes; return r; };
-    at = (I*)take((size_t)M * sizeof(I)); ah = (I*)take((size_t)M * sizeof(I));
-    ooff = (I*)take((size_t)(N + 1) * sizeof(I));
-    ioff = (I*)take((size_t)(N + 1) * sizeof(I)); iarc = (I*)take((size_t)M * sizeof(I));
-    hlab = (I*)take((size_t)N * sizeof(I)); lvl = (I*)take((size_t)(N + 1) * sizeof(I)); hscr = (I*)take((size_t)(N + 1) * sizeof(I));
-    p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
-    hcnt = (int32_t*)take((size_t)(N + 1) * 4); haux = (int32_t*)take((size_t)(N + 1) * 4);
-    lset = (uint32_t*)take((size_t)N * W * 4);
-    tpar = (I*)take((size_t)NT * sizeof(I)); tlab = (I*)take((size_t)NT * sizeof(I));
-    p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
-    tdeg = (int32_t*)take((size_t)(NT + 1) * 4); tleaf = (int32_t*)take((size_t)(NT + 1) * 4);
-    tmin = (int32_t*)take((size_t)(NT + 1) * 4); tmax = (int32_t*)take((size_t)(NT + 1) * 4);
-    l2h = (I*)take((size_t)L * sizeof(I)); l2t = (I*)take((size_t)L * sizeof(I));
-    p = (char*)(((uintptr_t)p + 3) & ~(uintptr_t)3);
-    sc = (int32_t*)take(kScalars * 4);
+    size_t o = 0;
+    auto take = [&](size_t nbytes) { const size_t r = o; o += nbytes; return r; };
+    auto align4 = [&]() { o = (o + 3) & ~(size_t)3; };
+    at = (I*)(base + take((size_t)M * sizeof(I))); ah = (I*)(base + take((size_t)M * sizeof(I)));
+    ooff = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
+    ioff = (I*)(base + take((size_t)(N + 1) * sizeof(I))); iarc = (I*)(base + take((size_t)M * sizeof(I)));
+    hlab = (I*)(base + take((size_t)(N + 1) * sizeof(I))); lvl = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
+    hscr = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
+    align4();
+    hcnt = (int32_t*)(base + take((size_t)(N + 1) * 4)); haux = (int32_t*)(base + take((size_t)(N + 1) * 4));
+    lset = (uint32_t*)(base + take((size_t)N * W * 4));
+    tpar = (I*)(base + take((size_t)NT * sizeof(I))); tlab = (I*)(base + take((size_t)NT * sizeof(I)));
+    align4();
+    tdeg = (int32_t*)(base + take((size_t)(NT + 1) * 4)); tleaf = (int32_t*)(base + take((size_t)(NT + 1) * 4));
+    tmin = (int32_t*)(base + take((size_t)(NT + 1) * 4)); tmax = (int32_t*)(base + take((size_t)(NT + 1) * 4));
+    l2h = (I*)(base + take((size_t)L * sizeof(I))); l2t = (I*)(base + take((size_t)L * sizeof(I)));
+    align4();
+    sc = (int32_t*)(base + take(kScalars * 4));
   }
 };
 
@@ -304,9 +311,28 @@ struct TcSolver {
   PT_NI void csr() {
     ex.phase = 3;
     if (ex.tid() == 0) w.sc[F_QTAIL] = 0;
+    m = ex.compact_arcs(w.at, w.ah, m);  // drops dead arcs (ends with a barrier)
+    // The instance shrinks quickly (on BASELINE config 2 the average snapshot has 67 of 228 nodes alive).  Once a quarter of
+    // the node ids is dead, renumber the live ones so that every later pass is proportional to what is left.
+    if (4 * (m + 1) < 3 * n) {
+      const int root = ex.uniform(&w.sc[F_ROOT]);
+      PT_FOR(v, n + 1) { w.hcnt[v] = (v < n && (w.hlab[v] >= 0 || v == root)) ? 1 : 0; }
+      ex.sync();
+      PT_FOR(e, m) { w.hcnt[w.at[e]] = 1; w.hcnt[w.ah[e]] = 1; }
+      ex.sync();
+      ex.exclusive_scan(w.hcnt, w.hscr, n);  // hscr[v] = new id of v
+      PT_FOR(e, m) { w.at[e] = w.hscr[w.at[e]]; w.ah[e] = w.hscr[w.ah[e]]; }
+      PT_FOR(v, n) { if (w.hcnt[v]) w.lvl[w.hscr[v]] = w.hlab[v]; }  // lvl is the second buffer of hlab
+      PT_FOR(l, L) { const int h = w.l2h[l]; if (h >= 0) w.l2h[l] = w.hscr[h]; }
+      if (ex.tid() == 0) w.sc[F_ROOT] = w.hscr[root];
+      const int n2 = w.hscr[n];
+      ex.sync();
+      I* const t = w.hlab; w.hlab = w.lvl; w.lvl = t;
+      n = n2;
+    }
     PT_FOR(v, n + 1) { w.haux[v] = 0; w.lvl[v] = (I)0; }  // lvl = "queued as a true cherry in this snapshot"
     ex.sync();
-    m = ex.compact_arcs(w.at, w.ah, m, w.haux);  // drops dead arcs, haux[h] = live in-degree of h
+    PT_FOR(e, m) { ex.atomic_add(&w.haux[w.ah[e]], 1); }
     PT_FOR(e, m + 1) {
       const int lo = e > 0 ? w.at[e - 1] + 1 : 0, hi = e < m ? (int)w.at[e] : n;
       PT_NOUNROLL for (int v = lo; v <= hi; ++v) w.ooff[v] = (I)e;
@@ -314,6 +340,9 @@ struct TcSolver {
     ex.exclusive_scan(w.haux, w.ioff, n);
     PT_FOR(e, m) { const int h = w.ah[e]; w.iarc[w.ioff[h] + ex.atomic_add(&w.haux[h], -1) - 1] = (I)e; }
     ex.sync();
+#ifdef PT_SIM_STATS
+    { int live = 0; for (int v = 0; v < n; ++v) live += (indeg(v) > 0 || outdeg(v) > 0); g_sim_csr_calls++; g_sim_live_nodes += live; g_sim_nodes += n; g_sim_live_arcs += m; }
+#endif
   }
 
   PT_HD bool suppressible(int v) const { return indeg(v) == 1 && outdeg(v) == 1; }

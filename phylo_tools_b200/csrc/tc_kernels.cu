@@ -85,7 +85,8 @@ struct WarpEx {
   __device__ __forceinline__ int nth() const { return 32; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   __device__ __forceinline__ int map(int i, int) const { return i; }
-  __device__ __forceinline__ int uniform(const int32_t* p) const { __syncwarp(); int v = 0; if (lane == 0) v = *(const volatile int32_t*)p; v = __shfl_sync(0xffffffffu, v, 0); __syncwarp(); return v; }
+  // shared memory: between the two barriers nobody writes, so every lane reads the same value (one broadcast load)
+  __device__ __forceinline__ int uniform(const int32_t* p) const { __syncwarp(); const int v = *(const volatile int32_t*)p; __syncwarp(); return v; }
   __device__ __forceinline__ int reduce_or(int v) const { return (int)__reduce_or_sync(0xffffffffu, (unsigned)v); }
   __device__ __forceinline__ int reduce_add(int v) const { return __reduce_add_sync(0xffffffffu, v); }
   __device__ __forceinline__ int atomic_add(int32_t* p, int v) const { return atomicAdd(p, v); }
@@ -98,10 +99,10 @@ struct WarpEx {
   __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
     return (int)(int16_t)atomicCAS((unsigned short*)p, (unsigned short)(int16_t)c, (unsigned short)(int16_t)v);
   }
-  // stable in-place compaction of the arc arrays (keeps at >= 0), counting the heads of the survivors; returns the new count.
+  // stable in-place compaction of the arc arrays (keeps at >= 0); returns the new count.
   // A tile's loads complete before its ballot does and its stores go to positions <= the ones just read.
   template <class I>
-  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m, int32_t* headcnt) const {
+  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m) const {
     int carry = 0;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
@@ -110,32 +111,52 @@ struct WarpEx {
       int t = -1, h = 0;
       if (i < m) { t = at[i]; h = ah[i]; }
       const unsigned mask = __ballot_sync(0xffffffffu, t >= 0);
-      if (t >= 0) { const int pos = carry + __popc(mask & lt); at[pos] = (I)t; ah[pos] = (I)h; atomicAdd(&headcnt[h], 1); }
+      if (t >= 0) { const int pos = carry + __popc(mask & lt); at[pos] = (I)t; ah[pos] = (I)h; }
       carry += __popc(mask);
     }
     __syncwarp();
     return carry;
   }
-  // out[0..n] = exclusive prefix sums of in[0..n): tiles of 32 consecutive elements (bank-conflict free), one shuffle scan
-  // per tile with a running carry.  (The first version gave every lane a contiguous chunk: 8-way bank conflicts, 7 % of all
-  // stall samples of the kernel.)
+  // out[0..n] = exclusive prefix sums of in[0..n): see warp_exclusive_scan below (one shared, out-of-line copy: inlined at its
+  // five call sites the scan was 46 KB of SASS, and instruction fetch was the kernel's first stall reason)
   template <class T>
-  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) const {
-    __syncwarp();
-    int carry = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const int v = i < n ? in[i] : 0;
-      int incl = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-      if (i < n) out[i] = (T)(carry + incl - v);
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) out[n] = (T)carry;
-    __syncwarp();
-  }
+  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) const;
 };
+
+// tiles of 32 consecutive elements (bank-conflict free), one shuffle scan per tile with a running carry.  (The first version
+// gave every lane a contiguous chunk: 8-way bank conflicts, 7 % of all stall samples of the kernel.)  Takes shared-window
+// addresses so that the out-of-line copy still uses LDS / STS.
+template <int OUT_BYTES>
+__device__ __noinline__ void warp_exclusive_scan(unsigned in_s, unsigned out_s, int n) {
+  const int lane = threadIdx.x & 31;
+  int carry = 0;
+#pragma unroll 1
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    int v = 0;
+    if (i < n) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(in_s + 4u * (unsigned)i) : "memory");
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    const int o = carry + incl - v;
+    if (i < n) {
+      if (OUT_BYTES == 2) asm volatile("st.shared.b16 [%0], %1;" ::"r"(out_s + 2u * (unsigned)i), "h"((short)o) : "memory");
+      else asm volatile("st.shared.b32 [%0], %1;" ::"r"(out_s + 4u * (unsigned)i), "r"(o) : "memory");
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    if (OUT_BYTES == 2) asm volatile("st.shared.b16 [%0], %1;" ::"r"(out_s + 2u * (unsigned)n), "h"((short)carry) : "memory");
+    else asm volatile("st.shared.b32 [%0], %1;" ::"r"(out_s + 4u * (unsigned)n), "r"(carry) : "memory");
+  }
+  __syncwarp();
+}
+template <class T>
+__device__ __forceinline__ void WarpEx::exclusive_scan(const int32_t* in, T* out, int n) const {
+  static_assert(sizeof(T) == 2 || sizeof(T) == 4, "index type");
+  __syncwarp();
+  warp_exclusive_scan<(int)sizeof(T)>((unsigned)__cvta_generic_to_shared(in), (unsigned)__cvta_generic_to_shared(out), n);
+}
 
 // ---- the CTA executor: one thread block per instance, workspace in GLOBAL memory (int32 ids), barrier = __syncthreads ----
 // For instances that do not fit one CTA's shared memory (BASELINE config 4: n = 10^6).  Same solver code, other executor.
@@ -193,7 +214,7 @@ struct CtaEx {
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   template <class I>
-  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m, int32_t* headcnt) {
+  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     sync();
@@ -207,7 +228,7 @@ struct CtaEx {
       __syncthreads();  // every thread has read its element of this tile
       int woff = 0, total = 0;
       for (int k = 0; k < nw; ++k) { const int c = red[k]; if (k < wid) woff += c; total += c; }
-      if (t >= 0) { const int pos = carry + woff + __popc(mask & lt); at[pos] = (I)t; ah[pos] = (I)h; atomicAdd(&headcnt[h], 1); }
+      if (t >= 0) { const int pos = carry + woff + __popc(mask & lt); at[pos] = (I)t; ah[pos] = (I)h; }
       carry += total;
       __syncthreads();
     }
@@ -257,7 +278,7 @@ struct TcSink {
 enum { CNT_DISPLAYED = 0, CNT_ITEMS, CNT_BRANCH_ITEMS, CNT_CHERRIES, CNT_RET, CNT_ARCS, CNT_PASSES, CNT_ERRORS, CNT_N };
 
 template <class I>
-__global__ void __launch_bounds__(640) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
+__global__ void __launch_bounds__(640, 1) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
                                                         uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                         uint8_t* __restrict__ branched, int32_t* __restrict__ ticket,
                                                         unsigned long long* __restrict__ counters) {
@@ -265,7 +286,7 @@ __global__ void __launch_bounds__(640) tc_reduce_kernel(TcSource src, TcSink sin
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpEx ex{lane, PT_PHASE_INIT};
   TcWork<I> w;
-  w.carve(smem + (size_t)warp * warp_bytes, capN, capM, capNT, capL);
+  w.carve(reinterpret_cast<char*>(smem) + (size_t)warp * warp_bytes, capN, capM, capNT, capL);
   const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
   unsigned long long c_disp = 0, c_items = 0, c_br = 0, c_ch = 0, c_ret = 0, c_arc = 0, c_pass = 0, c_err = 0;
   for (;;) {
@@ -347,7 +368,7 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
   __shared__ int s_red[40];
   CtaEx ex{s_red, 0, 0};
   TcWork<I> w;
-  w.carve(ws + (size_t)blockIdx.x * ws_bytes, capN, capM, capNT, capL);
+  w.carve(reinterpret_cast<char*>(ws) + (size_t)blockIdx.x * ws_bytes, capN, capM, capNT, capL);
   const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
   unsigned long long c_disp = 0, c_items = 0, c_br = 0, c_ch = 0, c_ret = 0, c_arc = 0, c_pass = 0, c_err = 0;
   for (;;) {

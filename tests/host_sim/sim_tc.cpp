@@ -46,9 +46,9 @@ struct HostEx {
   template <class T> T atomic_xor(T* p, T v) const { T o = *p; *p = (T)(o ^ v); return o; }
   template <class T> T atomic_cas(T* p, T c, T v) const { T o = *p; if (o == c) *p = v; return o; }
   template <class T> int atomic_cas_idx(T* p, int c, int v) const { int o = *p; if (o == c) *p = (T)v; return o; }
-  template <class T> int compact_arcs(T* at, T* ah, int m, int32_t* headcnt) const {
+  template <class T> int compact_arcs(T* at, T* ah, int m) const {
     int k = 0;
-    for (int e = 0; e < m; ++e) if (at[e] >= 0) { at[k] = at[e]; ah[k] = ah[e]; ++headcnt[ah[k]]; ++k; }
+    for (int e = 0; e < m; ++e) if (at[e] >= 0) { at[k] = at[e]; ah[k] = ah[e]; ++k; }
     return k;
   }
   template <class T> void exclusive_scan(const int32_t* in, T* out, int n) const { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (T)acc; acc += in[i]; } out[n] = (T)acc; }
