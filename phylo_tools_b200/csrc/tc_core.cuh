@@ -90,12 +90,12 @@ struct TcWork {
   I *ioff, *iarc;        // in CSR (arc ids)
   I *hlab;               // label of a live labelled leaf, else -1 (capN+1: csr() swaps it with lvl when it renumbers the nodes)
   I *lvl;                // height (longest path to a leaf) from the wavefront; scratch otherwise
-  int32_t *hcnt, *haux;  // atomic scratch, capN+1 each
+  I *hcnt, *haux;        // atomic scratch, max(capN, capNT)+1 each (the guest passes of clean_guest / emit_child borrow them)
   I* hscr;               // FIFO of the wavefront / scan target of emit_child, capN+1
   uint32_t* lset;        // capN * W : labels reachable below each node
   // guest tree
   I *tpar, *tlab;        // tpar: -1 root, -2 deleted
-  int32_t *tdeg, *tleaf, *tmin, *tmax;  // tdeg: live children; tmax: XOR of the children's ids; tleaf, tmin: scratch
+  I *tdeg, *tmax;        // tdeg: live children; tmax: XOR of the children's ids
   // labels
   I *l2h, *l2t;
   // scalars (shared)
@@ -110,17 +110,12 @@ struct TcWork {
   static constexpr int kMaxExactWords = 1;
   PT_HD static int sig_words(int L) { const int w = (L + 31) / 32; return w < 1 ? 1 : (w > kMaxExactWords ? kMaxExactWords : w); }
   PT_HD static size_t bytes(int N, int M, int NT, int L) {
-    const int W = sig_words(L);
+    const int W = sig_words(L), S = (N > NT ? N : NT) + 1;
     size_t b = 0;
-    b += (size_t)(2 * M + (N + 1) + (N + 1) + M + 3 * (N + 1)) * sizeof(I);  // at ah ooff ioff iarc hlab lvl hscr
+    b += (size_t)(3 * M + 5 * (N + 1) + 2 * S) * sizeof(I);   // at ah iarc | ooff ioff hlab lvl hscr | hcnt haux
+    b += (size_t)(2 * NT + 2 * (NT + 1) + 2 * L) * sizeof(I); // tpar tlab | tdeg tmax | l2h l2t
     b = (b + 3) & ~(size_t)3;
-    b += (size_t)(2 * (N + 1)) * 4;                                         // hcnt haux
-    b += (size_t)N * W * 4;                                                 // lset
-    b += (size_t)(2 * NT) * sizeof(I);                                      // tpar tlab
-    b = (b + 3) & ~(size_t)3;
-    b += (size_t)(4 * (NT + 1)) * 4;                                        // tdeg tleaf tmin tmax
-    b += (size_t)(2 * L) * sizeof(I);                                       // l2h l2t
-    b = (b + 3) & ~(size_t)3;
+    b += (size_t)N * W * 4;                                   // lset
     b += kScalars * 4;
     return (b + 15) & ~(size_t)15;
   }
@@ -128,23 +123,19 @@ struct TcWork {
   // address space of `base`, and the warp executor gets LDS / STS / ATOMS instead of generic LD / ST / ATOM.
   PT_HD void carve(char* base, int N, int M, int NT, int L) {
     capN = N; capM = M; capNT = NT; capL = L; W = sig_words(L);
+    const int S = (N > NT ? N : NT) + 1;
     size_t o = 0;
     auto take = [&](size_t nbytes) { const size_t r = o; o += nbytes; return r; };
-    auto align4 = [&]() { o = (o + 3) & ~(size_t)3; };
-    at = (I*)(base + take((size_t)M * sizeof(I))); ah = (I*)(base + take((size_t)M * sizeof(I)));
-    ooff = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
-    ioff = (I*)(base + take((size_t)(N + 1) * sizeof(I))); iarc = (I*)(base + take((size_t)M * sizeof(I)));
+    at = (I*)(base + take((size_t)M * sizeof(I))); ah = (I*)(base + take((size_t)M * sizeof(I))); iarc = (I*)(base + take((size_t)M * sizeof(I)));
+    ooff = (I*)(base + take((size_t)(N + 1) * sizeof(I))); ioff = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
     hlab = (I*)(base + take((size_t)(N + 1) * sizeof(I))); lvl = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
     hscr = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
-    align4();
-    hcnt = (int32_t*)(base + take((size_t)(N + 1) * 4)); haux = (int32_t*)(base + take((size_t)(N + 1) * 4));
-    lset = (uint32_t*)(base + take((size_t)N * W * 4));
+    hcnt = (I*)(base + take((size_t)S * sizeof(I))); haux = (I*)(base + take((size_t)S * sizeof(I)));
     tpar = (I*)(base + take((size_t)NT * sizeof(I))); tlab = (I*)(base + take((size_t)NT * sizeof(I)));
-    align4();
-    tdeg = (int32_t*)(base + take((size_t)(NT + 1) * 4)); tleaf = (int32_t*)(base + take((size_t)(NT + 1) * 4));
-    tmin = (int32_t*)(base + take((size_t)(NT + 1) * 4)); tmax = (int32_t*)(base + take((size_t)(NT + 1) * 4));
+    tdeg = (I*)(base + take((size_t)(NT + 1) * sizeof(I))); tmax = (I*)(base + take((size_t)(NT + 1) * sizeof(I)));
     l2h = (I*)(base + take((size_t)L * sizeof(I))); l2t = (I*)(base + take((size_t)L * sizeof(I)));
-    align4();
+    o = (o + 3) & ~(size_t)3;
+    lset = (uint32_t*)(base + take((size_t)N * W * 4));
     sc = (int32_t*)(base + take(kScalars * 4));
   }
 };
@@ -212,7 +203,7 @@ struct TcSolver {
       bad |= (p < -1) | (p >= nt) | (p == t);
       big |= (l >= w.capL) | (l < -1);
       maxlab = l > maxlab ? l : maxlab;
-      w.tpar[t] = (I)p; w.tlab[t] = (I)l; w.tdeg[t] = 0;
+      w.tpar[t] = (I)p; w.tlab[t] = (I)l; w.tdeg[t] = (I)0;
     }
     if (bad) w.sc[F_STATUS] = TCS_BAD_GRAPH; else if (big) w.sc[F_TMP2] = 1;
     ex.sync();
@@ -227,7 +218,7 @@ struct TcSolver {
     PT_FOR(l, L) { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
     ex.phase = 15;
     // guest: child counts, exactly one root, no cycles
-    PT_FOR(t, nt) { if (w.tpar[t] >= 0) ex.atomic_add(&w.tdeg[w.tpar[t]], 1); else ex.atomic_add(&w.sc[F_TMP], 1); }
+    PT_FOR(t, nt) { if (w.tpar[t] >= 0) ex.atomic_add_idx(&w.tdeg[w.tpar[t]], 1); else ex.atomic_add(&w.sc[F_TMP], 1); }
     if (nt > 0 && ex.uniform(&w.sc[F_TMP]) != 1) return TCS_BAD_GRAPH;
     PT_FOR(t, nt) {
       int x = t, steps = 0;
@@ -272,13 +263,13 @@ struct TcSolver {
         if (w.tpar[t] != TDEAD && w.tdeg[t] == 0 && w.tlab[t] < 0) {
           const int p = w.tpar[t];
           w.tpar[t] = (I)TDEAD;
-          if (p >= 0) ex.atomic_add(&w.tdeg[p], -1);
+          if (p >= 0) ex.atomic_add_idx(&w.tdeg[p], -1);
           w.sc[F_FLAG] = 1;
         }
       }
       if (!take_flag(F_FLAG)) break;
     }
-    // new parent = nearest proper ancestor with >= 2 live children (tmin used as the double buffer)
+    // new parent = nearest proper ancestor with >= 2 live children (haux is the double buffer)
     PT_FOR(t, nt) {
       int np = TDEAD;
       if (w.tpar[t] != TDEAD && w.tdeg[t] != 1) {
@@ -286,14 +277,14 @@ struct TcSolver {
         while (p >= 0 && w.tdeg[p] == 1) p = w.tpar[p];
         np = p;
       }
-      w.tmin[t] = np;
+      w.haux[t] = (I)np;
     }
     ex.sync();
-    PT_FOR(t, nt) { w.tpar[t] = (I)w.tmin[t]; if (w.tmin[t] == -1) w.sc[F_TROOT] = t; w.tmax[t] = 0; }
+    PT_FOR(t, nt) { w.tpar[t] = w.haux[t]; if (w.haux[t] == -1) w.sc[F_TROOT] = t; w.tmax[t] = (I)0; }
     ex.sync();
     // tmax[p] = XOR of the ids of p's children: the sibling of t below a binary p is tmax[p] ^ t.  Child SETS never change
     // afterwards (a collapse turns p into a leaf as a whole), so this is computed once per work item.
-    PT_FOR(t, nt) { if (w.tpar[t] >= 0) ex.atomic_xor(&w.tmax[w.tpar[t]], t); }
+    PT_FOR(t, nt) { if (w.tpar[t] >= 0) ex.atomic_xor_idx(&w.tmax[w.tpar[t]], t); }
     ex.sync();
   }
   // label of the other leaf of a binary guest cherry containing the leaf labelled l, else -1
@@ -316,9 +307,9 @@ struct TcSolver {
     // the node ids is dead, renumber the live ones so that every later pass is proportional to what is left.
     if (4 * (m + 1) < 3 * n) {
       const int root = ex.uniform(&w.sc[F_ROOT]);
-      PT_FOR(v, n + 1) { w.hcnt[v] = (v < n && (w.hlab[v] >= 0 || v == root)) ? 1 : 0; }
+      PT_FOR(v, n + 1) { w.hcnt[v] = (I)((v < n && (w.hlab[v] >= 0 || v == root)) ? 1 : 0); }
       ex.sync();
-      PT_FOR(e, m) { w.hcnt[w.at[e]] = 1; w.hcnt[w.ah[e]] = 1; }
+      PT_FOR(e, m) { w.hcnt[w.at[e]] = (I)1; w.hcnt[w.ah[e]] = (I)1; }
       ex.sync();
       ex.exclusive_scan(w.hcnt, w.hscr, n);  // hscr[v] = new id of v
       PT_FOR(e, m) { w.at[e] = w.hscr[w.at[e]]; w.ah[e] = w.hscr[w.ah[e]]; }
@@ -330,15 +321,15 @@ struct TcSolver {
       I* const t = w.hlab; w.hlab = w.lvl; w.lvl = t;
       n = n2;
     }
-    PT_FOR(v, n + 1) { w.haux[v] = 0; w.lvl[v] = (I)0; }  // lvl = "queued as a true cherry in this snapshot"
+    PT_FOR(v, n + 1) { w.haux[v] = (I)0; w.lvl[v] = (I)0; }  // lvl = "queued as a true cherry in this snapshot"
     ex.sync();
-    PT_FOR(e, m) { ex.atomic_add(&w.haux[w.ah[e]], 1); }
+    PT_FOR(e, m) { ex.atomic_add_idx(&w.haux[w.ah[e]], 1); }
     PT_FOR(e, m + 1) {
       const int lo = e > 0 ? w.at[e - 1] + 1 : 0, hi = e < m ? (int)w.at[e] : n;
       PT_NOUNROLL for (int v = lo; v <= hi; ++v) w.ooff[v] = (I)e;
     }
     ex.exclusive_scan(w.haux, w.ioff, n);
-    PT_FOR(e, m) { const int h = w.ah[e]; w.iarc[w.ioff[h] + ex.atomic_add(&w.haux[h], -1) - 1] = (I)e; }
+    PT_FOR(e, m) { const int h = w.ah[e]; w.iarc[w.ioff[h] + ex.atomic_add_idx(&w.haux[h], -1) - 1] = (I)e; }
     ex.sync();
 #ifdef PT_SIM_STATS
     { int live = 0; for (int v = 0; v < n; ++v) live += (indeg(v) > 0 || outdeg(v) > 0); g_sim_csr_calls++; g_sim_live_nodes += live; g_sim_nodes += n; g_sim_live_arcs += m; }
@@ -428,7 +419,7 @@ struct TcSolver {
         PT_FOR(v, n) {
           int y = -1;
           if (mergeable(v)) { int guard = 0; y = w.ah[out_arc(v, 0)]; while (mergeable(y) && ++guard <= n) y = w.ah[out_arc(y, 0)]; if (guard > n) w.sc[F_STATUS] = TCS_BAD_GRAPH; }
-          w.haux[v] = y;
+          w.haux[v] = (I)y;
         }
         if (take_flag(F_STATUS)) { *status = TCS_BAD_GRAPH; return; }
         PT_FOR(v, n) {
@@ -468,7 +459,7 @@ struct TcSolver {
     set_scalar(F_TMP, 0);  // queue tail
     PT_FOR(v, n) {
       PT_NOUNROLL for (int k = 0; k < W; ++k) w.lset[v * W + k] = 0;
-      w.hcnt[v] = outdeg(v);
+      w.hcnt[v] = (I)outdeg(v);
       w.lvl[v] = (I)LVL_INF;
       if (w.hlab[v] >= 0) { const int b = w.hlab[v] % (W * 32); w.lset[v * W + (b >> 5)] = 1u << (b & 31); }
       if (outdeg(v) == 0 && (indeg(v) > 0 || w.hlab[v] >= 0)) { w.lvl[v] = (I)0; w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)v; }
@@ -484,7 +475,7 @@ struct TcSolver {
         PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) {
           const int p = w.at[in_arc(v, k)];
           PT_NOUNROLL for (int j = 0; j < W; ++j) { const uint32_t b = w.lset[v * W + j]; if (b) ex.atomic_or(&w.lset[p * W + j], b); }
-          if (ex.atomic_add(&w.hcnt[p], -1) == 1) { w.lvl[p] = (I)(lv + 1); w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)p; }
+          if (ex.atomic_add_idx(&w.hcnt[p], -1) == 1) { w.lvl[p] = (I)(lv + 1); w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)p; }
         }
       }
       head = tail;
@@ -550,7 +541,7 @@ struct TcSolver {
           if (l != minl) { w.l2h[l] = (I)-1; w.l2t[l] = (I)-1; }
         }
         w.hlab[q] = (I)minl; w.l2h[minl] = (I)q;
-        w.tlab[p] = (I)minl; w.l2t[minl] = (I)p; w.tdeg[p] = 0;
+        w.tlab[p] = (I)minl; w.l2t[minl] = (I)p; w.tdeg[p] = (I)0;
         ++collapsed;
       }
       ex.sync();
@@ -610,7 +601,7 @@ struct TcSolver {
         w.hlab[hx] = (I)-1; w.hlab[hy] = (I)-1;
         w.tlab[ts] = (I)-1; w.tpar[ts] = (I)TDEAD; w.tlab[tt] = (I)-1; w.tpar[tt] = (I)TDEAD;
         w.hlab[q] = (I)s_lab; w.l2h[s_lab] = (I)q; w.l2h[t_lab] = (I)-1;
-        w.tlab[p] = (I)s_lab; w.l2t[s_lab] = (I)p; w.l2t[t_lab] = (I)-1; w.tdeg[p] = 0;
+        w.tlab[p] = (I)s_lab; w.l2t[s_lab] = (I)p; w.l2t[t_lab] = (I)-1; w.tdeg[p] = (I)0;
         w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)q;
         ++collapsed;
       } else ++fixed;
@@ -633,11 +624,11 @@ struct TcSolver {
     }
     if (outdeg(c) == 0) { if (!reach) w.sc[F_FAIL] = 1; return; }  // a labelled single-parent leaf that must die
     const int want = reach ? lam : -2;
-    if (w.haux[c] != want) { w.haux[c] = want; w.sc[F_TMP] = 1; }
+    if (w.haux[c] != want) { w.haux[c] = (I)want; w.sc[F_TMP] = 1; }
   }
   PT_NI int rule_sibling() {
     ex.phase = 10;
-    PT_FOR(v, n + 1) { w.haux[v] = -1; w.hcnt[v] = 0; }
+    PT_FOR(v, n + 1) { w.haux[v] = (I)-1; w.hcnt[v] = (I)0; }
     ex.sync();
     PT_FOR(x, L) {
       const int hx = w.l2h[x];
@@ -652,7 +643,7 @@ struct TcSolver {
       if (!take_flag(F_TMP)) break;
       PT_FOR(v, n) {
         if (w.haux[v] != -1 && !w.hcnt[v]) {
-          w.hcnt[v] = 1;
+          w.hcnt[v] = (I)1;
           PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) constrain_arc(out_arc(v, k), w.haux[v]);
         }
       }
@@ -687,7 +678,7 @@ struct TcSolver {
       const int live = (v < n && (v == root || indeg(v) > 0)) ? 1 : 0;
       int d = 0;
       if (live) PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) ++d; }
-      w.hcnt[v] = live; w.haux[v] = d;
+      w.hcnt[v] = (I)live; w.haux[v] = (I)d;
     }
     ex.sync();
     ex.exclusive_scan(w.hcnt, w.lvl, n);   // lvl[v] = new id of v, lvl[n] = n2
@@ -703,12 +694,13 @@ struct TcSolver {
       }
     }
     // guest
-    PT_FOR(t, nt + 1) { w.tleaf[t] = (t < nt && w.tpar[t] != TDEAD) ? 1 : 0; }
+    ex.sync();  // the host part is done with hcnt / haux
+    PT_FOR(t, nt + 1) { w.hcnt[t] = (I)((t < nt && w.tpar[t] != TDEAD) ? 1 : 0); }
     ex.sync();
-    ex.exclusive_scan(w.tleaf, w.tmin, nt);
-    const int nt2 = w.tmin[nt];
+    ex.exclusive_scan(w.hcnt, w.haux, nt);
+    const int nt2 = w.haux[nt];
     PT_FOR(t, nt) {
-      if (w.tleaf[t]) { const int id = w.tmin[t]; out.tparent[id] = w.tpar[t] >= 0 ? w.tmin[w.tpar[t]] : -1; out.tlabel[id] = w.tlab[t]; }
+      if (w.hcnt[t]) { const int id = w.haux[t]; out.tparent[id] = w.tpar[t] >= 0 ? w.haux[w.tpar[t]] : -1; out.tlabel[id] = w.tlab[t]; }
     }
     if (ex.tid() == 0) { out.succ_off[n2] = m2; out.dims[0] = n2; out.dims[1] = m2; out.dims[2] = nt2; out.dims[3] = L; }
     ex.sync();
@@ -721,7 +713,7 @@ struct TcSolver {
     int roots = 0;
     set_scalar(F_TMP, 0);
     PT_FOR(v, n) {
-      w.hcnt[v] = outdeg(v);
+      w.hcnt[v] = (I)outdeg(v);
       if (indeg(v) == 0) { ++roots; w.sc[F_ROOT] = v; }
       if (!trusted && outdeg(v) == 0) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)v;
     }
@@ -735,7 +727,7 @@ struct TcSolver {
       const int cnt = tail - head;
       PT_FOR(i, cnt) {
         const int v = w.hscr[head + i];
-        PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add(&w.hcnt[p], -1) == 1) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)p; }
+        PT_NOUNROLL for (int k = 0; k < indeg(v); ++k) { const int p = w.at[in_arc(v, k)]; if (ex.atomic_add_idx(&w.hcnt[p], -1) == 1) w.hscr[ex.atomic_add(&w.sc[F_TMP], 1)] = (I)p; }
       }
       head = tail;
       ex.sync();

@@ -99,6 +99,18 @@ struct WarpEx {
   __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
     return (int)(int16_t)atomicCAS((unsigned short*)p, (unsigned short)(int16_t)c, (unsigned short)(int16_t)v);
   }
+  // 16-bit counters, native 32-bit shared atomics on the word that holds them.  The counters are non-negative and never
+  // leave [0, 32767], so an add / sub never carries into the neighbouring half.
+  __device__ __forceinline__ int atomic_add_idx(int16_t* p, int v) const {
+    const unsigned odd = (unsigned)__cvta_generic_to_shared(p) & 2u, sh = odd << 3;
+    unsigned* wp = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p) - odd);
+    const unsigned old = v >= 0 ? atomicAdd(wp, (unsigned)v << sh) : atomicSub(wp, (unsigned)(-v) << sh);
+    return (int)(int16_t)(old >> sh);
+  }
+  __device__ __forceinline__ void atomic_xor_idx(int16_t* p, int v) const {
+    const unsigned odd = (unsigned)__cvta_generic_to_shared(p) & 2u, sh = odd << 3;
+    atomicXor(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(p) - odd), (unsigned)v << sh);
+  }
   // stable in-place compaction of the arc arrays (keeps at >= 0); returns the new count.
   // A tile's loads complete before its ballot does and its stores go to positions <= the ones just read.
   template <class I>
@@ -119,14 +131,14 @@ struct WarpEx {
   }
   // out[0..n] = exclusive prefix sums of in[0..n): see warp_exclusive_scan below (one shared, out-of-line copy: inlined at its
   // five call sites the scan was 46 KB of SASS, and instruction fetch was the kernel's first stall reason)
-  template <class T>
-  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) const;
+  template <class C, class T>
+  __device__ __forceinline__ void exclusive_scan(const C* in, T* out, int n) const;
 };
 
 // tiles of 32 consecutive elements (bank-conflict free), one shuffle scan per tile with a running carry.  (The first version
 // gave every lane a contiguous chunk: 8-way bank conflicts, 7 % of all stall samples of the kernel.)  Takes shared-window
 // addresses so that the out-of-line copy still uses LDS / STS.
-template <int OUT_BYTES>
+template <int IN_BYTES, int OUT_BYTES>
 __device__ __noinline__ void warp_exclusive_scan(unsigned in_s, unsigned out_s, int n) {
   const int lane = threadIdx.x & 31;
   int carry = 0;
@@ -134,7 +146,10 @@ __device__ __noinline__ void warp_exclusive_scan(unsigned in_s, unsigned out_s, 
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
     int v = 0;
-    if (i < n) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(in_s + 4u * (unsigned)i) : "memory");
+    if (i < n) {
+      if (IN_BYTES == 2) { short h; asm volatile("ld.shared.s16 %0, [%1];" : "=h"(h) : "r"(in_s + 2u * (unsigned)i) : "memory"); v = h; }
+      else asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(in_s + 4u * (unsigned)i) : "memory");
+    }
     int incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
@@ -151,11 +166,11 @@ __device__ __noinline__ void warp_exclusive_scan(unsigned in_s, unsigned out_s, 
   }
   __syncwarp();
 }
-template <class T>
-__device__ __forceinline__ void WarpEx::exclusive_scan(const int32_t* in, T* out, int n) const {
-  static_assert(sizeof(T) == 2 || sizeof(T) == 4, "index type");
+template <class C, class T>
+__device__ __forceinline__ void WarpEx::exclusive_scan(const C* in, T* out, int n) const {
+  static_assert((sizeof(T) == 2 || sizeof(T) == 4) && (sizeof(C) == 2 || sizeof(C) == 4), "index type");
   __syncwarp();
-  warp_exclusive_scan<(int)sizeof(T)>((unsigned)__cvta_generic_to_shared(in), (unsigned)__cvta_generic_to_shared(out), n);
+  warp_exclusive_scan<(int)sizeof(C), (int)sizeof(T)>((unsigned)__cvta_generic_to_shared(in), (unsigned)__cvta_generic_to_shared(out), n);
 }
 
 // ---- the CTA executor: one thread block per instance, workspace in GLOBAL memory (int32 ids), barrier = __syncthreads ----
@@ -213,6 +228,8 @@ struct CtaEx {
   __device__ __forceinline__ int ldg(const int32_t* p) const { return __ldg(p); }  // caller's arrays: read-only during the launch
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
+  __device__ __forceinline__ int atomic_add_idx(int32_t* p, int v) const { return atomicAdd(p, v); }
+  __device__ __forceinline__ void atomic_xor_idx(int32_t* p, int v) const { atomicXor(p, v); }
   template <class I>
   __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -236,8 +253,8 @@ struct CtaEx {
     return carry;
   }
   // tile-by-tile block scan with a running carry: coalesced, two barriers per tile of blockDim.x elements
-  template <class T>
-  __device__ __forceinline__ void exclusive_scan(const int32_t* in, T* out, int n) {
+  template <class C, class T>
+  __device__ __forceinline__ void exclusive_scan(const C* in, T* out, int n) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     sync();
     int carry = 0;
@@ -277,8 +294,10 @@ struct TcSink {
 };
 enum { CNT_DISPLAYED = 0, CNT_ITEMS, CNT_BRANCH_ITEMS, CNT_CHERRIES, CNT_RET, CNT_ARCS, CNT_PASSES, CNT_ERRORS, CNT_N };
 
-template <class I>
-__global__ void __launch_bounds__(640, 1) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
+// MAXT = launch bound = register budget: 640 threads -> 102 registers, 768 -> 85, 896 -> 73, 1024 -> 64.  The host picks the
+// smallest variant that holds the warps shared memory allows.
+template <class I, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
                                                         uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                         uint8_t* __restrict__ branched, int32_t* __restrict__ ticket,
                                                         unsigned long long* __restrict__ counters) {
@@ -471,6 +490,8 @@ extern "C" int pt_debug_profile(unsigned long long* out128) {
   return cudaMemcpyToSymbol(g_prof, z, sizeof(z)) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+static constexpr int kDefaultMaxWarps = 24;  // measured on config 2: 16 warps 8.5 ms, 20: 8.0, 24: 7.6, 28: 8.2 (instruction fetch, not latency, is the limit)
 
 struct pt_batch {
   int64_t B = 0;
@@ -687,14 +708,18 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   } else if (B > 0) {
     int wpc = 1, ctas_per_sm = 1;
     size_t smem = 0, ws_bytes = 0;
+    auto warp_kernel = tc_reduce_kernel<I, 640>;
     int cta_grid_cap = 0;
     if (!use_cta) {
-      // occupancy: as many warps per SM as shared memory (warp_bytes each) and the register file (launch bound 640 threads
-      // -> at most 102 registers/thread -> 20 warps) allow, in one CTA per SM
-      int warps_per_sm = (int)std::min<size_t>(20, ((size_t)dp.smem_optin) / warp_bytes);
+      // occupancy: as many warps per SM as shared memory allows (warp_bytes each), in one CTA per SM; the kernel variant
+      // (register budget) follows from the warp count
+      int max_warps = kDefaultMaxWarps;
+      if (const char* e = getenv("PT_TC_MAX_WARPS")) max_warps = std::max(1, std::min(32, atoi(e)));  // tuning aid
+      int warps_per_sm = (int)std::min<size_t>((size_t)max_warps, ((size_t)dp.smem_optin) / warp_bytes);
       wpc = std::max(warps_per_sm, 1);
       smem = (size_t)wpc * warp_bytes;
-      PT_CUDA(cudaFuncSetAttribute(tc_reduce_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      warp_kernel = wpc <= 20 ? tc_reduce_kernel<I, 640> : wpc <= 24 ? tc_reduce_kernel<I, 768> : wpc <= 28 ? tc_reduce_kernel<I, 896> : tc_reduce_kernel<I, 1024>;
+      PT_CUDA(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
       ws_bytes = (TcWork<int32_t>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL) + 255) & ~(size_t)255;
       size_t free_b = 0, total_b = 0;
@@ -759,7 +784,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
           tc_reduce_cta_kernel<<<grid, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits, stat, b->d_branched, ticket,
                                                     b->d_counters);
         else
-          tc_reduce_kernel<I><<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched, ticket,
+          warp_kernel<<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched, ticket,
                                                            b->d_counters);
         ++b->last_launches;
       }

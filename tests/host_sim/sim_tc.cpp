@@ -51,7 +51,9 @@ struct HostEx {
     for (int e = 0; e < m; ++e) if (at[e] >= 0) { at[k] = at[e]; ah[k] = ah[e]; ++k; }
     return k;
   }
-  template <class T> void exclusive_scan(const int32_t* in, T* out, int n) const { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (T)acc; acc += in[i]; } out[n] = (T)acc; }
+  template <class T> int atomic_add_idx(T* p, int v) const { const int o = *p; *p = (T)(o + v); return o; }
+  template <class T> void atomic_xor_idx(T* p, int v) const { *p = (T)(*p ^ v); }
+  template <class C, class T> void exclusive_scan(const C* in, T* out, int n) const { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (T)acc; acc += in[i]; } out[n] = (T)acc; }
 };
 
 struct Item { std::vector<int32_t> succ_off, succ_adj, hlabel, tparent, tlabel; int n, m, nt; };

@@ -58,7 +58,9 @@ struct GroupEx {
     sync();
     return k;
   }
-  template <class X> void exclusive_scan(const int32_t* in, X* out, int n) { sync(); if (t == 0) { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (X)acc; acc += in[i]; } out[n] = (X)acc; } sync(); }
+  template <class X> int atomic_add_idx(X* p, int v) const { return (int)__atomic_fetch_add(p, (X)v, __ATOMIC_SEQ_CST); }
+  template <class X> void atomic_xor_idx(X* p, int v) const { __atomic_fetch_xor(p, (X)v, __ATOMIC_SEQ_CST); }
+  template <class C, class X> void exclusive_scan(const C* in, X* out, int n) { sync(); if (t == 0) { int acc = 0; for (int i = 0; i < n; ++i) { out[i] = (X)acc; acc += in[i]; } out[n] = (X)acc; } sync(); }
 };
 
 struct Item { std::vector<int32_t> succ_off, succ_adj, hlabel, tparent, tlabel; int n, m, nt; };

@@ -233,10 +233,10 @@ def test_executors_agree_on_mid_size(pt):
 
 
 def test_instances_beyond_shared_memory(pt):
-    """n = 6 599 host nodes (l=3000, r=300) does not fit a CTA's shared memory: the global-memory executor takes over
+    """n = 8 799 host nodes (l=4000, r=400) does not fit a CTA's shared memory: the global-memory executor takes over
     automatically; positives are displayed by construction, a guest with a foreign label is not"""
     p = pt.Packer()
-    p.add_generated(24, 3000, 300, 99, 0)
+    p.add_generated(24, 4000, 400, 99, 0)
     a = p.arrays()
     gl = a["guest_label"]
     last = int(a["guest_node_off"][23])
