@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PT_GPU_ABI_VERSION 1
+#define PT_GPU_ABI_VERSION 2
 
 typedef enum pt_status {
   PT_OK = 0,
@@ -121,7 +121,10 @@ int pt_rmq_free(pt_rmq* h);
  *     the `tc` dispatch                               examples/tc.cpp:130-144
  * for B independent (host network, guest tree) instances at once.
  *
- * Flat layout (all int32 unless noted; instance i owns the slices given by the three offset tables):
+ * Flat layout (all int32 unless noted; instance i owns the slices given by the three offset tables).  With
+ * index_bytes = 2 the five data arrays (succ_off, succ_adj, both label arrays, guest_parent) hold int16_t instead
+ * (pass the pointers cast to const int32_t*): every instance then has fewer than 32 768 nodes, arcs and labels, and
+ * HOST input costs half the PCIe traffic -- the end-to-end path is bound by exactly that copy:
  *   host_node_off[B+1], host_arc_off[B+1], guest_node_off[B+1]   (int64 prefix sums of n_i, m_i, nt_i)
  *   host_succ_off  : sum(n_i + 1) entries; instance i starts at host_node_off[i] + i; values are LOCAL arc
  *                    positions 0..m_i  (the immutable CSR of utils/storage_adj_immutable.hpp:173-261)
@@ -159,6 +162,7 @@ typedef struct pt_batch_desc {
   const int32_t* guest_child_adj;  /* optional */
   /* per-batch maxima; 0 = let the library compute them (one extra pass + sync for DEVICE input) */
   int32_t max_host_nodes, max_host_arcs, max_guest_nodes, max_labels;
+  int32_t index_bytes;             /* 0 or 4: data arrays are int32_t; 2: they are int16_t (compact upload)   */
 } pt_batch_desc;
 
 /* per-instance status written next to the verdict bit */
@@ -257,6 +261,9 @@ int pt_packer_add_newick_text(pt_packer* p, const char* text, int64_t len, int n
 int pt_packer_add_generated(pt_packer* p, int64_t count, int32_t num_leaves, int32_t num_retis, uint64_t seed, int kind);
 /* fills `desc` with pointers into the packer's HOST buffers (valid until the next add / free) */
 int pt_packer_desc(pt_packer* p, pt_batch_desc* desc);
+/* the same batch with int16 data arrays (index_bytes = 2); PT_ERR_INVALID if some instance is too large for that.
+ * The arrays belong to the packer and stay valid until the next add_* / free. */
+int pt_packer_desc_compact(pt_packer* p, pt_batch_desc* desc);
 /* extended Newick text of instance i (host, then guest); two-call protocol on buffer lengths */
 int pt_packer_get_newick(pt_packer* p, int64_t i, char* host_buf, int64_t* host_len, char* guest_buf, int64_t* guest_len);
 int pt_packer_free(pt_packer* p);

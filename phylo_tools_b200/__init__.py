@@ -102,10 +102,15 @@ class Packer:
         _check(_L.pt_packer_desc(self._h, C.byref(d)), "pt_packer_desc")
         return d
 
-    def arrays(self):
-        """numpy views (copied) of the flat arrays, keyed like pt_batch_desc"""
-        d = self.desc()
+    def arrays(self, compact=False):
+        """numpy views (copied) of the flat arrays, keyed like pt_batch_desc; compact=True: int16 data arrays (index_bytes = 2)"""
+        if compact:
+            d = BatchDesc()
+            _check(_L.pt_packer_desc_compact(self._h, C.byref(d)), "pt_packer_desc_compact")
+        else:
+            d = self.desc()
         B = d.num_instances
+        it, nt = (C.c_int16, np.int16) if compact else (C.c_int32, np.int32)
 
         def view(ptr, count, ctype, dtype):
             if not ptr or count == 0:
@@ -116,9 +121,9 @@ class Packer:
         gn = view(d.guest_node_off, B + 1, C.c_int64, np.int64)
         NH, MH, NG = (int(hn[-1]), int(ha[-1]), int(gn[-1])) if B else (0, 0, 0)
         out = dict(num_instances=B, host_node_off=hn, host_arc_off=ha, guest_node_off=gn,
-                   host_succ_off=view(d.host_succ_off, NH + B, C.c_int32, np.int32), host_succ_adj=view(d.host_succ_adj, MH, C.c_int32, np.int32),
-                   host_label=view(d.host_label, NH, C.c_int32, np.int32), guest_parent=view(d.guest_parent, NG, C.c_int32, np.int32),
-                   guest_label=view(d.guest_label, NG, C.c_int32, np.int32),
+                   host_succ_off=view(d.host_succ_off, NH + B, it, nt), host_succ_adj=view(d.host_succ_adj, MH, it, nt),
+                   host_label=view(d.host_label, NH, it, nt), guest_parent=view(d.guest_parent, NG, it, nt),
+                   guest_label=view(d.guest_label, NG, it, nt), index_bytes=2 if compact else 4,
                    host_pred_off=view(d.host_pred_off, NH + B, C.c_int32, np.int32), host_pred_adj=view(d.host_pred_adj, MH, C.c_int32, np.int32),
                    guest_child_off=view(d.guest_child_off, NG + B, C.c_int32, np.int32), guest_child_adj=view(d.guest_child_adj, max(NG - B, 0), C.c_int32, np.int32),
                    max_host_nodes=d.max_host_nodes, max_host_arcs=d.max_host_arcs, max_guest_nodes=d.max_guest_nodes, max_labels=d.max_labels)
@@ -152,7 +157,7 @@ def make_desc(arrays, mem):
         setattr(d, k, _ptr(arrays[k]))
     for k in _OPT_KEYS:
         setattr(d, k, _ptr(arrays.get(k)) if arrays.get(k) is not None and (not hasattr(arrays[k], "__len__") or len(arrays[k])) else None)
-    for k in ("max_host_nodes", "max_host_arcs", "max_guest_nodes", "max_labels"):
+    for k in ("max_host_nodes", "max_host_arcs", "max_guest_nodes", "max_labels", "index_bytes"):
         setattr(d, k, int(arrays.get(k, 0)))
     return d
 

@@ -19,7 +19,8 @@ class BatchDesc(C.Structure):
                 ("host_succ_off", C.c_void_p), ("host_succ_adj", C.c_void_p), ("host_label", C.c_void_p),
                 ("guest_parent", C.c_void_p), ("guest_label", C.c_void_p),
                 ("host_pred_off", C.c_void_p), ("host_pred_adj", C.c_void_p), ("guest_child_off", C.c_void_p), ("guest_child_adj", C.c_void_p),
-                ("max_host_nodes", C.c_int32), ("max_host_arcs", C.c_int32), ("max_guest_nodes", C.c_int32), ("max_labels", C.c_int32)]
+                ("max_host_nodes", C.c_int32), ("max_host_arcs", C.c_int32), ("max_guest_nodes", C.c_int32), ("max_labels", C.c_int32),
+                ("index_bytes", C.c_int32)]
 
 
 class Counters(C.Structure):
@@ -78,6 +79,7 @@ def load():
         "pt_packer_add_newick_text": (C.c_int, [vp, C.c_char_p, C.c_int64, C.c_int, i64p]),
         "pt_packer_add_generated": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int]),
         "pt_packer_desc": (C.c_int, [vp, C.POINTER(BatchDesc)]),
+        "pt_packer_desc_compact": (C.c_int, [vp, C.POINTER(BatchDesc)]),
         "pt_packer_get_newick": (C.c_int, [vp, C.c_int64, C.c_char_p, i64p, C.c_char_p, i64p]),
         "pt_packer_free": (C.c_int, [vp]),
         "pt_gen_random_tree": (C.c_int, [C.c_int64, C.c_uint64, i32p]),
@@ -91,4 +93,4 @@ def load():
 EXPORTED = ["pt_last_error", "pt_abi_version", "pt_device_count", "pt_set_device", "pt_lca_build", "pt_lca_query", "pt_lca_get_info",
             "pt_lca_node_info", "pt_lca_free", "pt_tree_who_displays", "pt_net_bridges", "pt_rmq_build", "pt_rmq_query", "pt_rmq_free", "pt_get_limits", "pt_batch_create",
             "pt_batch_contain", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_parse_newick", "pt_packer_create",
-            "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree"]
+            "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree"]

@@ -52,26 +52,18 @@ static long g_sim_csr_calls, g_sim_live_nodes, g_sim_nodes, g_sim_live_arcs;
 // parallel-for over [0,n): i_ is the executor's slot, i the (possibly permuted) element
 #define PT_FOR(i, n) \
   PT_NOUNROLL for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
-// the same for the passes that read the caller's arrays from global memory (ex.ldg): four iterations in flight, so that
-// four load latencies overlap instead of one load -> store round trip per iteration
-#if defined(__CUDA_ARCH__)
-#define PT_FOR_LD(i, n) \
-  _Pragma("unroll 4") for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
-#else
-#define PT_FOR_LD(i, n) PT_FOR(i, n)
-#endif
-
 enum TcCode : int { TC_NOT = 0, TC_DISPLAYED = 1, TC_BRANCH = 2, TC_ERROR = 3 };
 enum TcStatus : int { TCS_OK = 0, TCS_MULTILABEL = 1, TCS_BAD_GRAPH = 2, TCS_TOO_LARGE = 3, TCS_POOL_OVERFLOW = 4 };
 
 // one instance in the flat layout of include/pt_gpu.h (pointers already offset to the instance)
 struct TcInst {
   int n, m, nt;
-  const int32_t* succ_off;  // n+1, local
-  const int32_t* succ_adj;  // m
-  const int32_t* hlabel;    // n
-  const int32_t* tparent;   // nt
-  const int32_t* tlabel;    // nt
+  const void* succ_off;  // n+1, local
+  const void* succ_adj;  // m
+  const void* hlabel;    // n
+  const void* tparent;   // nt
+  const void* tlabel;    // nt
+  int idx16;             // the five arrays hold int16_t (pt_batch_desc.index_bytes = 2), else int32_t
 };
 // where a branch child is written (same layout, caller provides capacity n+1 / m / n / nt / nt)
 struct TcEmit {
@@ -180,37 +172,22 @@ struct TcSolver {
     if (n > w.capN || m > w.capM || nt > w.capNT || n < 0 || m < 0 || nt < 0) return TCS_TOO_LARGE;
     if (ex.tid() == 0) { PT_NOUNROLL for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
     ex.sync();
-    // structure checks on the CSR offsets (branch-free bodies: the loads of consecutive iterations overlap)
-    int bad = 0, big = 0, maxlab = -1;
-    PT_FOR_LD(v, n + 1) {
-      const int o = ex.ldg(&in.succ_off[v]);
-      bad |= (o < 0) | (o > m) | (v == 0 && o != 0) | (v == n && o != m);
-      w.ooff[v] = (I)(o < 0 ? 0 : (o > m ? m : o));
-    }
-    PT_FOR_LD(v, n) {
-      const int l = ex.ldg(&in.hlabel[v]);
-      w.hlab[v] = (I)l;
-      big |= (l >= w.capL) | (l < -1);
-      maxlab = l > maxlab ? l : maxlab;
-    }
-    PT_FOR_LD(e, m) {
-      const int h = ex.ldg(&in.succ_adj[e]);
-      bad |= (h < 0) | (h >= n);
-      w.ah[e] = (I)h;
-    }
-    PT_FOR_LD(t, nt) {
-      const int p = ex.ldg(&in.tparent[t]), l = ex.ldg(&in.tlabel[t]);
-      bad |= (p < -1) | (p >= nt) | (p == t);
-      big |= (l >= w.capL) | (l < -1);
-      maxlab = l > maxlab ? l : maxlab;
-      w.tpar[t] = (I)p; w.tlab[t] = (I)l; w.tdeg[t] = (I)0;
-    }
+    // ex.load_array copies one caller array (int32 or int16, several loads in flight) into the workspace, clamped to
+    // [lo, hi]; it reports values outside that range and the maximum it saw
+    int bad = 0, big = 0, maxlab = -1, unused = -1;
+    bad |= ex.load_array(in.succ_off, in.idx16, w.ooff, n + 1, 0, m, unused);
+    big |= ex.load_array(in.hlabel, in.idx16, w.hlab, n, -1, w.capL - 1, maxlab);
+    bad |= ex.load_array(in.succ_adj, in.idx16, w.ah, m, 0, n - 1, unused);
+    bad |= ex.load_array(in.tparent, in.idx16, w.tpar, nt, -1, nt - 1, unused);   // (p == t is caught by the cycle check)
+    big |= ex.load_array(in.tlabel, in.idx16, w.tlab, nt, -1, w.capL - 1, maxlab);
     if (bad) w.sc[F_STATUS] = TCS_BAD_GRAPH; else if (big) w.sc[F_TMP2] = 1;
     ex.sync();
     PT_FOR(v, n) {
       if (w.ooff[v + 1] < w.ooff[v]) w.sc[F_STATUS] = TCS_BAD_GRAPH;
       PT_NOUNROLL for (int e = w.ooff[v]; e < w.ooff[v + 1]; ++e) w.at[e] = (I)v;
     }
+    PT_FOR(t, nt) { w.tdeg[t] = (I)0; }
+    if (ex.tid() == 0 && (w.ooff[0] != 0 || w.ooff[n] != m)) w.sc[F_STATUS] = TCS_BAD_GRAPH;
     ex.atomic_max(&w.sc[F_NLAB], maxlab + 1);
     if (take_flag(F_STATUS)) return TCS_BAD_GRAPH;
     if (take_flag(F_TMP2)) return TCS_TOO_LARGE;

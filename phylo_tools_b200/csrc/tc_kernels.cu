@@ -94,7 +94,8 @@ struct WarpEx {
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
   __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
   __device__ __forceinline__ int atomic_xor(int32_t* p, int v) const { return atomicXor(p, v); }
-  __device__ __forceinline__ int ldg(const int32_t* p) const { return __ldg(p); }  // caller's arrays: read-only during the launch
+  template <class T>
+  __device__ __forceinline__ int load_array(const void* src, int src16, T* dst, int n, int lo, int hi, int& vmax) const;
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
     return (int)(int16_t)atomicCAS((unsigned short*)p, (unsigned short)(int16_t)c, (unsigned short)(int16_t)v);
@@ -166,6 +167,34 @@ __device__ __noinline__ void warp_exclusive_scan(unsigned in_s, unsigned out_s, 
   }
   __syncwarp();
 }
+// one out-of-line copy of the input loop for all five arrays: four loads in flight per lane, so that four global-memory
+// latencies overlap instead of one load -> store round trip per element
+template <int DST_BYTES, class SRC>
+__device__ __forceinline__ void warp_load_loop(const SRC* __restrict__ src, unsigned dst_s, int n, int lo, int hi, int& flag, int& vmax) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = lane; i < n; i += 32) {
+    int v = (int)__ldg(src + i);
+    flag |= (v < lo) | (v > hi);
+    vmax = max(vmax, v);
+    v = min(max(v, lo), hi);
+    if (DST_BYTES == 2) asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst_s + 2u * (unsigned)i), "h"((short)v) : "memory");
+    else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst_s + 4u * (unsigned)i), "r"(v) : "memory");
+  }
+}
+template <int DST_BYTES>
+__device__ __noinline__ int2 warp_load_array(const void* src, int src16, unsigned dst_s, int n, int lo, int hi, int vmax) {
+  int flag = 0;
+  if (src16) warp_load_loop<DST_BYTES>(static_cast<const short*>(src), dst_s, n, lo, hi, flag, vmax);
+  else warp_load_loop<DST_BYTES>(static_cast<const int*>(src), dst_s, n, lo, hi, flag, vmax);
+  return make_int2(flag, vmax);
+}
+template <class T>
+__device__ __forceinline__ int WarpEx::load_array(const void* src, int src16, T* dst, int n, int lo, int hi, int& vmax) const {
+  const int2 r = warp_load_array<(int)sizeof(T)>(src, src16, (unsigned)__cvta_generic_to_shared(dst), n, lo, hi, vmax);
+  vmax = r.y;
+  return r.x;
+}
 template <class C, class T>
 __device__ __forceinline__ void WarpEx::exclusive_scan(const C* in, T* out, int n) const {
   static_assert((sizeof(T) == 2 || sizeof(T) == 4) && (sizeof(C) == 2 || sizeof(C) == 4), "index type");
@@ -225,7 +254,18 @@ struct CtaEx {
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
   __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
   __device__ __forceinline__ int atomic_xor(int32_t* p, int v) const { return atomicXor(p, v); }
-  __device__ __forceinline__ int ldg(const int32_t* p) const { return __ldg(p); }  // caller's arrays: read-only during the launch
+  // caller's arrays are read-only during the launch (ld.global.nc)
+  template <class T>
+  __device__ __forceinline__ int load_array(const void* src, int src16, T* dst, int n, int lo, int hi, int& vmax) const {
+    int flag = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int v = src16 ? (int)__ldg(static_cast<const short*>(src) + i) : __ldg(static_cast<const int*>(src) + i);
+      flag |= (v < lo) | (v > hi);
+      vmax = max(vmax, v);
+      dst[i] = (T)min(max(v, lo), hi);
+    }
+    return flag;
+  }
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_add_idx(int32_t* p, int v) const { return atomicAdd(p, v); }
@@ -283,7 +323,8 @@ struct TcSource {
   const int32_t* count_ptr; // pool mode: device counter (clamped to capacity)
   int is_pool, capacity;
   const int64_t *hnode_off, *harc_off, *gnode_off;
-  const int32_t *succ_off, *succ_adj, *hlabel, *tparent, *tlabel;
+  const void *succ_off, *succ_adj, *hlabel, *tparent, *tlabel;
+  int idx16;                     // batch mode: the five arrays hold int16_t; the pool is always int32_t
   const int32_t *dims, *origin;  // pool mode
   int sN1, sM, sN, sNT;          // pool strides (elements)
 };
@@ -321,16 +362,19 @@ __global__ void __launch_bounds__(MAXT, 1) tc_reduce_kernel(TcSource src, TcSink
       if (lane == 0) done = (int)((*(volatile uint32_t*)&result_bits[origin >> 5] >> (origin & 31)) & 1u);
       if (__shfl_sync(0xffffffffu, done, 0)) continue;  // a sibling branch already displayed it
       in.n = src.dims[4 * item]; in.m = src.dims[4 * item + 1]; in.nt = src.dims[4 * item + 2];
-      in.succ_off = src.succ_off + (size_t)item * src.sN1; in.succ_adj = src.succ_adj + (size_t)item * src.sM;
-      in.hlabel = src.hlabel + (size_t)item * src.sN; in.tparent = src.tparent + (size_t)item * src.sNT; in.tlabel = src.tlabel + (size_t)item * src.sNT;
+      in.succ_off = static_cast<const int32_t*>(src.succ_off) + (size_t)item * src.sN1; in.succ_adj = static_cast<const int32_t*>(src.succ_adj) + (size_t)item * src.sM;
+      in.hlabel = static_cast<const int32_t*>(src.hlabel) + (size_t)item * src.sN; in.tparent = static_cast<const int32_t*>(src.tparent) + (size_t)item * src.sNT;
+      in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT; in.idx16 = 0;
     } else {
       origin = item;
       const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
       const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
       in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
       if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
-      in.succ_off = src.succ_off + hb + item; in.succ_adj = src.succ_adj + ab; in.hlabel = src.hlabel + hb;
-      in.tparent = src.tparent + gb; in.tlabel = src.tlabel + gb;
+      const int sh = src.idx16 ? 1 : 2;  // log2 of the element size
+      in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + item) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
+      in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
+      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh); in.idx16 = src.idx16;
     }
     TcSolver<WarpEx, I> sv(ex, w);
     int st = 0, x = -1;
@@ -405,16 +449,19 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
       __syncthreads();
       if (s_red[37]) continue;
       in.n = src.dims[4 * item]; in.m = src.dims[4 * item + 1]; in.nt = src.dims[4 * item + 2];
-      in.succ_off = src.succ_off + (size_t)item * src.sN1; in.succ_adj = src.succ_adj + (size_t)item * src.sM;
-      in.hlabel = src.hlabel + (size_t)item * src.sN; in.tparent = src.tparent + (size_t)item * src.sNT; in.tlabel = src.tlabel + (size_t)item * src.sNT;
+      in.succ_off = static_cast<const int32_t*>(src.succ_off) + (size_t)item * src.sN1; in.succ_adj = static_cast<const int32_t*>(src.succ_adj) + (size_t)item * src.sM;
+      in.hlabel = static_cast<const int32_t*>(src.hlabel) + (size_t)item * src.sN; in.tparent = static_cast<const int32_t*>(src.tparent) + (size_t)item * src.sNT;
+      in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT; in.idx16 = 0;
     } else {
       origin = item;
       const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
       const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
       in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
       if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
-      in.succ_off = src.succ_off + hb + item; in.succ_adj = src.succ_adj + ab; in.hlabel = src.hlabel + hb;
-      in.tparent = src.tparent + gb; in.tlabel = src.tlabel + gb;
+      const int sh = src.idx16 ? 1 : 2;  // log2 of the element size
+      in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + item) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
+      in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
+      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh); in.idx16 = src.idx16;
     }
     TcSolver<CtaEx, I> sv(ex, w);
     int st = 0, x = -1;
@@ -464,14 +511,14 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
 
 // per-batch maxima of n, m, nt and label id (for DEVICE input without hints)
 __global__ void tc_maxima_kernel(int64_t B, const int64_t* hnode_off, const int64_t* harc_off, const int64_t* gnode_off,
-                                 const int32_t* hlabel, const int32_t* tlabel, int32_t* out4) {
+                                 const void* hlabel, const void* tlabel, int idx16, int32_t* out4) {
   int mn = 0, mm = 0, mt = 0, ml = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
     mn = max(mn, (int)(hnode_off[i + 1] - hnode_off[i])); mm = max(mm, (int)(harc_off[i + 1] - harc_off[i])); mt = max(mt, (int)(gnode_off[i + 1] - gnode_off[i]));
   }
   const int64_t NH = hnode_off[B], NG = gnode_off[B];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NH; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, hlabel[i] + 1);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NG; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, tlabel[i] + 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NH; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, (idx16 ? (int)static_cast<const short*>(hlabel)[i] : static_cast<const int*>(hlabel)[i]) + 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NG; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, (idx16 ? (int)static_cast<const short*>(tlabel)[i] : static_cast<const int*>(tlabel)[i]) + 1);
   for (int d = 16; d; d >>= 1) {
     mn = max(mn, __shfl_xor_sync(0xffffffffu, mn, d)); mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, d));
     mt = max(mt, __shfl_xor_sync(0xffffffffu, mt, d)); ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, d));
@@ -497,7 +544,8 @@ struct pt_batch {
   int64_t B = 0;
   bool owns_input = false;
   int64_t *d_hnode_off = nullptr, *d_harc_off = nullptr, *d_gnode_off = nullptr;
-  int32_t *d_succ_off = nullptr, *d_succ_adj = nullptr, *d_hlabel = nullptr, *d_tparent = nullptr, *d_tlabel = nullptr;
+  void *d_succ_off = nullptr, *d_succ_adj = nullptr, *d_hlabel = nullptr, *d_tparent = nullptr, *d_tlabel = nullptr;
+  int idx16 = 0;  // the five arrays above hold int16_t
   int32_t maxN = 0, maxM = 0, maxNT = 0, maxL = 0;
   // results + scratch
   uint32_t* d_bits = nullptr; uint8_t* d_status = nullptr; uint8_t* d_branched = nullptr;
@@ -509,7 +557,7 @@ struct pt_batch {
   unsigned char* d_ws = nullptr; size_t ws_cap = 0;  // global-memory workspaces of the CTA executor
   // HOST input is uploaded in chunks of instances on a private copy stream; round 0 launches one kernel per chunk as soon as
   // its bytes have landed, so the upload overlaps the solve (end-to-end path)
-  static constexpr int kMaxChunks = 8;
+  static constexpr int kMaxChunks = 32;
   cudaStream_t copy_stream = nullptr;
   int nchunks = 1; int64_t chunk_end[kMaxChunks] = {}; cudaEvent_t chunk_ev[kMaxChunks] = {};
   int64_t last_launches = 0;
@@ -586,11 +634,15 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   if (!d->host_node_off || !d->host_arc_off || !d->guest_node_off || !d->host_succ_off || !d->host_label || !d->guest_parent || !d->guest_label ||
       (!d->host_succ_adj && d->num_instances > 0))
     return set_error(PT_ERR_INVALID, "pt_batch_create: a required array is null");
+  if (d->index_bytes != 0 && d->index_bytes != 2 && d->index_bytes != 4) return set_error(PT_ERR_INVALID, "pt_batch_create: index_bytes must be 0, 2 or 4");
   if (int rc = require_device()) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   pt_batch* b = new (std::nothrow) pt_batch();
   if (!b) return set_error(PT_ERR_NOMEM, "out of host memory");
   const int64_t B = b->B = d->num_instances;
+  b->idx16 = d->index_bytes == 2;
+  const size_t esz = b->idx16 ? 2 : 4;
+  auto elem = [&](const int32_t* base, int64_t i) { return b->idx16 ? (int32_t) reinterpret_cast<const int16_t*>(base)[i] : base[i]; };
   b->used_stream = s; b->used_stream_valid = true;
   int rc = PT_OK;
   auto fail = [&](int code) { batch_release(b); return code; };
@@ -610,8 +662,8 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
         b->maxNT = std::max<int32_t>(b->maxNT, (int32_t)std::min<int64_t>(d->guest_node_off[i + 1] - d->guest_node_off[i], INT32_MAX));
       }
       int32_t ml = 0;
-      for (int64_t i = 0; i < NH; ++i) ml = std::max(ml, d->host_label[i] + 1);
-      for (int64_t i = 0; i < NG; ++i) ml = std::max(ml, d->guest_label[i] + 1);
+      for (int64_t i = 0; i < NH; ++i) ml = std::max(ml, elem(d->host_label, i) + 1);
+      for (int64_t i = 0; i < NG; ++i) ml = std::max(ml, elem(d->guest_label, i) + 1);
       b->maxL = std::max(b->maxL, ml);
     }
     b->owns_input = true;
@@ -619,21 +671,25 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
     if ((rc = upload(&b->d_hnode_off, d->host_node_off, B + 1, s, &b->h2d_bytes)) || (rc = upload(&b->d_harc_off, d->host_arc_off, B + 1, s, &b->h2d_bytes)) ||
         (rc = upload(&b->d_gnode_off, d->guest_node_off, B + 1, s, &b->h2d_bytes)))
       return fail(rc);
-    if ((rc = dev_alloc((void**)&b->d_succ_off, (size_t)std::max<int64_t>(NH + B, 1) * 4)) || (rc = dev_alloc((void**)&b->d_succ_adj, (size_t)std::max<int64_t>(MH, 1) * 4)) ||
-        (rc = dev_alloc((void**)&b->d_hlabel, (size_t)std::max<int64_t>(NH, 1) * 4)) || (rc = dev_alloc((void**)&b->d_tparent, (size_t)std::max<int64_t>(NG, 1) * 4)) ||
-        (rc = dev_alloc((void**)&b->d_tlabel, (size_t)std::max<int64_t>(NG, 1) * 4)))
+    if ((rc = dev_alloc(&b->d_succ_off, (size_t)std::max<int64_t>(NH + B, 1) * esz)) || (rc = dev_alloc(&b->d_succ_adj, (size_t)std::max<int64_t>(MH, 1) * esz)) ||
+        (rc = dev_alloc(&b->d_hlabel, (size_t)std::max<int64_t>(NH, 1) * esz)) || (rc = dev_alloc(&b->d_tparent, (size_t)std::max<int64_t>(NG, 1) * esz)) ||
+        (rc = dev_alloc(&b->d_tlabel, (size_t)std::max<int64_t>(NG, 1) * esz)))
       return fail(rc);
-    b->nchunks = B >= 8192 ? pt_batch::kMaxChunks : 1;
+    b->nchunks = B >= 8192 ? 6 : 1;
+    if (const char* e = getenv("PT_TC_CHUNKS")) b->nchunks = std::max(1, std::min((int)pt_batch::kMaxChunks, atoi(e)));  // tuning aid
     if (b->nchunks > 1 && cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); b->nchunks = 1; }
     cudaStream_t cs = b->nchunks > 1 ? b->copy_stream : s;
     for (int c = 0; c < b->nchunks; ++c) {
-      const int64_t i0 = B * c / b->nchunks / 32 * 32, i1 = (c + 1 == b->nchunks) ? B : B * (c + 1) / b->nchunks / 32 * 32;
+      // geometric chunks (B/32, B/16, ... B/2, B with six of them): the solve is slower than the upload, so it only ever waits
+      // for the FIRST chunk -- keep that one small and the number of launches low
+      auto chunk_bound = [&](int k) { return k >= b->nchunks ? B : (k <= 0 ? (int64_t)0 : (B >> (b->nchunks - k)) / 32 * 32); };
+      const int64_t i0 = chunk_bound(c), i1 = chunk_bound(c + 1);
       b->chunk_end[c] = i1;
       const int64_t h0 = d->host_node_off[i0], h1 = d->host_node_off[i1], a0 = d->host_arc_off[i0], a1 = d->host_arc_off[i1], g0 = d->guest_node_off[i0], g1 = d->guest_node_off[i1];
-      auto cp = [&](int32_t* dst, const int32_t* src, int64_t from, int64_t to) -> cudaError_t {
+      auto cp = [&](void* dst, const void* src, int64_t from, int64_t to) -> cudaError_t {
         if (to <= from) return cudaSuccess;
-        b->h2d_bytes += (to - from) * 4;
-        return cudaMemcpyAsync(dst + from, src + from, (size_t)(to - from) * 4, cudaMemcpyHostToDevice, cs);
+        b->h2d_bytes += (to - from) * (int64_t)esz;
+        return cudaMemcpyAsync(static_cast<char*>(dst) + from * esz, static_cast<const char*>(src) + from * esz, (size_t)(to - from) * esz, cudaMemcpyHostToDevice, cs);
       };
       cudaError_t e = cp(b->d_succ_off, d->host_succ_off, h0 + i0, h1 + i1);
       if (e == cudaSuccess) e = cp(b->d_succ_adj, d->host_succ_adj, a0, a1);
@@ -645,13 +701,13 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
     }
   } else {
     b->d_hnode_off = (int64_t*)d->host_node_off; b->d_harc_off = (int64_t*)d->host_arc_off; b->d_gnode_off = (int64_t*)d->guest_node_off;
-    b->d_succ_off = (int32_t*)d->host_succ_off; b->d_succ_adj = (int32_t*)d->host_succ_adj; b->d_hlabel = (int32_t*)d->host_label;
-    b->d_tparent = (int32_t*)d->guest_parent; b->d_tlabel = (int32_t*)d->guest_label;
+    b->d_succ_off = (void*)d->host_succ_off; b->d_succ_adj = (void*)d->host_succ_adj; b->d_hlabel = (void*)d->host_label;
+    b->d_tparent = (void*)d->guest_parent; b->d_tlabel = (void*)d->guest_label;
     if (need_max) {
       int32_t* d4 = nullptr; int32_t h4[4] = {0, 0, 0, 0};
       if (cudaMalloc((void**)&d4, 16) != cudaSuccess) return fail(set_error(PT_ERR_NOMEM, "cudaMalloc failed"));
       cudaMemsetAsync(d4, 0, 16, s);
-      tc_maxima_kernel<<<296, 256, 0, s>>>(B, b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_hlabel, b->d_tlabel, d4);
+      tc_maxima_kernel<<<296, 256, 0, s>>>(B, b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_hlabel, b->d_tlabel, b->idx16, d4);
       cudaError_t e = cudaMemcpyAsync(h4, d4, 16, cudaMemcpyDeviceToHost, s);
       if (e == cudaSuccess) e = cudaStreamSynchronize(s);
       cudaFree(d4);
@@ -663,7 +719,7 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   b->maxN = std::max(b->maxN, 1); b->maxNT = std::max(b->maxNT, 1); b->maxL = std::max(b->maxL, 1);
   const size_t words = (size_t)((B + 31) / 32) + 1;
   if ((rc = dev_alloc((void**)&b->d_bits, words * 4)) || (rc = dev_alloc((void**)&b->d_status, (size_t)B + 1)) ||
-      (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 64)) ||
+      (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 256)) ||
       (rc = dev_alloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long))))
     return fail(rc);
   *out = b;
@@ -695,7 +751,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   PT_CUDA(cudaMemsetAsync(stat, 0, (size_t)B, s));
   PT_CUDA(cudaMemsetAsync(b->d_branched, 0, (size_t)B, s));
   PT_CUDA(cudaMemsetAsync(b->d_counters, 0, CNT_N * sizeof(unsigned long long), s));
-  PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 64, s));
+  PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 256, s));
   uint64_t rounds = 0;
   // two executors over the same solver: warps with the instance in shared memory (int16 ids), or one CTA per instance with
   // the workspace in global memory (int32 ids) when an instance does not fit one CTA's shared memory
@@ -754,7 +810,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     const int max_rounds = opt && opt->max_rounds > 0 ? opt->max_rounds : 64;
     TcSource src{};
     src.count = B; src.is_pool = 0; src.hnode_off = b->d_hnode_off; src.harc_off = b->d_harc_off; src.gnode_off = b->d_gnode_off;
-    src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel;
+    src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel; src.idx16 = b->idx16;
     int64_t items = B;
     for (int round = 0; round < max_rounds && items > 0; ++round) {
       const int k = round & 1;
@@ -799,7 +855,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       // next round reads the pool just written; reset the ticket and the other pool's counter
       TcSink just = sink;
       src = TcSource{};
-      src.is_pool = 1; src.count_ptr = just.count; src.capacity = cap; src.succ_off = just.succ_off; src.succ_adj = just.succ_adj; src.hlabel = just.hlabel;
+      src.is_pool = 1; src.idx16 = 0; src.count_ptr = just.count; src.capacity = cap; src.succ_off = just.succ_off; src.succ_adj = just.succ_adj; src.hlabel = just.hlabel;
       src.tparent = just.tparent; src.tlabel = just.tlabel; src.dims = just.dims; src.origin = just.origin; src.sN1 = sN1; src.sM = sM; src.sN = sN; src.sNT = sNT;
       PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 4, s));
       PT_CUDA(cudaMemsetAsync(b->d_ticket + 1 + (k ^ 1), 0, 4, s));

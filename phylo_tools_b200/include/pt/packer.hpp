@@ -100,6 +100,23 @@ class BatchPacker {
     return d;
   }
 
+  // the same batch with int16 data arrays (pt_batch_desc.index_bytes = 2): half the bytes to upload
+  bool compact_ok() const { return max_host_nodes < 32768 && max_host_arcs < 32768 && max_guest_nodes < 32768 && max_labels < 32768; }
+  pt_batch_desc desc_compact() {
+    if (!compact_ok()) throw std::logic_error("an instance is too large for 16-bit ids");
+    auto narrow = [](const std::vector<int32_t>& a, std::vector<int16_t>& b) { b.resize(a.size()); for (size_t i = 0; i < a.size(); ++i) b[i] = (int16_t)a[i]; };
+    narrow(host_succ_off, c_succ_off); narrow(host_succ_adj, c_succ_adj); narrow(host_label, c_host_label);
+    narrow(guest_parent, c_guest_parent); narrow(guest_label, c_guest_label);
+    pt_batch_desc d = desc();
+    d.host_succ_off = reinterpret_cast<const int32_t*>(c_succ_off.data()); d.host_succ_adj = reinterpret_cast<const int32_t*>(c_succ_adj.data());
+    d.host_label = reinterpret_cast<const int32_t*>(c_host_label.data()); d.guest_parent = reinterpret_cast<const int32_t*>(c_guest_parent.data());
+    d.guest_label = reinterpret_cast<const int32_t*>(c_guest_label.data());
+    d.host_pred_off = d.host_pred_adj = d.guest_child_off = d.guest_child_adj = nullptr;
+    d.index_bytes = 2;
+    return d;
+  }
+  std::vector<int16_t> c_succ_off, c_succ_adj, c_host_label, c_guest_parent, c_guest_label;
+
   std::vector<std::vector<std::string>> dict_names;  // per instance: label id -> string
 
   // extended Newick (host, guest) of instance i, rebuilt from the flat arrays

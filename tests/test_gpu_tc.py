@@ -252,6 +252,41 @@ def test_instances_beyond_shared_memory(pt):
         assert (pt.Batch(a).contain(path=1)[1] == 0).all()   # forcing the shared-memory path reports PT_INST_TOO_LARGE
 
 
+def test_compact_int16_input_matches_int32(pt, gold_tc):
+    """pt_batch_desc.index_bytes = 2 (half the upload): same verdicts and statuses as the int32 layout, on both executors and
+    for HOST and DEVICE input; bad ids are still caught"""
+    import torch
+    items = gold_tc["items"]
+    p = pt.Packer()
+    for it in items:
+        p.add_newick(it["host"], it["guest"])
+    p.add_generated(300, 100, 20, 4242, 0); p.add_generated(300, 100, 20, 5252, 1); p.add_generated(100, 40, 8, 6262, 2)
+    a32, a16 = p.arrays(), p.arrays(compact=True)
+    b32, b16 = pt.Batch(a32), pt.Batch(a16)
+    assert b16.h2d_bytes() < 0.55 * b32.h2d_bytes()
+    v32, s32, _ = b32.contain()
+    v16, s16, _ = b16.contain()
+    v16c, s16c, _ = b16.contain(path=2)
+    b32.free(); b16.free()
+    assert (s32 == 0).all() and (s16 == 0).all() and (s16c == 0).all()
+    assert (v32 == v16).all() and (v32 == v16c).all()
+    assert [int(x) for x in v16[:len(items)]] == [it["truth"] for it in items]
+    dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in a16.items()}
+    dev["max_host_nodes"] = dev["max_host_arcs"] = dev["max_guest_nodes"] = dev["max_labels"] = 0   # let the library find the maxima
+    bd = pt.Batch(dev)
+    vd, sd, _ = bd.contain()
+    bd.free()
+    assert (sd == 0).all() and (vd == v32).all()
+    bad = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in a16.items()}
+    bad["host_succ_adj"][int(bad["host_arc_off"][5])] = 32000      # a child id far beyond n in instance 5
+    bad["guest_parent"][int(bad["guest_node_off"][7]) + 1] = -7    # and a parent id below -1 in instance 7
+    bb = pt.Batch(bad)
+    vb, sb, _ = bb.contain()
+    bb.free()
+    assert sb[5] == 2 and sb[7] == 2 and (np.delete(sb, [5, 7]) == 0).all()
+    assert (np.delete(vb, [5, 7]) == np.delete(v32, [5, 7])).all()
+
+
 def test_edge_cases(pt, oracle):
     """empty batch, one-node trees, one and two labels, unlabelled hosts, ragged batch (tiny next to large instances)"""
     b = pt.Batch(dict(num_instances=0, host_node_off=np.zeros(1, np.int64), host_arc_off=np.zeros(1, np.int64), guest_node_off=np.zeros(1, np.int64),

@@ -17,7 +17,7 @@ def test_exports_every_declared_symbol(pt):
     lib = C.CDLL(os.path.join(ROOT, "phylo_tools_b200", "libptgpu.so"))
     for name in declared:
         assert hasattr(lib, name), name
-    assert pt.lib().pt_abi_version() == 1
+    assert pt.lib().pt_abi_version() == 2
 
 
 def test_cpp_newick_reader_matches_reference(pt, gold_newick):
@@ -34,6 +34,22 @@ def test_malformed_newick(pt):
             pt.parse_newick(bad)
     # like the reference, the reader stops once the root's subtree is complete: an unmatched '(' on the left is ignored
     assert pt.parse_newick("((a,b),(c,d);") == (3, [(0, 1), (0, 2)], {1: "d", 2: "c"})
+
+
+def test_packer_compact_arrays(pt):
+    """index_bytes = 2: the same batch with int16 data arrays; refused when an instance needs wider ids"""
+    p = pt.Packer()
+    p.add_generated(20, 30, 5, 77, 0)
+    a, c = p.arrays(), p.arrays(compact=True)
+    assert c["index_bytes"] == 2 and a["index_bytes"] == 4
+    for k in ("host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"):
+        assert c[k].dtype == np.int16 and (c[k].astype(np.int32) == a[k]).all()
+    for k in ("host_node_off", "host_arc_off", "guest_node_off"):
+        assert (c[k] == a[k]).all()
+    big = pt.Packer()
+    big.add_generated(1, 20000, 10, 5, 0)   # 40 019 host nodes
+    with pytest.raises(pt.PtError):
+        big.arrays(compact=True)
 
 
 def test_packer_layout_and_roundtrip(pt, oracle):
