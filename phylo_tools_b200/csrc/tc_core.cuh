@@ -52,6 +52,16 @@ static long g_sim_csr_calls, g_sim_live_nodes, g_sim_nodes, g_sim_live_arcs;
 // parallel-for over [0,n): i_ is the executor's slot, i the (possibly permuted) element
 #define PT_FOR(i, n) \
   PT_NOUNROLL for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
+// the passes that read the caller's arrays from global memory (ex.ldg) keep four iterations in flight, so that four load
+// latencies overlap instead of one load -> store round trip per iteration.  (An out-of-line helper shared by the five
+// arrays was tried: 72 instead of 75 KB of SASS, but 6 % slower end to end.)
+#if defined(__CUDA_ARCH__)
+#define PT_FOR_LD(i, n) \
+  _Pragma("unroll 4") for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
+#else
+#define PT_FOR_LD(i, n) PT_FOR(i, n)
+#endif
+
 enum TcCode : int { TC_NOT = 0, TC_DISPLAYED = 1, TC_BRANCH = 2, TC_ERROR = 3 };
 enum TcStatus : int { TCS_OK = 0, TCS_MULTILABEL = 1, TCS_BAD_GRAPH = 2, TCS_TOO_LARGE = 3, TCS_POOL_OVERFLOW = 4 };
 
@@ -63,7 +73,7 @@ struct TcInst {
   const void* hlabel;    // n
   const void* tparent;   // nt
   const void* tlabel;    // nt
-  int idx16;             // the five arrays hold int16_t (pt_batch_desc.index_bytes = 2), else int32_t
+                         // element type S of the five arrays: int32_t, or int16_t for pt_batch_desc.index_bytes = 2
 };
 // where a branch child is written (same layout, caller provides capacity n+1 / m / n / nt / nt)
 struct TcEmit {
@@ -166,28 +176,47 @@ struct TcSolver {
 
   // ---- load + validate ---------------------------------------------------------------------------------
   // returns TCS_* ; sets up arcs, labels, guest arrays.  Leaves w.sc[F_FAIL]=1 if a guest label is missing in the host.
+  template <class S>
   PT_NI int load(const TcInst& in) {
     ex.phase = 1;
     n = in.n; m = in.m; nt = in.nt;
     if (n > w.capN || m > w.capM || nt > w.capNT || n < 0 || m < 0 || nt < 0) return TCS_TOO_LARGE;
     if (ex.tid() == 0) { PT_NOUNROLL for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
     ex.sync();
-    // ex.load_array copies one caller array (int32 or int16, several loads in flight) into the workspace, clamped to
-    // [lo, hi]; it reports values outside that range and the maximum it saw
-    int bad = 0, big = 0, maxlab = -1, unused = -1;
-    bad |= ex.load_array(in.succ_off, in.idx16, w.ooff, n + 1, 0, m, unused);
-    big |= ex.load_array(in.hlabel, in.idx16, w.hlab, n, -1, w.capL - 1, maxlab);
-    bad |= ex.load_array(in.succ_adj, in.idx16, w.ah, m, 0, n - 1, unused);
-    bad |= ex.load_array(in.tparent, in.idx16, w.tpar, nt, -1, nt - 1, unused);   // (p == t is caught by the cycle check)
-    big |= ex.load_array(in.tlabel, in.idx16, w.tlab, nt, -1, w.capL - 1, maxlab);
+    // structure checks on the CSR offsets (branch-free bodies: the loads of consecutive iterations overlap)
+    const S* const succ_off = static_cast<const S*>(in.succ_off); const S* const succ_adj = static_cast<const S*>(in.succ_adj);
+    const S* const hlabel = static_cast<const S*>(in.hlabel); const S* const tparent = static_cast<const S*>(in.tparent);
+    const S* const tlabel = static_cast<const S*>(in.tlabel);
+    int bad = 0, big = 0, maxlab = -1;
+    PT_FOR_LD(v, n + 1) {
+      const int o = ex.ldg(&succ_off[v]);
+      bad |= (o < 0) | (o > m) | (v == 0 && o != 0) | (v == n && o != m);
+      w.ooff[v] = (I)(o < 0 ? 0 : (o > m ? m : o));
+    }
+    PT_FOR_LD(v, n) {
+      const int l = ex.ldg(&hlabel[v]);
+      w.hlab[v] = (I)l;
+      big |= (l >= w.capL) | (l < -1);
+      maxlab = l > maxlab ? l : maxlab;
+    }
+    PT_FOR_LD(e, m) {
+      const int h = ex.ldg(&succ_adj[e]);
+      bad |= (h < 0) | (h >= n);
+      w.ah[e] = (I)h;
+    }
+    PT_FOR_LD(t, nt) {
+      const int p = ex.ldg(&tparent[t]), l = ex.ldg(&tlabel[t]);
+      bad |= (p < -1) | (p >= nt) | (p == t);
+      big |= (l >= w.capL) | (l < -1);
+      maxlab = l > maxlab ? l : maxlab;
+      w.tpar[t] = (I)p; w.tlab[t] = (I)l; w.tdeg[t] = (I)0;
+    }
     if (bad) w.sc[F_STATUS] = TCS_BAD_GRAPH; else if (big) w.sc[F_TMP2] = 1;
     ex.sync();
     PT_FOR(v, n) {
       if (w.ooff[v + 1] < w.ooff[v]) w.sc[F_STATUS] = TCS_BAD_GRAPH;
       PT_NOUNROLL for (int e = w.ooff[v]; e < w.ooff[v + 1]; ++e) w.at[e] = (I)v;
     }
-    PT_FOR(t, nt) { w.tdeg[t] = (I)0; }
-    if (ex.tid() == 0 && (w.ooff[0] != 0 || w.ooff[n] != m)) w.sc[F_STATUS] = TCS_BAD_GRAPH;
     ex.atomic_max(&w.sc[F_NLAB], maxlab + 1);
     if (take_flag(F_STATUS)) return TCS_BAD_GRAPH;
     if (take_flag(F_TMP2)) return TCS_TOO_LARGE;
@@ -715,9 +744,10 @@ struct TcSolver {
 
   // ---- the rule loop (apply_rules, containment.hpp:1054-1083) -----------------------------------------------
   // returns TcCode; on TC_ERROR *status holds the TCS_* ; on TC_BRANCH *branch_node is the node to branch on
+  template <class S>
   PT_HD int solve(const TcInst& in, bool trusted, int* status, int* branch_node) {
     *status = TCS_OK; *branch_node = -1;
-    int s = load(in);
+    int s = load<S>(in);
     if (s != TCS_OK) { *status = s; return TC_ERROR; }
     const int missing = ex.uniform(&w.sc[F_FAIL]);  // a guest label without a host leaf; reported after the input has been validated
     clean_guest();

@@ -94,8 +94,8 @@ struct WarpEx {
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
   __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
   __device__ __forceinline__ int atomic_xor(int32_t* p, int v) const { return atomicXor(p, v); }
-  template <class T>
-  __device__ __forceinline__ int load_array(const void* src, int src16, T* dst, int n, int lo, int hi, int& vmax) const;
+  template <class S>
+  __device__ __forceinline__ int ldg(const S* p) const { return (int)__ldg(p); }  // caller's arrays: read-only during the launch
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
     return (int)(int16_t)atomicCAS((unsigned short*)p, (unsigned short)(int16_t)c, (unsigned short)(int16_t)v);
@@ -167,34 +167,6 @@ __device__ __noinline__ void warp_exclusive_scan(unsigned in_s, unsigned out_s, 
   }
   __syncwarp();
 }
-// one out-of-line copy of the input loop for all five arrays: four loads in flight per lane, so that four global-memory
-// latencies overlap instead of one load -> store round trip per element
-template <int DST_BYTES, class SRC>
-__device__ __forceinline__ void warp_load_loop(const SRC* __restrict__ src, unsigned dst_s, int n, int lo, int hi, int& flag, int& vmax) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int i = lane; i < n; i += 32) {
-    int v = (int)__ldg(src + i);
-    flag |= (v < lo) | (v > hi);
-    vmax = max(vmax, v);
-    v = min(max(v, lo), hi);
-    if (DST_BYTES == 2) asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst_s + 2u * (unsigned)i), "h"((short)v) : "memory");
-    else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst_s + 4u * (unsigned)i), "r"(v) : "memory");
-  }
-}
-template <int DST_BYTES>
-__device__ __noinline__ int2 warp_load_array(const void* src, int src16, unsigned dst_s, int n, int lo, int hi, int vmax) {
-  int flag = 0;
-  if (src16) warp_load_loop<DST_BYTES>(static_cast<const short*>(src), dst_s, n, lo, hi, flag, vmax);
-  else warp_load_loop<DST_BYTES>(static_cast<const int*>(src), dst_s, n, lo, hi, flag, vmax);
-  return make_int2(flag, vmax);
-}
-template <class T>
-__device__ __forceinline__ int WarpEx::load_array(const void* src, int src16, T* dst, int n, int lo, int hi, int& vmax) const {
-  const int2 r = warp_load_array<(int)sizeof(T)>(src, src16, (unsigned)__cvta_generic_to_shared(dst), n, lo, hi, vmax);
-  vmax = r.y;
-  return r.x;
-}
 template <class C, class T>
 __device__ __forceinline__ void WarpEx::exclusive_scan(const C* in, T* out, int n) const {
   static_assert((sizeof(T) == 2 || sizeof(T) == 4) && (sizeof(C) == 2 || sizeof(C) == 4), "index type");
@@ -254,18 +226,8 @@ struct CtaEx {
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
   __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
   __device__ __forceinline__ int atomic_xor(int32_t* p, int v) const { return atomicXor(p, v); }
-  // caller's arrays are read-only during the launch (ld.global.nc)
-  template <class T>
-  __device__ __forceinline__ int load_array(const void* src, int src16, T* dst, int n, int lo, int hi, int& vmax) const {
-    int flag = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      int v = src16 ? (int)__ldg(static_cast<const short*>(src) + i) : __ldg(static_cast<const int*>(src) + i);
-      flag |= (v < lo) | (v > hi);
-      vmax = max(vmax, v);
-      dst[i] = (T)min(max(v, lo), hi);
-    }
-    return flag;
-  }
+  template <class S>
+  __device__ __forceinline__ int ldg(const S* p) const { return (int)__ldg(p); }  // caller's arrays: read-only during the launch
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_add_idx(int32_t* p, int v) const { return atomicAdd(p, v); }
@@ -324,7 +286,7 @@ struct TcSource {
   int is_pool, capacity;
   const int64_t *hnode_off, *harc_off, *gnode_off;
   const void *succ_off, *succ_adj, *hlabel, *tparent, *tlabel;
-  int idx16;                     // batch mode: the five arrays hold int16_t; the pool is always int32_t
+  int idx16;                     // batch mode: the five arrays hold int16_t (kernel variant S = int16_t); the pool is always int32_t
   const int32_t *dims, *origin;  // pool mode
   int sN1, sM, sN, sNT;          // pool strides (elements)
 };
@@ -335,9 +297,9 @@ struct TcSink {
 };
 enum { CNT_DISPLAYED = 0, CNT_ITEMS, CNT_BRANCH_ITEMS, CNT_CHERRIES, CNT_RET, CNT_ARCS, CNT_PASSES, CNT_ERRORS, CNT_N };
 
-// MAXT = launch bound = register budget: 640 threads -> 102 registers, 768 -> 85, 896 -> 73, 1024 -> 64.  The host picks the
-// smallest variant that holds the warps shared memory allows.
-template <class I, int MAXT>
+// S = element type of the caller's arrays this launch reads (int32_t; int16_t for index_bytes = 2 in round 0).  MAXT = launch
+// bound = register budget: 768 threads -> 80 registers (the default: 24 warps per SM), 1024 -> 64.
+template <class I, class S, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
                                                         uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                         uint8_t* __restrict__ branched, int32_t* __restrict__ ticket,
@@ -364,21 +326,21 @@ __global__ void __launch_bounds__(MAXT, 1) tc_reduce_kernel(TcSource src, TcSink
       in.n = src.dims[4 * item]; in.m = src.dims[4 * item + 1]; in.nt = src.dims[4 * item + 2];
       in.succ_off = static_cast<const int32_t*>(src.succ_off) + (size_t)item * src.sN1; in.succ_adj = static_cast<const int32_t*>(src.succ_adj) + (size_t)item * src.sM;
       in.hlabel = static_cast<const int32_t*>(src.hlabel) + (size_t)item * src.sN; in.tparent = static_cast<const int32_t*>(src.tparent) + (size_t)item * src.sNT;
-      in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT; in.idx16 = 0;
+      in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT;
     } else {
       origin = item;
       const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
       const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
       in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
       if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
-      const int sh = src.idx16 ? 1 : 2;  // log2 of the element size
+      const int sh = sizeof(S) == 2 ? 1 : 2;  // log2 of the element size
       in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + item) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
       in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
-      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh); in.idx16 = src.idx16;
+      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh);
     }
     TcSolver<WarpEx, I> sv(ex, w);
     int st = 0, x = -1;
-    const int code = sv.solve(in, src.is_pool != 0, &st, &x);
+    const int code = sv.template solve<S>(in, src.is_pool != 0, &st, &x);
     ex.phase = 13;
     ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
     if (code == TC_DISPLAYED) {
@@ -424,6 +386,7 @@ __global__ void __launch_bounds__(MAXT, 1) tc_reduce_kernel(TcSource src, TcSink
 }
 
 // one CTA per work item, workspace in global memory
+template <class S>
 __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, size_t ws_bytes,
                                                             unsigned char* __restrict__ ws, uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                             uint8_t* __restrict__ branched, int32_t* __restrict__ ticket, unsigned long long* __restrict__ counters) {
@@ -451,21 +414,21 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
       in.n = src.dims[4 * item]; in.m = src.dims[4 * item + 1]; in.nt = src.dims[4 * item + 2];
       in.succ_off = static_cast<const int32_t*>(src.succ_off) + (size_t)item * src.sN1; in.succ_adj = static_cast<const int32_t*>(src.succ_adj) + (size_t)item * src.sM;
       in.hlabel = static_cast<const int32_t*>(src.hlabel) + (size_t)item * src.sN; in.tparent = static_cast<const int32_t*>(src.tparent) + (size_t)item * src.sNT;
-      in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT; in.idx16 = 0;
+      in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT;
     } else {
       origin = item;
       const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
       const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
       in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
       if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
-      const int sh = src.idx16 ? 1 : 2;  // log2 of the element size
+      const int sh = sizeof(S) == 2 ? 1 : 2;  // log2 of the element size
       in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + item) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
       in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
-      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh); in.idx16 = src.idx16;
+      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh);
     }
     TcSolver<CtaEx, I> sv(ex, w);
     int st = 0, x = -1;
-    const int code = sv.solve(in, src.is_pool != 0, &st, &x);
+    const int code = sv.template solve<S>(in, src.is_pool != 0, &st, &x);
     ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
     if (code == TC_DISPLAYED) {
       if (threadIdx.x == 0) atomicOr(&result_bits[origin >> 5], 1u << (origin & 31));
@@ -764,7 +727,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   } else if (B > 0) {
     int wpc = 1, ctas_per_sm = 1;
     size_t smem = 0, ws_bytes = 0;
-    auto warp_kernel = tc_reduce_kernel<I, 640>;
+    auto warp_kernel = tc_reduce_kernel<I, int32_t, 768>, warp_kernel16 = tc_reduce_kernel<I, int16_t, 768>;
     int cta_grid_cap = 0;
     if (!use_cta) {
       // occupancy: as many warps per SM as shared memory allows (warp_bytes each), in one CTA per SM; the kernel variant
@@ -774,8 +737,9 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       int warps_per_sm = (int)std::min<size_t>((size_t)max_warps, ((size_t)dp.smem_optin) / warp_bytes);
       wpc = std::max(warps_per_sm, 1);
       smem = (size_t)wpc * warp_bytes;
-      warp_kernel = wpc <= 20 ? tc_reduce_kernel<I, 640> : wpc <= 24 ? tc_reduce_kernel<I, 768> : wpc <= 28 ? tc_reduce_kernel<I, 896> : tc_reduce_kernel<I, 1024>;
+      if (wpc > 24) { warp_kernel = tc_reduce_kernel<I, int32_t, 1024>; warp_kernel16 = tc_reduce_kernel<I, int16_t, 1024>; }
       PT_CUDA(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PT_CUDA(cudaFuncSetAttribute(warp_kernel16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
       ws_bytes = (TcWork<int32_t>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL) + 255) & ~(size_t)255;
       size_t free_b = 0, total_b = 0;
@@ -836,12 +800,13 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
           grid = use_cta ? (int)std::min<int64_t>(cta_grid_cap, cnt) : (int)std::min<int64_t>((int64_t)dp.sms * ctas_per_sm, (cnt + wpc - 1) / wpc);
           grid = std::max(grid, 1);
         }
+        const bool in16 = !src.is_pool && src.idx16;  // element type of what this launch reads
         if (use_cta)
-          tc_reduce_cta_kernel<<<grid, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits, stat, b->d_branched, ticket,
-                                                    b->d_counters);
+          (in16 ? tc_reduce_cta_kernel<int16_t> : tc_reduce_cta_kernel<int32_t>)<<<grid, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits,
+                                                                                                      stat, b->d_branched, ticket, b->d_counters);
         else
-          warp_kernel<<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched, ticket,
-                                                           b->d_counters);
+          (in16 ? warp_kernel16 : warp_kernel)<<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched,
+                                                                            ticket, b->d_counters);
         ++b->last_launches;
       }
       PT_CUDA(cudaGetLastError());

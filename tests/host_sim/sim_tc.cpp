@@ -36,15 +36,7 @@ struct HostEx {
     return (int)(((long long)a * i + b) % n);
   }
   int uniform(const int32_t* p) const { return *p; }
-  template <class T> int load_array(const void* src, int src16, T* dst, int n, int lo, int hi, int& vmax) const {
-    int flag = 0;
-    for (int i = tid(); i < n; i += nth()) {
-      const int v = src16 ? (int)static_cast<const int16_t*>(src)[i] : static_cast<const int32_t*>(src)[i];
-      flag |= (v < lo) | (v > hi); if (v > vmax) vmax = v;
-      dst[i] = (T)(v < lo ? lo : (v > hi ? hi : v));
-    }
-    return flag;
-  }
+  template <class S> int ldg(const S* p) const { return (int)*p; }
   int reduce_or(int v) const { return v; }
   int reduce_add(int v) const { return v; }
   template <class T> T atomic_add(T* p, T v) const { T o = *p; *p = (T)(o + v); return o; }
@@ -79,9 +71,9 @@ static int solve_instance(const Item& root, int capN, int capM, int capNT, int c
     HostEx ex{perm};
     TcWork<I> w; w.carve(mem.data(), capN, capM, capNT, capL);
     TcSolver<HostEx, I> sv(ex, w);
-    TcInst in{it.n, it.m, it.nt, it.succ_off.data(), it.succ_adj.data(), it.hlabel.data(), it.tparent.data(), it.tlabel.data(), 0};
+    TcInst in{it.n, it.m, it.nt, it.succ_off.data(), it.succ_adj.data(), it.hlabel.data(), it.tparent.data(), it.tlabel.data()};
     int st = 0, x = -1;
-    const int code = sv.solve(in, !first, &st, &x);
+    const int code = sv.template solve<int32_t>(in, !first, &st, &x);
     first = false;
     S.cherries += sv.st.cherries; S.ret += sv.st.retcherries; S.arcs += sv.st.arcs_deleted; S.passes += sv.st.passes;
     if (code == TC_ERROR) { *status = st; verdict = -1; break; }

@@ -39,15 +39,7 @@ struct GroupEx {
   int nth() const { return T; }
   void sync() { ++nsync; sh->bar.wait(); }
   int map(int i, int) const { return i; }
-  template <class T> int load_array(const void* src, int src16, T* dst, int n, int lo, int hi, int& vmax) const {
-    int flag = 0;
-    for (int i = tid(); i < n; i += nth()) {
-      const int v = src16 ? (int)static_cast<const int16_t*>(src)[i] : static_cast<const int32_t*>(src)[i];
-      flag |= (v < lo) | (v > hi); if (v > vmax) vmax = v;
-      dst[i] = (T)(v < lo ? lo : (v > hi ? hi : v));
-    }
-    return flag;
-  }
+  template <class S> int ldg(const S* p) const { return (int)*p; }
   int uniform(const int32_t* p) { sync(); if (t == 0) sh->scratch[0] = __atomic_load_n(p, __ATOMIC_SEQ_CST); sync(); const int v = sh->scratch[0]; sync(); return v; }
   int reduce_or(int v) { sync(); if (t == 0) sh->red_or = 0; sync(); if (v) sh->red_or.fetch_or(v); sync(); return sh->red_or.load(); }
   int reduce_add(int v) { sync(); if (t == 0) sh->red_add = 0; sync(); if (v) sh->red_add.fetch_add(v); sync(); return sh->red_add.load(); }
@@ -89,9 +81,9 @@ static int solve_instance(const Item& root, int capN, int capM, int capNT, int c
       GroupEx ex{t, T, &sh};
       TcWork<I> w; w.carve(mem.data(), capN, capM, capNT, capL);
       TcSolver<GroupEx, I> sv(ex, w);
-      TcInst in{it.n, it.m, it.nt, it.succ_off.data(), it.succ_adj.data(), it.hlabel.data(), it.tparent.data(), it.tlabel.data(), 0};
+      TcInst in{it.n, it.m, it.nt, it.succ_off.data(), it.succ_adj.data(), it.hlabel.data(), it.tparent.data(), it.tlabel.data()};
       int st = 0, x = -1;
-      const int code = sv.solve(in, !first, &st, &x);
+      const int code = sv.template solve<int32_t>(in, !first, &st, &x);
       codes[t] = code; xs[t] = x; sts[t] = st;
       if (code == TC_BRANCH) {
         const int d = sv.indeg(x);
