@@ -309,6 +309,7 @@ struct TcSolver {
     ex.phase = 3;
     if (ex.tid() == 0) w.sc[F_QTAIL] = 0;
     m = ex.compact_arcs(w.at, w.ah, m);  // drops dead arcs (ends with a barrier)
+    ex.phase = 31;
     // The instance shrinks quickly (on BASELINE config 2 the average snapshot has 67 of 228 nodes alive).  Once a quarter of
     // the node ids is dead, renumber the live ones so that every later pass is proportional to what is left.
     if (4 * (m + 1) < 3 * n) {
@@ -327,14 +328,17 @@ struct TcSolver {
       I* const t = w.hlab; w.hlab = w.lvl; w.lvl = t;
       n = n2;
     }
-    PT_FOR(v, n + 1) { w.haux[v] = (I)0; w.lvl[v] = (I)0; }  // lvl = "queued as a true cherry in this snapshot"
+    ex.phase = 32;
+    PT_FOR(v, n + 1) { w.haux[v] = (I)0; }
     ex.sync();
     PT_FOR(e, m) { ex.atomic_add_idx(&w.haux[w.ah[e]], 1); }
     PT_FOR(e, m + 1) {
       const int lo = e > 0 ? w.at[e - 1] + 1 : 0, hi = e < m ? (int)w.at[e] : n;
       PT_NOUNROLL for (int v = lo; v <= hi; ++v) w.ooff[v] = (I)e;
     }
+    ex.phase = 33;
     ex.exclusive_scan(w.haux, w.ioff, n);
+    ex.phase = 34;
     PT_FOR(e, m) { const int h = w.ah[e]; w.iarc[w.ioff[h] + ex.atomic_add_idx(&w.haux[h], -1) - 1] = (I)e; }
     ex.sync();
 #ifdef PT_SIM_STATS
@@ -365,6 +369,7 @@ struct TcSolver {
       int need = 0;
       PT_FOR(v, n) {
         const int od = outdeg(v), id = indeg(v);
+        int cnt = 0;
         if (od == 0) {
           if (w.hlab[v] < 0) { if (id > 0) need |= NEED_DEAD; }          // (a) unlabelled dead end
           else if (id == 0 && v != root) need |= NEED_FAIL;              // a labelled leaf lost every in-arc
@@ -379,10 +384,13 @@ struct TcSolver {
                 PT_NOUNROLL for (int b = 0; b < a; ++b)
                   if (w.ah[out_arc(v, a)] == w.ah[out_arc(v, b)]) need |= NEED_PARALLEL;
             }
-            // true-cherry candidates of this snapshot (only used when the snapshot turns out to be clean)
-            if (is_host_cherry(v)) { w.lvl[v] = (I)1; w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)v; }
+            // hcnt[v] = children that are labelled leaves with a single parent; all of them -> true-cherry candidate of this
+            // snapshot (only used when the snapshot turns out to be clean)
+            PT_NOUNROLL for (int k = 0; k < od; ++k) { const int c = w.ah[out_arc(v, k)]; cnt += (w.hlab[c] >= 0 && indeg(c) == 1); }
+            if (cnt == od) w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)v;
           }
         }
+        w.hcnt[v] = (I)cnt;
       }
       need = ex.reduce_or(need);
       if (need & NEED_FAIL) { set_scalar(F_FAIL, 1); return; }
@@ -494,24 +502,19 @@ struct TcSolver {
   }
 
   // ---- TC: true (multi-)cherries, as a worklist --------------------------------------------------------------
-  // q is a true cherry: >= 2 live children, every one a labelled leaf with a single parent.  Tolerates a CSR that is stale by
-  // arc DELETIONS (dead arcs have at = -1 and are skipped; in-degrees only over-count, so the test can only say "no" too often).
-  PT_HD bool is_host_cherry(int q) const {
-    int cnt = 0;
-    PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) {
-      const int e = out_arc(q, k);
-      if (w.at[e] < 0) continue;
-      const int c = w.ah[e];
-      if (w.hlab[c] < 0 || indeg(c) != 1) return false;
-      ++cnt;
-    }
-    return cnt >= 2;
+  // A host node q all of whose (>= 2) children are labelled leaves with a single parent must equal the guest node whose
+  // children are exactly those leaves: collapse both into one leaf (it keeps the smallest label), else NOT displayed
+  // (cf. CherryPicker :538-590, match_nodes :915-950).  hcnt[v] counts the children of v that are such leaves (detection
+  // pass of clean_host).  The queue hscr[head, F_QTAIL) holds the nodes whose count is complete; collapsing q tells q's
+  // parent, and the thread that completes the parent's count queues it for the next round, so a pendant subtree that
+  // matches collapses level by level and the total work is proportional to the cherries found.
+  // Tolerates a CSR that is stale by arc DELETIONS: dead arcs have at = -1, degrees only over-count, so a count is then
+  // never completed and the cherry is found after the next clean-up instead.
+  PT_HD void notify_parent(int q) {
+    if (indeg(q) != 1) return;
+    const int g = w.at[in_arc(q, 0)];
+    if (g >= 0 && ex.atomic_add_idx(&w.hcnt[g], 1) + 1 == outdeg(g)) w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)g;
   }
-  // The queue hscr[head, F_QTAIL) holds host nodes: candidates found by the detection pass of clean_host or by the parent
-  // check below (hlab < 0), and nodes that rule_ret_cherry collapsed on the spot (hlab >= 0: only their parent is checked).
-  // Each round: (1) every candidate is matched against the guest and collapsed (a candidate whose leaves are not exactly
-  // the children of one guest node -> NOT displayed), (2) the parent of every fresh leaf is tested and queued once
-  // (lvl = queued flag, reset by csr()).  Total work is proportional to the cherries found, not to rounds x labels.
   // returns 1 something collapsed, 0 nothing, -1 NOT displayed
   PT_NI int rule_true_cherry(int& head) {
     ex.phase = 7;
@@ -523,20 +526,19 @@ struct TcSolver {
       ++rounds;
       PT_FOR(i, cnt) {
         const int q = w.hscr[head + i];
-        if (w.hlab[q] >= 0) continue;  // collapsed by the reticulated-cherry rule
         int p = -1, num = 0, minl = 0x7fffffff;
-        bool ok = true, cherry = true;
+        bool ok = true;
         PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) {
           const int e = out_arc(q, k);
           if (w.at[e] < 0) continue;
-          const int c = w.ah[e], l = w.hlab[c];
-          if (l < 0 || indeg(c) != 1) { cherry = false; break; }
+          const int l = w.hlab[w.ah[e]];
+          if (l < 0) { num = -1000000; continue; }  // (cannot happen for a complete count; never collapse on a doubt)
           const int pp = w.tpar[w.l2t[l]];
           if (num == 0) p = pp; else if (pp != p) ok = false;
           ++num;
           if (l < minl) minl = l;
         }
-        if (!cherry || num < 2) continue;
+        if (num < 2) continue;
         if (!ok || p < 0 || w.tdeg[p] != num) { w.sc[F_FAIL] = 1; continue; }
         PT_NOUNROLL for (int k = 0; k < outdeg(q); ++k) {
           const int e = out_arc(q, k);
@@ -549,14 +551,7 @@ struct TcSolver {
         w.hlab[q] = (I)minl; w.l2h[minl] = (I)q;
         w.tlab[p] = (I)minl; w.l2t[minl] = (I)p; w.tdeg[p] = (I)0;
         ++collapsed;
-      }
-      ex.sync();
-      PT_FOR(i, cnt) {
-        const int q = w.hscr[head + i];
-        if (w.hlab[q] >= 0 && indeg(q) == 1) {
-          const int g = w.at[in_arc(q, 0)];
-          if (g >= 0 && is_host_cherry(g) && ex.atomic_cas_idx(&w.lvl[g], 0, 1) == 0) w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)g;
-        }
+        notify_parent(q);
       }
       head = tail;
     }
@@ -571,7 +566,7 @@ struct TcSolver {
   // out-degree-1 reticulation above y) has q among its parents -> keep that in-arc, delete the others.  (The mirrored case
   // is handled by the thread of y; both cannot apply at once: it would need q above z and z above q.)
   // returns bit 0: some multi-parent node got its parent fixed (needs a clean-up pass), bit 1: some reticulated cherry was
-  // collapsed on the spot (q had exactly the two children; q is appended to the true-cherry queue).
+  // collapsed on the spot (q had exactly the two children; q's parent is told like after a true cherry).
   // Tolerates a CSR that is stale by arc deletions: a dead arc has at = -1 and never matches q, degrees only over-count.
   PT_NI int rule_ret_cherry() {
     ex.phase = 9;
@@ -608,7 +603,7 @@ struct TcSolver {
         w.tlab[ts] = (I)-1; w.tpar[ts] = (I)TDEAD; w.tlab[tt] = (I)-1; w.tpar[tt] = (I)TDEAD;
         w.hlab[q] = (I)s_lab; w.l2h[s_lab] = (I)q; w.l2h[t_lab] = (I)-1;
         w.tlab[p] = (I)s_lab; w.l2t[s_lab] = (I)p; w.l2t[t_lab] = (I)-1; w.tdeg[p] = (I)0;
-        w.hscr[ex.atomic_add(&w.sc[F_QTAIL], 1)] = (I)q;
+        notify_parent(q);
         ++collapsed;
       } else ++fixed;
     }
