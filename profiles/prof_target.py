@@ -11,7 +11,7 @@ pt.set_device(0)
 if what == "tc":
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
     p = pt.Packer(); p.add_generated(B, 100, 20, 0xB200, 0)
-    a = p.arrays()
+    a = p.arrays(compact=True)   # the layout bench.py uses (int16 data arrays)
     dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
     bits = torch.zeros((B + 31) // 32, dtype=torch.int32, device="cuda"); stat = torch.zeros(B, dtype=torch.uint8, device="cuda")
     b = pt.Batch(dev)

@@ -12,11 +12,13 @@ FACADE = os.path.join(ROOT, "tests", "cpp", "build", "test_facade")
 
 @pytest.fixture(scope="module")
 def tools(pt):
-    if not os.path.exists(os.path.join(BIN, "tc")):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "phylo_tools_b200", "csrc"), "tools"])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "phylo_tools_b200", "csrc"), "tools"])   # no-op when up to date
     os.makedirs(os.path.dirname(FACADE), exist_ok=True)
     src = os.path.join(ROOT, "tests", "cpp", "test_facade.cpp")
-    if not os.path.exists(FACADE) or os.path.getmtime(FACADE) < os.path.getmtime(src):
+    deps = [src, os.path.join(ROOT, "include", "pt_gpu.h"), os.path.join(ROOT, "phylo_tools_b200", "libptgpu.so")]
+    hdr_dir = os.path.join(ROOT, "phylo_tools_b200", "include", "pt")
+    deps += [os.path.join(hdr_dir, f) for f in os.listdir(hdr_dir)]
+    if not os.path.exists(FACADE) or os.path.getmtime(FACADE) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", src, "-o", FACADE, "-L" + os.path.join(ROOT, "phylo_tools_b200"), "-lptgpu",
                                "-Wl,-rpath," + os.path.join(ROOT, "phylo_tools_b200")])
     return BIN

@@ -10,12 +10,14 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIM_SRC = os.path.join(ROOT, "tests", "host_sim", "sim_tc.cpp")
 SIM_BIN = os.path.join(ROOT, "tests", "host_sim", "build", "sim_tc")
+_PT_HDR = os.path.join(ROOT, "phylo_tools_b200", "include", "pt")
+HOST_HEADERS = [os.path.join(ROOT, "include", "pt_gpu.h")] + [os.path.join(_PT_HDR, f) for f in sorted(os.listdir(_PT_HDR))]
 
 
 @pytest.fixture(scope="module")
 def sim():
     os.makedirs(os.path.dirname(SIM_BIN), exist_ok=True)
-    deps = [SIM_SRC, os.path.join(ROOT, "phylo_tools_b200", "csrc", "tc_core.cuh")]
+    deps = [SIM_SRC, os.path.join(ROOT, "phylo_tools_b200", "csrc", "tc_core.cuh")] + HOST_HEADERS
     if not os.path.exists(SIM_BIN) or any(os.path.getmtime(d) > os.path.getmtime(SIM_BIN) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", SIM_SRC, "-o", SIM_BIN])
     return SIM_BIN
@@ -158,7 +160,7 @@ SIM_MT_BIN = os.path.join(ROOT, "tests", "host_sim", "build", "sim_tc_mt")
 @pytest.fixture(scope="module")
 def sim_mt():
     os.makedirs(os.path.dirname(SIM_MT_BIN), exist_ok=True)
-    deps = [SIM_MT_SRC, os.path.join(ROOT, "phylo_tools_b200", "csrc", "tc_core.cuh")]
+    deps = [SIM_MT_SRC, os.path.join(ROOT, "phylo_tools_b200", "csrc", "tc_core.cuh")] + HOST_HEADERS
     if not os.path.exists(SIM_MT_BIN) or any(os.path.getmtime(d) > os.path.getmtime(SIM_MT_BIN) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-pthread", SIM_MT_SRC, "-o", SIM_MT_BIN])
     return SIM_MT_BIN
