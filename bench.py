@@ -252,7 +252,7 @@ def config4_leg(pt, torch, count):
     return {"workload": "%d gen networks n=%d r=%d with a displayed tree each (BASELINE configs[3], one GPU's share)" % (count, 2 * retis + 2 * leaves - 1, retis),
             "instances_per_s": count / (ms / 1000.0), "ms": ms, "displayed": c["displayed"], "errors": c["errors"], "work_items": c["work_items"],
             "rule_passes": c["rule_passes"], "input_bytes": nbytes, "host_generation_s": gen_s,
-            "note": "one CTA per instance, workspace in global memory; the reference cannot run this size (extrapolated 3e5 s per instance, BASELINE.md)"}
+            "note": "one thread-block cluster per instance, workspace in global memory; the reference cannot run this size (extrapolated 3e5 s per instance, BASELINE.md)"}
 
 
 def config5_leg(pt, retis=24, leaves=30):

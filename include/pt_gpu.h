@@ -193,7 +193,9 @@ typedef struct pt_options {
   int32_t pool_slots;        /* capacity of the branching pool per round (0 = default)                  */
   int32_t max_rounds;        /* safety bound on branching depth (0 = default 64)                        */
   int32_t path;              /* 0 auto; 1 force the shared-memory executor (one warp per instance, int16 ids);
-                                2 force the global-memory executor (one CTA per instance, int32 ids)         */
+                                2 force the global-memory executor with one CTA per instance (int32 ids);
+                                3 the same with a thread-block cluster per instance (what auto picks for the
+                                  global-memory executor when a launch has fewer instances than half the SMs) */
   int32_t reserved[5];
 } pt_options;
 

@@ -90,6 +90,7 @@ struct TcWork {
   I *at, *ah;            // arc tail / head; at < 0 = deleted.  Arcs stay SORTED BY TAIL: rewriting only deletes arcs or moves heads
   I *ooff;               // out CSR: the out-arcs of v are the arc ids [ooff[v], ooff[v+1]) (csr() compacts the arc arrays)
   I *ioff, *iarc;        // in CSR (arc ids)
+  I *atmp;               // only for executors that cannot compact the arc arrays in place (cluster executor): capM spare entries
   I *hlab;               // label of a live labelled leaf, else -1 (capN+1: csr() swaps it with lvl when it renumbers the nodes)
   I *lvl;                // height (longest path to a leaf) from the wavefront; scratch otherwise
   I *hcnt, *haux;        // atomic scratch, max(capN, capNT)+1 each (the guest passes of clean_guest / emit_child borrow them)
@@ -111,10 +112,11 @@ struct TcWork {
   // (shared-memory occupancy) and make the rule independent of the instance size (n = 10^6 needs 8 MB, not 62 GB).
   static constexpr int kMaxExactWords = 1;
   PT_HD static int sig_words(int L) { const int w = (L + 31) / 32; return w < 1 ? 1 : (w > kMaxExactWords ? kMaxExactWords : w); }
-  PT_HD static size_t bytes(int N, int M, int NT, int L) {
+  PT_HD static size_t bytes(int N, int M, int NT, int L, bool spare_arcs = false) {
     const int W = sig_words(L), S = (N > NT ? N : NT) + 1;
     size_t b = 0;
     b += (size_t)(3 * M + 5 * (N + 1) + 2 * S) * sizeof(I);   // at ah iarc | ooff ioff hlab lvl hscr | hcnt haux
+    if (spare_arcs) b += (size_t)M * sizeof(I);               // atmp
     b += (size_t)(2 * NT + 2 * (NT + 1) + 2 * L) * sizeof(I); // tpar tlab | tdeg tmax | l2h l2t
     b = (b + 3) & ~(size_t)3;
     b += (size_t)N * W * 4;                                   // lset
@@ -123,12 +125,13 @@ struct TcWork {
   }
   // All pointers are formed as base + offset (no pointer -> integer -> pointer round trip): the CUDA compiler then keeps the
   // address space of `base`, and the warp executor gets LDS / STS / ATOMS instead of generic LD / ST / ATOM.
-  PT_HD void carve(char* base, int N, int M, int NT, int L) {
+  PT_HD void carve(char* base, int N, int M, int NT, int L, bool spare_arcs = false) {
     capN = N; capM = M; capNT = NT; capL = L; W = sig_words(L);
     const int S = (N > NT ? N : NT) + 1;
     size_t o = 0;
     auto take = [&](size_t nbytes) { const size_t r = o; o += nbytes; return r; };
     at = (I*)(base + take((size_t)M * sizeof(I))); ah = (I*)(base + take((size_t)M * sizeof(I))); iarc = (I*)(base + take((size_t)M * sizeof(I)));
+    atmp = spare_arcs ? (I*)(base + take((size_t)M * sizeof(I))) : nullptr;
     ooff = (I*)(base + take((size_t)(N + 1) * sizeof(I))); ioff = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
     hlab = (I*)(base + take((size_t)(N + 1) * sizeof(I))); lvl = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
     hscr = (I*)(base + take((size_t)(N + 1) * sizeof(I)));
@@ -308,7 +311,7 @@ struct TcSolver {
   PT_NI void csr() {
     ex.phase = 3;
     if (ex.tid() == 0) w.sc[F_QTAIL] = 0;
-    m = ex.compact_arcs(w.at, w.ah, m);  // drops dead arcs (ends with a barrier)
+    m = ex.compact_arcs(w.at, w.ah, m, w.iarc, w.atmp);  // drops dead arcs (ends with a barrier); iarc is rebuilt below
     ex.phase = 31;
     // The instance shrinks quickly (on BASELINE config 2 the average snapshot has 67 of 228 nodes alive).  Once a quarter of
     // the node ids is dead, renumber the live ones so that every later pass is proportional to what is left.

@@ -11,6 +11,7 @@
 #include "cuda_common.cuh"
 #include "tc_core.cuh"
 
+#include <cooperative_groups.h>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -115,7 +116,7 @@ struct WarpEx {
   // stable in-place compaction of the arc arrays (keeps at >= 0); returns the new count.
   // A tile's loads complete before its ballot does and its stores go to positions <= the ones just read.
   template <class I>
-  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m) const {
+  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m, I*, I*) const {
     int carry = 0;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
@@ -233,7 +234,7 @@ struct CtaEx {
   __device__ __forceinline__ int atomic_add_idx(int32_t* p, int v) const { return atomicAdd(p, v); }
   __device__ __forceinline__ void atomic_xor_idx(int32_t* p, int v) const { atomicXor(p, v); }
   template <class I>
-  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m) {
+  __device__ __forceinline__ int compact_arcs(I* at, I* ah, int m, I*, I*) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     sync();
@@ -276,6 +277,134 @@ struct CtaEx {
     }
     if (threadIdx.x == 0) out[n] = (T)carry;
     __syncthreads();
+  }
+};
+
+// ---- the cluster executor: one thread-block CLUSTER per instance, workspace in global memory -------------------------------
+// For a handful of huge instances (BASELINE config 4: 8 instances of n = 10^6 per GPU) one CTA per instance leaves most SMs
+// idle.  A cluster of up to 8 CTAs (hardware co-scheduled, hardware barrier) runs the same solver: a pass is spread over
+// all threads of the cluster, the barrier is barrier.cluster, reductions and scans combine per-CTA partials through a few
+// words of the workspace.  gsc = 64 ints at the front of the cluster's workspace: [0] reduce_or [1] reduce_add [2] ticket /
+// broadcast [16..31] per-CTA partial sums.
+struct ClusterEx {
+  int* red;           // 40 ints of shared memory (this CTA)
+  int32_t* gsc;       // 64 ints of global memory (this cluster)
+  int phase;
+  unsigned rank, csize;
+  __device__ __forceinline__ int tid() const { return (int)(rank * blockDim.x + threadIdx.x); }
+  __device__ __forceinline__ int nth() const { return (int)(csize * blockDim.x); }
+  __device__ __forceinline__ void sync() {
+    __threadfence();  // as in CtaEx: plain stores must reach L2 before another CTA's atomics / loads of the same words
+    cooperative_groups::this_cluster().sync();
+  }
+  __device__ __forceinline__ int map(int i, int) const { return i; }
+  __device__ __forceinline__ int uniform(const int32_t* p) { sync(); const int v = *(const volatile int32_t*)p; sync(); return v; }
+  __device__ __forceinline__ int reduce_or(int v) {
+    v = (int)__reduce_or_sync(0xffffffffu, (unsigned)v);
+    sync();
+    if (tid() == 0) gsc[0] = 0;
+    sync();
+    if ((threadIdx.x & 31) == 0 && v) atomicOr(&gsc[0], v);
+    sync();
+    return *(volatile int32_t*)&gsc[0];
+  }
+  __device__ __forceinline__ int reduce_add(int v) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    sync();
+    if (tid() == 0) gsc[1] = 0;
+    sync();
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&gsc[1], v);
+    sync();
+    return *(volatile int32_t*)&gsc[1];
+  }
+  __device__ __forceinline__ int atomic_add(int32_t* p, int v) const { return atomicAdd(p, v); }
+  __device__ __forceinline__ int atomic_min(int32_t* p, int v) const { return atomicMin(p, v); }
+  __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
+  __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
+  __device__ __forceinline__ int atomic_xor(int32_t* p, int v) const { return atomicXor(p, v); }
+  template <class S>
+  __device__ __forceinline__ int ldg(const S* p) const { return (int)__ldg(p); }
+  __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
+  __device__ __forceinline__ int atomic_cas_idx(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
+  __device__ __forceinline__ int atomic_add_idx(int32_t* p, int v) const { return atomicAdd(p, v); }
+  __device__ __forceinline__ void atomic_xor_idx(int32_t* p, int v) const { atomicXor(p, v); }
+  // sum of `mine` over the threads of this CTA (all threads get it)
+  __device__ __forceinline__ int cta_sum(int mine) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    __syncthreads();
+    if (lane == 0) red[wid] = mine;
+    __syncthreads();
+    int total = 0;
+    for (int k = 0; k < nw; ++k) total += red[k];
+    return total;
+  }
+  // every CTA publishes its partial; returns the sum over the lower ranks and, in *all, over the whole cluster
+  __device__ __forceinline__ int cluster_offsets(int cta_total, int* all) {
+    sync();
+    if (threadIdx.x == 0) gsc[16 + rank] = cta_total;
+    sync();
+    int base = 0, sum = 0;
+    for (unsigned k = 0; k < csize; ++k) { const int t = *(volatile int32_t*)&gsc[16 + k]; if (k < rank) base += t; sum += t; }
+    *all = sum;
+    return base;
+  }
+  // each CTA owns a contiguous slice of [0,n): a counting pass, the cluster-wide offsets, then the tile scan of CtaEx
+  template <class C, class T>
+  __device__ __forceinline__ void exclusive_scan(const C* in, T* out, int n) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lo = (int)((long long)n * rank / csize), hi = (int)((long long)n * (rank + 1) / csize);
+    int part = 0;
+    sync();
+    for (int i = lo + (int)threadIdx.x; i < hi; i += blockDim.x) part += in[i];
+    int all = 0;
+    int carry = cluster_offsets(cta_sum(part), &all);
+    for (int base = lo; base < hi; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      const int v = i < hi ? (int)in[i] : 0;
+      int incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      __syncthreads();
+      if (lane == 31) red[wid] = incl;
+      __syncthreads();
+      int woff = 0, total = 0;
+      for (int k = 0; k < nw; ++k) { const int t = red[k]; if (k < wid) woff += t; total += t; }
+      if (i < hi) out[i] = (T)(carry + woff + incl - v);
+      carry += total;
+    }
+    if (tid() == 0) out[n] = (T)all;
+    sync();
+  }
+  // stable compaction of the arc arrays (keeps at >= 0) into the two spare arrays, then the pointers are swapped: CTAs cannot
+  // compact in place (a CTA would overwrite elements a lower-ranked one has not read yet)
+  template <class I>
+  __device__ __forceinline__ int compact_arcs(I*& at, I*& ah, int m, I*& spare_a, I*& spare_b) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int lo = (int)((long long)m * rank / csize), hi = (int)((long long)m * (rank + 1) / csize);
+    int part = 0;
+    sync();
+    for (int i = lo + (int)threadIdx.x; i < hi; i += blockDim.x) part += at[i] >= 0;
+    int all = 0;
+    int carry = cluster_offsets(cta_sum(part), &all);
+    for (int base = lo; base < hi; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      int t = -1, h = 0;
+      if (i < hi) { t = at[i]; h = ah[i]; }
+      const unsigned mask = __ballot_sync(0xffffffffu, t >= 0);
+      __syncthreads();
+      if (lane == 0) red[wid] = __popc(mask);
+      __syncthreads();
+      int woff = 0, total = 0;
+      for (int k = 0; k < nw; ++k) { const int c = red[k]; if (k < wid) woff += c; total += c; }
+      if (t >= 0) { const int pos = carry + woff + __popc(mask & lt); spare_a[pos] = (I)t; spare_b[pos] = (I)h; }
+      carry += total;
+    }
+    sync();
+    I* x = at; at = spare_a; spare_a = x;
+    x = ah; ah = spare_b; spare_b = x;
+    return all;
   }
 };
 
@@ -461,6 +590,96 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
     }
   }
   if (threadIdx.x == 0) {
+    if (c_disp) atomicAdd(&counters[CNT_DISPLAYED], c_disp);
+    if (c_items) atomicAdd(&counters[CNT_ITEMS], c_items);
+    if (c_br) atomicAdd(&counters[CNT_BRANCH_ITEMS], c_br);
+    if (c_ch) atomicAdd(&counters[CNT_CHERRIES], c_ch);
+    if (c_ret) atomicAdd(&counters[CNT_RET], c_ret);
+    if (c_arc) atomicAdd(&counters[CNT_ARCS], c_arc);
+    if (c_pass) atomicAdd(&counters[CNT_PASSES], c_pass);
+    if (c_err) atomicAdd(&counters[CNT_ERRORS], c_err);
+  }
+}
+
+// one thread-block cluster per work item (launched with cudaLaunchAttributeClusterDimension), workspace in global memory:
+// 256 bytes of executor scalars, then the TcWork arrays with the spare arc arrays
+template <class S>
+__global__ void __launch_bounds__(512, 1) tc_reduce_cluster_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, size_t ws_bytes,
+                                                                unsigned char* __restrict__ ws, uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
+                                                                uint8_t* __restrict__ branched, int32_t* __restrict__ ticket, unsigned long long* __restrict__ counters) {
+  using I = int32_t;
+  __shared__ int s_red[40];
+  cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+  const unsigned csize = cl.num_blocks(), rank = cl.block_rank(), cluster_id = blockIdx.x / csize;
+  char* const base_ws = reinterpret_cast<char*>(ws) + (size_t)cluster_id * ws_bytes;
+  ClusterEx ex{s_red, reinterpret_cast<int32_t*>(base_ws), 0, rank, csize};
+  TcWork<I> w;
+  w.carve(base_ws + 256, capN, capM, capNT, capL, true);
+  const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
+  const bool leader = ex.tid() == 0;
+  unsigned long long c_disp = 0, c_items = 0, c_br = 0, c_ch = 0, c_ret = 0, c_arc = 0, c_pass = 0, c_err = 0;
+  for (;;) {
+    ex.sync();
+    if (leader) ex.gsc[2] = (int)src.first + atomicAdd(ticket, 1);
+    const int item = ex.uniform(&ex.gsc[2]);
+    if (item >= total) break;
+    TcInst in;
+    int origin;
+    if (src.is_pool) {
+      origin = src.origin[item];
+      ex.sync();
+      if (leader) ex.gsc[3] = (int)((*(volatile uint32_t*)&result_bits[origin >> 5] >> (origin & 31)) & 1u);
+      if (ex.uniform(&ex.gsc[3])) continue;
+      in.n = src.dims[4 * item]; in.m = src.dims[4 * item + 1]; in.nt = src.dims[4 * item + 2];
+      in.succ_off = static_cast<const int32_t*>(src.succ_off) + (size_t)item * src.sN1; in.succ_adj = static_cast<const int32_t*>(src.succ_adj) + (size_t)item * src.sM;
+      in.hlabel = static_cast<const int32_t*>(src.hlabel) + (size_t)item * src.sN; in.tparent = static_cast<const int32_t*>(src.tparent) + (size_t)item * src.sNT;
+      in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT;
+    } else {
+      origin = item;
+      const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
+      const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
+      in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
+      if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
+      const int sh = sizeof(S) == 2 ? 1 : 2;  // log2 of the element size
+      in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + item) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
+      in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
+      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh);
+    }
+    TcSolver<ClusterEx, I> sv(ex, w);
+    int st = 0, x = -1;
+    const int code = sv.template solve<S>(in, src.is_pool != 0, &st, &x);
+    ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
+    if (code == TC_DISPLAYED) {
+      if (leader) atomicOr(&result_bits[origin >> 5], 1u << (origin & 31));
+      ++c_disp;
+    } else if (code == TC_ERROR) {
+      if (leader) status[origin] = (uint8_t)st;
+      ++c_err;
+    } else if (code == TC_BRANCH) {
+      const int d = sv.indeg(x);
+      ex.sync();
+      if (leader) ex.gsc[4] = atomicAdd(sink.count, d);
+      const int base = ex.uniform(&ex.gsc[4]);
+      if (base + d > sink.capacity) {
+        if (leader) status[origin] = (uint8_t)TCS_POOL_OVERFLOW;
+      } else {
+        if (leader) branched[origin] = 1;
+        c_br += (unsigned long long)d;
+        int32_t* arcs = reinterpret_cast<int32_t*>(w.lset);  // signatures are dead by now; d <= n <= capN * W words
+        for (int k = ex.tid(); k < d; k += ex.nth()) arcs[k] = sv.in_arc(x, k);
+        ex.sync();
+        for (int k = 0; k < d; ++k) {
+          const int keep = *(volatile int32_t*)&arcs[k];
+          const size_t slot = (size_t)(base + k);
+          TcEmit out{sink.succ_off + slot * sink.sN1, sink.succ_adj + slot * sink.sM, sink.hlabel + slot * sink.sN,
+                     sink.tparent + slot * sink.sNT, sink.tlabel + slot * sink.sNT, sink.dims + slot * 4};
+          sv.emit_child(x, keep, out);
+          if (leader) sink.origin[slot] = origin;
+        }
+      }
+    }
+  }
+  if (leader) {
     if (c_disp) atomicAdd(&counters[CNT_DISPLAYED], c_disp);
     if (c_items) atomicAdd(&counters[CNT_ITEMS], c_items);
     if (c_br) atomicAdd(&counters[CNT_BRANCH_ITEMS], c_br);
@@ -721,14 +940,14 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   const int force = opt ? opt->path : 0;
   const bool fits16 = b->maxN <= 30000 && b->maxM <= 30000 && b->maxNT <= 30000 && b->maxL <= 30000;
   const size_t warp_bytes = TcWork<I>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL);
-  const bool use_cta = force == 2 || !fits16 || warp_bytes > (size_t)dp.smem_optin;
+  const bool use_cta = force == 2 || force == 3 || !fits16 || warp_bytes > (size_t)dp.smem_optin;
   if (force == 1 && use_cta && B > 0) {
     PT_CUDA(cudaMemsetAsync(stat, PT_INST_TOO_LARGE, (size_t)B, s));  // caller insisted on the shared-memory path
   } else if (B > 0) {
     int wpc = 1, ctas_per_sm = 1;
     size_t smem = 0, ws_bytes = 0;
     auto warp_kernel = tc_reduce_kernel<I, int32_t, 768>, warp_kernel16 = tc_reduce_kernel<I, int16_t, 768>;
-    int cta_grid_cap = 0;
+    int cta_grid_cap = 0, max_cluster = 8;
     if (!use_cta) {
       // occupancy: as many warps per SM as shared memory allows (warp_bytes each), in one CTA per SM; the kernel variant
       // (register budget) follows from the warp count
@@ -741,12 +960,18 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       PT_CUDA(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       PT_CUDA(cudaFuncSetAttribute(warp_kernel16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
-      ws_bytes = (TcWork<int32_t>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL) + 255) & ~(size_t)255;
+      // one stride for both global-memory executors: 256 bytes of cluster scalars + the arrays with the spare arc arrays
+      ws_bytes = (256 + TcWork<int32_t>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL, true) + 255) & ~(size_t)255;
       size_t free_b = 0, total_b = 0;
       PT_CUDA(cudaMemGetInfo(&free_b, &total_b));
       const size_t budget = free_b / 3;
       cta_grid_cap = (int)std::min<size_t>((size_t)dp.sms * 2, std::max<size_t>(1, budget / ws_bytes));
       cta_grid_cap = (int)std::min<int64_t>(cta_grid_cap, B);
+      // clusters of 16 are not portable: opt in, and use them only if the device accepts the attribute
+      if (cudaFuncSetAttribute(tc_reduce_cluster_kernel<int16_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+          cudaFuncSetAttribute(tc_reduce_cluster_kernel<int32_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) max_cluster = 16;
+      else cudaGetLastError();
+      if (const char* e = getenv("PT_TC_MAX_CLUSTER")) max_cluster = std::max(1, std::min(16, atoi(e)));  // tuning aid
       if (b->ws_cap < (size_t)cta_grid_cap * ws_bytes) {
         dev_free(b->d_ws); b->d_ws = nullptr; b->ws_cap = 0;
         if (int rc2 = dev_alloc((void**)&b->d_ws, (size_t)cta_grid_cap * ws_bytes)) return rc2;
@@ -801,7 +1026,20 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
           grid = std::max(grid, 1);
         }
         const bool in16 = !src.is_pool && src.idx16;  // element type of what this launch reads
-        if (use_cta)
+        // few huge instances: a cluster of CTAs per instance, as large as keeps every instance of this launch on its own SMs
+        auto cluster_kernel = in16 ? tc_reduce_cluster_kernel<int16_t> : tc_reduce_cluster_kernel<int32_t>;
+        int csize = 1;
+        if (use_cta && force != 2) { while (csize < max_cluster && (int64_t)grid * csize * 2 <= dp.sms) csize *= 2; }
+        if (use_cta && force == 3 && csize == 1) csize = 2;
+        if (use_cta && csize > 1) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3((unsigned)(grid * csize)); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          PT_CUDA(cudaLaunchKernelEx(&cfg, cluster_kernel, src, sink, (int)b->maxN, (int)b->maxM,
+                                     (int)b->maxNT, (int)b->maxL, ws_bytes, b->d_ws, bits, stat, b->d_branched, ticket, b->d_counters));
+        } else if (use_cta)
           (in16 ? tc_reduce_cta_kernel<int16_t> : tc_reduce_cta_kernel<int32_t>)<<<grid, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits,
                                                                                                       stat, b->d_branched, ticket, b->d_counters);
         else

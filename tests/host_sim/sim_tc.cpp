@@ -46,7 +46,7 @@ struct HostEx {
   template <class T> T atomic_xor(T* p, T v) const { T o = *p; *p = (T)(o ^ v); return o; }
   template <class T> T atomic_cas(T* p, T c, T v) const { T o = *p; if (o == c) *p = v; return o; }
   template <class T> int atomic_cas_idx(T* p, int c, int v) const { int o = *p; if (o == c) *p = (T)v; return o; }
-  template <class T> int compact_arcs(T* at, T* ah, int m) const {
+  template <class T> int compact_arcs(T* at, T* ah, int m, T*, T*) const {
     int k = 0;
     for (int e = 0; e < m; ++e) if (at[e] >= 0) { at[k] = at[e]; ah[k] = ah[e]; ++k; }
     return k;

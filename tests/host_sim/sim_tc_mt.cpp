@@ -50,7 +50,7 @@ struct GroupEx {
   template <class X> X atomic_xor(X* p, X v) const { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
   template <class X> X atomic_cas(X* p, X c, X v) const { __atomic_compare_exchange_n(p, &c, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return c; }
   template <class X> int atomic_cas_idx(X* p, int c, int v) const { X e = (X)c; __atomic_compare_exchange_n(p, &e, (X)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return (int)e; }
-  template <class X> int compact_arcs(X* at, X* ah, int m) {
+  template <class X> int compact_arcs(X* at, X* ah, int m, X*, X*) {
     sync();
     if (t == 0) { int k = 0; for (int e = 0; e < m; ++e) if (at[e] >= 0) { at[k] = at[e]; ah[k] = ah[e]; ++k; } sh->scratch[0] = k; }
     sync();

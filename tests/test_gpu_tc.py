@@ -218,6 +218,29 @@ def test_global_memory_executor_on_golden_instances(pt, gold_tc):
     assert [int(x) for x in v] == [it["truth"] for it in items]
 
 
+def test_cluster_executor_on_golden_instances(pt, gold_tc):
+    """pt_options.path = 3: one thread-block cluster per instance (the executor for a few huge instances) forced onto the
+    pinned small instances: same solver code, cluster-wide passes / scans / compaction, same verdicts"""
+    items = gold_tc["items"]
+    p = pt.Packer()
+    for it in items:
+        p.add_newick(it["host"], it["guest"])
+    b = pt.Batch(p.arrays())
+    v, s, c = b.contain(path=3)
+    b.free()
+    assert (s == 0).all()
+    assert [int(x) for x in v] == [it["truth"] for it in items]
+    # a handful of instances: the cluster size grows to 8 CTAs per instance
+    q = pt.Packer()
+    q.add_generated(3, 400, 60, 909, 0); q.add_generated(3, 400, 60, 919, 1); q.add_generated(2, 300, 40, 929, 2)
+    a = q.arrays()
+    b1, b3 = pt.Batch(a), pt.Batch(a)
+    v1, s1, _ = b1.contain(path=1)
+    v3, s3, _ = b3.contain(path=3)
+    b1.free(); b3.free()
+    assert (s1 == 0).all() and (s3 == 0).all() and (v1 == v3).all() and v1[:3].all()
+
+
 def test_executors_agree_on_mid_size(pt):
     p = pt.Packer()
     for kind in (0, 1, 2):
@@ -225,9 +248,10 @@ def test_executors_agree_on_mid_size(pt):
     b = pt.Batch(p.arrays())
     v1, s1, c1 = b.contain(path=1)
     v2, s2, c2 = b.contain(path=2)
+    v3, s3, c3 = b.contain(path=3)
     b.free()
-    assert (s1 == 0).all() and (s2 == 0).all()
-    assert (v1 == v2).all() and v1[:300].all()
+    assert (s1 == 0).all() and (s2 == 0).all() and (s3 == 0).all()
+    assert (v1 == v2).all() and (v1 == v3).all() and v1[:300].all()
     # (work-item counts may differ: a pool item is skipped when a sibling branch of the same launch has already displayed its origin)
     assert c1["displayed"] == c2["displayed"] and c1["instances"] == c2["instances"]
 
