@@ -280,6 +280,9 @@ struct CtaEx {
   }
 };
 
+#ifndef PT_CLUSTER_THREADS
+#define PT_CLUSTER_THREADS 1024  // config 4, clusters of 8: 512 threads (115 registers) 28.9 ms, 1024 threads (64 registers) 24.4 ms
+#endif
 // ---- the cluster executor: one thread-block CLUSTER per instance, workspace in global memory -------------------------------
 // For a handful of huge instances (BASELINE config 4: 8 instances of n = 10^6 per GPU) one CTA per instance leaves most SMs
 // idle.  A cluster of up to 8 CTAs (hardware co-scheduled, hardware barrier) runs the same solver: a pass is spread over
@@ -294,8 +297,10 @@ struct ClusterEx {
   __device__ __forceinline__ int tid() const { return (int)(rank * blockDim.x + threadIdx.x); }
   __device__ __forceinline__ int nth() const { return (int)(csize * blockDim.x); }
   __device__ __forceinline__ void sync() {
+#ifndef PT_CLUSTER_NO_FENCE
     __threadfence();  // as in CtaEx: plain stores must reach L2 before another CTA's atomics / loads of the same words
-    cooperative_groups::this_cluster().sync();
+#endif
+    cooperative_groups::this_cluster().sync();  // barrier.cluster.arrive.release + wait.acquire
   }
   __device__ __forceinline__ int map(int i, int) const { return i; }
   __device__ __forceinline__ int uniform(const int32_t* p) { sync(); const int v = *(const volatile int32_t*)p; sync(); return v; }
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
 // one thread-block cluster per work item (launched with cudaLaunchAttributeClusterDimension), workspace in global memory:
 // 256 bytes of executor scalars, then the TcWork arrays with the spare arc arrays
 template <class S>
-__global__ void __launch_bounds__(512, 1) tc_reduce_cluster_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, size_t ws_bytes,
+__global__ void __launch_bounds__(PT_CLUSTER_THREADS, 1) tc_reduce_cluster_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, size_t ws_bytes,
                                                                 unsigned char* __restrict__ ws, uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                                 uint8_t* __restrict__ branched, int32_t* __restrict__ ticket, unsigned long long* __restrict__ counters) {
   using I = int32_t;
@@ -967,11 +972,14 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       const size_t budget = free_b / 3;
       cta_grid_cap = (int)std::min<size_t>((size_t)dp.sms * 2, std::max<size_t>(1, budget / ws_bytes));
       cta_grid_cap = (int)std::min<int64_t>(cta_grid_cap, B);
-      // clusters of 16 are not portable: opt in, and use them only if the device accepts the attribute
-      if (cudaFuncSetAttribute(tc_reduce_cluster_kernel<int16_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-          cudaFuncSetAttribute(tc_reduce_cluster_kernel<int32_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) max_cluster = 16;
-      else cudaGetLastError();
-      if (const char* e = getenv("PT_TC_MAX_CLUSTER")) max_cluster = std::max(1, std::min(16, atoi(e)));  // tuning aid
+      // measured on config 4 (8 instances of n = 10^6): clusters of 4: 43.6 ms, 8: 29.8 ms, 16 (non-portable size): 35.0 ms
+      if (const char* e = getenv("PT_TC_MAX_CLUSTER")) {  // tuning aid; 16 needs the non-portable opt-in
+        max_cluster = std::max(1, std::min(16, atoi(e)));
+        if (max_cluster > 8 && (cudaFuncSetAttribute(tc_reduce_cluster_kernel<int16_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                                cudaFuncSetAttribute(tc_reduce_cluster_kernel<int32_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+          cudaGetLastError(); max_cluster = 8;
+        }
+      }
       if (b->ws_cap < (size_t)cta_grid_cap * ws_bytes) {
         dev_free(b->d_ws); b->d_ws = nullptr; b->ws_cap = 0;
         if (int rc2 = dev_alloc((void**)&b->d_ws, (size_t)cta_grid_cap * ws_bytes)) return rc2;
@@ -1033,7 +1041,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
         if (use_cta && force == 3 && csize == 1) csize = 2;
         if (use_cta && csize > 1) {
           cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = dim3((unsigned)(grid * csize)); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+          cfg.gridDim = dim3((unsigned)(grid * csize)); cfg.blockDim = dim3(PT_CLUSTER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
           cudaLaunchAttribute attr[1];
           attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
           cfg.attrs = attr; cfg.numAttrs = 1;
