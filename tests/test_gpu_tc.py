@@ -1,5 +1,7 @@
 """Parity of the CUDA containment path (through the C-ABI) with the oracle: exhaustive-switching truth on small
 instances, the pinned reference outputs, error statuses, and size-independent properties at BASELINE config 2 size."""
+import os
+
 import numpy as np
 import pytest
 
@@ -43,6 +45,26 @@ def test_generated_vs_bruteforce(pt, oracle, l, r):
     truth = np.array([oracle.tc_bruteforce_newick(*p.newick(i))[0] for i in range(len(p))])
     assert (v.astype(int) == truth).all(), np.where(v.astype(int) != truth)[0][:10]
     assert v[:120].all()  # kind 0 is displayed by construction
+
+
+@pytest.mark.skipif(not os.environ.get("PT_STRESS"), reason="long randomized parity run: set PT_STRESS=<instances per (l, r, kind)>")
+def test_stress_all_executors_vs_bruteforce(pt, oracle):
+    """every executor (warp / CTA / cluster) and both input layouts against exhaustive switching on fresh random instances"""
+    per = int(os.environ["PT_STRESS"])
+    seed = int(os.environ.get("PT_STRESS_SEED", "777"))
+    for l, r in [(4, 2), (6, 3), (9, 4), (12, 6), (16, 8), (22, 10)]:
+        p = pt.Packer()
+        for kind in (0, 1, 2):
+            p.add_generated(per, l, r, seed + 1000 * l + kind, kind)
+        truth = np.array([oracle.tc_bruteforce_newick(*p.newick(i))[0] for i in range(len(p))])
+        for compact in (False, True):
+            b = pt.Batch(p.arrays(compact=compact))
+            for path in (1, 2, 3):
+                v, s, _ = b.contain(path=path)
+                assert (s == 0).all(), (l, r, compact, path)
+                bad = np.where(v.astype(int) != truth)[0]
+                assert len(bad) == 0, (l, r, compact, path, bad[:10])
+            b.free()
 
 
 def test_tree_in_tree_and_degenerate(pt, oracle):
