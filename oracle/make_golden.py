@@ -206,6 +206,28 @@ def make_bridges():
     print("bridges_ref.json:", len(items), "networks,", crashed, "reference crashes")
 
 
+def make_bcc():
+    """networks -> bridges in the reference's post-order and the components its BiconnectedComponents iterator yields
+    (oracle/_ref/ref_tc bcc): pins the ORDER that pt/bridges.hpp reproduces on top of pt_net_bridges"""
+    lines = ["((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));", "((a,(b)#H1),(#H1,c));", "(((a,b),((c)#H1,d)),(#H1,e));"]
+    for (l, r, cnt) in [(5, 2, 12), (10, 4, 12), (20, 8, 8), (50, 10, 6)]:
+        lines += [h for h, _ in gen_pairs(cnt, l, r, 9300 + l, 0)]
+    out = run_lines(REF_TC, "bcc", lines)
+    blocks = [b.strip("\n").split("\n") for b in out.split("--\n")][:len(lines)]
+    items = []
+    for s, b in zip(lines, blocks):
+        if any(x in ("CRASH", "EXC") for x in b):
+            items.append(dict(newick=s, reference="CRASH"))
+            continue
+        bridges = [list(map(int, x.split()[1:])) for x in b if x.startswith("B ")]
+        comps = [[list(map(int, e.split(","))) for e in x.split()[1:]] for x in b if x.startswith("C")]
+        items.append(dict(newick=s, bridges=bridges, components=comps))
+    crashed = sum(1 for it in items if it.get("reference") == "CRASH")
+    json.dump(dict(source="oracle/_ref/ref_tc bcc (reference utils/bridges.hpp + utils/biconnected_comps.hpp)", crashed=crashed, items=items),
+              open(os.path.join(GOLD, "bcc_ref.json"), "w"), indent=0)
+    print("bcc_ref.json:", len(items), "networks,", crashed, "reference crashes")
+
+
 def pt_name(i):
     s = ""
     while True:
@@ -222,3 +244,4 @@ if __name__ == "__main__":
     make_lca()
     make_who()
     make_bridges()
+    make_bcc()

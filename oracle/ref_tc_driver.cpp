@@ -10,6 +10,8 @@
 //   ref_tc bench <file> <max_instances> : same fork-isolated loop, timed; prints a JSON line on stderr
 //        (rate = instances with a verdict / wall seconds; crashes and exceptions are counted separately).
 //   ref_tc who <file> : tree/tree pairs; prints who_displays(u) of the reference for every guest node
+//   ref_tc bcc <file> : per network line: the bridges in the reference's post-order ("B tail head"), then every component the
+//        reference's BiconnectedComponents iterator yields ("C" + its edges, sorted), then "--"
 //   ref_tc parse <file> : for each line: "n m" then edges "u v" in reference edge-list order, then
 //        labels "id name" sorted by id, then "--" (golden vectors for the Newick reader).
 #include "io/io.hpp"
@@ -19,6 +21,7 @@
 #include "utils/mul_wrapper.hpp"
 #include "utils/containment.hpp"
 #include "utils/bridges.hpp"
+#include "utils/biconnected_comps.hpp"
 
 #include <chrono>
 #include <fstream>
@@ -109,6 +112,43 @@ int main(int argc, char** argv) {
           for (auto& uv : out) br.emplace_back((size_t)uv.tail(), (size_t)uv.head());
           std::sort(br.begin(), br.end());
           for (auto& p : br) printf("%zu %zu\n", p.first, p.second);
+        } catch (...) { printf("EXC\n"); }
+        fflush(stdout); _exit(0);
+      }
+      int st = 0; waitpid(pid, &st, 0);
+      if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) printf("CRASH\n");
+      printf("--\n");
+    }
+    return 0;
+  }
+  if (mode == "bcc") {
+    // the reference iterator keeps its edge list protected: a subclass reads it (nothing of the reference is modified)
+    using Net = RONetwork<>;
+    struct OpenIter : public BiconnectedComponentIter<Net> {
+      OpenIter(const Net& N, const std::vector<typename Net::Edge>& br, bool end = false) : BiconnectedComponentIter<Net>(N, br, end) {}
+      const std::vector<typename Net::Edge>& edges() const { return this->current_edges; }
+    };
+    std::cout.setstate(std::ios::badbit);
+    for (auto& line : L) {
+      fflush(stdout);
+      pid_t pid = fork();
+      if (pid == 0) {
+        try {
+          ENL e; parse_line(line, e);
+          Net N(e.edges, *e.labels, consecutive_tag());
+          std::vector<typename Net::Edge> br;
+          BridgeFinder<Net, std::vector<typename Net::Edge>> bf(N, br);
+          for (auto& uv : br) printf("B %zu %zu\n", (size_t)uv.tail(), (size_t)uv.head());
+          OpenIter it(N, br), end(N, br, true);
+          int guard = 0;
+          for (; it != end && guard < 100000; ++it, ++guard) {
+            std::vector<std::pair<size_t, size_t>> ed;
+            for (auto& uv : it.edges()) ed.emplace_back((size_t)uv.tail(), (size_t)uv.head());
+            std::sort(ed.begin(), ed.end());
+            printf("C");
+            for (auto& p : ed) printf(" %zu,%zu", p.first, p.second);
+            printf("\n");
+          }
         } catch (...) { printf("EXC\n"); }
         fflush(stdout); _exit(0);
       }

@@ -7,6 +7,9 @@
 #include "../../phylo_tools_b200/include/pt/containment.hpp"
 #include "../../phylo_tools_b200/include/pt/io.hpp"
 #include "../../phylo_tools_b200/include/pt/lca.hpp"
+#include "../../phylo_tools_b200/include/pt/bridges.hpp"
+#include <algorithm>
+#include <fstream>
 
 using namespace PT;
 using MyTree = ROTree<>;
@@ -21,7 +24,31 @@ static bool tc(const std::string& host, const std::string& guest) {
   return c.displayed();
 }
 
-int main() {
+// `test_facade bcc <file>`: one network per line; prints the bridges in post-order ("B tail head") and the components of
+// BiconnectedComponents ("C" + sorted edges), then "--": the format of oracle/_ref/ref_tc bcc, compared by tests/test_cli.py
+static int bcc_mode(const char* path) {
+  std::ifstream in(path);
+  std::string line;
+  while (std::getline(in, line)) {
+    if (line.empty()) continue;
+    EdgeVec e; auto l = std::make_shared<LabelMapDefault>();
+    const size_t n = parse_newick(line, e, l);
+    RONetwork<> N(e, l, consecutive_tag(), n);
+    for (const auto& uv : list_bridges(N)) std::cout << "B " << uv.first << " " << uv.second << "\n";
+    for (const auto& comp : BiconnectedComponents<RONetwork<>>(N)) {
+      std::vector<std::pair<Node, Node>> ed(comp.begin(), comp.end());
+      std::sort(ed.begin(), ed.end());
+      std::cout << "C";
+      for (const auto& p : ed) std::cout << " " << p.first << "," << p.second;
+      std::cout << "\n";
+    }
+    std::cout << "--\n";
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc >= 3 && std::string(argv[1]) == "bcc") return bcc_mode(argv[2]);
   // data/test.nw of the reference: ground truth "not displayed" (the reference itself crashes on it)
   assert(!tc("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));"));
   assert(tc("((a,(b)#H1),(#H1,c));", "(a,(b,c));"));

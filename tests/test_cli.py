@@ -64,3 +64,24 @@ def test_tc_cli_protocol(tools, tmp_path):
 def test_cpp_facade(tools):
     r = subprocess.run([FACADE], capture_output=True, text=True)
     assert r.returncode == 0 and "facade ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_bridges_and_components_in_reference_order(tools, tmp_path):
+    """pt/bridges.hpp over pt_net_bridges: bridges in the post-order of the reference BridgeFinder (utils/bridges.hpp:73-103) and
+    the components its BiconnectedComponents iterator yields (utils/biconnected_comps.hpp:34-96), pinned by
+    tests/golden/bcc_ref.json (generated from the reference itself, oracle/make_golden.py make_bcc)"""
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "bcc_ref.json")))
+    items = [it for it in gold["items"] if "bridges" in it]
+    assert len(items) >= 40
+    f = tmp_path / "nets.nw"
+    f.write_text("".join(it["newick"] + "\n" for it in items))
+    r = subprocess.run([FACADE, "bcc", str(f)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    blocks = [b.strip("\n").split("\n") for b in r.stdout.split("--\n")][:len(items)]
+    for it, b in zip(items, blocks):
+        bridges = [list(map(int, x.split()[1:])) for x in b if x.startswith("B ")]
+        comps = [[list(map(int, e.split(","))) for e in x.split()[1:]] for x in b if x.startswith("C")]
+        assert bridges == it["bridges"], it["newick"]
+        assert comps == it["components"], it["newick"]
