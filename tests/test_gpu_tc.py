@@ -85,7 +85,8 @@ def test_tree_in_tree_and_degenerate(pt, oracle):
     assert truth == [1, 0, 1, 0, 1, 0, 1, 0, 1, 1, 1, 1, 1, 0]
 
 
-def test_error_statuses_do_not_poison_the_batch(pt):
+@pytest.mark.parametrize("path", [0, 2, 3])
+def test_error_statuses_do_not_poison_the_batch(pt, path):
     p = pt.Packer()
     p.add_generated(3, 8, 2, 5, 0)
     a = p.arrays()
@@ -98,7 +99,7 @@ def test_error_statuses_do_not_poison_the_batch(pt):
     ab = int(a["host_arc_off"][2])
     a["host_succ_adj"][ab + 5] = 0
     b = pt.Batch(a)
-    v, s, c = b.contain()
+    v, s, c = b.contain(path=path)
     b.free()
     assert s.tolist()[0] == 0 and v[0]
     assert s[1] == 1        # PT_INST_MULTILABEL
@@ -106,13 +107,14 @@ def test_error_statuses_do_not_poison_the_batch(pt):
     assert c["errors"] == 2
 
 
-def test_pool_overflow_is_reported(pt, oracle):
+@pytest.mark.parametrize("path", [0, 3])
+def test_pool_overflow_is_reported(pt, oracle, path):
     p = pt.Packer()
     p.add_generated(400, 16, 7, 777, 0)
     b = pt.Batch(p.arrays())
-    v, s, c = b.contain()
+    v, s, c = b.contain(path=path)
     assert (s == 0).all() and v.all() and c["branched"] > 4
-    v2, s2, c2 = b.contain(pool_slots=2)
+    v2, s2, c2 = b.contain(pool_slots=2, path=path)
     b.free()
     assert ((s2 == 0) | (s2 == 4)).all() and (s2 == 4).sum() >= 1   # PT_INST_POOL_OVERFLOW, never a wrong verdict
     assert v2[s2 == 0].all()
