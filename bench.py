@@ -191,13 +191,15 @@ def cpu_baseline_leg(pt, sample_seconds=15.0):
                       % (cores * per, per, disp, cores * per, sum(single) / len(single))}
 
 
-def lca_leg(pt, torch, leaves, queries, peak):
+def lca_leg(pt, torch, leaves, queries, peak, rank=0, world=1, dist=None):
+    """BASELINE configs[2]; with N ranks the table is replicated (built on every GPU) and every rank answers its own `queries`
+    (weak scaling, no data-path collective): aggregate = N * queries / max over ranks of the batch time"""
     par = pt.random_tree(leaves, SEED)
     n = len(par)
     dpar = torch.from_numpy(par).cuda()
     lca = pt.Lca(dpar)
     info = lca.info()
-    g = torch.Generator(device="cuda").manual_seed(1)
+    g = torch.Generator(device="cuda").manual_seed(1 + rank)
     u = torch.randint(0, n, (queries,), generator=g, device="cuda", dtype=torch.int32)
     v = torch.randint(0, n, (queries,), generator=g, device="cuda", dtype=torch.int32)
     out = torch.empty_like(u)
@@ -217,12 +219,16 @@ def lca_leg(pt, torch, leaves, queries, peak):
     avg = tot / reps
     checksum = int(out.long().sum().item())
     lca.free()
-    qps = queries / (avg / 1000.0)
+    if world > 1:
+        t = torch.tensor([avg, best], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        avg, best = float(t[0].item()), float(t[1].item())
+    qps = world * queries / (avg / 1000.0)
     ach = LCA_BYTES_PER_QUERY * qps / 1e9
-    return {"workload": "batched LCA: %d queries on a %d-leaf random binary tree (BASELINE configs[2])" % (queries, leaves),
-            "queries_per_s": qps, "ms_per_batch": avg, "best_ms": best, "build_ms": info["build_ms"], "levels": info["num_levels"],
+    return {"workload": "batched LCA: %d queries per GPU on a %d-leaf random binary tree (BASELINE configs[2])" % (queries, leaves),
+            "n_gpus": world, "scaling": "weak (table replicated, queries sharded, no collective)", "queries_per_s": qps, "ms_per_batch": avg, "best_ms": best, "build_ms": info["build_ms"], "levels": info["num_levels"],
             "resident_bytes": info["device_bytes"], "checksum": checksum,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("lca_query_kernel", queries),
+            "roofline": {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak, "traffic": measured_traffic("lca_query_kernel", queries),
                          "model": "40 B/query (SURVEY 8(d)); this layout needs 2 random records per query and B200 moves a 128-byte line per random read (profiles/micro_gather.cu): 254 B/query measured, ceiling ~25 G queries/s"}}
 
 
@@ -255,7 +261,7 @@ def config4_leg(pt, torch, count):
             "note": "one thread-block cluster per instance, workspace in global memory; the reference cannot run this size (extrapolated 3e5 s per instance, BASELINE.md)"}
 
 
-def config5_leg(pt, retis=24, leaves=30):
+def config5_leg(pt, retis=24, leaves=30, rank=0, world=1, dist=None, torch=None):
     """BASELINE configs[4]: exhaustive 2^r switching enumeration of one general network (guest = random tree: not displayed,
     so the whole index space is visited)"""
     p = pt.Packer()
@@ -263,11 +269,19 @@ def config5_leg(pt, retis=24, leaves=30):
     a = p.arrays()
     args = (a["host_succ_off"], a["host_succ_adj"], a["host_label"], a["guest_parent"], a["guest_label"])
     pt.enum_switchings(*args, begin=0, end=1 << 16)  # warm-up
+    total = 1 << retis  # binary network: in-degree 2 at every reticulation
+    lo, hi = total * rank // world, total * (rank + 1) // world  # contiguous sub-ranges of [0, 2^r), one reduction
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    tot, nd, first = pt.enum_switchings(*args)
+    tot, nd, first = pt.enum_switchings(*args, begin=lo, end=hi) if world > 1 else pt.enum_switchings(*args)
     dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([float(tot), float(nd)], dtype=torch.float64, device="cuda"); m = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM); dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        tot, nd, dt = int(tot), int(t[1].item()), float(m[0].item())  # n_switchings is the size of the whole index space on every rank
     return {"workload": "exhaustive switching enumeration, gen network l=%d r=%d, random guest tree (BASELINE configs[4])" % (leaves, retis),
-            "switchings": tot, "displaying": nd, "seconds": dt, "switchings_per_s": tot / dt, "host_nodes": int(a["host_node_off"][1]),
+            "n_gpus": world, "switchings": tot, "displaying": nd, "seconds": dt, "switchings_per_s": tot / dt, "host_nodes": int(a["host_node_off"][1]),
             "note": "wall time of pt_enum_switchings incl. upload; bound by integer ALU + L1-resident accumulators, not HBM"}
 
 
@@ -445,10 +459,12 @@ def main():
            "host_generation_s": t_gen}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg(pt)
-    if rank == 0 and not args.no_lca:
+    if not args.no_lca:  # every rank: queries are sharded
         try:
-            out["lca"] = lca_leg(pt, torch, args.lca_leaves, args.lca_queries, peak)
+            out["lca"] = lca_leg(pt, torch, args.lca_leaves, args.lca_queries, peak, rank, world, dist if world > 1 else None)
         except Exception as ex:  # the secondary leg must not take the headline line down
+            if world > 1:
+                raise
             out["lca"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -460,10 +476,12 @@ def main():
             out["config4"] = config4_leg(pt, torch, args.config4_instances)
         except Exception as ex:
             out["config4"] = {"error": repr(ex)}
-    if rank == 0 and not args.no_config5:
+    if not args.no_config5:  # every rank: the index range is sharded
         try:
-            out["config5"] = config5_leg(pt)
+            out["config5"] = config5_leg(pt, rank=rank, world=world, dist=dist if world > 1 else None, torch=torch)
         except Exception as ex:
+            if world > 1:
+                raise
             out["config5"] = {"error": repr(ex)}
     if world > 1:
         dist.barrier()
