@@ -36,6 +36,25 @@ L, R = 100, 20
 SEED = 0xB200
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """one process per GPU: run on the CPU cores next to that GPU, so that the pinned staging buffers of the end-to-end path are
+    first-touched on its NUMA node (8 ranks uploading through one node's memory halve the end-to-end rate)"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_traffic(kernel, units):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r01.json), only when the
     launch here processes the same number of units as the captured one; else None"""
@@ -336,6 +355,7 @@ def main():
 
     if pt.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned allocation (first touch)
     torch.cuda.set_device(local_rank)
     pt.set_device(local_rank)
     if world > 1:
@@ -451,7 +471,8 @@ def main():
                       "instances_per_gpu": B, "leaves": L, "reticulations": R, "host_nodes": 2 * R + 2 * L - 1, "generator_seed": SEED,
                       "input_layout": "int32 arrays" if args.int32_input else "int16 arrays (pt_batch_desc.index_bytes = 2)",
                       "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" % (in_bytes_actual / 1e6),
-                      "parallelism": "instances sharded %d-way, one all-reduce of result words" % world if world > 1 else "single GPU"},
+                      "parallelism": "instances sharded %d-way, one all-reduce of result words" % world if world > 1 else "single GPU",
+                      "cpu_affinity": ("%d cores next to the GPU" % numa) if numa else "default"},
            "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": words * 4 + B,
                    "api": "pt_batch_create(HOST pinned) + pt_batch_contain(HOST outputs) + pt_batch_free", "displayed": e2e_disp},
            "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline,
