@@ -92,6 +92,37 @@ int pt_tree_who_displays(const int32_t* host_parent, const int32_t* host_label, 
                          const int32_t* guest_label, int64_t nt, int32_t* out_host_node, pt_mem mem, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Network isomorphism -- replaces  make_iso_mapper(N0, N1, flags).check_isomorph()
+ *                                  utils/isomorphism.hpp:33-324 (examples/iso.cpp:96-112, the `iso` tool)
+ * for P pairs of networks at once.  Graph g = 2 * pair + side owns the slices given by node_off / arc_off
+ * ([2P+1] prefix sums); succ_off / pred_off have n_g + 1 entries per graph starting at node_off[g] + g (LOCAL arc
+ * positions), succ_adj / pred_adj m_g LOCAL node ids (children / parents), label a dense id shared by the two
+ * networks of a pair or -1.  flags = which labels have to match (FLAG_MAP_* utils/isomorphism.hpp:10-13); the `iso`
+ * tool's default is PT_ISO_LEAF_LABELS.  Result bit p = 1 iff the two networks of pair p are isomorphic (arc- and
+ * label-preserving bijection): exact -- positives are verified arc by arc, negatives follow from invariants.
+ * status[p]: PT_INST_OK, PT_INST_BAD_GRAPH (index out of range), PT_INST_TOO_LARGE (more than 4 096 nodes per
+ * network), PT_INST_POOL_OVERFLOW (too many tied sub-problems).
+ * ---------------------------------------------------------------------------------------------- */
+#define PT_ISO_LEAF_LABELS 0x01
+#define PT_ISO_TREE_LABELS 0x02
+#define PT_ISO_RETI_LABELS 0x04
+#define PT_ISO_ALL_LABELS 0x07
+typedef struct pt_iso_desc {
+  int64_t num_pairs;
+  pt_mem mem;                /* where the arrays below live */
+  const int64_t* node_off;   /* [2P+1] */
+  const int64_t* arc_off;    /* [2P+1] */
+  const int32_t* succ_off;
+  const int32_t* succ_adj;
+  const int32_t* pred_off;
+  const int32_t* pred_adj;
+  const int32_t* label;
+  int32_t flags;
+  int32_t max_nodes;         /* largest network of the batch; 0 = compute (HOST input only) */
+} pt_iso_desc;
+int pt_iso_batch(const pt_iso_desc* d, uint32_t* result_bits, uint8_t* status, pt_mem out_mem, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Bridges -- replaces  BridgeFinder / list_bridges(N, root)   utils/bridges.hpp:42-128
  *            (Network::get_bridges utils/network.hpp:85-88; consumer: the bridge-separated components that
  *             utils/biconnected_comps.hpp:15-120 iterates)

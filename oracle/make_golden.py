@@ -228,6 +228,39 @@ def make_bcc():
     print("bcc_ref.json:", len(items), "networks,", crashed, "reference crashes")
 
 
+def make_iso():
+    """pairs of networks -> verdict of the REFERENCE IsomorphismMapper (oracle/_ref/ref_tc iso, default flags = leaf labels) and the
+    truth by definition (oracle/pt_oracle.c orc_iso).  Variants of generated networks: children / hybrid numbering shuffled
+    (isomorphic), two leaf labels swapped, one reticulation arc moved, and unrelated networks of the same size."""
+    import random
+    from oracle.newick import parse_newick, write_newick
+    rnd = random.Random(20261020)
+    pairs = [("(a,(((b)#H1,(c)#H2),(#H1,#H2)),d);", "(d,(((b)#H1,(c)#H2),(#H1,#H2)),a);", "data/nets.nw"),
+             ("((a,b),(c,d));", "((d,c),(b,a));", "tree mirrored"), ("((a,b),(c,d));", "((a,c),(b,d));", "tree, other pairs"),
+             ("((a,(b)#H1),(#H1,c));", "((c,(b)#H1),(#H1,a));", "one reticulation mirrored"), ("((a,(b)#H1),(#H1,c));", "((b,(a)#H1),(#H1,c));", "leaf under the reticulation changed")]
+    for (l, r, cnt) in [(4, 1, 6), (6, 2, 10), (9, 3, 10), (12, 4, 8), (16, 6, 6)]:
+        nets = [h for h, _ in gen_pairs(cnt + 1, l, r, 9500 + l, 0)]
+        for i in range(cnt):
+            n, e, lab = parse_newick(nets[i])
+            e2 = list(e); rnd.shuffle(e2)
+            pairs.append((nets[i], write_newick(n, e2, lab), "gen l=%d r=%d shuffled" % (l, r)))
+            leaves = sorted(v for v in lab if lab[v] != "")
+            a, b = rnd.sample(leaves, 2)
+            lab2 = dict(lab); lab2[a], lab2[b] = lab[b], lab[a]
+            pairs.append((nets[i], write_newick(n, e2, lab2), "gen l=%d r=%d two labels swapped" % (l, r)))
+            pairs.append((nets[i], nets[i + 1], "gen l=%d r=%d unrelated" % (l, r)))
+    lines = [x for a, b, _ in pairs for x in (a, b)]
+    ref = run_lines(REF_TC, "iso", lines).strip()
+    assert len(ref) == len(pairs), (len(ref), len(pairs))
+    items = []
+    for (a, b, tag), rv in zip(pairs, ref):
+        items.append(dict(a=a, b=b, tag=tag, reference=rv, truth=O.iso_newick(a, b)))
+    agree = sum(1 for it in items if it["reference"] == str(it["truth"]))
+    json.dump(dict(source="oracle/_ref/ref_tc iso (reference utils/isomorphism.hpp, flags = FLAG_MAP_LEAF_LABELS) + oracle/pt_oracle.c orc_iso",
+                   reference_agrees=agree, items=items), open(os.path.join(GOLD, "iso_ref.json"), "w"), indent=0)
+    print("iso_ref.json:", len(items), "pairs,", agree, "where the reference agrees with the definition;", sum(it["truth"] for it in items), "isomorphic")
+
+
 def pt_name(i):
     s = ""
     while True:
@@ -245,3 +278,4 @@ if __name__ == "__main__":
     make_who()
     make_bridges()
     make_bcc()
+    make_iso()

@@ -101,3 +101,42 @@ def parse_newick(s):
         st["back"] -= 1
         read_subtree()
     return st["n"], edges, labels
+
+
+def write_newick(n, edges, labels):
+    """extended Newick of a rooted DAG given as (n, [(tail, head)], {node: name}); a node with several parents is written out
+    below the first parent that reaches it (as `(...)name#Hk`) and referenced as `#Hk` below the others (the format
+    io/newick.hpp:29-55 writes and :64-272 reads).  Children are written in the order of `edges`."""
+    ch = [[] for _ in range(n)]
+    indeg = [0] * n
+    for t, h in edges:
+        ch[t].append(h); indeg[h] += 1
+    roots = [v for v in range(n) if indeg[v] == 0]
+    assert len(roots) == 1, "need exactly one root"
+    hyb, done = {}, set()
+    out = []
+
+    def name(v):
+        s = labels.get(v, "") if isinstance(labels, dict) else labels[v]
+        if indeg[v] >= 2:
+            s += "#H%d" % hyb.setdefault(v, len(hyb) + 1)
+        return s
+    # iterative DFS
+    stack = [(roots[0], 0)]
+    while stack:
+        v, k = stack.pop()
+        if k == 0 and indeg[v] >= 2 and v in done:
+            out.append(name(v)); continue
+        if k == 0:
+            done.add(v)
+            if ch[v]:
+                out.append("(")
+        if k < len(ch[v]):
+            if k > 0:
+                out.append(",")
+            stack.append((v, k + 1)); stack.append((ch[v][k], 0))
+        else:
+            if ch[v]:
+                out.append(")")
+            out.append(name(v))
+    return "".join(out) + ";"

@@ -318,3 +318,80 @@ int orc_bridges(int n, int m, const int32_t* tail, const int32_t* head, uint8_t*
   free(off); free(adj); free(aid); free(pos); free(seen); free(stk);
   return count;
 }
+
+/* ---- network isomorphism: utils/isomorphism.hpp:33-324 (IsomorphismMapper::check_isomorph), examples/iso.cpp:96-112 ------
+ * The reference keeps a set of possible images per node, propagates along arcs and branches on a node with several
+ * possibilities.  Restated from the DEFINITION: is there a bijection phi of the nodes with (u,v) an arc <=> (phi u, phi v) an
+ * arc, and label(u) == label(phi u) for every node whose label counts under `flags` (0x01 leaves, 0x02 internal tree nodes,
+ * 0x04 internal reticulations: FLAG_MAP_* :10-13)?  Plain backtracking over the nodes in an order in which every node but
+ * the first follows a neighbour, candidates filtered by degrees, counted label and the arcs to already mapped nodes.
+ * lab*: dense label ids shared by the two networks, -1 = unlabelled.  returns 1 / 0. */
+typedef struct {
+  int n, m; const int32_t *t1, *h1, *l1, *t2, *h2, *l2; int flags;
+  int32_t *so1, *sa1, *po1, *pa1, *so2, *sa2, *po2, *pa2, *order, *map, *inv;
+} orc_iso_ctx;
+static void iso_csr(int n, int m, const int32_t* key, const int32_t* val, int32_t* off, int32_t* adj) {
+  memset(off, 0, (size_t)(n + 1) * 4);
+  for (int e = 0; e < m; ++e) off[key[e] + 1]++;
+  for (int v = 0; v < n; ++v) off[v + 1] += off[v];
+  int32_t* pos = (int32_t*)malloc((size_t)(n + 1) * 4); memcpy(pos, off, (size_t)(n + 1) * 4);
+  for (int e = 0; e < m; ++e) adj[pos[key[e]]++] = val[e];
+  free(pos);
+}
+static int iso_has(const int32_t* off, const int32_t* adj, int u, int v) { int c = 0; for (int k = off[u]; k < off[u + 1]; ++k) c += adj[k] == v; return c; }
+static int iso_label(const orc_iso_ctx* c, int side, int v) {
+  const int32_t* so = side ? c->so2 : c->so1; const int32_t* po = side ? c->po2 : c->po1; const int32_t* l = side ? c->l2 : c->l1;
+  const int od = so[v + 1] - so[v], id = po[v + 1] - po[v];
+  const int counts = od == 0 ? (c->flags & 1) : (id >= 2 ? (c->flags & 4) : (c->flags & 2));
+  return counts ? l[v] : -1;
+}
+static int iso_rec(orc_iso_ctx* c, int k) {
+  if (k == c->n) return 1;
+  const int u = c->order[k];
+  for (int v = 0; v < c->n; ++v) {
+    if (c->inv[v] >= 0) continue;
+    if (c->so1[u + 1] - c->so1[u] != c->so2[v + 1] - c->so2[v] || c->po1[u + 1] - c->po1[u] != c->po2[v + 1] - c->po2[v]) continue;
+    if (iso_label(c, 0, u) != iso_label(c, 1, v)) continue;
+    int ok = 1;
+    for (int j = c->so1[u]; ok && j < c->so1[u + 1]; ++j) { const int w = c->sa1[j]; if (c->map[w] >= 0 && iso_has(c->so1, c->sa1, u, w) != iso_has(c->so2, c->sa2, v, c->map[w])) ok = 0; }
+    for (int j = c->po1[u]; ok && j < c->po1[u + 1]; ++j) { const int w = c->pa1[j]; if (c->map[w] >= 0 && iso_has(c->so1, c->sa1, w, u) != iso_has(c->so2, c->sa2, c->map[w], v)) ok = 0; }
+    /* arcs of v towards already used images must have a preimage arc too (degrees are equal, so counting one direction suffices
+       once every neighbour is mapped; checked here for early pruning) */
+    for (int j = c->so2[v]; ok && j < c->so2[v + 1]; ++j) { const int w = c->inv[c->sa2[j]]; if (w >= 0 && !iso_has(c->so1, c->sa1, u, w)) ok = 0; }
+    for (int j = c->po2[v]; ok && j < c->po2[v + 1]; ++j) { const int w = c->inv[c->pa2[j]]; if (w >= 0 && !iso_has(c->so1, c->sa1, w, u)) ok = 0; }
+    if (!ok) continue;
+    c->map[u] = v; c->inv[v] = u;
+    if (iso_rec(c, k + 1)) return 1;
+    c->map[u] = -1; c->inv[v] = -1;
+  }
+  return 0;
+}
+int orc_iso(int n1, int m1, const int32_t* tail1, const int32_t* head1, const int32_t* lab1,
+            int n2, int m2, const int32_t* tail2, const int32_t* head2, const int32_t* lab2, int flags) {
+  if (n1 != n2 || m1 != m2) return 0;
+  if (n1 == 0) return 1;
+  const int n = n1, m = m1;
+  orc_iso_ctx c; c.n = n; c.m = m; c.t1 = tail1; c.h1 = head1; c.l1 = lab1; c.t2 = tail2; c.h2 = head2; c.l2 = lab2; c.flags = flags;
+  int32_t* buf = (int32_t*)malloc((size_t)(4 * (n + 1) + 4 * (m + 1) + 3 * n + 8) * 4);
+  int32_t* p = buf;
+  c.so1 = p; p += n + 1; c.po1 = p; p += n + 1; c.so2 = p; p += n + 1; c.po2 = p; p += n + 1;
+  c.sa1 = p; p += m + 1; c.pa1 = p; p += m + 1; c.sa2 = p; p += m + 1; c.pa2 = p; p += m + 1;
+  c.order = p; p += n; c.map = p; p += n; c.inv = p;
+  iso_csr(n, m, tail1, head1, c.so1, c.sa1); iso_csr(n, m, head1, tail1, c.po1, c.pa1);
+  iso_csr(n, m, tail2, head2, c.so2, c.sa2); iso_csr(n, m, head2, tail2, c.po2, c.pa2);
+  /* order: breadth-first over the undirected graph from every yet unseen node */
+  int cnt = 0; uint8_t* seen = (uint8_t*)calloc((size_t)n, 1);
+  for (int s = 0; s < n; ++s) {
+    if (seen[s]) continue;
+    seen[s] = 1; c.order[cnt++] = s;
+    for (int q = cnt - 1; q < cnt; ++q) {
+      const int u = c.order[q];
+      for (int j = c.so1[u]; j < c.so1[u + 1]; ++j) if (!seen[c.sa1[j]]) { seen[c.sa1[j]] = 1; c.order[cnt++] = c.sa1[j]; }
+      for (int j = c.po1[u]; j < c.po1[u + 1]; ++j) if (!seen[c.pa1[j]]) { seen[c.pa1[j]] = 1; c.order[cnt++] = c.pa1[j]; }
+    }
+  }
+  for (int v = 0; v < n; ++v) { c.map[v] = -1; c.inv[v] = -1; }
+  const int r = iso_rec(&c, 0);
+  free(seen); free(buf);
+  return r;
+}

@@ -43,6 +43,8 @@ def lib():
         L.orc_bridges.argtypes = [C.c_int, C.c_int, i32p, i32p, C.POINTER(C.c_uint8)]
         L.orc_who_displays.restype = C.c_int
         L.orc_who_displays.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p, i32p, i32p]
+        L.orc_iso.restype = C.c_int
+        L.orc_iso.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int]
     return _LIB
 
 
@@ -115,6 +117,30 @@ def bridges(n, edges):
     out = np.zeros(max(len(t), 1), dtype=np.uint8)
     lib().orc_bridges(int(n), len(t), _p(t), _p(h), out.ctypes.data_as(C.POINTER(C.c_uint8)))
     return out[:len(t)].astype(bool)
+
+
+def iso(n1, edges1, labels1, n2, edges2, labels2, flags=1):
+    """network isomorphism by definition (backtracking); labels*: dense ids shared by both networks, -1 = none;
+    flags: 1 leaf labels count, 2 internal tree nodes, 4 internal reticulations (utils/isomorphism.hpp:10-13)"""
+    e1, e2 = _arr(edges1).reshape(-1, 2), _arr(edges2).reshape(-1, 2)
+    t1, h1, t2, h2 = _arr(e1[:, 0]), _arr(e1[:, 1]), _arr(e2[:, 0]), _arr(e2[:, 1])
+    l1, l2 = _arr(labels1), _arr(labels2)
+    return int(lib().orc_iso(int(n1), len(t1), _p(t1), _p(h1), _p(l1), int(n2), len(t2), _p(t2), _p(h2), _p(l2), int(flags)))
+
+
+def iso_newick(nw1, nw2, flags=1):
+    """the same for two extended-Newick strings (label strings -> shared dense ids)"""
+    from .newick import parse_newick
+    n1, e1, lab1 = parse_newick(nw1)
+    n2, e2, lab2 = parse_newick(nw2)
+    ids = {}
+    def enc(n, lab):
+        out = np.full(n, -1, dtype=np.int32)
+        for v, name in lab.items():
+            if name != "":
+                out[int(v)] = ids.setdefault(name, len(ids))
+        return out
+    return iso(n1, e1, enc(n1, lab1), n2, e2, enc(n2, lab2), flags)
 
 
 def who_displays(host_parent, host_label, guest_parent, guest_label):

@@ -12,6 +12,8 @@
 //   ref_tc who <file> : tree/tree pairs; prints who_displays(u) of the reference for every guest node
 //   ref_tc bcc <file> : per network line: the bridges in the reference's post-order ("B tail head"), then every component the
 //        reference's BiconnectedComponents iterator yields ("C" + its edges, sorted), then "--"
+//   ref_tc iso <file> [flags] : pairs of network lines; one char per pair: 1 isomorph / 0 not (make_iso_mapper(...).check_isomorph(),
+//        examples/iso.cpp:96-112; flags as FLAG_MAP_* utils/isomorphism.hpp:10-13, default 1), E exception, S signal
 //   ref_tc parse <file> : for each line: "n m" then edges "u v" in reference edge-list order, then
 //        labels "id name" sorted by id, then "--" (golden vectors for the Newick reader).
 #include "io/io.hpp"
@@ -22,6 +24,7 @@
 #include "utils/containment.hpp"
 #include "utils/bridges.hpp"
 #include "utils/biconnected_comps.hpp"
+#include "utils/isomorphism.hpp"
 
 #include <chrono>
 #include <fstream>
@@ -156,6 +159,37 @@ int main(int argc, char** argv) {
       if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) printf("CRASH\n");
       printf("--\n");
     }
+    return 0;
+  }
+  if (mode == "iso") {
+    const unsigned char flags = argc > 3 ? (unsigned char)atoi(argv[3]) : (unsigned char)FLAG_MAP_LEAF_LABELS;
+    std::cout.setstate(std::ios::badbit);
+    std::string out;
+    for (size_t i = 0; i + 1 < L.size(); i += 2) {
+      int fd[2]; if (pipe(fd)) return 3;
+      pid_t pid = fork();
+      if (pid == 0) {
+        close(fd[0]);
+        char c = 'E';
+        try {
+          ENL a, b; parse_line(L[i], a); parse_line(L[i + 1], b);
+          RONetwork<> N0(a.edges, *a.labels, consecutive_tag());
+          RONetwork<> N1(b.edges, *b.labels, consecutive_tag());
+          auto M = make_iso_mapper(N0, N1, flags);
+          c = M.check_isomorph() ? '1' : '0';
+        } catch (...) { c = 'E'; }
+        if (write(fd[1], &c, 1) != 1) _exit(2);
+        _exit(0);
+      }
+      close(fd[1]);
+      char c = 'S';
+      if (read(fd[0], &c, 1) != 1) c = 'S';
+      close(fd[0]);
+      int st = 0; waitpid(pid, &st, 0);
+      out.push_back(c);
+    }
+    std::cout.clear();
+    printf("%s\n", out.c_str());
     return 0;
   }
   if (mode == "who") {

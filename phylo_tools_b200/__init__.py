@@ -315,3 +315,67 @@ def enum_switchings(succ_off, succ_adj, host_label, guest_parent, guest_label, b
     _check(_L.pt_enum_switchings(len(a[2]), len(a[1]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[3]), a[3].ctypes.data, a[4].ctypes.data,
                                  begin, end, 1 if stop_at_first else 0, C.byref(tot), C.byref(nd), C.byref(fi), None), "pt_enum_switchings")
     return tot.value, nd.value, (None if fi.value == 2**64 - 1 else fi.value)
+
+
+def _csr(n, keys, vals):
+    """CSR of `vals` grouped by `keys` (stable): (off[n+1], adj[m]) as int32"""
+    keys, vals = np.asarray(keys, dtype=np.int64), np.asarray(vals, dtype=np.int32)
+    off = np.zeros(n + 1, dtype=np.int32)
+    if len(keys):
+        np.add.at(off, keys + 1, 1)
+    off = np.cumsum(off, dtype=np.int64).astype(np.int32)
+    order = np.argsort(keys, kind="stable")
+    return off, vals[order].astype(np.int32)
+
+
+def iso_arrays(networks):
+    """[(n, edges, labels) ...] with labels as dense ids (or -1), two consecutive entries per pair -> dict keyed like pt_iso_desc"""
+    node_off, arc_off = [0], [0]
+    so, sa, po, pa, lab = [], [], [], [], []
+    for n, edges, labels in networks:
+        e = np.asarray(edges, dtype=np.int32).reshape(-1, 2)
+        o, a = _csr(n, e[:, 0], e[:, 1])
+        so.append(o); sa.append(a)
+        o, a = _csr(n, e[:, 1], e[:, 0])
+        po.append(o); pa.append(a)
+        lab.append(np.asarray(labels, dtype=np.int32))
+        node_off.append(node_off[-1] + n); arc_off.append(arc_off[-1] + len(e))
+    cat = lambda xs: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0, np.int32), dtype=np.int32)
+    return dict(num_pairs=len(networks) // 2, node_off=np.asarray(node_off, dtype=np.int64), arc_off=np.asarray(arc_off, dtype=np.int64),
+                succ_off=cat(so), succ_adj=cat(sa), pred_off=cat(po), pred_adj=cat(pa), label=cat(lab),
+                max_nodes=max([n for n, _, _ in networks], default=0))
+
+
+def iso_batch(arrays, flags=1):
+    """pt_iso_batch: make_iso_mapper(N0, N1, flags).check_isomorph() (utils/isomorphism.hpp) for a batch of pairs
+    -> (bool verdicts[P], status uint8[P]).  arrays: dict from iso_arrays (numpy = HOST)"""
+    P = int(arrays["num_pairs"])
+    d = _capi.IsoDesc()
+    d.num_pairs = P; d.mem = PT_MEM_HOST; d.flags = int(flags); d.max_nodes = int(arrays.get("max_nodes", 0))
+    keep = {}
+    for k in ("node_off", "arc_off", "succ_off", "succ_adj", "pred_off", "pred_adj", "label"):
+        a = arrays[k]
+        if len(a) == 0:
+            a = np.zeros(1, dtype=a.dtype)
+        keep[k] = a
+        setattr(d, k, a.ctypes.data)
+    bits = np.zeros((P + 31) // 32 + 1, dtype=np.uint32)
+    status = np.zeros(P + 1, dtype=np.uint8)
+    _check(_L.pt_iso_batch(C.byref(d), bits.ctypes.data, status.ctypes.data, PT_MEM_HOST, None), "pt_iso_batch")
+    return np.unpackbits(bits.view(np.uint8), bitorder="little")[:P].astype(bool), status[:P]
+
+
+def iso_newick(pairs, flags=1):
+    """[(newick0, newick1)] -> (bool verdicts, status): the `iso` tool of examples/iso.cpp for a list of pairs (label strings get
+    dense ids shared by the two networks of a pair)"""
+    nets = []
+    for a, b in pairs:
+        ids = {}
+        for s in (a, b):
+            n, edges, labels = parse_newick(s)
+            lab = np.full(n, -1, dtype=np.int32)
+            for v, name in labels.items():
+                if name != "":
+                    lab[v] = ids.setdefault(name, len(ids))
+            nets.append((n, edges, lab))
+    return iso_batch(iso_arrays(nets), flags)

@@ -23,6 +23,12 @@ class BatchDesc(C.Structure):
                 ("index_bytes", C.c_int32)]
 
 
+class IsoDesc(C.Structure):
+    _fields_ = [("num_pairs", C.c_int64), ("mem", C.c_int), ("node_off", C.c_void_p), ("arc_off", C.c_void_p), ("succ_off", C.c_void_p),
+                ("succ_adj", C.c_void_p), ("pred_off", C.c_void_p), ("pred_adj", C.c_void_p), ("label", C.c_void_p),
+                ("flags", C.c_int32), ("max_nodes", C.c_int32)]
+
+
 class Counters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("instances", "displayed", "not_displayed", "errors", "resolved_by_rules", "branched", "work_items", "rounds",
                                           "cherry_reductions", "reticulated_cherries", "arcs_deleted", "rule_passes")]
@@ -83,6 +89,7 @@ def load():
         "pt_packer_get_newick": (C.c_int, [vp, C.c_int64, C.c_char_p, i64p, C.c_char_p, i64p]),
         "pt_packer_free": (C.c_int, [vp]),
         "pt_gen_random_tree": (C.c_int, [C.c_int64, C.c_uint64, i32p]),
+        "pt_iso_batch": (C.c_int, [C.POINTER(IsoDesc), vp, vp, C.c_int, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)  # AttributeError here = the library does not export what include/pt_gpu.h declares
@@ -93,4 +100,4 @@ def load():
 EXPORTED = ["pt_last_error", "pt_abi_version", "pt_device_count", "pt_set_device", "pt_lca_build", "pt_lca_query", "pt_lca_get_info",
             "pt_lca_node_info", "pt_lca_free", "pt_tree_who_displays", "pt_net_bridges", "pt_rmq_build", "pt_rmq_query", "pt_rmq_free", "pt_get_limits", "pt_batch_create",
             "pt_batch_contain", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_parse_newick", "pt_packer_create",
-            "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree"]
+            "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree", "pt_iso_batch"]

@@ -1,0 +1,71 @@
+// tools/iso.cpp -- replacement for examples/iso.cpp of the reference, same command line and output:
+//   iso [-v] [-mr] [-mt] [-ma] [-il] <file1> [file2]
+// two networks (2 lines of extended Newick in file1, or one per file); prints "reading networks...", "checking isomorphism..."
+// and, as the LAST line, "isomorph!" or "not isomorph!" (examples/iso.cpp:66-112); exit code 1 on usage or file errors.
+//   -mr / -mt / -ma : labels of reticulations / internal tree nodes / all nodes have to match;  -il : leaf labels need not match
+//   iso --batch <file> : NEW: many pairs (2 lines each), one verdict per line
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+#include "../include/pt/io.hpp"
+#include "../include/pt/isomorphism.hpp"
+
+using namespace PT;
+using Net = RONetwork<>;
+using ENL = EdgesAndNodeLabels<Net>;
+
+static int usage(const char* argv0) {
+  std::cerr << argv0 << " <file1> [file2]\n\tfile1 and file2 describe two networks (either file1 contains 2 lines of extended newick or both file1 and file2 describe a network in extended newick or edgelist format)\n"
+            << "FLAGS:\n\t-v\tverbose output, prints networks\n\t-mr\tlabels of reticulations have to match\n\t-mt\tlabels of non-leaf tree vertices have to match\n"
+            << "\t-ma\tlabels of all vertices have to match (shortcut for -mr -mt (-ma overrides -il))\n\t-il\tlabels of leaves do NOT have to match\n"
+            << argv0 << " --batch <file>\n\tcheck every pair of lines of <file>; one verdict per line\n";
+  return EXIT_FAILURE;
+}
+
+int main(int argc, char** argv) {
+  bool verbose = false, mr = false, mt = false, ma = false, il = false; std::vector<std::string> files; std::string batch;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "-v") verbose = true; else if (a == "-mr") mr = true; else if (a == "-mt") mt = true; else if (a == "-ma") ma = true; else if (a == "-il") il = true;
+    else if (a == "-h" || a == "--help") { usage(argv[0]); return EXIT_SUCCESS; }
+    else if (a == "--batch") { if (i + 1 >= argc) return usage(argv[0]); batch = argv[++i]; }
+    else if (!a.empty() && a[0] == '-') return usage(argv[0]);
+    else files.push_back(a);
+  }
+  const unsigned char flags = (unsigned char)((!il ? FLAG_MAP_LEAF_LABELS : 0) | (mt ? FLAG_MAP_TREE_LABELS : 0) | (mr ? FLAG_MAP_RETI_LABELS : 0) | (ma ? FLAG_MAP_ALL_LABELS : 0));
+  try {
+    std::vector<ENL> el;
+    if (!batch.empty()) {
+      if (!file_exists(batch)) { std::cerr << batch << " cannot be opened for reading" << std::endl; return EXIT_FAILURE; }
+      read_edgelists(batch, el);
+      if (el.size() % 2) { std::cerr << "odd number of networks in " << batch << std::endl; return EXIT_FAILURE; }
+      std::vector<Net> nets; nets.reserve(el.size());
+      for (auto& e : el) nets.emplace_back(e.edges, e.labels, consecutive_tag(), e.num_nodes);
+      BatchIsomorphism b;
+      for (size_t i = 0; i + 1 < nets.size(); i += 2) b.add(nets[i], nets[i + 1]);
+      b.run(flags);
+      for (size_t i = 0; i < b.size(); ++i) std::cout << (b.isomorph(i) ? "isomorph!" : "not isomorph!") << "\n";
+      return EXIT_SUCCESS;
+    }
+    if (files.empty() || files.size() > 2) return usage(argv[0]);
+    for (const auto& f : files) if (!file_exists(f)) { std::cerr << f << " cannot be opened for reading" << std::endl; return EXIT_FAILURE; }
+    std::cout << "reading networks..." << std::endl;
+    read_edgelists(files[0], el);
+    if (el.empty()) { std::cerr << "could not read any network from " << files[0] << std::endl; return EXIT_FAILURE; }
+    if (el.size() < 2) {
+      if (files.size() < 2) { std::cerr << "could not read 2 networks from " << files[0] << " but no other useable source was found" << std::endl; return EXIT_FAILURE; }
+      read_edgelists(files[1], el);
+      if (el.size() < 2) { std::cerr << "could not read any network from " << files[1] << std::endl; return EXIT_FAILURE; }
+    }
+    Net N0(el[0].edges, el[0].labels, consecutive_tag(), el[0].num_nodes), N1(el[1].edges, el[1].labels, consecutive_tag(), el[1].num_nodes);
+    if (verbose) std::cout << "N0: " << std::endl << get_extended_newick(N0) << std::endl << "N1:" << std::endl << get_extended_newick(N1) << std::endl;
+    std::cout << "checking isomorphism..." << std::endl;
+    std::cout << (make_iso_mapper(N0, N1, flags).check_isomorph() ? "isomorph!" : "not isomorph!") << std::endl;
+  } catch (const std::exception& e) {
+    std::cerr << "error: " << e.what() << std::endl;
+    return EXIT_FAILURE;
+  }
+  return EXIT_SUCCESS;
+}

@@ -85,3 +85,27 @@ def test_bridges_and_components_in_reference_order(tools, tmp_path):
         comps = [[list(map(int, e.split(","))) for e in x.split()[1:]] for x in b if x.startswith("C")]
         assert bridges == it["bridges"], it["newick"]
         assert comps == it["components"], it["newick"]
+
+
+@pytest.mark.gpu
+def test_iso_cli_protocol(tools, tmp_path):
+    """the `iso` replacement (examples/iso.cpp): verdict = last line of stdout, data/nets.nw of the reference is isomorphic"""
+    iso = os.path.join(tools, "iso")
+    f = tmp_path / "nets.nw"
+    f.write_text("(a,(((b)#H1,(c)#H2),(#H1,#H2)),d);\n(d,(((b)#H1,(c)#H2),(#H1,#H2)),a);\n")   # data/nets.nw
+    r = subprocess.run([iso, str(f)], capture_output=True, text=True)
+    lines = r.stdout.strip().split("\n")
+    assert r.returncode == 0 and lines[0] == "reading networks..." and lines[-2] == "checking isomorphism..." and lines[-1] == "isomorph!"
+    g = tmp_path / "one.nw"
+    h = tmp_path / "two.nw"
+    g.write_text("((a,b),(c,d));\n"); h.write_text("((a,c),(b,d));\n")
+    r = subprocess.run([iso, str(g), str(h)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().split("\n")[-1] == "not isomorph!"
+    r = subprocess.run([iso, "-il", str(g), str(h)], capture_output=True, text=True)    # leaf labels need not match: same shape
+    assert r.returncode == 0 and r.stdout.strip().split("\n")[-1] == "isomorph!"
+    r = subprocess.run([iso, str(tmp_path / "missing.nw")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot be opened for reading" in r.stderr
+    b = tmp_path / "batch.nw"
+    b.write_text(f.read_text() + g.read_text() + h.read_text())
+    r = subprocess.run([iso, "--batch", str(b)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().split("\n") == ["isomorph!", "not isomorph!"]

@@ -102,3 +102,18 @@ def test_bridges_restatement_matches_reference(oracle):
         n, e, _ = parse_newick(it["newick"])
         br = oracle.bridges(n, e)
         assert sorted([list(x) for x, b in zip(e, br) if b]) == it["reference"]
+
+
+def test_iso_restatement_matches_reference(oracle):
+    """orc_iso (isomorphism by definition) against the reference IsomorphismMapper on the 125 pinned pairs (tests/golden/iso_ref.json,
+    oracle/_ref/ref_tc iso): it agrees on every pair, and data/nets.nw is isomorphic; the Newick writer used to make the variants
+    round-trips through the reader"""
+    from conftest import load_golden
+    from oracle.newick import write_newick
+    g = load_golden("iso_ref.json")
+    assert len(g["items"]) >= 120 and g["items"][0]["tag"] == "data/nets.nw" and g["items"][0]["reference"] == "1"
+    for it in g["items"]:
+        assert str(oracle.iso_newick(it["a"], it["b"])) == it["reference"] == str(it["truth"]), it["tag"]
+    for it in g["items"][:40]:
+        n, e, lab = parse_newick(it["a"])
+        assert oracle.iso_newick(it["a"], write_newick(n, e, lab), flags=7) == 1
