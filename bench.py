@@ -304,6 +304,33 @@ def config5_leg(pt, retis=24, leaves=30, rank=0, world=1, dist=None, torch=None)
             "note": "wall time of pt_enum_switchings incl. upload; bound by integer ALU + L1-resident accumulators, not HBM"}
 
 
+def iso_leg(pt, pairs=20000):
+    """batched network isomorphism (pt_iso_batch) on pairs of config-2-sized networks: each network against an
+    identical copy (isomorphic) and against the next one (not isomorphic); wall time of the call incl. the upload"""
+    import numpy as np
+    p = pt.Packer()
+    p.add_generated(pairs + 1, L, R, SEED + 6, 0)
+    a = p.arrays()
+    n, m = int(a["host_node_off"][1]), int(a["host_arc_off"][1])
+    so, sa = a["host_succ_off"].reshape(pairs + 1, n + 1), a["host_succ_adj"].reshape(pairs + 1, m)
+    po, pa, lab = a["host_pred_off"].reshape(pairs + 1, n + 1), a["host_pred_adj"].reshape(pairs + 1, m), a["host_label"].reshape(pairs + 1, n)
+
+    def arrays(idx):
+        g = len(idx)
+        c = lambda x: np.ascontiguousarray(x[idx]).ravel()
+        return dict(num_pairs=g // 2, node_off=np.arange(g + 1, dtype=np.int64) * n, arc_off=np.arange(g + 1, dtype=np.int64) * m,
+                    succ_off=c(so), succ_adj=c(sa), pred_off=c(po), pred_adj=c(pa), label=c(lab), max_nodes=n)
+    out = {"workload": "%d pairs of gen networks l=%d r=%d (n = %d), leaf labels have to match" % (pairs, L, R, n)}
+    for name, arr, want in (("isomorphic", arrays(np.repeat(np.arange(pairs), 2)), pairs),
+                            ("not_isomorphic", arrays(np.stack([np.arange(pairs), np.arange(pairs) + 1], axis=1).ravel()), 0)):
+        pt.iso_batch(arr)  # warm-up
+        t0 = time.perf_counter()
+        v, st = pt.iso_batch(arr)
+        dt = time.perf_counter() - t0
+        out[name] = {"pairs_per_s": pairs / dt, "ms": dt * 1e3, "verdicts_ok": bool(int(v.sum()) == want and (st == 0).all())}
+    return out
+
+
 def ingest_leg(pt, pairs=20000):
     """text -> flat arrays: the parallel batch reader on the first `pairs` instances of the workload"""
     p = pt.Packer()
@@ -492,6 +519,11 @@ def main():
             out["newick_ingest"] = ingest_leg(pt)
         except Exception as ex:
             out["newick_ingest"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out["iso"] = iso_leg(pt)
+        except Exception as ex:
+            out["iso"] = {"error": repr(ex)}
     if rank == 0 and not args.no_config4:
         try:
             out["config4"] = config4_leg(pt, torch, args.config4_instances)

@@ -70,8 +70,8 @@ __device__ void iso_sort(u64* key, uint32_t* idx, int NP) {
     }
 }
 
-// pool mode: items come from `src`; batch mode (src.pair == nullptr): item = pair
-__global__ void __launch_bounds__(256) iso_kernel(IsoGraphs G, int64_t num_items, IsoPool src, IsoPool dst, int maxN, int NP, int flags, int depth,
+// pool mode: the num_items sub-problems of `src`; batch mode (src.pair == nullptr): item = pair
+__global__ void __launch_bounds__(256) iso_kernel(IsoGraphs G, int64_t num_items, IsoPool src, IsoPool dst, IsoPool cold, int maxN, int NP, int flags, int depth,
                                                   uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status, int32_t* __restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char iso_smem[];
   // colours c[side][v] (current), k[side][*] (next colours / sort keys, NP each), idx[side][*]
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) iso_kernel(IsoGraphs G, int64_t num_items
   __shared__ int s_item, s_flag, s_cnt;
   __shared__ unsigned long long s_best;
   const int tid = threadIdx.x, nth = blockDim.x;
-  const int64_t total = src.pair ? (int64_t)min(*src.count, src.capacity) : num_items;
+  const int64_t total = num_items;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_item = atomicAdd(ticket, 1);
@@ -191,19 +191,30 @@ __global__ void __launch_bounds__(256) iso_kernel(IsoGraphs G, int64_t num_items
     }
     __syncthreads();
     const int len = (int)(s_best >> 32), kb = (int)(s_best & 0xffffffffu);
-    if (tid == 0) s_item = atomicAdd(dst.count, len);
+    // the first candidate goes to the "hot" pool (searched next: depth first), its siblings to the "cold" one (searched only
+    // if the hot branch fails): for an isomorphic pair whose tied class is an orbit the first descent already succeeds
+    __shared__ int s_cold;
+    if (tid == 0) { s_item = atomicAdd(dst.count, 1); s_cold = atomicAdd(cold.count, len - 1); }
     __syncthreads();
-    const int base = s_item;
-    if (base + len > dst.capacity) { if (tid == 0) status[pair] = ISO_ST_POOL_OVERFLOW; continue; }
+    const int hot_slot = s_item, cold_base = s_cold;
+    if (hot_slot >= dst.capacity || cold_base + len - 1 > cold.capacity) { if (tid == 0) status[pair] = ISO_ST_POOL_OVERFLOW; continue; }
     const int u = (int)i0[kb];
     const u64 fresh = iso_mix(k0[kb] + 0x632BE59BD9B4E019ull * (u64)(depth + 1));
     for (int j = 0; j < len; ++j) {
       const int v = (int)i1[kb + j];
-      u64* pc = dst.colours + (size_t)(base + j) * 2 * maxN;
+      u64* pc = j == 0 ? dst.colours + (size_t)hot_slot * 2 * maxN : cold.colours + (size_t)(cold_base + j - 1) * 2 * maxN;
       for (int x = tid; x < n; x += nth) { pc[x] = x == u ? fresh : c0[x]; pc[maxN + x] = x == v ? fresh : c1[x]; }
-      if (tid == 0) dst.pair[base + j] = pair;
+      if (tid == 0) { if (j == 0) dst.pair[hot_slot] = pair; else cold.pair[cold_base + j - 1] = pair; }
     }
   }
+}
+
+// a pair that some branch proved isomorphic is fine even if another of its branches ran out of pool space
+__global__ void iso_status_kernel(int64_t P, const uint32_t* __restrict__ bits, uint8_t* __restrict__ status, int unresolved_status) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  if ((bits[i >> 5] >> (i & 31)) & 1u) status[i] = ISO_ST_OK;
+  else if (unresolved_status && status[i] == ISO_ST_OK) status[i] = (uint8_t)unresolved_status;
 }
 
 static int iso_upload(void** d, const void* h, size_t bytes, cudaStream_t s) {
@@ -270,30 +281,62 @@ extern "C" int pt_iso_batch(const pt_iso_desc* d, uint32_t* result_bits, uint8_t
     if ((e = cudaMemsetAsync(stat, ISO_ST_TOO_LARGE, (size_t)P, s)) != cudaSuccess) return fail(e, "memset");
   } else if (P > 0) {
     if ((e = cudaFuncSetAttribute(iso_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return fail(e, "cudaFuncSetAttribute");
-    // pools (ping-pong) for the sub-problems of tied colourings
+    // Sub-problems of tied colourings live on a device STACK: every round pops the newest `width` of them, and what they emit
+    // (into a scratch pool) is pushed back on top.  Depth-first in effect: an isomorphic pair with many symmetries (every
+    // candidate of a tied class works) is settled after one descent instead of a breadth that doubles per level, and the
+    // memory is bounded by depth x width.
     const size_t slot_bytes = (size_t)2 * maxN * 8;
-    const int cap = (int)std::max<size_t>(64, std::min<size_t>((size_t)std::max<int64_t>(1024, 4 * P), ((size_t)512 << 20) / slot_bytes));
-    IsoPool pool[2];
-    for (int k = 0; k < 2; ++k) {
-      void *pp = nullptr, *pc = nullptr;
-      if ((rc = dev_alloc(&pp, (size_t)cap * 4)) || (rc = dev_alloc(&pc, slot_bytes * cap))) { if (pp) owned.push_back(pp); cleanup(); return rc; }
-      owned.push_back(pp); owned.push_back(pc);
-      pool[k].pair = (int32_t*)pp; pool[k].colours = (u64*)pc; pool[k].count = ctl + 1 + k; pool[k].capacity = cap;
-    }
     const int ctas_per_sm = std::max(1, std::min(8, (int)((size_t)dp.smem_optin / std::max<size_t>(smem, 1024))));
-    int64_t items = P;
-    IsoPool src{}; src.pair = nullptr;
-    for (int depth = 0; items > 0 && depth <= maxN + 1; ++depth) {
-      const int k = depth & 1;
+    const int width = dp.sms * ctas_per_sm * 2;
+    const int cap_t = (int)std::max<size_t>(64, std::min<size_t>((size_t)std::max<int64_t>(8 * (int64_t)width, 2 * P), ((size_t)256 << 20) / slot_bytes));
+    const int cap_s = (int)std::max<size_t>(64, std::min<size_t>((size_t)std::max<int64_t>(1 << 16, 4 * P), ((size_t)1 << 30) / slot_bytes));
+    IsoPool stack{}, scratch{}, coldp{};
+    {
+      void *sp = nullptr, *sc = nullptr, *tp = nullptr, *tc = nullptr, *cp = nullptr, *cc = nullptr;
+      if ((rc = dev_alloc(&sp, (size_t)cap_s * 4)) == PT_OK) owned.push_back(sp);
+      if (rc == PT_OK && (rc = dev_alloc(&sc, slot_bytes * cap_s)) == PT_OK) owned.push_back(sc);
+      if (rc == PT_OK && (rc = dev_alloc(&tp, (size_t)cap_t * 4)) == PT_OK) owned.push_back(tp);
+      if (rc == PT_OK && (rc = dev_alloc(&tc, slot_bytes * cap_t)) == PT_OK) owned.push_back(tc);
+      if (rc == PT_OK && (rc = dev_alloc(&cp, (size_t)cap_t * 4)) == PT_OK) owned.push_back(cp);
+      if (rc == PT_OK && (rc = dev_alloc(&cc, slot_bytes * cap_t)) == PT_OK) owned.push_back(cc);
+      if (rc) { cleanup(); return rc; }
+      coldp.pair = (int32_t*)cp; coldp.colours = (u64*)cc; coldp.count = ctl + 2; coldp.capacity = cap_t;
+      stack.pair = (int32_t*)sp; stack.colours = (u64*)sc; stack.count = nullptr; stack.capacity = cap_s;
+      scratch.pair = (int32_t*)tp; scratch.colours = (u64*)tc; scratch.count = ctl + 1; scratch.capacity = cap_t;
+    }
+    int64_t top = 0, hot_on_top = 0;
+    int unresolved = 0;  // status for pairs still undecided when the search is cut off
+    const int64_t max_rounds = 200000;
+    for (int64_t round = 0;; ++round) {
+      IsoPool src{}; int64_t items; 
+      if (round == 0) { src.pair = nullptr; items = P; }
+      else {
+        if (top == 0) break;
+        if (round > max_rounds) { unresolved = ISO_ST_POOL_OVERFLOW; break; }
+        items = std::min<int64_t>(hot_on_top > 0 ? hot_on_top : top, width);  // the newest first candidates, else whatever is left
+        src = stack; src.pair = stack.pair + (top - items); src.colours = stack.colours + (size_t)(top - items) * 2 * maxN;
+      }
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(items, (int64_t)dp.sms * ctas_per_sm));
-      iso_kernel<<<grid, 256, smem, s>>>(G, items, src, pool[k], maxN, NP, d->flags, depth, bits, stat, ctl);
+      iso_kernel<<<grid, 256, smem, s>>>(G, items, src, scratch, coldp, maxN, NP, d->flags, (int)(round & 0x3fffffff), bits, stat, ctl);
       if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "iso_kernel launch");
       int32_t h[4];
       if ((e = cudaMemcpyAsync(h, ctl, 16, cudaMemcpyDeviceToHost, s)) != cudaSuccess || (e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "iso_kernel");
-      items = std::min<int64_t>(h[1 + k], cap);
-      src = pool[k];
-      if ((e = cudaMemsetAsync(ctl, 0, 4, s)) != cudaSuccess || (e = cudaMemsetAsync(ctl + 1 + (k ^ 1), 0, 4, s)) != cudaSuccess) return fail(e, "memset");
+      const int64_t hot = std::min<int64_t>(h[1], cap_t), cold_n = std::min<int64_t>(h[2], cap_t);
+      if (round > 0) top -= items;
+      if (top + hot + cold_n > cap_s) { unresolved = ISO_ST_POOL_OVERFLOW; break; }
+      auto push = [&](const IsoPool& from, int64_t cnt) -> cudaError_t {
+        if (cnt <= 0) return cudaSuccess;
+        cudaError_t pe = cudaMemcpyAsync(stack.pair + top, from.pair, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, s);
+        if (pe == cudaSuccess) pe = cudaMemcpyAsync(stack.colours + (size_t)top * 2 * maxN, from.colours, (size_t)cnt * slot_bytes, cudaMemcpyDeviceToDevice, s);
+        top += cnt;
+        return pe;
+      };
+      if ((e = push(coldp, cold_n)) != cudaSuccess || (e = push(scratch, hot)) != cudaSuccess) return fail(e, "push");  // hot ones on top
+      hot_on_top = hot;
+      if ((e = cudaMemsetAsync(ctl, 0, 12, s)) != cudaSuccess) return fail(e, "memset");
     }
+    iso_status_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(P, bits, stat, unresolved);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "iso_status_kernel launch");
   }
   if (!dev_out) {
     if ((e = cudaMemcpyAsync(result_bits, bits, (size_t)((P + 31) / 32) * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "copy");

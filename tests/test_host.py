@@ -169,3 +169,13 @@ def test_batch_reader_is_bit_identical_to_the_per_instance_reader(pt, gold_tc, g
     assert "pair 1" in str(e.value) and len(bad) == 0
     with pytest.raises(pt.PtError):
         bad.add_newick_text("(a,b);\n((a)#H1,(#H1,b));\n((a)#H1,(#H1,b));\n((a)#H1,(#H1,b));\n")   # second pair: guest is not a tree
+
+
+def test_iso_arrays_layout(pt):
+    """pt.iso_arrays: the flat layout of pt_iso_desc (graph g = 2 * pair + side; succ / pred CSR with local ids)"""
+    a = pt.iso_arrays([(3, [(0, 1), (0, 2)], [-1, 0, 1]), (4, [(0, 3), (0, 1), (1, 2)], [-1, -1, 1, 0])])
+    assert a["num_pairs"] == 1 and a["max_nodes"] == 4
+    assert a["node_off"].tolist() == [0, 3, 7] and a["arc_off"].tolist() == [0, 2, 5]
+    assert a["succ_off"].tolist() == [0, 2, 2, 2, 0, 2, 3, 3, 3] and a["succ_adj"].tolist() == [1, 2, 3, 1, 2]
+    assert a["pred_off"].tolist() == [0, 0, 1, 2, 0, 0, 1, 2, 3] and a["pred_adj"].tolist() == [0, 0, 0, 1, 0]
+    assert a["label"].tolist() == [-1, 0, 1, -1, -1, 1, 0]
