@@ -253,6 +253,13 @@ int pt_batch_round_ms(const pt_batch* b, int round, float* ms);
 int64_t pt_batch_h2d_bytes(const pt_batch* b);
 int pt_batch_free(pt_batch* b);
 
+/* The whole node in one call, without torch: the instances of a HOST batch are split into contiguous ranges (boundaries
+ * multiples of 32), one per GPU (num_devices <= 0: all visible ones; more shards than GPUs share them round-robin), each solved by pt_batch_create / pt_batch_contain on its
+ * own host thread; result bits, status and counters land in the caller's buffers as for pt_batch_contain with PT_MEM_HOST
+ * (counters.rounds = the largest branching depth of any shard).  SURVEY 8(e): the path shards with no collective. */
+int pt_batch_contain_multi(const pt_batch_desc* d, int num_devices, const pt_options* opt, uint32_t* result_bits, uint8_t* status,
+                           pt_counters* counters);
+
 /* ------------------------------------------------------------------------------------------------
  * Exhaustive switching enumeration (one instance, a range of the mixed-radix switching index).
  * The reference has no counterpart: it branches on one reticulation at a time (containment.hpp:1225-1266);

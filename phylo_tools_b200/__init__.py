@@ -210,6 +210,18 @@ class Batch:
     __del__ = free
 
 
+def contain_multi(arrays, num_devices=0, pool_slots=0, max_rounds=0):
+    """pt_batch_contain_multi: one call for all GPUs of the node (HOST arrays, one host thread per device, no collective)
+    -> (verdicts bool[B], status uint8[B], counters dict)"""
+    B = int(arrays["num_instances"])
+    d = make_desc(arrays, PT_MEM_HOST)
+    bits = np.zeros((B + 31) // 32 + 1, dtype=np.uint32)
+    status = np.zeros(B + 1, dtype=np.uint8)
+    opt, cnt = Options(pool_slots, max_rounds, 0), Counters()
+    _check(_L.pt_batch_contain_multi(C.byref(d), int(num_devices), C.byref(opt), _ptr(bits), _ptr(status), C.byref(cnt)), "pt_batch_contain_multi")
+    return np.unpackbits(bits.view(np.uint8), bitorder="little")[:B].astype(bool), status[:B], cnt.as_dict()
+
+
 def contain_newick(pairs):
     """[(host_newick, guest_newick)] -> (bool verdicts, status) ; the `tc` protocol of examples/tc.cpp:110-142 for a list"""
     p = Packer()

@@ -15,6 +15,8 @@
 #include <cooperative_groups.h>
 #include <map>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <unordered_map>
 
 namespace ptgpu {
@@ -1107,5 +1109,67 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
 }
 
 int pt_batch_free(pt_batch* b) { batch_release(b); return PT_OK; }
+
+// One call, all GPUs of the node, no torch: contiguous instance ranges (boundaries multiples of 32, so every device owns whole
+// result words) on one host thread per device; no collective is needed -- the caller's buffers are filled shard by shard.
+int pt_batch_contain_multi(const pt_batch_desc* d, int num_devices, const pt_options* opt, uint32_t* result_bits, uint8_t* status, pt_counters* counters) {
+  if (!d || !result_bits) return set_error(PT_ERR_INVALID, "pt_batch_contain_multi: null argument");
+  if (d->mem != PT_MEM_HOST) return set_error(PT_ERR_INVALID, "pt_batch_contain_multi: HOST arrays only (a DEVICE batch lives on one GPU: use pt_batch_create there)");
+  if (int rc = require_device()) return rc;
+  int have = 0;
+  PT_CUDA(cudaGetDeviceCount(&have));
+  const int G = num_devices <= 0 ? have : std::min(num_devices, 64);  // more shards than devices: they share the devices round-robin
+  const int64_t B = d->num_instances;
+  if (B < 0 || !d->host_node_off || !d->host_arc_off || !d->guest_node_off) return set_error(PT_ERR_INVALID, "pt_batch_contain_multi: bad batch");
+  for (int64_t i = 0; i < B; ++i)
+    if (d->host_node_off[i + 1] < d->host_node_off[i] || d->host_arc_off[i + 1] < d->host_arc_off[i] || d->guest_node_off[i + 1] < d->guest_node_off[i])
+      return set_error(PT_ERR_INVALID, "pt_batch_contain_multi: offset tables must be non-decreasing (instance %lld)", (long long)i);
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  const size_t esz = d->index_bytes == 2 ? 2 : 4;
+  std::vector<int> rcs((size_t)G, PT_OK);
+  std::vector<std::string> msgs((size_t)G);
+  std::vector<pt_counters> cnt((size_t)G);
+  std::vector<std::thread> workers;
+  for (int g = 0; g < G; ++g) {
+    const int64_t i0 = B * g / G / 32 * 32, i1 = (g + 1 == G) ? B : B * (g + 1) / G / 32 * 32;
+    workers.emplace_back([&, g, i0, i1]() {
+      memset(&cnt[(size_t)g], 0, sizeof(pt_counters));
+      const int64_t nb = i1 - i0;
+      if (nb <= 0) return;
+      auto fail = [&](int rc) { rcs[(size_t)g] = rc; msgs[(size_t)g] = pt_last_error(); };
+      if (cudaSetDevice(g % have) != cudaSuccess) { cudaGetLastError(); rcs[(size_t)g] = PT_ERR_CUDA; msgs[(size_t)g] = "cudaSetDevice failed"; return; }
+      // the shard as its own batch: offset tables rebased to 0, data pointers moved to the shard's first element
+      std::vector<int64_t> hn((size_t)nb + 1), ha((size_t)nb + 1), gn((size_t)nb + 1);
+      for (int64_t k = 0; k <= nb; ++k) { hn[(size_t)k] = d->host_node_off[i0 + k] - d->host_node_off[i0]; ha[(size_t)k] = d->host_arc_off[i0 + k] - d->host_arc_off[i0]; gn[(size_t)k] = d->guest_node_off[i0 + k] - d->guest_node_off[i0]; }
+      auto at = [&](const int32_t* base, int64_t elems) { return base ? reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(base) + (size_t)elems * esz) : nullptr; };
+      pt_batch_desc sd = *d;
+      sd.num_instances = nb; sd.host_node_off = hn.data(); sd.host_arc_off = ha.data(); sd.guest_node_off = gn.data();
+      sd.host_succ_off = at(d->host_succ_off, d->host_node_off[i0] + i0); sd.host_succ_adj = at(d->host_succ_adj, d->host_arc_off[i0]);
+      sd.host_label = at(d->host_label, d->host_node_off[i0]); sd.guest_parent = at(d->guest_parent, d->guest_node_off[i0]); sd.guest_label = at(d->guest_label, d->guest_node_off[i0]);
+      sd.host_pred_off = sd.host_pred_adj = sd.guest_child_off = sd.guest_child_adj = nullptr;
+      pt_batch* h = nullptr;
+      int rc = pt_batch_create(&h, &sd, nullptr);
+      if (rc != PT_OK) { fail(rc); return; }
+      rc = pt_batch_contain(h, opt, result_bits + i0 / 32, status ? status + i0 : nullptr, PT_MEM_HOST, &cnt[(size_t)g], nullptr);
+      if (rc != PT_OK) fail(rc);
+      pt_batch_free(h);
+    });
+  }
+  for (auto& w : workers) w.join();
+  cudaSetDevice(prev_dev);
+  for (int g = 0; g < G; ++g) if (rcs[(size_t)g] != PT_OK) return set_error(rcs[(size_t)g], "device %d: %s", g, msgs[(size_t)g].c_str());
+  if (counters) {
+    memset(counters, 0, sizeof(*counters));
+    for (int g = 0; g < G; ++g) {
+      const pt_counters& c = cnt[(size_t)g];
+      counters->instances += c.instances; counters->displayed += c.displayed; counters->not_displayed += c.not_displayed; counters->errors += c.errors;
+      counters->resolved_by_rules += c.resolved_by_rules; counters->branched += c.branched; counters->work_items += c.work_items;
+      counters->rounds = std::max(counters->rounds, c.rounds); counters->cherry_reductions += c.cherry_reductions;
+      counters->reticulated_cherries += c.reticulated_cherries; counters->arcs_deleted += c.arcs_deleted; counters->rule_passes += c.rule_passes;
+    }
+  }
+  return PT_OK;
+}
 
 }  // extern "C"

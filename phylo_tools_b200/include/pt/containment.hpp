@@ -65,6 +65,17 @@ class BatchContainment {
     for (size_t i = 0; i < B; ++i) verdict_[i] = (bits[i >> 5] >> (i & 31)) & 1u;
     done_ = true;
   }
+  // the same on every GPU of the node (pt_batch_contain_multi: contiguous shards, one host thread per device)
+  void run_all_gpus(int num_devices = 0) {
+    const size_t B = packer_.size();
+    std::vector<uint32_t> bits((B + 31) / 32 + 1, 0);
+    status_.assign(B + 1, 0);
+    const pt_batch_desc d = packer_.desc();
+    throw_status(pt_batch_contain_multi(&d, num_devices, nullptr, bits.data(), status_.data(), &counters_), "pt_batch_contain_multi");
+    verdict_.resize(B);
+    for (size_t i = 0; i < B; ++i) verdict_[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+    done_ = true;
+  }
   // verdict of instance i; throws like the reference would for a malformed instance
   bool displayed(size_t i) {
     if (!done_) run();

@@ -78,6 +78,8 @@ int main(int argc, char** argv) {
   b.add_newick("((a,b),(c,d));", "(((a)#H1,b),(#H1,(c,d)));");  // tree first, network second -> network is the host
   b.run();
   assert(b.displayed(0) && b.displayed(1) && b.counters().instances == 2);
+  b.run_all_gpus();   // every GPU of the node, one host thread each
+  assert(b.displayed(0) && b.displayed(1) && b.counters().instances == 2);
   // LCA: the tree of rmq/lca.cpp:24-43 and its four known answers
   LCAOracle L(std::vector<int32_t>{3, 3, 3, 8, 5, 7, 7, 8, -1});
   assert(L.query(8, 8) == 8 && L.query(3, 7) == 8 && L.query(0, 2) == 3 && L.query(4, 6) == 7);

@@ -335,6 +335,30 @@ def test_compact_int16_input_matches_int32(pt, gold_tc):
     assert (np.delete(vb, [5, 7]) == np.delete(v32, [5, 7])).all()
 
 
+def test_contain_multi_matches_single_batch(pt, gold_tc):
+    """pt_batch_contain_multi: the instances split into contiguous shards (one host thread each, devices round-robin), results
+    written straight into the caller's buffers: same verdicts, statuses and summed counters as one pt_batch, for both layouts
+    and for shard counts that do not divide the batch"""
+    items = gold_tc["items"]
+    p = pt.Packer()
+    for it in items:
+        p.add_newick(it["host"], it["guest"])
+    p.add_generated(700, 60, 12, 8181, 0); p.add_generated(333, 60, 12, 8282, 1)
+    for compact in (False, True):
+        a = p.arrays(compact=compact)
+        b = pt.Batch(a)
+        v1, s1, c1 = b.contain()
+        b.free()
+        for shards in (0, 1, 3, 7):
+            v, s, c = pt.contain_multi(a, num_devices=shards)
+            assert (v == v1).all() and (s == s1).all(), (compact, shards)
+            assert c["instances"] == c1["instances"] and c["displayed"] == c1["displayed"] and c["branched"] == c1["branched"]
+    bad = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in p.arrays().items()}
+    bad["host_succ_adj"][int(bad["host_arc_off"][900])] = 10 ** 6       # an out-of-range child id in a late shard
+    v, s, c = pt.contain_multi(bad, num_devices=4)
+    assert s[900] == 2 and (np.delete(s, 900) == 0).all() and (np.delete(v, 900) == np.delete(v1, 900)).all()
+
+
 def test_edge_cases(pt, oracle):
     """empty batch, one-node trees, one and two labels, unlabelled hosts, ragged batch (tiny next to large instances)"""
     b = pt.Batch(dict(num_instances=0, host_node_off=np.zeros(1, np.int64), host_arc_off=np.zeros(1, np.int64), guest_node_off=np.zeros(1, np.int64),
