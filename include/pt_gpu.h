@@ -253,6 +253,18 @@ int pt_batch_round_ms(const pt_batch* b, int round, float* ms);
 int64_t pt_batch_h2d_bytes(const pt_batch* b);
 int pt_batch_free(pt_batch* b);
 
+/* Extended-Newick text straight to a device-resident batch, PARSED ON THE GPU: every two non-blank lines of text[0, len) are
+ * one instance (the network is the host, or the first line if both are trees, examples/tc.cpp:110-111).  Same node numbering,
+ * child order and label ids as parse_newick (io/newick.hpp:274-290) + the packer, i.e. the arrays are bit-identical to
+ * pt_packer_add_newick_text on the same text -- but no host copy of them ever exists: the text is uploaded (mem = where it
+ * lives), one thread parses each line, one thread per pair writes the CSR (int16 layout whenever every id fits).  On malformed
+ * input nothing is created and PT_ERR_PARSE / PT_ERR_INVALID names the first bad pair.  Use with pt_batch_contain / _free. */
+int pt_batch_create_from_newick(pt_batch** out, const char* text, int64_t len, pt_mem mem, int64_t* num_pairs, void* stream);
+/* copy one of the batch's device arrays to the host (tests, debugging): which = 0 host_node_off, 1 host_arc_off,
+ * 2 guest_node_off (int64), 3 host_succ_off, 4 host_succ_adj, 5 host_label, 6 guest_parent, 7 guest_label (*index_bytes wide);
+ * dst == NULL only queries *bytes; maxima = {max_host_nodes, max_host_arcs, max_guest_nodes, max_labels} */
+int pt_batch_download(pt_batch* b, int which, void* dst, int64_t capacity_bytes, int64_t* bytes, int32_t* index_bytes, int32_t maxima[4]);
+
 /* The whole node in one call, without torch: the instances of a HOST batch are split into contiguous ranges (boundaries
  * multiples of 32), one per GPU (num_devices <= 0: all visible ones; more shards than GPUs share them round-robin), each solved by pt_batch_create / pt_batch_contain on its
  * own host thread; result bits, status and counters land in the caller's buffers as for pt_batch_contain with PT_MEM_HOST

@@ -174,6 +174,42 @@ class Batch:
         d = make_desc(arrays, PT_MEM_DEVICE if dev else PT_MEM_HOST)
         _check(_L.pt_batch_create(C.byref(self._h), C.byref(d), stream), "pt_batch_create")
 
+    @classmethod
+    def from_newick_text(cls, text, stream=None):
+        """pt_batch_create_from_newick: extended-Newick text (two lines per instance) parsed ON THE GPU into a device-resident
+        batch; text: bytes / str (HOST) or a torch CUDA uint8 tensor (DEVICE)"""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        n = C.c_int64(0)
+        if _is_device(text):
+            self._keep = text
+            rc = _L.pt_batch_create_from_newick(C.byref(self._h), text.data_ptr(), int(text.numel()), PT_MEM_DEVICE, C.byref(n), stream)
+        else:
+            data = text if isinstance(text, (bytes, bytearray)) else text.encode()
+            self._keep = data
+            rc = _L.pt_batch_create_from_newick(C.byref(self._h), C.cast(C.c_char_p(bytes(data)), C.c_void_p), len(data), PT_MEM_HOST, C.byref(n), stream)
+        if rc == _capi.PT_ERR_PARSE:
+            raise MalformedNewick((_L.pt_last_error() or b"").decode(errors="replace"))
+        _check(rc, "pt_batch_create_from_newick")
+        self.num_instances = int(n.value)
+        return self
+
+    def download(self):
+        """the batch's device arrays copied back to numpy (pt_batch_download), keyed like Packer.arrays()"""
+        keys = ["host_node_off", "host_arc_off", "guest_node_off", "host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"]
+        out = dict(num_instances=self.num_instances)
+        ib, mx = C.c_int32(0), (C.c_int32 * 4)()
+        for which, k in enumerate(keys):
+            nb = C.c_int64(0)
+            _check(_L.pt_batch_download(self._h, which, None, 0, C.byref(nb), C.byref(ib), mx), "pt_batch_download")
+            dt = np.int64 if which < 3 else (np.int16 if ib.value == 2 else np.int32)
+            a = np.zeros(max(nb.value // np.dtype(dt).itemsize, 0), dtype=dt)
+            if nb.value:
+                _check(_L.pt_batch_download(self._h, which, a.ctypes.data, nb.value, C.byref(nb), None, None), "pt_batch_download")
+            out[k] = a
+        out.update(index_bytes=int(ib.value), max_host_nodes=mx[0], max_host_arcs=mx[1], max_guest_nodes=mx[2], max_labels=mx[3])
+        return out
+
     def contain(self, result_bits=None, status=None, want_counters=True, stream=None, pool_slots=0, max_rounds=0, path=0):
         """returns (verdicts bool[B] or None when device outputs are given, status uint8[B] or None, counters dict or None)"""
         B = self.num_instances

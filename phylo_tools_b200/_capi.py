@@ -75,6 +75,8 @@ def load():
         "pt_batch_create": (C.c_int, [C.POINTER(vp), C.POINTER(BatchDesc), vp]),
         "pt_batch_contain": (C.c_int, [vp, C.POINTER(Options), vp, vp, C.c_int, C.POINTER(Counters), vp]),
         "pt_batch_contain_multi": (C.c_int, [C.POINTER(BatchDesc), C.c_int, C.POINTER(Options), vp, vp, C.POINTER(Counters)]),
+        "pt_batch_create_from_newick": (C.c_int, [C.POINTER(vp), vp, C.c_int64, C.c_int, i64p, vp]),
+        "pt_batch_download": (C.c_int, [vp, C.c_int, vp, C.c_int64, i64p, i32p, i32p]),
         "pt_batch_last_launches": (C.c_int64, [vp]),
         "pt_batch_round_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
         "pt_batch_h2d_bytes": (C.c_int64, [vp]),
@@ -100,5 +102,5 @@ def load():
 
 EXPORTED = ["pt_last_error", "pt_abi_version", "pt_device_count", "pt_set_device", "pt_lca_build", "pt_lca_query", "pt_lca_get_info",
             "pt_lca_node_info", "pt_lca_free", "pt_tree_who_displays", "pt_net_bridges", "pt_rmq_build", "pt_rmq_query", "pt_rmq_free", "pt_get_limits", "pt_batch_create",
-            "pt_batch_contain", "pt_batch_contain_multi", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_parse_newick", "pt_packer_create",
+            "pt_batch_contain", "pt_batch_contain_multi", "pt_batch_create_from_newick", "pt_batch_download", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_parse_newick", "pt_packer_create",
             "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree", "pt_iso_batch"]

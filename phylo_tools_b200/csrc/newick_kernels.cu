@@ -1,0 +1,333 @@
+// csrc/newick_kernels.cu -- extended-Newick text -> device-resident batch, parsed ON THE GPU (pt_batch_create_from_newick).
+//
+// SURVEY 8(f) rank 1.  The reference reads one network at a time (NewickParser io/newick.hpp:64-272, read_edgelists
+// io/io.hpp:52-62); the host batch reader (pt/fast_newick.hpp) does 2.6e5 pairs/s on 16 cores, fifty times slower than the
+// containment kernel consumes them.  Here the text is uploaded once and
+//   1. the newlines are located (CUB select), the lines trimmed and the blank ones dropped (one thread per line),
+//   2. every line is parsed by ONE THREAD with the same right-to-left scan as the reference (same node numbering: root 0, ids
+//      in the order the name tokens are met from the right; hybrid "#H<k>": first occurrence from the right creates the
+//      node; ":length" and white space skipped) into scratch arrays addressed by the line's text offset,
+//   3. one thread per pair picks host and guest (the network is the host, or the first line if both are trees,
+//      examples/tc.cpp:110-111), gives the labels dense ids by first appearance (host nodes, then guest nodes) through an
+//      open-addressing table kept in the pair's own scratch span, and publishes the sizes,
+//   4. prefix sums over the pairs give the offset tables,
+//   5. one thread per pair writes the CSR (children in reverse arc order, utils/storage_adj_immutable.hpp:119), the label
+//      ids and the guest parent array -- directly in the int16 layout when the batch allows it.
+// The arrays are bit-identical to BatchPacker::add_newick_text on the same text (tests/test_gpu_newick.py); the handle
+// owns them (no host copy ever exists).  Malformed input: PT_ERR_PARSE / PT_ERR_INVALID naming the first bad pair.
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <algorithm>
+#include <vector>
+#include "cuda_common.cuh"
+
+extern "C" int ptgpu_batch_adopt(pt_batch** out, int64_t B, void* const arrays[8], int idx16, const int32_t maxima[4], void* stream);
+
+namespace ptgpu {
+
+struct IsNewline {
+  const char* text;
+  __device__ __forceinline__ bool operator()(const int64_t& i) const { return text[i] == '\n'; }
+};
+
+// raw line r = text between newline r-1 and newline r (virtual newlines at -1 and len); trimmed like pt/fast_newick.hpp
+__global__ void nw_trim_kernel(const char* __restrict__ text, int64_t len, const int64_t* __restrict__ nlpos, int64_t num_nl,
+                               int64_t* __restrict__ lbeg, int32_t* __restrict__ llen, int32_t* __restrict__ flag) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r > num_nl) return;
+  int64_t b = r == 0 ? 0 : nlpos[r - 1] + 1, e = r == num_nl ? len : nlpos[r];
+  while (b < e && (text[b] == ' ' || text[b] == '\t' || text[b] == '\r')) ++b;
+  while (e > b && (text[e - 1] == ' ' || text[e - 1] == '\t' || text[e - 1] == '\r')) --e;
+  lbeg[r] = b; llen[r] = (int32_t)min(e - b, (int64_t)INT32_MAX); flag[r] = e > b;
+}
+__global__ void nw_compact_kernel(int64_t num_raw, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen, const int32_t* __restrict__ flag,
+                                  const int32_t* __restrict__ pos, int64_t* __restrict__ obeg, int32_t* __restrict__ olen) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= num_raw || !flag[r]) return;
+  obeg[pos[r]] = lbeg[r]; olen[pos[r]] = llen[r];
+}
+
+enum { NW_OK = 0, NW_SEMI = 1, NW_HYBRID = 2, NW_START = 3, NW_SEP = 4, NW_GUEST = 5, NW_DOUBLE = 6 };
+__host__ const char* nw_error_text(int code) {
+  switch (code) {
+    case NW_SEMI: return "MalformedNewick: expected ';'";
+    case NW_HYBRID: return "MalformedNewick: found '#' but no hybrid number";
+    case NW_START: return "MalformedNewick: unexpected start of string";
+    case NW_SEP: return "MalformedNewick: expected ',' or '('";
+    case NW_GUEST: return "guest must be a tree";
+    case NW_DOUBLE: return "MalformedNewick: read double edge";
+    default: return "ok";
+  }
+}
+
+struct NwScratch {  // all int32, addressed by region index (region of line k starts at lbeg[k] + 2k, holds llen[k] + 2 entries)
+  int32_t *tl, *hd, *lo, *ll, *st, *hk, *hi;
+};
+__device__ __forceinline__ bool nw_ws(char c) { return c == ' ' || (unsigned)(c - 9) < 5u; }
+__device__ __forceinline__ bool nw_digit(char c) { return c >= '0' && c <= '9'; }
+
+// the scan of pt/fast_newick.hpp parse_line (= io/newick.hpp:159-272), one thread, one line
+__global__ void nw_parse_kernel(const char* __restrict__ text, int64_t num_lines, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen,
+                                NwScratch S, int32_t* __restrict__ ln, int32_t* __restrict__ lm, int32_t* __restrict__ lhyb, int32_t* __restrict__ lerr) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= num_lines) return;
+  const char* s = text + lbeg[k];
+  const int len = llen[k];
+  const int64_t reg = lbeg[k] + 2 * k;
+  int32_t *tl = S.tl + reg, *hd = S.hd + reg, *lo = S.lo + reg, *ll = S.ll + reg, *st = S.st + reg, *hk = S.hk + reg, *hi = S.hi + reg;
+  int n = 0, m = 0, nh = 0, sp = 0, err = NW_OK, has_h = 0;
+  int back = len - 1;
+#define NW_SKIP_WS() while (back >= 0 && nw_ws(s[back])) --back
+#define NW_SKIP_LEN() do { int i_ = back; while (i_ >= 0) { const char c_ = s[i_]; if (nw_digit(c_) || c_ == '.' || c_ == '-' || c_ == '+' || c_ == 'E' || c_ == 'e') --i_; else break; } if (i_ >= 0 && s[i_] == ':') back = i_ - 1; } while (0)
+  NW_SKIP_WS();
+  if (back >= 0) {
+    if (s[back] != ';') err = NW_SEMI;
+    else {
+      --back;
+      bool want = true;
+      int done = 0;
+      for (;;) {
+        if (want) {
+          NW_SKIP_WS();
+          int i = back, sharp = -1;
+          while (i >= 0) { const char c = s[i]; if (c == '(' || c == ')' || c == ',') break; if (c == '#' && sharp < 0) sharp = i; --i; }
+          const int nb = i + 1, nl = back - i;
+          back = i;
+          int id;
+          if (sharp >= 0) {
+            int d = sharp;
+            while (d < nb + nl && !nw_digit(s[d])) ++d;
+            if (d == nb + nl) { err = NW_HYBRID; break; }
+            int key = 0;
+            while (d < nb + nl && nw_digit(s[d])) { key = key * 10 + (s[d] - '0'); ++d; }
+            id = -1;
+            for (int h = 0; h < nh; ++h) if (hk[h] == key) { id = hi[h]; break; }
+            if (id < 0) { id = n; hk[nh] = key; hi[nh++] = id; lo[n] = nb; ll[n] = sharp - nb; ++n; }
+            has_h = 1;
+          } else { id = n; lo[n] = nb; ll[n] = nl; ++n; }
+          if (back > 0 && s[back] == ')') { --back; st[sp++] = id; NW_SKIP_LEN(); continue; }
+          done = id; want = false;
+        }
+        NW_SKIP_WS();
+        if (sp == 0) break;
+        const int parent = st[sp - 1];
+        tl[m] = parent; hd[m++] = done;
+        if (back < 0) { err = NW_START; break; }
+        const char c = s[back];
+        if (c == ',') { --back; NW_SKIP_LEN(); want = true; }
+        else if (c == '(') { --back; --sp; done = parent; }
+        else { err = NW_SEP; break; }
+      }
+    }
+  }
+#undef NW_SKIP_WS
+#undef NW_SKIP_LEN
+  ln[k] = n; lm[k] = m; lhyb[k] = has_h; lerr[k] = err;
+}
+
+// per pair: host / guest, label ids (written over the hybrid-key scratch of each node), sizes, maxima, first error
+__global__ void nw_pair_kernel(const char* __restrict__ text, int64_t num_pairs, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen, NwScratch S,
+                               const int32_t* __restrict__ ln, const int32_t* __restrict__ lm, const int32_t* __restrict__ lhyb, const int32_t* __restrict__ lerr,
+                               int64_t* __restrict__ hn, int64_t* __restrict__ hm, int64_t* __restrict__ gn, int32_t* __restrict__ swapped,
+                               int32_t* __restrict__ maxima /* n m nt labels */, unsigned long long* __restrict__ first_err /* pair << 8 | code */) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= num_pairs) return;
+  const int64_t a = 2 * p, b = 2 * p + 1;
+  hn[p] = 0; hm[p] = 0; gn[p] = 0; swapped[p] = 0;
+  int err = lerr[a] ? lerr[a] : lerr[b];
+  const bool t0 = lm[a] + 1 == ln[a], t1 = lm[b] + 1 == ln[b];
+  const bool sw = t0 && !t1;
+  const int64_t H = sw ? b : a, G = sw ? a : b;
+  if (!err && (lm[G] + 1 != ln[G] || lhyb[G])) err = NW_GUEST;
+  if (err) { atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)err); return; }
+  swapped[p] = sw;
+  // label dictionary: open addressing over the pair's contiguous span of the `st` scratch (free after parsing)
+  const int64_t reg_a = lbeg[a] + 2 * a, reg_b = lbeg[b] + 2 * b, span = reg_b + llen[b] + 2 - reg_a;
+  int cap = 1; while ((int64_t)cap * 2 <= span) cap <<= 1;
+  int32_t* slots = S.st + reg_a;  // entry = region index of the first node with that label, relative to reg_a; -1 empty
+  for (int i = 0; i < cap; ++i) slots[i] = -1;
+  int count = 0;
+  for (int side = 0; side < 2; ++side) {
+    const int64_t L = side ? G : H, reg = lbeg[L] + 2 * L;
+    const char* base = text + lbeg[L];
+    const int n = ln[L];
+    for (int v = 0; v < n; ++v) {
+      const int off = S.lo[reg + v], len = S.ll[reg + v];
+      int id = -1;
+      if (len > 0) {
+        unsigned h = 2166136261u;
+        for (int k = 0; k < len; ++k) h = (h ^ (unsigned char)base[off + k]) * 16777619u;
+        int i = (int)(h & (unsigned)(cap - 1));
+        for (;;) {
+          const int sidx = slots[i];
+          if (sidx < 0) { slots[i] = (int)(reg + v - reg_a); id = count++; break; }
+          const int64_t g = reg_a + sidx;                      // an earlier node: in line a's region or in line b's
+          const int64_t gl = g >= reg_b ? b : a;
+          const char* gb = text + lbeg[gl];
+          const int goff = S.lo[g], glen = S.ll[g];
+          bool same = glen == len;
+          for (int k = 0; same && k < len; ++k) same = gb[goff + k] == base[off + k];
+          if (same) { id = S.hk[g]; break; }
+          i = (i + 1) & (cap - 1);
+        }
+      }
+      S.hk[reg + v] = id;  // label id of node v (the hybrid keys are no longer needed)
+    }
+  }
+  hn[p] = ln[H]; hm[p] = lm[H]; gn[p] = ln[G];
+  atomicMax(&maxima[0], ln[H]); atomicMax(&maxima[1], lm[H]); atomicMax(&maxima[2], ln[G]); atomicMax(&maxima[3], count);
+}
+
+// per pair: the final arrays.  OUT = int32_t or int16_t (pt_batch_desc.index_bytes)
+template <class OUT>
+__global__ void nw_emit_kernel(int64_t num_pairs, const int64_t* __restrict__ lbeg, NwScratch S, const int32_t* __restrict__ ln, const int32_t* __restrict__ lm,
+                               const int32_t* __restrict__ swapped, const int64_t* __restrict__ hoff, const int64_t* __restrict__ aoff, const int64_t* __restrict__ goff,
+                               OUT* __restrict__ succ_off, OUT* __restrict__ succ_adj, OUT* __restrict__ hlabel, OUT* __restrict__ gparent, OUT* __restrict__ glabel,
+                               unsigned long long* __restrict__ first_err) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= num_pairs) return;
+  const int64_t a = 2 * p, b = 2 * p + 1, H = swapped[p] ? b : a, G = swapped[p] ? a : b;
+  const int64_t rh = lbeg[H] + 2 * H, rg = lbeg[G] + 2 * G;
+  const int n = ln[H], m = lm[H], nt = ln[G], mt = lm[G];
+  OUT* O = succ_off + hoff[p] + p; OUT* A = succ_adj + aoff[p];
+  const int32_t *tl = S.tl + rh, *hd = S.hd + rh;
+  int32_t* cur = S.hi + rh;  // cursors (the hybrid ids are no longer needed)
+  for (int v = 0; v <= n; ++v) O[v] = 0;
+  for (int e = 0; e < m; ++e) O[tl[e] + 1] = (OUT)(O[tl[e] + 1] + 1);
+  for (int v = 0; v < n; ++v) O[v + 1] = (OUT)(O[v + 1] + O[v]);
+  for (int v = 0; v < n; ++v) cur[v] = O[v + 1];
+  for (int e = 0; e < m; ++e) A[--cur[tl[e]]] = (OUT)hd[e];   // children in reverse arc order (Phylogeny::build)
+  bool dbl = false;
+  for (int v = 0; v < n; ++v) for (int x = O[v]; x < O[v + 1]; ++x) for (int y = x + 1; y < O[v + 1]; ++y) dbl |= A[x] == A[y];
+  if (dbl) atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)NW_DOUBLE);
+  OUT* HL = hlabel + hoff[p];
+  for (int v = 0; v < n; ++v) HL[v] = (OUT)S.hk[rh + v];
+  OUT* GP = gparent + goff[p]; OUT* GL = glabel + goff[p];
+  for (int v = 0; v < nt; ++v) { GP[v] = (OUT)-1; GL[v] = (OUT)S.hk[rg + v]; }
+  const int32_t *gtl = S.tl + rg, *ghd = S.hd + rg;
+  for (int e = 0; e < mt; ++e) GP[ghd[e]] = (OUT)gtl[e];
+}
+
+__global__ void nw_set_first_kernel(int64_t* a, int64_t* b, int64_t* c) { a[0] = 0; b[0] = 0; c[0] = 0; }
+
+}  // namespace ptgpu
+
+using namespace ptgpu;
+
+extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int64_t len, pt_mem mem, int64_t* num_pairs, void* stream) {
+  if (!out || (!text && len > 0) || len < 0) return set_error(PT_ERR_INVALID, "pt_batch_create_from_newick: bad argument");
+  *out = nullptr;
+  if (num_pairs) *num_pairs = 0;
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<void*> tmp;  // freed on return
+  void* keep[8] = {};       // owned by the handle on success
+  auto cleanup = [&](bool ok) { cudaStreamSynchronize(s); for (void* p : tmp) dev_free(p); if (!ok) for (void* p : keep) dev_free(p); };
+  auto alloc = [&](void** p, size_t bytes, bool temp) -> int { const int rc = dev_alloc(p, std::max<size_t>(bytes, 16)); if (rc == PT_OK && temp) tmp.push_back(*p); return rc; };
+#define NW_TRY(expr) do { const int rc__ = (expr); if (rc__ != PT_OK) { cleanup(false); return rc__; } } while (0)
+#define NW_CUDA(call) do { const cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(false); return set_error(PT_ERR_CUDA, "pt_batch_create_from_newick: %s: %s", #call, cudaGetErrorString(e__)); } } while (0)
+  const char* d_text = text;
+  if (mem == PT_MEM_HOST) {
+    void* p = nullptr;
+    NW_TRY(alloc(&p, (size_t)len + 1, true));
+    if (len) NW_CUDA(cudaMemcpyAsync(p, text, (size_t)len, cudaMemcpyHostToDevice, s));
+    d_text = (const char*)p;
+  }
+  // ---- 1. lines ----
+  int64_t *d_nlpos = nullptr, *d_count = nullptr;
+  NW_TRY(alloc((void**)&d_nlpos, (size_t)(len + 1) * 8, true));
+  NW_TRY(alloc((void**)&d_count, 64, true));
+  int64_t num_nl = 0;
+  if (len > 0) {
+    thrust::counting_iterator<int64_t> idx(0);
+    size_t tb = 0;
+    NW_CUDA(cub::DeviceSelect::If(nullptr, tb, idx, d_nlpos, d_count, len, IsNewline{d_text}, s));
+    void* d_tmp = nullptr;
+    NW_TRY(alloc(&d_tmp, tb, true));
+    NW_CUDA(cub::DeviceSelect::If(d_tmp, tb, idx, d_nlpos, d_count, len, IsNewline{d_text}, s));
+    NW_CUDA(cudaMemcpyAsync(&num_nl, d_count, 8, cudaMemcpyDeviceToHost, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+  }
+  const int64_t num_raw = num_nl + 1;
+  int64_t *d_rbeg = nullptr, *d_lbeg = nullptr; int32_t *d_rlen = nullptr, *d_flag = nullptr, *d_pos = nullptr, *d_llen = nullptr;
+  NW_TRY(alloc((void**)&d_rbeg, (size_t)num_raw * 8, true)); NW_TRY(alloc((void**)&d_rlen, (size_t)num_raw * 4, true));
+  NW_TRY(alloc((void**)&d_flag, (size_t)(num_raw + 1) * 4, true)); NW_TRY(alloc((void**)&d_pos, (size_t)(num_raw + 1) * 4, true));
+  nw_trim_kernel<<<(unsigned)((num_raw + 255) / 256), 256, 0, s>>>(d_text, len, d_nlpos, num_nl, d_rbeg, d_rlen, d_flag);
+  NW_CUDA(cudaMemsetAsync(d_flag + num_raw, 0, 4, s));
+  {
+    size_t tb = 0;
+    NW_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag, d_pos, num_raw + 1, s));
+    void* d_tmp = nullptr;
+    NW_TRY(alloc(&d_tmp, tb, true));
+    NW_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_flag, d_pos, num_raw + 1, s));
+  }
+  int32_t num_lines32 = 0;
+  NW_CUDA(cudaMemcpyAsync(&num_lines32, d_pos + num_raw, 4, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  const int64_t num_lines = num_lines32, P = num_lines / 2;
+  NW_TRY(alloc((void**)&d_lbeg, (size_t)(num_lines + 1) * 8, true)); NW_TRY(alloc((void**)&d_llen, (size_t)(num_lines + 1) * 4, true));
+  nw_compact_kernel<<<(unsigned)((num_raw + 255) / 256), 256, 0, s>>>(num_raw, d_rbeg, d_rlen, d_flag, d_pos, d_lbeg, d_llen);
+  // ---- 2. parse every line ----
+  const size_t S_len = (size_t)len + 2 * (size_t)num_lines + 8;
+  NwScratch S{};
+  int32_t** sarr[7] = {&S.tl, &S.hd, &S.lo, &S.ll, &S.st, &S.hk, &S.hi};
+  for (auto pp : sarr) NW_TRY(alloc((void**)pp, S_len * 4, true));
+  int32_t *d_ln = nullptr, *d_lm = nullptr, *d_lh = nullptr, *d_le = nullptr;
+  for (int32_t** pp : {&d_ln, &d_lm, &d_lh, &d_le}) NW_TRY(alloc((void**)pp, (size_t)(num_lines + 1) * 4, true));
+  if (2 * P > 0) nw_parse_kernel<<<(unsigned)((2 * P + 127) / 128), 128, 0, s>>>(d_text, 2 * P, d_lbeg, d_llen, S, d_ln, d_lm, d_lh, d_le);
+  // ---- 3. pairs ----
+  int64_t *d_hn = nullptr, *d_hm = nullptr, *d_gn = nullptr; int32_t *d_sw = nullptr, *d_max = nullptr; unsigned long long* d_err = nullptr;
+  for (int k = 0; k < 3; ++k) NW_TRY(alloc(&keep[k], (size_t)(P + 1) * 8, false));
+  NW_TRY(alloc((void**)&d_hn, (size_t)(P + 1) * 8, true)); NW_TRY(alloc((void**)&d_hm, (size_t)(P + 1) * 8, true)); NW_TRY(alloc((void**)&d_gn, (size_t)(P + 1) * 8, true));
+  NW_TRY(alloc((void**)&d_sw, (size_t)(P + 1) * 4, true)); NW_TRY(alloc((void**)&d_max, 16, true)); NW_TRY(alloc((void**)&d_err, 8, true));
+  NW_CUDA(cudaMemsetAsync(d_max, 0, 16, s)); NW_CUDA(cudaMemsetAsync(d_err, 0xff, 8, s));
+  if (P > 0) nw_pair_kernel<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(d_text, P, d_lbeg, d_llen, S, d_ln, d_lm, d_lh, d_le, d_hn, d_hm, d_gn, d_sw, d_max, d_err);
+  // ---- 4. offset tables ----
+  int64_t* off[3] = {(int64_t*)keep[0], (int64_t*)keep[1], (int64_t*)keep[2]};
+  nw_set_first_kernel<<<1, 1, 0, s>>>(off[0], off[1], off[2]);
+  if (P > 0) {
+    size_t tb = 0;
+    NW_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, d_hn, off[0] + 1, P, s));
+    void* d_tmp = nullptr;
+    NW_TRY(alloc(&d_tmp, tb, true));
+    NW_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_hn, off[0] + 1, P, s));
+    NW_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_hm, off[1] + 1, P, s));
+    NW_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_gn, off[2] + 1, P, s));
+  }
+  int64_t totals[3] = {0, 0, 0}; int32_t maxima[4] = {0, 0, 0, 0}; unsigned long long first_err = ~0ull;
+  for (int k = 0; k < 3; ++k) NW_CUDA(cudaMemcpyAsync(&totals[k], off[k] + P, 8, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaMemcpyAsync(maxima, d_max, 16, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaMemcpyAsync(&first_err, d_err, 8, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  auto report = [&](unsigned long long fe) {
+    const int code = (int)(fe & 0xff);
+    const long long pair = (long long)(fe >> 8);
+    cleanup(false);
+    return set_error(code == NW_GUEST ? PT_ERR_INVALID : PT_ERR_PARSE, "pair %lld: %s", pair, nw_error_text(code));
+  };
+  if (first_err != ~0ull) return report(first_err);
+  // ---- 5. final arrays (int16 when every id fits) ----
+  const bool idx16 = maxima[0] < 32768 && maxima[1] < 32768 && maxima[2] < 32768 && maxima[3] < 32768;
+  const size_t esz = idx16 ? 2 : 4;
+  const size_t counts[5] = {(size_t)(totals[0] + P), (size_t)totals[1], (size_t)totals[0], (size_t)totals[2], (size_t)totals[2]};
+  for (int k = 0; k < 5; ++k) NW_TRY(alloc(&keep[3 + k], counts[k] * esz, false));
+  if (P > 0) {
+    if (idx16) nw_emit_kernel<int16_t><<<(unsigned)((P + 127) / 128), 128, 0, s>>>(P, d_lbeg, S, d_ln, d_lm, d_sw, off[0], off[1], off[2], (int16_t*)keep[3], (int16_t*)keep[4],
+                                                                                   (int16_t*)keep[5], (int16_t*)keep[6], (int16_t*)keep[7], d_err);
+    else nw_emit_kernel<int32_t><<<(unsigned)((P + 127) / 128), 128, 0, s>>>(P, d_lbeg, S, d_ln, d_lm, d_sw, off[0], off[1], off[2], (int32_t*)keep[3], (int32_t*)keep[4],
+                                                                             (int32_t*)keep[5], (int32_t*)keep[6], (int32_t*)keep[7], d_err);
+    NW_CUDA(cudaGetLastError());
+    NW_CUDA(cudaMemcpyAsync(&first_err, d_err, 8, cudaMemcpyDeviceToHost, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    if (first_err != ~0ull) return report(first_err);
+  }
+  pt_batch* h = nullptr;
+  NW_TRY(ptgpu_batch_adopt(&h, P, keep, idx16 ? 1 : 0, maxima, stream));
+  cleanup(true);
+  *out = h;
+  if (num_pairs) *num_pairs = P;
+  return PT_OK;
+#undef NW_TRY
+#undef NW_CUDA
+}

@@ -922,7 +922,50 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   return PT_OK;
 }
 
+// array `which` of the batch as it lives on the device (0 host_node_off, 1 host_arc_off, 2 guest_node_off: int64; 3 succ_off,
+// 4 succ_adj, 5 host_label, 6 guest_parent, 7 guest_label: int32 or int16 per *index_bytes) copied to `dst`
+int pt_batch_download(pt_batch* b, int which, void* dst, int64_t capacity_bytes, int64_t* bytes, int32_t* index_bytes, int32_t maxima[4]) {
+  if (!b || which < 0 || which > 7 || !bytes) return set_error(PT_ERR_INVALID, "pt_batch_download: bad argument");
+  const int64_t B = b->B;
+  int64_t tail[3] = {0, 0, 0};
+  if (B > 0) {
+    if (b->used_stream_valid) PT_CUDA(cudaStreamSynchronize(b->used_stream));
+    if (b->copy_stream) PT_CUDA(cudaStreamSynchronize(b->copy_stream));
+    PT_CUDA(cudaMemcpy(&tail[0], b->d_hnode_off + B, 8, cudaMemcpyDeviceToHost)); PT_CUDA(cudaMemcpy(&tail[1], b->d_harc_off + B, 8, cudaMemcpyDeviceToHost));
+    PT_CUDA(cudaMemcpy(&tail[2], b->d_gnode_off + B, 8, cudaMemcpyDeviceToHost));
+  }
+  const int64_t esz = b->idx16 ? 2 : 4;
+  const void* src[8] = {b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_succ_off, b->d_succ_adj, b->d_hlabel, b->d_tparent, b->d_tlabel};
+  const int64_t n[8] = {(B + 1) * 8, (B + 1) * 8, (B + 1) * 8, (tail[0] + B) * esz, tail[1] * esz, tail[0] * esz, tail[2] * esz, tail[2] * esz};
+  *bytes = n[which];
+  if (index_bytes) *index_bytes = (int32_t)esz;
+  if (maxima) { maxima[0] = b->maxN; maxima[1] = b->maxM; maxima[2] = b->maxNT; maxima[3] = b->maxL; }
+  if (dst) {
+    if (capacity_bytes < n[which]) return set_error(PT_ERR_INVALID, "pt_batch_download: buffer too small");
+    if (n[which] > 0) PT_CUDA(cudaMemcpy(dst, src[which], (size_t)n[which], cudaMemcpyDeviceToHost));
+  }
+  return PT_OK;
+}
+
 int64_t pt_batch_last_launches(const pt_batch* b) { return b ? b->last_launches : 0; }
+
+// A batch whose device arrays were produced on the device (csrc/newick_kernels.cu): the handle takes ownership of the eight
+// dev_alloc'ed arrays (order: host_node_off, host_arc_off, guest_node_off, succ_off, succ_adj, host_label, guest_parent, guest_label).
+int ptgpu_batch_adopt(pt_batch** out, int64_t B, void* const arrays[8], int idx16, const int32_t maxima[4], void* stream) {
+  pt_batch* b = new (std::nothrow) pt_batch();
+  if (!b) return set_error(PT_ERR_NOMEM, "out of host memory");
+  b->B = B; b->owns_input = true; b->idx16 = idx16;
+  b->used_stream = (cudaStream_t)stream; b->used_stream_valid = true;
+  b->d_hnode_off = (int64_t*)arrays[0]; b->d_harc_off = (int64_t*)arrays[1]; b->d_gnode_off = (int64_t*)arrays[2];
+  b->d_succ_off = arrays[3]; b->d_succ_adj = arrays[4]; b->d_hlabel = arrays[5]; b->d_tparent = arrays[6]; b->d_tlabel = arrays[7];
+  b->maxN = std::max(maxima[0], 1); b->maxM = std::max(maxima[1], 1); b->maxNT = std::max(maxima[2], 1); b->maxL = std::max(maxima[3], 1);
+  int rc = PT_OK;
+  if ((rc = dev_alloc((void**)&b->d_bits, ((size_t)((B + 31) / 32) + 1) * 4)) || (rc = dev_alloc((void**)&b->d_status, (size_t)B + 1)) ||
+      (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 256)) ||
+      (rc = dev_alloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long)))) { batch_release(b); return rc; }
+  *out = b;
+  return PT_OK;
+}
 int64_t pt_batch_h2d_bytes(const pt_batch* b) { return b ? b->h2d_bytes : 0; }
 int pt_batch_round_ms(const pt_batch* b, int round, float* ms) {
   if (!b || !ms || round < 0 || round >= b->timed_rounds) return set_error(PT_ERR_INVALID, "pt_batch_round_ms: round %d did not run (or was not timed)", round);

@@ -1,0 +1,86 @@
+"""pt_batch_create_from_newick (extended-Newick text parsed ON THE GPU into a device-resident batch) against the host batch reader
+(pt_packer_add_newick_text = the reference reader's numbering, pinned by tests/golden/newick_ref.json): the arrays must be
+bit-identical, the verdicts the pinned truths, malformed input must name the first bad pair."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["host_node_off", "host_arc_off", "guest_node_off", "host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"]
+
+
+def _same_arrays(pt, text):
+    b = pt.Batch.from_newick_text(text)
+    d = b.download()
+    p = pt.Packer()
+    k = p.add_newick_text(text)
+    assert k == b.num_instances
+    a = p.arrays(compact=d["index_bytes"] == 2)
+    for key in KEYS:
+        assert d[key].dtype == a[key].dtype and d[key].shape == a[key].shape and (d[key] == a[key]).all(), key
+    for key in ("max_host_nodes", "max_host_arcs", "max_guest_nodes", "max_labels"):
+        assert d[key] == max(a[key], 1), key
+    return b, p
+
+
+def test_device_reader_matches_host_reader_on_golden_instances(pt, gold_tc):
+    items = gold_tc["items"]
+    text = "".join(it["host"] + "\n" + it["guest"] + "\n" for it in items)
+    b, _ = _same_arrays(pt, text)
+    v, s, _ = b.contain()
+    b.free()
+    assert (s == 0).all() and [int(x) for x in v] == [it["truth"] for it in items]
+
+
+def test_device_reader_on_generated_batches_and_formatting(pt):
+    p = pt.Packer()
+    p.add_generated(3000, 100, 20, 0xB200, 0); p.add_generated(500, 30, 6, 99, 1); p.add_generated(500, 12, 3, 98, 2)
+    pairs = [p.newick(i) for i in range(len(p))]
+    text = "".join(h + "\n" + g + "\n" for h, g in pairs)
+    b, _ = _same_arrays(pt, text)
+    v, s, _ = b.contain()
+    b.free()
+    pv, ps, _ = pt.Batch(p.arrays()).contain()
+    assert (s == 0).all() and (v == pv).all() and v[:3000].all()
+    # blank lines, CRLF, indentation, tree first (the network becomes the host), branch lengths, no newline at the end
+    odd = ("\n\n  ((a:1.5,b:2):0.1,(c,d):3e-2);\r\n\t((a,(b)#H1:0.5),(#H1,(c,d)));   \n\n"
+           "((x,(y)#H7),(#H7,z));\n((x,y),z);\n   \n"
+           "(a,b,c);\n(c,b,a);")
+    b2, _ = _same_arrays(pt, odd)
+    v2, s2, _ = b2.contain()
+    b2.free()
+    assert b2.num_instances == 3 and (s2 == 0).all() and v2.tolist() == [True, True, True]
+    # an odd number of lines: the last one is ignored, like the host reader
+    b3, _ = _same_arrays(pt, "((a,b),c);\n((a,b),c);\n(a,b);\n")
+    assert b3.num_instances == 1
+    b3.free()
+    # empty text
+    b4 = pt.Batch.from_newick_text("")
+    assert b4.num_instances == 0
+    v4, s4, _ = b4.contain()
+    assert len(v4) == 0
+    b4.free()
+
+
+def test_device_reader_text_already_on_the_device(pt):
+    import torch
+    p = pt.Packer()
+    p.add_generated(2000, 50, 10, 4711, 0)
+    text = "".join(h + "\n" + g + "\n" for h, g in (p.newick(i) for i in range(len(p)))).encode()
+    t = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    b = pt.Batch.from_newick_text(t)
+    v, s, _ = b.contain()
+    b.free()
+    assert b.num_instances == 2000 and (s == 0).all() and v.all()
+
+
+def test_device_reader_reports_the_first_bad_pair(pt):
+    good = "((a,b),(c,d));\n((a,b),(c,d));\n"
+    for bad, what in [("((a,b),(c,d))\n((a,b),(c,d));\n", "expected ';'"), ("((a,b)#H,(c,d));\n((a,b),(c,d));\n", "hybrid number"),
+                      ("((a,b),(c,d));\n(a,b));\n", "unexpected start"), ("((a)#H1,(#H1,#H1));\n(a,b);\n", "double edge")]:
+        with pytest.raises(pt.MalformedNewick) as ei:
+            pt.Batch.from_newick_text(good * 5 + bad + good * 3)
+        assert "pair 5" in str(ei.value) and what in str(ei.value), str(ei.value)
+    with pytest.raises(pt.PtError) as ei:   # two networks: the guest has to be a tree (examples/tc.cpp:135-137)
+        pt.Batch.from_newick_text(good + "((a,(b)#H1),(#H1,c));\n((a,(b)#H1),(#H1,c));\n")
+    assert "pair 1" in str(ei.value) and "guest must be a tree" in str(ei.value)
