@@ -364,6 +364,41 @@ def iso_leg(pt, pairs=20000):
     return out
 
 
+def text_leg(pt, torch, pairs=100_000):
+    """SURVEY 8(f) rank 1 on the device: extended-Newick TEXT of the whole workload (two lines per instance) -> verdicts.
+    pt_batch_create_from_newick parses on the GPU (text from pinned host memory, upload included), pt_batch_contain solves;
+    compare newick_ingest (the same text through the host reader)"""
+    import numpy as np
+    p = pt.Packer()
+    p.add_generated(pairs, L, R, SEED, 0)
+    text = ("\n".join(h + "\n" + g for h, g in (p.newick(i) for i in range(pairs))) + "\n").encode()
+    pinned = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()
+    lib = pt.lib()
+    words = (pairs + 31) // 32
+    h_bits = torch.zeros(words + 1, dtype=torch.int32).pin_memory()
+    h_stat = torch.zeros(pairs + 1, dtype=torch.uint8).pin_memory()
+    opt = pt.Options(0, 0)
+    best_parse = best_total = 1e30
+    for it in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = ctypes.c_void_p()
+        n = ctypes.c_int64(0)
+        rc = lib.pt_batch_create_from_newick(ctypes.byref(h), pinned.data_ptr(), len(text), pt.PT_MEM_HOST, ctypes.byref(n), None)
+        assert rc == 0, lib.pt_last_error()
+        t1 = time.perf_counter()
+        rc = lib.pt_batch_contain(h, ctypes.byref(opt), h_bits.data_ptr(), h_stat.data_ptr(), pt.PT_MEM_HOST, None, None)
+        assert rc == 0, lib.pt_last_error()
+        t2 = time.perf_counter()
+        lib.pt_batch_free(h)
+        if it:
+            best_parse, best_total = min(best_parse, t1 - t0), min(best_total, t2 - t0)
+    disp = int(np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[:pairs].sum())
+    return {"workload": "extended-Newick text of %d instances (l=%d, r=%d), %d bytes, pinned host memory -> verdicts" % (pairs, L, R, len(text)),
+            "parse_pairs_per_s": pairs / best_parse, "parse_ms": best_parse * 1e3, "parse_GB_per_s": len(text) / best_parse / 1e9,
+            "text_to_verdict_pairs_per_s": pairs / best_total, "text_to_verdict_ms": best_total * 1e3, "displayed": disp}
+
+
 def ingest_leg(pt, pairs=20000):
     """text -> flat arrays: the parallel batch reader on the first `pairs` instances of the workload"""
     p = pt.Packer()
@@ -557,6 +592,10 @@ def main():
             out["iso"] = iso_leg(pt)
         except Exception as ex:
             out["iso"] = {"error": repr(ex)}
+        try:
+            out["newick_on_gpu"] = text_leg(pt, torch)
+        except Exception as ex:
+            out["newick_on_gpu"] = {"error": repr(ex)}
         for key, leg in (("who_displays", who_leg), ("bridges", bridges_leg)):
             try:
                 out[key] = leg(pt)
