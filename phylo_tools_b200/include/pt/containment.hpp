@@ -34,6 +34,32 @@ inline void throw_status(int rc, const char* where) {
   throw EngineError(rc, msg);
 }
 
+// many pairs given as TEXT (two extended-Newick lines per instance): parsed on the GPU into a device-resident batch
+// (pt_batch_create_from_newick) and solved there; no flat arrays on the host at all
+class NewickTextContainment {
+  std::vector<uint8_t> status_;
+  std::vector<bool> verdict_;
+  pt_counters counters_{};
+
+ public:
+  explicit NewickTextContainment(const std::string& text, void* stream = nullptr) {
+    pt_batch* h = nullptr;
+    int64_t pairs = 0;
+    throw_status(pt_batch_create_from_newick(&h, text.data(), (int64_t)text.size(), PT_MEM_HOST, &pairs, stream), "pt_batch_create_from_newick");
+    std::vector<uint32_t> bits((size_t)(pairs + 31) / 32 + 1, 0);
+    status_.assign((size_t)pairs + 1, 0);
+    const int rc = pt_batch_contain(h, nullptr, bits.data(), status_.data(), PT_MEM_HOST, &counters_, stream);
+    pt_batch_free(h);
+    throw_status(rc, "pt_batch_contain");
+    verdict_.resize((size_t)pairs);
+    for (size_t i = 0; i < (size_t)pairs; ++i) verdict_[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+  }
+  size_t size() const { return verdict_.size(); }
+  bool displayed(size_t i) const { return verdict_.at(i); }
+  int status(size_t i) const { return status_.at(i); }
+  const pt_counters& counters() const { return counters_; }
+};
+
 // many (host, guest) pairs at once
 class BatchContainment {
   BatchPacker packer_;

@@ -44,9 +44,7 @@ int main(int argc, char** argv) {
     if (!batch.empty()) {
       if (!file_exists(batch)) { std::cerr << batch << " cannot be opened for reading" << std::endl; return EXIT_FAILURE; }
       std::ifstream in(batch, std::ios::binary); std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-      BatchContainment bc;
-      bc.add_newick_text(text);   // parallel batch reader (pt/fast_newick.hpp)
-      bc.run();
+      NewickTextContainment bc(text);   // parsed and solved on the GPU (pt_batch_create_from_newick)
       for (size_t i = 0; i < bc.size(); ++i) std::cout << (bc.status(i) ? "error" : (bc.displayed(i) ? "displayed" : "not displayed")) << "\n";
       return EXIT_SUCCESS;
     }

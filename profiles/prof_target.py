@@ -19,6 +19,16 @@ if what == "tc":
         b.contain(result_bits=bits, status=stat, want_counters=False)
     torch.cuda.synchronize()
     print("tc ok", b.round_ms(0), "ms round 0")
+elif what == "text":
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
+    p = pt.Packer(); p.add_generated(B, 100, 20, 0xB200, 0)
+    text = ("\n".join(h + "\n" + g for h, g in (p.newick(i) for i in range(B))) + "\n").encode()
+    t = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    for _ in range(2):
+        b = pt.Batch.from_newick_text(t)
+        b.free()
+    torch.cuda.synchronize()
+    print("text ok", len(text), "bytes")
 elif what == "lca":
     leaves = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
     q = int(sys.argv[3]) if len(sys.argv) > 3 else 100_000_000
