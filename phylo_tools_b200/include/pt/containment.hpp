@@ -31,6 +31,7 @@ inline void throw_status(int rc, const char* where) {
   if (rc == PT_OK) return;
   const std::string msg = std::string(where) + ": " + pt_last_error();
   if (rc == PT_ERR_INVALID) throw std::logic_error(msg);
+  if (rc == PT_ERR_PARSE) throw MalformedNewick(std::string(), 0, msg);   // io/newick.hpp:15-26
   throw EngineError(rc, msg);
 }
 

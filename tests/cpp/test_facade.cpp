@@ -78,6 +78,13 @@ int main(int argc, char** argv) {
   b.add_newick("((a,b),(c,d));", "(((a)#H1,b),(#H1,(c,d)));");  // tree first, network second -> network is the host
   b.run();
   assert(b.displayed(0) && b.displayed(1) && b.counters().instances == 2);
+  {  // the same two pairs as text, parsed on the GPU
+    NewickTextContainment t("((a,b),(c,d));\n((a,b),(c,d));\n\n((a,b),(c,d));\n(((a)#H1,b),(#H1,(c,d)));\n");
+    assert(t.size() == 2 && t.displayed(0) && t.displayed(1) && t.status(0) == 0 && t.counters().instances == 2);
+    bool bad = false;
+    try { NewickTextContainment u("((a,b),(c,d));\n((a,b),(c,d))\n"); } catch (const MalformedNewick&) { bad = true; }
+    assert(bad);
+  }
   b.run_all_gpus();   // every GPU of the node, one host thread each
   assert(b.displayed(0) && b.displayed(1) && b.counters().instances == 2);
   // LCA: the tree of rmq/lca.cpp:24-43 and its four known answers
