@@ -61,8 +61,10 @@ __host__ const char* nw_error_text(int code) {
   }
 }
 
-struct NwScratch {  // all int32, addressed by region index (region of line k starts at lbeg[k] + 2k, holds llen[k] + 2 entries)
-  int32_t *tl, *hd, *lo, *ll, *st, *hk, *hi;
+struct NwScratch {  // addressed by region index (region of line k starts at lbeg[k] + 2k, holds llen[k] + 2 entries)
+  int2 *arc;  // (tail, head) in reference arc order          -- one 8-byte store per arc: every thread writes its own region, so
+  int2 *lab;  // (offset, length) of each node's name in the line   a store costs a 32-byte sector whatever its width
+  int32_t *st, *hk, *hi;
 };
 __device__ __forceinline__ bool nw_ws(char c) { return c == ' ' || (unsigned)(c - 9) < 5u; }
 __device__ __forceinline__ bool nw_digit(char c) { return c >= '0' && c <= '9'; }
@@ -75,7 +77,8 @@ __global__ void nw_parse_kernel(const char* __restrict__ text, int64_t num_lines
   const char* s = text + lbeg[k];
   const int len = llen[k];
   const int64_t reg = lbeg[k] + 2 * k;
-  int32_t *tl = S.tl + reg, *hd = S.hd + reg, *lo = S.lo + reg, *ll = S.ll + reg, *st = S.st + reg, *hk = S.hk + reg, *hi = S.hi + reg;
+  int2 *arc = S.arc + reg, *lab = S.lab + reg;
+  int32_t *st = S.st + reg, *hk = S.hk + reg, *hi = S.hi + reg;
   int n = 0, m = 0, nh = 0, sp = 0, err = NW_OK, has_h = 0;
   int back = len - 1;
 #define NW_SKIP_WS() while (back >= 0 && nw_ws(s[back])) --back
@@ -103,16 +106,16 @@ __global__ void nw_parse_kernel(const char* __restrict__ text, int64_t num_lines
             while (d < nb + nl && nw_digit(s[d])) { key = key * 10 + (s[d] - '0'); ++d; }
             id = -1;
             for (int h = 0; h < nh; ++h) if (hk[h] == key) { id = hi[h]; break; }
-            if (id < 0) { id = n; hk[nh] = key; hi[nh++] = id; lo[n] = nb; ll[n] = sharp - nb; ++n; }
+            if (id < 0) { id = n; hk[nh] = key; hi[nh++] = id; lab[n] = make_int2(nb, sharp - nb); ++n; }
             has_h = 1;
-          } else { id = n; lo[n] = nb; ll[n] = nl; ++n; }
+          } else { id = n; lab[n] = make_int2(nb, nl); ++n; }
           if (back > 0 && s[back] == ')') { --back; st[sp++] = id; NW_SKIP_LEN(); continue; }
           done = id; want = false;
         }
         NW_SKIP_WS();
         if (sp == 0) break;
         const int parent = st[sp - 1];
-        tl[m] = parent; hd[m++] = done;
+        arc[m++] = make_int2(parent, done);
         if (back < 0) { err = NW_START; break; }
         const char c = s[back];
         if (c == ',') { --back; NW_SKIP_LEN(); want = true; }
@@ -144,7 +147,9 @@ __global__ void nw_pair_kernel(const char* __restrict__ text, int64_t num_pairs,
   swapped[p] = sw;
   // label dictionary: open addressing over the pair's contiguous span of the `st` scratch (free after parsing)
   const int64_t reg_a = lbeg[a] + 2 * a, reg_b = lbeg[b] + 2 * b, span = reg_b + llen[b] + 2 - reg_a;
-  int cap = 1; while ((int64_t)cap * 2 <= span) cap <<= 1;
+  int named = 0;
+  for (int side = 0; side < 2; ++side) { const int64_t L = side ? G : H, reg = lbeg[L] + 2 * L; for (int v = 0; v < ln[L]; ++v) named += S.lab[reg + v].y > 0; }
+  int cap = 1; while ((int64_t)cap * 2 <= span && cap < 2 * named + 2) cap <<= 1;   // > named, and inside the pair's span (a name costs >= 2 characters)
   int32_t* slots = S.st + reg_a;  // entry = region index of the first node with that label, relative to reg_a; -1 empty
   for (int i = 0; i < cap; ++i) slots[i] = -1;
   int count = 0;
@@ -153,7 +158,8 @@ __global__ void nw_pair_kernel(const char* __restrict__ text, int64_t num_pairs,
     const char* base = text + lbeg[L];
     const int n = ln[L];
     for (int v = 0; v < n; ++v) {
-      const int off = S.lo[reg + v], len = S.ll[reg + v];
+      const int2 sp = S.lab[reg + v];
+      const int off = sp.x, len = sp.y;
       int id = -1;
       if (len > 0) {
         unsigned h = 2166136261u;
@@ -165,7 +171,8 @@ __global__ void nw_pair_kernel(const char* __restrict__ text, int64_t num_pairs,
           const int64_t g = reg_a + sidx;                      // an earlier node: in line a's region or in line b's
           const int64_t gl = g >= reg_b ? b : a;
           const char* gb = text + lbeg[gl];
-          const int goff = S.lo[g], glen = S.ll[g];
+          const int2 gs = S.lab[g];
+          const int goff = gs.x, glen = gs.y;
           bool same = glen == len;
           for (int k = 0; same && k < len; ++k) same = gb[goff + k] == base[off + k];
           if (same) { id = S.hk[g]; break; }
@@ -191,13 +198,13 @@ __global__ void nw_emit_kernel(int64_t num_pairs, const int64_t* __restrict__ lb
   const int64_t rh = lbeg[H] + 2 * H, rg = lbeg[G] + 2 * G;
   const int n = ln[H], m = lm[H], nt = ln[G], mt = lm[G];
   OUT* O = succ_off + hoff[p] + p; OUT* A = succ_adj + aoff[p];
-  const int32_t *tl = S.tl + rh, *hd = S.hd + rh;
+  const int2* arc = S.arc + rh;
   int32_t* cur = S.hi + rh;  // cursors (the hybrid ids are no longer needed)
   for (int v = 0; v <= n; ++v) O[v] = 0;
-  for (int e = 0; e < m; ++e) O[tl[e] + 1] = (OUT)(O[tl[e] + 1] + 1);
+  for (int e = 0; e < m; ++e) { const int t = arc[e].x; O[t + 1] = (OUT)(O[t + 1] + 1); }
   for (int v = 0; v < n; ++v) O[v + 1] = (OUT)(O[v + 1] + O[v]);
   for (int v = 0; v < n; ++v) cur[v] = O[v + 1];
-  for (int e = 0; e < m; ++e) A[--cur[tl[e]]] = (OUT)hd[e];   // children in reverse arc order (Phylogeny::build)
+  for (int e = 0; e < m; ++e) { const int2 a2 = arc[e]; A[--cur[a2.x]] = (OUT)a2.y; }   // children in reverse arc order (Phylogeny::build)
   bool dbl = false;
   for (int v = 0; v < n; ++v) for (int x = O[v]; x < O[v + 1]; ++x) for (int y = x + 1; y < O[v + 1]; ++y) dbl |= A[x] == A[y];
   if (dbl) atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)NW_DOUBLE);
@@ -205,8 +212,8 @@ __global__ void nw_emit_kernel(int64_t num_pairs, const int64_t* __restrict__ lb
   for (int v = 0; v < n; ++v) HL[v] = (OUT)S.hk[rh + v];
   OUT* GP = gparent + goff[p]; OUT* GL = glabel + goff[p];
   for (int v = 0; v < nt; ++v) { GP[v] = (OUT)-1; GL[v] = (OUT)S.hk[rg + v]; }
-  const int32_t *gtl = S.tl + rg, *ghd = S.hd + rg;
-  for (int e = 0; e < mt; ++e) GP[ghd[e]] = (OUT)gtl[e];
+  const int2* garc = S.arc + rg;
+  for (int e = 0; e < mt; ++e) { const int2 a2 = garc[e]; GP[a2.y] = (OUT)a2.x; }
 }
 
 __global__ void nw_set_first_kernel(int64_t* a, int64_t* b, int64_t* c) { a[0] = 0; b[0] = 0; c[0] = 0; }
@@ -271,7 +278,8 @@ extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int
   // ---- 2. parse every line ----
   const size_t S_len = (size_t)len + 2 * (size_t)num_lines + 8;
   NwScratch S{};
-  int32_t** sarr[7] = {&S.tl, &S.hd, &S.lo, &S.ll, &S.st, &S.hk, &S.hi};
+  NW_TRY(alloc((void**)&S.arc, S_len * 8, true)); NW_TRY(alloc((void**)&S.lab, S_len * 8, true));
+  int32_t** sarr[3] = {&S.st, &S.hk, &S.hi};
   for (auto pp : sarr) NW_TRY(alloc((void**)pp, S_len * 4, true));
   int32_t *d_ln = nullptr, *d_lm = nullptr, *d_lh = nullptr, *d_le = nullptr;
   for (int32_t** pp : {&d_ln, &d_lm, &d_lh, &d_le}) NW_TRY(alloc((void**)pp, (size_t)(num_lines + 1) * 4, true));
