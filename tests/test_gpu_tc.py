@@ -359,6 +359,55 @@ def test_contain_multi_matches_single_batch(pt, gold_tc):
     assert s[900] == 2 and (np.delete(s, 900) == 0).all() and (np.delete(v, 900) == np.delete(v1, 900)).all()
 
 
+def test_verdict_is_invariant_under_renumbering(pt):
+    """metamorphic, at BASELINE config 2's size (no oracle can enumerate 2^20 switchings per instance): writing host and guest
+    with shuffled child order and hybrid numbering renumbers every node and reorders every adjacency list -- the verdicts of
+    displayed (kind 0), label-swapped (kind 1) and random (kind 2) guests must not move"""
+    import random
+    from oracle.newick import parse_newick, write_newick
+    rnd = random.Random(99)
+    p = pt.Packer()
+    p.add_generated(250, 100, 20, 1234, 0); p.add_generated(250, 100, 20, 2234, 1); p.add_generated(100, 100, 20, 3234, 2)
+    pairs = [p.newick(i) for i in range(len(p))]
+    v0, s0, _ = pt.Batch(p.arrays()).contain()
+
+    def shuffled(nw):
+        n, e, lab = parse_newick(nw)
+        e = list(e); rnd.shuffle(e)
+        return write_newick(n, e, lab)
+    text = "".join(shuffled(h) + "\n" + shuffled(g) + "\n" for h, g in pairs)
+    b = pt.Batch.from_newick_text(text)
+    v1, s1, _ = b.contain()
+    b.free()
+    assert (s0 == 0).all() and (s1 == 0).all()
+    assert (v0 == v1).all() and v0[:250].all() and not v0[500:].any()
+
+
+def test_concurrent_handles_from_host_threads(pt, gold_tc):
+    """distinct handles driven from distinct host threads (the C-ABI's threading contract): same verdicts as one after the other"""
+    import threading
+    items = gold_tc["items"]
+    p = pt.Packer()
+    for it in items:
+        p.add_newick(it["host"], it["guest"])
+    p.add_generated(3000, 60, 12, 555, 0)
+    a = p.arrays(compact=True)
+    ref, sref, _ = pt.Batch(a).contain()
+    out = [None] * 6
+
+    def work(k):
+        for _ in range(3):
+            b = pt.Batch(a)
+            v, s, _ = b.contain(path=(0, 2, 3)[k % 3])
+            b.free()
+            out[k] = (v, s)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    for t in th: t.start()
+    for t in th: t.join()
+    for v, s in out:
+        assert (v == ref).all() and (s == sref).all()
+
+
 def test_edge_cases(pt, oracle):
     """empty batch, one-node trees, one and two labels, unlabelled hosts, ragged batch (tiny next to large instances)"""
     b = pt.Batch(dict(num_instances=0, host_node_off=np.zeros(1, np.int64), host_arc_off=np.zeros(1, np.int64), guest_node_off=np.zeros(1, np.int64),
