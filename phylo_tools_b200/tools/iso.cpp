@@ -17,10 +17,15 @@ using Net = RONetwork<>;
 using ENL = EdgesAndNodeLabels<Net>;
 
 static int usage(const char* argv0) {
-  std::cerr << argv0 << " <file1> [file2]\n\tfile1 and file2 describe two networks (either file1 contains 2 lines of extended newick or both file1 and file2 describe a network in extended newick or edgelist format)\n"
-            << "FLAGS:\n\t-v\tverbose output, prints networks\n\t-mr\tlabels of reticulations have to match\n\t-mt\tlabels of non-leaf tree vertices have to match\n"
-            << "\t-ma\tlabels of all vertices have to match (shortcut for -mr -mt (-ma overrides -il))\n\t-il\tlabels of leaves do NOT have to match\n"
-            << argv0 << " --batch <file>\n\tcheck every pair of lines of <file>; one verdict per line\n";
+  std::cerr << "usage: " << argv0 << " [flags] <file1> [file2]\n"
+            << "  two networks in extended Newick or edge-list format: both in file1 (one per line), or one in each file\n"
+            << "  -v    print both networks before checking\n"
+            << "  -mr   reticulation labels must agree\n"
+            << "  -mt   labels of internal tree nodes must agree\n"
+            << "  -ma   all labels must agree (= -mr -mt, and leaf labels even with -il)\n"
+            << "  -il   ignore leaf labels\n"
+            << "usage: " << argv0 << " [flags] --batch <file>\n"
+            << "  every two lines of <file> are one pair; prints one verdict per line\n";
   return EXIT_FAILURE;
 }
 
