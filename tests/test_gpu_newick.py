@@ -84,3 +84,51 @@ def test_device_reader_reports_the_first_bad_pair(pt):
     with pytest.raises(pt.PtError) as ei:   # two networks: the guest has to be a tree (examples/tc.cpp:135-137)
         pt.Batch.from_newick_text(good + "((a,(b)#H1),(#H1,c));\n((a,(b)#H1),(#H1,c));\n")
     assert "pair 1" in str(ei.value) and "guest must be a tree" in str(ei.value)
+
+
+def test_device_reader_fuzz_against_host_reader(pt):
+    """mutated Newick lines (characters deleted, duplicated, replaced by structure characters): the device reader must accept
+    exactly what the host reader accepts, with identical arrays, and reject the rest -- never crash or hang"""
+    import random
+    rnd = random.Random(4242)
+    p = pt.Packer()
+    p.add_generated(60, 8, 3, 321, 0)
+    base = [p.newick(i) for i in range(len(p))]
+    alphabet = "(),;#H:0123456789ab \t"
+    ok = bad = 0
+    for it in range(1500):
+        h, g = base[it % len(base)]
+        s = list(h if it % 2 else g)
+        for _ in range(rnd.randint(1, 3)):
+            k = rnd.randrange(len(s))
+            op = rnd.randrange(3)
+            if op == 0:
+                del s[k]
+            elif op == 1:
+                s.insert(k, rnd.choice(alphabet))
+            else:
+                s[k] = rnd.choice(alphabet)
+        m = "".join(s).replace("\n", "")
+        text = (m + "\n" + g + "\n") if it % 2 else (h + "\n" + m + "\n")
+        host_err = dev_err = None
+        q = pt.Packer()
+        try:
+            q.add_newick_text(text)
+        except Exception as ex:
+            host_err = ex
+        try:
+            b = pt.Batch.from_newick_text(text)
+        except Exception as ex:
+            dev_err = ex
+        assert (host_err is None) == (dev_err is None), (text, host_err, dev_err)
+        if host_err is None:
+            d = b.download()
+            a = q.arrays(compact=d["index_bytes"] == 2)
+            for key in KEYS:
+                assert (d[key] == a[key]).all(), (key, text)
+            b.free()
+            ok += 1
+        else:
+            assert type(host_err).__name__ == type(dev_err).__name__, (text, host_err, dev_err)
+            bad += 1
+    assert ok > 100 and bad > 100
