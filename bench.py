@@ -337,9 +337,9 @@ def bridges_leg(pt, leaves=499_001, retis=1000):
             "bridges": int(br.sum()), "components": int(len(set(comp.tolist())))}
 
 
-def iso_leg(pt, pairs=20000):
+def iso_leg(pt, torch, pairs=20000):
     """batched network isomorphism (pt_iso_batch) on pairs of config-2-sized networks: each network against an
-    identical copy (isomorphic) and against the next one (not isomorphic); wall time of the call incl. the upload"""
+    identical copy (isomorphic) and against the next one (not isomorphic); wall time of the call incl. the upload from pinned memory"""
     import numpy as np
     p = pt.Packer()
     p.add_generated(pairs + 1, L, R, SEED + 6, 0)
@@ -350,7 +350,7 @@ def iso_leg(pt, pairs=20000):
 
     def arrays(idx):
         g = len(idx)
-        c = lambda x: np.ascontiguousarray(x[idx]).ravel()
+        c = lambda x: torch.from_numpy(np.ascontiguousarray(x[idx]).ravel()).pin_memory().numpy()   # pinned, like the e2e leg
         return dict(num_pairs=g // 2, node_off=np.arange(g + 1, dtype=np.int64) * n, arc_off=np.arange(g + 1, dtype=np.int64) * m,
                     succ_off=c(so), succ_adj=c(sa), pred_off=c(po), pred_adj=c(pa), label=c(lab), max_nodes=n)
     out = {"workload": "%d pairs of gen networks l=%d r=%d (n = %d), leaf labels have to match" % (pairs, L, R, n)}
@@ -589,7 +589,7 @@ def main():
             out["newick_ingest"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            out["iso"] = iso_leg(pt)
+            out["iso"] = iso_leg(pt, torch)
         except Exception as ex:
             out["iso"] = {"error": repr(ex)}
         try:
