@@ -304,7 +304,7 @@ def config5_leg(pt, retis=24, leaves=30, rank=0, world=1, dist=None, torch=None)
             "note": "wall time of pt_enum_switchings incl. upload; bound by integer ALU + L1-resident accumulators, not HBM"}
 
 
-def who_leg(pt, leaves=1_000_000):
+def who_leg(pt, torch, leaves=1_000_000):
     """SURVEY 8(f) rank 2: TreeInTreeContainment::who_displays for every guest node, host = random binary tree with `leaves`
     leaves, guest = the same tree (every node is displayed, by itself); wall time of the call incl. upload and download"""
     import numpy as np
@@ -313,6 +313,7 @@ def who_leg(pt, leaves=1_000_000):
     deg = np.bincount(par[par >= 0], minlength=n)
     lab = np.full(n, -1, dtype=np.int32)
     lab[deg == 0] = np.arange(int((deg == 0).sum()), dtype=np.int32)
+    par, lab = torch.from_numpy(par).pin_memory().numpy(), torch.from_numpy(lab).pin_memory().numpy()
     pt.who_displays(par, lab, par, lab)  # warm-up
     t0 = time.perf_counter()
     out = pt.who_displays(par, lab, par, lab)
@@ -321,14 +322,14 @@ def who_leg(pt, leaves=1_000_000):
             "guest_nodes_per_s": n / dt, "ms": dt * 1e3, "verdicts_ok": bool((out == np.arange(n)).all())}
 
 
-def bridges_leg(pt, leaves=499_001, retis=1000):
+def bridges_leg(pt, torch, leaves=499_001, retis=1000):
     """bridges and bridge-free components of one network of BASELINE config 4's size (n = 10^6); wall time of
     pt_net_bridges incl. upload and download"""
     p = pt.Packer()
     p.add_generated(1, leaves, retis, SEED + 8, 0)
     a = p.arrays()
     n, m = int(a["host_node_off"][1]), int(a["host_arc_off"][1])
-    so, sa = a["host_succ_off"][:n + 1], a["host_succ_adj"][:m]
+    so, sa = torch.from_numpy(a["host_succ_off"][:n + 1].copy()).pin_memory().numpy(), torch.from_numpy(a["host_succ_adj"][:m].copy()).pin_memory().numpy()
     pt.net_bridges(so, sa)  # warm-up
     t0 = time.perf_counter()
     br, comp = pt.net_bridges(so, sa)
@@ -598,7 +599,7 @@ def main():
             out["newick_on_gpu"] = {"error": repr(ex)}
         for key, leg in (("who_displays", who_leg), ("bridges", bridges_leg)):
             try:
-                out[key] = leg(pt)
+                out[key] = leg(pt, torch)
             except Exception as ex:
                 out[key] = {"error": repr(ex)}
     if rank == 0 and not args.no_config4:
