@@ -231,8 +231,10 @@ extern "C" int pt_iso_batch(const pt_iso_desc* d, uint32_t* result_bits, uint8_t
   if (!d || !result_bits) return set_error(PT_ERR_INVALID, "pt_iso_batch: null argument");
   const int64_t P = d->num_pairs;
   if (P < 0 || P > (int64_t)INT32_MAX / 4) return set_error(PT_ERR_INVALID, "pt_iso_batch: bad num_pairs");
-  if (!d->node_off || !d->arc_off || !d->succ_off || !d->pred_off || !d->label || ((!d->succ_adj || !d->pred_adj) && P > 0))
-    return set_error(PT_ERR_INVALID, "pt_iso_batch: a required array is null");
+  if (!d->node_off || !d->arc_off || !d->succ_off || !d->pred_off || !d->label) return set_error(PT_ERR_INVALID, "pt_iso_batch: a required array is null");
+  // the adjacency arrays may only be null when there is not a single arc (HOST input can be checked here)
+  if ((!d->succ_adj || !d->pred_adj) && P > 0 && (d->mem != PT_MEM_HOST || d->arc_off[2 * P] > 0))
+    return set_error(PT_ERR_INVALID, "pt_iso_batch: succ_adj / pred_adj is null");
   if (int rc = require_device()) return rc;
   DeviceProps dp;
   if (int rc = device_props(&dp)) return rc;
