@@ -821,9 +821,11 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   if (!out || !d) return set_error(PT_ERR_INVALID, "pt_batch_create: null argument");
   *out = nullptr;
   if (d->num_instances < 0 || d->num_instances > (int64_t)INT32_MAX - 64) return set_error(PT_ERR_INVALID, "pt_batch_create: bad num_instances");
-  if (!d->host_node_off || !d->host_arc_off || !d->guest_node_off || !d->host_succ_off || !d->host_label || !d->guest_parent || !d->guest_label ||
-      (!d->host_succ_adj && d->num_instances > 0))
+  if (!d->host_node_off || !d->host_arc_off || !d->guest_node_off || !d->host_succ_off || !d->host_label || !d->guest_parent || !d->guest_label)
     return set_error(PT_ERR_INVALID, "pt_batch_create: a required array is null");
+  // host_succ_adj may only be null when the batch has no arc at all (std::vector::data() of an empty vector)
+  if (!d->host_succ_adj && d->num_instances > 0 && (d->mem != PT_MEM_HOST || d->host_arc_off[d->num_instances] > 0))
+    return set_error(PT_ERR_INVALID, "pt_batch_create: host_succ_adj is null");
   if (d->index_bytes != 0 && d->index_bytes != 2 && d->index_bytes != 4) return set_error(PT_ERR_INVALID, "pt_batch_create: index_bytes must be 0, 2 or 4");
   if (int rc = require_device()) return rc;
   cudaStream_t s = (cudaStream_t)stream;

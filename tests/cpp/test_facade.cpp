@@ -55,6 +55,7 @@ int main(int argc, char** argv) {
   assert(tc("((a,(b)#H1),(#H1,c));", "((a,b),c);"));
   assert(!tc("((a,(b)#H1),(#H1,c));", "((a,c),b);"));
   assert(tc("((a,b),(c,d));", "((d,c),(b,a));"));
+  assert(tc("a;", "a;"));   // one node on both sides: no arc at all (the adjacency array of the batch is empty / null)
   assert(!tc("((a,b),(c,d));", "((a,c),(b,d));"));
   // force_parent (containment.hpp:1186): H1 = node 4 in reader numbering of "((a,(b)#H1),(#H1,c));": edges (1,2)(1,3)... check via parents()
   {
