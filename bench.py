@@ -304,6 +304,24 @@ def config5_leg(pt, retis=24, leaves=30, rank=0, world=1, dist=None, torch=None)
             "note": "wall time of pt_enum_switchings incl. upload; bound by integer ALU + L1-resident accumulators, not HBM"}
 
 
+def config1_leg(pt):
+    """BASELINE configs[0]: the reference's own data/test.nw (one instance; ground truth "not displayed", the reference crashes on it):
+    latency of one pt_batch_create + pt_batch_contain + pt_batch_free from host arrays"""
+    p = pt.Packer()
+    p.add_newick("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));")
+    a = p.arrays()
+    ts = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        b = pt.Batch(a)
+        v, s, _ = b.contain(want_counters=False)
+        b.free()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return {"workload": "data/test.nw of the reference, one instance", "displayed": bool(v[0]), "status": int(s[0]), "latency_us_median": ts[len(ts) // 2] * 1e6,
+            "latency_us_min": ts[0] * 1e6, "note": "launch-latency bound: memsets, one kernel, one branching round, result copy"}
+
+
 def who_leg(pt, torch, leaves=1_000_000):
     """SURVEY 8(f) rank 2: TreeInTreeContainment::who_displays for every guest node, host = random binary tree with `leaves`
     leaves, guest = the same tree (every node is displayed, by itself); wall time of the call incl. upload and download"""
@@ -597,6 +615,10 @@ def main():
             out["newick_on_gpu"] = text_leg(pt, torch)
         except Exception as ex:
             out["newick_on_gpu"] = {"error": repr(ex)}
+        try:
+            out["config1"] = config1_leg(pt)
+        except Exception as ex:
+            out["config1"] = {"error": repr(ex)}
         for key, leg in (("who_displays", who_leg), ("bridges", bridges_leg)):
             try:
                 out[key] = leg(pt, torch)
