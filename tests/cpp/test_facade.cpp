@@ -8,6 +8,7 @@
 #include "../../phylo_tools_b200/include/pt/io.hpp"
 #include "../../phylo_tools_b200/include/pt/lca.hpp"
 #include "../../phylo_tools_b200/include/pt/bridges.hpp"
+#include "../../phylo_tools_b200/include/pt/isomorphism.hpp"
 #include <algorithm>
 #include <fstream>
 
@@ -103,6 +104,19 @@ int main(int argc, char** argv) {
     const int exp[7] = {-1, 0, 2, 5, 0, 3, 6};
     for (Node u = 0; u < 7; ++u) { const auto w = c.who_displays(u); assert(exp[u] < 0 ? w.empty() : (w.size() == 1 && w[0] == (Node)exp[u])); }
     assert(!c.displayed());
+  }
+  // isomorphism (utils/isomorphism.hpp:309-321): data/nets.nw of the reference, and what the flags change
+  {
+    auto net = [](const char* nw) { EdgeVec e; auto l = std::make_shared<LabelMapDefault>(); const size_t n = parse_newick(std::string(nw), e, l); return RONetwork<>(e, l, consecutive_tag(), n); };
+    const auto A = net("(a,(((b)#H1,(c)#H2),(#H1,#H2)),d);"), B = net("(d,(((b)#H1,(c)#H2),(#H1,#H2)),a);");
+    assert(make_iso_mapper(A, B, FLAG_MAP_LEAF_LABELS).check_isomorph());
+    const auto T1 = net("((a,b),(c,d));"), T2 = net("((a,c),(b,d));");
+    assert(!make_iso_mapper(T1, T2, FLAG_MAP_LEAF_LABELS).check_isomorph());
+    assert(make_iso_mapper(T1, T2, 0).check_isomorph());   // -il: same shape
+    BatchIsomorphism bi;
+    bi.add(A, B); bi.add(T1, T2); bi.add(T1, T1);
+    bi.run();
+    assert(bi.isomorph(0) && !bi.isomorph(1) && bi.isomorph(2));
   }
   std::cout << "facade ok\n";
   return 0;
