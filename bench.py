@@ -399,6 +399,24 @@ def iso_leg(pt, torch, pairs=20000):
         v, st = pt.iso_batch(arr)
         dt = time.perf_counter() - t0
         out[name] = {"pairs_per_s": pairs / dt, "ms": dt * 1e3, "verdicts_ok": bool(int(v.sum()) == want and (st == 0).all())}
+    # the same question asked from extended-Newick TEXT (pt_iso_from_newick: parsed and compared on the device)
+    lines = [p.newick(i)[0] for i in range(pairs + 1)]
+    text = ("\n".join(lines[i] + "\n" + lines[i + 1] for i in range(pairs)) + "\n").encode()
+    pinned = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()
+    cap = len(text) // 4 + 2
+    bits = torch.zeros((cap + 31) // 32 + 1, dtype=torch.int32).pin_memory()
+    stat = torch.zeros(cap + 1, dtype=torch.uint8).pin_memory()
+    found = ctypes.c_int64(0)
+    best = 1e30
+    for it in range(3):
+        t0 = time.perf_counter()
+        rc = pt.lib().pt_iso_from_newick(pinned.data_ptr(), len(text), 0, 1, bits.data_ptr(), stat.data_ptr(), 0, ctypes.byref(found), None)
+        best = min(best, time.perf_counter() - t0)
+        if rc != 0:
+            raise RuntimeError("pt_iso_from_newick failed: %d" % rc)
+    nz = int((bits.numpy().view("uint32") != 0).sum())
+    out["not_isomorphic_from_text"] = {"pairs_per_s": pairs / best, "ms": best * 1e3, "text_mb": len(text) / 1e6,
+                                       "verdicts_ok": bool(found.value == pairs and nz == 0 and int(stat[:pairs].sum()) == 0)}
     return out
 
 

@@ -121,6 +121,12 @@ typedef struct pt_iso_desc {
   int32_t max_nodes;         /* largest network of the batch; 0 = compute (HOST input only) */
 } pt_iso_desc;
 int pt_iso_batch(const pt_iso_desc* d, uint32_t* result_bits, uint8_t* status, pt_mem out_mem, void* stream);
+/* the same from TEXT: every two non-blank lines of text[0, len) are one pair of networks in extended Newick (the two-line file of
+ * examples/iso.cpp); parsed on the GPU (see pt_batch_create_from_newick) and solved there.  result_bits / status need room
+ * for len / 4 pairs at most (a pair takes at least four characters); *num_pairs receives the number found.  A malformed
+ * line or an odd number of lines: PT_ERR_PARSE (naming the first bad pair), nothing is written. */
+int pt_iso_from_newick(const char* text, int64_t len, pt_mem mem, int32_t flags, uint32_t* result_bits, uint8_t* status, pt_mem out_mem,
+                       int64_t* num_pairs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Bridges -- replaces  BridgeFinder / list_bridges(N, root)   utils/bridges.hpp:42-128

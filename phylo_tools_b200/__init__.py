@@ -427,3 +427,18 @@ def iso_newick(pairs, flags=1):
                     lab[v] = ids.setdefault(name, len(ids))
             nets.append((n, edges, lab))
     return iso_batch(iso_arrays(nets), flags)
+
+
+def iso_newick_text(text, flags=1):
+    """pt_iso_from_newick: two extended-Newick lines per pair, parsed and compared on the GPU -> (bool verdicts, status)"""
+    data = text if isinstance(text, (bytes, bytearray)) else text.encode()
+    cap = len(data) // 4 + 2
+    bits = np.zeros((cap + 31) // 32 + 1, dtype=np.uint32)
+    status = np.zeros(cap + 1, dtype=np.uint8)
+    n = C.c_int64(0)
+    rc = _L.pt_iso_from_newick(C.cast(C.c_char_p(bytes(data)), C.c_void_p), len(data), PT_MEM_HOST, int(flags), bits.ctypes.data, status.ctypes.data, PT_MEM_HOST, C.byref(n), None)
+    if rc == _capi.PT_ERR_PARSE:
+        raise MalformedNewick((_L.pt_last_error() or b"").decode(errors="replace"))
+    _check(rc, "pt_iso_from_newick")
+    P = int(n.value)
+    return np.unpackbits(bits.view(np.uint8), bitorder="little")[:P].astype(bool), status[:P]

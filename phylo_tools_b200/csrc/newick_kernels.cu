@@ -226,24 +226,92 @@ __global__ void nw_emit_kernel(int64_t num_pairs, const int64_t* __restrict__ lb
   for (int e = 0; e < mt; ++e) { const int2 a2 = garc[e]; GP[a2.y] = (OUT)a2.x; }
 }
 
+// ---- pairs of NETWORKS for pt_iso_from_newick: no host / guest roles, both lines keep their order ------------------------------
+// label ids shared by the two networks of a pair (first appearance: first line, then second), sizes per graph g = 2 * pair + side
+__global__ void nw_iso_pair_kernel(const char* __restrict__ text, int64_t num_pairs, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen, NwScratch S,
+                                   const int32_t* __restrict__ ln, const int32_t* __restrict__ lm, const int32_t* __restrict__ lerr,
+                                   int64_t* __restrict__ gn, int64_t* __restrict__ gm, int32_t* __restrict__ max_nodes, unsigned long long* __restrict__ first_err) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= num_pairs) return;
+  const int64_t a = 2 * p, b = 2 * p + 1;
+  gn[a] = ln[a]; gn[b] = ln[b]; gm[a] = lm[a]; gm[b] = lm[b];
+  const int err = lerr[a] ? lerr[a] : lerr[b];
+  if (err) { atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)err); return; }
+  const int64_t reg_a = lbeg[a] + 2 * a, reg_b = lbeg[b] + 2 * b, span = reg_b + llen[b] + 2 - reg_a;
+  int named = 0;
+  for (int side = 0; side < 2; ++side) { const int64_t L = side ? b : a, reg = lbeg[L] + 2 * L; for (int v = 0; v < ln[L]; ++v) named += S.lab[reg + v].y > 0; }
+  int cap = 1; while ((int64_t)cap * 2 <= span && cap < 2 * named + 2) cap <<= 1;
+  int32_t* slots = S.st + reg_a;
+  for (int i = 0; i < cap; ++i) slots[i] = -1;
+  int count = 0;
+  for (int side = 0; side < 2; ++side) {
+    const int64_t L = side ? b : a, reg = lbeg[L] + 2 * L;
+    const char* base = text + lbeg[L];
+    for (int v = 0; v < ln[L]; ++v) {
+      const int2 sp = S.lab[reg + v];
+      int id = -1;
+      if (sp.y > 0) {
+        unsigned h = 2166136261u;
+        for (int k = 0; k < sp.y; ++k) h = (h ^ (unsigned char)base[sp.x + k]) * 16777619u;
+        int i = (int)(h & (unsigned)(cap - 1));
+        for (;;) {
+          const int sidx = slots[i];
+          if (sidx < 0) { slots[i] = (int)(reg + v - reg_a); id = count++; break; }
+          const int64_t g = reg_a + sidx;
+          const char* gb = text + lbeg[g >= reg_b ? b : a];
+          const int2 gs = S.lab[g];
+          bool same = gs.y == sp.y;
+          for (int k = 0; same && k < sp.y; ++k) same = gb[gs.x + k] == base[sp.x + k];
+          if (same) { id = S.hk[g]; break; }
+          i = (i + 1) & (cap - 1);
+        }
+      }
+      S.hk[reg + v] = id;
+    }
+  }
+  atomicMax(max_nodes, max(ln[a], ln[b]));
+}
+// one thread per GRAPH: successor and predecessor CSR (the order inside a list does not matter to pt_iso_batch) and label ids
+__global__ void nw_iso_emit_kernel(int64_t num_graphs, const int64_t* __restrict__ lbeg, NwScratch S, const int32_t* __restrict__ ln, const int32_t* __restrict__ lm,
+                                   const int64_t* __restrict__ noff, const int64_t* __restrict__ aoff, int32_t* __restrict__ succ_off, int32_t* __restrict__ succ_adj,
+                                   int32_t* __restrict__ pred_off, int32_t* __restrict__ pred_adj, int32_t* __restrict__ label) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= num_graphs) return;
+  const int64_t reg = lbeg[g] + 2 * g;
+  const int n = ln[g], m = lm[g];
+  const int2* arc = S.arc + reg;
+  int32_t* cur = S.hi + reg;
+  for (int dir = 0; dir < 2; ++dir) {
+    int32_t* O = (dir ? pred_off : succ_off) + noff[g] + g; int32_t* A = (dir ? pred_adj : succ_adj) + aoff[g];
+    for (int v = 0; v <= n; ++v) O[v] = 0;
+    for (int e = 0; e < m; ++e) O[(dir ? arc[e].y : arc[e].x) + 1]++;
+    for (int v = 0; v < n; ++v) O[v + 1] += O[v];
+    for (int v = 0; v < n; ++v) cur[v] = O[v + 1];
+    for (int e = 0; e < m; ++e) { const int2 a2 = arc[e]; A[--cur[dir ? a2.y : a2.x]] = dir ? a2.x : a2.y; }
+  }
+  int32_t* Lb = label + noff[g];
+  for (int v = 0; v < n; ++v) Lb[v] = S.hk[reg + v];
+}
+
 __global__ void nw_set_first_kernel(int64_t* a, int64_t* b, int64_t* c) { a[0] = 0; b[0] = 0; c[0] = 0; }
 
 }  // namespace ptgpu
 
-using namespace ptgpu;
+namespace ptgpu {
 
-extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int64_t len, pt_mem mem, int64_t* num_pairs, void* stream) {
-  if (!out || (!text && len > 0) || len < 0) return set_error(PT_ERR_INVALID, "pt_batch_create_from_newick: bad argument");
-  *out = nullptr;
-  if (num_pairs) *num_pairs = 0;
-  if (int rc = require_device()) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  std::vector<void*> tmp;  // freed on return
-  void* keep[8] = {};       // owned by the handle on success
-  auto cleanup = [&](bool ok) { cudaStreamSynchronize(s); for (void* p : tmp) dev_free(p); if (!ok) for (void* p : keep) dev_free(p); };
-  auto alloc = [&](void** p, size_t bytes, bool temp) -> int { const int rc = dev_alloc(p, std::max<size_t>(bytes, 16)); if (rc == PT_OK && temp) tmp.push_back(*p); return rc; };
-#define NW_TRY(expr) do { const int rc__ = (expr); if (rc__ != PT_OK) { cleanup(false); return rc__; } } while (0)
-#define NW_CUDA(call) do { const cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(false); return set_error(PT_ERR_CUDA, "pt_batch_create_from_newick: %s: %s", #call, cudaGetErrorString(e__)); } } while (0)
+// what both text entry points share: the device copy of the text, its non-blank lines, and every line parsed into scratch
+struct NwFront {
+  const char* d_text = nullptr;
+  int64_t num_lines = 0, P = 0;
+  int64_t* d_lbeg = nullptr; int32_t* d_llen = nullptr;
+  NwScratch S{};
+  int32_t *d_ln = nullptr, *d_lm = nullptr, *d_lh = nullptr, *d_le = nullptr;
+};
+// every allocation goes to `tmp` (the caller frees it, also on failure)
+static int nw_front(const char* text, int64_t len, pt_mem mem, cudaStream_t s, std::vector<void*>& tmp, NwFront& F) {
+  auto alloc = [&](void** p, size_t bytes, bool) -> int { const int rc = dev_alloc(p, std::max<size_t>(bytes, 16)); if (rc == PT_OK) tmp.push_back(*p); return rc; };
+#define NW_TRY(expr) do { const int rc__ = (expr); if (rc__ != PT_OK) return rc__; } while (0)
+#define NW_CUDA(call) do { const cudaError_t e__ = (call); if (e__ != cudaSuccess) return set_error(PT_ERR_CUDA, "newick reader: %s: %s", #call, cudaGetErrorString(e__)); } while (0)
   // own, 16-byte aligned copy of the text with 16 bytes of padding (the parser reads aligned 128-bit words)
   const char* d_text = nullptr;
   {
@@ -296,6 +364,32 @@ extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int
   int32_t *d_ln = nullptr, *d_lm = nullptr, *d_lh = nullptr, *d_le = nullptr;
   for (int32_t** pp : {&d_ln, &d_lm, &d_lh, &d_le}) NW_TRY(alloc((void**)pp, (size_t)(num_lines + 1) * 4, true));
   if (2 * P > 0) nw_parse_kernel<<<(unsigned)((2 * P + 127) / 128), 128, 0, s>>>(d_text, 2 * P, d_lbeg, d_llen, S, d_ln, d_lm, d_lh, d_le);
+  F.d_text = d_text; F.num_lines = num_lines; F.P = P; F.d_lbeg = d_lbeg; F.d_llen = d_llen; F.S = S; F.d_ln = d_ln; F.d_lm = d_lm; F.d_lh = d_lh; F.d_le = d_le;
+  return PT_OK;
+#undef NW_TRY
+#undef NW_CUDA
+}
+
+}  // namespace ptgpu
+
+using namespace ptgpu;
+
+extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int64_t len, pt_mem mem, int64_t* num_pairs, void* stream) {
+  if (!out || (!text && len > 0) || len < 0) return set_error(PT_ERR_INVALID, "pt_batch_create_from_newick: bad argument");
+  *out = nullptr;
+  if (num_pairs) *num_pairs = 0;
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<void*> tmp;  // freed on return
+  void* keep[8] = {};       // owned by the handle on success
+  auto cleanup = [&](bool ok) { cudaStreamSynchronize(s); for (void* p : tmp) dev_free(p); if (!ok) for (void* p : keep) dev_free(p); };
+  auto alloc = [&](void** p, size_t bytes, bool temp) -> int { const int rc = dev_alloc(p, std::max<size_t>(bytes, 16)); if (rc == PT_OK && temp) tmp.push_back(*p); return rc; };
+#define NW_TRY(expr) do { const int rc__ = (expr); if (rc__ != PT_OK) { cleanup(false); return rc__; } } while (0)
+#define NW_CUDA(call) do { const cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(false); return set_error(PT_ERR_CUDA, "pt_batch_create_from_newick: %s: %s", #call, cudaGetErrorString(e__)); } } while (0)
+  NwFront F;
+  NW_TRY(nw_front(text, len, mem, s, tmp, F));
+  const char* d_text = F.d_text; const int64_t P = F.P; int64_t* d_lbeg = F.d_lbeg; int32_t* d_llen = F.d_llen; NwScratch S = F.S;
+  int32_t *d_ln = F.d_ln, *d_lm = F.d_lm, *d_lh = F.d_lh, *d_le = F.d_le;
   // ---- 3. pairs ----
   int64_t *d_hn = nullptr, *d_hm = nullptr, *d_gn = nullptr; int32_t *d_sw = nullptr, *d_max = nullptr; unsigned long long* d_err = nullptr;
   for (int k = 0; k < 3; ++k) NW_TRY(alloc(&keep[k], (size_t)(P + 1) * 8, false));
@@ -348,6 +442,62 @@ extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int
   *out = h;
   if (num_pairs) *num_pairs = P;
   return PT_OK;
+#undef NW_TRY
+#undef NW_CUDA
+}
+
+// Isomorphism straight from text: every two non-blank lines are one pair of networks (the `iso` tool's two-line file, examples/iso.cpp),
+// parsed on the GPU like pt_batch_create_from_newick and handed to pt_iso_batch without ever leaving the device.
+extern "C" int pt_iso_from_newick(const char* text, int64_t len, pt_mem mem, int32_t flags, uint32_t* result_bits, uint8_t* status, pt_mem out_mem,
+                                  int64_t* num_pairs, void* stream) {
+  if ((!text && len > 0) || len < 0 || !result_bits) return set_error(PT_ERR_INVALID, "pt_iso_from_newick: bad argument");
+  if (num_pairs) *num_pairs = 0;
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { cudaStreamSynchronize(s); for (void* p : tmp) dev_free(p); };
+  auto alloc = [&](void** p, size_t bytes) -> int { const int rc = dev_alloc(p, std::max<size_t>(bytes, 16)); if (rc == PT_OK) tmp.push_back(*p); return rc; };
+#define NW_TRY(expr) do { const int rc__ = (expr); if (rc__ != PT_OK) { cleanup(); return rc__; } } while (0)
+#define NW_CUDA(call) do { const cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return set_error(PT_ERR_CUDA, "pt_iso_from_newick: %s: %s", #call, cudaGetErrorString(e__)); } } while (0)
+  NwFront F;
+  NW_TRY(nw_front(text, len, mem, s, tmp, F));
+  if (F.num_lines & 1) { cleanup(); return set_error(PT_ERR_PARSE, "pt_iso_from_newick: odd number of networks (%lld)", (long long)F.num_lines); }
+  const int64_t P = F.P, G = 2 * P;
+  int64_t *d_gn = nullptr, *d_gm = nullptr, *d_noff = nullptr, *d_aoff = nullptr; int32_t* d_max = nullptr; unsigned long long* d_err = nullptr;
+  NW_TRY(alloc((void**)&d_gn, (size_t)(G + 1) * 8)); NW_TRY(alloc((void**)&d_gm, (size_t)(G + 1) * 8));
+  NW_TRY(alloc((void**)&d_noff, (size_t)(G + 1) * 8)); NW_TRY(alloc((void**)&d_aoff, (size_t)(G + 1) * 8));
+  NW_TRY(alloc((void**)&d_max, 16)); NW_TRY(alloc((void**)&d_err, 8));
+  NW_CUDA(cudaMemsetAsync(d_max, 0, 16, s)); NW_CUDA(cudaMemsetAsync(d_err, 0xff, 8, s));
+  if (P > 0) nw_iso_pair_kernel<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(F.d_text, P, F.d_lbeg, F.d_llen, F.S, F.d_ln, F.d_lm, F.d_le, d_gn, d_gm, d_max, d_err);
+  nw_set_first_kernel<<<1, 1, 0, s>>>(d_noff, d_aoff, d_noff);
+  if (G > 0) {
+    size_t tb = 0;
+    NW_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, d_gn, d_noff + 1, G, s));
+    void* d_tmp = nullptr;
+    NW_TRY(alloc(&d_tmp, tb));
+    NW_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_gn, d_noff + 1, G, s));
+    NW_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_gm, d_aoff + 1, G, s));
+  }
+  int64_t totals[2] = {0, 0}; int32_t max_nodes = 0; unsigned long long first_err = ~0ull;
+  NW_CUDA(cudaMemcpyAsync(&totals[0], d_noff + G, 8, cudaMemcpyDeviceToHost, s)); NW_CUDA(cudaMemcpyAsync(&totals[1], d_aoff + G, 8, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaMemcpyAsync(&max_nodes, d_max, 4, cudaMemcpyDeviceToHost, s)); NW_CUDA(cudaMemcpyAsync(&first_err, d_err, 8, cudaMemcpyDeviceToHost, s));
+  NW_CUDA(cudaStreamSynchronize(s));
+  if (first_err != ~0ull) {
+    cleanup();
+    return set_error(PT_ERR_PARSE, "pair %lld: %s", (long long)(first_err >> 8), nw_error_text((int)(first_err & 0xff)));
+  }
+  int32_t *d_so = nullptr, *d_sa = nullptr, *d_po = nullptr, *d_pa = nullptr, *d_lab = nullptr;
+  NW_TRY(alloc((void**)&d_so, (size_t)(totals[0] + G) * 4)); NW_TRY(alloc((void**)&d_po, (size_t)(totals[0] + G) * 4));
+  NW_TRY(alloc((void**)&d_sa, (size_t)totals[1] * 4)); NW_TRY(alloc((void**)&d_pa, (size_t)totals[1] * 4)); NW_TRY(alloc((void**)&d_lab, (size_t)totals[0] * 4));
+  if (G > 0) nw_iso_emit_kernel<<<(unsigned)((G + 127) / 128), 128, 0, s>>>(G, F.d_lbeg, F.S, F.d_ln, F.d_lm, d_noff, d_aoff, d_so, d_sa, d_po, d_pa, d_lab);
+  NW_CUDA(cudaGetLastError());
+  pt_iso_desc d{};
+  d.num_pairs = P; d.mem = PT_MEM_DEVICE; d.node_off = d_noff; d.arc_off = d_aoff; d.succ_off = d_so; d.succ_adj = d_sa; d.pred_off = d_po; d.pred_adj = d_pa;
+  d.label = d_lab; d.flags = flags; d.max_nodes = std::max(max_nodes, 1);
+  const int rc = P > 0 ? pt_iso_batch(&d, result_bits, status, out_mem, stream) : PT_OK;
+  cleanup();
+  if (rc == PT_OK && num_pairs) *num_pairs = P;
+  return rc;
 #undef NW_TRY
 #undef NW_CUDA
 }

@@ -19,6 +19,26 @@
 
 namespace PT {
 
+// two extended-Newick lines per pair, parsed AND compared on the GPU (pt_iso_from_newick): the `iso --batch` route
+class NewickTextIsomorphism {
+  std::vector<uint8_t> verdict_, status_;
+
+ public:
+  explicit NewickTextIsomorphism(const std::string& text, unsigned char flags = FLAG_MAP_LEAF_LABELS, void* stream = nullptr) {
+    const size_t cap = text.size() / 4 + 2;
+    std::vector<uint32_t> bits((cap + 31) / 32 + 1, 0);
+    status_.assign(cap + 1, 0);
+    int64_t pairs = 0;
+    throw_status(pt_iso_from_newick(text.data(), (int64_t)text.size(), PT_MEM_HOST, flags, bits.data(), status_.data(), PT_MEM_HOST, &pairs, stream), "pt_iso_from_newick");
+    status_.resize((size_t)pairs);
+    verdict_.resize((size_t)pairs);
+    for (size_t i = 0; i < (size_t)pairs; ++i) verdict_[i] = (bits[i >> 5] >> (i & 31)) & 1u;
+  }
+  size_t size() const { return verdict_.size(); }
+  bool isomorph(size_t i) const { return verdict_.at(i) != 0; }
+  int status(size_t i) const { return status_.at(i); }
+};
+
 class BatchIsomorphism {
   std::vector<int64_t> node_off_{0}, arc_off_{0};
   std::vector<int32_t> succ_off_, succ_adj_, pred_off_, pred_adj_, label_;

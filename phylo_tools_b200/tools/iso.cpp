@@ -44,14 +44,9 @@ int main(int argc, char** argv) {
     std::vector<ENL> el;
     if (!batch.empty()) {
       if (!file_exists(batch)) { std::cerr << batch << " cannot be opened for reading" << std::endl; return EXIT_FAILURE; }
-      read_edgelists(batch, el);
-      if (el.size() % 2) { std::cerr << "odd number of networks in " << batch << std::endl; return EXIT_FAILURE; }
-      std::vector<Net> nets; nets.reserve(el.size());
-      for (auto& e : el) nets.emplace_back(e.edges, e.labels, consecutive_tag(), e.num_nodes);
-      BatchIsomorphism b;
-      for (size_t i = 0; i + 1 < nets.size(); i += 2) b.add(nets[i], nets[i + 1]);
-      b.run(flags);
-      for (size_t i = 0; i < b.size(); ++i) std::cout << (b.isomorph(i) ? "isomorph!" : "not isomorph!") << "\n";
+      std::ifstream in(batch, std::ios::binary); std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+      NewickTextIsomorphism b(text, flags);   // parsed and compared on the GPU (pt_iso_from_newick)
+      for (size_t i = 0; i < b.size(); ++i) std::cout << (b.status(i) ? "error" : (b.isomorph(i) ? "isomorph!" : "not isomorph!")) << "\n";
       return EXIT_SUCCESS;
     }
     if (files.empty() || files.size() > 2) return usage(argv[0]);
