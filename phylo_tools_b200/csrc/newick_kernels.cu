@@ -140,157 +140,195 @@ __global__ void nw_parse_kernel(const char* __restrict__ text, int64_t num_lines
 }
 
 // per pair: host / guest, label ids (written over the hybrid-key scratch of each node), sizes, maxima, first error
-__global__ void nw_pair_kernel(const char* __restrict__ text, int64_t num_pairs, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen, NwScratch S,
+// ONE WARP per pair.  Label ids must come out in first-appearance order (host line, then guest line), so the nodes are taken in
+// chunks of 32 in that order: inside a chunk every lane hashes and probes its own name, a slot keeps the SMALLEST node index of its
+// label (claim by CAS, lower by atomicMin), and the lanes that ended up owning a slot number the new labels by lane order.
+__device__ __forceinline__ void nw_label_chunks(const char* __restrict__ text, const int64_t* __restrict__ lbeg, NwScratch S, int64_t L, int n, int64_t reg_a, int64_t reg_b,
+                                                int64_t la, int64_t lb, int32_t* slots, int cap, int& count, int lane) {
+  const int64_t reg = lbeg[L] + 2 * L;
+  const char* base = text + lbeg[L];
+  for (int v0 = 0; v0 < n; v0 += 32) {
+    const int v = v0 + lane;
+    const int2 sp = v < n ? S.lab[reg + v] : make_int2(0, 0);
+    const int me = (int)(reg + v - reg_a);
+    const int chunk_end = (int)(reg - reg_a) + min(v0 + 32, n);  // nodes of THIS chunk of THIS line are [me - lane, chunk_end)
+    int pos = -1;
+    if (sp.y > 0) {
+      unsigned h = 2166136261u;
+      for (int k = 0; k < sp.y; ++k) h = (h ^ (unsigned char)base[sp.x + k]) * 16777619u;
+      int i = (int)(h & (unsigned)(cap - 1));
+      for (;;) {
+        int sidx = __ldcg(&slots[i]);
+        if (sidx < 0) { sidx = atomicCAS(&slots[i], -1, me); if (sidx < 0) { pos = i; break; } }
+        const int64_t g = reg_a + sidx;
+        const char* gb = text + (g >= reg_b ? lb : la);
+        const int2 gs = S.lab[g];
+        bool same = gs.y == sp.y;
+        for (int k = 0; same && k < sp.y; ++k) same = gb[gs.x + k] == base[sp.x + k];
+        if (same) { if (sidx > me && sidx < chunk_end) atomicMin(&slots[i], me); pos = i; break; }  // lower only inside this chunk: the host line may be the second one
+        i = (i + 1) & (cap - 1);
+      }
+    }
+    __syncwarp();
+    const int rep = pos >= 0 ? __ldcg(&slots[pos]) : -1;
+    const bool fresh = pos >= 0 && rep == me;
+    const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+    int id = -1;
+    if (fresh) { id = count + __popc(fm & ((1u << lane) - 1u)); S.hk[reg + v] = id; }
+    __syncwarp();
+    if (pos >= 0 && !fresh) id = S.hk[reg_a + rep];
+    __syncwarp();
+    if (v < n) S.hk[reg + v] = id;  // label id of node v (the hybrid keys are no longer needed)
+    count += __popc(fm);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(256) nw_pair_kernel(const char* __restrict__ text, int64_t num_pairs, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen, NwScratch S,
                                const int32_t* __restrict__ ln, const int32_t* __restrict__ lm, const int32_t* __restrict__ lhyb, const int32_t* __restrict__ lerr,
                                int64_t* __restrict__ hn, int64_t* __restrict__ hm, int64_t* __restrict__ gn, int32_t* __restrict__ swapped,
                                int32_t* __restrict__ maxima /* n m nt labels */, unsigned long long* __restrict__ first_err /* pair << 8 | code */) {
-  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (p >= num_pairs) return;
   const int64_t a = 2 * p, b = 2 * p + 1;
-  hn[p] = 0; hm[p] = 0; gn[p] = 0; swapped[p] = 0;
   int err = lerr[a] ? lerr[a] : lerr[b];
   const bool t0 = lm[a] + 1 == ln[a], t1 = lm[b] + 1 == ln[b];
   const bool sw = t0 && !t1;
   const int64_t H = sw ? b : a, G = sw ? a : b;
   if (!err && (lm[G] + 1 != ln[G] || lhyb[G])) err = NW_GUEST;
-  if (err) { atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)err); return; }
-  swapped[p] = sw;
+  if (err) {
+    if (lane == 0) { hn[p] = 0; hm[p] = 0; gn[p] = 0; swapped[p] = 0; atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)err); }
+    return;
+  }
   // label dictionary: open addressing over the pair's contiguous span of the `st` scratch (free after parsing)
   const int64_t reg_a = lbeg[a] + 2 * a, reg_b = lbeg[b] + 2 * b, span = reg_b + llen[b] + 2 - reg_a;
   int named = 0;
-  for (int side = 0; side < 2; ++side) { const int64_t L = side ? G : H, reg = lbeg[L] + 2 * L; for (int v = 0; v < ln[L]; ++v) named += S.lab[reg + v].y > 0; }
+  for (int side = 0; side < 2; ++side) { const int64_t L = side ? G : H, reg = lbeg[L] + 2 * L; for (int v = lane; v < ln[L]; v += 32) named += S.lab[reg + v].y > 0; }
+  for (int o = 16; o; o >>= 1) named += __shfl_xor_sync(0xffffffffu, named, o);
   int cap = 1; while ((int64_t)cap * 2 <= span && cap < 2 * named + 2) cap <<= 1;   // > named, and inside the pair's span (a name costs >= 2 characters)
-  int32_t* slots = S.st + reg_a;  // entry = region index of the first node with that label, relative to reg_a; -1 empty
-  for (int i = 0; i < cap; ++i) slots[i] = -1;
+  int32_t* slots = S.st + reg_a;  // entry = region index (relative to reg_a) of the first node with that label; -1 empty
+  for (int i = lane; i < cap; i += 32) slots[i] = -1;
+  __syncwarp();
   int count = 0;
-  for (int side = 0; side < 2; ++side) {
-    const int64_t L = side ? G : H, reg = lbeg[L] + 2 * L;
-    const char* base = text + lbeg[L];
-    const int n = ln[L];
-    for (int v = 0; v < n; ++v) {
-      const int2 sp = S.lab[reg + v];
-      const int off = sp.x, len = sp.y;
-      int id = -1;
-      if (len > 0) {
-        unsigned h = 2166136261u;
-        for (int k = 0; k < len; ++k) h = (h ^ (unsigned char)base[off + k]) * 16777619u;
-        int i = (int)(h & (unsigned)(cap - 1));
-        for (;;) {
-          const int sidx = slots[i];
-          if (sidx < 0) { slots[i] = (int)(reg + v - reg_a); id = count++; break; }
-          const int64_t g = reg_a + sidx;                      // an earlier node: in line a's region or in line b's
-          const int64_t gl = g >= reg_b ? b : a;
-          const char* gb = text + lbeg[gl];
-          const int2 gs = S.lab[g];
-          const int goff = gs.x, glen = gs.y;
-          bool same = glen == len;
-          for (int k = 0; same && k < len; ++k) same = gb[goff + k] == base[off + k];
-          if (same) { id = S.hk[g]; break; }
-          i = (i + 1) & (cap - 1);
-        }
-      }
-      S.hk[reg + v] = id;  // label id of node v (the hybrid keys are no longer needed)
-    }
+  nw_label_chunks(text, lbeg, S, H, ln[H], reg_a, reg_b, lbeg[a], lbeg[b], slots, cap, count, lane);
+  nw_label_chunks(text, lbeg, S, G, ln[G], reg_a, reg_b, lbeg[a], lbeg[b], slots, cap, count, lane);
+  if (lane == 0) {
+    hn[p] = ln[H]; hm[p] = lm[H]; gn[p] = ln[G]; swapped[p] = sw;
+    atomicMax(&maxima[0], ln[H]); atomicMax(&maxima[1], lm[H]); atomicMax(&maxima[2], ln[G]); atomicMax(&maxima[3], count);
   }
-  hn[p] = ln[H]; hm[p] = lm[H]; gn[p] = ln[G];
-  atomicMax(&maxima[0], ln[H]); atomicMax(&maxima[1], lm[H]); atomicMax(&maxima[2], ln[G]); atomicMax(&maxima[3], count);
 }
 
-// per pair: the final arrays.  OUT = int32_t or int16_t (pt_batch_desc.index_bytes)
+// one warp: CSR of n nodes from m arcs (keyed by tail, or by head when BY_HEAD), neighbours in REVERSE arc order like the sequential
+// `A[--cursor[key]] = other` over ascending arcs.  Arcs are taken 32 at a time in arc order, lanes sharing a key rank themselves with
+// match.any, and the group's lowest lane moves the key's counter / cursor -- no atomics, the order is exact.  cur: n ints of scratch.
+template <class OUT, bool BY_HEAD>
+__device__ __forceinline__ void nw_warp_csr(const int2* __restrict__ arc, int m, int n, int32_t* cur, OUT* __restrict__ O, OUT* __restrict__ A, int lane) {
+  const unsigned lt = (1u << lane) - 1u;
+  for (int v = lane; v < n; v += 32) cur[v] = 0;
+  __syncwarp();
+  for (int e0 = 0; e0 < m; e0 += 32) {
+    const int e = e0 + lane;
+    const int t = e < m ? (BY_HEAD ? arc[e].y : arc[e].x) : -1 - lane;
+    const unsigned grp = __match_any_sync(0xffffffffu, t);
+    if (e < m && !(grp & lt)) cur[t] += __popc(grp);
+    __syncwarp();
+  }
+  int carry = 0;
+  for (int v0 = 0; v0 < n; v0 += 32) {
+    const int v = v0 + lane;
+    int x = v < n ? cur[v] : 0;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (v < n) { O[v + 1] = (OUT)(carry + x); cur[v] = carry + x; }
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) O[0] = 0;
+  __syncwarp();
+  for (int e0 = 0; e0 < m; e0 += 32) {
+    const int e = e0 + lane;
+    int2 a2 = e < m ? arc[e] : make_int2(-1 - lane, 0);
+    if (BY_HEAD && e < m) a2 = make_int2(a2.y, a2.x);
+    const unsigned grp = __match_any_sync(0xffffffffu, a2.x);
+    int c = 0;
+    if (e < m) { c = cur[a2.x]; A[c - 1 - __popc(grp & lt)] = (OUT)a2.y; }
+    __syncwarp();
+    if (e < m && !(grp & lt)) cur[a2.x] = c - __popc(grp);
+    __syncwarp();
+  }
+}
+
+// ONE WARP per pair: the final arrays, written with coalesced stores.  OUT = int32_t or int16_t (pt_batch_desc.index_bytes).
+// Children come out in reverse arc order (Phylogeny::build), see nw_warp_csr.
 template <class OUT>
-__global__ void nw_emit_kernel(int64_t num_pairs, const int64_t* __restrict__ lbeg, NwScratch S, const int32_t* __restrict__ ln, const int32_t* __restrict__ lm,
+__global__ void __launch_bounds__(256) nw_emit_kernel(int64_t num_pairs, const int64_t* __restrict__ lbeg, NwScratch S, const int32_t* __restrict__ ln, const int32_t* __restrict__ lm,
                                const int32_t* __restrict__ swapped, const int64_t* __restrict__ hoff, const int64_t* __restrict__ aoff, const int64_t* __restrict__ goff,
                                OUT* __restrict__ succ_off, OUT* __restrict__ succ_adj, OUT* __restrict__ hlabel, OUT* __restrict__ gparent, OUT* __restrict__ glabel,
                                unsigned long long* __restrict__ first_err) {
-  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (p >= num_pairs) return;
   const int64_t a = 2 * p, b = 2 * p + 1, H = swapped[p] ? b : a, G = swapped[p] ? a : b;
   const int64_t rh = lbeg[H] + 2 * H, rg = lbeg[G] + 2 * G;
   const int n = ln[H], m = lm[H], nt = ln[G], mt = lm[G];
   OUT* O = succ_off + hoff[p] + p; OUT* A = succ_adj + aoff[p];
   const int2* arc = S.arc + rh;
-  int32_t* cur = S.hi + rh;  // cursors (the hybrid ids are no longer needed)
-  for (int v = 0; v <= n; ++v) O[v] = 0;
-  for (int e = 0; e < m; ++e) { const int t = arc[e].x; O[t + 1] = (OUT)(O[t + 1] + 1); }
-  for (int v = 0; v < n; ++v) O[v + 1] = (OUT)(O[v + 1] + O[v]);
-  for (int v = 0; v < n; ++v) cur[v] = O[v + 1];
-  for (int e = 0; e < m; ++e) { const int2 a2 = arc[e]; A[--cur[a2.x]] = (OUT)a2.y; }   // children in reverse arc order (Phylogeny::build)
+  int32_t* cur = S.hi + rh;  // counters, then cursors (the hybrid ids are no longer needed)
+  nw_warp_csr<OUT, false>(arc, m, n, cur, O, A, lane);
   bool dbl = false;
-  for (int v = 0; v < n; ++v) for (int x = O[v]; x < O[v + 1]; ++x) for (int y = x + 1; y < O[v + 1]; ++y) dbl |= A[x] == A[y];
-  if (dbl) atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)NW_DOUBLE);
+  for (int v = lane; v < n; v += 32) {
+    const int x0 = v ? (int)O[v] : 0, x1 = (int)O[v + 1];
+    for (int x = x0; x < x1; ++x) for (int y = x + 1; y < x1; ++y) dbl |= A[x] == A[y];
+  }
+  if (__any_sync(0xffffffffu, dbl) && lane == 0) atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)NW_DOUBLE);
   OUT* HL = hlabel + hoff[p];
-  for (int v = 0; v < n; ++v) HL[v] = (OUT)S.hk[rh + v];
+  for (int v = lane; v < n; v += 32) HL[v] = (OUT)S.hk[rh + v];
   OUT* GP = gparent + goff[p]; OUT* GL = glabel + goff[p];
-  for (int v = 0; v < nt; ++v) { GP[v] = (OUT)-1; GL[v] = (OUT)S.hk[rg + v]; }
+  for (int v = lane; v < nt; v += 32) { GP[v] = (OUT)-1; GL[v] = (OUT)S.hk[rg + v]; }
+  __syncwarp();
   const int2* garc = S.arc + rg;
-  for (int e = 0; e < mt; ++e) { const int2 a2 = garc[e]; GP[a2.y] = (OUT)a2.x; }
+  for (int e = lane; e < mt; e += 32) { const int2 a2 = garc[e]; GP[a2.y] = (OUT)a2.x; }
 }
 
 // ---- pairs of NETWORKS for pt_iso_from_newick: no host / guest roles, both lines keep their order ------------------------------
 // label ids shared by the two networks of a pair (first appearance: first line, then second), sizes per graph g = 2 * pair + side
-__global__ void nw_iso_pair_kernel(const char* __restrict__ text, int64_t num_pairs, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen, NwScratch S,
+__global__ void __launch_bounds__(256) nw_iso_pair_kernel(const char* __restrict__ text, int64_t num_pairs, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen, NwScratch S,
                                    const int32_t* __restrict__ ln, const int32_t* __restrict__ lm, const int32_t* __restrict__ lerr,
                                    int64_t* __restrict__ gn, int64_t* __restrict__ gm, int32_t* __restrict__ max_nodes, unsigned long long* __restrict__ first_err) {
-  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (p >= num_pairs) return;
   const int64_t a = 2 * p, b = 2 * p + 1;
-  gn[a] = ln[a]; gn[b] = ln[b]; gm[a] = lm[a]; gm[b] = lm[b];
+  if (lane == 0) { gn[a] = ln[a]; gn[b] = ln[b]; gm[a] = lm[a]; gm[b] = lm[b]; }
   const int err = lerr[a] ? lerr[a] : lerr[b];
-  if (err) { atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)err); return; }
+  if (err) { if (lane == 0) atomicMin(first_err, ((unsigned long long)p << 8) | (unsigned)err); return; }
   const int64_t reg_a = lbeg[a] + 2 * a, reg_b = lbeg[b] + 2 * b, span = reg_b + llen[b] + 2 - reg_a;
   int named = 0;
-  for (int side = 0; side < 2; ++side) { const int64_t L = side ? b : a, reg = lbeg[L] + 2 * L; for (int v = 0; v < ln[L]; ++v) named += S.lab[reg + v].y > 0; }
+  for (int side = 0; side < 2; ++side) { const int64_t L = side ? b : a, reg = lbeg[L] + 2 * L; for (int v = lane; v < ln[L]; v += 32) named += S.lab[reg + v].y > 0; }
+  for (int o = 16; o; o >>= 1) named += __shfl_xor_sync(0xffffffffu, named, o);
   int cap = 1; while ((int64_t)cap * 2 <= span && cap < 2 * named + 2) cap <<= 1;
   int32_t* slots = S.st + reg_a;
-  for (int i = 0; i < cap; ++i) slots[i] = -1;
+  for (int i = lane; i < cap; i += 32) slots[i] = -1;
+  __syncwarp();
   int count = 0;
-  for (int side = 0; side < 2; ++side) {
-    const int64_t L = side ? b : a, reg = lbeg[L] + 2 * L;
-    const char* base = text + lbeg[L];
-    for (int v = 0; v < ln[L]; ++v) {
-      const int2 sp = S.lab[reg + v];
-      int id = -1;
-      if (sp.y > 0) {
-        unsigned h = 2166136261u;
-        for (int k = 0; k < sp.y; ++k) h = (h ^ (unsigned char)base[sp.x + k]) * 16777619u;
-        int i = (int)(h & (unsigned)(cap - 1));
-        for (;;) {
-          const int sidx = slots[i];
-          if (sidx < 0) { slots[i] = (int)(reg + v - reg_a); id = count++; break; }
-          const int64_t g = reg_a + sidx;
-          const char* gb = text + lbeg[g >= reg_b ? b : a];
-          const int2 gs = S.lab[g];
-          bool same = gs.y == sp.y;
-          for (int k = 0; same && k < sp.y; ++k) same = gb[gs.x + k] == base[sp.x + k];
-          if (same) { id = S.hk[g]; break; }
-          i = (i + 1) & (cap - 1);
-        }
-      }
-      S.hk[reg + v] = id;
-    }
-  }
-  atomicMax(max_nodes, max(ln[a], ln[b]));
+  nw_label_chunks(text, lbeg, S, a, ln[a], reg_a, reg_b, lbeg[a], lbeg[b], slots, cap, count, lane);
+  nw_label_chunks(text, lbeg, S, b, ln[b], reg_a, reg_b, lbeg[a], lbeg[b], slots, cap, count, lane);
+  if (lane == 0) atomicMax(max_nodes, max(ln[a], ln[b]));
 }
-// one thread per GRAPH: successor and predecessor CSR (the order inside a list does not matter to pt_iso_batch) and label ids
-__global__ void nw_iso_emit_kernel(int64_t num_graphs, const int64_t* __restrict__ lbeg, NwScratch S, const int32_t* __restrict__ ln, const int32_t* __restrict__ lm,
+// one warp per GRAPH: successor and predecessor CSR (the order inside a list does not matter to pt_iso_batch) and label ids
+__global__ void __launch_bounds__(256) nw_iso_emit_kernel(int64_t num_graphs, const int64_t* __restrict__ lbeg, NwScratch S, const int32_t* __restrict__ ln, const int32_t* __restrict__ lm,
                                    const int64_t* __restrict__ noff, const int64_t* __restrict__ aoff, int32_t* __restrict__ succ_off, int32_t* __restrict__ succ_adj,
                                    int32_t* __restrict__ pred_off, int32_t* __restrict__ pred_adj, int32_t* __restrict__ label) {
-  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (g >= num_graphs) return;
   const int64_t reg = lbeg[g] + 2 * g;
   const int n = ln[g], m = lm[g];
   const int2* arc = S.arc + reg;
   int32_t* cur = S.hi + reg;
-  for (int dir = 0; dir < 2; ++dir) {
-    int32_t* O = (dir ? pred_off : succ_off) + noff[g] + g; int32_t* A = (dir ? pred_adj : succ_adj) + aoff[g];
-    for (int v = 0; v <= n; ++v) O[v] = 0;
-    for (int e = 0; e < m; ++e) O[(dir ? arc[e].y : arc[e].x) + 1]++;
-    for (int v = 0; v < n; ++v) O[v + 1] += O[v];
-    for (int v = 0; v < n; ++v) cur[v] = O[v + 1];
-    for (int e = 0; e < m; ++e) { const int2 a2 = arc[e]; A[--cur[dir ? a2.y : a2.x]] = dir ? a2.x : a2.y; }
-  }
+  nw_warp_csr<int32_t, false>(arc, m, n, cur, succ_off + noff[g] + g, succ_adj + aoff[g], lane);
+  nw_warp_csr<int32_t, true>(arc, m, n, cur, pred_off + noff[g] + g, pred_adj + aoff[g], lane);
   int32_t* Lb = label + noff[g];
-  for (int v = 0; v < n; ++v) Lb[v] = S.hk[reg + v];
+  for (int v = lane; v < n; v += 32) Lb[v] = S.hk[reg + v];
 }
 
 __global__ void nw_set_first_kernel(int64_t* a, int64_t* b, int64_t* c) { a[0] = 0; b[0] = 0; c[0] = 0; }
@@ -396,7 +434,7 @@ extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int
   NW_TRY(alloc((void**)&d_hn, (size_t)(P + 1) * 8, true)); NW_TRY(alloc((void**)&d_hm, (size_t)(P + 1) * 8, true)); NW_TRY(alloc((void**)&d_gn, (size_t)(P + 1) * 8, true));
   NW_TRY(alloc((void**)&d_sw, (size_t)(P + 1) * 4, true)); NW_TRY(alloc((void**)&d_max, 16, true)); NW_TRY(alloc((void**)&d_err, 8, true));
   NW_CUDA(cudaMemsetAsync(d_max, 0, 16, s)); NW_CUDA(cudaMemsetAsync(d_err, 0xff, 8, s));
-  if (P > 0) nw_pair_kernel<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(d_text, P, d_lbeg, d_llen, S, d_ln, d_lm, d_lh, d_le, d_hn, d_hm, d_gn, d_sw, d_max, d_err);
+  if (P > 0) nw_pair_kernel<<<(unsigned)((P + 7) / 8), 256, 0, s>>>(d_text, P, d_lbeg, d_llen, S, d_ln, d_lm, d_lh, d_le, d_hn, d_hm, d_gn, d_sw, d_max, d_err);
   // ---- 4. offset tables ----
   int64_t* off[3] = {(int64_t*)keep[0], (int64_t*)keep[1], (int64_t*)keep[2]};
   nw_set_first_kernel<<<1, 1, 0, s>>>(off[0], off[1], off[2]);
@@ -427,9 +465,9 @@ extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int
   const size_t counts[5] = {(size_t)(totals[0] + P), (size_t)totals[1], (size_t)totals[0], (size_t)totals[2], (size_t)totals[2]};
   for (int k = 0; k < 5; ++k) NW_TRY(alloc(&keep[3 + k], counts[k] * esz, false));
   if (P > 0) {
-    if (idx16) nw_emit_kernel<int16_t><<<(unsigned)((P + 127) / 128), 128, 0, s>>>(P, d_lbeg, S, d_ln, d_lm, d_sw, off[0], off[1], off[2], (int16_t*)keep[3], (int16_t*)keep[4],
+    if (idx16) nw_emit_kernel<int16_t><<<(unsigned)((P + 7) / 8), 256, 0, s>>>(P, d_lbeg, S, d_ln, d_lm, d_sw, off[0], off[1], off[2], (int16_t*)keep[3], (int16_t*)keep[4],
                                                                                    (int16_t*)keep[5], (int16_t*)keep[6], (int16_t*)keep[7], d_err);
-    else nw_emit_kernel<int32_t><<<(unsigned)((P + 127) / 128), 128, 0, s>>>(P, d_lbeg, S, d_ln, d_lm, d_sw, off[0], off[1], off[2], (int32_t*)keep[3], (int32_t*)keep[4],
+    else nw_emit_kernel<int32_t><<<(unsigned)((P + 7) / 8), 256, 0, s>>>(P, d_lbeg, S, d_ln, d_lm, d_sw, off[0], off[1], off[2], (int32_t*)keep[3], (int32_t*)keep[4],
                                                                              (int32_t*)keep[5], (int32_t*)keep[6], (int32_t*)keep[7], d_err);
     NW_CUDA(cudaGetLastError());
     NW_CUDA(cudaMemcpyAsync(&first_err, d_err, 8, cudaMemcpyDeviceToHost, s));
@@ -468,7 +506,7 @@ extern "C" int pt_iso_from_newick(const char* text, int64_t len, pt_mem mem, int
   NW_TRY(alloc((void**)&d_noff, (size_t)(G + 1) * 8)); NW_TRY(alloc((void**)&d_aoff, (size_t)(G + 1) * 8));
   NW_TRY(alloc((void**)&d_max, 16)); NW_TRY(alloc((void**)&d_err, 8));
   NW_CUDA(cudaMemsetAsync(d_max, 0, 16, s)); NW_CUDA(cudaMemsetAsync(d_err, 0xff, 8, s));
-  if (P > 0) nw_iso_pair_kernel<<<(unsigned)((P + 127) / 128), 128, 0, s>>>(F.d_text, P, F.d_lbeg, F.d_llen, F.S, F.d_ln, F.d_lm, F.d_le, d_gn, d_gm, d_max, d_err);
+  if (P > 0) nw_iso_pair_kernel<<<(unsigned)((P + 7) / 8), 256, 0, s>>>(F.d_text, P, F.d_lbeg, F.d_llen, F.S, F.d_ln, F.d_lm, F.d_le, d_gn, d_gm, d_max, d_err);
   nw_set_first_kernel<<<1, 1, 0, s>>>(d_noff, d_aoff, d_noff);
   if (G > 0) {
     size_t tb = 0;
@@ -489,7 +527,7 @@ extern "C" int pt_iso_from_newick(const char* text, int64_t len, pt_mem mem, int
   int32_t *d_so = nullptr, *d_sa = nullptr, *d_po = nullptr, *d_pa = nullptr, *d_lab = nullptr;
   NW_TRY(alloc((void**)&d_so, (size_t)(totals[0] + G) * 4)); NW_TRY(alloc((void**)&d_po, (size_t)(totals[0] + G) * 4));
   NW_TRY(alloc((void**)&d_sa, (size_t)totals[1] * 4)); NW_TRY(alloc((void**)&d_pa, (size_t)totals[1] * 4)); NW_TRY(alloc((void**)&d_lab, (size_t)totals[0] * 4));
-  if (G > 0) nw_iso_emit_kernel<<<(unsigned)((G + 127) / 128), 128, 0, s>>>(G, F.d_lbeg, F.S, F.d_ln, F.d_lm, d_noff, d_aoff, d_so, d_sa, d_po, d_pa, d_lab);
+  if (G > 0) nw_iso_emit_kernel<<<(unsigned)((G + 7) / 8), 256, 0, s>>>(G, F.d_lbeg, F.S, F.d_ln, F.d_lm, d_noff, d_aoff, d_so, d_sa, d_po, d_pa, d_lab);
   NW_CUDA(cudaGetLastError());
   pt_iso_desc d{};
   d.num_pairs = P; d.mem = PT_MEM_DEVICE; d.node_off = d_noff; d.arc_off = d_aoff; d.succ_off = d_so; d.succ_adj = d_sa; d.pred_off = d_po; d.pred_adj = d_pa;

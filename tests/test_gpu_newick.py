@@ -132,3 +132,24 @@ def test_device_reader_fuzz_against_host_reader(pt):
             assert type(host_err).__name__ == type(dev_err).__name__, (text, host_err, dev_err)
             bad += 1
     assert ok > 100 and bad > 100
+
+
+def test_device_reader_short_swapped_pairs_and_repeated_labels(pt):
+    """the guest line first (so the host is the SECOND line), lines shorter than a warp, and labels repeated inside one line (MUL-trees):
+    label ids still come out in the host reader's first-appearance order"""
+    import random
+    rnd = random.Random(5)
+    lines = []
+    for _ in range(400):
+        k = rnd.randint(2, 40)
+        names = [rnd.choice("abcdefgh") + str(rnd.randint(0, 6)) for _ in range(k)]
+        def tree(xs):
+            if len(xs) == 1:
+                return xs[0]
+            c = rnd.randint(1, len(xs) - 1)
+            return "(" + tree(xs[:c]) + "," + tree(xs[c:]) + ")"
+        t = tree(names) + ";"
+        n = "((" + tree(names) + ")#H1,(#H1," + rnd.choice(names) + "));"
+        lines += [t, n] if rnd.random() < 0.5 else [n, t]
+    b, _ = _same_arrays(pt, "\n".join(lines) + "\n")
+    b.free()
