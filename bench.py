@@ -355,8 +355,17 @@ def who_leg(pt, torch, leaves=1_000_000):
     t0 = time.perf_counter()
     out = pt.who_displays(par, lab, par, lab)
     dt = time.perf_counter() - t0
+    # highest_displayed_ancestor of every guest node from that table (containment.hpp:328-344): everything is displayed here, so every
+    # climb ends at the guest root -- the longest possible chains for the pointer jumping
+    root = int(np.where(par < 0)[0][0])
+    who = torch.from_numpy(out).pin_memory().numpy()
+    pt.highest_displayed(par, who, root)
+    t1 = time.perf_counter()
+    hda = pt.highest_displayed(par, who, root)
+    dt1 = time.perf_counter() - t1
     return {"workload": "who_displays of all %d guest nodes, host = guest = random binary tree with %d leaves" % (n, leaves),
-            "guest_nodes_per_s": n / dt, "ms": dt * 1e3, "verdicts_ok": bool((out == np.arange(n)).all())}
+            "guest_nodes_per_s": n / dt, "ms": dt * 1e3, "verdicts_ok": bool((out == np.arange(n)).all()),
+            "highest_displayed_ancestor": {"guest_nodes_per_s": n / dt1, "ms": dt1 * 1e3, "ok": bool((hda == root).all())}}
 
 
 def bridges_leg(pt, torch, leaves=499_001, retis=1000):

@@ -90,6 +90,12 @@ int pt_lca_free(pt_lca* h);
  * ---------------------------------------------------------------------------------------------- */
 int pt_tree_who_displays(const int32_t* host_parent, const int32_t* host_label, int64_t n, const int32_t* guest_parent,
                          const int32_t* guest_label, int64_t nt, int32_t* out_host_node, pt_mem mem, void* stream);
+/* replaces  TreeInComponent::highest_displayed_ancestor(v)   utils/containment.hpp:328-344, for ALL guest nodes at once, on top of
+ * the table pt_tree_who_displays returned (`who`, -1 = not displayed): out[v] = the highest ancestor-or-self of v reached by the
+ * reference's climb -- stay at v if its parent is not displayed; otherwise move to the parent and stop there if it is the guest
+ * root or is displayed by `host_root` (the root of the host tree / tree component), else keep climbing.  out[root] = root (the
+ * reference never asks).  guest_parent[root] = -1.  Pointer jumping, O(nt log depth). */
+int pt_tree_highest_displayed(const int32_t* guest_parent, const int32_t* who, int64_t nt, int32_t host_root, int32_t* out, pt_mem mem, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Network isomorphism -- replaces  make_iso_mapper(N0, N1, flags).check_isomorph()

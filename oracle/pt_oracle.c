@@ -294,6 +294,29 @@ int orc_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, int n
   return 0;
 }
 
+/* ---- highest_displayed_ancestor: TreeInComponent::highest_displayed_ancestor utils/containment.hpp:328-344 -----------------
+ * The reference's loop, one guest node at a time, over the who_displays table (who[u] = the one host node displaying u, or -1):
+ *   pv = parent(v); forever { if who[pv] is empty return v; v = pv; if v is the guest root return v;
+ *                             if who[v] == { host root } return v; pv = parent(v); }
+ * out[root] = root (the reference is never called on the root).  PARITY UNPINNED: the function is private to TreeInComponent and
+ * cannot be driven from outside the reference's network solver; this is a restatement of the quoted lines only. */
+int orc_highest_displayed(int nt, const int32_t* tparent, const int32_t* who, int32_t host_root, int32_t* out) {
+  for (int s = 0; s < nt; ++s) {
+    int v = s;
+    if (tparent[v] < 0) { out[s] = v; continue; }
+    int pv = tparent[v];
+    for (;;) {
+      if (who[pv] < 0) break;
+      v = pv;
+      if (tparent[v] < 0) break;
+      if (who[v] == host_root) break;
+      pv = tparent[v];
+    }
+    out[s] = v;
+  }
+  return 0;
+}
+
 /* ---- bridges: utils/bridges.hpp:42-118 (BridgeFinder) -------------------------------------------------------------------
  * The reference finds the arcs whose removal disconnects the underlying undirected graph with two DFS passes over DFS
  * intervals (is_bridge_head :27-30).  Restated from the DEFINITION (remove the arc, test connectivity), which is

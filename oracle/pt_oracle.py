@@ -43,6 +43,8 @@ def lib():
         L.orc_bridges.argtypes = [C.c_int, C.c_int, i32p, i32p, C.POINTER(C.c_uint8)]
         L.orc_who_displays.restype = C.c_int
         L.orc_who_displays.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p, i32p, i32p]
+        L.orc_highest_displayed.restype = C.c_int
+        L.orc_highest_displayed.argtypes = [C.c_int, i32p, i32p, C.c_int32, i32p]
         L.orc_iso.restype = C.c_int
         L.orc_iso.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int]
     return _LIB
@@ -149,6 +151,14 @@ def who_displays(host_parent, host_label, guest_parent, guest_label):
     rc = lib().orc_who_displays(len(hp), _p(hp), _p(hl), len(gp), _p(gp), _p(gl), _p(out))
     if rc != 0:
         raise ValueError("orc_who_displays failed: %d" % rc)
+    return out
+
+
+def highest_displayed(guest_parent, who, host_root):
+    """orc_highest_displayed (utils/containment.hpp:328-344) for every guest node"""
+    gp = np.ascontiguousarray(guest_parent, dtype=np.int32); wd = np.ascontiguousarray(who, dtype=np.int32)
+    out = np.empty(len(gp), dtype=np.int32)
+    lib().orc_highest_displayed(len(gp), _p(gp), _p(wd), int(host_root), _p(out))
     return out
 
 

@@ -322,6 +322,17 @@ def who_displays(host_parent, host_label, guest_parent, guest_label):
     return out
 
 
+def highest_displayed(guest_parent, who, host_root):
+    """pt_tree_highest_displayed: int32[nt], TreeInComponent::highest_displayed_ancestor (utils/containment.hpp:328-344) of every
+    guest node, from the table who_displays returned"""
+    gp = np.ascontiguousarray(guest_parent, dtype=np.int32); wd = np.ascontiguousarray(who, dtype=np.int32)
+    if len(gp) != len(wd):
+        raise ValueError("guest_parent and who differ in length")
+    out = np.empty(len(gp), dtype=np.int32)
+    _check(_L.pt_tree_highest_displayed(gp.ctypes.data, wd.ctypes.data, len(gp), int(host_root), out.ctypes.data, PT_MEM_HOST, None), "pt_tree_highest_displayed")
+    return out
+
+
 def net_bridges(succ_off, succ_adj):
     """pt_net_bridges -> (bool[m] is_bridge per CSR arc, int32[n] component id); utils/bridges.hpp"""
     so = np.ascontiguousarray(succ_off, dtype=np.int32)

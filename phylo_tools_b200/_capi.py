@@ -67,6 +67,7 @@ def load():
         "pt_lca_node_info": (C.c_int, [vp, vp, vp, C.c_int, vp]),
         "pt_lca_free": (C.c_int, [vp]),
         "pt_tree_who_displays": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int, vp]),
+        "pt_tree_highest_displayed": (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp, C.c_int, vp]),
         "pt_net_bridges": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, vp, C.c_int, vp]),
         "pt_rmq_build": (C.c_int, [C.POINTER(vp), vp, C.c_int64, C.c_int, vp]),
         "pt_rmq_query": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int, vp]),
@@ -102,6 +103,6 @@ def load():
 
 
 EXPORTED = ["pt_last_error", "pt_abi_version", "pt_device_count", "pt_set_device", "pt_lca_build", "pt_lca_query", "pt_lca_get_info",
-            "pt_lca_node_info", "pt_lca_free", "pt_tree_who_displays", "pt_net_bridges", "pt_rmq_build", "pt_rmq_query", "pt_rmq_free", "pt_get_limits", "pt_batch_create",
+            "pt_lca_node_info", "pt_lca_free", "pt_tree_who_displays", "pt_tree_highest_displayed", "pt_net_bridges", "pt_rmq_build", "pt_rmq_query", "pt_rmq_free", "pt_get_limits", "pt_batch_create",
             "pt_batch_contain", "pt_batch_contain_multi", "pt_batch_create_from_newick", "pt_batch_download", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_parse_newick", "pt_packer_create",
             "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree", "pt_iso_batch", "pt_iso_from_newick"]

@@ -750,6 +750,72 @@ extern "C" int pt_tree_who_displays(const int32_t* host_parent, const int32_t* h
   return PT_OK;
 }
 
+// ---- highest_displayed_ancestor for every guest node at once (TreeInComponent::highest_displayed_ancestor, containment.hpp:328-344)
+// The reference climbs from v: parent not displayed -> stop at v; else move up and stop there if that node is the guest root or is
+// displayed by the host root alone.  "First ancestor-or-self x of parent(v) with stop(x)" is pointer jumping: O(log depth) rounds.
+namespace ptgpu {
+__global__ void hda_init_kernel(int64_t nt, const int32_t* __restrict__ gparent, const int32_t* __restrict__ who, int32_t host_root, int32_t* __restrict__ jump) {
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < nt; x += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t px = gparent[x];
+    const bool stop = px < 0 || who[x] == host_root || who[px] < 0;   // a climb that reached x ends here
+    jump[x] = stop ? (int32_t)x : px;
+  }
+}
+__global__ void hda_jump_kernel(int64_t nt, const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t* __restrict__ changed) {
+  bool any = false;
+  for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < nt; x += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = in[x], jj = in[j];
+    out[x] = jj; any |= jj != j;
+  }
+  if (any) *changed = 1;
+}
+__global__ void hda_finish_kernel(int64_t nt, const int32_t* __restrict__ gparent, const int32_t* __restrict__ who, const int32_t* __restrict__ jump, int32_t* __restrict__ out) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nt; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t pv = gparent[v];
+    out[v] = (pv < 0 || who[pv] < 0) ? (int32_t)v : jump[pv];
+  }
+}
+}  // namespace ptgpu
+
+extern "C" int pt_tree_highest_displayed(const int32_t* guest_parent, const int32_t* who, int64_t nt, int32_t host_root, int32_t* out, pt_mem mem, void* stream) {
+  if (!guest_parent || !who || !out || nt <= 0 || nt > INT32_MAX / 2 || host_root < 0) return set_error(PT_ERR_INVALID, "pt_tree_highest_displayed: bad argument");
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  std::vector<void*> owned;
+  auto cleanup = [&]() { cudaStreamSynchronize(s); for (void* p : owned) cudaFree(p); };
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
+#define HD_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return set_error(PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
+  const size_t bytes = (size_t)nt * 4;
+  int32_t *gp = (int32_t*)guest_parent, *wd = (int32_t*)who, *res = out;
+  int32_t* a = (int32_t*)dalloc(bytes); int32_t* b = (int32_t*)dalloc(bytes); int32_t* flag = (int32_t*)dalloc(4);
+  if (!a || !b || !flag) { cleanup(); return set_error(PT_ERR_NOMEM, "pt_tree_highest_displayed: out of device memory"); }
+  if (mem == PT_MEM_HOST) {
+    gp = (int32_t*)dalloc(bytes); wd = (int32_t*)dalloc(bytes); res = (int32_t*)dalloc(bytes);
+    if (!gp || !wd || !res) { cleanup(); return set_error(PT_ERR_NOMEM, "pt_tree_highest_displayed: out of device memory"); }
+    HD_TRY(cudaMemcpyAsync(gp, guest_parent, bytes, cudaMemcpyHostToDevice, s)); HD_TRY(cudaMemcpyAsync(wd, who, bytes, cudaMemcpyHostToDevice, s));
+  }
+  const int grid = (int)std::min<int64_t>((nt + 255) / 256, (int64_t)dp.sms * 8);
+  ptgpu::hda_init_kernel<<<grid, 256, 0, s>>>(nt, gp, wd, host_root, a);
+  for (int round = 0; round < 40; ++round) {   // the distance covered doubles every round
+    int32_t changed = 0;
+    HD_TRY(cudaMemsetAsync(flag, 0, 4, s));
+    ptgpu::hda_jump_kernel<<<grid, 256, 0, s>>>(nt, a, b, flag);
+    HD_TRY(cudaMemcpyAsync(&changed, flag, 4, cudaMemcpyDeviceToHost, s));
+    HD_TRY(cudaStreamSynchronize(s));
+    std::swap(a, b);
+    if (!changed) break;
+  }
+  ptgpu::hda_finish_kernel<<<grid, 256, 0, s>>>(nt, gp, wd, a, res);
+  HD_TRY(cudaGetLastError());
+  if (mem == PT_MEM_HOST) HD_TRY(cudaMemcpyAsync(out, res, bytes, cudaMemcpyDeviceToHost, s));
+  HD_TRY(cudaStreamSynchronize(s));
+#undef HD_TRY
+  cleanup();
+  return PT_OK;
+}
+
 // ---- bridges / 2-edge-connected components of a rooted network -------------------------------------------------------------
 // BridgeFinder utils/bridges.hpp:42-118 (two recursive DFS passes over DFS intervals) re-designed as data-parallel steps:
 //   1. spanning tree: every node keeps its first in-arc (a rooted DAG with one root gives a rooted tree)

@@ -154,7 +154,7 @@ template <class Host, class Guest> TreeInNetContainment(Host&&, Guest&&) -> Tree
 // preorder -- for a single-labelled host at most one node.  Computed for all guest nodes at once (pt_tree_who_displays).
 template <class Host, class Guest>
 class TreeInTreeContainment : public TreeInNetContainment<Host, Guest> {
-  std::vector<int32_t> table_;
+  std::vector<int32_t> table_, hda_;
   void fill_table() {
     const Host& H = this->host(); const Guest& G = this->guest();
     std::unordered_map<std::string, int32_t> dict;
@@ -174,6 +174,18 @@ class TreeInTreeContainment : public TreeInNetContainment<Host, Guest> {
     std::vector<Node> r;
     if (table_.at(u) >= 0) r.push_back((Node)table_[u]);
     return r;
+  }
+  // TreeInComponent::highest_displayed_ancestor(v) (containment.hpp:328-344) with this host as the component: the highest
+  // ancestor of v the climb reaches; all guest nodes are answered by one pt_tree_highest_displayed call and cached
+  Node highest_displayed_ancestor(const Node v) {
+    if (table_.empty()) fill_table();
+    if (hda_.empty()) {
+      const std::vector<int32_t> gp = this->guest().parent_array();
+      hda_.assign(gp.size(), -1);
+      throw_status(pt_tree_highest_displayed(gp.data(), table_.data(), (int64_t)gp.size(), (int32_t)this->host().root(), hda_.data(), PT_MEM_HOST, nullptr),
+                   "pt_tree_highest_displayed");
+    }
+    return (Node)hda_.at(v);
   }
 };
 template <class Host, class Guest> TreeInTreeContainment(const Host&, const Guest&) -> TreeInTreeContainment<Host, Guest>;

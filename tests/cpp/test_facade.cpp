@@ -103,6 +103,8 @@ int main(int argc, char** argv) {
     TreeInTreeContainment c(H, G);
     const int exp[7] = {-1, 0, 2, 5, 0, 3, 6};
     for (Node u = 0; u < 7; ++u) { const auto w = c.who_displays(u); assert(exp[u] < 0 ? w.empty() : (w.size() == 1 && w[0] == (Node)exp[u])); }
+    const int hda[7] = {0, 1, 1, 1, 4, 4, 4};   // highest_displayed_ancestor (containment.hpp:328-344), traced by hand
+    for (Node u = 0; u < 7; ++u) assert(c.highest_displayed_ancestor(u) == (Node)hda[u]);
     assert(!c.displayed());
   }
   // isomorphism (utils/isomorphism.hpp:309-321): data/nets.nw of the reference, and what the flags change

@@ -218,6 +218,37 @@ def test_who_displays_larger_trees(pt, oracle):
         pt.who_displays([-1, 0, 0], [-1, 5, 5], [-1, 0, 0], [-1, 5, 6])   # multi-labelled host
 
 
+
+def test_highest_displayed_ancestor(pt, oracle):
+    """pt_tree_highest_displayed (pointer jumping over the who_displays table) against the restated loop of
+    TreeInComponent::highest_displayed_ancestor (containment.hpp:328-344): golden pairs, a hand-checked case, deep and random tables"""
+    from conftest import load_golden
+    hp, hl, gp, gl = oracle.tree_arrays_from_newick("((a,b),(c,d));", "((a,c),(b,d));")
+    who = pt.who_displays(hp, hl, gp, gl)
+    assert who.tolist() == [-1, 0, 2, 5, 0, 3, 6]
+    assert pt.highest_displayed(gp, who, 0).tolist() == [0, 1, 1, 1, 4, 4, 4]
+    for it in load_golden("who_ref.json")["items"][:60]:
+        hp, hl, gp, gl = oracle.tree_arrays_from_newick(it["host"], it["guest"])
+        who = pt.who_displays(hp, hl, gp, gl)
+        root = int(np.where(np.asarray(hp) < 0)[0][0])
+        assert pt.highest_displayed(gp, who, root).tolist() == oracle.highest_displayed(gp, who, root).tolist(), (it["host"], it["guest"])
+    rng = np.random.default_rng(21)
+    for n, shape in [(5000, "path"), (20000, "random"), (300000, "random"), (100000, "path")]:
+        if shape == "path":      # node i hangs below i - 1: the climb is as long as it can be
+            gp = np.arange(-1, n - 1, dtype=np.int32)
+        else:
+            gp = np.concatenate([[-1], (rng.random(n - 1) * np.arange(1, n)).astype(np.int64)]).astype(np.int32)
+        for holes in (0.0, 0.001, 0.2):
+            who = rng.integers(0, 50, size=n).astype(np.int32)          # 0 plays the host root
+            who[rng.random(n) < holes] = -1
+            if holes == 0.0:
+                who[:] = 7
+            got = pt.highest_displayed(gp, who, 0)
+            assert (got == oracle.highest_displayed(gp, who, 0)).all(), (n, shape, holes)
+    with pytest.raises(pt.PtError):
+        pt.highest_displayed(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), 0)
+
+
 def _csr(n, edges):
     edges = sorted(edges)
     off = np.zeros(n + 1, dtype=np.int32)

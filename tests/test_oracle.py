@@ -117,3 +117,15 @@ def test_iso_restatement_matches_reference(oracle):
     for it in g["items"][:40]:
         n, e, lab = parse_newick(it["a"])
         assert oracle.iso_newick(it["a"], write_newick(n, e, lab), flags=7) == 1
+
+
+def test_highest_displayed_restatement(oracle):
+    """orc_highest_displayed = the loop of TreeInComponent::highest_displayed_ancestor (containment.hpp:328-344), traced by hand on the
+    pair the reference itself prints (who_ref.json item 1): guest ((a,c),(b,d)) in host ((a,b),(c,d))"""
+    gp = [-1, 0, 1, 1, 0, 4, 4]
+    who = [-1, 0, 2, 5, 0, 3, 6]
+    assert oracle.highest_displayed(gp, who, 0).tolist() == [0, 1, 1, 1, 4, 4, 4]
+    # a path 0 <- 1 <- 2 <- 3 <- 4, everything displayed, node 2 by the host root: climbs from below stop at 2, from 2 and above at 0
+    assert oracle.highest_displayed([-1, 0, 1, 2, 3], [9, 8, 0, 6, 5], 0).tolist() == [0, 0, 0, 2, 2]
+    # parent not displayed: stay (node 2); node 1 still climbs to the displayed root
+    assert oracle.highest_displayed([-1, 0, 1, 2, 3], [9, -1, 7, 6, 5], 0).tolist() == [0, 0, 2, 2, 2]
