@@ -441,13 +441,23 @@ def iso_newick(pairs, flags=1):
 
 
 def iso_newick_text(text, flags=1):
-    """pt_iso_from_newick: two extended-Newick lines per pair, parsed and compared on the GPU -> (bool verdicts, status)"""
-    data = text if isinstance(text, (bytes, bytearray)) else text.encode()
-    cap = len(data) // 4 + 2
-    bits = np.zeros((cap + 31) // 32 + 1, dtype=np.uint32)
-    status = np.zeros(cap + 1, dtype=np.uint8)
+    """pt_iso_from_newick: two extended-Newick lines per pair, parsed and compared on the GPU -> (bool verdicts, status);
+    text: bytes / str (HOST) or a torch CUDA uint8 tensor (DEVICE: verdict words and status then stay on the device until read here)"""
     n = C.c_int64(0)
-    rc = _L.pt_iso_from_newick(C.cast(C.c_char_p(bytes(data)), C.c_void_p), len(data), PT_MEM_HOST, int(flags), bits.ctypes.data, status.ctypes.data, PT_MEM_HOST, C.byref(n), None)
+    if _is_device(text):
+        import torch
+        size = int(text.numel())
+        cap = size // 4 + 2
+        d_bits = torch.zeros((cap + 31) // 32 + 1, dtype=torch.int32, device=text.device)
+        d_stat = torch.zeros(cap + 1, dtype=torch.uint8, device=text.device)
+        rc = _L.pt_iso_from_newick(text.data_ptr(), size, PT_MEM_DEVICE, int(flags), d_bits.data_ptr(), d_stat.data_ptr(), PT_MEM_DEVICE, C.byref(n), None)
+        bits, status = d_bits.cpu().numpy().view(np.uint32), d_stat.cpu().numpy()
+    else:
+        data = text if isinstance(text, (bytes, bytearray)) else text.encode()
+        cap = len(data) // 4 + 2
+        bits = np.zeros((cap + 31) // 32 + 1, dtype=np.uint32)
+        status = np.zeros(cap + 1, dtype=np.uint8)
+        rc = _L.pt_iso_from_newick(C.cast(C.c_char_p(bytes(data)), C.c_void_p), len(data), PT_MEM_HOST, int(flags), bits.ctypes.data, status.ctypes.data, PT_MEM_HOST, C.byref(n), None)
     if rc == _capi.PT_ERR_PARSE:
         raise MalformedNewick((_L.pt_last_error() or b"").decode(errors="replace"))
     _check(rc, "pt_iso_from_newick")

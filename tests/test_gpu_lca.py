@@ -247,6 +247,14 @@ def test_highest_displayed_ancestor(pt, oracle):
             assert (got == oracle.highest_displayed(gp, who, 0)).all(), (n, shape, holes)
     with pytest.raises(pt.PtError):
         pt.highest_displayed(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), 0)
+    # arrays already on the device (PT_MEM_DEVICE): nothing is copied, the answer stays there
+    import torch
+    n = 50000
+    gp = np.concatenate([[-1], (rng.random(n - 1) * np.arange(1, n)).astype(np.int64)]).astype(np.int32)
+    who = rng.integers(0, 9, size=n).astype(np.int32); who[rng.random(n) < 0.05] = -1
+    d_gp, d_who, d_out = torch.from_numpy(gp).cuda(), torch.from_numpy(who).cuda(), torch.empty(n, dtype=torch.int32, device="cuda")
+    assert pt.lib().pt_tree_highest_displayed(d_gp.data_ptr(), d_who.data_ptr(), n, 0, d_out.data_ptr(), 1, None) == 0
+    assert (d_out.cpu().numpy() == oracle.highest_displayed(gp, who, 0)).all()
 
 
 def _csr(n, edges):
