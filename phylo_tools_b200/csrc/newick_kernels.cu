@@ -4,7 +4,7 @@
 // io/io.hpp:52-62); the host batch reader (pt/fast_newick.hpp) does 2.6e5 pairs/s on 16 cores, fifty times slower than the
 // containment kernel consumes them.  Here the text is uploaded once and
 //   1. the newlines are located (CUB select), the lines trimmed and the blank ones dropped (one thread per line),
-//   2. every line is parsed by ONE THREAD with the same right-to-left scan as the reference (same node numbering: root 0, ids
+//   2. every line is parsed by ONE WARP (nw_parse_line_warp; odd or malformed lines by one thread) with the right-to-left scan of the reference (same node numbering: root 0, ids
 //      in the order the name tokens are met from the right; hybrid "#H<k>": first occurrence from the right creates the
 //      node; ":length" and white space skipped) into scratch arrays addressed by the line's text offset,
 //   3. one thread per pair picks host and guest (the network is the host, or the first line if both are trees,
@@ -69,11 +69,10 @@ struct NwScratch {  // addressed by region index (region of line k starts at lbe
 __device__ __forceinline__ bool nw_ws(char c) { return c == ' ' || (unsigned)(c - 9) < 5u; }
 __device__ __forceinline__ bool nw_digit(char c) { return c >= '0' && c <= '9'; }
 
-// the scan of pt/fast_newick.hpp parse_line (= io/newick.hpp:159-272), one thread, one line
-__global__ void nw_parse_kernel(const char* __restrict__ text, int64_t num_lines, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen,
-                                NwScratch S, int32_t* __restrict__ ln, int32_t* __restrict__ lm, int32_t* __restrict__ lhyb, int32_t* __restrict__ lerr) {
-  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (k >= num_lines) return;
+// the scan of pt/fast_newick.hpp parse_line (= io/newick.hpp:159-272), one thread, one line.  This is the DEFINITION of the numbering
+// and of every error; nw_parse_kernel runs it for the lines its warp-parallel path does not take.
+__device__ __noinline__ void nw_parse_line_seq(const char* __restrict__ text, int64_t k, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen,
+                                               NwScratch S, int32_t* __restrict__ ln, int32_t* __restrict__ lm, int32_t* __restrict__ lhyb, int32_t* __restrict__ lerr) {
   // the line is read through a 16-byte register window (one aligned 128-bit load per 16 characters of the backward scan
   // instead of one byte load per character); `text` is 16-byte aligned and padded by the caller
   const int64_t line0 = lbeg[k];
@@ -137,6 +136,137 @@ __global__ void nw_parse_kernel(const char* __restrict__ text, int64_t num_lines
 #undef NW_SKIP_WS
 #undef NW_SKIP_LEN
   ln[k] = n; lm[k] = m; lhyb[k] = has_h; lerr[k] = err;
+}
+
+// ONE WARP per line, for well-formed lines (everything else -- any error, text left of the tree, a ')' at the very start -- goes to
+// nw_parse_line_seq, so errors and oddities keep their sequential definition).  The reader's right-to-left scan is a sequence of
+// TOKEN SLOTS (one left of the ';', one left of every ')' and ','; each makes a node or names an existing hybrid) and of ARCS (one
+// per ',' and '(': from the owner of the open group to the subtree just finished).  Both are counted with ballots over 32
+// characters at a time; "the owner of depth d" is the nearest ')' to the right that opened depth d -- found inside the chunk with
+// match.any, else in the per-depth array st[] the previous chunks left behind.  Then one lane per slot scans its own short token
+// with the sequential rules (branch length, blanks, '#'), repeated hybrid numbers are folded onto their first slot, ids and names
+// are compacted in slot order, and the arcs renamed.  Returns false if the line has to go the sequential way.
+__device__ __forceinline__ bool nw_parse_line_warp(const char* __restrict__ T, int len, int2* arc, int2* lab, int32_t* st, int32_t* hk, int32_t* hi, int lane,
+                                                   int& n_out, int& m_out, int& hyb_out) {
+  const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+  enum { D_SEMI, D_CL, D_OP, D_CM };
+  int sp = 0, nslots = 1, narcs = 0, lastD = D_SEMI;
+  if (lane == 0) hi[0] = len - 2;  // slot 0: the root's token, left of the ';'
+  for (int r0 = 1; r0 < len; r0 += 32) {
+    const int r = r0 + lane, p = len - 1 - r;   // lane order = reading order (right to left)
+    const bool act = r < len;
+    const char c = act ? T[p] : ' ';
+    const bool isCL = c == ')', isOP = c == '(', isCM = c == ',';
+    const unsigned cl = __ballot_sync(FULL, isCL), op = __ballot_sync(FULL, isOP), cm = __ballot_sync(FULL, isCM), dm = cl | op | cm;
+    int rD = lastD;  // the delimiter met before this character
+    if (dm & lt) { const unsigned b = 1u << (31 - __clz(dm & lt)); rD = (cl & b) ? D_CL : (op & b) ? D_OP : D_CM; }
+    const int spb = sp + __popc(cl & lt) - __popc(op & lt);   // open groups when this character is met
+    const int ls = nslots + __popc((cl | cm) & lt) - 1;       // the slot opened last
+    const bool want = isOP || isCM;
+    bool bad = false;
+    if (isCL) bad = p == 0 || rD == D_OP;       // the reader never opens a group at the first character; ")" right after "(" is an error
+    else if (want) bad = spb < 1;               // the tree is finished, what follows is ignored or an error
+    else bad = act && rD == D_OP && !nw_ws(c);  // only blanks between "(" and the next "," or "("
+    if (__any_sync(FULL, bad)) return false;
+    int memP = 0, memC = 0;
+    const bool wantC = want && rD == D_OP;      // the subtree just finished is the group that "(" closed: its owner sits at depth spb
+    if (want) { memP = st[spb - 1]; if (wantC) memC = st[spb]; }
+    __syncwarp();
+    const unsigned gA = __match_any_sync(FULL, isCL ? spb : want ? spb - 1 : -1 - lane);
+    const unsigned candA = gA & cl & lt;
+    const int vA = __shfl_sync(FULL, ls, candA ? 31 - __clz(candA) : lane);
+    const unsigned gB = __match_any_sync(FULL, isCL ? spb : wantC ? spb : -1 - lane);
+    const unsigned candB = gB & cl & lt;
+    const int vB = __shfl_sync(FULL, ls, candB ? 31 - __clz(candB) : lane);
+    if (isCL && !(gA & cl & ~lt & ~(1u << lane))) st[spb] = ls;   // the last ")" of this depth in the chunk stays
+    if (isCL || isCM) hi[ls + 1] = p - 1;                          // where the slot this delimiter opens begins
+    if (want) arc[narcs + __popc((cm | op) & lt)] = make_int2(candA ? vA : memP, wantC ? (candB ? vB : memC) : ls);
+    sp += __popc(cl) - __popc(op); nslots += __popc(cl | cm); narcs += __popc(cm | op);
+    if (dm) { const unsigned b = 1u << (31 - __clz(dm)); lastD = (cl & b) ? D_CL : (op & b) ? D_OP : D_CM; }
+    __syncwarp();
+  }
+  if (sp != 0) return false;
+  // tokens: names and hybrid numbers, by slot
+  int H = 0;
+  for (int s0 = 0; s0 < nslots; s0 += 32) {
+    const int s = s0 + lane;
+    bool isH = false, tbad = false;
+    int key = 0;
+    int2 span = make_int2(0, 0);
+    if (s < nslots) {
+      int back = hi[s];
+      if (s != 0) {  // ":<number>" right of the name (the first slot has none: io/newick.hpp reads the root's name straight after ';')
+        int i_ = back;
+        while (i_ >= 0) { const char c_ = T[i_]; if (nw_digit(c_) || c_ == '.' || c_ == '-' || c_ == '+' || c_ == 'E' || c_ == 'e') --i_; else break; }
+        if (i_ >= 0 && T[i_] == ':') back = i_ - 1;
+      }
+      while (back >= 0 && nw_ws(T[back])) --back;
+      int i = back, sharp = -1;
+      while (i >= 0) { const char c = T[i]; if (c == '(' || c == ')' || c == ',') break; if (c == '#' && sharp < 0) sharp = i; --i; }
+      const int nb = i + 1, nl = back - i;
+      if (sharp >= 0) {
+        int d = sharp;
+        while (d < nb + nl && !nw_digit(T[d])) ++d;
+        if (d == nb + nl) tbad = true;
+        else {
+          while (d < nb + nl && nw_digit(T[d])) { key = key * 10 + (T[d] - '0'); ++d; }
+          isH = true; span = make_int2(nb, sharp - nb);
+        }
+      } else span = make_int2(nb, nl);
+    }
+    if (__any_sync(FULL, tbad)) return false;
+    const unsigned hm = __ballot_sync(FULL, isH);
+    __syncwarp();
+    if (s < nslots) { lab[s] = span; hk[s] = key; hi[s] = s; }
+    if (isH) st[H + __popc(hm & lt)] = s;
+    H += __popc(hm);
+  }
+  __syncwarp();
+  // a hybrid number met before names the node of its first slot: hi[s] = that slot
+  for (int i0 = 0; i0 < H; i0 += 32) {
+    const int i = i0 + lane;
+    if (i < H) {
+      const int s = st[i], key = hk[s];
+      for (int j = 0; j < i; ++j) { const int sj = st[j]; if (hk[sj] == key) { hi[s] = sj; break; } }
+    }
+  }
+  __syncwarp();
+  // node ids = slots without the repeats, in slot order; names move to their node's place; hk[s] = node of slot s
+  int ndup = 0;
+  for (int s0 = 0; s0 < nslots; s0 += 32) {
+    const int s = s0 + lane;
+    const bool in = s < nslots;
+    const int rep = in ? hi[s] : 0;
+    const bool dup = in && rep != s;
+    const int2 span = in ? lab[s] : make_int2(0, 0);
+    const unsigned dmk = __ballot_sync(FULL, dup);
+    const int id = s - ndup - __popc(dmk & lt);
+    __syncwarp();
+    if (in && !dup) { hk[s] = id; lab[id] = span; }
+    __syncwarp();
+    if (dup) hk[s] = hk[rep];
+    ndup += __popc(dmk);
+    __syncwarp();
+  }
+  for (int e = lane; e < narcs; e += 32) { const int2 a = arc[e]; arc[e] = make_int2(hk[a.x], hk[a.y]); }
+  __syncwarp();
+  n_out = nslots - ndup; m_out = narcs; hyb_out = H > 0;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) nw_parse_kernel(const char* __restrict__ text, int64_t num_lines, const int64_t* __restrict__ lbeg, const int32_t* __restrict__ llen,
+                                NwScratch S, int32_t* __restrict__ ln, int32_t* __restrict__ lm, int32_t* __restrict__ lhyb, int32_t* __restrict__ lerr) {
+  const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= num_lines) return;
+  const int64_t line0 = lbeg[k], reg = line0 + 2 * k;
+  const int len = llen[k];
+  const char* T = text + line0;
+  int n = 0, m = 0, hyb = 0;
+  bool ok = len >= 1 && T[len - 1] == ';';
+  if (ok) ok = nw_parse_line_warp(T, len, S.arc + reg, S.lab + reg, S.st + reg, S.hk + reg, S.hi + reg, lane, n, m, hyb);
+  if (ok) { if (lane == 0) { ln[k] = n; lm[k] = m; lhyb[k] = hyb; lerr[k] = NW_OK; } }
+  else { __syncwarp(); if (lane == 0) nw_parse_line_seq(text, k, lbeg, llen, S, ln, lm, lhyb, lerr); }
 }
 
 // per pair: host / guest, label ids (written over the hybrid-key scratch of each node), sizes, maxima, first error
@@ -401,7 +531,7 @@ static int nw_front(const char* text, int64_t len, pt_mem mem, cudaStream_t s, s
   for (auto pp : sarr) NW_TRY(alloc((void**)pp, S_len * 4, true));
   int32_t *d_ln = nullptr, *d_lm = nullptr, *d_lh = nullptr, *d_le = nullptr;
   for (int32_t** pp : {&d_ln, &d_lm, &d_lh, &d_le}) NW_TRY(alloc((void**)pp, (size_t)(num_lines + 1) * 4, true));
-  if (2 * P > 0) nw_parse_kernel<<<(unsigned)((2 * P + 127) / 128), 128, 0, s>>>(d_text, 2 * P, d_lbeg, d_llen, S, d_ln, d_lm, d_lh, d_le);
+  if (2 * P > 0) nw_parse_kernel<<<(unsigned)((2 * P + 7) / 8), 256, 0, s>>>(d_text, 2 * P, d_lbeg, d_llen, S, d_ln, d_lm, d_lh, d_le);
   F.d_text = d_text; F.num_lines = num_lines; F.P = P; F.d_lbeg = d_lbeg; F.d_llen = d_llen; F.S = S; F.d_ln = d_ln; F.d_lm = d_lm; F.d_lh = d_lh; F.d_le = d_le;
   return PT_OK;
 #undef NW_TRY

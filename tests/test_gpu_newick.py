@@ -153,3 +153,79 @@ def test_device_reader_short_swapped_pairs_and_repeated_labels(pt):
         lines += [t, n] if rnd.random() < 0.5 else [n, t]
     b, _ = _same_arrays(pt, "\n".join(lines) + "\n")
     b.free()
+
+
+def test_device_reader_well_formed_lines_with_rich_formatting(pt):
+    """lines the warp-parallel path of nw_parse_kernel takes (well-formed), but with everything the sequential rules look at:
+    blanks around names and after '(', branch lengths in several spellings, names made of digits / '.' / 'e' / '+' (which look like a
+    length until the ':' is missing), unnamed inner nodes and leaves, hybrids given two or three times with and without names and
+    lengths, high degrees, deep chains -- arrays bit-identical to the host reader's"""
+    import random
+    rnd = random.Random(77)
+    alphabet = ["a", "b", "x1", "12", "3e", "e5", "t.1", "L+", "n-2", "Q", "7", "ab_c", "E", "0.5"]
+
+    def blanks():
+        return rnd.choice(["", "", "", " ", "  ", "\t"])
+
+    def length():
+        return rnd.choice(["", "", ":1", ":0.5", ":1e-3", ":2.5E+2", ":", ":-1", ":.5"])
+
+    lines = []
+    for it in range(600):
+        k = rnd.randint(2, 60)
+        names = ["%s%d" % (rnd.choice(alphabet), i) if rnd.random() < 0.8 else "%d" % (1000 + i) for i in range(k)]   # distinct
+
+        def build(xs, depth):
+            if len(xs) == 1:
+                return xs[0]
+            if depth > 40 or rnd.random() < 0.15:          # high degree
+                return [build([x], depth + 1) for x in xs]
+            c = rnd.randint(1, len(xs) - 1) if rnd.random() < 0.7 else 1   # c = 1: deep chains
+            return [build(xs[:c], depth + 1), build(xs[c:], depth + 1)]
+        tree = build(names, 0)
+        inner = []
+
+        def collect(t):
+            if isinstance(t, list):
+                inner.append(t)
+                for c in t:
+                    collect(c)
+        collect(tree)
+        nh = rnd.randint(0, 4)
+        hyb = {}
+        for h in range(nh):   # a new leaf below a hybrid node that hangs under two or three different inner nodes
+            key = rnd.choice([h + 1, 10 * h + 7, 100 + h])
+            if key in hyb or len(inner) < 3:
+                continue
+            homes = rnd.sample(inner, 3 if rnd.random() < 0.3 else 2)
+            hname = rnd.choice(["", "h", "r%d" % h])
+            hyb[key] = True
+            first = True
+            for home in reversed(homes):   # the reader meets the LAST one in the line first, but any of them may carry the child
+                home.append(("hyb", key, hname, "w%d" % h if first else None))
+                first = False
+
+        def render(t, net):
+            if isinstance(t, tuple):
+                _, key, hname, child = t
+                if not net:
+                    return None
+                tag = "%s#%s%d" % (hname, rnd.choice(["H", "LGT", "R"]), key)
+                return ("(" + blanks() + child + length() + ")" if child else "") + tag + length()
+            if isinstance(t, str):
+                return blanks() + t + length() + blanks() if rnd.random() < 0.5 else t + length()
+            kids = [r for r in (render(c, net) for c in t) if r is not None]
+            if len(kids) == 1 and not net:
+                return kids[0]
+            name = rnd.choice(["", "", "i%d" % rnd.randint(0, 9)])
+            return "(" + blanks() + ",".join(kids) + ")" + name + length() + blanks()
+        net = render(tree, True).strip()
+        # the root's token sits right of the last ')' with no ',' or ')' after it: no length is skipped there, keep it plain
+        net = net[:net.rindex(")") + 1] + rnd.choice(["", "root"]) + ";"
+        gt = render(tree, False).strip()
+        gt = gt[:gt.rindex(")") + 1] + ";"
+        lines += [net, gt]
+    text = "\n".join(lines) + "\n"
+    b, _ = _same_arrays(pt, text)
+    assert b.num_instances == 600
+    b.free()
