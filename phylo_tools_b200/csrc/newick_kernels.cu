@@ -4,14 +4,15 @@
 // io/io.hpp:52-62); the host batch reader (pt/fast_newick.hpp) does 2.6e5 pairs/s on 16 cores, fifty times slower than the
 // containment kernel consumes them.  Here the text is uploaded once and
 //   1. the newlines are located (CUB select), the lines trimmed and the blank ones dropped (one thread per line),
-//   2. every line is parsed by ONE WARP (nw_parse_line_warp; odd or malformed lines by one thread) with the right-to-left scan of the reference (same node numbering: root 0, ids
-//      in the order the name tokens are met from the right; hybrid "#H<k>": first occurrence from the right creates the
-//      node; ":length" and white space skipped) into scratch arrays addressed by the line's text offset,
-//   3. one thread per pair picks host and guest (the network is the host, or the first line if both are trees,
+//   2. every line is parsed by ONE WARP (nw_parse_line_warp; odd or malformed lines by one thread, nw_parse_line_seq) with the
+//      result of the reference's right-to-left scan (same node numbering: root 0, ids in the order the name tokens are met from
+//      the right; hybrid "#H<k>": first occurrence from the right creates the node; ":length" and white space skipped) into
+//      scratch arrays addressed by the line's text offset,
+//   3. one warp per pair picks host and guest (the network is the host, or the first line if both are trees,
 //      examples/tc.cpp:110-111), gives the labels dense ids by first appearance (host nodes, then guest nodes) through an
 //      open-addressing table kept in the pair's own scratch span, and publishes the sizes,
 //   4. prefix sums over the pairs give the offset tables,
-//   5. one thread per pair writes the CSR (children in reverse arc order, utils/storage_adj_immutable.hpp:119), the label
+//   5. one warp per pair writes the CSR (children in reverse arc order, utils/storage_adj_immutable.hpp:119), the label
 //      ids and the guest parent array -- directly in the int16 layout when the batch allows it.
 // The arrays are bit-identical to BatchPacker::add_newick_text on the same text (tests/test_gpu_newick.py); the handle
 // owns them (no host copy ever exists).  Malformed input: PT_ERR_PARSE / PT_ERR_INVALID naming the first bad pair.
