@@ -1,10 +1,15 @@
 """pt_batch_create_from_newick (extended-Newick text parsed ON THE GPU into a device-resident batch) against the host batch reader
 (pt_packer_add_newick_text = the reference reader's numbering, pinned by tests/golden/newick_ref.json): the arrays must be
 bit-identical, the verdicts the pinned truths, malformed input must name the first bad pair."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+# PT_STRESS=<k>: k more seeds for the two randomised reader tests (a one-off soak, not part of the regular run)
+EXTRA_SEEDS = [9000 + i for i in range(int(os.environ.get("PT_STRESS", "0") or 0))]
 
 KEYS = ["host_node_off", "host_arc_off", "guest_node_off", "host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"]
 
@@ -86,13 +91,14 @@ def test_device_reader_reports_the_first_bad_pair(pt):
     assert "pair 1" in str(ei.value) and "guest must be a tree" in str(ei.value)
 
 
-def test_device_reader_fuzz_against_host_reader(pt):
+@pytest.mark.parametrize("seed", [4242] + EXTRA_SEEDS)
+def test_device_reader_fuzz_against_host_reader(pt, seed):
     """mutated Newick lines (characters deleted, duplicated, replaced by structure characters): the device reader must accept
     exactly what the host reader accepts, with identical arrays, and reject the rest -- never crash or hang"""
     import random
-    rnd = random.Random(4242)
+    rnd = random.Random(seed)
     p = pt.Packer()
-    p.add_generated(60, 8, 3, 321, 0)
+    p.add_generated(60, 8, 3, 321 + seed % 1000, 0)
     base = [p.newick(i) for i in range(len(p))]
     alphabet = "(),;#H:0123456789ab \t"
     ok = bad = 0
@@ -155,13 +161,14 @@ def test_device_reader_short_swapped_pairs_and_repeated_labels(pt):
     b.free()
 
 
-def test_device_reader_well_formed_lines_with_rich_formatting(pt):
+@pytest.mark.parametrize("seed", [77] + EXTRA_SEEDS)
+def test_device_reader_well_formed_lines_with_rich_formatting(pt, seed):
     """lines the warp-parallel path of nw_parse_kernel takes (well-formed), but with everything the sequential rules look at:
     blanks around names and after '(', branch lengths in several spellings, names made of digits / '.' / 'e' / '+' (which look like a
     length until the ':' is missing), unnamed inner nodes and leaves, hybrids given two or three times with and without names and
     lengths, high degrees, deep chains -- arrays bit-identical to the host reader's"""
     import random
-    rnd = random.Random(77)
+    rnd = random.Random(seed)
     alphabet = ["a", "b", "x1", "12", "3e", "e5", "t.1", "L+", "n-2", "Q", "7", "ab_c", "E", "0.5"]
 
     def blanks():
