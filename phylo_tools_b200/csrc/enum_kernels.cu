@@ -161,12 +161,13 @@ extern "C" int pt_enum_switchings(int32_t n, int32_t m, const int32_t* succ_off,
   grid = std::max(grid, 1);
   const size_t T = (size_t)grid * 256;
   EnumNode* d_nodes = nullptr; int32_t *d_radix = nullptr, *d_off = nullptr, *d_par = nullptr; u64 *d_S1 = nullptr, *d_S2 = nullptr, *d_res = nullptr; uint32_t* d_cnt = nullptr;
-  auto freeall = [&]() { cudaFree(d_nodes); cudaFree(d_radix); cudaFree(d_off); cudaFree(d_par); cudaFree(d_S1); cudaFree(d_S2); cudaFree(d_cnt); cudaFree(d_res); };
+  auto en_malloc = [](void** p, size_t bytes) -> cudaError_t { return dev_alloc(p, bytes) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation; };  // cached: raw cudaMalloc/cudaFree cost milliseconds
+  auto freeall = [&]() { cudaStreamSynchronize(s); dev_free(d_nodes); dev_free(d_radix); dev_free(d_off); dev_free(d_par); dev_free(d_S1); dev_free(d_S2); dev_free(d_cnt); dev_free(d_res); };
 #define EN_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { freeall(); return set_error(e__ == cudaErrorMemoryAllocation ? PT_ERR_NOMEM : PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
-  EN_TRY(cudaMalloc((void**)&d_nodes, nodes.size() * sizeof(EnumNode))); EN_TRY(cudaMalloc((void**)&d_radix, radix.size() * 4));
-  EN_TRY(cudaMalloc((void**)&d_off, par_off.size() * 4)); EN_TRY(cudaMalloc((void**)&d_par, par_pos.size() * 4));
-  EN_TRY(cudaMalloc((void**)&d_S1, T * (size_t)n * 8)); EN_TRY(cudaMalloc((void**)&d_S2, T * (size_t)n * 8)); EN_TRY(cudaMalloc((void**)&d_cnt, T * (size_t)n * 4));
-  EN_TRY(cudaMalloc((void**)&d_res, 32));
+  EN_TRY(en_malloc((void**)&d_nodes, nodes.size() * sizeof(EnumNode))); EN_TRY(en_malloc((void**)&d_radix, radix.size() * 4));
+  EN_TRY(en_malloc((void**)&d_off, par_off.size() * 4)); EN_TRY(en_malloc((void**)&d_par, par_pos.size() * 4));
+  EN_TRY(en_malloc((void**)&d_S1, T * (size_t)n * 8)); EN_TRY(en_malloc((void**)&d_S2, T * (size_t)n * 8)); EN_TRY(en_malloc((void**)&d_cnt, T * (size_t)n * 4));
+  EN_TRY(en_malloc((void**)&d_res, 32));
   const u64 init[4] = {0, ~0ull, 0, 0};
   EN_TRY(cudaMemcpyAsync(d_nodes, nodes.data(), nodes.size() * sizeof(EnumNode), cudaMemcpyHostToDevice, s));
   EN_TRY(cudaMemcpyAsync(d_radix, radix.data(), radix.size() * 4, cudaMemcpyHostToDevice, s));

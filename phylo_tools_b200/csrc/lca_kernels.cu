@@ -21,6 +21,12 @@
 #include <vector>
 #include "cuda_common.cuh"
 
+// Device memory comes from the caching allocator (cuda_common.cuh): raw cudaMalloc / cudaFree cost tens of milliseconds per call
+// once the process holds a few GB (measured: pt_tree_who_displays 23 ms -> 151 ms after the text legs of bench.py had run).
+// dev_free does not synchronise the way cudaFree does, so every release below is preceded by a stream / device synchronise.
+static inline cudaError_t lca_malloc(void** p, size_t bytes) { return ptgpu::dev_alloc(p, bytes) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation; }
+using ptgpu::dev_free;
+
 namespace cg = cooperative_groups;
 
 namespace ptgpu {
@@ -431,7 +437,8 @@ struct pt_lca {
 
 static void lca_release(pt_lca* h) {
   if (!h) return;
-  cudaFree(h->rec); cudaFree(h->keypos); cudaFree(h->table); cudaFree(h->d_level_base); cudaFree(h->d_u); cudaFree(h->d_v); cudaFree(h->d_out); cudaFree(h->size);
+  cudaDeviceSynchronize();
+  dev_free(h->rec); dev_free(h->keypos); dev_free(h->table); dev_free(h->d_level_base); dev_free(h->d_u); dev_free(h->d_v); dev_free(h->d_out); dev_free(h->size);
   delete h;
 }
 
@@ -454,9 +461,10 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int rc = PT_OK;
   auto cleanup = [&]() {
-    if (parent_mem == PT_MEM_HOST) cudaFree(d_parent);
-    cudaFree(deg); cudaFree(child_off); cudaFree(child_adj); cudaFree(order); cudaFree(depth); if (size != h->size) cudaFree(size); cudaFree(pre); cudaFree(level_off); cudaFree(small);
-    cudaFree(nodeat); cudaFree(scan_tmp);
+    cudaStreamSynchronize(s);
+    if (parent_mem == PT_MEM_HOST) dev_free(d_parent);
+    dev_free(deg); dev_free(child_off); dev_free(child_adj); dev_free(order); dev_free(depth); if (size != h->size) dev_free(size); dev_free(pre); dev_free(level_off); dev_free(small);
+    dev_free(nodeat); dev_free(scan_tmp);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
   };
@@ -469,21 +477,21 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
     }                                                                                                                     \
   } while (0)
   const size_t n4 = (size_t)n * 4;
-  if (parent_mem == PT_MEM_HOST) { LCA_TRY(cudaMalloc((void**)&d_parent, n4)); LCA_TRY(cudaMemcpyAsync(d_parent, parent, n4, cudaMemcpyHostToDevice, s)); }
+  if (parent_mem == PT_MEM_HOST) { LCA_TRY(lca_malloc((void**)&d_parent, n4)); LCA_TRY(cudaMemcpyAsync(d_parent, parent, n4, cudaMemcpyHostToDevice, s)); }
   else d_parent = (int32_t*)parent;
   LCA_TRY(cudaEventCreate(&ev0)); LCA_TRY(cudaEventCreate(&ev1));
-  LCA_TRY(cudaMalloc((void**)&deg, n4 + 4)); LCA_TRY(cudaMalloc((void**)&child_off, n4 + 4)); LCA_TRY(cudaMalloc((void**)&child_adj, n4));
-  LCA_TRY(cudaMalloc((void**)&order, n4)); LCA_TRY(cudaMalloc((void**)&depth, n4)); LCA_TRY(cudaMalloc((void**)&size, n4)); LCA_TRY(cudaMalloc((void**)&pre, n4));
-  LCA_TRY(cudaMalloc((void**)&level_off, n4 + 8)); LCA_TRY(cudaMalloc((void**)&small, 64)); LCA_TRY(cudaMalloc((void**)&nodeat, n4));
-  LCA_TRY(cudaMalloc((void**)&scan_tmp, ((size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1) * 8));
-  LCA_TRY(cudaMalloc((void**)&h->rec, (size_t)n * sizeof(LcaRecord)));
-  LCA_TRY(cudaMalloc((void**)&h->keypos, (size_t)n * 8));
+  LCA_TRY(lca_malloc((void**)&deg, n4 + 4)); LCA_TRY(lca_malloc((void**)&child_off, n4 + 4)); LCA_TRY(lca_malloc((void**)&child_adj, n4));
+  LCA_TRY(lca_malloc((void**)&order, n4)); LCA_TRY(lca_malloc((void**)&depth, n4)); LCA_TRY(lca_malloc((void**)&size, n4)); LCA_TRY(lca_malloc((void**)&pre, n4));
+  LCA_TRY(lca_malloc((void**)&level_off, n4 + 8)); LCA_TRY(lca_malloc((void**)&small, 64)); LCA_TRY(lca_malloc((void**)&nodeat, n4));
+  LCA_TRY(lca_malloc((void**)&scan_tmp, ((size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1) * 8));
+  LCA_TRY(lca_malloc((void**)&h->rec, (size_t)n * sizeof(LcaRecord)));
+  LCA_TRY(lca_malloc((void**)&h->keypos, (size_t)n * 8));
   // table geometry: level k has nblocks - 2^k + 1 entries
   std::vector<int64_t> level_base; int64_t total = 0;
   for (int k = 0; ((int64_t)1 << k) <= h->nblocks; ++k) { level_base.push_back(total); total += h->nblocks - ((int64_t)1 << k) + 1; }
   h->table_levels = (int64_t)level_base.size();
-  LCA_TRY(cudaMalloc((void**)&h->table, (size_t)total * 8));
-  LCA_TRY(cudaMalloc((void**)&h->d_level_base, level_base.size() * 8));
+  LCA_TRY(lca_malloc((void**)&h->table, (size_t)total * 8));
+  LCA_TRY(lca_malloc((void**)&h->d_level_base, level_base.size() * 8));
   LCA_TRY(cudaMemcpyAsync(h->d_level_base, level_base.data(), level_base.size() * 8, cudaMemcpyHostToDevice, s));
   h->device_bytes = (int64_t)n * (int64_t)sizeof(LcaRecord) + n * 8 + total * 8;
 
@@ -549,8 +557,9 @@ int pt_lca_query(const pt_lca* hc, const int32_t* u, const int32_t* v, int32_t* 
   const int32_t *du = u, *dv = v; int32_t* dout = out;
   if (mem == PT_MEM_HOST) {
     if (h->qcap < q) {
-      cudaFree(h->d_u); cudaFree(h->d_v); cudaFree(h->d_out); h->d_u = h->d_v = h->d_out = nullptr; h->qcap = 0;
-      PT_CUDA(cudaMalloc((void**)&h->d_u, (size_t)q * 4)); PT_CUDA(cudaMalloc((void**)&h->d_v, (size_t)q * 4)); PT_CUDA(cudaMalloc((void**)&h->d_out, (size_t)q * 4));
+      cudaStreamSynchronize(s);
+      dev_free(h->d_u); dev_free(h->d_v); dev_free(h->d_out); h->d_u = h->d_v = h->d_out = nullptr; h->qcap = 0;
+      PT_CUDA(lca_malloc((void**)&h->d_u, (size_t)q * 4)); PT_CUDA(lca_malloc((void**)&h->d_v, (size_t)q * 4)); PT_CUDA(lca_malloc((void**)&h->d_out, (size_t)q * 4));
       h->qcap = q;
     }
     PT_CUDA(cudaMemcpyAsync(h->d_u, u, (size_t)q * 4, cudaMemcpyHostToDevice, s));
@@ -582,14 +591,14 @@ int pt_lca_node_info(const pt_lca* h, int32_t* depth, int32_t* preorder, pt_mem 
   cudaStream_t s = (cudaStream_t)stream;
   int32_t *dd = depth, *dp = preorder;
   const size_t n4 = (size_t)h->n * 4;
-  if (mem == PT_MEM_HOST) { dd = dp = nullptr; if (depth) PT_CUDA(cudaMalloc((void**)&dd, n4)); if (preorder) PT_CUDA(cudaMalloc((void**)&dp, n4)); }
+  if (mem == PT_MEM_HOST) { dd = dp = nullptr; if (depth) PT_CUDA(lca_malloc((void**)&dd, n4)); if (preorder) PT_CUDA(lca_malloc((void**)&dp, n4)); }
   lca_node_info_kernel<<<592, 256, 0, s>>>(h->n, h->rec, dd, dp);
   PT_CUDA(cudaGetLastError());
   if (mem == PT_MEM_HOST) {
     if (depth) PT_CUDA(cudaMemcpyAsync(depth, dd, n4, cudaMemcpyDeviceToHost, s));
     if (preorder) PT_CUDA(cudaMemcpyAsync(preorder, dp, n4, cudaMemcpyDeviceToHost, s));
     PT_CUDA(cudaStreamSynchronize(s));
-    cudaFree(dd); cudaFree(dp);
+    dev_free(dd); dev_free(dp);
   }
   return PT_OK;
 }
@@ -603,7 +612,7 @@ struct pt_rmq {
   int64_t n = 0, nblocks = 0;
   LcaRecord* rec = nullptr; u64* keypos = nullptr; u64* table = nullptr; int64_t* d_level_base = nullptr;
 };
-static void rmq_release(pt_rmq* h) { if (!h) return; cudaFree(h->rec); cudaFree(h->keypos); cudaFree(h->table); cudaFree(h->d_level_base); delete h; }
+static void rmq_release(pt_rmq* h) { if (!h) return; cudaDeviceSynchronize(); dev_free(h->rec); dev_free(h->keypos); dev_free(h->table); dev_free(h->d_level_base); delete h; }
 
 extern "C" {
 
@@ -618,16 +627,16 @@ int pt_rmq_build(pt_rmq** out, const int32_t* values, int64_t n, pt_mem mem, voi
   if (!h) return set_error(PT_ERR_NOMEM, "out of host memory");
   h->n = n; h->nblocks = (n + 31) / 32;
   int32_t* dvals = nullptr;
-  auto fail = [&](int code) { if (mem == PT_MEM_HOST) cudaFree(dvals); rmq_release(h); return code; };
+  auto fail = [&](int code) { cudaStreamSynchronize(s); if (mem == PT_MEM_HOST) dev_free(dvals); rmq_release(h); return code; };
 #define RMQ_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(set_error(e__ == cudaErrorMemoryAllocation ? PT_ERR_NOMEM : PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__))); } while (0)
-  if (mem == PT_MEM_HOST) { RMQ_TRY(cudaMalloc((void**)&dvals, (size_t)n * 4)); RMQ_TRY(cudaMemcpyAsync(dvals, values, (size_t)n * 4, cudaMemcpyHostToDevice, s)); }
+  if (mem == PT_MEM_HOST) { RMQ_TRY(lca_malloc((void**)&dvals, (size_t)n * 4)); RMQ_TRY(cudaMemcpyAsync(dvals, values, (size_t)n * 4, cudaMemcpyHostToDevice, s)); }
   else dvals = (int32_t*)values;
   std::vector<int64_t> level_base; int64_t total = 0;
   for (int k = 0; ((int64_t)1 << k) <= h->nblocks; ++k) { level_base.push_back(total); total += h->nblocks - ((int64_t)1 << k) + 1; }
-  RMQ_TRY(cudaMalloc((void**)&h->rec, (size_t)n * sizeof(LcaRecord)));
-  RMQ_TRY(cudaMalloc((void**)&h->keypos, (size_t)n * 8));
-  RMQ_TRY(cudaMalloc((void**)&h->table, (size_t)total * 8));
-  RMQ_TRY(cudaMalloc((void**)&h->d_level_base, level_base.size() * 8));
+  RMQ_TRY(lca_malloc((void**)&h->rec, (size_t)n * sizeof(LcaRecord)));
+  RMQ_TRY(lca_malloc((void**)&h->keypos, (size_t)n * 8));
+  RMQ_TRY(lca_malloc((void**)&h->table, (size_t)total * 8));
+  RMQ_TRY(lca_malloc((void**)&h->d_level_base, level_base.size() * 8));
   RMQ_TRY(cudaMemcpyAsync(h->d_level_base, level_base.data(), level_base.size() * 8, cudaMemcpyHostToDevice, s));
   const int grid = dp.sms * 8;
   rmq_keys_kernel<<<grid, 256, 0, s>>>(n, dvals, h->keypos);
@@ -640,7 +649,7 @@ int pt_rmq_build(pt_rmq** out, const int32_t* values, int64_t n, pt_mem mem, voi
   RMQ_TRY(cudaGetLastError());
   RMQ_TRY(cudaStreamSynchronize(s));
 #undef RMQ_TRY
-  if (mem == PT_MEM_HOST) cudaFree(dvals);
+  if (mem == PT_MEM_HOST) dev_free(dvals);
   *out = h;
   return PT_OK;
 }
@@ -653,7 +662,7 @@ int pt_rmq_query(const pt_rmq* h, const int64_t* l, const int64_t* r, int64_t* o
   const int64_t *dl = l, *dr = r; int64_t* dout = out_index;
   int64_t* buf = nullptr;
   if (mem == PT_MEM_HOST) {
-    PT_CUDA(cudaMalloc((void**)&buf, (size_t)q * 24));
+    PT_CUDA(lca_malloc((void**)&buf, (size_t)q * 24));
     PT_CUDA(cudaMemcpyAsync(buf, l, (size_t)q * 8, cudaMemcpyHostToDevice, s));
     PT_CUDA(cudaMemcpyAsync(buf + q, r, (size_t)q * 8, cudaMemcpyHostToDevice, s));
     dl = buf; dr = buf + q; dout = buf + 2 * q;
@@ -662,7 +671,7 @@ int pt_rmq_query(const pt_rmq* h, const int64_t* l, const int64_t* r, int64_t* o
   rmq_query_kernel<<<std::max(grid, 1), 256, 0, s>>>(q, h->n, dl, dr, dout, h->rec, h->keypos, h->table, h->d_level_base);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && mem == PT_MEM_HOST) { e = cudaMemcpyAsync(out_index, dout, (size_t)q * 8, cudaMemcpyDeviceToHost, s); if (e == cudaSuccess) e = cudaStreamSynchronize(s); }
-  if (mem == PT_MEM_HOST) cudaFree(buf);
+  if (mem == PT_MEM_HOST) { cudaStreamSynchronize(s); dev_free(buf); }
   if (e != cudaSuccess) return set_error(PT_ERR_CUDA, "pt_rmq_query: %s", cudaGetErrorString(e));
   return PT_OK;
 }
@@ -682,8 +691,8 @@ extern "C" int pt_tree_who_displays(const int32_t* host_parent, const int32_t* h
   if (int rc = device_props(&dp)) return rc;
   std::vector<void*> owned;
   pt_lca* H = nullptr;
-  auto cleanup = [&]() { for (void* p : owned) cudaFree(p); if (H) pt_lca_free(H); };
-  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
+  auto cleanup = [&]() { cudaStreamSynchronize(s); for (void* p : owned) dev_free(p); if (H) pt_lca_free(H); };
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (lca_malloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
 #define WD_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return set_error(PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
 #define WD_PTR(p) do { if (!(p)) { cleanup(); return set_error(PT_ERR_NOMEM, "pt_tree_who_displays: out of device memory"); } } while (0)
   const int32_t *hp = host_parent, *hl = host_label, *gp = guest_parent, *gl = guest_label;
@@ -784,8 +793,8 @@ extern "C" int pt_tree_highest_displayed(const int32_t* guest_parent, const int3
   DeviceProps dp;
   if (int rc = device_props(&dp)) return rc;
   std::vector<void*> owned;
-  auto cleanup = [&]() { cudaStreamSynchronize(s); for (void* p : owned) cudaFree(p); };
-  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
+  auto cleanup = [&]() { cudaStreamSynchronize(s); for (void* p : owned) dev_free(p); };
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (lca_malloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
 #define HD_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return set_error(PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
   const size_t bytes = (size_t)nt * 4;
   int32_t *gp = (int32_t*)guest_parent, *wd = (int32_t*)who, *res = out;
@@ -870,8 +879,8 @@ extern "C" int pt_net_bridges(int64_t n, int64_t m, const int32_t* succ_off, con
   DeviceProps dp;
   if (int rc = device_props(&dp)) return rc;
   std::vector<void*> owned; pt_lca* H = nullptr;
-  auto cleanup = [&]() { for (void* p : owned) cudaFree(p); if (H) pt_lca_free(H); };
-  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
+  auto cleanup = [&]() { cudaStreamSynchronize(s); for (void* p : owned) dev_free(p); if (H) pt_lca_free(H); };
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (lca_malloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
 #define BR_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return set_error(PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
 #define BR_PTR(p) do { if (!(p)) { cleanup(); return set_error(PT_ERR_NOMEM, "pt_net_bridges: out of device memory"); } } while (0)
   const int32_t *so = succ_off, *sa = succ_adj;

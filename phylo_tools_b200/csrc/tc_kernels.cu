@@ -27,7 +27,7 @@ std::mutex g_alloc_mu;
 std::multimap<size_t, void*> g_free_blocks;          // (device << 48 | size) -> block
 std::unordered_map<void*, size_t> g_block_size;      // every live or cached block we own -> its key
 size_t g_cached_bytes = 0;
-constexpr size_t kCacheLimit = (size_t)16 << 30;
+constexpr size_t kCacheLimit = (size_t)64 << 30;  // of 180 GB: beyond it blocks go back to the driver, and cudaFree costs ~20 ms in a process holding this much
 size_t size_class(size_t b) { const size_t g = b < ((size_t)1 << 20) ? 4096 : ((size_t)1 << 20); return (b + g - 1) / g * g; }
 }  // namespace
 int dev_alloc(void** p, size_t bytes) {
@@ -37,8 +37,12 @@ int dev_alloc(void** p, size_t bytes) {
   const size_t key = ((size_t)dev << 48) | sz;
   {
     std::lock_guard<std::mutex> lk(g_alloc_mu);
-    auto it = g_free_blocks.find(key);
-    if (it != g_free_blocks.end()) { *p = it->second; g_free_blocks.erase(it); g_cached_bytes -= sz; return PT_OK; }
+    // smallest cached block of this device that fits and is at most a quarter larger (the block keeps its own size class)
+    auto it = g_free_blocks.lower_bound(key);
+    if (it != g_free_blocks.end() && (it->first >> 48) == (size_t)dev) {
+      const size_t have = it->first & (((size_t)1 << 48) - 1);
+      if (have <= sz + sz / 4) { *p = it->second; g_free_blocks.erase(it); g_cached_bytes -= have; return PT_OK; }
+    }
   }
   cudaError_t e = cudaMalloc(p, sz);
   if (e != cudaSuccess) {  // release the cache and retry once
