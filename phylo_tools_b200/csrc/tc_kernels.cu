@@ -907,12 +907,12 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
     b->d_tparent = (void*)d->guest_parent; b->d_tlabel = (void*)d->guest_label;
     if (need_max) {
       int32_t* d4 = nullptr; int32_t h4[4] = {0, 0, 0, 0};
-      if (cudaMalloc((void**)&d4, 16) != cudaSuccess) return fail(set_error(PT_ERR_NOMEM, "cudaMalloc failed"));
+      if (int rc = dev_alloc((void**)&d4, 16)) return fail(rc);
       cudaMemsetAsync(d4, 0, 16, s);
       tc_maxima_kernel<<<296, 256, 0, s>>>(B, b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_hlabel, b->d_tlabel, b->idx16, d4);
       cudaError_t e = cudaMemcpyAsync(h4, d4, 16, cudaMemcpyDeviceToHost, s);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-      cudaFree(d4);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s); else cudaStreamSynchronize(s);
+      dev_free(d4);
       if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "maxima pass failed: %s", cudaGetErrorString(e)));
       b->maxN = std::max(b->maxN, h4[0]); b->maxM = std::max(b->maxM, h4[1]); b->maxNT = std::max(b->maxNT, h4[2]); b->maxL = std::max(b->maxL, h4[3]);
     }
