@@ -269,7 +269,7 @@ int pt_batch_free(pt_batch* b);
  * one instance (the network is the host, or the first line if both are trees, examples/tc.cpp:110-111).  Same node numbering,
  * child order and label ids as parse_newick (io/newick.hpp:274-290) + the packer, i.e. the arrays are bit-identical to
  * pt_packer_add_newick_text on the same text -- but no host copy of them ever exists: the text is uploaded (mem = where it
- * lives), one thread parses each line, one thread per pair writes the CSR (int16 layout whenever every id fits).  On malformed
+ * lives), one warp parses each line, one warp per pair writes the CSR (int16 layout whenever every id fits).  On malformed
  * input nothing is created and PT_ERR_PARSE / PT_ERR_INVALID names the first bad pair.  Use with pt_batch_contain / _free. */
 int pt_batch_create_from_newick(pt_batch** out, const char* text, int64_t len, pt_mem mem, int64_t* num_pairs, void* stream);
 /* copy one of the batch's device arrays to the host (tests, debugging): which = 0 host_node_off, 1 host_arc_off,
