@@ -147,3 +147,87 @@ def test_counting_equals_the_pinned_reader_on_random_and_mutated_strings(seed):
             s = "".join(t)
         counted += _same(s, onw) == "counted"
     assert counted > 150
+
+
+def _label_ids_by_chunks(lines):
+    """nw_label_chunks: the nodes of the lines, in order, 32 at a time; inside a chunk every node claims or joins its label's slot, the
+    slot keeps the SMALLEST node index seen in THIS chunk (a claim made by an earlier chunk or line stays), and the nodes that own a
+    slot afterwards number the new labels in lane order"""
+    slot, ids, count = {}, [], 0                            # slot: label -> region index of its owner
+    for names, base in lines:                               # base = where the line's nodes sit in the pair's region: the HOST line comes
+                                                            # first even when it is the second line of the pair (larger indices)
+        for c0 in range(0, len(names), 32):
+            chunk = list(range(c0, min(c0 + 32, len(names))))
+            lanes = chunk[:]
+            random.Random(c0).shuffle(lanes)                # the hardware order of the claims inside a chunk is arbitrary
+            for v in lanes:
+                if names[v] == "":
+                    continue
+                me = base + v
+                if names[v] not in slot:
+                    slot[names[v]] = me
+                elif me < slot[names[v]] < base + chunk[-1] + 1 and slot[names[v]] >= base + c0:
+                    slot[names[v]] = me                     # atomicMin, only against an owner of the same chunk
+            fresh = [v for v in chunk if names[v] != "" and slot[names[v]] == base + v]
+            new_id = {base + v: count + i for i, v in enumerate(fresh)}
+            count += len(fresh)
+            for v in chunk:
+                if names[v] == "":
+                    ids.append(-1)
+                elif base + v in new_id:
+                    ids.append(new_id[base + v]); slot_id[names[v]] = new_id[base + v]
+                else:
+                    ids.append(slot_id[names[v]])
+    return ids
+
+
+slot_id = {}
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_label_ids_by_chunks_are_first_appearance_ids(seed):
+    rnd = random.Random(seed)
+    for it in range(300):
+        two = [[rnd.choice(["", "a", "b", "c", "d", "e", "f"]) + (str(rnd.randint(0, 30)) if rnd.random() < 0.8 else "") for _ in range(rnd.randint(1, 100))] for _ in range(2)]
+        swapped = it % 2 == 1                               # the guest line first: the host (processed first) is the second line
+        lines = [(two[1], len(two[0]) + 2), (two[0], 0)] if swapped else [(two[0], 0), (two[1], len(two[0]) + 2)]
+        slot_id.clear()
+        got = _label_ids_by_chunks(lines)
+        seen, want = {}, []
+        for names, _ in lines:
+            for x in names:
+                want.append(-1 if x == "" else seen.setdefault(x, len(seen)))
+        assert got == want, lines
+
+
+def _csr_by_chunks(n, arcs):
+    """nw_warp_csr: arcs 32 at a time in arc order; lanes sharing a tail rank themselves (match.any), the lowest lane moves the cursor"""
+    cnt = [0] * n
+    for t, _ in arcs:
+        cnt[t] += 1
+    off = [0]
+    for v in range(n):
+        off.append(off[-1] + cnt[v])
+    cur, adj = off[1:], [None] * len(arcs)
+    for e0 in range(0, len(arcs), 32):
+        chunk = arcs[e0:e0 + 32]
+        snapshot = cur[:]                                   # every lane reads its cursor before any lane writes
+        for lane, (t, h) in enumerate(chunk):
+            rank = sum(1 for tt, _ in chunk[:lane] if tt == t)
+            adj[snapshot[t] - 1 - rank] = h
+        for t in {t for t, _ in chunk}:
+            cur[t] = snapshot[t] - sum(1 for tt, _ in chunk if tt == t)
+    return off, adj
+
+
+def test_csr_by_chunks_keeps_the_sequential_child_order():
+    rnd = random.Random(9)
+    for it in range(300):
+        n = rnd.randint(1, 80)
+        arcs = [(rnd.randrange(n) if rnd.random() < 0.7 else 0, rnd.randrange(n)) for _ in range(rnd.randint(0, 200))]
+        off, adj = _csr_by_chunks(n, arcs)
+        cur, want = off[1:], [None] * len(arcs)
+        for t, h in arcs:                                   # Phylogeny::build order: A[--cursor[tail]] = head over ascending arcs
+            cur[t] -= 1
+            want[cur[t]] = h
+        assert adj == want
