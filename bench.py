@@ -490,7 +490,8 @@ def main():
     ap.add_argument("--instances", type=int, default=100_000, help="instances per GPU")
     ap.add_argument("--lca-leaves", type=int, default=10_000_000)
     ap.add_argument("--lca-queries", type=int, default=100_000_000)
-    ap.add_argument("--int32-input", action="store_true", help="use the int32 batch layout instead of the compact int16 one")
+    ap.add_argument("--int32-input", action="store_true", help="use the int32 batch layout instead of the compact one")
+    ap.add_argument("--layout", type=int, default=1, choices=[1, 2, 4], help="element size of the batch arrays (pt_batch_desc.index_bytes): 1 = uint8 with out-degrees (default), 2 = int16, 4 = int32")
     ap.add_argument("--no-lca", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
@@ -529,7 +530,8 @@ def main():
     t_gen = time.perf_counter()
     packer = pt.Packer()
     packer.add_generated(B, L, R, SEED + rank * B, 0)
-    host = packer.arrays(compact=not args.int32_input)  # int16 data arrays (pt_batch_desc.index_bytes = 2): half the upload
+    layout = 4 if args.int32_input else args.layout
+    host = packer.arrays(compact=layout if layout != 4 else 0)  # uint8 data arrays (pt_batch_desc.index_bytes = 1): a quarter of the int32 upload
     t_gen = time.perf_counter() - t_gen
     pinned = {k: (torch.from_numpy(v).pin_memory() if isinstance(v, np.ndarray) else v) for k, v in host.items()}
     dev = {k: (v.cuda(non_blocking=True) if hasattr(v, "cuda") else v) for k, v in pinned.items()}
@@ -583,7 +585,7 @@ def main():
     _, _, counters = resident.contain(result_bits=d_bits, status=d_stat, want_counters=True, stream=stream)
     k0 = sum(k0_ms) / len(k0_ms)
     ach = ALG_BYTES_PER_INSTANCE * B / (k0 / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tc_reduce_kernel<int16> (round 0, %d instances)" % B, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+    roofline = {"bound": "hbm", "kernel": "tc_persistent_kernel (the one launch of a step, %d instances)" % B, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": measured_traffic("tc_reduce_kernel", B), "kernel_ms": k0, "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
                 "algorithmic_bytes_per_instance": ALG_BYTES_PER_INSTANCE, "bytes_actually_read_per_instance": in_bytes_actual / B,
                 "note": "instance-resident shared-memory solver: bound by dependent shared-memory latency and barriers, not HBM (SURVEY 8(d)); see profiles/"}
@@ -629,7 +631,7 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
            "config": {"workload": "batch of 10^5 gen networks l=100 r=20 with a displayed tree each, per GPU (BASELINE configs[1])",
                       "instances_per_gpu": B, "leaves": L, "reticulations": R, "host_nodes": 2 * R + 2 * L - 1, "generator_seed": SEED,
-                      "input_layout": "int32 arrays" if args.int32_input else "int16 arrays (pt_batch_desc.index_bytes = 2)",
+                      "input_layout": {4: "int32 arrays", 2: "int16 arrays (pt_batch_desc.index_bytes = 2)", 1: "uint8 arrays, out-degrees instead of offsets (pt_batch_desc.index_bytes = 1)"}[layout],
                       "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" % (in_bytes_actual / 1e6),
                       "parallelism": "instances sharded %d-way, one all-reduce of result words" % world if world > 1 else "single GPU",
                       "cpu_affinity": ("%d cores next to the GPU" % numa) if numa else "default"},

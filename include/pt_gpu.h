@@ -167,7 +167,11 @@ int pt_rmq_free(pt_rmq* h);
  * Flat layout (all int32 unless noted; instance i owns the slices given by the three offset tables).  With
  * index_bytes = 2 the five data arrays (succ_off, succ_adj, both label arrays, guest_parent) hold int16_t instead
  * (pass the pointers cast to const int32_t*): every instance then has fewer than 32 768 nodes, arcs and labels, and
- * HOST input costs half the PCIe traffic -- the end-to-end path is bound by exactly that copy:
+ * HOST input costs half the PCIe traffic -- the end-to-end path is bound by exactly that copy.
+ * With index_bytes = 1 they hold uint8_t, 255 standing for -1, and host_succ_off holds the n_i OUT-DEGREES of instance i
+ * (sum(n_i) entries, instance i at host_node_off[i]) instead of n_i + 1 offsets: arc positions may exceed 255 (BASELINE
+ * config 2 has m = 258) while every node id, label id and degree fits a byte -- 1 134 B per config-2 instance instead of
+ * 2 294 B (int16) or 4 564 B (int32).  Needs at most 255 host nodes, guest nodes and labels per instance.
  *   host_node_off[B+1], host_arc_off[B+1], guest_node_off[B+1]   (int64 prefix sums of n_i, m_i, nt_i)
  *   host_succ_off  : sum(n_i + 1) entries; instance i starts at host_node_off[i] + i; values are LOCAL arc
  *                    positions 0..m_i  (the immutable CSR of utils/storage_adj_immutable.hpp:173-261)
@@ -205,7 +209,7 @@ typedef struct pt_batch_desc {
   const int32_t* guest_child_adj;  /* optional */
   /* per-batch maxima; 0 = let the library compute them (one extra pass + sync for DEVICE input) */
   int32_t max_host_nodes, max_host_arcs, max_guest_nodes, max_labels;
-  int32_t index_bytes;             /* 0 or 4: data arrays are int32_t; 2: they are int16_t (compact upload)   */
+  int32_t index_bytes;             /* 0 or 4: data arrays are int32_t; 2: int16_t; 1: uint8_t with out-degrees (see above) */
 } pt_batch_desc;
 
 /* per-instance status written next to the verdict bit */
@@ -214,7 +218,8 @@ typedef enum pt_inst_status {
   PT_INST_MULTILABEL = 1,   /* duplicate leaf label: std::logic_error in label_matching.hpp:51-52,61-62 */
   PT_INST_BAD_GRAPH = 2,    /* index out of range, cycle, no/multiple roots (storage_adj_common.hpp:103-109) */
   PT_INST_TOO_LARGE = 3,    /* pt_options.path = 1 was forced and the instance exceeds pt_limits          */
-  PT_INST_POOL_OVERFLOW = 4 /* branching pool exhausted (raise pt_options.pool_slots)                   */
+  PT_INST_POOL_OVERFLOW = 4,/* branching pool exhausted (raise pt_options.pool_slots)                   */
+  PT_INST_ROUND_LIMIT = 5   /* pt_options.max_rounds ended the branching before a verdict was reached   */
 } pt_inst_status;
 
 typedef struct pt_counters {
@@ -225,7 +230,7 @@ typedef struct pt_counters {
   uint64_t resolved_by_rules;    /* decided without branching                                          */
   uint64_t branched;             /* original instances that needed >= 1 branching                      */
   uint64_t work_items;           /* (sub)instances solved over all rounds                              */
-  uint64_t rounds;               /* kernel launches of the reduce kernel                               */
+  uint64_t rounds;               /* kernel launches (1 on the shared-memory executor: one persistent launch)  */
   uint64_t cherry_reductions;    /* true (multi-)cherries collapsed        (CherryPicker  :500-600)    */
   uint64_t reticulated_cherries; /* reticulation parents fixed                                         */
   uint64_t arcs_deleted;         /* arcs removed by the sibling-constraint rule                        */
@@ -234,7 +239,8 @@ typedef struct pt_counters {
 
 typedef struct pt_options {
   int32_t pool_slots;        /* capacity of the branching pool per round (0 = default)                  */
-  int32_t max_rounds;        /* safety bound on branching depth (0 = default 64)                        */
+  int32_t max_rounds;        /* global-memory executors only: bound on the branching depth (0 = none: the depth is
+                                bounded by the node count anyway); instances still pending then get PT_INST_ROUND_LIMIT */
   int32_t path;              /* 0 auto; 1 force the shared-memory executor (one warp per instance, int16 ids);
                                 2 force the global-memory executor with one CTA per instance (int32 ids);
                                 3 the same with a thread-block cluster per instance (what auto picks for the
@@ -328,6 +334,9 @@ int pt_packer_desc(pt_packer* p, pt_batch_desc* desc);
 /* the same batch with int16 data arrays (index_bytes = 2); PT_ERR_INVALID if some instance is too large for that.
  * The arrays belong to the packer and stay valid until the next add_* / free. */
 int pt_packer_desc_compact(pt_packer* p, pt_batch_desc* desc);
+/* the same batch with uint8 data arrays (index_bytes = 1, host_succ_off = out-degrees); PT_ERR_INVALID if some instance has more
+ * than 255 host nodes, guest nodes or labels.  Same ownership as pt_packer_desc_compact. */
+int pt_packer_desc_bytes(pt_packer* p, pt_batch_desc* desc);
 /* extended Newick text of instance i (host, then guest); two-call protocol on buffer lengths */
 int pt_packer_get_newick(pt_packer* p, int64_t i, char* host_buf, int64_t* host_len, char* guest_buf, int64_t* guest_len);
 int pt_packer_free(pt_packer* p);

@@ -103,14 +103,19 @@ class Packer:
         return d
 
     def arrays(self, compact=False):
-        """numpy views (copied) of the flat arrays, keyed like pt_batch_desc; compact=True: int16 data arrays (index_bytes = 2)"""
-        if compact:
+        """numpy views (copied) of the flat arrays, keyed like pt_batch_desc; compact=True or 2: int16 data arrays
+        (index_bytes = 2); compact=1: uint8 data arrays with out-degrees in host_succ_off (index_bytes = 1)"""
+        compact = 2 if compact is True else int(compact)
+        if compact == 2:
             d = BatchDesc()
             _check(_L.pt_packer_desc_compact(self._h, C.byref(d)), "pt_packer_desc_compact")
+        elif compact == 1:
+            d = BatchDesc()
+            _check(_L.pt_packer_desc_bytes(self._h, C.byref(d)), "pt_packer_desc_bytes")
         else:
             d = self.desc()
         B = d.num_instances
-        it, nt = (C.c_int16, np.int16) if compact else (C.c_int32, np.int32)
+        it, nt = {2: (C.c_int16, np.int16), 1: (C.c_uint8, np.uint8)}.get(compact, (C.c_int32, np.int32))
 
         def view(ptr, count, ctype, dtype):
             if not ptr or count == 0:
@@ -121,9 +126,9 @@ class Packer:
         gn = view(d.guest_node_off, B + 1, C.c_int64, np.int64)
         NH, MH, NG = (int(hn[-1]), int(ha[-1]), int(gn[-1])) if B else (0, 0, 0)
         out = dict(num_instances=B, host_node_off=hn, host_arc_off=ha, guest_node_off=gn,
-                   host_succ_off=view(d.host_succ_off, NH + B, it, nt), host_succ_adj=view(d.host_succ_adj, MH, it, nt),
+                   host_succ_off=view(d.host_succ_off, NH + (0 if compact == 1 else B), it, nt), host_succ_adj=view(d.host_succ_adj, MH, it, nt),
                    host_label=view(d.host_label, NH, it, nt), guest_parent=view(d.guest_parent, NG, it, nt),
-                   guest_label=view(d.guest_label, NG, it, nt), index_bytes=2 if compact else 4,
+                   guest_label=view(d.guest_label, NG, it, nt), index_bytes=compact if compact in (1, 2) else 4,
                    host_pred_off=view(d.host_pred_off, NH + B, C.c_int32, np.int32), host_pred_adj=view(d.host_pred_adj, MH, C.c_int32, np.int32),
                    guest_child_off=view(d.guest_child_off, NG + B, C.c_int32, np.int32), guest_child_adj=view(d.guest_child_adj, max(NG - B, 0), C.c_int32, np.int32),
                    max_host_nodes=d.max_host_nodes, max_host_arcs=d.max_host_arcs, max_guest_nodes=d.max_guest_nodes, max_labels=d.max_labels)
@@ -202,7 +207,7 @@ class Batch:
         for which, k in enumerate(keys):
             nb = C.c_int64(0)
             _check(_L.pt_batch_download(self._h, which, None, 0, C.byref(nb), C.byref(ib), mx), "pt_batch_download")
-            dt = np.int64 if which < 3 else (np.int16 if ib.value == 2 else np.int32)
+            dt = np.int64 if which < 3 else {2: np.int16, 1: np.uint8}.get(ib.value, np.int32)
             a = np.zeros(max(nb.value // np.dtype(dt).itemsize, 0), dtype=dt)
             if nb.value:
                 _check(_L.pt_batch_download(self._h, which, a.ctypes.data, nb.value, C.byref(nb), None, None), "pt_batch_download")

@@ -8,7 +8,7 @@ LIB_PATH = os.environ.get("PT_GPU_LIB") or os.path.join(_HERE, "libptgpu.so")  #
 
 PT_OK, PT_ERR_INVALID, PT_ERR_CUDA, PT_ERR_NOMEM, PT_ERR_NO_DEVICE, PT_ERR_UNSUPPORTED, PT_ERR_PARSE = 0, -1, -2, -3, -4, -5, -6
 PT_MEM_HOST, PT_MEM_DEVICE = 0, 1
-INST_OK, INST_MULTILABEL, INST_BAD_GRAPH, INST_TOO_LARGE, INST_POOL_OVERFLOW = 0, 1, 2, 3, 4
+INST_OK, INST_MULTILABEL, INST_BAD_GRAPH, INST_TOO_LARGE, INST_POOL_OVERFLOW, INST_ROUND_LIMIT = 0, 1, 2, 3, 4, 5
 
 i32p, i64p, u32p, u64p, u8p = (C.POINTER(t) for t in (C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_uint8))
 
@@ -90,6 +90,7 @@ def load():
         "pt_packer_add_generated": (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int]),
         "pt_packer_desc": (C.c_int, [vp, C.POINTER(BatchDesc)]),
         "pt_packer_desc_compact": (C.c_int, [vp, C.POINTER(BatchDesc)]),
+        "pt_packer_desc_bytes": (C.c_int, [vp, C.POINTER(BatchDesc)]),
         "pt_packer_get_newick": (C.c_int, [vp, C.c_int64, C.c_char_p, i64p, C.c_char_p, i64p]),
         "pt_packer_free": (C.c_int, [vp]),
         "pt_gen_random_tree": (C.c_int, [C.c_int64, C.c_uint64, i32p]),
@@ -105,4 +106,4 @@ def load():
 EXPORTED = ["pt_last_error", "pt_abi_version", "pt_device_count", "pt_set_device", "pt_lca_build", "pt_lca_query", "pt_lca_get_info",
             "pt_lca_node_info", "pt_lca_free", "pt_tree_who_displays", "pt_tree_highest_displayed", "pt_net_bridges", "pt_rmq_build", "pt_rmq_query", "pt_rmq_free", "pt_get_limits", "pt_batch_create",
             "pt_batch_contain", "pt_batch_contain_multi", "pt_batch_create_from_newick", "pt_batch_download", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_parse_newick", "pt_packer_create",
-            "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree", "pt_iso_batch", "pt_iso_from_newick"]
+            "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_desc_bytes", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree", "pt_iso_batch", "pt_iso_from_newick"]

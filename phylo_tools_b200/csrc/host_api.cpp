@@ -85,6 +85,12 @@ int pt_packer_desc_compact(pt_packer* p, pt_batch_desc* desc) {
   catch (const std::bad_alloc&) { return set_error(PT_ERR_NOMEM, "out of host memory"); }
   catch (const std::exception& e) { return set_error(PT_ERR_INVALID, "pt_packer_desc_compact: %s", e.what()); }
 }
+int pt_packer_desc_bytes(pt_packer* p, pt_batch_desc* desc) {
+  if (!p || !desc) return set_error(PT_ERR_INVALID, "pt_packer_desc_bytes: null argument");
+  try { *desc = p->p.desc_bytes(); return PT_OK; }
+  catch (const std::bad_alloc&) { return set_error(PT_ERR_NOMEM, "out of host memory"); }
+  catch (const std::exception& e) { return set_error(PT_ERR_INVALID, "pt_packer_desc_bytes: %s", e.what()); }
+}
 int pt_packer_get_newick(pt_packer* p, int64_t i, char* host_buf, int64_t* host_len, char* guest_buf, int64_t* guest_len) {
   if (!p || !host_len || !guest_len || i < 0 || (size_t)i >= p->p.size()) return set_error(PT_ERR_INVALID, "pt_packer_get_newick: bad argument");
   try {

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) iso_kernel(IsoGraphs G, int64_t num_items
     const int item = s_item;
     if (item >= total) break;
     const int pair = src.pair ? src.pair[item] : item;
+    if (pair < 0) continue;  // a cold slot reserved by a branching whose hot reservation failed (marked empty there)
     if (src.pair) {  // another branch may already have proved this pair (one thread looks, so that the block cannot diverge)
       if (tid == 0) s_flag = (int)((*(volatile uint32_t*)&result_bits[pair >> 5] >> (pair & 31)) & 1u);
       __syncthreads();
@@ -194,10 +195,31 @@ __global__ void __launch_bounds__(256) iso_kernel(IsoGraphs G, int64_t num_items
     // the first candidate goes to the "hot" pool (searched next: depth first), its siblings to the "cold" one (searched only
     // if the hot branch fails): for an isomorphic pair whose tied class is an orbit the first descent already succeeds
     __shared__ int s_cold;
-    if (tid == 0) { s_item = atomicAdd(dst.count, 1); s_cold = atomicAdd(cold.count, len - 1); }
+    // both reservations or neither, and a counter only ever advances over slots that WILL be written: the host pushes
+    // min(count, capacity) slots of each pool onto the stack, so a counted but unwritten slot would be read as a pair index
+    if (tid == 0) {
+      int hot = -1, cb = -1;
+      for (int old = *(volatile int*)cold.count;;) {
+        if (old + len - 1 > cold.capacity) break;
+        const int seen = atomicCAS(cold.count, old, old + len - 1);
+        if (seen == old) { cb = old; break; }
+        old = seen;
+      }
+      if (cb >= 0) {
+        for (int old = *(volatile int*)dst.count;;) {
+          if (old + 1 > dst.capacity) break;
+          const int seen = atomicCAS(dst.count, old, old + 1);
+          if (seen == old) { hot = old; break; }
+          old = seen;
+        }
+        // the cold slots cannot be handed back (others may have reserved behind them): mark them empty instead
+        if (hot < 0) for (int j = 0; j < len - 1; ++j) cold.pair[cb + j] = -1;
+      }
+      s_item = hot; s_cold = cb;
+    }
     __syncthreads();
     const int hot_slot = s_item, cold_base = s_cold;
-    if (hot_slot >= dst.capacity || cold_base + len - 1 > cold.capacity) { if (tid == 0) status[pair] = ISO_ST_POOL_OVERFLOW; continue; }
+    if (hot_slot < 0 || cold_base < 0) { if (tid == 0) status[pair] = ISO_ST_POOL_OVERFLOW; continue; }
     const int u = (int)i0[kb];
     const u64 fresh = iso_mix(k0[kb] + 0x632BE59BD9B4E019ull * (u64)(depth + 1));
     for (int j = 0; j < len; ++j) {

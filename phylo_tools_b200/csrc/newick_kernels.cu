@@ -22,7 +22,7 @@
 #include <vector>
 #include "cuda_common.cuh"
 
-extern "C" int ptgpu_batch_adopt(pt_batch** out, int64_t B, void* const arrays[8], int idx16, const int32_t maxima[4], void* stream);
+extern "C" int ptgpu_batch_adopt(pt_batch** out, int64_t B, void* const arrays[8], int index_bytes, const int32_t maxima[4], void* stream);
 
 namespace ptgpu {
 
@@ -652,7 +652,7 @@ extern "C" int pt_batch_create_from_newick(pt_batch** out, const char* text, int
     if (first_err != ~0ull) return report(first_err);
   }
   pt_batch* h = nullptr;
-  NW_TRY(ptgpu_batch_adopt(&h, P, keep, idx16 ? 1 : 0, maxima, stream));
+  NW_TRY(ptgpu_batch_adopt(&h, P, keep, idx16 ? 2 : 4, maxima, stream));
   cleanup(true);
   *out = h;
   if (num_pairs) *num_pairs = P;

@@ -50,6 +50,7 @@ static long g_sim_csr_calls, g_sim_live_nodes, g_sim_nodes, g_sim_live_arcs;
 #endif
 
 // parallel-for over [0,n): i_ is the executor's slot, i the (possibly permuted) element
+// (a tiled form with a group-uniform trip count and a predicated tail was tried: 2 % MORE instructions, no fewer BSSY / BSYNC)
 #define PT_FOR(i, n) \
   PT_NOUNROLL for (int i##_ = ex.tid(), i = 0; i##_ < (n) && ((i = ex.map(i##_, (n))), true); i##_ += ex.nth())
 // the passes that read the caller's arrays from global memory (ex.ldg) keep four iterations in flight, so that four load
@@ -62,8 +63,8 @@ static long g_sim_csr_calls, g_sim_live_nodes, g_sim_nodes, g_sim_live_arcs;
 #define PT_FOR_LD(i, n) PT_FOR(i, n)
 #endif
 
-enum TcCode : int { TC_NOT = 0, TC_DISPLAYED = 1, TC_BRANCH = 2, TC_ERROR = 3 };
-enum TcStatus : int { TCS_OK = 0, TCS_MULTILABEL = 1, TCS_BAD_GRAPH = 2, TCS_TOO_LARGE = 3, TCS_POOL_OVERFLOW = 4 };
+enum TcCode : int { TC_NOT = 0, TC_DISPLAYED = 1, TC_BRANCH = 2, TC_ERROR = 3, TC_CONTINUE = 4 };
+enum TcStatus : int { TCS_OK = 0, TCS_MULTILABEL = 1, TCS_BAD_GRAPH = 2, TCS_TOO_LARGE = 3, TCS_POOL_OVERFLOW = 4, TCS_ROUND_LIMIT = 5 };
 
 // one instance in the flat layout of include/pt_gpu.h (pointers already offset to the instance)
 struct TcInst {
@@ -75,11 +76,27 @@ struct TcInst {
   const void* tlabel;    // nt
                          // element type S of the five arrays: int32_t, or int16_t for pt_batch_desc.index_bytes = 2
 };
-// where a branch child is written (same layout, caller provides capacity n+1 / m / n / nt / nt)
-struct TcEmit {
-  int32_t* succ_off; int32_t* succ_adj; int32_t* hlabel; int32_t* tparent; int32_t* tlabel;
+// Element type S of the caller's five arrays and what it implies for the layout (include/pt_gpu.h, pt_batch_desc.index_bytes):
+//   int32_t / int16_t : succ_off holds n+1 arc positions, -1 = "none" for labels and the guest root
+//   uint8_t           : succ_off holds the n OUT-DEGREES (arc positions may exceed 255 while every id still fits a byte),
+//                       255 = "none"; the offsets are rebuilt by one prefix sum when the instance is loaded
+template <class S> struct TcLayout {
+  static constexpr bool kDegrees = false;
+  PT_HD static int dec(int x) { return x; }
+  PT_HD static S enc(int x) { return (S)x; }
+};
+template <> struct TcLayout<uint8_t> {
+  static constexpr bool kDegrees = true;
+  PT_HD static int dec(int x) { return x == 255 ? -1 : x; }
+  PT_HD static uint8_t enc(int x) { return (uint8_t)(x < 0 ? 255 : x); }
+};
+// where a branch child is written (same layout as the input of element type S; the caller provides capacity n+1 / m / n / nt / nt)
+template <class S>
+struct TcEmitT {
+  S* succ_off; S* succ_adj; S* hlabel; S* tparent; S* tlabel;
   int32_t* dims;  // n, m, nt, num_labels
 };
+typedef TcEmitT<int32_t> TcEmit;
 
 struct TcStats { unsigned cherries, retcherries, arcs_deleted, passes; };
 
@@ -153,7 +170,7 @@ struct TcSolver {
   int n, m, nt, L;  // uniform across the group
   TcStats st;
 
-  PT_HD TcSolver(Ex& e, TcWork<I>& work) : ex(e), w(work), n(0), m(0), nt(0), L(0) { st.cherries = st.retcherries = st.arcs_deleted = st.passes = 0; }
+  PT_HD TcSolver(Ex& e, TcWork<I>& work) : ex(e), w(work), n(0), m(0), nt(0), L(0), missing_(0), dag_state_(0) { st.cherries = st.retcherries = st.arcs_deleted = st.passes = 0; }
 
   enum { F_FLAG = 0, F_FAIL = 1, F_ROOT = 2, F_TROOT = 3, F_NLAB = 4, F_BEST = 5, F_STATUS = 6, F_TMP = 7, F_TMP2 = 8, F_QTAIL = 9 };
   static constexpr int TDEAD = -2;
@@ -190,14 +207,23 @@ struct TcSolver {
     const S* const succ_off = static_cast<const S*>(in.succ_off); const S* const succ_adj = static_cast<const S*>(in.succ_adj);
     const S* const hlabel = static_cast<const S*>(in.hlabel); const S* const tparent = static_cast<const S*>(in.tparent);
     const S* const tlabel = static_cast<const S*>(in.tlabel);
+    typedef TcLayout<S> Lay;
     int bad = 0, big = 0, maxlab = -1;
-    PT_FOR_LD(v, n + 1) {
-      const int o = ex.ldg(&succ_off[v]);
-      bad |= (o < 0) | (o > m) | (v == 0 && o != 0) | (v == n && o != m);
-      w.ooff[v] = (I)(o < 0 ? 0 : (o > m ? m : o));
+    if (Lay::kDegrees) {
+      // out-degrees: their sum must be m (checked before anything is indexed by them), the offsets are their prefix sums
+      int sum = 0;
+      PT_FOR_LD(v, n) { const int d = ex.ldg(&succ_off[v]); sum += d; w.hcnt[v] = (I)d; }
+      if (ex.reduce_add(sum) != m) return TCS_BAD_GRAPH;
+      ex.exclusive_scan(w.hcnt, w.ooff, n);
+    } else {
+      PT_FOR_LD(v, n + 1) {
+        const int o = ex.ldg(&succ_off[v]);
+        bad |= (o < 0) | (o > m) | (v == 0 && o != 0) | (v == n && o != m);
+        w.ooff[v] = (I)(o < 0 ? 0 : (o > m ? m : o));
+      }
     }
     PT_FOR_LD(v, n) {
-      const int l = ex.ldg(&hlabel[v]);
+      const int l = Lay::dec(ex.ldg(&hlabel[v]));
       w.hlab[v] = (I)l;
       big |= (l >= w.capL) | (l < -1);
       maxlab = l > maxlab ? l : maxlab;
@@ -208,7 +234,7 @@ struct TcSolver {
       w.ah[e] = (I)h;
     }
     PT_FOR_LD(t, nt) {
-      const int p = ex.ldg(&tparent[t]), l = ex.ldg(&tlabel[t]);
+      const int p = Lay::dec(ex.ldg(&tparent[t])), l = Lay::dec(ex.ldg(&tlabel[t]));
       bad |= (p < -1) | (p >= nt) | (p == t);
       big |= (l >= w.capL) | (l < -1);
       maxlab = l > maxlab ? l : maxlab;
@@ -674,7 +700,9 @@ struct TcSolver {
 
   // write the current (clean) state, with only in-arc `keep` of node x kept, as a compact instance.
   // Label ids are kept (no renumbering), so L and the bitset width stay those of the parent.
-  PT_NI void emit_child(int x, int keep, const TcEmit& out) {
+  template <class S>
+  PT_NI void emit_child(int x, int keep, const TcEmitT<S>& out) {
+    typedef TcLayout<S> Lay;
     ex.phase = 12;
     const int root = ex.uniform(&w.sc[F_ROOT]);
     // live host nodes (root, or any live in-arc) -> new ids by a scan of the flags (lvl is free after pick_branch_node)
@@ -691,10 +719,10 @@ struct TcSolver {
     PT_FOR(v, n) {
       if (w.hcnt[v]) {
         const int id = w.lvl[v];
-        out.succ_off[id] = w.hscr[v];
-        out.hlabel[id] = w.hlab[v];
+        out.succ_off[id] = Lay::kDegrees ? (S)w.haux[v] : (S)w.hscr[v];
+        out.hlabel[id] = Lay::enc(w.hlab[v]);
         int pos = w.hscr[v];
-        PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) out.succ_adj[pos++] = w.lvl[w.ah[e]]; }
+        PT_NOUNROLL for (int k = 0; k < outdeg(v); ++k) { const int e = out_arc(v, k); if (w.ah[e] != x || e == keep) out.succ_adj[pos++] = (S)w.lvl[w.ah[e]]; }
       }
     }
     // guest
@@ -704,9 +732,9 @@ struct TcSolver {
     ex.exclusive_scan(w.hcnt, w.haux, nt);
     const int nt2 = w.haux[nt];
     PT_FOR(t, nt) {
-      if (w.hcnt[t]) { const int id = w.haux[t]; out.tparent[id] = w.tpar[t] >= 0 ? w.haux[w.tpar[t]] : -1; out.tlabel[id] = w.tlab[t]; }
+      if (w.hcnt[t]) { const int id = w.haux[t]; out.tparent[id] = Lay::enc(w.tpar[t] >= 0 ? (int)w.haux[w.tpar[t]] : -1); out.tlabel[id] = Lay::enc(w.tlab[t]); }
     }
-    if (ex.tid() == 0) { out.succ_off[n2] = m2; out.dims[0] = n2; out.dims[1] = m2; out.dims[2] = nt2; out.dims[3] = L; }
+    if (ex.tid() == 0) { if (!Lay::kDegrees) out.succ_off[n2] = (S)m2; out.dims[0] = n2; out.dims[1] = m2; out.dims[2] = nt2; out.dims[3] = L; }
     ex.sync();
   }
 
@@ -740,21 +768,36 @@ struct TcSolver {
     return head == n;  // every node was released exactly once <=> no cycle
   }
 
+  // ---- branching in place: keep only in-arc `keep` of node x and go on with the same workspace (first child of a branching;
+  // the siblings are emitted as compact instances before this is called) ---------------------------------------------------
+  PT_NI void keep_only(int x, int keep) {
+    PT_FOR(k, indeg(x)) { const int e = in_arc(x, k); if (e != keep) w.at[e] = (I)-1; }
+    ex.sync();
+  }
+
   // ---- the rule loop (apply_rules, containment.hpp:1054-1083) -----------------------------------------------
-  // returns TcCode; on TC_ERROR *status holds the TCS_* ; on TC_BRANCH *branch_node is the node to branch on
+  // begin(): load + validate + guest clean-up; returns TC_CONTINUE (go on with rule_loop), or TC_ERROR with *status set.
+  // rule_loop(): returns TC_NOT / TC_DISPLAYED / TC_ERROR (*status holds the TCS_*) / TC_BRANCH (*branch_node = the node to
+  // branch on; the caller emits the children and / or calls keep_only and rule_loop again).
+  int missing_;    // a guest label without a host leaf; reported after the input has been validated
+  int dag_state_;  // see clean_host
   template <class S>
-  PT_HD int solve(const TcInst& in, bool trusted, int* status, int* branch_node) {
-    *status = TCS_OK; *branch_node = -1;
+  PT_HD int begin(const TcInst& in, bool trusted, int* status) {
+    *status = TCS_OK;
     int s = load<S>(in);
     if (s != TCS_OK) { *status = s; return TC_ERROR; }
-    const int missing = ex.uniform(&w.sc[F_FAIL]);  // a guest label without a host leaf; reported after the input has been validated
+    missing_ = ex.uniform(&w.sc[F_FAIL]);
     clean_guest();
-    int dag_state = trusted ? 2 : 0;
+    dag_state_ = trusted ? 2 : 0;
+    return TC_CONTINUE;
+  }
+  PT_HD int rule_loop(int* status, int* branch_node) {
+    *branch_node = -1;
     for (;;) {
       ++st.passes;
-      clean_host(dag_state, status);
+      clean_host(dag_state_, status);
       if (*status != TCS_OK) return TC_ERROR;
-      if (missing || ex.uniform(&w.sc[F_FAIL])) return TC_NOT;
+      if (missing_ || ex.uniform(&w.sc[F_FAIL])) return TC_NOT;
       ex.phase = 14;
       if (count_labels() <= 2) return TC_DISPLAYED;  // containment.hpp:1061,1208
       // true cherries and on-the-spot reticulated cherries alternate without rebuilding the CSR: pendant subtrees that match
@@ -779,6 +822,13 @@ struct TcSolver {
       *branch_node = x;
       return TC_BRANCH;
     }
+  }
+  template <class S>
+  PT_HD int solve(const TcInst& in, bool trusted, int* status, int* branch_node) {
+    *branch_node = -1;
+    const int c = begin<S>(in, trusted, status);
+    if (c != TC_CONTINUE) return c;
+    return rule_loop(status, branch_node);
   }
 };
 

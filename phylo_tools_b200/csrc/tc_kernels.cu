@@ -102,8 +102,10 @@ struct WarpEx {
   __device__ __forceinline__ int atomic_max(int32_t* p, int v) const { return atomicMax(p, v); }
   __device__ __forceinline__ uint32_t atomic_or(uint32_t* p, uint32_t v) const { return atomicOr(p, v); }
   __device__ __forceinline__ int atomic_xor(int32_t* p, int v) const { return atomicXor(p, v); }
+  // L2-coherent (ld.global.cg), not the read-only path: branch children are written by other SMs during the same launch, and
+  // the chunks of a HOST batch land (copy engine) while the kernel is already running
   template <class S>
-  __device__ __forceinline__ int ldg(const S* p) const { return (int)__ldg(p); }  // caller's arrays: read-only during the launch
+  __device__ __forceinline__ int ldg(const S* p) const { return (int)__ldcg(p); }
   __device__ __forceinline__ int atomic_cas(int32_t* p, int c, int v) const { return atomicCAS(p, c, v); }
   __device__ __forceinline__ int atomic_cas_idx(int16_t* p, int c, int v) const {
     return (int)(int16_t)atomicCAS((unsigned short*)p, (unsigned short)(int16_t)c, (unsigned short)(int16_t)v);
@@ -427,7 +429,6 @@ struct TcSource {
   int is_pool, capacity;
   const int64_t *hnode_off, *harc_off, *gnode_off;
   const void *succ_off, *succ_adj, *hlabel, *tparent, *tlabel;
-  int idx16;                     // batch mode: the five arrays hold int16_t (kernel variant S = int16_t); the pool is always int32_t
   const int32_t *dims, *origin;  // pool mode
   int sN1, sM, sN, sNT;          // pool strides (elements)
 };
@@ -438,83 +439,192 @@ struct TcSink {
 };
 enum { CNT_DISPLAYED = 0, CNT_ITEMS, CNT_BRANCH_ITEMS, CNT_CHERRIES, CNT_RET, CNT_ARCS, CNT_PASSES, CNT_ERRORS, CNT_N };
 
-// S = element type of the caller's arrays this launch reads (int32_t; int16_t for index_bytes = 2 in round 0).  MAXT = launch
+// instance `item` of the caller's batch (element type S) as a TcInst
+template <class S>
+__device__ __forceinline__ void batch_inst(const TcSource& src, int item, TcInst& in) {
+  const int sh = sizeof(S) == 1 ? 0 : (sizeof(S) == 2 ? 1 : 2);  // log2 of the element size
+  const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
+  const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
+  in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
+  if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
+  // the degree layout (uint8_t) has n entries per instance in succ_off, the offset layouts n + 1
+  in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + (TcLayout<S>::kDegrees ? 0 : item)) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
+  in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
+  in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh);
+}
+
+// ---- the persistent warp kernel: ONE launch per pt_batch_contain ------------------------------------------------------------
+// Work items are the batch's instances (ticket) and the branch children other warps have pushed into the pool during the same
+// launch.  A branching warp pushes all children but the first as compact instances (same element type S as the batch) and goes
+// on with the first one IN PLACE (keep_only: no emit / reload); idle warps take pool items before fresh instances, so deep
+// branching chains start early instead of forming the kernel's tail.  Termination: `finished` counts completed items; a warp
+// with nothing to take leaves when finished == B + pool_tail (read in that order: both only grow, and every push happens
+// before its parent finishes).  HOST batches are uploaded in chunks on a copy stream that writes chunk_ready[c] after chunk c;
+// a warp whose ticket lies in a chunk that has not landed yet waits for the flag, so the solve overlaps the upload inside one
+// launch.  Every wait is bounded by a watchdog (ctl->abort), so a lost flag becomes an error instead of a hang.
+struct TcCtl {
+  int32_t ticket, pool_tail, pool_head, finished, abort, overflow, done, pad;
+  unsigned long long t_first, t_batch_done, t_last;  // %globaltimer (ns): first warp in, first warp that found the ticket exhausted, last warp out
+};
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+struct TcPool {   // fixed-stride slots of element type S (see TcLayout); ready[slot] == epoch once the slot is complete
+  void *succ_off, *succ_adj, *hlabel, *tparent, *tlabel;
+  int32_t *dims, *origin, *ready;
+  int capacity, sN1, sM, sN, sNT, epoch;
+};
+struct TcChunks { int n; int32_t end[32]; const int32_t* ready; int flags; };  // n = 0: everything is resident; flags: tuning aids (PT_TC_FLAGS)
+
+__device__ __forceinline__ int ld_volatile(const int32_t* p) { return *(const volatile int32_t*)p; }
+constexpr long long kWatchdogCycles = 8000000000ll;  // ~4 s at 1.9 GHz: far beyond any legitimate wait
+
+// S = element type of the caller's arrays (int32_t, int16_t for index_bytes = 2, uint8_t for index_bytes = 1).  MAXT = launch
 // bound = register budget: 768 threads -> 80 registers (the default: 24 warps per SM), 1024 -> 64.
 template <class I, class S, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) tc_reduce_kernel(TcSource src, TcSink sink, int capN, int capM, int capNT, int capL, int warp_bytes,
-                                                        uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
-                                                        uint8_t* __restrict__ branched, int32_t* __restrict__ ticket,
-                                                        unsigned long long* __restrict__ counters) {
+__global__ void __launch_bounds__(MAXT, 1) tc_persistent_kernel(TcSource src, TcPool pool, TcChunks chunks, TcCtl* __restrict__ ctl, int capN, int capM, int capNT, int capL,
+                                                                int warp_bytes, uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
+                                                                uint8_t* __restrict__ branched, unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpEx ex{lane, PT_PHASE_INIT};
   TcWork<I> w;
   w.carve(reinterpret_cast<char*>(smem) + (size_t)warp * warp_bytes, capN, capM, capNT, capL);
-  const int64_t total = src.is_pool ? (int64_t)min(*src.count_ptr, src.capacity) : src.count;
+  const int B = (int)src.count;
   unsigned long long c_disp = 0, c_items = 0, c_br = 0, c_ch = 0, c_ret = 0, c_arc = 0, c_pass = 0, c_err = 0;
+  bool batch_done = false;        // (lane 0) the ticket has run past B
+  int avail = chunks.n ? 0 : B;   // (lane 0) instances [0, avail) are known to be resident
+  int nready = 0;
+  int mine = -1;                  // (lane 0) claimed pool index not consumed yet
+  __shared__ int s_done;
+  if (threadIdx.x == 0) s_done = 0;
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) ctl->t_first = global_ns();
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = (int)src.first + atomicAdd(ticket, 1);
+    // ---- take a work item --------------------------------------------------------------------------------------------------
+    // `mine` is a pool index this warp has claimed with ONE atomicAdd (no retry loop: a compare-and-swap on the head serialises
+    // thousands of idle warps -- measured 3.4 us per item).  A claim is only made when the pool looks non-empty or when there is
+    // nothing else to do; if the claimed slot has not been pushed yet the warp goes on with the batch and looks again later, and
+    // at the end it waits on ITS OWN ready word (every idle warp polls a different address).  The end of the job is published
+    // by the last finisher in ctl->done; warp 0 of a CTA relays it to the CTA through shared memory.
+    int item = -1, from_pool = 0;
+    if (lane == 0) {
+      long long t0 = 0;
+      unsigned spins = 0;
+      for (;;) {
+        if (mine < 0 && (batch_done || !(chunks.flags & 2))) {
+          const int h = ld_volatile(&ctl->pool_head), t = ld_volatile(&ctl->pool_tail);
+          if (h < t || batch_done) mine = atomicAdd(&ctl->pool_head, 1);
+        }
+        if (mine >= 0 && mine < pool.capacity && ld_volatile(&pool.ready[mine]) == pool.epoch) { __threadfence(); item = mine; from_pool = 1; mine = -1; break; }
+        if (!batch_done) {
+          const int i = atomicAdd(&ctl->ticket, 1);
+          if (i < B) { item = i; break; }
+          batch_done = true;
+          atomicMin(&ctl->t_batch_done, global_ns());
+          continue;
+        }
+        // nothing to do: wait for the claimed slot or for the end of the job
+        if (*(volatile int*)&s_done) { item = -2; break; }
+        if (warp == 0 || (spins & 31) == 31) { if (ld_volatile(&ctl->done) || ld_volatile(&ctl->abort)) { *(volatile int*)&s_done = 1; item = -2; break; } }
+        if (!t0) t0 = clock64(); else if ((spins & 255) == 255 && clock64() - t0 > kWatchdogCycles) { atomicExch(&ctl->abort, 1); item = -2; break; }
+        ++spins;
+        __nanosleep(spins < 64 ? 100 : 400);
+      }
+      if (item >= 0 && !from_pool && item >= avail) {    // the instance's chunk may still be on its way (HOST batch)
+        long long t1 = 0;
+        while (item >= avail) {
+          if (nready < chunks.n && ld_volatile(&chunks.ready[nready])) { avail = chunks.end[nready]; ++nready; continue; }
+          if (!t1) t1 = clock64(); else if (clock64() - t1 > kWatchdogCycles || nready >= chunks.n) { atomicExch(&ctl->abort, 1); item = -2; break; }
+          __nanosleep(500);
+        }
+        __threadfence();
+      }
+    }
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= total) break;
+    from_pool = __shfl_sync(0xffffffffu, from_pool, 0);
+    if (item < 0) break;
     TcInst in;
     int origin;
-    if (src.is_pool) {
-      origin = src.origin[item];
+    bool skip = false;
+    if (from_pool) {
+      origin = pool.origin[item];
       int done = 0;
       if (lane == 0) done = (int)((*(volatile uint32_t*)&result_bits[origin >> 5] >> (origin & 31)) & 1u);
-      if (__shfl_sync(0xffffffffu, done, 0)) continue;  // a sibling branch already displayed it
-      in.n = src.dims[4 * item]; in.m = src.dims[4 * item + 1]; in.nt = src.dims[4 * item + 2];
-      in.succ_off = static_cast<const int32_t*>(src.succ_off) + (size_t)item * src.sN1; in.succ_adj = static_cast<const int32_t*>(src.succ_adj) + (size_t)item * src.sM;
-      in.hlabel = static_cast<const int32_t*>(src.hlabel) + (size_t)item * src.sN; in.tparent = static_cast<const int32_t*>(src.tparent) + (size_t)item * src.sNT;
-      in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT;
+      skip = __shfl_sync(0xffffffffu, done, 0) != 0;  // a sibling branch already displayed it
+      in.n = pool.dims[4 * item]; in.m = pool.dims[4 * item + 1]; in.nt = pool.dims[4 * item + 2];
+      in.succ_off = static_cast<const S*>(pool.succ_off) + (size_t)item * pool.sN1; in.succ_adj = static_cast<const S*>(pool.succ_adj) + (size_t)item * pool.sM;
+      in.hlabel = static_cast<const S*>(pool.hlabel) + (size_t)item * pool.sN; in.tparent = static_cast<const S*>(pool.tparent) + (size_t)item * pool.sNT;
+      in.tlabel = static_cast<const S*>(pool.tlabel) + (size_t)item * pool.sNT;
     } else {
       origin = item;
-      const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
-      const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
-      in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
-      if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
-      const int sh = sizeof(S) == 2 ? 1 : 2;  // log2 of the element size
-      in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + item) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
-      in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
-      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh);
+      batch_inst<S>(src, item, in);
     }
-    TcSolver<WarpEx, I> sv(ex, w);
-    int st = 0, x = -1;
-    const int code = sv.template solve<S>(in, src.is_pool != 0, &st, &x);
-    ex.phase = 13;
-    ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
-    if (code == TC_DISPLAYED) {
-      if (lane == 0) { atomicOr(&result_bits[origin >> 5], 1u << (origin & 31)); }
-      ++c_disp;
-    } else if (code == TC_ERROR) {
-      if (lane == 0) status[origin] = (uint8_t)st;
-      ++c_err;
-    } else if (code == TC_BRANCH) {
-      const int d = sv.indeg(x);
-      int base = 0;
-      if (lane == 0) base = atomicAdd(sink.count, d);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base + d > sink.capacity) {
-        if (lane == 0) status[origin] = (uint8_t)TCS_POOL_OVERFLOW;
-      } else {
-        if (lane == 0) branched[origin] = 1;
+    if (!skip) {
+      TcSolver<WarpEx, I> sv(ex, w);
+      int st = 0, x = -1;
+      int code = sv.template begin<S>(in, from_pool != 0, &st);
+      ++c_items;
+      while (code == TC_CONTINUE) {
+        code = sv.rule_loop(&st, &x);
+        ex.phase = 13;
+        if (code != TC_BRANCH) break;
+        // ---- branch on x: children 1 .. d-1 go to the pool, child 0 continues in place -------------------------------------
+        const int d = sv.indeg(x);
+        int base = -1;
+        if (lane == 0) {
+          int old = ld_volatile(&ctl->pool_tail);
+          for (;;) {  // reserve without ever counting a slot that will not be written
+            if (old + (d - ((chunks.flags & 1) ? 0 : 1)) > pool.capacity) { base = -1; break; }
+            const int seen = atomicCAS(&ctl->pool_tail, old, old + (d - ((chunks.flags & 1) ? 0 : 1)));
+            if (seen == old) { base = old; break; }
+            old = seen;
+          }
+          if (base < 0) { status[origin] = (uint8_t)TCS_POOL_OVERFLOW; atomicExch(&ctl->overflow, 1); }
+          else if (!from_pool) branched[origin] = 1;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base < 0) { code = TC_ERROR; st = TCS_POOL_OVERFLOW; ++c_err; break; }
         c_br += (unsigned long long)d;
         int32_t* arcs = reinterpret_cast<int32_t*>(w.lset);  // the label sets are dead by now; d <= n <= capN * W words
         for (int k = lane; k < d; k += 32) arcs[k] = sv.in_arc(x, k);
         __syncwarp();
-        for (int k = 0; k < d; ++k) {
-          const int keep = arcs[k];
-          const size_t slot = (size_t)(base + k);
-          TcEmit out{sink.succ_off + slot * sink.sN1, sink.succ_adj + slot * sink.sM, sink.hlabel + slot * sink.sN,
-                     sink.tparent + slot * sink.sNT, sink.tlabel + slot * sink.sNT, sink.dims + slot * 4};
-          sv.emit_child(x, keep, out);
-          if (lane == 0) sink.origin[slot] = origin;
+        const int k0 = (chunks.flags & 1) ? 0 : 1;  // tuning aid: bit 0 = no in-place continuation (the parent only emits)
+        for (int k = k0; k < d; ++k) {
+          const size_t slot = (size_t)(base + k - k0);
+          TcEmitT<S> out{static_cast<S*>(pool.succ_off) + slot * pool.sN1, static_cast<S*>(pool.succ_adj) + slot * pool.sM, static_cast<S*>(pool.hlabel) + slot * pool.sN,
+                         static_cast<S*>(pool.tparent) + slot * pool.sNT, static_cast<S*>(pool.tlabel) + slot * pool.sNT, pool.dims + slot * 4};
+          sv.emit_child(x, arcs[k], out);
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) { pool.origin[slot] = origin; __threadfence(); atomicExch(&pool.ready[slot], pool.epoch); }
         }
+        int done = 0;
+        if (lane == 0) done = (int)((*(volatile uint32_t*)&result_bits[origin >> 5] >> (origin & 31)) & 1u);
+        if (__shfl_sync(0xffffffffu, done, 0) || (chunks.flags & 1)) { code = TC_NOT; break; }  // a sibling branch displayed it meanwhile
+        sv.keep_only(x, arcs[0]);
+        ++c_items;
+        code = TC_CONTINUE;
       }
+      c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
+      if (code == TC_DISPLAYED) {
+        if (lane == 0) { atomicOr(&result_bits[origin >> 5], 1u << (origin & 31)); }
+        ++c_disp;
+      } else if (code == TC_ERROR && st != TCS_POOL_OVERFLOW) {
+        if (lane == 0) status[origin] = (uint8_t)st;
+        ++c_err;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      // the LAST finisher sees finished == B + pool_tail (finished is read by the add, the tail after it: both only grow and
+      // every push precedes its parent's finish) and publishes the end of the job
+      __threadfence();
+      const int f = atomicAdd(&ctl->finished, 1) + 1;
+      __threadfence();
+      if (f == B + ld_volatile(&ctl->pool_tail)) atomicExch(&ctl->done, 1);
     }
   }
   if (lane == 0) {
+    atomicMax(&ctl->t_last, global_ns());
     if (c_disp) atomicAdd(&counters[CNT_DISPLAYED], c_disp);
     if (c_items) atomicAdd(&counters[CNT_ITEMS], c_items);
     if (c_br) atomicAdd(&counters[CNT_BRANCH_ITEMS], c_br);
@@ -523,6 +633,18 @@ __global__ void __launch_bounds__(MAXT, 1) tc_reduce_kernel(TcSource src, TcSink
     if (c_arc) atomicAdd(&counters[CNT_ARCS], c_arc);
     if (c_pass) atomicAdd(&counters[CNT_PASSES], c_pass);
     if (c_err) atomicAdd(&counters[CNT_ERRORS], c_err);
+  }
+}
+
+// reserve d consecutive pool slots; -1 if they do not fit.  The counter is only ever advanced over slots that WILL be written
+// (an add-then-check would leave counted but unwritten slots behind for the next round to read)
+__device__ __forceinline__ int pool_reserve(int32_t* count, int d, int capacity) {
+  int old = *(volatile int32_t*)count;
+  for (;;) {
+    if (old + d > capacity) return -1;
+    const int seen = atomicCAS(count, old, old + d);
+    if (seen == old) return old;
+    old = seen;
   }
 }
 
@@ -558,14 +680,7 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
       in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT;
     } else {
       origin = item;
-      const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
-      const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
-      in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
-      if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
-      const int sh = sizeof(S) == 2 ? 1 : 2;  // log2 of the element size
-      in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + item) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
-      in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
-      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh);
+      batch_inst<S>(src, item, in);
     }
     TcSolver<CtaEx, I> sv(ex, w);
     int st = 0, x = -1;
@@ -579,10 +694,10 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
       ++c_err;
     } else if (code == TC_BRANCH) {
       const int d = sv.indeg(x);
-      if (threadIdx.x == 0) s_red[38] = atomicAdd(sink.count, d);
+      if (threadIdx.x == 0) s_red[38] = pool_reserve(sink.count, d, sink.capacity);
       __syncthreads();
       const int base = s_red[38];
-      if (base + d > sink.capacity) {
+      if (base < 0) {
         if (threadIdx.x == 0) status[origin] = (uint8_t)TCS_POOL_OVERFLOW;
       } else {
         if (threadIdx.x == 0) branched[origin] = 1;
@@ -648,14 +763,7 @@ __global__ void __launch_bounds__(PT_CLUSTER_THREADS, 1) tc_reduce_cluster_kerne
       in.tlabel = static_cast<const int32_t*>(src.tlabel) + (size_t)item * src.sNT;
     } else {
       origin = item;
-      const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
-      const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
-      in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
-      if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
-      const int sh = sizeof(S) == 2 ? 1 : 2;  // log2 of the element size
-      in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + item) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
-      in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
-      in.tlabel = static_cast<const char*>(src.tlabel) + (gb << sh);
+      batch_inst<S>(src, item, in);
     }
     TcSolver<ClusterEx, I> sv(ex, w);
     int st = 0, x = -1;
@@ -670,9 +778,9 @@ __global__ void __launch_bounds__(PT_CLUSTER_THREADS, 1) tc_reduce_cluster_kerne
     } else if (code == TC_BRANCH) {
       const int d = sv.indeg(x);
       ex.sync();
-      if (leader) ex.gsc[4] = atomicAdd(sink.count, d);
+      if (leader) ex.gsc[4] = pool_reserve(sink.count, d, sink.capacity);
       const int base = ex.uniform(&ex.gsc[4]);
-      if (base + d > sink.capacity) {
+      if (base < 0) {
         if (leader) status[origin] = (uint8_t)TCS_POOL_OVERFLOW;
       } else {
         if (leader) branched[origin] = 1;
@@ -703,16 +811,29 @@ __global__ void __launch_bounds__(PT_CLUSTER_THREADS, 1) tc_reduce_cluster_kerne
   }
 }
 
+// pt_options.max_rounds cut the branching short: the instances that still have children pending and no "displayed" child yet
+// get a status instead of a silent "not displayed"
+__global__ void tc_round_limit_kernel(const int32_t* __restrict__ origin, int items, const uint32_t* __restrict__ bits, uint8_t* __restrict__ status) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
+    const int o = origin[i];
+    if (!((bits[o >> 5] >> (o & 31)) & 1u)) status[o] = (uint8_t)TCS_ROUND_LIMIT;
+  }
+}
+
 // per-batch maxima of n, m, nt and label id (for DEVICE input without hints)
 __global__ void tc_maxima_kernel(int64_t B, const int64_t* hnode_off, const int64_t* harc_off, const int64_t* gnode_off,
-                                 const void* hlabel, const void* tlabel, int idx16, int32_t* out4) {
+                                 const void* hlabel, const void* tlabel, int idx_bytes, int32_t* out4) {
+  auto lab = [idx_bytes](const void* a, int64_t i) -> int {
+    if (idx_bytes == 1) { const int x = static_cast<const uint8_t*>(a)[i]; return x == 255 ? -1 : x; }
+    return idx_bytes == 2 ? (int)static_cast<const short*>(a)[i] : static_cast<const int*>(a)[i];
+  };
   int mn = 0, mm = 0, mt = 0, ml = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
     mn = max(mn, (int)(hnode_off[i + 1] - hnode_off[i])); mm = max(mm, (int)(harc_off[i + 1] - harc_off[i])); mt = max(mt, (int)(gnode_off[i + 1] - gnode_off[i]));
   }
   const int64_t NH = hnode_off[B], NG = gnode_off[B];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NH; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, (idx16 ? (int)static_cast<const short*>(hlabel)[i] : static_cast<const int*>(hlabel)[i]) + 1);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NG; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, (idx16 ? (int)static_cast<const short*>(tlabel)[i] : static_cast<const int*>(tlabel)[i]) + 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NH; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, lab(hlabel, i) + 1);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < NG; i += (int64_t)gridDim.x * blockDim.x) ml = max(ml, lab(tlabel, i) + 1);
   for (int d = 16; d; d >>= 1) {
     mn = max(mn, __shfl_xor_sync(0xffffffffu, mn, d)); mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, d));
     mt = max(mt, __shfl_xor_sync(0xffffffffu, mt, d)); ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, d));
@@ -739,21 +860,25 @@ struct pt_batch {
   bool owns_input = false;
   int64_t *d_hnode_off = nullptr, *d_harc_off = nullptr, *d_gnode_off = nullptr;
   void *d_succ_off = nullptr, *d_succ_adj = nullptr, *d_hlabel = nullptr, *d_tparent = nullptr, *d_tlabel = nullptr;
-  int idx16 = 0;  // the five arrays above hold int16_t
+  int idx_bytes = 4;  // element size of the five arrays above: 4, 2 (int16_t) or 1 (uint8_t, out-degrees instead of offsets)
   int32_t maxN = 0, maxM = 0, maxNT = 0, maxL = 0;
   // results + scratch
   uint32_t* d_bits = nullptr; uint8_t* d_status = nullptr; uint8_t* d_branched = nullptr;
-  int32_t* d_ticket = nullptr;  // [0] ticket, [1] pool count A, [2] pool count B
+  int32_t* d_ticket = nullptr;  // 256 bytes: the warp path's TcCtl; the global-memory executors: [0] ticket, [1] pool count A, [2] pool count B, [4..] chunk tickets
   unsigned long long* d_counters = nullptr;
-  // pools (ping-pong)
+  // pools of the global-memory executors (ping-pong, int32) and of the persistent warp kernel (one, element type of the batch)
   int pool_cap = 0;
   int32_t* d_pool[2] = {nullptr, nullptr};
+  unsigned char* d_ppool = nullptr; size_t ppool_bytes = 0; int ppool_cap = 0; int32_t* d_pready = nullptr; int pool_epoch = 0;
   unsigned char* d_ws = nullptr; size_t ws_cap = 0;  // global-memory workspaces of the CTA executor
-  // HOST input is uploaded in chunks of instances on a private copy stream; round 0 launches one kernel per chunk as soon as
-  // its bytes have landed, so the upload overlaps the solve (end-to-end path)
+  // HOST input is uploaded in chunks of instances on a private copy stream.  The persistent warp kernel polls d_chunk_ready[c]
+  // (written by the copy stream after chunk c); the global-memory executors launch one kernel per chunk behind chunk_ev[c].
   static constexpr int kMaxChunks = 32;
   cudaStream_t copy_stream = nullptr;
   int nchunks = 1; int64_t chunk_end[kMaxChunks] = {}; cudaEvent_t chunk_ev[kMaxChunks] = {};
+  int32_t* d_chunk_ready = nullptr; cudaEvent_t flags_zeroed = nullptr;
+  int32_t* h_ctl = nullptr;  // pinned copy of the TcCtl of the last warp-path launch (watchdog / overflow), read at the next call
+  bool ctl_pending = false;
   int64_t last_launches = 0;
   int64_t h2d_bytes = 0;
   static constexpr int kMaxTimedRounds = 16;
@@ -765,16 +890,27 @@ struct pt_batch {
 static void batch_release(pt_batch* b) {
   if (!b) return;
   if (b->used_stream_valid) cudaStreamSynchronize(b->used_stream);  // cached blocks may be handed to another handle at once
+  if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
   if (b->owns_input) {
     dev_free(b->d_hnode_off); dev_free(b->d_harc_off); dev_free(b->d_gnode_off);
     dev_free(b->d_succ_off); dev_free(b->d_succ_adj); dev_free(b->d_hlabel); dev_free(b->d_tparent); dev_free(b->d_tlabel);
   }
   dev_free(b->d_bits); dev_free(b->d_status); dev_free(b->d_branched); dev_free(b->d_ticket); dev_free(b->d_counters);
-  dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); dev_free(b->d_ws);
+  dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); dev_free(b->d_ws); dev_free(b->d_ppool); dev_free(b->d_pready); dev_free(b->d_chunk_ready);
   for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : b->chunk_ev) if (e) cudaEventDestroy(e);
-  if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
+  if (b->flags_zeroed) cudaEventDestroy(b->flags_zeroed);
+  if (b->h_ctl) cudaFreeHost(b->h_ctl);
   delete b;
+}
+
+// the word "1" in pinned host memory: what the copy stream writes into chunk_ready[c] (a 4-byte copy-engine transfer that is
+// ordered behind the chunk's own copies; a memset could be a kernel and would not find room next to the persistent kernel)
+static const int32_t* pinned_one() {
+  static int32_t* one = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() { if (cudaHostAlloc((void**)&one, 64, cudaHostAllocPortable) == cudaSuccess) *one = 1; else { cudaGetLastError(); one = nullptr; } });
+  return one;
 }
 
 template <class T>
@@ -783,6 +919,42 @@ static int upload(T** dst, const T* src, int64_t count, cudaStream_t s, int64_t*
   if (int rc = dev_alloc((void**)dst, nb)) return rc;
   if (count > 0) { PT_CUDA(cudaMemcpyAsync(*dst, src, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, s)); *bytes += (int64_t)count * (int64_t)sizeof(T); }
   return PT_OK;
+}
+
+// common scratch of a handle (result words, status, flags, counters)
+static int batch_scratch(pt_batch* b) {
+  const int64_t B = b->B;
+  int rc = PT_OK;
+  if ((rc = dev_alloc((void**)&b->d_bits, ((size_t)((B + 31) / 32) + 1) * 4)) || (rc = dev_alloc((void**)&b->d_status, (size_t)B + 1)) ||
+      (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 256)) ||
+      (rc = dev_alloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long))))
+    return rc;
+  if (cudaHostAlloc((void**)&b->h_ctl, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); b->h_ctl = nullptr; return set_error(PT_ERR_NOMEM, "cudaHostAlloc failed"); }
+  memset(b->h_ctl, 0, 64);
+  return PT_OK;
+}
+
+// the TcCtl of the previous warp-path launch on this handle: a fired watchdog is an error of THAT call, reported here
+static int batch_check_ctl(pt_batch* b) {
+  if (!b->ctl_pending) return PT_OK;
+  b->ctl_pending = false;
+  if (b->used_stream_valid) PT_CUDA(cudaStreamSynchronize(b->used_stream));
+  const TcCtl* c = reinterpret_cast<const TcCtl*>(b->h_ctl);
+  if (c->abort) return set_error(PT_ERR_CUDA, "pt_batch_contain: the device watchdog fired (a wait for an upload chunk or a pool slot did not end); results are incomplete");
+  return PT_OK;
+}
+
+// launch of the persistent warp kernel for element type S
+template <class S>
+static cudaError_t launch_persistent(int wpc, int grid, size_t smem, cudaStream_t s, const TcSource& src, const TcPool& pool, const TcChunks& ch, TcCtl* ctl, const pt_batch* b,
+                                     int warp_bytes, uint32_t* bits, uint8_t* stat) {
+  using I = int16_t;
+  auto k768 = tc_persistent_kernel<I, S, 768>; auto k1024 = tc_persistent_kernel<I, S, 1024>;
+  auto kern = wpc > 24 ? k1024 : k768;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, wpc * 32, smem, s>>>(src, pool, ch, ctl, (int)b->maxN, (int)b->maxM, (int)b->maxNT, (int)b->maxL, warp_bytes, bits, stat, b->d_branched, b->d_counters);
+  return cudaGetLastError();
 }
 
 extern "C" {
@@ -830,15 +1002,19 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   // host_succ_adj may only be null when the batch has no arc at all (std::vector::data() of an empty vector)
   if (!d->host_succ_adj && d->num_instances > 0 && (d->mem != PT_MEM_HOST || d->host_arc_off[d->num_instances] > 0))
     return set_error(PT_ERR_INVALID, "pt_batch_create: host_succ_adj is null");
-  if (d->index_bytes != 0 && d->index_bytes != 2 && d->index_bytes != 4) return set_error(PT_ERR_INVALID, "pt_batch_create: index_bytes must be 0, 2 or 4");
+  if (d->index_bytes != 0 && d->index_bytes != 1 && d->index_bytes != 2 && d->index_bytes != 4) return set_error(PT_ERR_INVALID, "pt_batch_create: index_bytes must be 0, 1, 2 or 4");
   if (int rc = require_device()) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   pt_batch* b = new (std::nothrow) pt_batch();
   if (!b) return set_error(PT_ERR_NOMEM, "out of host memory");
   const int64_t B = b->B = d->num_instances;
-  b->idx16 = d->index_bytes == 2;
-  const size_t esz = b->idx16 ? 2 : 4;
-  auto elem = [&](const int32_t* base, int64_t i) { return b->idx16 ? (int32_t) reinterpret_cast<const int16_t*>(base)[i] : base[i]; };
+  b->idx_bytes = d->index_bytes ? d->index_bytes : 4;
+  const size_t esz = (size_t)b->idx_bytes;
+  const bool deg = b->idx_bytes == 1;  // succ_off holds n out-degrees per instance instead of n + 1 offsets
+  auto elem = [&](const int32_t* base, int64_t i) {
+    return b->idx_bytes == 1 ? (reinterpret_cast<const uint8_t*>(base)[i] == 255 ? -1 : (int32_t) reinterpret_cast<const uint8_t*>(base)[i])
+                             : (b->idx_bytes == 2 ? (int32_t) reinterpret_cast<const int16_t*>(base)[i] : base[i]);
+  };
   b->used_stream = s; b->used_stream_valid = true;
   int rc = PT_OK;
   auto fail = [&](int code) { batch_release(b); return code; };
@@ -867,25 +1043,28 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
     if ((rc = upload(&b->d_hnode_off, d->host_node_off, B + 1, s, &b->h2d_bytes)) || (rc = upload(&b->d_harc_off, d->host_arc_off, B + 1, s, &b->h2d_bytes)) ||
         (rc = upload(&b->d_gnode_off, d->guest_node_off, B + 1, s, &b->h2d_bytes)))
       return fail(rc);
-    if ((rc = dev_alloc(&b->d_succ_off, (size_t)std::max<int64_t>(NH + B, 1) * esz)) || (rc = dev_alloc(&b->d_succ_adj, (size_t)std::max<int64_t>(MH, 1) * esz)) ||
+    if ((rc = dev_alloc(&b->d_succ_off, (size_t)std::max<int64_t>(NH + (deg ? 0 : B), 1) * esz)) || (rc = dev_alloc(&b->d_succ_adj, (size_t)std::max<int64_t>(MH, 1) * esz)) ||
         (rc = dev_alloc(&b->d_hlabel, (size_t)std::max<int64_t>(NH, 1) * esz)) || (rc = dev_alloc(&b->d_tparent, (size_t)std::max<int64_t>(NG, 1) * esz)) ||
         (rc = dev_alloc(&b->d_tlabel, (size_t)std::max<int64_t>(NG, 1) * esz)))
       return fail(rc);
-    b->nchunks = B >= 8192 ? 6 : 1;  // measured with factor 1.7: 6 chunks 11.6 M instances/s end to end, 8: 11.3, 10: 10.7 (each launch has its own tail)
+    // equal chunks of at least 2048 instances: the persistent kernel starts on the first one while the others are in flight
+    b->nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, B / 2048));
     if (const char* e = getenv("PT_TC_CHUNKS")) b->nchunks = std::max(1, std::min((int)pt_batch::kMaxChunks, atoi(e)));  // tuning aid
-    if (b->nchunks > 1 && cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); b->nchunks = 1; }
+    const int32_t* one = b->nchunks > 1 ? pinned_one() : nullptr;
+    if (b->nchunks > 1 && (!one || cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess)) { cudaGetLastError(); b->nchunks = 1; b->copy_stream = nullptr; }
     cudaStream_t cs = b->nchunks > 1 ? b->copy_stream : s;
+    if (b->nchunks > 1) {
+      // the flags are zeroed on the copy stream before anything else happens there; `s` (and any other stream a later
+      // pt_batch_contain uses) waits for that, so no kernel can see a stale "ready" left in the cached block
+      if ((rc = dev_alloc((void**)&b->d_chunk_ready, pt_batch::kMaxChunks * 4))) return fail(rc);
+      cudaError_t e = cudaMemsetAsync(b->d_chunk_ready, 0, pt_batch::kMaxChunks * 4, cs);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->flags_zeroed, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventRecord(b->flags_zeroed, cs);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s, b->flags_zeroed, 0);
+      if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: %s", cudaGetErrorString(e)));
+    }
     for (int c = 0; c < b->nchunks; ++c) {
-      // geometric chunks: the solve (7 ms per 10^5 instances of config 2) is slower than the upload (4 ms), so it should only
-      // ever wait for the FIRST chunk: chunk k+1 must have landed before chunk k is solved, i.e. grow by less than the ratio of
-      // the two rates (1.75) -- factor 1.7, first chunk 3 % of the batch with six chunks
-      auto chunk_bound = [&](int k) {
-        if (k <= 0) return (int64_t)0;
-        if (k >= b->nchunks) return B;
-        const double r = 1.7;
-        return (int64_t)((double)B * (pow(r, k) - 1.0) / (pow(r, b->nchunks) - 1.0)) / 32 * 32;
-      };
-      const int64_t i0 = chunk_bound(c), i1 = chunk_bound(c + 1);
+      const int64_t i0 = B * c / b->nchunks / 32 * 32, i1 = c + 1 == b->nchunks ? B : B * (c + 1) / b->nchunks / 32 * 32;
       b->chunk_end[c] = i1;
       const int64_t h0 = d->host_node_off[i0], h1 = d->host_node_off[i1], a0 = d->host_arc_off[i0], a1 = d->host_arc_off[i1], g0 = d->guest_node_off[i0], g1 = d->guest_node_off[i1];
       auto cp = [&](void* dst, const void* src, int64_t from, int64_t to) -> cudaError_t {
@@ -893,12 +1072,16 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
         b->h2d_bytes += (to - from) * (int64_t)esz;
         return cudaMemcpyAsync(static_cast<char*>(dst) + from * esz, static_cast<const char*>(src) + from * esz, (size_t)(to - from) * esz, cudaMemcpyHostToDevice, cs);
       };
-      cudaError_t e = cp(b->d_succ_off, d->host_succ_off, h0 + i0, h1 + i1);
+      cudaError_t e = cp(b->d_succ_off, d->host_succ_off, h0 + (deg ? 0 : i0), h1 + (deg ? 0 : i1));
       if (e == cudaSuccess) e = cp(b->d_succ_adj, d->host_succ_adj, a0, a1);
       if (e == cudaSuccess) e = cp(b->d_hlabel, d->host_label, h0, h1);
       if (e == cudaSuccess) e = cp(b->d_tparent, d->guest_parent, g0, g1);
       if (e == cudaSuccess) e = cp(b->d_tlabel, d->guest_label, g0, g1);
-      if (e == cudaSuccess && b->nchunks > 1) { e = cudaEventCreateWithFlags(&b->chunk_ev[c], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventRecord(b->chunk_ev[c], cs); }
+      if (e == cudaSuccess && b->nchunks > 1) {
+        e = cudaMemcpyAsync(b->d_chunk_ready + c, one, 4, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->chunk_ev[c], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(b->chunk_ev[c], cs);
+      }
       if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: upload failed: %s", cudaGetErrorString(e)));
     }
   } else {
@@ -909,7 +1092,7 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       int32_t* d4 = nullptr; int32_t h4[4] = {0, 0, 0, 0};
       if (int rc = dev_alloc((void**)&d4, 16)) return fail(rc);
       cudaMemsetAsync(d4, 0, 16, s);
-      tc_maxima_kernel<<<296, 256, 0, s>>>(B, b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_hlabel, b->d_tlabel, b->idx16, d4);
+      tc_maxima_kernel<<<296, 256, 0, s>>>(B, b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_hlabel, b->d_tlabel, b->idx_bytes, d4);
       cudaError_t e = cudaMemcpyAsync(h4, d4, 16, cudaMemcpyDeviceToHost, s);
       if (e == cudaSuccess) e = cudaStreamSynchronize(s); else cudaStreamSynchronize(s);
       dev_free(d4);
@@ -919,17 +1102,15 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   }
   if (b->maxM <= 0) b->maxM = std::max(1, 2 * b->maxN);
   b->maxN = std::max(b->maxN, 1); b->maxNT = std::max(b->maxNT, 1); b->maxL = std::max(b->maxL, 1);
-  const size_t words = (size_t)((B + 31) / 32) + 1;
-  if ((rc = dev_alloc((void**)&b->d_bits, words * 4)) || (rc = dev_alloc((void**)&b->d_status, (size_t)B + 1)) ||
-      (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 256)) ||
-      (rc = dev_alloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long))))
-    return fail(rc);
+  if (b->idx_bytes == 1 && (b->maxN > 255 || b->maxNT > 255 || b->maxL > 255))
+    return fail(set_error(PT_ERR_INVALID, "pt_batch_create: index_bytes = 1 needs at most 255 host nodes, guest nodes and labels per instance"));
+  if ((rc = batch_scratch(b))) return fail(rc);
   *out = b;
   return PT_OK;
 }
 
 // array `which` of the batch as it lives on the device (0 host_node_off, 1 host_arc_off, 2 guest_node_off: int64; 3 succ_off,
-// 4 succ_adj, 5 host_label, 6 guest_parent, 7 guest_label: int32 or int16 per *index_bytes) copied to `dst`
+// 4 succ_adj, 5 host_label, 6 guest_parent, 7 guest_label: int32, int16 or uint8 per *index_bytes) copied to `dst`
 int pt_batch_download(pt_batch* b, int which, void* dst, int64_t capacity_bytes, int64_t* bytes, int32_t* index_bytes, int32_t maxima[4]) {
   if (!b || which < 0 || which > 7 || !bytes) return set_error(PT_ERR_INVALID, "pt_batch_download: bad argument");
   const int64_t B = b->B;
@@ -940,9 +1121,9 @@ int pt_batch_download(pt_batch* b, int which, void* dst, int64_t capacity_bytes,
     PT_CUDA(cudaMemcpy(&tail[0], b->d_hnode_off + B, 8, cudaMemcpyDeviceToHost)); PT_CUDA(cudaMemcpy(&tail[1], b->d_harc_off + B, 8, cudaMemcpyDeviceToHost));
     PT_CUDA(cudaMemcpy(&tail[2], b->d_gnode_off + B, 8, cudaMemcpyDeviceToHost));
   }
-  const int64_t esz = b->idx16 ? 2 : 4;
+  const int64_t esz = b->idx_bytes;
   const void* src[8] = {b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_succ_off, b->d_succ_adj, b->d_hlabel, b->d_tparent, b->d_tlabel};
-  const int64_t n[8] = {(B + 1) * 8, (B + 1) * 8, (B + 1) * 8, (tail[0] + B) * esz, tail[1] * esz, tail[0] * esz, tail[2] * esz, tail[2] * esz};
+  const int64_t n[8] = {(B + 1) * 8, (B + 1) * 8, (B + 1) * 8, (tail[0] + (esz == 1 ? 0 : B)) * esz, tail[1] * esz, tail[0] * esz, tail[2] * esz, tail[2] * esz};
   *bytes = n[which];
   if (index_bytes) *index_bytes = (int32_t)esz;
   if (maxima) { maxima[0] = b->maxN; maxima[1] = b->maxM; maxima[2] = b->maxNT; maxima[3] = b->maxL; }
@@ -957,31 +1138,41 @@ int64_t pt_batch_last_launches(const pt_batch* b) { return b ? b->last_launches 
 
 // A batch whose device arrays were produced on the device (csrc/newick_kernels.cu): the handle takes ownership of the eight
 // dev_alloc'ed arrays (order: host_node_off, host_arc_off, guest_node_off, succ_off, succ_adj, host_label, guest_parent, guest_label).
-int ptgpu_batch_adopt(pt_batch** out, int64_t B, void* const arrays[8], int idx16, const int32_t maxima[4], void* stream) {
+int ptgpu_batch_adopt(pt_batch** out, int64_t B, void* const arrays[8], int index_bytes, const int32_t maxima[4], void* stream) {
   pt_batch* b = new (std::nothrow) pt_batch();
   if (!b) return set_error(PT_ERR_NOMEM, "out of host memory");
-  b->B = B; b->owns_input = true; b->idx16 = idx16;
+  b->B = B; b->owns_input = true; b->idx_bytes = index_bytes;
   b->used_stream = (cudaStream_t)stream; b->used_stream_valid = true;
   b->d_hnode_off = (int64_t*)arrays[0]; b->d_harc_off = (int64_t*)arrays[1]; b->d_gnode_off = (int64_t*)arrays[2];
   b->d_succ_off = arrays[3]; b->d_succ_adj = arrays[4]; b->d_hlabel = arrays[5]; b->d_tparent = arrays[6]; b->d_tlabel = arrays[7];
   b->maxN = std::max(maxima[0], 1); b->maxM = std::max(maxima[1], 1); b->maxNT = std::max(maxima[2], 1); b->maxL = std::max(maxima[3], 1);
-  int rc = PT_OK;
-  if ((rc = dev_alloc((void**)&b->d_bits, ((size_t)((B + 31) / 32) + 1) * 4)) || (rc = dev_alloc((void**)&b->d_status, (size_t)B + 1)) ||
-      (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 256)) ||
-      (rc = dev_alloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long)))) { batch_release(b); return rc; }
+  if (int rc = batch_scratch(b)) { batch_release(b); return rc; }
   *out = b;
   return PT_OK;
 }
 int64_t pt_batch_h2d_bytes(const pt_batch* b) { return b ? b->h2d_bytes : 0; }
-int pt_batch_round_ms(const pt_batch* b, int round, float* ms) {
-  if (!b || !ms || round < 0 || round >= b->timed_rounds) return set_error(PT_ERR_INVALID, "pt_batch_round_ms: round %d did not run (or was not timed)", round);
-  PT_CUDA(cudaEventElapsedTime(ms, b->ev[2 * round], b->ev[2 * round + 1]));
+// debug / profiling aid (not part of include/pt_gpu.h): phases of the last persistent launch in microseconds --
+// out[0] = first warp in -> first warp that found the batch ticket exhausted, out[1] = from there to the last warp out (the tail),
+// out[2] = pool slots used, out[3] = items finished
+int pt_debug_last_phases(pt_batch* b, double out[4]) {
+  if (!b || !b->h_ctl) return PT_ERR_INVALID;
+  if (b->used_stream_valid) cudaStreamSynchronize(b->used_stream);
+  const TcCtl* c = reinterpret_cast<const TcCtl*>(b->h_ctl);
+  out[0] = (double)(c->t_batch_done - c->t_first) / 1e3; out[1] = (double)(c->t_last - c->t_batch_done) / 1e3; out[2] = c->pool_tail; out[3] = c->finished;
   return PT_OK;
+}
+int pt_batch_round_ms(const pt_batch* bc, int round, float* ms) {
+  pt_batch* b = const_cast<pt_batch*>(bc);
+  if (!b || !ms || round < 0 || round >= b->timed_rounds) return set_error(PT_ERR_INVALID, "pt_batch_round_ms: round %d did not run (or was not timed)", round);
+  PT_CUDA(cudaEventSynchronize(b->ev[2 * round + 1]));  // pt_batch_contain with DEVICE outputs does not wait for its kernel
+  PT_CUDA(cudaEventElapsedTime(ms, b->ev[2 * round], b->ev[2 * round + 1]));
+  return batch_check_ctl(b);
 }
 
 int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, uint8_t* status, pt_mem out_mem, pt_counters* counters, void* stream) {
   if (!b || !result_bits) return set_error(PT_ERR_INVALID, "pt_batch_contain: null argument");
   if (int rc = require_device()) return rc;
+  if (int rc = batch_check_ctl(b)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   DeviceProps dp;
   if (int rc = device_props(&dp)) return rc;
@@ -989,6 +1180,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   const int64_t B = b->B;
   const size_t words = (size_t)((B + 31) / 32);
   b->last_launches = 0; b->timed_rounds = 0;
+  if (b->flags_zeroed && (!b->used_stream_valid || b->used_stream != s)) PT_CUDA(cudaStreamWaitEvent(s, b->flags_zeroed, 0));
   b->used_stream = s; b->used_stream_valid = true;
   uint32_t* bits = out_mem == PT_MEM_DEVICE ? result_bits : b->d_bits;
   uint8_t* stat = (out_mem == PT_MEM_DEVICE && status) ? status : b->d_status;
@@ -998,31 +1190,75 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   PT_CUDA(cudaMemsetAsync(b->d_counters, 0, CNT_N * sizeof(unsigned long long), s));
   PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 256, s));
   uint64_t rounds = 0;
-  // two executors over the same solver: warps with the instance in shared memory (int16 ids), or one CTA per instance with
-  // the workspace in global memory (int32 ids) when an instance does not fit one CTA's shared memory
+  // executors over the same solver: warps with the instance in shared memory (int16 ids, ONE persistent launch), or one CTA /
+  // one cluster per instance with the workspace in global memory (int32 ids, one launch per branching depth) when an instance
+  // does not fit one CTA's shared memory
   const int force = opt ? opt->path : 0;
   const bool fits16 = b->maxN <= 30000 && b->maxM <= 30000 && b->maxNT <= 30000 && b->maxL <= 30000;
   const size_t warp_bytes = TcWork<I>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL);
   const bool use_cta = force == 2 || force == 3 || !fits16 || warp_bytes > (size_t)dp.smem_optin;
+  const int sN1 = b->maxN + 1, sM = std::max(1, (int)b->maxM), sN = b->maxN, sNT = b->maxNT;
+  const size_t slot_elems = (size_t)sN1 + sM + sN + 2 * (size_t)sNT;
+  int want = opt && opt->pool_slots > 0 ? opt->pool_slots : (int)std::min<int64_t>(std::max<int64_t>(8192, B), 1 << 22);
   if (force == 1 && use_cta && B > 0) {
     PT_CUDA(cudaMemsetAsync(stat, PT_INST_TOO_LARGE, (size_t)B, s));  // caller insisted on the shared-memory path
+  } else if (B > 0 && !use_cta) {
+    // ---- the warp executor: one persistent launch --------------------------------------------------------------------------
+    // occupancy: as many warps per SM as shared memory allows (warp_bytes each), in one CTA per SM; the kernel variant
+    // (register budget) follows from the warp count
+    int max_warps = kDefaultMaxWarps;
+    if (const char* e = getenv("PT_TC_MAX_WARPS")) max_warps = std::max(1, std::min(32, atoi(e)));  // tuning aid
+    const int wpc = std::max(1, (int)std::min<size_t>((size_t)max_warps, ((size_t)dp.smem_optin) / warp_bytes));
+    const size_t smem = (size_t)wpc * warp_bytes;
+    const size_t esz = (size_t)b->idx_bytes;
+    if (!(opt && opt->pool_slots > 0)) want = (int)std::max<size_t>(16, std::min<size_t>((size_t)want, ((size_t)4 << 30) / (slot_elems * esz + 32)));  // <= 4 GB
+    const size_t stride_bytes = (slot_elems * esz + 15) & ~(size_t)15;
+    if (b->ppool_cap < want) {
+      dev_free(b->d_ppool); dev_free(b->d_pready); b->d_ppool = nullptr; b->d_pready = nullptr; b->ppool_cap = 0;
+      const size_t arrays = ((size_t)(sN1 + sM + sN + 2 * (size_t)sNT) * esz * (size_t)want + 63) & ~(size_t)63;
+      if (int rc2 = dev_alloc((void**)&b->d_ppool, arrays + (size_t)want * 5 * 4 + 64)) return rc2;
+      if (int rc2 = dev_alloc((void**)&b->d_pready, (size_t)want * 4)) return rc2;
+      PT_CUDA(cudaMemsetAsync(b->d_pready, 0, (size_t)want * 4, s));
+      b->ppool_cap = want; b->pool_epoch = 0; b->ppool_bytes = arrays;
+    }
+    (void)stride_bytes;
+    if (++b->pool_epoch == 0x7fffffff) { PT_CUDA(cudaMemsetAsync(b->d_pready, 0, (size_t)b->ppool_cap * 4, s)); b->pool_epoch = 1; }
+    const int cap = std::min(b->ppool_cap, want);  // an explicit pt_options.pool_slots also caps an already larger pool
+    TcPool pool{};
+    {
+      // arrays are laid out for the handle's full capacity so that the int32 tail stays aligned whatever `cap` is
+      unsigned char* p = b->d_ppool; const size_t C = (size_t)b->ppool_cap;
+      pool.succ_off = p; p += (size_t)sN1 * esz * C; pool.succ_adj = p; p += (size_t)sM * esz * C; pool.hlabel = p; p += (size_t)sN * esz * C;
+      pool.tparent = p; p += (size_t)sNT * esz * C; pool.tlabel = p;
+      int32_t* q = reinterpret_cast<int32_t*>(b->d_ppool + b->ppool_bytes);
+      pool.dims = q; q += 4 * C; pool.origin = q;
+      pool.ready = b->d_pready; pool.capacity = cap; pool.sN1 = sN1; pool.sM = sM; pool.sN = sN; pool.sNT = sNT; pool.epoch = b->pool_epoch;
+    }
+    TcSource src{};
+    src.first = 0; src.count = B; src.is_pool = 0; src.hnode_off = b->d_hnode_off; src.harc_off = b->d_harc_off; src.gnode_off = b->d_gnode_off;
+    src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel;
+    TcChunks ch{};
+    if (const char* e = getenv("PT_TC_FLAGS")) ch.flags = atoi(e);
+    if (b->nchunks > 1 && b->d_chunk_ready) { ch.n = b->nchunks; for (int c = 0; c < b->nchunks; ++c) ch.end[c] = (int32_t)b->chunk_end[c]; ch.ready = b->d_chunk_ready; }
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)dp.sms, (B + wpc - 1) / wpc));
+    for (int j = 0; j < 2; ++j) if (!b->ev[j]) PT_CUDA(cudaEventCreate(&b->ev[j]));
+    PT_CUDA(cudaEventRecord(b->ev[0], s));
+    TcCtl* ctl = reinterpret_cast<TcCtl*>(b->d_ticket);
+    PT_CUDA(cudaMemsetAsync(&ctl->t_batch_done, 0xff, 8, s));
+    cudaError_t e = b->idx_bytes == 1 ? launch_persistent<uint8_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat)
+                  : b->idx_bytes == 2 ? launch_persistent<int16_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat)
+                                      : launch_persistent<int32_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat);
+    if (e != cudaSuccess) return set_error(PT_ERR_CUDA, "pt_batch_contain: launch failed: %s", cudaGetErrorString(e));
+    PT_CUDA(cudaEventRecord(b->ev[1], s));
+    b->timed_rounds = 1; b->last_launches = 1; rounds = 1;
+    PT_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ticket, sizeof(TcCtl), cudaMemcpyDeviceToHost, s));
+    b->ctl_pending = true;
   } else if (B > 0) {
-    int wpc = 1, ctas_per_sm = 1;
-    size_t smem = 0, ws_bytes = 0;
-    auto warp_kernel = tc_reduce_kernel<I, int32_t, 768>, warp_kernel16 = tc_reduce_kernel<I, int16_t, 768>;
+    // ---- the global-memory executors: one launch per branching depth over ping-pong pools ----------------------------------
+    int ctas_per_sm = 1;
+    size_t ws_bytes = 0;
     int cta_grid_cap = 0, max_cluster = 8;
-    if (!use_cta) {
-      // occupancy: as many warps per SM as shared memory allows (warp_bytes each), in one CTA per SM; the kernel variant
-      // (register budget) follows from the warp count
-      int max_warps = kDefaultMaxWarps;
-      if (const char* e = getenv("PT_TC_MAX_WARPS")) max_warps = std::max(1, std::min(32, atoi(e)));  // tuning aid
-      int warps_per_sm = (int)std::min<size_t>((size_t)max_warps, ((size_t)dp.smem_optin) / warp_bytes);
-      wpc = std::max(warps_per_sm, 1);
-      smem = (size_t)wpc * warp_bytes;
-      if (wpc > 24) { warp_kernel = tc_reduce_kernel<I, int32_t, 1024>; warp_kernel16 = tc_reduce_kernel<I, int16_t, 1024>; }
-      PT_CUDA(cudaFuncSetAttribute(warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PT_CUDA(cudaFuncSetAttribute(warp_kernel16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else {
+    {
       // one stride for both global-memory executors: 256 bytes of cluster scalars + the arrays with the spare arc arrays
       ws_bytes = (256 + TcWork<int32_t>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL, true) + 255) & ~(size_t)255;
       size_t free_b = 0, total_b = 0;
@@ -1034,7 +1270,8 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       if (const char* e = getenv("PT_TC_MAX_CLUSTER")) {  // tuning aid; 16 needs the non-portable opt-in
         max_cluster = std::max(1, std::min(16, atoi(e)));
         if (max_cluster > 8 && (cudaFuncSetAttribute(tc_reduce_cluster_kernel<int16_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-                                cudaFuncSetAttribute(tc_reduce_cluster_kernel<int32_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+                                cudaFuncSetAttribute(tc_reduce_cluster_kernel<int32_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                                cudaFuncSetAttribute(tc_reduce_cluster_kernel<uint8_t>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
           cudaGetLastError(); max_cluster = 8;
         }
       }
@@ -1045,13 +1282,11 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       }
     }
     // pool
-    const int sN1 = b->maxN + 1, sM = std::max(1, (int)b->maxM), sN = b->maxN, sNT = b->maxNT;
-    const size_t slot_elems = (size_t)sN1 + sM + sN + 2 * (size_t)sNT + 4 + 1;
-    int want = opt && opt->pool_slots > 0 ? opt->pool_slots : (int)std::min<int64_t>(std::max<int64_t>(8192, B), 1 << 22);
-    if (!(opt && opt->pool_slots > 0)) want = (int)std::max<size_t>(16, std::min<size_t>((size_t)want, ((size_t)4 << 30) / (slot_elems * 4)));  // <= 4 GB per pool
+    const size_t slot_ints = slot_elems + 4 + 1;
+    if (!(opt && opt->pool_slots > 0)) want = (int)std::max<size_t>(16, std::min<size_t>((size_t)want, ((size_t)4 << 30) / (slot_ints * 4)));  // <= 4 GB per pool
     if (b->pool_cap < want) {
       dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); b->d_pool[0] = b->d_pool[1] = nullptr; b->pool_cap = 0;
-      for (int k = 0; k < 2; ++k) if (int rc2 = dev_alloc((void**)&b->d_pool[k], slot_elems * (size_t)want * 4)) return rc2;
+      for (int k = 0; k < 2; ++k) if (int rc2 = dev_alloc((void**)&b->d_pool[k], slot_ints * (size_t)want * 4)) return rc2;
       b->pool_cap = want;
     }
     const int cap = std::min(b->pool_cap, want);  // an explicit pt_options.pool_slots also caps an already larger pool
@@ -1062,16 +1297,23 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       t.count = b->d_ticket + 1 + k; t.capacity = cap; t.sN1 = sN1; t.sM = sM; t.sN = sN; t.sNT = sNT;
       return t;
     };
-    const int max_rounds = opt && opt->max_rounds > 0 ? opt->max_rounds : 64;
+    // every round fixes one more multi-parent node, so the depth is bounded by the number of nodes; pt_options.max_rounds can
+    // only lower that bound (whatever is still pending then is REPORTED, see tc_round_limit_kernel)
+    const int64_t max_rounds = opt && opt->max_rounds > 0 ? opt->max_rounds : (int64_t)b->maxN + 2;
     TcSource src{};
     src.count = B; src.is_pool = 0; src.hnode_off = b->d_hnode_off; src.harc_off = b->d_harc_off; src.gnode_off = b->d_gnode_off;
-    src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel; src.idx16 = b->idx16;
+    src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel;
     int64_t items = B;
-    for (int round = 0; round < max_rounds && items > 0; ++round) {
-      const int k = round & 1;
+    TcSink pending{};
+    for (int64_t round = 0; items > 0; ++round) {
+      if (round >= max_rounds) {  // not a verdict: whoever is still in the pool is told so
+        tc_round_limit_kernel<<<(unsigned)std::min<int64_t>((items + 255) / 256, 1024), 256, 0, s>>>(pending.origin, (int)items, bits, stat);
+        PT_CUDA(cudaGetLastError());
+        break;
+      }
+      const int k = (int)(round & 1);
       TcSink sink = sink_of(k);
-      int grid = use_cta ? (int)std::min<int64_t>(cta_grid_cap, items) : (int)std::min<int64_t>((int64_t)dp.sms * ctas_per_sm, (items + wpc - 1) / wpc);
-      grid = std::max(grid, 1);
+      int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cta_grid_cap, items));
       const bool timed = round < pt_batch::kMaxTimedRounds;
       if (timed) {
         for (int j = 0; j < 2; ++j) if (!b->ev[2 * round + j]) PT_CUDA(cudaEventCreate(&b->ev[2 * round + j]));
@@ -1088,16 +1330,16 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
           if (b->chunk_ev[c]) PT_CUDA(cudaStreamWaitEvent(s, b->chunk_ev[c], 0));
           const int64_t cnt = src.count - src.first;
           if (cnt <= 0) continue;
-          grid = use_cta ? (int)std::min<int64_t>(cta_grid_cap, cnt) : (int)std::min<int64_t>((int64_t)dp.sms * ctas_per_sm, (cnt + wpc - 1) / wpc);
-          grid = std::max(grid, 1);
+          grid = (int)std::max<int64_t>(1, std::min<int64_t>(cta_grid_cap, cnt));
         }
-        const bool in16 = !src.is_pool && src.idx16;  // element type of what this launch reads
+        const int in_bytes = src.is_pool ? 4 : b->idx_bytes;  // element type of what this launch reads
         // few huge instances: a cluster of CTAs per instance, as large as keeps every instance of this launch on its own SMs
-        auto cluster_kernel = in16 ? tc_reduce_cluster_kernel<int16_t> : tc_reduce_cluster_kernel<int32_t>;
+        auto cluster_kernel = in_bytes == 1 ? tc_reduce_cluster_kernel<uint8_t> : (in_bytes == 2 ? tc_reduce_cluster_kernel<int16_t> : tc_reduce_cluster_kernel<int32_t>);
+        auto cta_kernel = in_bytes == 1 ? tc_reduce_cta_kernel<uint8_t> : (in_bytes == 2 ? tc_reduce_cta_kernel<int16_t> : tc_reduce_cta_kernel<int32_t>);
         int csize = 1;
-        if (use_cta && force != 2) { while (csize < max_cluster && (int64_t)grid * csize * 2 <= dp.sms) csize *= 2; }
-        if (use_cta && force == 3 && csize == 1) csize = 2;
-        if (use_cta && csize > 1) {
+        if (force != 2) { while (csize < max_cluster && (int64_t)grid * csize * 2 <= dp.sms) csize *= 2; }
+        if (force == 3 && csize == 1) csize = 2;
+        if (csize > 1) {
           cudaLaunchConfig_t cfg = {};
           cfg.gridDim = dim3((unsigned)(grid * csize)); cfg.blockDim = dim3(PT_CLUSTER_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
           cudaLaunchAttribute attr[1];
@@ -1105,16 +1347,12 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
           cfg.attrs = attr; cfg.numAttrs = 1;
           PT_CUDA(cudaLaunchKernelEx(&cfg, cluster_kernel, src, sink, (int)b->maxN, (int)b->maxM,
                                      (int)b->maxNT, (int)b->maxL, ws_bytes, b->d_ws, bits, stat, b->d_branched, ticket, b->d_counters));
-        } else if (use_cta)
-          (in16 ? tc_reduce_cta_kernel<int16_t> : tc_reduce_cta_kernel<int32_t>)<<<grid, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits,
-                                                                                                      stat, b->d_branched, ticket, b->d_counters);
-        else
-          (in16 ? warp_kernel16 : warp_kernel)<<<grid, wpc * 32, smem, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, (int)warp_bytes, bits, stat, b->d_branched,
-                                                                            ticket, b->d_counters);
+        } else
+          cta_kernel<<<grid * ctas_per_sm, 512, 0, s>>>(src, sink, b->maxN, b->maxM, b->maxNT, b->maxL, ws_bytes, b->d_ws, bits, stat, b->d_branched, ticket, b->d_counters);
         ++b->last_launches;
       }
       PT_CUDA(cudaGetLastError());
-      if (timed) { PT_CUDA(cudaEventRecord(b->ev[2 * round + 1], s)); b->timed_rounds = round + 1; }
+      if (timed) { PT_CUDA(cudaEventRecord(b->ev[2 * round + 1], s)); b->timed_rounds = (int)round + 1; }
       ++rounds;
       int32_t h[4];
       PT_CUDA(cudaMemcpyAsync(h, b->d_ticket, 16, cudaMemcpyDeviceToHost, s));
@@ -1122,10 +1360,10 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       items = std::min<int64_t>(h[1 + k], cap);
       if (items <= 0) break;
       // next round reads the pool just written; reset the ticket and the other pool's counter
-      TcSink just = sink;
+      pending = sink;
       src = TcSource{};
-      src.is_pool = 1; src.idx16 = 0; src.count_ptr = just.count; src.capacity = cap; src.succ_off = just.succ_off; src.succ_adj = just.succ_adj; src.hlabel = just.hlabel;
-      src.tparent = just.tparent; src.tlabel = just.tlabel; src.dims = just.dims; src.origin = just.origin; src.sN1 = sN1; src.sM = sM; src.sN = sN; src.sNT = sNT;
+      src.is_pool = 1; src.count_ptr = pending.count; src.capacity = cap; src.succ_off = pending.succ_off; src.succ_adj = pending.succ_adj; src.hlabel = pending.hlabel;
+      src.tparent = pending.tparent; src.tlabel = pending.tlabel; src.dims = pending.dims; src.origin = pending.origin; src.sN1 = sN1; src.sM = sM; src.sN = sN; src.sNT = sNT;
       PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 4, s));
       PT_CUDA(cudaMemsetAsync(b->d_ticket + 1 + (k ^ 1), 0, 4, s));
     }
@@ -1154,6 +1392,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   } else if (out_mem == PT_MEM_HOST) {
     PT_CUDA(cudaStreamSynchronize(s));
   }
+  if (out_mem == PT_MEM_HOST || counters) return batch_check_ctl(b);  // the stream has been synchronised: report a fired watchdog now
   return PT_OK;
 }
 
@@ -1175,7 +1414,8 @@ int pt_batch_contain_multi(const pt_batch_desc* d, int num_devices, const pt_opt
       return set_error(PT_ERR_INVALID, "pt_batch_contain_multi: offset tables must be non-decreasing (instance %lld)", (long long)i);
   int prev_dev = 0;
   cudaGetDevice(&prev_dev);
-  const size_t esz = d->index_bytes == 2 ? 2 : 4;
+  const size_t esz = d->index_bytes == 2 ? 2 : (d->index_bytes == 1 ? 1 : 4);
+  const bool deg = d->index_bytes == 1;  // succ_off holds n out-degrees per instance, not n + 1 offsets
   std::vector<int> rcs((size_t)G, PT_OK);
   std::vector<std::string> msgs((size_t)G);
   std::vector<pt_counters> cnt((size_t)G);
@@ -1194,7 +1434,7 @@ int pt_batch_contain_multi(const pt_batch_desc* d, int num_devices, const pt_opt
       auto at = [&](const int32_t* base, int64_t elems) { return base ? reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(base) + (size_t)elems * esz) : nullptr; };
       pt_batch_desc sd = *d;
       sd.num_instances = nb; sd.host_node_off = hn.data(); sd.host_arc_off = ha.data(); sd.guest_node_off = gn.data();
-      sd.host_succ_off = at(d->host_succ_off, d->host_node_off[i0] + i0); sd.host_succ_adj = at(d->host_succ_adj, d->host_arc_off[i0]);
+      sd.host_succ_off = at(d->host_succ_off, d->host_node_off[i0] + (deg ? 0 : i0)); sd.host_succ_adj = at(d->host_succ_adj, d->host_arc_off[i0]);
       sd.host_label = at(d->host_label, d->host_node_off[i0]); sd.guest_parent = at(d->guest_parent, d->guest_node_off[i0]); sd.guest_label = at(d->guest_label, d->guest_node_off[i0]);
       sd.host_pred_off = sd.host_pred_adj = sd.guest_child_off = sd.guest_child_adj = nullptr;
       pt_batch* h = nullptr;

@@ -117,6 +117,32 @@ class BatchPacker {
   }
   std::vector<int16_t> c_succ_off, c_succ_adj, c_host_label, c_guest_parent, c_guest_label;
 
+  // the same batch with uint8 data arrays (pt_batch_desc.index_bytes = 1): a quarter of the bytes to upload.  host_succ_off
+  // then holds the n OUT-DEGREES of an instance (at host_node_off[i], no "+ i") instead of n + 1 offsets -- arc positions can
+  // exceed 255 (config 2: m = 258) while every node id, label id and degree still fits a byte; 255 stands for -1.
+  bool bytes_ok() const { return max_host_nodes <= 255 && max_guest_nodes <= 255 && max_labels <= 255; }
+  pt_batch_desc desc_bytes() {
+    if (!bytes_ok()) throw std::logic_error("an instance is too large for 8-bit ids");
+    const size_t B = size();
+    b_degree.resize((size_t)host_node_off[B]);
+    for (size_t i = 0; i < B; ++i)
+      for (int64_t v = 0, n = host_node_off[i + 1] - host_node_off[i]; v < n; ++v) {
+        const int32_t* off = &host_succ_off[(size_t)(host_node_off[i] + (int64_t)i + v)];
+        if (off[1] - off[0] > 255) throw std::logic_error("an out-degree is too large for the 8-bit layout");
+        b_degree[(size_t)(host_node_off[i] + v)] = (uint8_t)(off[1] - off[0]);
+      }
+    auto narrow = [](const std::vector<int32_t>& a, std::vector<uint8_t>& b) { b.resize(a.size()); for (size_t i = 0; i < a.size(); ++i) b[i] = (uint8_t)(a[i] < 0 ? 255 : a[i]); };
+    narrow(host_succ_adj, b_succ_adj); narrow(host_label, b_host_label); narrow(guest_parent, b_guest_parent); narrow(guest_label, b_guest_label);
+    pt_batch_desc d = desc();
+    d.host_succ_off = reinterpret_cast<const int32_t*>(b_degree.data()); d.host_succ_adj = reinterpret_cast<const int32_t*>(b_succ_adj.data());
+    d.host_label = reinterpret_cast<const int32_t*>(b_host_label.data()); d.guest_parent = reinterpret_cast<const int32_t*>(b_guest_parent.data());
+    d.guest_label = reinterpret_cast<const int32_t*>(b_guest_label.data());
+    d.host_pred_off = d.host_pred_adj = d.guest_child_off = d.guest_child_adj = nullptr;
+    d.index_bytes = 1;
+    return d;
+  }
+  std::vector<uint8_t> b_degree, b_succ_adj, b_host_label, b_guest_parent, b_guest_label;
+
   std::vector<std::vector<std::string>> dict_names;  // per instance: label id -> string
 
   // extended Newick (host, guest) of instance i, rebuilt from the flat arrays

@@ -17,16 +17,20 @@ def shard_ranges(weights, world_size, align=32):
     for r in range(1, world_size):
         target = total * r // world_size
         i = int(np.searchsorted(cum, target, side="left"))
-        i = min(B, max(cuts[-1], (i + align // 2) // align * align))
+        # interior cuts stay aligned even when rounding runs past B: only the LAST rank may own a ragged tail
+        i = min(B // align * align, max(cuts[-1], (i + align // 2) // align * align))
         cuts.append(i)
     cuts.append(B)
     return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
 
 
 def place_words(local_bits_words, begin, total_instances):
-    """a rank's packed result words placed into a zeroed full-length word vector (begin must be a multiple of 32)"""
-    assert begin % 32 == 0
+    """a rank's packed result words placed into a zeroed full-length word vector (begin must be a multiple of 32 unless the
+    rank's range is empty)"""
     full = np.zeros((total_instances + 31) // 32, dtype=np.int64)
+    if len(local_bits_words) == 0:
+        return full
+    assert begin % 32 == 0
     w0 = begin // 32
     full[w0:w0 + len(local_bits_words)] = np.asarray(local_bits_words, dtype=np.uint32).astype(np.int64)
     return full

@@ -8,6 +8,7 @@
 //   sim_tc gen <count> <leaves> <retis> <seed> <kind> <perm>   -> one char per instance (1 / 0 / E) on stdout,
 //                                                               a JSON line of statistics on stderr
 //   sim_tc file <path> <perm>                                  (path: pairs of Newick lines)
+//   environment SIM_LAYOUT = 4 | 2 | 1 : element type of the arrays the solver loads and emits (int32, int16, uint8 with degrees)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -60,44 +61,75 @@ struct Item { std::vector<int32_t> succ_off, succ_adj, hlabel, tparent, tlabel; 
 
 struct Stats { long items = 0, branched = 0, cherries = 0, ret = 0, arcs = 0, passes = 0, max_items = 0, rules_only = 0; };
 
-static int solve_instance(const Item& root, int capN, int capM, int capNT, int capL, int perm, Stats& S, int* status) {
+static int g_layout = 4;  // element size of the arrays the solver reads: 4 (int32), 2 (int16), 1 (uint8: out-degrees instead of offsets)
+
+// an instance in the layout of element type S (what the kernel's load<S> reads and emit_child<S> writes)
+template <class S>
+struct ItemS {
+  std::vector<S> succ_off, succ_adj, hlabel, tparent, tlabel; int n, m, nt;
+  explicit ItemS(int cn, int cm, int cnt) : succ_off(cn + 1), succ_adj(cm + 1), hlabel(cn + 1), tparent(cnt + 1), tlabel(cnt + 1), n(0), m(0), nt(0) {}
+  explicit ItemS(const Item& it) : n(it.n), m(it.m), nt(it.nt) {
+    typedef TcLayout<S> Lay;
+    if (Lay::kDegrees) { for (int v = 0; v < n; ++v) succ_off.push_back((S)(it.succ_off[v + 1] - it.succ_off[v])); }
+    else for (int v = 0; v <= n; ++v) succ_off.push_back((S)it.succ_off[v]);
+    for (int e = 0; e < m; ++e) succ_adj.push_back((S)it.succ_adj[e]);
+    for (int v = 0; v < n; ++v) hlabel.push_back(Lay::enc(it.hlabel[v]));
+    for (int t = 0; t < nt; ++t) { tparent.push_back(Lay::enc(it.tparent[t])); tlabel.push_back(Lay::enc(it.tlabel[t])); }
+  }
+};
+
+// the kernel's work loop (tc_persistent_kernel): children 1 .. d-1 of a branching go to the pool (here: a stack) as compact
+// instances of element type S, child 0 continues IN PLACE on the same workspace
+template <class S>
+static int solve_instance_t(const Item& root, int capN, int capM, int capNT, int capL, int perm, Stats& St, int* status) {
   using I = int16_t;
   std::vector<char> mem(TcWork<I>::bytes(capN, capM, capNT, capL) + 64);
-  std::vector<Item> stack{root};
+  std::vector<ItemS<S>> stack; stack.emplace_back(root);
   bool first = true; long items = 0; int verdict = 0; *status = 0;
-  while (!stack.empty()) {
-    Item it = std::move(stack.back()); stack.pop_back();
+  while (!stack.empty() && verdict == 0) {
+    ItemS<S> it = std::move(stack.back()); stack.pop_back();
     ++items;
     HostEx ex{perm};
     TcWork<I> w; w.carve(mem.data(), capN, capM, capNT, capL);
     TcSolver<HostEx, I> sv(ex, w);
     TcInst in{it.n, it.m, it.nt, it.succ_off.data(), it.succ_adj.data(), it.hlabel.data(), it.tparent.data(), it.tlabel.data()};
     int st = 0, x = -1;
-    const int code = sv.template solve<int32_t>(in, !first, &st, &x);
+    int code = sv.template begin<S>(in, !first, &st);
     first = false;
-    S.cherries += sv.st.cherries; S.ret += sv.st.retcherries; S.arcs += sv.st.arcs_deleted; S.passes += sv.st.passes;
-    if (code == TC_ERROR) { *status = st; verdict = -1; break; }
-    if (code == TC_DISPLAYED) { verdict = 1; break; }
-    if (code == TC_BRANCH) {
+    while (code == TC_CONTINUE) {
+      code = sv.rule_loop(&st, &x);
+      if (code != TC_BRANCH) break;
       const int d = sv.indeg(x);
       std::vector<int> arcs; for (int k = 0; k < d; ++k) arcs.push_back(sv.in_arc(x, k));
-      for (int k = 0; k < d; ++k) {
-        Item ch; ch.succ_off.resize(sv.n + 1); ch.succ_adj.resize(sv.m + 1); ch.hlabel.resize(sv.n + 1); ch.tparent.resize(sv.nt + 1); ch.tlabel.resize(sv.nt + 1);
+      for (int k = 1; k < d; ++k) {
+        ItemS<S> ch(sv.n, sv.m, sv.nt);
         int32_t dims[4];
-        TcEmit out{ch.succ_off.data(), ch.succ_adj.data(), ch.hlabel.data(), ch.tparent.data(), ch.tlabel.data(), dims};
+        TcEmitT<S> out{ch.succ_off.data(), ch.succ_adj.data(), ch.hlabel.data(), ch.tparent.data(), ch.tlabel.data(), dims};
         sv.emit_child(x, arcs[k], out);
         ch.n = dims[0]; ch.m = dims[1]; ch.nt = dims[2];
         stack.push_back(std::move(ch));
       }
+      sv.keep_only(x, arcs[0]);
+      ++items;
+      code = TC_CONTINUE;
     }
+    St.cherries += sv.st.cherries; St.ret += sv.st.retcherries; St.arcs += sv.st.arcs_deleted; St.passes += sv.st.passes;
+    if (code == TC_ERROR) { *status = st; verdict = -1; break; }
+    if (code == TC_DISPLAYED) { verdict = 1; break; }
   }
-  S.items += items; if (items > 1) S.branched++; else S.rules_only++;
-  if (items > S.max_items) S.max_items = items;
+  St.items += items; if (items > 1) St.branched++; else St.rules_only++;
+  if (items > St.max_items) St.max_items = items;
   return verdict;
+}
+static int solve_instance(const Item& root, int capN, int capM, int capNT, int capL, int perm, Stats& S, int* status) {
+  if (g_layout == 1) return solve_instance_t<uint8_t>(root, capN, capM, capNT, capL, perm, S, status);
+  if (g_layout == 2) return solve_instance_t<int16_t>(root, capN, capM, capNT, capL, perm, S, status);
+  return solve_instance_t<int32_t>(root, capN, capM, capNT, capL, perm, S, status);
 }
 
 int main(int argc, char** argv) {
   if (argc < 2) return 1;
+  if (const char* e = getenv("SIM_LAYOUT")) g_layout = atoi(e);  // 4 / 2 / 1: element size of the arrays the solver reads
   PT::BatchPacker P; int perm = 0;
   if (!strcmp(argv[1], "gen") && argc >= 8) {
     const long count = atol(argv[2]); const int l = atoi(argv[3]), r = atoi(argv[4]); const uint64_t seed = strtoull(argv[5], 0, 0); const int kind = atoi(argv[6]); perm = atoi(argv[7]);

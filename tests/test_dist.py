@@ -47,6 +47,22 @@ def test_shard_ranges_are_aligned_and_cover():
                 assert max(loads) < 1.3 * (sum(loads) / world) + 32 * 500
 
 
+def test_only_the_last_rank_owns_a_ragged_tail():
+    """B not a multiple of 32 and more ranks than 32-instance words: every non-empty range starts on a word boundary, so the
+    all-reduce SUM of the placed words is an OR (no two ranks share a word)"""
+    from phylo_tools_b200.shard import place_words
+    for B, world in ((49, 8), (33, 4), (95, 8), (31, 2)):
+        r = shard_ranges(np.ones(B), world)
+        assert r[0][0] == 0 and r[-1][1] == B
+        owners = np.zeros((B + 31) // 32, dtype=int)
+        for b, e in r:
+            if e > b:
+                assert b % 32 == 0, (B, world, r)
+                owners[b // 32:(e + 31) // 32] += 1
+            place_words(np.zeros((e - b + 31) // 32, dtype=np.uint32), b, B)   # empty ranges are accepted at any begin
+        assert (owners == 1).all(), (B, world, r)
+
+
 def test_two_rank_allreduce_merge(tmp_path):
     B = 1000
     weights = np.random.default_rng(1).integers(100, 600, B)

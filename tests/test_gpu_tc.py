@@ -107,7 +107,105 @@ def test_error_statuses_do_not_poison_the_batch(pt, path):
     assert c["errors"] == 2
 
 
-@pytest.mark.parametrize("path", [0, 3])
+def _layouts(p):
+    """every input layout the batch fits: int32, int16, and uint8 (out-degrees) when every id fits a byte"""
+    a = p.arrays()
+    out = [0, 2]
+    if max(a["max_host_nodes"], a["max_guest_nodes"], a["max_labels"]) <= 255:
+        out.append(1)
+    return out
+
+
+def test_reference_verdicts_at_headline_size(pt):
+    """the REFERENCE's own verdicts (oracle/_ref/ref_tc = unmodified utils/containment.hpp:1202) at BASELINE config 2's size
+    (l=100, r=20: 300 instances x displayed / two labels swapped / random guest) and at l=300, r=60, generated by
+    oracle/make_golden_r02.py.  The reference never says "not displayed" wrongly: every '0' must be matched; a '1'
+    must be matched or be one of the disagreements that exhaustive switching settled at generation time ("settled")."""
+    from conftest import load_golden
+    gold = load_golden("tc_ref_l100.json")
+    checked = 0
+    for cfg in gold["configs"]:
+        p = pt.Packer()
+        p.add_generated(cfg["count"], cfg["leaves"], cfg["reticulations"], cfg["seed"], cfg["kind"])
+        ref, settled = cfg["reference"], {int(k): v for k, v in cfg["settled"].items()}
+        for compact in _layouts(p):
+            b = pt.Batch(p.arrays(compact=compact))
+            for path in (0, 2):
+                v, s, _ = b.contain(path=path)
+                assert (s == 0).all(), (cfg["leaves"], cfg["kind"], compact, path)
+                bad = []
+                for i, r in enumerate(ref):
+                    if r not in "01":
+                        continue            # the reference crashed or threw here
+                    want = settled.get(i, int(r))
+                    if int(v[i]) != want:
+                        bad.append((i, r, int(v[i])))
+                    checked += 1
+                assert not bad, (cfg["leaves"], cfg["reticulations"], cfg["kind"], compact, path, bad[:10])
+            b.free()
+        if cfg["kind"] == 0:
+            assert ref.count("0") == 0
+    assert checked > 5000
+
+
+def test_exhaustive_truth_uniform_sample_at_headline_size(pt):
+    """exhaustive-switching truth (all 2^20 switchings, oracle/pt_oracle.c) of a seeded UNIFORM sample of label-swapped and random
+    guests at l=100, r=20 -- no solver chose the sample (oracle/make_golden_r02.py)"""
+    from conftest import load_golden
+    gold = load_golden("tc_exh_l100.json")
+    for cfg in gold["configs"]:
+        p = pt.Packer()
+        p.add_generated(cfg["count"], cfg["leaves"], cfg["reticulations"], cfg["seed"], cfg["kind"])
+        truth = np.array([int(c) for c in cfg["truth"]])
+        for compact in _layouts(p):
+            b = pt.Batch(p.arrays(compact=compact))
+            for path in (0, 2, 3):
+                v, s, _ = b.contain(path=path)
+                assert (s == 0).all()
+                assert (v.astype(int) == truth).all(), (cfg["kind"], compact, path, np.where(v.astype(int) != truth)[0][:10])
+            b.free()
+
+
+def test_byte_layout_equals_the_others(pt, oracle):
+    """index_bytes = 1 (uint8 ids, out-degrees instead of offsets): same verdicts, statuses and counters as int32 / int16, on
+    every executor; refused when an instance does not fit"""
+    p = pt.Packer()
+    for kind in (0, 1, 2):
+        p.add_generated(300, 14, 6, 4100 + kind, kind)
+    truth = np.array([oracle.tc_bruteforce_newick(*p.newick(i))[0] for i in range(len(p))])
+    ref = None
+    for compact in (0, 2, 1):
+        b = pt.Batch(p.arrays(compact=compact))
+        for path in (1, 2, 3):
+            v, s, c = b.contain(path=path)
+            assert (s == 0).all() and (v.astype(int) == truth).all(), (compact, path)
+            key = (c["displayed"], c["branched"], c["resolved_by_rules"])
+            ref = ref or key
+            assert key == ref, (compact, path, key, ref)
+        b.free()
+    big = pt.Packer()
+    big.add_generated(2, 150, 10, 1, 0)     # 319 host nodes: too many for a byte
+    with pytest.raises(pt.PtError):
+        big.arrays(compact=1)
+
+
+@pytest.mark.parametrize("path", [2, 3])
+def test_round_limit_is_reported(pt, path):
+    """pt_options.max_rounds on the global-memory executors: instances still branching when the limit ends the loop get
+    PT_INST_ROUND_LIMIT, never a silent "not displayed" """
+    p = pt.Packer()
+    p.add_generated(400, 16, 7, 777, 0)
+    b = pt.Batch(p.arrays())
+    v, s, c = b.contain(path=path)
+    assert (s == 0).all() and v.all() and c["branched"] > 4 and c["rounds"] >= 2
+    v1, s1, c1 = b.contain(path=path, max_rounds=1)
+    b.free()
+    assert ((s1 == 0) | (s1 == 5)).all() and (s1 == 5).sum() >= 1     # PT_INST_ROUND_LIMIT
+    assert v1[s1 == 0].all()                                            # whoever has status 0 has its true verdict
+    assert not v1[s1 == 5].any()
+
+
+@pytest.mark.parametrize("path", [0, 2, 3])
 def test_pool_overflow_is_reported(pt, oracle, path):
     p = pt.Packer()
     p.add_generated(400, 16, 7, 777, 0)

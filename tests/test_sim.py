@@ -181,3 +181,30 @@ def test_group_execution_with_real_barriers(sim_mt, gold_tc, threads, int32):
     assert r.returncode == 0, r.stderr[-500:]
     out = r.stdout.strip()
     assert [c for c in out] == [str(it["truth"]) for it in items]
+
+
+def test_simulated_kernel_logic_at_headline_size(sim):
+    """the reference's verdicts and the exhaustive truth at l=100, r=20 (tests/golden/tc_ref_l100.json, tc_exh_l100.json) against
+    the kernel logic, on the CPU: the first 40 instances of every config, read through the uint8 layout the bench uploads"""
+    from conftest import load_golden
+    env = dict(os.environ, SIM_LAYOUT="1")
+    for cfg in load_golden("tc_ref_l100.json")["configs"]:
+        if cfg["leaves"] != 100:
+            continue
+        got = subprocess.run([sim, "gen", "40", "100", "20", str(cfg["seed"]), str(cfg["kind"]), "3"], capture_output=True, text=True, check=True, env=env).stdout.strip()
+        settled = cfg["settled"]
+        bad = [(i, r, got[i]) for i, r in enumerate(cfg["reference"][:40]) if r in "01" and got[i] != str(settled.get(str(i), r))]
+        assert not bad, (cfg["kind"], bad)
+    for cfg in load_golden("tc_exh_l100.json")["configs"]:
+        got = subprocess.run([sim, "gen", "40", "100", "20", str(cfg["seed"]), str(cfg["kind"]), "0"], capture_output=True, text=True, check=True, env=env).stdout.strip()
+        assert got == cfg["truth"][:40], cfg["kind"]
+
+
+@pytest.mark.parametrize("layout", ["2", "1"])
+def test_simulated_layouts_agree(sim, layout):
+    """int16 and uint8 (out-degree) input layouts, children emitted in the same layout: same verdicts as int32"""
+    for kind in (0, 1, 2):
+        ref = subprocess.run([sim, "gen", "80", "12", "6", str(900 + kind), str(kind), "0"], capture_output=True, text=True, check=True).stdout.strip()
+        got = subprocess.run([sim, "gen", "80", "12", "6", str(900 + kind), str(kind), "5"], capture_output=True, text=True, check=True,
+                             env=dict(os.environ, SIM_LAYOUT=layout)).stdout.strip()
+        assert got == ref and "E" not in got
