@@ -1,21 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- the headline benchmark of BASELINE.json on B200.
 
-metric   : tree-containment instances/s  (BASELINE.json "metric"; config = configs[1]: a batch of 10^5 `gen` networks
+metric   : tree-containment instances/s  (BASELINE.json "metric"; config = configs[1]: ONE batch of 10^5 `gen` networks
            l=100, r=20, each with a displayed tree)
-step     : one pass of the hot path (pt_batch_contain) over one batch of 10^5 synthetic instances per GPU
+step     : one pass of the hot path over the whole batch.  With N GPUs the batch is cut into N contiguous ranges (STRONG scaling:
+           12 500 instances per GPU at N = 8, as SURVEY 8(e) and the north star name it); every rank solves its range with one
+           persistent kernel launch and the library's own collective (pt_batch_contain_sharded: one NCCL all-reduce of the packed
+           result words) leaves the whole verdict vector on every rank.
 value    : whole-job instances/s with the batch RESIDENT in HBM when the timed region starts (CUDA events, max over ranks)
-e2e      : the same through the public C-ABI call with HOST (pinned) buffers: pt_batch_create (H2D) + pt_batch_contain
-           (kernels + D2H of the result bits) + pt_batch_free, every step
-roofline : dominant kernel = tc_reduce_kernel over the original instances (round 0), timed live with CUDA events inside
-           the library; algorithmic bytes = 8124 B/instance; peak = MEASURED_PEAKS.json hbm_gbs
+e2e      : the same through the public C-ABI with HOST (pinned) buffers: pt_batch_create (H2D, uint8 layout) +
+           pt_batch_contain_sharded (kernel + collective) + D2H of the result words + pt_batch_free, every step
+roofline : dominant kernel = tc_persistent_kernel (the one launch of a step), timed live with CUDA events inside the library;
+           algorithmic bytes = 8124 B/instance; peak = MEASURED_PEAKS.json hbm_gbs
 cpu_baseline / --impl reference : the reference's own TreeInNetContainment::displayed() (oracle/_ref/ref_tc, unmodified
            reference headers, std::cout silenced) on the box's host cores, one process per core over disjoint slices
-lca      : secondary leg (BASELINE config 3): 10^8 LCA queries on a 10^7-leaf tree, outside the timed region
-
-N > 1: one process per GPU (torchrun), instances sharded with no data-path collective; the only collective is the
-all-reduce of the packed result words and counters (phylo_tools_b200/shard.py), inside the timed region. Weak scaling:
-10^5 instances per GPU.
+extras   : weak scaling (10^5 instances per GPU), the LCA legs (BASELINE config 3: uniform pairs, and the consecutive
+           preorder-sorted candidates the path really issues), config 4 (64 large instances, 8 per rank at N = 8), config 5
+           (switching enumeration with the cross-GPU found flag), text / isomorphism / who_displays / bridges legs at N = 1
 """
 import argparse
 import ctypes
@@ -140,34 +141,38 @@ def _ref_json(stderr_text):
     return {}
 
 
+def _gen_pair_files(count_per_file, nfiles, seed):
+    """`nfiles` files of `count_per_file` (network, tree) pairs each, made by the stand-alone generator phylo_tools_b200/bin/gen
+    (host code only; it does not load libptgpu.so) -- the same instances pt_packer_add_generated(count, L, R, seed, 0) makes"""
+    gen = os.path.join(ROOT, "phylo_tools_b200", "bin", "gen")
+    files = []
+    for k in range(nfiles):
+        f = tempfile.NamedTemporaryFile("w", suffix=".nw", delete=False)
+        f.close()
+        subprocess.check_call([gen, "--pairs", str(count_per_file), "-l", str(L), "-r", str(R), "--seed", str(seed + k * count_per_file), f.name],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        files.append(f.name)
+    return files
+
+
 def reference_arm(args, rank, world):
-    """the reference's CPU implementation of the path on the host cores (rank 0 only)"""
+    """the reference's CPU implementation of the path on the host cores (rank 0 only); the product library is not imported"""
     if rank != 0:
         return
-    import phylo_tools_b200 as pt
     from oracle import pt_oracle as O
     ref = O.ref_binary("ref_tc")
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     per = args.ref_instances_per_core
     res = {"metric": "tree-containment instances/s", "unit": "instances/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
            "config": {"workload": "batch of 10^5 gen networks l=100 r=20 with a displayed tree each (BASELINE configs[1]); bounded sample per step",
                       "leaves": L, "reticulations": R}}
     if ref is None:
         res["unavailable"] = "oracle/_ref/ref_tc was not built (needs /root/reference at build time)"
         print(json.dumps(res))
         return
-    p = pt.Packer()
-    p.add_generated(procs * per, L, R, SEED, 0)
-    files = []
-    for k in range(procs):
-        f = tempfile.NamedTemporaryFile("w", suffix=".nw", delete=False)
-        for i in range(k * per, (k + 1) * per):
-            h, g = p.newick(i)
-            f.write(h + "\n" + g + "\n")
-        f.close()
-        files.append(f.name)
+    files = _gen_pair_files(per, procs, SEED)
 
     def one_step():
         t0 = time.perf_counter()
@@ -189,13 +194,14 @@ def reference_arm(args, rank, world):
     val = done / (ms / 1000.0)  # instances on which the reference terminated with a verdict
     res.update({"value": val, "ms_per_step": ms, "gpu_launches": 0,
                 "cpu_baseline": {"value": val, "unit": "instances/s", "cores": procs, "kind": "reference",
-                                 "sample": "%d instances per step (%d per core); reference gave a verdict on %d (%d displayed), crashed/threw on %d" % (total, per, done, disp, total - done)},
+                                 "sample": "%d instances per step (the first %d of the batch, %d per core); reference gave a verdict on %d (%d displayed), crashed/threw on %d" % (total, total, per, done, disp, total - done)},
                 "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(res))
 
 
-def cpu_baseline_leg(pt, sample_seconds=15.0):
-    """bounded sample of the same workload through the reference on all host cores (reported, not the target)"""
+def cpu_baseline_leg(sample_seconds=15.0):
+    """bounded sample of the same workload through the reference on all host cores (reported, not the target), plus the one-core
+    rate of the same driver"""
     from oracle import pt_oracle as O
     ref = O.ref_binary("ref_tc")
     if ref is None:
@@ -203,35 +209,47 @@ def cpu_baseline_leg(pt, sample_seconds=15.0):
     cores = max(1, min(os.cpu_count() or 1, 64))
     per = max(8, int(sample_seconds * 45))  # ~50 instances/s/core survey-time
     per = min(per, 400)
-    p = pt.Packer()
-    p.add_generated(cores * per, L, R, SEED, 0)
-    files = []
-    for k in range(cores):
-        f = tempfile.NamedTemporaryFile("w", suffix=".nw", delete=False)
-        for i in range(k * per, (k + 1) * per):
-            h, g = p.newick(i)
-            f.write(h + "\n" + g + "\n")
-        f.close()
-        files.append(f.name)
+    files = _gen_pair_files(per, cores, SEED)
     t0 = time.perf_counter()
     ps = [subprocess.Popen([ref, "bench", fn, str(per)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True) for fn in files]
     outs = [q.communicate()[1] for q in ps]
     dt = time.perf_counter() - t0
-    for fn in files:
-        os.unlink(fn)
     js = [_ref_json(o) for o in outs]
     disp = sum(j.get("displayed", 0) for j in js)
     done = sum(j.get("displayed", 0) + j.get("not_displayed", 0) for j in js)
     crashed = cores * per - done
-    single = [j.get("inst_per_s", 0.0) for j in js]
+    # one core alone (no neighbours competing for the memory system): the first 100 instances
+    one = _ref_json(subprocess.run([ref, "bench", files[0], "100"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True).stderr)
+    for fn in files:
+        os.unlink(fn)
     return {"value": done / dt, "reference_crashes_or_exceptions": crashed, "unit": "instances/s", "cores": cores, "kind": "reference",
-            "sample": "first %d instances of the batch, %d per core, reference TreeInNetContainment::displayed() with std::cout silenced; %d/%d displayed; per-core rate %.1f inst/s"
-                      % (cores * per, per, disp, cores * per, sum(single) / len(single))}
+            "one_core_instances_per_s": one.get("inst_per_s"),
+            "sample": "first %d instances of the batch, %d per core, reference TreeInNetContainment::displayed() with std::cout silenced; %d/%d displayed"
+                      % (cores * per, per, disp, cores * per)}
+
+
+def lca_cpu_baseline(leaves=1_000_000, queries=2_000_000):
+    """the reference's own lca (rmq/lca.hpp: Euler tour + pm_rmq) through oracle/_ref/ref_lca on one host core; the reference's
+    recursive tree<T> does not reach 10^7 leaves comfortably, so the sample is a 10^6-leaf tree"""
+    from oracle import pt_oracle as O
+    ref = O.ref_binary("ref_lca")
+    if ref is None:
+        return {"value": None, "kind": "reference", "sample": "oracle/_ref/ref_lca not built"}
+    try:
+        out = subprocess.run([ref, "bench_lca", str(leaves), str(queries), str(SEED)], capture_output=True, text=True, timeout=300).stdout.strip()
+        j = json.loads(out)
+        return {"value": j["queries"] / j["query_s"], "unit": "queries/s", "cores": 1, "kind": "reference", "build_s": j["build_s"],
+                "sample": "%d uniform queries on a %d-leaf random binary tree, reference lca<>::query (rmq/lca.hpp:91-106)" % (queries, leaves)}
+    except Exception as ex:
+        return {"value": None, "kind": "reference", "sample": "ref_lca failed: %r" % (ex,)}
 
 
 def lca_leg(pt, torch, leaves, queries, peak, rank=0, world=1, dist=None):
     """BASELINE configs[2]; with N ranks the table is replicated (built on every GPU) and every rank answers its own `queries`
-    (weak scaling, no data-path collective): aggregate = N * queries / max over ranks of the batch time"""
+    (weak scaling, no data-path collective): aggregate = N * queries / max over ranks of the batch time.  Two workloads:
+    uniform pairs (the config as SURVEY 8(d) defines it) and the one the containment path really issues -- consecutive
+    candidates of a preorder-sorted list (utils/induced_tree.hpp:128-138) on a tree numbered in preorder like the reference's"""
+    import numpy as np
     par = pt.random_tree(leaves, SEED)
     n = len(par)
     dpar = torch.from_numpy(par).cuda()
@@ -242,41 +260,90 @@ def lca_leg(pt, torch, leaves, queries, peak, rank=0, world=1, dist=None):
     v = torch.randint(0, n, (queries,), generator=g, device="cuda", dtype=torch.int32)
     out = torch.empty_like(u)
     stream = torch.cuda.current_stream().cuda_stream
-    for _ in range(3):
-        lca.query(u, v, out=out, stream=stream)
-    torch.cuda.synchronize()
-    reps, best, tot = 5, 1e30, 0.0
-    for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        lca.query(u, v, out=out, stream=stream)
-        e1.record()
+
+    def timed(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        best, tot = min(best, ms), tot + ms
-    avg = tot / reps
+        best, tot = 1e30, 0.0
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best, tot = min(best, ms), tot + ms
+        avg = tot / reps
+        if world > 1:
+            t = torch.tensor([avg, best], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            avg, best = float(t[0].item()), float(t[1].item())
+        return avg, best
+    avg, best = timed(lambda: lca.query(u, v, out=out, stream=stream))
     checksum = int(out.long().sum().item())
-    lca.free()
-    if world > 1:
-        t = torch.tensor([avg, best], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        avg, best = float(t[0].item()), float(t[1].item())
     qps = world * queries / (avg / 1000.0)
     ach = LCA_BYTES_PER_QUERY * qps / 1e9
-    return {"workload": "batched LCA: %d queries per GPU on a %d-leaf random binary tree (BASELINE configs[2])" % (queries, leaves),
-            "n_gpus": world, "scaling": "weak (table replicated, queries sharded, no collective)", "queries_per_s": qps, "ms_per_batch": avg, "best_ms": best, "build_ms": info["build_ms"], "levels": info["num_levels"],
-            "resident_bytes": info["device_bytes"], "checksum": checksum,
-            "roofline": {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak, "traffic": measured_traffic("lca_query_kernel", queries),
-                         "model": "40 B/query (SURVEY 8(d)); this layout needs 2 random records per query and B200 moves a 128-byte line per random read (profiles/micro_gather.cu): 254 B/query measured, ceiling ~25 G queries/s"}}
+    res = {"workload": "batched LCA: %d uniform queries per GPU on a %d-leaf random binary tree (BASELINE configs[2])" % (queries, leaves),
+           "n_gpus": world, "scaling": "weak (table replicated, queries sharded, no collective)", "queries_per_s": qps, "ms_per_batch": avg, "best_ms": best, "build_ms": info["build_ms"], "levels": info["num_levels"],
+           "resident_bytes": info["device_bytes"], "checksum": checksum,
+           "roofline": {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak, "traffic": measured_traffic("lca_query_kernel", queries),
+                        "model": "40 B/query (SURVEY 8(d)); uniform pairs need 2 random records per query and B200 moves a 128-byte line per random read (profiles/micro_gather.cu): 254 B/query measured, "
+                                 "i.e. the kernel moves 5.3 TB/s of DRAM lines = 0.81 of the measured peak; bound for uniform pairs with this layout = peak / 254 B = 25.7 G queries/s"}}
+    if rank == 0:
+        # end to end: queries in pinned host memory in, answers in pinned host memory out (H2D 8 B + D2H 4 B per query inside the call)
+        q2 = min(queries, 20_000_000)
+        hu, hv = u[:q2].cpu().pin_memory(), v[:q2].cpu().pin_memory()
+        ho = torch.empty(q2, dtype=torch.int32).pin_memory()
+        lib = pt.lib()
+        for _ in range(2):
+            lib.pt_lca_query(lca._h, hu.data_ptr(), hv.data_ptr(), ho.data_ptr(), q2, pt.PT_MEM_HOST, stream)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            lib.pt_lca_query(lca._h, hu.data_ptr(), hv.data_ptr(), ho.data_ptr(), q2, pt.PT_MEM_HOST, stream)
+        dt = (time.perf_counter() - t0) / 3
+        res["e2e"] = {"value": q2 / dt, "unit": "queries/s", "h2d_bytes_per_step": 8 * q2, "d2h_bytes_per_step": 4 * q2, "queries": q2,
+                      "answers_ok": bool((ho[:1000].numpy() == out[:1000].cpu().numpy()).all()), "api": "pt_lca_query(HOST pinned u, v -> HOST pinned out)"}
+    lca.free()
+    # ---- the consumer's workload: tree numbered in preorder, candidates sorted by preorder, consecutive pairs ----
+    l0 = pt.Lca(dpar)
+    pre = torch.empty(n, dtype=torch.int32, device="cuda")
+    pt._check(pt.lib().pt_lca_node_info(l0._h, None, pre.data_ptr(), pt.PT_MEM_DEVICE, None), "pt_lca_node_info")
+    l0.free()
+    newpar = torch.empty_like(dpar)
+    newpar[pre.long()] = torch.where(dpar >= 0, pre[dpar.clamp(min=0).long()], torch.full_like(dpar, -1))
+    del dpar
+    lca = pt.Lca(newpar)
+    pos = torch.empty(n, dtype=torch.int32, device="cuda")
+    pt._check(pt.lib().pt_lca_node_info(lca._h, None, pos.data_ptr(), pt.PT_MEM_DEVICE, None), "pt_lca_node_info")
+    res["adjacent"] = {"workload": "consecutive pairs of a preorder-sorted candidate list (utils/induced_tree.hpp:128-138), tree ids = a preorder like the reference's readers assign; "
+                                   "pt_lca_query_adjacent: every record read once"}
+    for dens in (1.0, 0.25):
+        keep = torch.rand(n, generator=g, device="cuda") < dens
+        cand = torch.nonzero(keep).squeeze(1).to(torch.int32)
+        cand = cand[torch.argsort(pos[cand.long()])].contiguous()
+        o2 = torch.empty(cand.numel() - 1, dtype=torch.int32, device="cuda")
+        a2, b2 = timed(lambda: lca.query_adjacent(cand, out=o2, stream=stream))
+        qn = cand.numel() - 1
+        qps2 = world * qn / (a2 / 1000.0)
+        ok = bool((o2[:2000].cpu().numpy() == lca.query(cand[:2000].cpu().numpy(), cand[1:2001].cpu().numpy())).all())
+        res["adjacent"]["density_%g" % dens] = {"queries": qn, "ms": a2, "queries_per_s": qps2, "answers_ok": ok,
+                                                "roofline": {"bound": "hbm", "achieved": LCA_BYTES_PER_QUERY * qps2 / 1e9 / world, "peak": peak, "unit": "GB/s",
+                                                             "frac": LCA_BYTES_PER_QUERY * qps2 / 1e9 / world / peak, "model": "40 B/query: 4 B id in, one 32-byte record, 4 B out"}}
+    lca.free()
+    if rank == 0 and world == 1:
+        res["cpu_baseline"] = lca_cpu_baseline()
+    return res
 
 
-def config4_leg(pt, torch, count):
-    """BASELINE configs[3]: large networks n = 10^6, r = 10^3 (global-memory executor, one CTA per instance)"""
+def config4_leg(pt, torch, count, rank=0, world=1, dist=None):
+    """BASELINE configs[3]: large networks n = 10^6, r = 10^3, 64 instances sharded over 8 GPUs = 8 per rank; every rank solves
+    its own 8 (global-memory executor, one thread-block cluster per instance); aggregate = world * count / max over ranks"""
     import numpy as np
     leaves, retis = 499_001, 1000
     t0 = time.perf_counter()
     p = pt.Packer()
-    p.add_generated(count, leaves, retis, SEED + 4, 0)
+    p.add_generated(count, leaves, retis, SEED + 4 + 1000 * rank, 0)
     a = p.arrays()
     gen_s = time.perf_counter() - t0
     dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in a.items()}
@@ -285,6 +352,8 @@ def config4_leg(pt, torch, count):
     b = pt.Batch(dev)
     b.contain(result_bits=bits, status=stat, want_counters=False)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     _, _, c = b.contain(result_bits=bits, status=stat, want_counters=True)
@@ -292,14 +361,22 @@ def config4_leg(pt, torch, count):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     b.free()
+    disp, errs = c["displayed"], c["errors"]
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        t = torch.tensor([disp, errs], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        disp, errs = int(t[0].item()), int(t[1].item())
     nbytes = sum(int(dev[k].numel()) * dev[k].element_size() for k in ("host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"))
-    return {"workload": "%d gen networks n=%d r=%d with a displayed tree each (BASELINE configs[3], one GPU's share)" % (count, 2 * retis + 2 * leaves - 1, retis),
-            "instances_per_s": count / (ms / 1000.0), "ms": ms, "displayed": c["displayed"], "errors": c["errors"], "work_items": c["work_items"],
-            "rule_passes": c["rule_passes"], "input_bytes": nbytes, "host_generation_s": gen_s,
+    return {"workload": "%d gen networks n=%d r=%d with a displayed tree each, %d per GPU on %d GPU(s) (BASELINE configs[3]: 64 over 8)" % (count * world, 2 * retis + 2 * leaves - 1, retis, count, world),
+            "n_gpus": world, "instances_per_s": world * count / (ms / 1000.0), "ms": ms, "displayed": disp, "errors": errs, "work_items": c["work_items"],
+            "rule_passes": c["rule_passes"], "input_bytes_per_gpu": nbytes, "host_generation_s": gen_s,
             "note": "one thread-block cluster per instance, workspace in global memory; the reference cannot run this size (extrapolated 3e5 s per instance, BASELINE.md)"}
 
 
-def config5_leg(pt, retis=24, leaves=30, rank=0, world=1, dist=None, torch=None):
+def config5_leg(pt, retis=24, leaves=30, rank=0, world=1, dist=None, torch=None, comm=None):
     """BASELINE configs[4]: exhaustive 2^r switching enumeration of one general network (guest = random tree: not displayed,
     so the whole index space is visited)"""
     p = pt.Packer()
@@ -487,15 +564,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--instances", type=int, default=100_000, help="instances per GPU")
+    ap.add_argument("--instances", type=int, default=100_000, help="instances of the WHOLE batch (sharded over the GPUs)")
     ap.add_argument("--lca-leaves", type=int, default=10_000_000)
     ap.add_argument("--lca-queries", type=int, default=100_000_000)
-    ap.add_argument("--int32-input", action="store_true", help="use the int32 batch layout instead of the compact one")
     ap.add_argument("--layout", type=int, default=1, choices=[1, 2, 4], help="element size of the batch arrays (pt_batch_desc.index_bytes): 1 = uint8 with out-degrees (default), 2 = int16, 4 = int32")
     ap.add_argument("--no-lca", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
-    ap.add_argument("--config4-instances", type=int, default=8)
+    ap.add_argument("--config4-instances", type=int, default=8, help="per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-instances-per-core", type=int, default=100)
     args = ap.parse_args()
@@ -512,7 +589,6 @@ def main():
     import torch.distributed as dist
 
     import phylo_tools_b200 as pt
-    from phylo_tools_b200.shard import place_words
 
     if pt.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
@@ -521,79 +597,106 @@ def main():
     pt.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL_DEBUG asks for goes to stderr: rank 0 prints ONE JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    peak, peak_src = measured_peak()
-    B = args.instances
-    total_B = B * world
-    # ---- synthetic batch of this rank: instances [rank*B, (rank+1)*B) of the global batch (seed = SEED + global index) ----
-    t_gen = time.perf_counter()
-    packer = pt.Packer()
-    packer.add_generated(B, L, R, SEED + rank * B, 0)
-    layout = 4 if args.int32_input else args.layout
-    host = packer.arrays(compact=layout if layout != 4 else 0)  # uint8 data arrays (pt_batch_desc.index_bytes = 1): a quarter of the int32 upload
-    t_gen = time.perf_counter() - t_gen
-    pinned = {k: (torch.from_numpy(v).pin_memory() if isinstance(v, np.ndarray) else v) for k, v in host.items()}
-    dev = {k: (v.cuda(non_blocking=True) if hasattr(v, "cuda") else v) for k, v in pinned.items()}
-    torch.cuda.synchronize()
-    words = (B + 31) // 32
-    d_bits = torch.zeros(words, dtype=torch.int32, device="cuda")
-    d_stat = torch.zeros(B, dtype=torch.uint8, device="cuda")
-    full_words = torch.zeros((total_B + 31) // 32, dtype=torch.int64, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-    resident = pt.Batch(dev, stream=stream)
-    in_bytes_actual = sum(int(dev[k].numel()) * dev[k].element_size() for k in ("host_node_off", "host_arc_off", "guest_node_off", "host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"))
 
-    def step_resident():
-        resident.contain(result_bits=d_bits, status=d_stat, want_counters=False, stream=stream)
-        if world > 1:  # the path's only collective: packed result words (disjoint per rank -> SUM == OR)
-            full_words.zero_()
-            w0 = rank * B // 32
-            full_words[w0:w0 + words] = d_bits.to(torch.int64) & 0xFFFFFFFF
-            dist.all_reduce(full_words, op=dist.ReduceOp.SUM)
+    def bootstrap(ident):  # the library's NCCL id travels by torch.distributed (the host program's own bootstrap)
+        box = [ident]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    comm = pt.Comm(world, rank, bootstrap if world > 1 else None)
+    peak, peak_src = measured_peak()
+    layout = args.layout
+    stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    launches = 0
-    k0_ms = []
-    with ClockSampler(local_rank) as clocks:
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def make_shard(total, seed):
+        """this rank's contiguous range of a batch of `total` generated instances (boundaries multiples of 32): instance i of
+        the batch is pt_packer_add_generated(..., seed + i, kind 0) whichever rank makes it"""
+        cuts = [min(total, (total * r // world + 31) // 32 * 32) for r in range(world)] + [total]
+        first, count = cuts[rank], cuts[rank + 1] - cuts[rank]
+        packer = pt.Packer()
+        packer.add_generated(count, L, R, seed + first, 0)
+        host = packer.arrays(compact=layout if layout != 4 else 0)
+        pinned = {k: (torch.from_numpy(v).pin_memory() if isinstance(v, np.ndarray) else v) for k, v in host.items()}
+        return first, count, pinned
+
+    def run_resident(total, first, count, pinned, steps, warmup, clocks_for=None):
+        dev = {k: (v.cuda(non_blocking=True) if hasattr(v, "cuda") else v) for k, v in pinned.items()}
+        torch.cuda.synchronize()
+        words = (total + 31) // 32
+        full_bits = torch.zeros(words, dtype=torch.int32, device="cuda")
+        full_stat = torch.zeros((total + 3) // 4 * 4, dtype=torch.uint8, device="cuda")
+        resident = pt.Batch(dev, stream=stream)
+
+        def step():
+            comm.contain_sharded(resident, first, total, full_bits, full_stat, stream=stream)
+        for _ in range(warmup):
+            step()
+        barrier()
+        k0 = []
+        launches = 0
+        ctx = ClockSampler(local_rank) if clocks_for is not None else None
+        if ctx:
+            ctx.__enter__()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            step_resident()
+        for _ in range(steps):
+            step()
             launches += resident.last_launches()
-            k0_ms.append(resident.round_ms(0))
+            k0.append(resident.round_ms(0))
         e1.record()
         barrier()
-        elapsed_ms = e0.elapsed_time(e1)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = total_B / (ms_per_step / 1000.0)
-    # verdict sanity (outside the timed region): every instance is a positive by construction
-    n_disp = int(np.unpackbits(d_bits.cpu().numpy().view(np.uint8), bitorder="little")[:B].sum())
-    n_err = int((d_stat != 0).sum().item())
-    _, _, counters = resident.contain(result_bits=d_bits, status=d_stat, want_counters=True, stream=stream)
-    k0 = sum(k0_ms) / len(k0_ms)
-    ach = ALG_BYTES_PER_INSTANCE * B / (k0 / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": "tc_persistent_kernel (the one launch of a step, %d instances)" % B, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": measured_traffic("tc_reduce_kernel", B), "kernel_ms": k0, "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
-                "algorithmic_bytes_per_instance": ALG_BYTES_PER_INSTANCE, "bytes_actually_read_per_instance": in_bytes_actual / B,
-                "note": "instance-resident shared-memory solver: bound by dependent shared-memory latency and barriers, not HBM (SURVEY 8(d)); see profiles/"}
-    resident.free()
+        if ctx:
+            ctx.__exit__(None, None, None)
+            clocks_for.update(ctx.summary())
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        counters = comm.contain_sharded(resident, first, total, full_bits, full_stat, want_counters=True, stream=stream)
+        n_disp = int(np.unpackbits(full_bits.cpu().numpy().view(np.uint8), bitorder="little")[:total].sum())
+        n_err = int((full_stat[:total] != 0).sum().item())
+        in_bytes = sum(int(dev[k].numel()) * dev[k].element_size() for k in ("host_node_off", "host_arc_off", "guest_node_off", "host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"))
+        resident.free()
+        return dict(ms=ms, k0=sum(k0) / len(k0), launches=launches, counters=counters, displayed=n_disp, errors=n_err, in_bytes=in_bytes)
 
-    # ---- end to end: HOST (pinned) buffers -> pt_batch_create (H2D) -> pt_batch_contain (HOST result bits, D2H) -> free ----
+    # ---- headline: ONE batch of `args.instances`, sharded over the ranks (strong scaling) ----
+    total_B = args.instances
+    t_gen = time.perf_counter()
+    first, B, pinned = make_shard(total_B, SEED)
+    t_gen = time.perf_counter() - t_gen
+    clocks = {}
+    r = run_resident(total_B, first, B, pinned, args.steps, args.warmup, clocks_for=clocks)
+    ms_per_step = r["ms"]
+    value = total_B / (ms_per_step / 1000.0)
+    k0 = r["k0"]
+    ach = ALG_BYTES_PER_INSTANCE * B / (k0 / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": "tc_persistent_kernel (the one launch of a step; %d instances on this GPU)" % B, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": measured_traffic("tc_persistent_kernel", B), "kernel_ms": k0, "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
+                "algorithmic_bytes_per_instance": ALG_BYTES_PER_INSTANCE, "bytes_actually_read_per_instance": r["in_bytes"] / max(B, 1),
+                "note": "instance-resident shared-memory solver: bound by instruction fetch and dependent shared-memory latency, not HBM (SURVEY 8(d)); see profiles/"}
+
+    # ---- end to end: HOST (pinned) buffers -> pt_batch_create (H2D) -> pt_batch_contain_sharded -> D2H of the result words -> free ----
+    words = (total_B + 31) // 32
+    full_bits = torch.zeros(words, dtype=torch.int32, device="cuda")
     h_bits = torch.zeros(max(words, 1), dtype=torch.int32).pin_memory()
-    h_stat = torch.zeros(max(B, 1), dtype=torch.uint8).pin_memory()
     pinned_np = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in pinned.items()}
     h2d = 0
 
@@ -601,13 +704,10 @@ def main():
         nonlocal h2d
         b = pt.Batch(pinned_np, stream=stream)
         h2d = b.h2d_bytes()
-        opt = pt.Options(0, 0)
-        rc = pt.lib().pt_batch_contain(b._h, ctypes.byref(opt), h_bits.data_ptr(), h_stat.data_ptr(), pt.PT_MEM_HOST, None, stream)
-        assert rc == 0, pt.lib().pt_last_error()
+        comm.contain_sharded(b, first, total_B, full_bits, None, stream=stream)
+        h_bits.copy_(full_bits, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
         b.free()
-        if world > 1:
-            fw = torch.from_numpy(place_words(h_bits.numpy().view(np.uint32)[:words], rank * B // 32 * 32, total_B)).cuda()
-            dist.all_reduce(fw, op=dist.ReduceOp.SUM)
 
     for _ in range(args.warmup):
         step_e2e()
@@ -620,28 +720,34 @@ def main():
     e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1000.0
-    e2e_ms = max(e0.elapsed_time(e1), wall_ms)  # host syncs inside the call: take the larger of device and wall time
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = total_B / (float(t.item()) / args.steps / 1000.0)
-    e2e_disp = int(np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[:B].sum())
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))  # host syncs inside the call: take the larger of device and wall time
+    e2e_val = total_B / (e2e_ms / args.steps / 1000.0)
+    e2e_disp = int(np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[:total_B].sum())
+    h2d_total = sum_over_ranks(h2d)
 
     out = {"metric": "tree-containment instances/s", "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-           "config": {"workload": "batch of 10^5 gen networks l=100 r=20 with a displayed tree each, per GPU (BASELINE configs[1])",
-                      "instances_per_gpu": B, "leaves": L, "reticulations": R, "host_nodes": 2 * R + 2 * L - 1, "generator_seed": SEED,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+           "config": {"workload": "ONE batch of %d gen networks l=100 r=20 with a displayed tree each (BASELINE configs[1]), sharded over %d GPU(s)" % (total_B, world),
+                      "instances": total_B, "instances_on_this_gpu": B, "leaves": L, "reticulations": R, "host_nodes": 2 * R + 2 * L - 1, "generator_seed": SEED,
                       "input_layout": {4: "int32 arrays", 2: "int16 arrays (pt_batch_desc.index_bytes = 2)", 1: "uint8 arrays, out-degrees instead of offsets (pt_batch_desc.index_bytes = 1)"}[layout],
-                      "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" % (in_bytes_actual / 1e6),
-                      "parallelism": "instances sharded %d-way, one all-reduce of result words" % world if world > 1 else "single GPU",
+                      "l2": "the solver's working set is shared memory; inputs are %.0f MB per step on this GPU (at N = 1 close to the 126 MB L2; they are read once per step, nothing else competes for them); no explicit flush" % (r["in_bytes"] / 1e6),
+                      "parallelism": "instances sharded %d-way (contiguous ranges), one NCCL all-reduce of the packed result words issued by the library (pt_batch_contain_sharded)" % world if world > 1 else "single GPU",
                       "cpu_affinity": ("%d cores next to the GPU" % numa) if numa else "default"},
-           "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": words * 4 + B,
-                   "api": "pt_batch_create(HOST pinned) + pt_batch_contain(HOST outputs) + pt_batch_free", "displayed": e2e_disp},
-           "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline,
-           "verdicts": {"displayed": n_disp, "errors": n_err, "expected_displayed": B}, "counters": counters,
+           "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": words * 4 * world,
+                   "api": "pt_batch_create(HOST pinned) + pt_batch_contain_sharded + D2H of the result words + pt_batch_free, on every rank", "displayed": e2e_disp},
+           "gpu_launches": r["launches"] * world, "clocks": clocks, "roofline": roofline,
+           "verdicts": {"displayed": r["displayed"], "errors": r["errors"], "expected_displayed": total_B}, "counters": r["counters"],
            "host_generation_s": t_gen}
+    del pinned, pinned_np
+    # ---- extra: weak scaling, 10^5 instances per GPU ----
+    if world > 1 and not args.no_weak:
+        wf, wB, wp = make_shard(args.instances * world, SEED + (1 << 30))
+        wr = run_resident(args.instances * world, wf, wB, wp, args.steps, args.warmup)
+        out["weak_scaling"] = {"instances": args.instances * world, "instances_per_gpu": wB, "value": args.instances * world / (wr["ms"] / 1000.0), "unit": "instances/s",
+                               "ms_per_step": wr["ms"], "displayed": wr["displayed"], "errors": wr["errors"]}
+        del wp
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline_leg(pt)
+        out["cpu_baseline"] = cpu_baseline_leg()
     if not args.no_lca:  # every rank: queries are sharded
         try:
             out["lca"] = lca_leg(pt, torch, args.lca_leaves, args.lca_queries, peak, rank, world, dist if world > 1 else None)
@@ -650,40 +756,27 @@ def main():
                 raise
             out["lca"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            out["newick_ingest"] = ingest_leg(pt)
-        except Exception as ex:
-            out["newick_ingest"] = {"error": repr(ex)}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            out["iso"] = iso_leg(pt, torch)
-        except Exception as ex:
-            out["iso"] = {"error": repr(ex)}
-        try:
-            out["newick_on_gpu"] = text_leg(pt, torch)
-        except Exception as ex:
-            out["newick_on_gpu"] = {"error": repr(ex)}
-        try:
-            out["config1"] = config1_leg(pt)
-        except Exception as ex:
-            out["config1"] = {"error": repr(ex)}
-        for key, leg in (("who_displays", who_leg), ("bridges", bridges_leg)):
+        for key, leg in (("newick_ingest", lambda: ingest_leg(pt)), ("iso", lambda: iso_leg(pt, torch)), ("newick_on_gpu", lambda: text_leg(pt, torch)),
+                         ("config1", lambda: config1_leg(pt)), ("who_displays", lambda: who_leg(pt, torch)), ("bridges", lambda: bridges_leg(pt, torch))):
             try:
-                out[key] = leg(pt, torch)
+                out[key] = leg()
             except Exception as ex:
                 out[key] = {"error": repr(ex)}
-    if rank == 0 and not args.no_config4:
+    if not args.no_config4:  # every rank: 8 instances each
         try:
-            out["config4"] = config4_leg(pt, torch, args.config4_instances)
+            out["config4"] = config4_leg(pt, torch, args.config4_instances, rank, world, dist if world > 1 else None)
         except Exception as ex:
+            if world > 1:
+                raise
             out["config4"] = {"error": repr(ex)}
     if not args.no_config5:  # every rank: the index range is sharded
         try:
-            out["config5"] = config5_leg(pt, rank=rank, world=world, dist=dist if world > 1 else None, torch=torch)
+            out["config5"] = config5_leg(pt, rank=rank, world=world, dist=dist if world > 1 else None, torch=torch, comm=comm)
         except Exception as ex:
             if world > 1:
                 raise
             out["config5"] = {"error": repr(ex)}
+    comm.free()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

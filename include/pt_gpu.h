@@ -73,6 +73,11 @@ typedef struct pt_lca_info {
 int pt_lca_build(pt_lca** out, const int32_t* parent, int64_t n, pt_mem parent_mem, void* stream);
 int pt_lca_query(const pt_lca* h, const int32_t* u, const int32_t* v, int32_t* out, int64_t q,
                  pt_mem mem, void* stream);
+/* out[i] = lca(nodes[i], nodes[i+1]) for i < count - 1: the induced-subtree step of the reference, which takes the LCAs of
+ * CONSECUTIVE candidates of a preorder-sorted list (compute_inner_nodes, utils/induced_tree.hpp:128-138).  Any list is accepted;
+ * each node's record is read once (the right neighbour's arrives by a warp shuffle), so a list sorted by preorder on a tree whose
+ * ids follow a preorder -- what the reference's own readers produce (io/newick.hpp:164, containment.hpp:292) -- streams. */
+int pt_lca_query_adjacent(const pt_lca* h, const int32_t* nodes, int64_t count, int32_t* out, pt_mem mem, void* stream);
 int pt_lca_get_info(const pt_lca* h, pt_lca_info* info);
 /* depth[v] and preorder position of every node (DEVICE or HOST output, n entries each; either may be NULL);
  * the order_number / dist_to_root of InducedSubtreeInfo  utils/induced_tree.hpp:11-35 */
@@ -289,6 +294,32 @@ int pt_batch_download(pt_batch* b, int which, void* dst, int64_t capacity_bytes,
  * (counters.rounds = the largest branching depth of any shard).  SURVEY 8(e): the path shards with no collective. */
 int pt_batch_contain_multi(const pt_batch_desc* d, int num_devices, const pt_options* opt, uint32_t* result_bits, uint8_t* status,
                            pt_counters* counters);
+
+/* ------------------------------------------------------------------------------------------------
+ * One process per GPU: the instances of a batch are cut into contiguous ranges whose boundaries are multiples of
+ * 32, so that every rank owns whole words of the packed result vector; the path's ONLY collective is one all-reduce(SUM) of the
+ * result words of the whole batch (disjoint words: SUM == OR) plus one of the counters -- issued here, inside the library,
+ * through NCCL (dlopen of libnccl.so.2: the NCCL the host process already uses, e.g. torch's).  The reference has no
+ * counterpart (single-threaded, no communication backend: SURVEY 5).
+ *   pt_comm_unique_id : rank 0 makes the 128-byte id and hands it to the other ranks by the host program's own bootstrap
+ *   pt_comm_init      : every rank, same id; nranks == 1 needs no id and no NCCL
+ *   pt_batch_contain_sharded : `b` = this rank's range [first_instance, first_instance + local_instances) of a batch of
+ *       total_instances (first_instance a multiple of 32).  full_bits: DEVICE, ceil(total / 32) words; full_status: DEVICE,
+ *       total bytes padded to a multiple of 4, or NULL; both hold the WHOLE batch on every rank afterwards.  The local kernel
+ *       writes straight into this rank's words.  total (HOST, optional): counters summed over the ranks (rounds: the maximum);
+ *       the call synchronises the stream only when it is given.
+ *   pt_comm_allreduce : in-place all-reduce of `count` DEVICE words of elem_bytes 4 or 8, op 0 = sum, 1 = max (the enumerator's
+ *       found word)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_comm pt_comm;
+int pt_comm_unique_id(void* id128);
+int pt_comm_init(pt_comm** out, int nranks, int rank, const void* id128);
+int pt_comm_rank(const pt_comm* c);
+int pt_comm_size(const pt_comm* c);
+int pt_comm_allreduce(pt_comm* c, void* device_words, int64_t count, int elem_bytes, int op, void* stream);
+int pt_batch_contain_sharded(pt_batch* b, pt_comm* c, const pt_options* opt, int64_t first_instance, int64_t total_instances, int64_t local_instances,
+                             uint32_t* full_bits, uint8_t* full_status, pt_counters* total, void* stream);
+int pt_comm_free(pt_comm* c);
 
 /* ------------------------------------------------------------------------------------------------
  * Exhaustive switching enumeration (one instance, a range of the mixed-radix switching index).

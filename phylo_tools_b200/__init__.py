@@ -263,6 +263,44 @@ def contain_multi(arrays, num_devices=0, pool_slots=0, max_rounds=0):
     return np.unpackbits(bits.view(np.uint8), bitorder="little")[:B].astype(bool), status[:B], cnt.as_dict()
 
 
+class Comm:
+    """pt_comm_*: the library's own NCCL communicator, one process per GPU (include/pt_gpu.h).  `bootstrap(id_bytes_or_None)`
+    must hand rank 0's 128-byte id to every rank (bench.py: a torch.distributed broadcast) and return it."""
+
+    def __init__(self, nranks, rank, bootstrap=None):
+        self.nranks, self.rank = int(nranks), int(rank)
+        ident = None
+        if self.nranks > 1:
+            buf = C.create_string_buffer(128)
+            if self.rank == 0:
+                _check(_L.pt_comm_unique_id(buf), "pt_comm_unique_id")
+            ident = bootstrap(bytes(buf.raw) if self.rank == 0 else None)
+            ident = C.create_string_buffer(bytes(ident), 128)
+        self._h = C.c_void_p()
+        _check(_L.pt_comm_init(C.byref(self._h), self.nranks, self.rank, ident), "pt_comm_init")
+
+    def allreduce(self, words, op="sum", stream=None):
+        """in place on a torch CUDA tensor of 4- or 8-byte elements"""
+        _check(_L.pt_comm_allreduce(self._h, words.data_ptr(), int(words.numel()), int(words.element_size()), 0 if op == "sum" else 1, stream), "pt_comm_allreduce")
+
+    def contain_sharded(self, batch, first_instance, total_instances, full_bits, full_status=None, want_counters=False, stream=None, pool_slots=0):
+        """pt_batch_contain_sharded: solve this rank's range and all-reduce the packed result words of the whole batch
+        (full_bits / full_status: torch CUDA tensors for the WHOLE batch) -> counters dict summed over ranks, or None"""
+        opt = Options(pool_slots, 0, 0)
+        cnt = Counters() if want_counters else None
+        _check(_L.pt_batch_contain_sharded(batch._h, self._h, C.byref(opt), int(first_instance), int(total_instances), int(batch.num_instances),
+                                           full_bits.data_ptr(), full_status.data_ptr() if full_status is not None else None,
+                                           C.byref(cnt) if cnt is not None else None, stream), "pt_batch_contain_sharded")
+        return cnt.as_dict() if cnt is not None else None
+
+    def free(self):
+        if getattr(self, "_h", None) and _L is not None:
+            _L.pt_comm_free(self._h)
+            self._h = None
+
+    __del__ = free
+
+
 def contain_newick(pairs):
     """[(host_newick, guest_newick)] -> (bool verdicts, status) ; the `tc` protocol of examples/tc.cpp:110-142 for a list"""
     p = Packer()
@@ -297,6 +335,16 @@ class Lca:
                 out = np.empty(len(u), dtype=np.int32)
         q = int(u.shape[0])
         _check(_L.pt_lca_query(self._h, _ptr(u), _ptr(v), _ptr(out), q, PT_MEM_DEVICE if dev else PT_MEM_HOST, stream), "pt_lca_query")
+        return out
+
+    def query_adjacent(self, nodes, out=None, stream=None):
+        """pt_lca_query_adjacent: out[i] = lca(nodes[i], nodes[i+1]) (utils/induced_tree.hpp:128-138)"""
+        dev = _is_device(nodes)
+        if not dev:
+            nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+            if out is None:
+                out = np.empty(max(len(nodes) - 1, 0), dtype=np.int32)
+        _check(_L.pt_lca_query_adjacent(self._h, _ptr(nodes), int(nodes.shape[0]), _ptr(out), PT_MEM_DEVICE if dev else PT_MEM_HOST, stream), "pt_lca_query_adjacent")
         return out
 
     def info(self):

@@ -255,11 +255,79 @@ __global__ void __launch_bounds__(256) lca_query_kernel(int64_t q, int64_t n, co
           if (bl == br) {
             const uint32_t m = (uint32_t)(r0 >> 32) >> ((lp & 31) + 1);        // stack entries strictly right of lp
             const uint32_t jpos = (lp & 31) + 1 + (uint32_t)__ffs(m) - 1;        // m != 0: bit (rp & 31) is always set
-            best = keypos[((int64_t)bl << 5) + jpos];
+            best = jpos == (rp & 31) ? (swap ? a3[j] : b3[j]) : keypos[((int64_t)bl << 5) + jpos];  // the right end itself: its own key is in the record
           } else {
             best = lsuf < rpre ? lsuf : rpre;      // (lp, end of its block]  and  [start of rp's block, rp]
             if (br - bl >= 2) {
               const uint32_t span = br - bl - 1;   // whole blocks bl+1 .. br-1
+              const int k = 31 - __clz(span);
+              const u64* lvl = table + level_base[k];
+              const u64 t1 = ld_u64_hint(lvl + (bl + 1), keep), t2 = ld_u64_hint(lvl + (br - (1u << k)), keep);
+              const u64 t = t1 < t2 ? t1 : t2;
+              best = t < best ? t : best;
+            }
+          }
+          ans = (int32_t)(uint32_t)(best & 0xffffffffull);
+        }
+      }
+      st_stream(out + i, ans);
+    }
+  }
+}
+
+// ---- consecutive pairs of a list: out[i] = lca(nodes[i], nodes[i+1]) -- the induced-subtree step of the reference
+// (utils/induced_tree.hpp:128-138: LCAs of consecutive candidates of a preorder-sorted list).  Every record is loaded ONCE: a
+// lane gets the record of its right neighbour by shuffle (the last lane of a warp loads the one record beyond the warp).  For a
+// list sorted by preorder on a tree whose node ids follow a preorder (what the reference's readers produce) the record loads
+// stream: 4 B in + 32 B record + 4 B out per query = SURVEY's 40-byte model, moved once.
+template <int QPT>
+__global__ void __launch_bounds__(256) lca_adjacent_kernel(int64_t q /* = count - 1 */, int64_t n, const int32_t* __restrict__ nodes, int32_t* __restrict__ out,
+                                                           const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table,
+                                                           const int64_t* __restrict__ level_base) {
+  const int lane = threadIdx.x & 31;
+  const u64 keep = l2_policy_evict_last();
+  const int64_t tile = (int64_t)blockDim.x * QPT;
+  for (int64_t t0 = blockIdx.x * tile; t0 < q; t0 += (int64_t)gridDim.x * tile) {
+    int32_t u[QPT]; u64 a0[QPT], a1[QPT], a2[QPT], a3[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t i = t0 + (int64_t)j * blockDim.x + threadIdx.x;   // element i of the list (i <= q is a valid element)
+      u[j] = i <= q ? ld_stream(nodes + i) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      a0[j] = a1[j] = a2[j] = a3[j] = 0;
+      if ((uint64_t)(uint32_t)u[j] < (uint64_t)n) { const uint4* p = reinterpret_cast<const uint4*>(rec + u[j]); const uint4 x = __ldg(p), y = __ldg(p + 1);
+        a0[j] = ((u64)x.y << 32) | x.x; a1[j] = ((u64)x.w << 32) | x.z; a2[j] = ((u64)y.y << 32) | y.x; a3[j] = ((u64)y.w << 32) | y.z; }
+    }
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+      const int64_t i = t0 + (int64_t)j * blockDim.x + threadIdx.x;
+      // right neighbour: element i + 1
+      int32_t v = __shfl_down_sync(0xffffffffu, u[j], 1);
+      u64 b0 = __shfl_down_sync(0xffffffffu, a0[j], 1), b2 = __shfl_down_sync(0xffffffffu, a2[j], 1), b3 = __shfl_down_sync(0xffffffffu, a3[j], 1), b1 = __shfl_down_sync(0xffffffffu, a1[j], 1);
+      if (lane == 31 && i < q) {
+        v = ld_stream(nodes + i + 1);
+        if ((uint64_t)(uint32_t)v < (uint64_t)n) { const LcaRecord r = rec[v]; b0 = ((u64)r.mask << 32) | r.pos; b1 = r.suf; b2 = r.pre; b3 = r.key; }
+      }
+      if (i >= q) continue;
+      int32_t ans = -1;
+      if ((uint64_t)(uint32_t)u[j] < (uint64_t)n && (uint64_t)(uint32_t)v < (uint64_t)n) {
+        if (u[j] == v) ans = v;
+        else {
+          const bool swap = (uint32_t)a0[j] > (uint32_t)b0;
+          const u64 l0 = swap ? b0 : a0[j], lsuf = swap ? b1 : a1[j];
+          const u64 r0 = swap ? a0[j] : b0, rpre = swap ? a2[j] : b2, rkey = swap ? a3[j] : b3;
+          const uint32_t lp = (uint32_t)l0, rp = (uint32_t)r0, bl = lp >> 5, br = rp >> 5;
+          u64 best;
+          if (bl == br) {
+            const uint32_t m = (uint32_t)(r0 >> 32) >> ((lp & 31) + 1);
+            const uint32_t jpos = (lp & 31) + 1 + (uint32_t)__ffs(m) - 1;
+            best = jpos == (rp & 31) ? rkey : keypos[((int64_t)bl << 5) + jpos];
+          } else {
+            best = lsuf < rpre ? lsuf : rpre;
+            if (br - bl >= 2) {
+              const uint32_t span = br - bl - 1;
               const int k = 31 - __clz(span);
               const u64* lvl = table + level_base[k];
               const u64 t1 = ld_u64_hint(lvl + (bl + 1), keep), t2 = ld_u64_hint(lvl + (br - (1u << k)), keep);
@@ -570,6 +638,37 @@ int pt_lca_query(const pt_lca* hc, const int32_t* u, const int32_t* v, int32_t* 
   const int64_t threads = (q + QPT - 1) / QPT;
   const int grid = (int)std::min<int64_t>((threads + 255) / 256, (int64_t)dp.sms * 8);
   lca_query_kernel<QPT><<<std::max(grid, 1), 256, 0, s>>>(q, h->n, du, dv, dout, h->rec, h->keypos, h->table, h->d_level_base);
+  PT_CUDA(cudaGetLastError());
+  if (mem == PT_MEM_HOST) {
+    PT_CUDA(cudaMemcpyAsync(out, dout, (size_t)q * 4, cudaMemcpyDeviceToHost, s));
+    PT_CUDA(cudaStreamSynchronize(s));
+  }
+  return PT_OK;
+}
+
+int pt_lca_query_adjacent(const pt_lca* hc, const int32_t* nodes, int64_t count, int32_t* out, pt_mem mem, void* stream) {
+  pt_lca* h = const_cast<pt_lca*>(hc);
+  if (!h || count < 0 || (count > 1 && (!nodes || !out))) return set_error(PT_ERR_INVALID, "pt_lca_query_adjacent: bad argument");
+  if (count < 2) return PT_OK;
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceProps dp;
+  if (int rc = device_props(&dp)) return rc;
+  const int64_t q = count - 1;
+  const int32_t* dn = nodes; int32_t* dout = out;
+  if (mem == PT_MEM_HOST) {
+    if (h->qcap < count) {
+      cudaStreamSynchronize(s);
+      dev_free(h->d_u); dev_free(h->d_v); dev_free(h->d_out); h->d_u = h->d_v = h->d_out = nullptr; h->qcap = 0;
+      PT_CUDA(lca_malloc((void**)&h->d_u, (size_t)count * 4)); PT_CUDA(lca_malloc((void**)&h->d_v, (size_t)count * 4)); PT_CUDA(lca_malloc((void**)&h->d_out, (size_t)count * 4));
+      h->qcap = count;
+    }
+    PT_CUDA(cudaMemcpyAsync(h->d_u, nodes, (size_t)count * 4, cudaMemcpyHostToDevice, s));
+    dn = h->d_u; dout = h->d_out;
+  }
+  constexpr int QPT = 4;
+  const int grid = (int)std::min<int64_t>((q + 256 * QPT - 1) / (256 * QPT), (int64_t)dp.sms * 8);
+  lca_adjacent_kernel<QPT><<<std::max(grid, 1), 256, 0, s>>>(q, h->n, dn, dout, h->rec, h->keypos, h->table, h->d_level_base);
   PT_CUDA(cudaGetLastError());
   if (mem == PT_MEM_HOST) {
     PT_CUDA(cudaMemcpyAsync(out, dout, (size_t)q * 4, cudaMemcpyDeviceToHost, s));

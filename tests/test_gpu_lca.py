@@ -76,6 +76,43 @@ def test_same_block_neighbours(pt, oracle):
     L.free()
 
 
+def test_adjacent_pairs_of_a_list(pt, oracle):
+    """pt_lca_query_adjacent: out[i] = lca(nodes[i], nodes[i+1]) -- the reference's induced-subtree step on consecutive
+    candidates (utils/induced_tree.hpp:128-138): preorder-sorted lists, random lists, lists with repeats and out-of-range ids,
+    every length around the warp / tile boundaries, HOST and DEVICE memory"""
+    import torch
+    rng = np.random.default_rng(23)
+    for kind, n in (("random", 5000), ("bushy", 70000), ("cat", 3000), ("star", 400)):
+        par = _shape(rng, n, kind)
+        L = pt.Lca(par)
+        _, pre = L.node_info()
+        by_pre = np.argsort(pre).astype(np.int32)
+        for count in (0, 1, 2, 3, 31, 32, 33, 64, 1023, 1024, 1025, 2049, min(n, 50000)):
+            for mode in ("sorted", "random", "repeats"):
+                if mode == "sorted":
+                    nodes = by_pre[np.sort(rng.choice(n, min(count, n), replace=False))] if count else np.zeros(0, np.int32)
+                elif mode == "random":
+                    nodes = rng.integers(0, n, count).astype(np.int32)
+                else:
+                    nodes = np.repeat(rng.integers(0, n, count // 2 + 1), 2)[:count].astype(np.int32)
+                got = L.query_adjacent(nodes)
+                assert len(got) == max(len(nodes) - 1, 0)
+                if len(nodes) >= 2:
+                    assert (got == oracle.lca_euler(par, nodes[:-1], nodes[1:])).all(), (kind, count, mode)
+        # DEVICE lists, with ids outside the tree answering -1
+        nodes = rng.integers(0, n, 4000).astype(np.int32)
+        nodes[[7, 100, 3999]] = [-1, n, n + 5]
+        d = torch.from_numpy(nodes).cuda()
+        out = torch.empty(len(nodes) - 1, dtype=torch.int32, device="cuda")
+        L.query_adjacent(d, out=out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        ok = (nodes[:-1] >= 0) & (nodes[:-1] < n) & (nodes[1:] >= 0) & (nodes[1:] < n)
+        assert (got[~ok] == -1).all()
+        assert (got[ok] == oracle.lca_euler(par, nodes[:-1][ok], nodes[1:][ok])).all()
+        L.free()
+
+
 def test_device_memory_path(pt, oracle):
     import torch
     par = pt.random_tree(50000, 3)
