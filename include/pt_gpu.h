@@ -103,6 +103,42 @@ int pt_tree_who_displays(const int32_t* host_parent, const int32_t* host_label, 
 int pt_tree_highest_displayed(const int32_t* guest_parent, const int32_t* who, int64_t nt, int32_t host_root, int32_t* out, pt_mem mem, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The tree-in-tree DP in its general form -- replaces
+ *     TreeInTreeContainment<Host, Guest>::who_displays(u), displayed()    utils/containment.hpp:27-233
+ *       (merge_child_poss :180-230, the induced subtree utils/induced_tree.hpp:65-168, the child-set registration :140-149,
+ *        perfect_child_matching :174-177 = bipartite_matching utils/matching.hpp:8-93)
+ *     TreeInComponent::unzip_retis / highest_displayed_ancestor            utils/containment.hpp:262-312, 328-344
+ *     TreeComponentInfos (comp_root, visible_leaf, component DAG)           utils/tree_components.hpp:41-234
+ * The host tree may be MULTI-LABELLED (the reference's ROMulTree: a leaf label may occur several times); the guest is a
+ * single-labelled tree.  pt_who_build runs the whole DP (a wavefront over the guest's levels on top of pt_lca) and keeps, per
+ * guest node u, the list of host nodes that MINIMALLY display the guest subtree below u, ascending in host preorder -- what
+ * who_displays(u) returns.  The guest is displayed iff the list of its root is not empty (:83).  Guest nodes with more than 64
+ * children: PT_ERR_UNSUPPORTED.  Labels: dense ids < n + nt shared by both trees, -1 = none; only leaf labels count.
+ *   pt_who_total : number of entries over all lists;  pt_who_lists : off[nt + 1] and the concatenated lists (HOST or DEVICE)
+ *   pt_who_highest_displayed : highest_displayed_ancestor of EVERY guest node over those lists ("displayed by the host root
+ *       alone" = the list is exactly { host_root }, :340); out[guest root] = guest root
+ *   pt_net_unzip : the multi-labelled tree the reference unfolds below node `root` of a network (edge traversal without a
+ *       seen-set, arcs leaving out-degree-1 nodes skipped, out-degree-1 heads replaced by the end of their chain): node 0 = root,
+ *       ids in preorder with the children in CSR order; out_origin[i] = the network node copy i stands for; out_label = the
+ *       label of out-degree-0 origins.  *count receives the size; if it exceeds `capacity` (or the outputs are NULL) nothing
+ *       is written and PT_ERR_UNSUPPORTED (PT_OK for NULL outputs) is returned: call again with room for *count nodes.
+ *   pt_net_tree_components : comp_root[v] (-1 = NoNode) and visible_leaf[v] (for component roots: a leaf whose comp_root is v,
+ *       the largest such id; else -1) as TreeComponentInfos computes them for a fresh network, and the arcs of the component
+ *       DAG as (root above << 32 | root below), duplicates included (*dag_count of them; at most dag_capacity are written).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pt_who pt_who;
+int pt_who_build(pt_who** out, const int32_t* host_parent, const int32_t* host_label, int64_t n, const int32_t* guest_parent,
+                 const int32_t* guest_label, int64_t nt, pt_mem mem, void* stream);
+int pt_who_total(const pt_who* h, int64_t* total_entries);
+int pt_who_lists(const pt_who* h, int32_t* out_off, int32_t* out_adj, pt_mem mem, void* stream);
+int pt_who_highest_displayed(const pt_who* h, int32_t host_root, int32_t* out, pt_mem mem, void* stream);
+int pt_who_free(pt_who* h);
+int pt_net_unzip(int64_t n, int64_t m, const int32_t* succ_off, const int32_t* succ_adj, const int32_t* label, int32_t root,
+                 int32_t* out_parent, int32_t* out_label, int32_t* out_origin, int64_t capacity, int64_t* count, pt_mem mem, void* stream);
+int pt_net_tree_components(int64_t n, int64_t m, const int32_t* succ_off, const int32_t* succ_adj, int32_t* comp_root, int32_t* visible_leaf,
+                           int64_t* dag_edges, int64_t dag_capacity, int64_t* dag_count, pt_mem mem, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Network isomorphism -- replaces  make_iso_mapper(N0, N1, flags).check_isomorph()
  *                                  utils/isomorphism.hpp:33-324 (examples/iso.cpp:96-112, the `iso` tool)
  * for P pairs of networks at once.  Graph g = 2 * pair + side owns the slices given by node_off / arc_off

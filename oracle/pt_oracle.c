@@ -294,6 +294,149 @@ int orc_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, int n
   return 0;
 }
 
+/* ---- who_displays for MULTI-LABELLED tree hosts: TreeInTreeContainment::who_displays utils/containment.hpp:72-230 --------
+ * The reference keeps, per guest node u, the preorder-sorted list of host nodes that MINIMALLY display the guest subtree below
+ * u: base case = the host leaves carrying u's label (:115-126); a node with one child maps where the child maps (:167); for
+ * d >= 2 children it builds the host subtree induced by the children's candidates (utils/induced_tree.hpp:65-168), lets every
+ * candidate tell its induced ancestors which guest child it can display (:140-149) and accepts, lowest first, every induced
+ * node at which the guest children can be matched to DISTINCT induced children (bipartite matching, utils/matching.hpp; :152-163).
+ * Restated from the DEFINITION that algorithm computes: A(u) = host nodes whose subtree displays T_u (leaves not needed may be
+ * ignored: a MUL-tree displays T if SOME choice of one leaf per label does), A'(u) = nodes x with an assignment of u's children
+ * to distinct children y of x, y in A(child); A(u) = ancestors-or-self of A'(u); the answer M(u) = the minimal nodes of A'(u).
+ * Every host node is tried, no induced tree, no LCA.  Unlabelled guest leaves are cleaned away (as everywhere in this repo).
+ * out_off[nt+1] / out_adj: M(u) in ascending node id (the reference sorts by ITS preorder: compare as sets).
+ * returns the total number of entries, or -1 if out_adj (capacity cap) is too small, -3 on more than 64 guest children. */
+typedef struct { int nl, nr; const uint64_t* adj; int matchR[4096]; uint8_t seen[4096]; } orc_match_ctx;
+static int orc_try_match(orc_match_ctx* c, int i) {
+  for (int y = 0; y < c->nr; ++y) if (((c->adj[y] >> i) & 1ull) && !c->seen[y]) {
+    c->seen[y] = 1;
+    if (c->matchR[y] < 0 || orc_try_match(c, c->matchR[y])) { c->matchR[y] = i; return 1; }
+  }
+  return 0;
+}
+int orc_mul_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, int nt, const int32_t* tparent, const int32_t* tlabel,
+                         int32_t* out_off, int32_t* out_adj, int cap) {
+  int32_t* hdeg = (int32_t*)calloc((size_t)n, 4); int32_t* tdeg = (int32_t*)calloc((size_t)nt, 4);
+  for (int v = 0; v < n; ++v) if (hparent[v] >= 0) hdeg[hparent[v]]++;
+  for (int t = 0; t < nt; ++t) if (tparent[t] >= 0) tdeg[tparent[t]]++;
+  int32_t* tdepth = (int32_t*)calloc((size_t)nt, 4); int maxtd = 0;
+  for (int t = 0; t < nt; ++t) { int d = 0, x = t; while (tparent[x] >= 0) { x = tparent[x]; ++d; } tdepth[t] = d; if (d > maxtd) maxtd = d; }
+  /* host children lists */
+  int32_t* hoff = (int32_t*)calloc((size_t)n + 1, 4); int32_t* hadj = (int32_t*)malloc((size_t)(n + 1) * 4);
+  for (int v = 0; v < n; ++v) if (hparent[v] >= 0) hoff[hparent[v] + 1]++;
+  for (int v = 0; v < n; ++v) hoff[v + 1] += hoff[v];
+  { int32_t* pos = (int32_t*)malloc((size_t)(n + 1) * 4); memcpy(pos, hoff, (size_t)(n + 1) * 4); for (int v = 0; v < n; ++v) if (hparent[v] >= 0) hadj[pos[hparent[v]]++] = v; free(pos); }
+  /* A[u] (n bytes per guest node), state: 0 computed, 1 dead (cleaned away) */
+  uint8_t* A = (uint8_t*)calloc((size_t)nt * (size_t)n, 1); uint8_t* M = (uint8_t*)calloc((size_t)nt * (size_t)n, 1); uint8_t* dead = (uint8_t*)calloc((size_t)nt, 1);
+  int rc = 0;
+  orc_match_ctx* mc = (orc_match_ctx*)malloc(sizeof(orc_match_ctx));
+  uint64_t* adj = (uint64_t*)malloc(4096 * 8);
+  for (int d = maxtd; d >= 0 && rc == 0; --d) for (int u = 0; u < nt && rc == 0; ++u) if (tdepth[u] == d) {
+    uint8_t* Au = A + (size_t)u * n; uint8_t* Mu = M + (size_t)u * n;
+    if (tdeg[u] == 0) {
+      if (tlabel[u] < 0) { dead[u] = 1; continue; }
+      for (int v = 0; v < n; ++v) if (hdeg[v] == 0 && hlabel[v] == tlabel[u]) Mu[v] = 1;
+    } else {
+      int kids[64], nk = 0, empty = 0;
+      for (int c = 0; c < nt; ++c) if (tparent[c] == u && !dead[c]) {
+        if (nk == 64) { rc = -3; break; }
+        kids[nk++] = c;
+        int any = 0; for (int v = 0; v < n; ++v) any |= M[(size_t)c * n + v];
+        if (!any) empty = 1;
+      }
+      if (rc) break;
+      if (nk == 0) { dead[u] = 1; continue; }
+      if (empty) continue;
+      if (nk == 1) memcpy(Mu, M + (size_t)kids[0] * n, (size_t)n);
+      else {
+        uint8_t* Ap = (uint8_t*)calloc((size_t)n, 1);
+        for (int x = 0; x < n; ++x) {
+          const int r = hoff[x + 1] - hoff[x];
+          if (r < nk || r > 4096) continue;
+          for (int k = 0; k < r; ++k) { const int y = hadj[hoff[x] + k]; uint64_t m = 0; for (int i = 0; i < nk; ++i) if (A[(size_t)kids[i] * n + y]) m |= 1ull << i; adj[k] = m; }
+          mc->nl = nk; mc->nr = r; mc->adj = adj;
+          for (int k = 0; k < r; ++k) mc->matchR[k] = -1;
+          int ok = 1;
+          for (int i = 0; i < nk && ok; ++i) { memset(mc->seen, 0, (size_t)r); ok = orc_try_match(mc, i); }
+          Ap[x] = (uint8_t)ok;
+        }
+        /* minimal elements of A' */
+        for (int x = 0; x < n; ++x) if (Ap[x]) {
+          int below = 0;
+          for (int w = 0; w < n && !below; ++w) if (w != x && Ap[w]) { int z = hparent[w]; while (z >= 0 && z != x) z = hparent[z]; if (z == x) below = 1; }
+          if (!below) Mu[x] = 1;
+        }
+        free(Ap);
+      }
+    }
+    /* A(u) = ancestors-or-self of M(u) */
+    for (int v = 0; v < n; ++v) if (Mu[v]) { int z = v; while (z >= 0 && !Au[z]) { Au[z] = 1; z = hparent[z]; } }
+  }
+  int total = 0;
+  if (rc == 0) {
+    for (int u = 0; u < nt; ++u) {
+      out_off[u] = total;
+      for (int v = 0; v < n; ++v) if (M[(size_t)u * n + v]) { if (total >= cap) { rc = -1; break; } out_adj[total++] = v; }
+      if (rc) break;
+    }
+    out_off[nt] = total;
+  }
+  free(hdeg); free(tdeg); free(tdepth); free(hoff); free(hadj); free(A); free(M); free(dead); free(mc); free(adj);
+  return rc ? rc : total;
+}
+
+/* highest_displayed_ancestor over LISTS (the general table): as orc_highest_displayed, "displayed by the host root alone" =
+ * the list of that guest node is exactly { host_root } (utils/containment.hpp:340) */
+int orc_highest_displayed_lists(int nt, const int32_t* tparent, const int32_t* off, const int32_t* adj, int32_t host_root, int32_t* out) {
+  for (int s = 0; s < nt; ++s) {
+    int v = s;
+    if (tparent[v] < 0) { out[s] = v; continue; }
+    int pv = tparent[v];
+    for (;;) {
+      if (off[pv + 1] == off[pv]) break;
+      v = pv;
+      if (tparent[v] < 0) break;
+      if (off[v + 1] - off[v] == 1 && adj[off[v]] == host_root) break;
+      pv = tparent[v];
+    }
+    out[s] = v;
+  }
+  return 0;
+}
+
+/* ---- unzip_retis: TreeInComponent::unzip_retis utils/containment.hpp:262-312 ------------------------------------------------
+ * The reference walks the host below u with an EDGE traversal that keeps no seen-set, so everything below a reticulation is
+ * visited once per way of reaching it: the network unfolds into a multi-labelled tree.  Arcs leaving a node of out-degree 1 are
+ * skipped (:281) and a head of out-degree 1 is replaced by the end of its out-degree-1 chain (:284), i.e. unary nodes
+ * (reticulations, suppressible nodes) disappear.  New node ids are handed out in visiting order (a preorder; the visiting order
+ * of siblings is the storage's and not contractual); only labels of out-degree-0 nodes are kept (leaf_labels_only).
+ * Restated as a plain recursive unfolding.  succ_off/succ_adj: host CSR; out_parent / out_label / out_origin (the host node a
+ * copy stands for): capacity cap; returns the number of nodes of the MUL-tree, or -1 when it exceeds cap. */
+typedef struct { const int32_t *off, *adj, *lab; int32_t *par, *olab, *orig; int cap, count; } orc_unzip_ctx;
+static int orc_unzip_rec(orc_unzip_ctx* c, int x, int st_x) {
+  if (c->off[x + 1] - c->off[x] == 1) return 0;                       /* never entered: heads are chain ends */
+  for (int k = c->off[x]; k < c->off[x + 1]; ++k) {
+    int y = c->adj[k];
+    while (c->off[y + 1] - c->off[y] == 1) y = c->adj[c->off[y]];
+    if (c->count >= c->cap) return -1;
+    const int st_y = c->count++;
+    c->par[st_y] = st_x; c->orig[st_y] = y;
+    c->olab[st_y] = (c->off[y + 1] == c->off[y]) ? c->lab[y] : -1;
+    if (orc_unzip_rec(c, y, st_y) < 0) return -1;
+  }
+  return 0;
+}
+int orc_unzip(int n, const int32_t* succ_off, const int32_t* succ_adj, const int32_t* label, int u, int32_t* out_parent, int32_t* out_label, int32_t* out_origin, int cap) {
+  (void)n;
+  orc_unzip_ctx c = {succ_off, succ_adj, label, out_parent, out_label, out_origin, cap, 0};
+  if (cap < 1) return -1;
+  /* the root: the reference translates u itself to 0 (:274) whatever its out-degree; if u is unary its arcs are skipped and the
+   * subtree is the single node 0 -- callers pass a tree-component root, which is never unary after the clean-up */
+  c.par[0] = -1; c.orig[0] = u; c.olab[0] = (succ_off[u + 1] == succ_off[u]) ? label[u] : -1; c.count = 1;
+  if (orc_unzip_rec(&c, u, 0) < 0) return -1;
+  return c.count;
+}
+
 /* ---- highest_displayed_ancestor: TreeInComponent::highest_displayed_ancestor utils/containment.hpp:328-344 -----------------
  * The reference's loop, one guest node at a time, over the who_displays table (who[u] = the one host node displaying u, or -1):
  *   pv = parent(v); forever { if who[pv] is empty return v; v = pv; if v is the guest root return v;

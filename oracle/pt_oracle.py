@@ -45,6 +45,12 @@ def lib():
         L.orc_who_displays.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p, i32p, i32p]
         L.orc_highest_displayed.restype = C.c_int
         L.orc_highest_displayed.argtypes = [C.c_int, i32p, i32p, C.c_int32, i32p]
+        L.orc_mul_who_displays.restype = C.c_int
+        L.orc_mul_who_displays.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p, i32p, i32p, i32p, C.c_int]
+        L.orc_highest_displayed_lists.restype = C.c_int
+        L.orc_highest_displayed_lists.argtypes = [C.c_int, i32p, i32p, i32p, C.c_int32, i32p]
+        L.orc_unzip.restype = C.c_int
+        L.orc_unzip.argtypes = [C.c_int, i32p, i32p, i32p, C.c_int, i32p, i32p, i32p, C.c_int]
         L.orc_iso.restype = C.c_int
         L.orc_iso.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int]
     return _LIB
@@ -152,6 +158,43 @@ def who_displays(host_parent, host_label, guest_parent, guest_label):
     if rc != 0:
         raise ValueError("orc_who_displays failed: %d" % rc)
     return out
+
+
+def mul_who_displays(host_parent, host_label, guest_parent, guest_label):
+    """orc_mul_who_displays: (off[nt+1], adj) = per guest node the host nodes that minimally display it, ascending node id;
+    the host may be multi-labelled (utils/containment.hpp:72-230)"""
+    hp, hl, gp, gl = _arr(host_parent), _arr(host_label), _arr(guest_parent), _arr(guest_label)
+    cap = max(16, 4 * (len(hp) + len(gp)) * 4)
+    while True:
+        off = np.zeros(len(gp) + 1, dtype=np.int32); adj = np.zeros(cap, dtype=np.int32)
+        rc = lib().orc_mul_who_displays(len(hp), _p(hp), _p(hl), len(gp), _p(gp), _p(gl), _p(off), _p(adj), cap)
+        if rc == -1:
+            cap *= 4
+            continue
+        if rc < 0:
+            raise ValueError("orc_mul_who_displays failed: %d" % rc)
+        return off, adj[:rc].copy()
+
+
+def highest_displayed_lists(guest_parent, off, adj, host_root):
+    gp, o, a = _arr(guest_parent), _arr(off), _arr(adj if len(adj) else [0])
+    out = np.empty(len(gp), dtype=np.int32)
+    lib().orc_highest_displayed_lists(len(gp), _p(gp), _p(o), _p(a), int(host_root), _p(out))
+    return out
+
+
+def unzip(succ_off, succ_adj, label, u):
+    """orc_unzip (TreeInComponent::unzip_retis, utils/containment.hpp:262-312) -> (parent, label, origin) of the MUL-tree below u"""
+    so, sa, lab = _arr(succ_off), _arr(succ_adj if len(succ_adj) else [0]), _arr(label)
+    cap = 1 << 12
+    while True:
+        par, ol, org = (np.empty(cap, dtype=np.int32) for _ in range(3))
+        k = lib().orc_unzip(len(so) - 1, _p(so), _p(sa), _p(lab), int(u), _p(par), _p(ol), _p(org), cap)
+        if k >= 0:
+            return par[:k].copy(), ol[:k].copy(), org[:k].copy()
+        cap *= 8
+        if cap > 1 << 27:
+            raise ValueError("orc_unzip: the MUL-tree is too large")
 
 
 def highest_displayed(guest_parent, who, host_root):

@@ -14,6 +14,14 @@
 //        reference's BiconnectedComponents iterator yields ("C" + its edges, sorted), then "--"
 //   ref_tc iso <file> [flags] : pairs of network lines; one char per pair: 1 isomorph / 0 not (make_iso_mapper(...).check_isomorph(),
 //        examples/iso.cpp:96-112; flags as FLAG_MAP_* utils/isomorphism.hpp:10-13, default 1), E exception, S signal
+//   ref_tc whomul <file> : (multi-labelled host TREE, guest tree) pairs; who_displays(u) of the reference for every guest node with the
+//        host as a ROMulTree (TreeInTreeContainment<ROMulTree<>, ROTree<>>, utils/containment.hpp:27-233)
+//   ref_tc hda <file> : (host network, guest tree) pairs; TreeInComponent (utils/containment.hpp:241-347) built at the host's root:
+//        first the unzipped MUL-tree ("U n" then "parent label|-" per node: unzip_retis :262-312), then per guest node v != root
+//        "v: highest_displayed_ancestor(v)" (:328-344).  The class keeps the MUL-tree private; the driver reads it through an explicit
+//        template instantiation naming the member (legal C++; nothing of the reference is modified)
+//   ref_tc comps <file> : per network line: per node "v comp_root visible_leaf" (-1 = NoNode) of TreeComponentInfos
+//        (utils/tree_components.hpp:41-234), then the arcs of its component DAG "D u v", then "--"
 //   ref_tc parse <file> : for each line: "n m" then edges "u v" in reference edge-list order, then
 //        labels "id name" sorted by id, then "--" (golden vectors for the Newick reader).
 #include "io/io.hpp"
@@ -71,6 +79,53 @@ static void run_who(const std::string& l0, const std::string& l1) {
     for (const auto v : tc.who_displays(u)) out += " " + std::to_string((size_t)v);
     out += "\n";
   }
+  fputs(out.c_str(), stdout);
+}
+
+// who_displays with a multi-labelled host
+static void run_whomul(const std::string& l0, const std::string& l1) {
+  using MulTree = ROMulTree<>;
+  std::vector<ENL> el(2);
+  parse_line(l0, el[0]); parse_line(l1, el[1]);
+  const size_t nt = el[1].num_nodes;
+  MulTree H(el[0].edges, *el[0].labels, consecutive_tag());
+  MyTree T(el[1].edges, *el[1].labels, consecutive_tag());
+  TreeInTreeContainment<MulTree, MyTree> tc(H, T);
+  std::string out;
+  for (size_t u = 0; u < nt; ++u) {
+    out += std::to_string(u) + ":";
+    for (const auto v : tc.who_displays(u)) out += " " + std::to_string((size_t)v);
+    out += "\n";
+  }
+  fputs(out.c_str(), stdout);
+}
+
+// access to TreeInComponent::subtree (a private member): an explicit instantiation may name it, and hands the pointer out
+using HdaMulTree = ROMulTree<>;
+using HdaTic = TreeInComponent<HdaMulTree, MyTree, true>;
+template <class Tag, typename Tag::type M> struct PtRob { friend typename Tag::type pt_get(Tag) { return M; } };
+struct HdaSubtreeTag { typedef HdaMulTree HdaTic::*type; friend type pt_get(HdaSubtreeTag); };
+template struct PtRob<HdaSubtreeTag, &HdaTic::subtree>;
+
+// TreeInComponent at the root of the host network: the unzipped MUL-tree and highest_displayed_ancestor of every guest node
+static void run_hda(const std::string& l0, const std::string& l1) {
+  using MulTree = ROMulTree<>;
+  std::vector<ENL> el(2);
+  parse_line(l0, el[0]); parse_line(l1, el[1]);
+  const size_t nt = el[1].num_nodes;
+  MyNet N(std::move(el[0].edges), std::move(el[0].labels), consecutive_tag());
+  MyTree T(std::move(el[1].edges), std::move(el[1].labels), consecutive_tag());
+  using LM = LabelMatchingFromNets<MyNet, MyTree, std::vector>;
+  LM match(get_leaf_label_matching<MyNet, MyTree, std::vector>(N, T));
+  HdaTic tic(N, T, match, N.root());
+  const MulTree& sub = tic.*pt_get(HdaSubtreeTag());
+  std::string out = "U " + std::to_string(sub.num_nodes()) + "\n";
+  for (size_t v = 0; v < sub.num_nodes(); ++v) {
+    const long p = (v == (size_t)sub.root()) ? -1 : (long)sub.parent(v);
+    const std::string& lab = sub.label(v);
+    out += std::to_string(p) + " " + (lab.empty() ? std::string("-") : lab) + "\n";
+  }
+  for (size_t v = 0; v < nt; ++v) if (v != (size_t)T.root()) out += std::to_string(v) + ": " + std::to_string((size_t)tic.highest_displayed_ancestor(v)) + "\n";
   fputs(out.c_str(), stdout);
 }
 
@@ -190,6 +245,50 @@ int main(int argc, char** argv) {
     }
     std::cout.clear();
     printf("%s\n", out.c_str());
+    return 0;
+  }
+  if (mode == "whomul" || mode == "hda") {
+    for (size_t i = 0; i + 1 < L.size(); i += 2) {
+      fflush(stdout);
+      pid_t pid = fork();
+      if (pid == 0) {
+        std::cout.setstate(std::ios::badbit);
+        try { if (mode == "whomul") run_whomul(L[i], L[i + 1]); else run_hda(L[i], L[i + 1]); } catch (...) { printf("EXC\n"); }
+        fflush(stdout); _exit(0);
+      }
+      int st = 0; waitpid(pid, &st, 0);
+      if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) printf("CRASH\n");
+      printf("--\n");
+    }
+    return 0;
+  }
+  if (mode == "comps") {
+    std::cout.setstate(std::ios::badbit);
+    for (auto& line : L) {
+      fflush(stdout);
+      pid_t pid = fork();
+      if (pid == 0) {
+        try {
+          ENL e; parse_line(line, e);
+          MyNet N0(e.edges, *e.labels, consecutive_tag());
+          using Net = CompatibleRWNetwork<MyNet, ComponentData>;   // what TreeInNetContainment uses as RWHost (containment.hpp:975)
+          Net N(N0);
+          TreeComponentInfos<Net> ci(N);
+          for (size_t v = 0; v < e.num_nodes; ++v) {
+            const auto& cd = N[v];
+            printf("%zu %ld %ld\n", v, cd.comp_root == NoNode ? -1L : (long)cd.comp_root, cd.visible_leaf == NoNode ? -1L : (long)cd.visible_leaf);
+          }
+          std::vector<std::pair<size_t, size_t>> ed;
+          for (const auto& uv : ci.comp_DAG.edges()) ed.emplace_back((size_t)uv.tail(), (size_t)uv.head());
+          std::sort(ed.begin(), ed.end());
+          for (auto& p : ed) printf("D %zu %zu\n", p.first, p.second);
+        } catch (...) { printf("EXC\n"); }
+        fflush(stdout); _exit(0);
+      }
+      int st = 0; waitpid(pid, &st, 0);
+      if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) printf("CRASH\n");
+      printf("--\n");
+    }
     return 0;
   }
   if (mode == "who") {

@@ -375,6 +375,71 @@ def who_displays(host_parent, host_label, guest_parent, guest_label):
     return out
 
 
+class Who:
+    """pt_who_*: TreeInTreeContainment<Host, Guest>::who_displays for a (possibly multi-labelled) tree host
+    (utils/containment.hpp:27-233): per guest node the host nodes that minimally display it, ascending in host preorder"""
+
+    def __init__(self, host_parent, host_label, guest_parent, guest_label):
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (host_parent, host_label, guest_parent, guest_label)]
+        self.nt = len(a[2])
+        self._h = C.c_void_p()
+        _check(_L.pt_who_build(C.byref(self._h), a[0].ctypes.data, a[1].ctypes.data, len(a[0]), a[2].ctypes.data, a[3].ctypes.data, len(a[2]), PT_MEM_HOST, None), "pt_who_build")
+
+    def lists(self):
+        """(off[nt+1], adj)"""
+        t = C.c_int64(0)
+        _check(_L.pt_who_total(self._h, C.byref(t)), "pt_who_total")
+        off, adj = np.zeros(self.nt + 1, dtype=np.int32), np.zeros(max(t.value, 1), dtype=np.int32)
+        _check(_L.pt_who_lists(self._h, off.ctypes.data, adj.ctypes.data, PT_MEM_HOST, None), "pt_who_lists")
+        return off, adj[:t.value]
+
+    def who_displays(self, u):
+        off, adj = self.lists()
+        return adj[off[u]:off[u + 1]]
+
+    def highest_displayed(self, host_root):
+        out = np.empty(self.nt, dtype=np.int32)
+        _check(_L.pt_who_highest_displayed(self._h, int(host_root), out.ctypes.data, PT_MEM_HOST, None), "pt_who_highest_displayed")
+        return out
+
+    def free(self):
+        if getattr(self, "_h", None) and _L is not None:
+            _L.pt_who_free(self._h)
+            self._h = None
+
+    __del__ = free
+
+
+def net_unzip(succ_off, succ_adj, label, root):
+    """pt_net_unzip (TreeInComponent::unzip_retis, utils/containment.hpp:262-312) -> (parent, label, origin) of the MUL-tree"""
+    so = np.ascontiguousarray(succ_off, dtype=np.int32); sa = np.ascontiguousarray(succ_adj, dtype=np.int32); lab = np.ascontiguousarray(label, dtype=np.int32)
+    n, m = len(so) - 1, len(sa)
+    cnt = C.c_int64(0)
+    _check(_L.pt_net_unzip(n, m, so.ctypes.data, sa.ctypes.data if m else None, lab.ctypes.data, int(root), None, None, None, 0, C.byref(cnt), PT_MEM_HOST, None), "pt_net_unzip")
+    k = cnt.value
+    par, ol, org = (np.empty(max(k, 1), dtype=np.int32) for _ in range(3))
+    _check(_L.pt_net_unzip(n, m, so.ctypes.data, sa.ctypes.data if m else None, lab.ctypes.data, int(root), par.ctypes.data, ol.ctypes.data, org.ctypes.data, k, C.byref(cnt), PT_MEM_HOST, None), "pt_net_unzip")
+    return par[:k], ol[:k], org[:k]
+
+
+def net_tree_components(succ_off, succ_adj):
+    """pt_net_tree_components (TreeComponentInfos, utils/tree_components.hpp:41-234) -> (comp_root, visible_leaf, sorted unique
+    component-DAG arcs [(root above, root below)])"""
+    so = np.ascontiguousarray(succ_off, dtype=np.int32); sa = np.ascontiguousarray(succ_adj, dtype=np.int32)
+    n, m = len(so) - 1, len(sa)
+    comp, vis = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+    cap = max(16, 4 * m)
+    while True:
+        edges = np.zeros(cap, dtype=np.int64)
+        cnt = C.c_int64(0)
+        _check(_L.pt_net_tree_components(n, m, so.ctypes.data, sa.ctypes.data if m else None, comp.ctypes.data, vis.ctypes.data, edges.ctypes.data, cap, C.byref(cnt), PT_MEM_HOST, None), "pt_net_tree_components")
+        if cnt.value <= cap:
+            break
+        cap = int(cnt.value)
+    e = np.unique(edges[:cnt.value])
+    return comp, vis, [(int(x >> 32), int(x & 0xFFFFFFFF)) for x in e]
+
+
 def highest_displayed(guest_parent, who, host_root):
     """pt_tree_highest_displayed: int32[nt], TreeInComponent::highest_displayed_ancestor (utils/containment.hpp:328-344) of every
     guest node, from the table who_displays returned"""

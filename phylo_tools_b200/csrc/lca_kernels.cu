@@ -108,6 +108,20 @@ __global__ void lca_fill_children_kernel(const int32_t* __restrict__ parent, int
   }
 }
 
+// children lists in ascending node id: the atomic fill above leaves them in arrival order, which would make the preorder (and
+// with it the order of every who_displays list) differ from build to build; lists are short, one thread sorts one list
+__global__ void lca_sort_children_kernel(int64_t n, const int32_t* __restrict__ child_off, int32_t* __restrict__ child_adj) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t b = child_off[v], e = child_off[v + 1];
+    if (e - b == 2) { const int32_t x = child_adj[b], y = child_adj[b + 1]; if (x > y) { child_adj[b] = y; child_adj[b + 1] = x; } continue; }
+    if (e - b <= 64) { for (int32_t i = b + 1; i < e; ++i) { const int32_t x = child_adj[i]; int32_t j = i; while (j > b && child_adj[j - 1] > x) { child_adj[j] = child_adj[j - 1]; --j; } child_adj[j] = x; } continue; }
+    // long lists (stars): heap sort in place
+    const int32_t m = e - b; int32_t* a = child_adj + b;
+    for (int32_t start = m / 2 - 1; start >= 0; --start) { int32_t r = start; const int32_t val = a[r]; for (;;) { int32_t c = 2 * r + 1; if (c >= m) break; if (c + 1 < m && a[c + 1] > a[c]) ++c; if (a[c] <= val) break; a[r] = a[c]; r = c; } a[r] = val; }
+    for (int32_t end = m - 1; end > 0; --end) { const int32_t val = a[end]; a[end] = a[0]; int32_t r = 0; for (;;) { int32_t c = 2 * r + 1; if (c >= end) break; if (c + 1 < end && a[c + 1] > a[c]) ++c; if (a[c] <= val) break; a[r] = a[c]; r = c; } a[r] = val; }
+  }
+}
+
 // ---- build step 4: three level-synchronous sweeps in ONE cooperative kernel -------------------------------------
 //   top-down   : BFS order + depth (wavefront, children appended with one atomic per parent)
 //   bottom-up  : subtree sizes
@@ -499,14 +513,15 @@ struct pt_lca {
   int64_t n = 0, nblocks = 0, levels = 0, table_levels = 0, device_bytes = 0;
   float build_ms = 0.f;
   LcaRecord* rec = nullptr; u64* keypos = nullptr; u64* table = nullptr; int64_t* d_level_base = nullptr;
-  int32_t* size = nullptr;  // subtree sizes (kept only when requested: bridges need preorder intervals)
+  int32_t* size = nullptr;    // subtree sizes (kept only when requested: bridges need preorder intervals)
+  int32_t* nodeat = nullptr;  // node at every preorder position (kept with `size`: the tree-in-tree DP works on positions)
   int32_t *d_u = nullptr, *d_v = nullptr, *d_out = nullptr; int64_t qcap = 0;  // staging for HOST queries
 };
 
 static void lca_release(pt_lca* h) {
   if (!h) return;
   cudaDeviceSynchronize();
-  dev_free(h->rec); dev_free(h->keypos); dev_free(h->table); dev_free(h->d_level_base); dev_free(h->d_u); dev_free(h->d_v); dev_free(h->d_out); dev_free(h->size);
+  dev_free(h->rec); dev_free(h->keypos); dev_free(h->table); dev_free(h->d_level_base); dev_free(h->d_u); dev_free(h->d_v); dev_free(h->d_out); dev_free(h->size); dev_free(h->nodeat);
   delete h;
 }
 
@@ -532,7 +547,8 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
     cudaStreamSynchronize(s);
     if (parent_mem == PT_MEM_HOST) dev_free(d_parent);
     dev_free(deg); dev_free(child_off); dev_free(child_adj); dev_free(order); dev_free(depth); if (size != h->size) dev_free(size); dev_free(pre); dev_free(level_off); dev_free(small);
-    dev_free(nodeat); dev_free(scan_tmp);
+    if (nodeat != h->nodeat) dev_free(nodeat);
+    dev_free(scan_tmp);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
   };
@@ -570,6 +586,7 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
   if ((rc = device_exclusive_scan(deg, n, child_off, scan_tmp, s)) != PT_OK) { cleanup(); lca_release(h); return rc; }
   LCA_TRY(cudaMemsetAsync(deg, 0, n4, s));
   lca_fill_children_kernel<<<grid, 256, 0, s>>>(d_parent, n, child_off, deg, child_adj);
+  lca_sort_children_kernel<<<grid, 256, 0, s>>>(n, child_off, child_adj);
   int32_t info[8];
   LCA_TRY(cudaMemcpyAsync(info, small, 32, cudaMemcpyDeviceToHost, s));
   LCA_TRY(cudaStreamSynchronize(s));
@@ -606,7 +623,7 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
   LCA_TRY(cudaStreamSynchronize(s));
   LCA_TRY(cudaEventElapsedTime(&h->build_ms, ev0, ev1));
 #undef LCA_TRY
-  if (keep_size) h->size = size;
+  if (keep_size) { h->size = size; h->nodeat = nodeat; }
   cleanup();
   *out = h;
   return PT_OK;
@@ -1020,3 +1037,5 @@ extern "C" int pt_net_bridges(int64_t n, int64_t m, const int32_t* succ_off, con
   cleanup();
   return PT_OK;
 }
+
+#include "dp_kernels.cuh"

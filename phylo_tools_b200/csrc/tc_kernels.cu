@@ -876,7 +876,7 @@ struct pt_batch {
   static constexpr int kMaxChunks = 32;
   cudaStream_t copy_stream = nullptr;
   int nchunks = 1; int64_t chunk_end[kMaxChunks] = {}; cudaEvent_t chunk_ev[kMaxChunks] = {};
-  int32_t* d_chunk_ready = nullptr; cudaEvent_t flags_zeroed = nullptr;
+  int32_t* d_chunk_ready = nullptr; cudaEvent_t flags_zeroed = nullptr, upload_done = nullptr;
   int32_t* h_ctl = nullptr;  // pinned copy of the TcCtl of the last warp-path launch (watchdog / overflow), read at the next call
   bool ctl_pending = false;
   int64_t last_launches = 0;
@@ -887,10 +887,47 @@ struct pt_batch {
   cudaStream_t used_stream = nullptr; bool used_stream_valid = false;
 };
 
+// per-handle host resources that are expensive to create (cudaHostAlloc, cudaStreamCreate: tens of microseconds each, on the
+// end-to-end path once per batch): kept in process-wide free lists
+namespace {
+std::mutex g_res_mu;
+std::vector<int32_t*> g_free_ctl;                     // pinned 64-byte blocks
+std::vector<std::pair<int, cudaStream_t>> g_free_streams;  // (device, non-blocking stream)
+}
+static int32_t* take_pinned_ctl() {
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    if (!g_free_ctl.empty()) { int32_t* p = g_free_ctl.back(); g_free_ctl.pop_back(); return p; }
+  }
+  int32_t* p = nullptr;
+  if (cudaHostAlloc((void**)&p, 64, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+static void give_pinned_ctl(int32_t* p) { if (p) { std::lock_guard<std::mutex> lk(g_res_mu); g_free_ctl.push_back(p); } }
+static cudaStream_t take_copy_stream() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_res_mu);
+    for (size_t i = 0; i < g_free_streams.size(); ++i)
+      if (g_free_streams[i].first == dev) { cudaStream_t s = g_free_streams[i].second; g_free_streams.erase(g_free_streams.begin() + (long)i); return s; }
+  }
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return s;
+}
+static void give_copy_stream(cudaStream_t s) {
+  if (!s) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_res_mu);
+  g_free_streams.emplace_back(dev, s);
+}
+
 static void batch_release(pt_batch* b) {
   if (!b) return;
   if (b->used_stream_valid) cudaStreamSynchronize(b->used_stream);  // cached blocks may be handed to another handle at once
-  if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
+  if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); give_copy_stream(b->copy_stream); }
   if (b->owns_input) {
     dev_free(b->d_hnode_off); dev_free(b->d_harc_off); dev_free(b->d_gnode_off);
     dev_free(b->d_succ_off); dev_free(b->d_succ_adj); dev_free(b->d_hlabel); dev_free(b->d_tparent); dev_free(b->d_tlabel);
@@ -900,7 +937,8 @@ static void batch_release(pt_batch* b) {
   for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : b->chunk_ev) if (e) cudaEventDestroy(e);
   if (b->flags_zeroed) cudaEventDestroy(b->flags_zeroed);
-  if (b->h_ctl) cudaFreeHost(b->h_ctl);
+  if (b->upload_done) cudaEventDestroy(b->upload_done);
+  give_pinned_ctl(b->h_ctl);
   delete b;
 }
 
@@ -929,7 +967,7 @@ static int batch_scratch(pt_batch* b) {
       (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 256)) ||
       (rc = dev_alloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long))))
     return rc;
-  if (cudaHostAlloc((void**)&b->h_ctl, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); b->h_ctl = nullptr; return set_error(PT_ERR_NOMEM, "cudaHostAlloc failed"); }
+  if (!(b->h_ctl = take_pinned_ctl())) return set_error(PT_ERR_NOMEM, "cudaHostAlloc failed");
   memset(b->h_ctl, 0, 64);
   return PT_OK;
 }
@@ -1047,12 +1085,17 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
         (rc = dev_alloc(&b->d_hlabel, (size_t)std::max<int64_t>(NH, 1) * esz)) || (rc = dev_alloc(&b->d_tparent, (size_t)std::max<int64_t>(NG, 1) * esz)) ||
         (rc = dev_alloc(&b->d_tlabel, (size_t)std::max<int64_t>(NG, 1) * esz)))
       return fail(rc);
-    // equal chunks of at least 2048 instances: the persistent kernel starts on the first one while the others are in flight
-    b->nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, B / 2048));
+    // Chunks that double in size (1/32, 1/32, 1/16, ... 1/2 of the batch): the persistent kernel starts on a small first chunk
+    // and the copy engine stays ahead of the solver from then on (the upload is 3-4 times faster than the solve), with few
+    // API calls: their host time comes BEFORE the kernel launch and delays it.
+    b->nchunks = B >= 8192 ? 6 : 1;
     if (const char* e = getenv("PT_TC_CHUNKS")) b->nchunks = std::max(1, std::min((int)pt_batch::kMaxChunks, atoi(e)));  // tuning aid
     const int32_t* one = b->nchunks > 1 ? pinned_one() : nullptr;
-    if (b->nchunks > 1 && (!one || cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess)) { cudaGetLastError(); b->nchunks = 1; b->copy_stream = nullptr; }
+    if (b->nchunks > 1 && (!one || !(b->copy_stream = take_copy_stream()))) { b->nchunks = 1; b->copy_stream = nullptr; }
     cudaStream_t cs = b->nchunks > 1 ? b->copy_stream : s;
+    // which executor will run?  (the same test as pt_batch_contain; only the global-memory executors need one event per chunk)
+    const bool warp_path = b->maxN > 0 && b->maxN <= 30000 && b->maxM <= 30000 && b->maxNT <= 30000 && b->maxL <= 30000 &&
+                           TcWork<int16_t>::bytes(std::max(b->maxN, 1), std::max(b->maxM > 0 ? b->maxM : 2 * b->maxN, 1), std::max(b->maxNT, 1), std::max(b->maxL, 1)) <= (size_t)kMaxSmemPerBlock;
     if (b->nchunks > 1) {
       // the flags are zeroed on the copy stream before anything else happens there; `s` (and any other stream a later
       // pt_batch_contain uses) waits for that, so no kernel can see a stale "ready" left in the cached block
@@ -1063,8 +1106,13 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       if (e == cudaSuccess) e = cudaStreamWaitEvent(s, b->flags_zeroed, 0);
       if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: %s", cudaGetErrorString(e)));
     }
+    auto chunk_bound = [&](int k) -> int64_t {
+      if (k <= 0) return 0;
+      if (k >= b->nchunks) return B;
+      return (B >> (b->nchunks - k)) / 32 * 32;   // B/32, B/16, ..., B/2
+    };
     for (int c = 0; c < b->nchunks; ++c) {
-      const int64_t i0 = B * c / b->nchunks / 32 * 32, i1 = c + 1 == b->nchunks ? B : B * (c + 1) / b->nchunks / 32 * 32;
+      const int64_t i0 = chunk_bound(c), i1 = chunk_bound(c + 1);
       b->chunk_end[c] = i1;
       const int64_t h0 = d->host_node_off[i0], h1 = d->host_node_off[i1], a0 = d->host_arc_off[i0], a1 = d->host_arc_off[i1], g0 = d->guest_node_off[i0], g1 = d->guest_node_off[i1];
       auto cp = [&](void* dst, const void* src, int64_t from, int64_t to) -> cudaError_t {
@@ -1079,10 +1127,14 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       if (e == cudaSuccess) e = cp(b->d_tlabel, d->guest_label, g0, g1);
       if (e == cudaSuccess && b->nchunks > 1) {
         e = cudaMemcpyAsync(b->d_chunk_ready + c, one, 4, cudaMemcpyHostToDevice, cs);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->chunk_ev[c], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventRecord(b->chunk_ev[c], cs);
+        if (e == cudaSuccess && !warp_path) { e = cudaEventCreateWithFlags(&b->chunk_ev[c], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventRecord(b->chunk_ev[c], cs); }
       }
       if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: upload failed: %s", cudaGetErrorString(e)));
+    }
+    if (b->nchunks > 1) {  // for an executor that was not expected here (pt_options.path): everything has landed
+      cudaError_t e = cudaEventCreateWithFlags(&b->upload_done, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventRecord(b->upload_done, cs);
+      if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: %s", cudaGetErrorString(e)));
     }
   } else {
     b->d_hnode_off = (int64_t*)d->host_node_off; b->d_harc_off = (int64_t*)d->host_arc_off; b->d_gnode_off = (int64_t*)d->guest_node_off;
@@ -1319,8 +1371,11 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
         for (int j = 0; j < 2; ++j) if (!b->ev[2 * round + j]) PT_CUDA(cudaEventCreate(&b->ev[2 * round + j]));
         PT_CUDA(cudaEventRecord(b->ev[2 * round], s));
       }
-      // round 0 of a HOST batch: one launch per upload chunk, each waiting only for its own bytes
-      const int launches = (round == 0) ? b->nchunks : 1;
+      // round 0 of a HOST batch: one launch per upload chunk, each waiting only for its own bytes (if the handle was created
+      // expecting the warp executor there are no per-chunk events: wait for the whole upload, one launch)
+      const bool per_chunk = b->nchunks > 1 && b->chunk_ev[0] != nullptr;
+      if (round == 0 && b->nchunks > 1 && !per_chunk && b->upload_done) PT_CUDA(cudaStreamWaitEvent(s, b->upload_done, 0));
+      const int launches = (round == 0 && per_chunk) ? b->nchunks : 1;
       for (int c = 0; c < launches; ++c) {
         int32_t* ticket = b->d_ticket;
         if (round == 0) {

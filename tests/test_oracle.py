@@ -129,3 +129,92 @@ def test_highest_displayed_restatement(oracle):
     assert oracle.highest_displayed([-1, 0, 1, 2, 3], [9, 8, 0, 6, 5], 0).tolist() == [0, 0, 0, 2, 2]
     # parent not displayed: stay (node 2); node 1 still climbs to the displayed root
     assert oracle.highest_displayed([-1, 0, 1, 2, 3], [9, -1, 7, 6, 5], 0).tolist() == [0, 0, 2, 2, 2]
+
+
+# ---- the general tree-in-tree DP (multi-labelled hosts), unzip_retis and highest_displayed_ancestor on network hosts ----------
+def _net_arrays(O, host_nw, guest_nw):
+    """(succ_off, succ_adj, label) of the host network (children in reverse edge order like the reference's immutable storage),
+    guest parent / label arrays, shared dense label ids"""
+    from oracle.newick import parse_newick
+    names = {}
+    n, e, lab = parse_newick(host_nw)
+    kids = [[] for _ in range(n)]
+    for a, b in e:
+        kids[a].insert(0, b)
+    off = np.zeros(n + 1, dtype=np.int32)
+    for v in range(n):
+        off[v + 1] = off[v] + len(kids[v])
+    adj = np.array([c for v in range(n) for c in kids[v]], dtype=np.int32)
+    hl = np.full(n, -1, dtype=np.int32)
+    for v, s in lab.items():
+        if s != "":
+            hl[v] = names.setdefault(s, len(names))
+    nt, et, labt = parse_newick(guest_nw)
+    gp = np.full(nt, -1, dtype=np.int32)
+    for a, b in et:
+        gp[b] = a
+    gl = np.full(nt, -1, dtype=np.int32)
+    for v, s in labt.items():
+        if s != "":
+            gl[v] = names.setdefault(s, len(names))
+    return off, adj, hl, gp, gl, names
+
+
+def _canon(parent, label):
+    """canonical form of a leaf-labelled rooted tree (child order forgotten)"""
+    n = len(parent)
+    kids = [[] for _ in range(n)]
+    root = 0
+    for v, p in enumerate(parent):
+        if p < 0:
+            root = v
+        else:
+            kids[p].append(v)
+
+    def rec(v):
+        if not kids[v]:
+            return ("L", label[v])
+        return ("N",) + tuple(sorted((rec(c) for c in kids[v]), key=repr))
+    import sys
+    sys.setrecursionlimit(100000)
+    return rec(root)
+
+
+def test_mul_who_displays_oracle_equals_reference(oracle):
+    """the definition-based restatement (orc_mul_who_displays) against the reference's own lists on multi-labelled hosts
+    (tests/golden/whomul_ref.json, data/test_tree.nw first); the reference sorts by its own preorder: compared as sets"""
+    from conftest import load_golden
+    gold = load_golden("whomul_ref.json")
+    checked = nonempty = 0
+    for it in gold["items"]:
+        if it["reference"] == "CRASH":
+            continue
+        hp, hl, gp, gl = oracle.tree_arrays_from_newick(it["host"], it["guest"])
+        off, adj = oracle.mul_who_displays(hp, hl, gp, gl)
+        for u, ref in enumerate(it["reference"]):
+            assert sorted(adj[off[u]:off[u + 1]].tolist()) == sorted(ref), (it["host"], it["guest"], u)
+            nonempty += len(ref) > 1
+        checked += 1
+    assert checked >= 150 and nonempty >= 100   # lists with several entries: the multi-labelled case is really exercised
+
+
+def test_unzip_and_hda_oracle_equal_reference(oracle):
+    """orc_unzip + orc_mul_who_displays + orc_highest_displayed_lists against the reference's TreeInComponent at the host's root
+    (tests/golden/hda_ref.json): the unzipped MUL-tree up to child order, and highest_displayed_ancestor of every guest node"""
+    from conftest import load_golden
+    gold = load_golden("hda_ref.json")
+    checked = 0
+    for it in gold["items"]:
+        if it.get("reference") == "CRASH":
+            continue
+        off, adj, hl, gp, gl, names = _net_arrays(oracle, it["host"], it["guest"])
+        par, lab, org = oracle.unzip(off, adj, hl, 0)
+        inv = {v: k for k, v in names.items()}
+        assert len(par) == len(it["mul_parent"])
+        assert _canon(par.tolist(), [inv.get(int(x), "-") for x in lab]) == _canon(it["mul_parent"], it["mul_label"]), it["host"]
+        woff, wadj = oracle.mul_who_displays(par, lab, gp, gl)
+        hda = oracle.highest_displayed_lists(gp, woff, wadj, 0)
+        for v, want in it["hda"].items():
+            assert int(hda[int(v)]) == want, (it["host"], it["guest"], v, int(hda[int(v)]), want)
+        checked += 1
+    assert checked >= 150
