@@ -382,6 +382,11 @@ int pt_enum_switchings(int32_t n, int32_t m, const int32_t* succ_off, const int3
 int pt_parse_newick(const char* text, int64_t* num_nodes, int64_t* num_edges, int32_t* edges /* 2*num_edges */,
                     int64_t* num_labels, int32_t* label_node, char* label_buf, int64_t* label_buf_len);
 
+/* parse_edgelist  io/edgelist.hpp:41-86 : white-space separated name pairs, one arc per line; node ids by first appearance; EVERY
+ * node is labelled with its name.  Same two-call protocol and outputs as pt_parse_newick; MalformedEdgeVec -> PT_ERR_PARSE. */
+int pt_parse_edgelist(const char* text, int64_t* num_nodes, int64_t* num_edges, int32_t* edges /* 2*num_edges */,
+                      int64_t* num_labels, int32_t* label_node, char* label_buf, int64_t* label_buf_len);
+
 /* Opaque packer: accumulates (host newick, guest newick) pairs into the flat layout of pt_batch_desc. */
 typedef struct pt_packer pt_packer;
 int pt_packer_create(pt_packer** out);

@@ -155,7 +155,41 @@ def make_comps():
     print("comps_ref.json:", len(items), "networks,", crashed, "reference crashes,", sum(len(it.get("dag", [])) for it in items), "component-DAG arcs")
 
 
+
+
+def make_edgelist():
+    """edge-list texts -> (num_nodes, edges, labels) of the REFERENCE's parse_edgelist (io/edgelist.hpp:41-86, via `ref_tc parse_el`),
+    malformed texts included ("ERR" = MalformedEdgeVec)"""
+    texts = ["a b\na c\nb d\nb e\n", "root x\nroot y\nx l1\nx r\ny r\nr l2\n", "1 2\n2 3\n3 4\n", "a\tb\nb\tc\n", "u v\n", "a b\nc d\nb c\n",
+             "a  b\n a c\n", "a b", "a b\n\n\nb c\n", "a b c\n", "a\n", "", "x y \nz w\n", "n1 n2\nn1 n3\nn2 n4\nn3 n4\nn4 n5\n"]
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        n = int(rng.integers(4, 30))
+        lines = []
+        for v in range(1, n):
+            lines.append("v%d v%d" % (int(rng.integers(0, v)), v))
+        rng.shuffle(lines)
+        texts.append("\n".join(lines) + "\n")
+    items = []
+    for t in texts:
+        with tempfile.NamedTemporaryFile("w", suffix=".el", delete=False) as f:
+            f.write(t)
+        out = subprocess.run([REF_TC, "parse_el", f.name], capture_output=True, text=True)
+        os.unlink(f.name)
+        b = out.stdout.split("--\n")[0].strip("\n").split("\n")
+        if out.returncode != 0 or not b or b[0] == "ERR" or b[0] == "":
+            items.append(dict(text=t, reference="ERR" if out.returncode == 0 else "CRASH"))
+            continue
+        n, m = map(int, b[0].split())
+        edges = [list(map(int, x.split())) for x in b[1:1 + m]]
+        labels = {x.split(" ", 2)[1]: x.split(" ", 2)[2] for x in b[1 + m:]}
+        items.append(dict(text=t, num_nodes=n, edges=edges, labels=labels))
+    json.dump(dict(source="oracle/_ref/ref_tc parse_el (reference io/edgelist.hpp parse_edgelist)", items=items), open(os.path.join(GOLD, "edgelist_ref.json"), "w"), indent=0)
+    print("edgelist_ref.json:", len(items), "texts,", sum(1 for it in items if "reference" in it), "malformed / crashed")
+
+
 if __name__ == "__main__":
     make_whomul()
     make_hda()
     make_comps()
+    make_edgelist()

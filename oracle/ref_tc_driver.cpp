@@ -22,6 +22,8 @@
 //        template instantiation naming the member (legal C++; nothing of the reference is modified)
 //   ref_tc comps <file> : per network line: per node "v comp_root visible_leaf" (-1 = NoNode) of TreeComponentInfos
 //        (utils/tree_components.hpp:41-234), then the arcs of its component DAG "D u v", then "--"
+//   ref_tc parse_el <file> : the whole file as ONE edge list through the reference's parse_edgelist (io/edgelist.hpp:41-86): same output
+//        format as `parse` ("ERR" for MalformedEdgeVec)
 //   ref_tc parse <file> : for each line: "n m" then edges "u v" in reference edge-list order, then
 //        labels "id name" sorted by id, then "--" (golden vectors for the Newick reader).
 #include "io/io.hpp"
@@ -138,6 +140,19 @@ static std::vector<std::string> read_lines(const char* fn) {
 int main(int argc, char** argv) {
   if (argc < 3) { fprintf(stderr, "usage: ref_tc verdicts|bench|parse <file> [max]\n"); return 1; }
   std::string mode = argv[1];
+  if (mode == "parse_el") {
+    std::ifstream in(argv[2]);
+    ENL e;
+    try { e.num_nodes = parse_edgelist(in, e.edges, *e.labels); } catch (std::exception& ex) { printf("ERR\n--\n"); return 0; }
+    printf("%zu %zu\n", e.num_nodes, e.edges.size());
+    for (auto& ed : e.edges) printf("%zu %zu\n", (size_t)ed.tail(), (size_t)ed.head());
+    std::vector<std::pair<size_t, std::string>> labs;
+    for (auto&& p : *e.labels) if (!p.second.empty()) labs.emplace_back((size_t)p.first, p.second);
+    std::sort(labs.begin(), labs.end());
+    for (auto& p : labs) printf("L %zu %s\n", p.first, p.second.c_str());
+    printf("--\n");
+    return 0;
+  }
   std::vector<std::string> L = read_lines(argv[2]);
   if (mode == "parse") {
     std::cout.setstate(std::ios::badbit);

@@ -70,6 +70,26 @@ def parse_newick(text):
     return n.value, [(edges[2 * i], edges[2 * i + 1]) for i in range(m.value)], {nodes[i]: names[i].decode() for i in range(nl.value)}
 
 
+class MalformedEdgeVec(ValueError):
+    """io/edgelist.hpp:10-15"""
+
+
+def parse_edgelist(text):
+    """parse_edgelist (io/edgelist.hpp:77-86) -> (num_nodes, edges[(tail, head)], {node: label}); every node carries its name"""
+    s = text.encode()
+    n, m, nl, bl = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(0)
+    rc = _L.pt_parse_edgelist(s, C.byref(n), C.byref(m), None, C.byref(nl), None, None, C.byref(bl))
+    if rc == _capi.PT_ERR_PARSE:
+        raise MalformedEdgeVec((_L.pt_last_error() or b"").decode(errors="replace"))
+    _check(rc, "pt_parse_edgelist")
+    edges = (C.c_int32 * max(1, 2 * m.value))()
+    nodes = (C.c_int32 * max(1, nl.value))()
+    buf = C.create_string_buffer(max(1, bl.value))
+    _check(_L.pt_parse_edgelist(s, C.byref(n), C.byref(m), edges, C.byref(nl), nodes, buf, C.byref(bl)), "pt_parse_edgelist")
+    names = buf.raw[:bl.value].split(b"\0")[:-1] if bl.value else []
+    return n.value, [(edges[2 * i], edges[2 * i + 1]) for i in range(m.value)], {nodes[i]: names[i].decode() for i in range(nl.value)}
+
+
 def random_tree(num_leaves, seed):
     """parent array (int32, 2*num_leaves-1 entries) of a random rooted binary tree"""
     out = np.empty(2 * num_leaves - 1, dtype=np.int32)

@@ -10,6 +10,8 @@
 #include "../include/pt/newick.hpp"
 #include "../include/pt/fast_newick.hpp"
 #include "../include/pt/packer.hpp"
+#include "../include/pt/io.hpp"
+#include <sstream>
 #include "pt_error.h"
 
 namespace ptgpu {
@@ -45,6 +47,31 @@ int pt_parse_newick(const char* text, int64_t* num_nodes, int64_t* num_edges, in
     }
     return PT_OK;
   } catch (const PT::MalformedNewick& e) { return set_error(PT_ERR_PARSE, "MalformedNewick: %s", e.what());
+  } catch (const std::bad_alloc&) { return set_error(PT_ERR_NOMEM, "out of host memory");
+  } catch (const std::exception& e) { return set_error(PT_ERR_INVALID, "%s", e.what()); }
+}
+
+int pt_parse_edgelist(const char* text, int64_t* num_nodes, int64_t* num_edges, int32_t* edges, int64_t* num_labels,
+                      int32_t* label_node, char* label_buf, int64_t* label_buf_len) {
+  if (!text || !num_nodes || !num_edges) return set_error(PT_ERR_INVALID, "pt_parse_edgelist: null argument");
+  try {
+    PT::EdgeVec el; std::vector<std::string> names;
+    std::istringstream in{std::string(text)};
+    const size_t n = PT::parse_edgelist(in, el, names);
+    *num_nodes = (int64_t)n; *num_edges = (int64_t)el.size();
+    int64_t nl = 0, bytes = 0;
+    for (size_t v = 0; v < names.size(); ++v) if (!names[v].empty()) { ++nl; bytes += (int64_t)names[v].size() + 1; }
+    if (num_labels) *num_labels = nl;
+    const int64_t cap = label_buf_len ? *label_buf_len : 0;
+    if (label_buf_len) *label_buf_len = bytes;
+    if (edges) for (size_t e = 0; e < el.size(); ++e) { edges[2 * e] = (int32_t)el[e].tail(); edges[2 * e + 1] = (int32_t)el[e].head(); }
+    if (label_node && label_buf) {
+      if (cap < bytes) return set_error(PT_ERR_INVALID, "pt_parse_edgelist: label buffer too small (%lld < %lld)", (long long)cap, (long long)bytes);
+      int64_t k = 0, off = 0;
+      for (size_t v = 0; v < names.size(); ++v) if (!names[v].empty()) { label_node[k++] = (int32_t)v; memcpy(label_buf + off, names[v].c_str(), names[v].size() + 1); off += (int64_t)names[v].size() + 1; }
+    }
+    return PT_OK;
+  } catch (const PT::MalformedEdgeVec& e) { return set_error(PT_ERR_PARSE, "MalformedEdgeVec: %s", e.what());
   } catch (const std::bad_alloc&) { return set_error(PT_ERR_NOMEM, "out of host memory");
   } catch (const std::exception& e) { return set_error(PT_ERR_INVALID, "%s", e.what()); }
 }

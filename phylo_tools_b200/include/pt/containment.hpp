@@ -7,12 +7,16 @@
 //   TreeInTreeContainment<Host,Guest>(host, guest)  :50-54, .displayed() :83
 // plus BatchContainment, the batched form the reference lacks: the engine's unit of work is a BATCH of instances
 // (one warp per instance), so single-instance calls are batches of one.
-//   TreeInTreeContainment::who_displays(u)          :72-81 (single-labelled tree hosts; all guest nodes in one GPU pass)
+//   TreeInTreeContainment::who_displays(u)          :72-81 (multi-labelled tree hosts included; all guest nodes in one GPU pass)
+//   TreeInComponent(host, guest, label_match, u).highest_displayed_ancestor(v)   :241-347
+//   TreeComponentInfos(N)                           utils/tree_components.hpp:41-234
 //
 // Errors follow the reference: duplicate labels and malformed graphs throw std::logic_error
 // (utils/label_matching.hpp:51-52, utils/storage_adj_common.hpp:103-109); engine failures throw std::runtime_error.
 // There is no CPU fallback: without a CUDA device displayed() throws.
 #pragma once
+#include <algorithm>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -149,46 +153,163 @@ class TreeInNetContainment {
 template <class Host, class Guest> TreeInNetContainment(const Host&, const Guest&) -> TreeInNetContainment<Host, Guest>;
 template <class Host, class Guest> TreeInNetContainment(Host&&, Guest&&) -> TreeInNetContainment<std::decay_t<Host>, std::decay_t<Guest>>;
 
-// a tree host is a network without reticulations: same engine (the true-cherry rule alone decides it).
-// who_displays(u) (containment.hpp:72-81): host nodes that minimally display the guest subtree below u, sorted by host
-// preorder -- for a single-labelled host at most one node.  Computed for all guest nodes at once (pt_tree_who_displays).
-template <class Host, class Guest>
-class TreeInTreeContainment : public TreeInNetContainment<Host, Guest> {
-  std::vector<int32_t> table_, hda_;
-  void fill_table() {
-    const Host& H = this->host(); const Guest& G = this->guest();
+// ---- vocabulary of the tree-in-tree DP (utils/induced_tree.hpp:11-35, utils/label_matching.hpp:23-82) ---------------------------
+struct InducedSubtreeInfo { size_t dist_to_root = 0, order_number = 0; InducedSubtreeInfo(size_t d = 0, size_t o = 0) : dist_to_root(d), order_number(o) {} };
+template <class Tree> using InducedSubtreeInfoMap = std::unordered_map<Node, InducedSubtreeInfo>;
+// label -> (host nodes, guest nodes)
+using LabelMatchingMap = std::unordered_map<std::string, std::pair<std::vector<Node>, std::vector<Node>>>;
+
+// shared by the checkers below: the flat arrays of a host / guest pair with one label dictionary
+struct DpArrays {
+  std::vector<int32_t> hp, hl, gp, gl;
+  template <class Host, class Guest>
+  DpArrays(const Host& H, const Guest& G) : hp(H.parent_array()), hl(H.num_nodes()), gp(G.parent_array()), gl(G.num_nodes()) {
     std::unordered_map<std::string, int32_t> dict;
     auto id_of = [&](const std::string& s) -> int32_t { if (s.empty()) return -1; auto it = dict.find(s); if (it != dict.end()) return it->second; const int32_t id = (int32_t)dict.size(); dict.emplace(s, id); return id; };
-    std::vector<int32_t> hp = H.parent_array(), gp = G.parent_array(), hl(H.num_nodes()), gl(G.num_nodes());
     for (Node v = 0; v < H.num_nodes(); ++v) hl[v] = id_of(H.label(v));
     for (Node v = 0; v < G.num_nodes(); ++v) gl[v] = id_of(G.label(v));
-    table_.assign(G.num_nodes(), -1);
-    throw_status(pt_tree_who_displays(hp.data(), hl.data(), (int64_t)hp.size(), gp.data(), gl.data(), (int64_t)gp.size(), table_.data(), PT_MEM_HOST, nullptr),
-                 "pt_tree_who_displays");
+  }
+};
+
+// TreeInTreeContainment (utils/containment.hpp:27-233): the host may be MULTI-LABELLED (the reference's ROMulTree: the label map
+// may give the same name to several leaves); the guest is a single-labelled tree.  who_displays(u) (:72-81) = the host nodes that
+// minimally display the guest subtree below u, sorted by host preorder; the whole table is computed by ONE pass of the GPU DP
+// (pt_who_build) at the first question.  displayed() (:83) = the root's list is not empty.
+// The 5-argument constructor of the reference (:50-54) is kept: node infos that are handed in empty are filled (make_node_infos,
+// induced_tree.hpp:54-59: depth and preorder number of every host node), a label matching is accepted and not needed.
+template <class Host, class Guest>
+class TreeInTreeContainment {
+ public:
+  using NodeList = std::vector<Node>;
+  using NodeInfos = InducedSubtreeInfoMap<Host>;
+  using LabelMatching = LabelMatchingMap;
+
+ private:
+  Host host_;
+  Guest guest_;
+  std::shared_ptr<NodeInfos> node_infos_;
+  std::vector<NodeList> table_;
+  std::vector<int32_t> hda_;
+  bool have_ = false;
+
+  void fill_table() {
+    const DpArrays a(host_, guest_);
+    pt_who* h = nullptr;
+    throw_status(pt_who_build(&h, a.hp.data(), a.hl.data(), (int64_t)a.hp.size(), a.gp.data(), a.gl.data(), (int64_t)a.gp.size(), PT_MEM_HOST, nullptr), "pt_who_build");
+    int64_t total = 0;
+    pt_who_total(h, &total);
+    std::vector<int32_t> off(a.gp.size() + 1), adj((size_t)std::max<int64_t>(total, 1));
+    int rc = pt_who_lists(h, off.data(), adj.data(), PT_MEM_HOST, nullptr);
+    hda_.assign(a.gp.size(), -1);
+    if (rc == PT_OK) rc = pt_who_highest_displayed(h, (int32_t)host_.root(), hda_.data(), PT_MEM_HOST, nullptr);
+    pt_who_free(h);
+    throw_status(rc, "pt_who_lists");
+    table_.assign(a.gp.size(), NodeList());
+    for (size_t u = 0; u < a.gp.size(); ++u) table_[u].assign(adj.begin() + off[u], adj.begin() + off[u + 1]);
+    have_ = true;
+  }
+  void fill_node_infos() {
+    if (!node_infos_ || !node_infos_->empty()) return;
+    pt_lca* L = nullptr;
+    const std::vector<int32_t> hp = host_.parent_array();
+    throw_status(pt_lca_build(&L, hp.data(), (int64_t)hp.size(), PT_MEM_HOST, nullptr), "pt_lca_build");
+    std::vector<int32_t> d(hp.size()), o(hp.size());
+    const int rc = pt_lca_node_info(L, d.data(), o.data(), PT_MEM_HOST, nullptr);
+    pt_lca_free(L);
+    throw_status(rc, "pt_lca_node_info");
+    for (size_t v = 0; v < hp.size(); ++v) node_infos_->emplace((Node)v, InducedSubtreeInfo((size_t)d[v], (size_t)o[v]));
   }
 
  public:
-  using TreeInNetContainment<Host, Guest>::TreeInNetContainment;
-  std::vector<Node> who_displays(const Node u) {
-    if (table_.empty()) fill_table();
-    std::vector<Node> r;
-    if (table_.at(u) >= 0) r.push_back((Node)table_[u]);
-    return r;
-  }
-  // TreeInComponent::highest_displayed_ancestor(v) (containment.hpp:328-344) with this host as the component: the highest
-  // ancestor of v the climb reaches; all guest nodes are answered by one pt_tree_highest_displayed call and cached
-  Node highest_displayed_ancestor(const Node v) {
-    if (table_.empty()) fill_table();
-    if (hda_.empty()) {
-      const std::vector<int32_t> gp = this->guest().parent_array();
-      hda_.assign(gp.size(), -1);
-      throw_status(pt_tree_highest_displayed(gp.data(), table_.data(), (int64_t)gp.size(), (int32_t)this->host().root(), hda_.data(), PT_MEM_HOST, nullptr),
-                   "pt_tree_highest_displayed");
-    }
-    return (Node)hda_.at(v);
-  }
+  TreeInTreeContainment(const Host& H, const Guest& G, std::shared_ptr<NodeInfos> node_infos = {}, std::shared_ptr<LabelMatching> = {}, const bool = false)
+      : host_(H), guest_(G), node_infos_(std::move(node_infos)) { fill_node_infos(); }
+  TreeInTreeContainment(Host&& H, Guest&& G) : host_(std::move(H)), guest_(std::move(G)) {}
+
+  const NodeList& who_displays(const Node u) { if (!have_) fill_table(); return table_.at(u); }
+  bool displayed() { return !who_displays(guest_.root()).empty(); }
+  // TreeInComponent::highest_displayed_ancestor(v) (:328-344) with this host as the component
+  Node highest_displayed_ancestor(const Node v) { if (!have_) fill_table(); return (Node)hda_.at(v); }
+  const Host& host() const { return host_; }
+  const Guest& guest() const { return guest_; }
 };
 template <class Host, class Guest> TreeInTreeContainment(const Host&, const Guest&) -> TreeInTreeContainment<Host, Guest>;
 template <class Host, class Guest> TreeInTreeContainment(Host&&, Guest&&) -> TreeInTreeContainment<std::decay_t<Host>, std::decay_t<Guest>>;
+
+// TreeInComponent (utils/containment.hpp:241-347): the part of a host NETWORK below node u is unfolded into a multi-labelled tree
+// (unzip_retis :262-312 -> pt_net_unzip) and the tree-in-tree DP answers, for a guest node v, the highest ancestor of v that this
+// component still displays (:328-344).  subtree() / origin() expose the unfolding: node 0 is u, ids are a preorder.
+template <class MulSubtree, class Guest, bool leaf_labels_only = true>
+class TreeInComponent {
+  MulSubtree subtree_;
+  std::vector<Node> origin_;
+  TreeInTreeContainment<MulSubtree, Guest> display_;
+
+  template <class Host>
+  static MulSubtree unzip(const Host& host, const Node u, std::vector<Node>& origin) {
+    std::unordered_map<std::string, int32_t> dict; std::vector<std::string> names;
+    std::vector<int32_t> lab(host.num_nodes(), -1);
+    for (Node v = 0; v < host.num_nodes(); ++v) {
+      const std::string& s = host.label(v);
+      if (s.empty() || (leaf_labels_only && !host.is_leaf(v))) continue;
+      auto it = dict.find(s);
+      if (it == dict.end()) { it = dict.emplace(s, (int32_t)names.size()).first; names.push_back(s); }
+      lab[v] = it->second;
+    }
+    int64_t count = 0;
+    const int64_t m = (int64_t)host.num_edges();
+    throw_status(pt_net_unzip((int64_t)host.num_nodes(), m, host.succ_off().data(), host.succ_adj().data(), lab.data(), (int32_t)u, nullptr, nullptr, nullptr, 0, &count, PT_MEM_HOST, nullptr), "pt_net_unzip");
+    std::vector<int32_t> par((size_t)count), ol((size_t)count), org((size_t)count);
+    throw_status(pt_net_unzip((int64_t)host.num_nodes(), m, host.succ_off().data(), host.succ_adj().data(), lab.data(), (int32_t)u, par.data(), ol.data(), org.data(), count, &count, PT_MEM_HOST, nullptr), "pt_net_unzip");
+    EdgeVec edges; typename MulSubtree::LabelMap labels;
+    // children in reverse order, so that the immutable storage (which reverses once more) keeps the unfolding's child order
+    for (size_t v = (size_t)count; v-- > 1;) edges.emplace_back((Node)par[v], (Node)v);
+    for (size_t v = 0; v < (size_t)count; ++v) if (ol[v] >= 0) labels.emplace((Node)v, names[(size_t)ol[v]]);
+    origin.assign(org.begin(), org.end());
+    return MulSubtree(edges, labels, consecutive_tag(), (size_t)count);
+  }
+
+ public:
+  template <class Host, class HG_Label_Matching>
+  TreeInComponent(const Host& host, const Guest& guest, const HG_Label_Matching&, const Node u) : subtree_(unzip(host, u, origin_)), display_(subtree_, guest) {}
+  template <class Host>
+  TreeInComponent(const Host& host, const Guest& guest, const Node u) : subtree_(unzip(host, u, origin_)), display_(subtree_, guest) {}
+
+  Node highest_displayed_ancestor(const Node v) { return display_.highest_displayed_ancestor(v); }
+  const std::vector<Node>& who_displays(const Node u) { return display_.who_displays(u); }
+  const MulSubtree& subtree() const { return subtree_; }
+  Node origin(const Node copy) const { return origin_.at(copy); }
+};
+
+// TreeComponentInfos (utils/tree_components.hpp:41-234) of a fresh network: comp_root / visible_leaf per node (NoNode where the
+// reference leaves it unset) and the component DAG as an edge list (root above, root below), computed by pt_net_tree_components
+struct ComponentData { Node comp_root = NoNode; Node visible_leaf = NoNode; };
+template <class Network>
+class TreeComponentInfos {
+  std::vector<ComponentData> data_;
+  EdgeVec dag_;
+
+ public:
+  explicit TreeComponentInfos(const Network& N) {
+    const int64_t n = (int64_t)N.num_nodes(), m = (int64_t)N.num_edges();
+    std::vector<int32_t> comp((size_t)n), vis((size_t)n);
+    std::vector<int64_t> e((size_t)std::max<int64_t>(4 * m, 16));
+    int64_t cnt = 0;
+    throw_status(pt_net_tree_components(n, m, N.succ_off().data(), N.succ_adj().data(), comp.data(), vis.data(), e.data(), (int64_t)e.size(), &cnt, PT_MEM_HOST, nullptr), "pt_net_tree_components");
+    if (cnt > (int64_t)e.size()) {
+      e.assign((size_t)cnt, 0);
+      throw_status(pt_net_tree_components(n, m, N.succ_off().data(), N.succ_adj().data(), comp.data(), vis.data(), e.data(), (int64_t)e.size(), &cnt, PT_MEM_HOST, nullptr), "pt_net_tree_components");
+    }
+    e.resize((size_t)cnt);
+    std::sort(e.begin(), e.end());
+    e.erase(std::unique(e.begin(), e.end()), e.end());
+    for (const int64_t x : e) dag_.emplace_back((Node)(x >> 32), (Node)(x & 0xffffffff));
+    data_.resize((size_t)n);
+    for (int64_t v = 0; v < n; ++v) { data_[(size_t)v].comp_root = comp[(size_t)v] < 0 ? NoNode : (Node)comp[(size_t)v]; data_[(size_t)v].visible_leaf = vis[(size_t)v] < 0 ? NoNode : (Node)vis[(size_t)v]; }
+  }
+  const ComponentData& operator[](const Node v) const { return data_.at(v); }
+  Node comp_root(const Node v) const { return data_.at(v).comp_root; }
+  Node visible_leaf(const Node v) const { return data_.at(v).visible_leaf; }
+  const EdgeVec& comp_DAG_edges() const { return dag_; }
+};
 
 }  // namespace PT

@@ -3,6 +3,7 @@
 //   lca<node_t>::lca(root), query()   rmq/lca.hpp:79-106
 // plus the batched query the engine is built for.
 #pragma once
+#include <iterator>
 #include <stdexcept>
 #include <vector>
 #include "../../../include/pt_gpu.h"
@@ -35,5 +36,39 @@ class LCAOracle {
   pt_lca_info info() const { pt_lca_info i{}; throw_status(pt_lca_get_info(h_, &i), "pt_lca_get_info"); return i; }
   const pt_lca* handle() const { return h_; }
 };
+
+// the reference's class names (rmq/lca.hpp:28-107, rmq/rmq.hpp:17-75, rmq/sparse_rmq.hpp:19-91) over the same engine
+//   lca<Tree> L(T);  L.query(u, v) -> Node                         (rmq/lca.hpp:79, :91)
+//   sparse_rmq<It> R(begin, end);  R.query(u, v) -> It,  R.query_offset(u, v) -> index of the RIGHTMOST minimum of [u, v)   (rmq/rmq.hpp:63-72)
+template <class Tree>
+class lca {
+  LCAOracle o_;
+ public:
+  explicit lca(const Tree& T, size_t = 0) : o_(T) {}
+  Node query(Node u, Node v) const { return o_.query(u, v); }
+};
+template <class It>
+class rmq {
+ protected:
+  It begin_;
+  pt_rmq* h_ = nullptr;
+ public:
+  rmq(It b, It e) : begin_(b) {
+    std::vector<int32_t> v;
+    for (It i = b; i != e; ++i) v.push_back((int32_t)*i);
+    throw_status(pt_rmq_build(&h_, v.data(), (int64_t)v.size(), PT_MEM_HOST, nullptr), "pt_rmq_build");
+  }
+  rmq(const rmq&) = delete;
+  ~rmq() { pt_rmq_free(h_); }
+  size_t query_offset(size_t u, size_t v) const { const int64_t l = (int64_t)u, r = (int64_t)v; int64_t o = -1; throw_status(pt_rmq_query(h_, &l, &r, &o, 1, PT_MEM_HOST, nullptr), "pt_rmq_query"); return (size_t)o; }
+  It query(size_t u, size_t v) const { It i = begin_; std::advance(i, (long)query_offset(u, v)); return i; }
+};
+template <class It> using sparse_rmq = rmq<It>;
+template <class It> using pm_rmq = rmq<It>;
+
+// Tree::LCA(x, y) / naiveLCA (utils/tree.hpp:202-223) as a call on the tree: LCA(T, x, y); the structure is built per call, so
+// use LCAOracle (or lca<Tree>) for more than a handful of queries on the same tree
+template <class Tree> Node LCA(const Tree& T, Node x, Node y) { return LCAOracle(T).query(x, y); }
+template <class Tree> Node naiveLCA(const Tree& T, Node x, Node y) { return LCAOracle(T).query(x, y); }
 
 }  // namespace PT

@@ -107,6 +107,42 @@ int main(int argc, char** argv) {
     for (Node u = 0; u < 7; ++u) assert(c.highest_displayed_ancestor(u) == (Node)hda[u]);
     assert(!c.displayed());
   }
+  // multi-labelled host: data/test_tree.nw of the reference; the lists printed by the reference itself (tests/golden/whomul_ref.json item 0)
+  {
+    EdgeVec he, ge; LabelMapDefault hl, gl;
+    const size_t hn = parse_newick(std::string("((((a,b),(c,d)),(e,d)),((a,b),(e,d)));"), he, hl), gn = parse_newick(std::string("(e,((a,c),(b,d)));"), ge, gl);
+    using MulTree = ROTree<>;   // the facade's label map may repeat a name: the reference's ROMulTree
+    MulTree H(he, hl, consecutive_tag(), hn); MyTree G(ge, gl, consecutive_tag(), gn);
+    auto infos = std::make_shared<TreeInTreeContainment<MulTree, MyTree>::NodeInfos>();
+    TreeInTreeContainment<MulTree, MyTree> c(H, G, infos);       // the reference's 5-argument constructor (containment.hpp:50-54), defaults for the rest
+    assert(infos->size() == hn && infos->at(H.root()).dist_to_root == 0 && infos->at(H.root()).order_number == 0);
+    const std::vector<std::vector<Node>> exp = {{}, {0}, {1, 12}, {3, 10, 14}, {6, 17}, {12}, {15}, {7, 18}, {4, 11}};
+    for (Node u = 0; u < gn; ++u) { std::vector<Node> w = c.who_displays(u); std::sort(w.begin(), w.end()); assert(w == exp[u]); }
+    for (Node u = 0; u < gn; ++u) { const auto& w = c.who_displays(u); for (size_t k = 1; k < w.size(); ++k) assert(infos->at(w[k - 1]).order_number < infos->at(w[k]).order_number); }
+    assert(!c.displayed());
+  }
+  // TreeInComponent (containment.hpp:241-347) at the root of data/test.nw: the unfolding has 11 nodes and highest_displayed_ancestor is what
+  // the reference prints (tests/golden/hda_ref.json item 0); TreeComponentInfos of the same network (comps_ref.json item 0)
+  {
+    EdgeVec he, ge; LabelMapDefault hl, gl;
+    const size_t hn = parse_newick(std::string("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);"), he, hl), gn = parse_newick(std::string("((a,b),(c,d));"), ge, gl);
+    MyNet N(he, hl, consecutive_tag(), hn); MyTree G(ge, gl, consecutive_tag(), gn);
+    TreeInComponent<ROTree<>, MyTree> tic(N, G, LabelMatchingMap(), N.root());
+    assert(tic.subtree().num_nodes() == 11 && tic.origin(0) == N.root());
+    const int hda[7] = {-1, 1, 1, 1, 4, 4, 4};
+    for (Node v = 1; v < 7; ++v) assert(tic.highest_displayed_ancestor(v) == (Node)hda[v]);
+    TreeComponentInfos<MyNet> ci(N);
+    for (Node v = 0; v < hn; ++v) assert(ci.comp_root(v) == 0);
+    assert(ci.visible_leaf(0) != NoNode && N.is_leaf(ci.visible_leaf(0)) && ci.comp_DAG_edges().empty());
+  }
+  // the reference's class names for LCA / RMQ (rmq/lca.hpp:79-106, rmq/rmq.hpp:63-72): lca<Tree>, sparse_rmq<It>::query / query_offset
+  {
+    lca<MyTree> L3(T2);
+    assert(L3.query(T2.root(), 3) == T2.root() && LCA(T2, 2, 3) == L2.query(2, 3) && naiveLCA(T2, 5, 6) == L2.query(5, 6));
+    const std::vector<int> a = {5, 3, 8, 3, 9, 1, 7};
+    sparse_rmq<std::vector<int>::const_iterator> R(a.begin(), a.end());
+    assert(R.query_offset(0, 5) == 3 && *R.query(0, 5) == 3 && R.query_offset(0, 7) == 5 && R.query_offset(2, 3) == 2);   // ties -> right (sparse_rmq.hpp:63,89)
+  }
   // isomorphism (utils/isomorphism.hpp:309-321): data/nets.nw of the reference, and what the flags change
   {
     auto net = [](const char* nw) { EdgeVec e; auto l = std::make_shared<LabelMapDefault>(); const size_t n = parse_newick(std::string(nw), e, l); return RONetwork<>(e, l, consecutive_tag(), n); };

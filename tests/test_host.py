@@ -179,3 +179,27 @@ def test_iso_arrays_layout(pt):
     assert a["succ_off"].tolist() == [0, 2, 2, 2, 0, 2, 3, 3, 3] and a["succ_adj"].tolist() == [1, 2, 3, 1, 2]
     assert a["pred_off"].tolist() == [0, 0, 1, 2, 0, 0, 1, 2, 3] and a["pred_adj"].tolist() == [0, 0, 0, 1, 0]
     assert a["label"].tolist() == [-1, 0, 1, -1, -1, 1, 0]
+
+
+def test_edgelist_reader_equals_reference(pt, tmp_path):
+    """parse_edgelist (io/edgelist.hpp:41-86): ids by first appearance, EVERY node labelled with its name, the reference's own
+    acceptance of blanks / tabs / empty lines and its MalformedEdgeVec cases -- tests/golden/edgelist_ref.json, produced by the
+    reference reader itself (oracle/_ref/ref_tc parse_el); then read_edgelists (io/io.hpp:52-62) through the `tc` tool's reader:
+    an edge list labels its inner nodes too, which is why the reference's tc cannot use it"""
+    import pytest
+    from conftest import load_golden
+    gold = load_golden("edgelist_ref.json")
+    ok = bad = 0
+    for it in gold["items"]:
+        if it.get("reference") == "ERR":
+            with pytest.raises(pt.MalformedEdgeVec):
+                pt.parse_edgelist(it["text"])
+            bad += 1
+            continue
+        n, edges, labels = pt.parse_edgelist(it["text"])
+        assert n == it["num_nodes"], it["text"]
+        assert [list(e) for e in edges] == it["edges"], it["text"]
+        assert {str(k): v for k, v in labels.items()} == it["labels"], it["text"]
+        assert len(labels) == n      # every node carries its name
+        ok += 1
+    assert ok >= 12 and bad >= 3
