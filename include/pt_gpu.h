@@ -366,11 +366,25 @@ int pt_comm_free(pt_comm* c);
  * n_switchings receives the size of the full index space; n_displaying the number of indices in
  * [begin, end) whose switching displays the guest; first_index the smallest such index or UINT64_MAX.
  * end == 0 means "to the end".
+ * HOW equality is decided: the kernel compares a canonical 64-bit Merkle hash of the display tree with the guest's (collision
+ * probability about 2^-64 per comparison), so n_displaying is exact up to that probability; first_index -- the WITNESS -- is
+ * confirmed exactly before it is returned (the switching is applied to the host and the exact solver of pt_batch_contain decides;
+ * a collision would be skipped and counted out).
+ * pt_enum_create / pt_enum_run / pt_enum_free: the same with a persistent handle (host preprocessing, upload and accumulators once;
+ * a run is one kernel launch per chunk of the range).  With a pt_comm and stop_at_first the found word is all-reduced (MAX)
+ * across the ranks after every chunk of `chunk` switchings (0 = 2^20): every rank stops as soon as any rank has a witness
+ * (SURVEY 8(e) row 2); *stopped_early reports it.  Every rank of the communicator must call pt_enum_run together.
  * ---------------------------------------------------------------------------------------------- */
 int pt_enum_switchings(int32_t n, int32_t m, const int32_t* succ_off, const int32_t* succ_adj, const int32_t* host_label,
                        int32_t nt, const int32_t* guest_parent, const int32_t* guest_label,
                        uint64_t begin, uint64_t end, int stop_at_first,
                        uint64_t* n_switchings, uint64_t* n_displaying, uint64_t* first_index, void* stream);
+typedef struct pt_enum pt_enum;
+int pt_enum_create(pt_enum** out, int32_t n, int32_t m, const int32_t* succ_off, const int32_t* succ_adj, const int32_t* host_label, int32_t nt,
+                   const int32_t* guest_parent, const int32_t* guest_label, uint64_t* n_switchings, void* stream);
+int pt_enum_run(pt_enum* h, uint64_t begin, uint64_t end, int stop_at_first, pt_comm* comm, uint64_t chunk, uint64_t* n_displaying,
+                uint64_t* first_index, int* stopped_early, void* stream);
+int pt_enum_free(pt_enum* h);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-side readers / generators (no GPU needed).  C wrappers over the C++ facade so that non-C++ callers

@@ -514,6 +514,32 @@ def enum_switchings(succ_off, succ_adj, host_label, guest_parent, guest_label, b
     return tot.value, nd.value, (None if fi.value == 2**64 - 1 else fi.value)
 
 
+class Enum:
+    """pt_enum_*: the switching enumerator with a persistent handle (no allocation / upload per run) and, with a Comm, the
+    cross-GPU found flag: every rank stops as soon as any rank has a witness"""
+
+    def __init__(self, succ_off, succ_adj, host_label, guest_parent, guest_label):
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (succ_off, succ_adj, host_label, guest_parent, guest_label)]
+        self._h = C.c_void_p()
+        tot = C.c_uint64()
+        _check(_L.pt_enum_create(C.byref(self._h), len(a[2]), len(a[1]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, len(a[3]), a[3].ctypes.data, a[4].ctypes.data,
+                                 C.byref(tot), None), "pt_enum_create")
+        self.total = tot.value
+
+    def run(self, begin=0, end=0, stop_at_first=False, comm=None, chunk=0):
+        """-> (n_displaying, first_index or None, stopped_early)"""
+        nd, fi, early = C.c_uint64(), C.c_uint64(), C.c_int(0)
+        _check(_L.pt_enum_run(self._h, begin, end, 1 if stop_at_first else 0, comm._h if comm is not None else None, chunk, C.byref(nd), C.byref(fi), C.byref(early), None), "pt_enum_run")
+        return nd.value, (None if fi.value == 2**64 - 1 else fi.value), bool(early.value)
+
+    def free(self):
+        if getattr(self, "_h", None) and _L is not None:
+            _L.pt_enum_free(self._h)
+            self._h = None
+
+    __del__ = free
+
+
 def _csr(n, keys, vals):
     """CSR of `vals` grouped by `keys` (stable): (off[n+1], adj[m]) as int32"""
     keys, vals = np.asarray(keys, dtype=np.int64), np.asarray(vals, dtype=np.int32)

@@ -13,6 +13,11 @@ sys.path.insert(0, ROOT)
 import phylo_tools_b200 as pt  # noqa: E402
 
 
+def lo_of(index, tot, world):
+    r = min(index * world // tot, world - 1)
+    return tot * r // world
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -60,6 +65,37 @@ def main():
     comm.allreduce(w, op="max")
     torch.cuda.synchronize()
     assert w.cpu().tolist() == [world, 0]
+    # the enumerator's cross-GPU early exit: every rank enumerates its own slice of the index space; the rank
+    # whose slice holds the first witness finds it, the others learn it from the all-reduced found word and stop early
+    pe = pt.Packer()
+    pe.add_generated(1, 14, 16, 777, 0)       # r = 16: 65536 switchings, displayed by construction
+    ea = pe.arrays()
+    args = (ea["host_succ_off"], ea["host_succ_adj"], ea["host_label"], ea["guest_parent"], ea["guest_label"])
+    tot, nd_all, first_all = pt.enum_switchings(*args)
+    assert first_all is not None
+    E = pt.Enum(*args)
+    lo, hi = tot * rank // world, tot * (rank + 1) // world
+    nd, first, early = E.run(begin=lo, end=hi, stop_at_first=True, comm=comm, chunk=256)
+    owner = min(first_all * world // tot, world - 1)
+    if rank == owner:
+        assert first == first_all, (first, first_all)
+    t = torch.tensor([1 if early else 0, 1 if first is not None else 0], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t)
+    assert int(t[1].item()) >= 1                       # somebody has a witness
+    if tot // world > 4 * 256 and first_all - lo_of(first_all, tot, world) + 256 < tot // world:
+        assert int(t[0].item()) >= world - 1, t        # everybody else stopped before its slice was exhausted
+    # without a witness anywhere (random guest) every rank runs to the end and nobody reports an early stop
+    pn = pt.Packer()
+    pn.add_generated(1, 14, 12, 778, 2)
+    na = pn.arrays()
+    nargs = (na["host_succ_off"], na["host_succ_adj"], na["host_label"], na["guest_parent"], na["guest_label"])
+    tot2, nd2, first2 = pt.enum_switchings(*nargs)
+    E2 = pt.Enum(*nargs)
+    r2 = E2.run(begin=tot2 * rank // world, end=tot2 * (rank + 1) // world, stop_at_first=True, comm=comm, chunk=512)
+    t2 = torch.tensor([r2[0]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t2)
+    assert int(t2.item()) == nd2 and (nd2 > 0 or not r2[2])
+    E.free(); E2.free()
     comm.free()
     dist.barrier()
     dist.destroy_process_group()

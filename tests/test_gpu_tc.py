@@ -526,3 +526,33 @@ def test_edge_cases(pt, oracle):
     truth = [oracle.tc_bruteforce_newick(*p.newick(i))[0] for i in range(len(p))]
     assert v.astype(int).tolist() == truth
     assert truth[:10] == [1, 0, 1, 1, 1, 1, 0, 0, 1, 1] and truth[10:13] == [1, 1, 1] and truth[13] == 0
+
+
+def test_enum_handle_chunks_and_exact_witness(pt, oracle):
+    """pt_enum_create / pt_enum_run: one handle, many runs; chunked runs equal the one-shot call; the witness index is confirmed by
+    the exact solver; stop_at_first ends a run at the first chunk that holds a witness"""
+    p = pt.Packer()
+    p.add_generated(12, 12, 9, 4242, 0)          # displayed by construction: witnesses exist
+    p.add_generated(6, 12, 9, 4243, 2)           # random guests: mostly no witness
+    a = p.arrays()
+    for i in range(len(p)):
+        hb, he = int(a["host_node_off"][i]), int(a["host_node_off"][i + 1])
+        ab, ae = int(a["host_arc_off"][i]), int(a["host_arc_off"][i + 1])
+        gb, ge = int(a["guest_node_off"][i]), int(a["guest_node_off"][i + 1])
+        args = (a["host_succ_off"][hb + i: he + i + 1], a["host_succ_adj"][ab:ae], a["host_label"][hb:he], a["guest_parent"][gb:ge], a["guest_label"][gb:ge])
+        tot, nd, first = pt.enum_switchings(*args)
+        E = pt.Enum(*args)
+        assert E.total == tot
+        nd2, first2, early = E.run(chunk=37)                     # many small chunks
+        assert (nd2, first2, early) == (nd, first, False)
+        parts = [E.run(begin=tot * k // 3, end=tot * (k + 1) // 3, chunk=64) for k in range(3)]
+        assert sum(x[0] for x in parts) == nd
+        firsts = [x[1] for x in parts if x[1] is not None]
+        assert (min(firsts) if firsts else None) == first
+        nd3, first3, early3 = E.run(stop_at_first=True, chunk=16)
+        assert first3 == first and (first is None or nd3 >= 1)
+        if first is not None and first + 16 < tot:
+            assert early3                                        # the run ended before the range was exhausted
+        E.free()
+        truth = oracle.tc_bruteforce_newick(*p.newick(i), stop_at_first=False)
+        assert nd == truth[1] and (first is None) == (truth[1] == 0)   # (the index numbering follows the arc order given, the count does not)
