@@ -377,27 +377,52 @@ def config4_leg(pt, torch, count, rank=0, world=1, dist=None):
 
 
 def config5_leg(pt, retis=24, leaves=30, rank=0, world=1, dist=None, torch=None, comm=None):
-    """BASELINE configs[4]: exhaustive 2^r switching enumeration of one general network (guest = random tree: not displayed,
-    so the whole index space is visited)"""
-    p = pt.Packer()
-    p.add_generated(1, leaves, retis, SEED + 5, 2)
-    a = p.arrays()
-    args = (a["host_succ_off"], a["host_succ_adj"], a["host_label"], a["guest_parent"], a["guest_label"])
-    pt.enum_switchings(*args, begin=0, end=1 << 16)  # warm-up
-    total = 1 << retis  # binary network: in-degree 2 at every reticulation
-    lo, hi = total * rank // world, total * (rank + 1) // world  # SURVEY 8(e): contiguous sub-ranges of [0, 2^r), one reduction
+    """BASELINE configs[4]: exhaustive 2^r switching enumeration of one general network, the index space cut into one contiguous
+    range per GPU.  Persistent handle (pt_enum_create once; a run = kernel launches only).  Two runs:
+    a random guest (not displayed: the whole space is visited), and a displayed guest with stop_at_first, where the found word
+    is all-reduced after every chunk and every GPU stops as soon as one has a witness."""
+    def make(kind, seed):
+        p = pt.Packer()
+        p.add_generated(1, leaves, retis, seed, kind)
+        a = p.arrays()
+        return pt.Enum(a["host_succ_off"], a["host_succ_adj"], a["host_label"], a["guest_parent"], a["guest_label"]), int(a["host_node_off"][1])
+    E, hn = make(2, SEED + 5)
+    E.run(begin=0, end=1 << 16)  # warm-up
+    total = E.total
+    lo, hi = total * rank // world, total * (rank + 1) // world
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            m = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            dt = float(m[0].item())
+        return r, dt
+    (nd, first, _), dt = timed(lambda: E.run(begin=lo, end=hi, comm=comm, chunk=1 << 21))
     if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    tot, nd, first = pt.enum_switchings(*args, begin=lo, end=hi) if world > 1 else pt.enum_switchings(*args)
-    dt = time.perf_counter() - t0
+        t = torch.tensor([nd], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        nd = int(t[0].item())
+    E.free()
+    out = {"workload": "exhaustive switching enumeration, gen network l=%d r=%d, random guest tree (BASELINE configs[4]); index space sharded over %d GPU(s)" % (leaves, retis, world),
+           "n_gpus": world, "switchings": total, "displaying": nd, "seconds": dt, "switchings_per_s": total / dt, "host_nodes": hn,
+           "note": "wall time of pt_enum_run on a persistent handle (no allocation / upload per run); bound by integer ALU + L1-resident accumulators, not HBM"}
+    # early exit: a displayed guest; every rank stops once any rank has a witness
+    E2, _ = make(0, SEED + 6)
+    (nd2, first2, early), dt2 = timed(lambda: E2.run(begin=lo, end=hi, stop_at_first=True, comm=comm, chunk=1 << 18))
+    E2.free()
+    flags = [1 if early else 0, 1 if first2 is not None else 0]
     if world > 1:
-        t = torch.tensor([float(tot), float(nd)], dtype=torch.float64, device="cuda"); m = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM); dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        tot, nd, dt = int(tot), int(t[1].item()), float(m[0].item())  # n_switchings is the size of the whole index space on every rank
-    return {"workload": "exhaustive switching enumeration, gen network l=%d r=%d, random guest tree (BASELINE configs[4])" % (leaves, retis),
-            "n_gpus": world, "switchings": tot, "displaying": nd, "seconds": dt, "switchings_per_s": tot / dt, "host_nodes": int(a["host_node_off"][1]),
-            "note": "wall time of pt_enum_switchings incl. upload; bound by integer ALU + L1-resident accumulators, not HBM"}
+        t = torch.tensor(flags, dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        flags = [int(t[0].item()), int(t[1].item())]
+    out["early_exit"] = {"workload": "the same network with a DISPLAYED guest, stop_at_first, found word all-reduced (MAX) across the GPUs every 2^18 switchings",
+                         "seconds": dt2, "ranks_with_a_witness": flags[1], "ranks_stopped_early": flags[0], "fraction_of_full_enumeration_time": dt2 / dt}
+    return out
 
 
 def config1_leg(pt):

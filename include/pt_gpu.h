@@ -285,7 +285,12 @@ typedef struct pt_options {
   int32_t path;              /* 0 auto; 1 force the shared-memory executor (one warp per instance, int16 ids);
                                 2 force the global-memory executor with one CTA per instance (int32 ids);
                                 3 the same with a thread-block cluster per instance (what auto picks for the
-                                  global-memory executor when a launch has fewer instances than half the SMs) */
+                                  global-memory executor when a launch has fewer instances than half the SMs);
+                                4 auto, but never split along bridges; 5 split along the bridges whatever the size.
+                                Auto (0) splits instances that do not fit shared memory along their bridges
+                                (utils/bridges.hpp:42-118): tree parts are decided by cluster comparisons, every bridge-free
+                                component becomes a small instance for the shared-memory executor; batches that are not
+                                clean (unlabelled leaves, labels on one side only, unary guest nodes) go to 3 / 2 */
   int32_t reserved[5];
 } pt_options;
 

@@ -1039,3 +1039,4 @@ extern "C" int pt_net_bridges(int64_t n, int64_t m, const int32_t* succ_off, con
 }
 
 #include "dp_kernels.cuh"
+#include "split_kernels.cuh"

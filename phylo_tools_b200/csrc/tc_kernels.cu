@@ -983,6 +983,11 @@ static int batch_check_ctl(pt_batch* b) {
 }
 
 // launch of the persistent warp kernel for element type S
+// csrc/split_kernels.cuh (compiled into lca_kernels.o): the bridge-splitting path for instances beyond shared memory
+extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const int64_t* d_harc_off, const int64_t* d_gnode_off, const void* d_succ_off, const void* d_succ_adj,
+                                   const void* d_hlabel, const void* d_tparent, const void* d_tlabel, int idx_bytes, uint32_t* d_bits, uint8_t* d_status, uint64_t* blobs_solved,
+                                   int* applied, void* stream);
+
 template <class S>
 static cudaError_t launch_persistent(int wpc, int grid, size_t smem, cudaStream_t s, const TcSource& src, const TcPool& pool, const TcChunks& ch, TcCtl* ctl, const pt_batch* b,
                                      int warp_bytes, uint32_t* bits, uint8_t* stat) {
@@ -1245,14 +1250,37 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   // executors over the same solver: warps with the instance in shared memory (int16 ids, ONE persistent launch), or one CTA /
   // one cluster per instance with the workspace in global memory (int32 ids, one launch per branching depth) when an instance
   // does not fit one CTA's shared memory
-  const int force = opt ? opt->path : 0;
+  // pt_options.path: 0 auto, 1 / 2 / 3 force an executor, 4 = automatic choice but never split (what the split path uses for its
+  // blobs), 5 = split along the bridges whatever the size (falls back to the automatic choice when the batch is not clean)
+  const bool want_split = opt && opt->path == 5, no_split = opt && opt->path == 4;
+  const int force = (opt && opt->path >= 1 && opt->path <= 3) ? opt->path : 0;
   const bool fits16 = b->maxN <= 30000 && b->maxM <= 30000 && b->maxNT <= 30000 && b->maxL <= 30000;
   const size_t warp_bytes = TcWork<I>::bytes(b->maxN, b->maxM, b->maxNT, b->maxL);
   const bool use_cta = force == 2 || force == 3 || !fits16 || warp_bytes > (size_t)dp.smem_optin;
   const int sN1 = b->maxN + 1, sM = std::max(1, (int)b->maxM), sN = b->maxN, sNT = b->maxNT;
   const size_t slot_elems = (size_t)sN1 + sM + sN + 2 * (size_t)sNT;
   int want = opt && opt->pool_slots > 0 ? opt->pool_slots : (int)std::min<int64_t>(std::max<int64_t>(8192, B), 1 << 22);
-  if (force == 1 && use_cta && B > 0) {
+  bool split_done = false;
+  if (B > 0 && force == 0 && !no_split && (use_cta || want_split)) {
+    // ---- split along the bridges first (north_star subsystem 1): instances beyond shared memory when the path is chosen
+    // automatically, or any batch on request.  The split path decides CLEAN batches completely (tree parts by cluster
+    // comparisons, bridge-free blobs on the shared-memory executor); anything else goes to the executors below.
+    if (b->copy_stream) PT_CUDA(cudaStreamSynchronize(b->copy_stream));   // a HOST batch: its chunks must have landed
+    int applied = 0; uint64_t blobs = 0;
+    if (int rc = ptgpu_split_contain(B, b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_succ_off, b->d_succ_adj, b->d_hlabel, b->d_tparent, b->d_tlabel, b->idx_bytes,
+                                     bits, stat, &blobs, &applied, stream)) return rc;
+    if (applied) {
+      split_done = true; rounds = 1; b->last_launches = 40;
+      const unsigned long long items = blobs;
+      PT_CUDA(cudaMemcpyAsync(b->d_counters + CNT_ITEMS, &items, 8, cudaMemcpyHostToDevice, s));
+      PT_CUDA(cudaStreamSynchronize(s));
+    } else {
+      PT_CUDA(cudaMemsetAsync(bits, 0, words * 4, s));
+      PT_CUDA(cudaMemsetAsync(stat, 0, (size_t)B, s));
+    }
+  }
+  if (split_done) {
+  } else if (force == 1 && use_cta && B > 0) {
     PT_CUDA(cudaMemsetAsync(stat, PT_INST_TOO_LARGE, (size_t)B, s));  // caller insisted on the shared-memory path
   } else if (B > 0 && !use_cta) {
     // ---- the warp executor: one persistent launch --------------------------------------------------------------------------

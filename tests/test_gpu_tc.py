@@ -556,3 +556,93 @@ def test_enum_handle_chunks_and_exact_witness(pt, oracle):
         E.free()
         truth = oracle.tc_bruteforce_newick(*p.newick(i), stop_at_first=False)
         assert nd == truth[1] and (first is None) == (truth[1] == 0)   # (the index numbering follows the arc order given, the count does not)
+
+
+@pytest.mark.parametrize("l,r", [(6, 2), (10, 4), (14, 6), (20, 9)])
+def test_bridge_splitting_vs_bruteforce(pt, oracle, l, r):
+    """pt_options.path = 5: the batch is split along its bridges (north_star subsystem 1; utils/bridges.hpp:42-118 as the semantic
+    spec) -- tree parts decided by cluster comparisons, bridge-free blobs solved as small instances -- on instances small enough for
+    exhaustive switching to give the truth; both layouts the split path reads"""
+    p = pt.Packer()
+    for kind in (0, 1, 2):
+        p.add_generated(150, l, r, 51000 + 13 * l + kind, kind)
+    truth = np.array([oracle.tc_bruteforce_newick(*p.newick(i))[0] for i in range(len(p))])
+    for compact in (0, 2):
+        b = pt.Batch(p.arrays(compact=compact))
+        v, s, c = b.contain(path=5)
+        b.free()
+        assert (s == 0).all()
+        bad = np.where(v.astype(int) != truth)[0]
+        assert len(bad) == 0, (l, r, compact, bad[:10], [p.newick(int(i)) for i in bad[:2]])
+        assert c["rounds"] == 1 and c["work_items"] > 0      # the split path ran (work items = blobs solved)
+
+
+def test_bridge_splitting_on_golden_instances(pt, gold_tc):
+    """the pinned instances (reference verdicts + exhaustive truth): instances that are not clean for the split path (labels on one
+    side only, unlabelled leaves ...) fall back, whole batch, to the general executors -- verdicts are the truth either way"""
+    items = gold_tc["items"]
+    p = pt.Packer()
+    for it in items:
+        p.add_newick(it["host"], it["guest"])
+    b = pt.Batch(p.arrays())
+    v, s, c = b.contain(path=5)
+    b.free()
+    assert (s == 0).all() and [int(x) for x in v] == [it["truth"] for it in items]
+    clean = [it for it in items if it["tag"].startswith("gen")]
+    q = pt.Packer()
+    for it in clean:
+        q.add_newick(it["host"], it["guest"])
+    b = pt.Batch(q.arrays())
+    v, s, c = b.contain(path=5)
+    b.free()
+    assert (s == 0).all() and [int(x) for x in v] == [it["truth"] for it in clean] and c["work_items"] > 0 and c["rounds"] == 1
+
+
+def test_large_instances_split_vs_cluster_executor(pt):
+    """n >= 10^5 nodes per instance (beyond shared memory): the automatic path splits along the bridges; verdicts equal the cluster
+    executor's on displayed guests, label-swapped guests and random guests, and a guest with a foreign label (not clean: the batch
+    falls back) is refused by both"""
+    p = pt.Packer()
+    p.add_generated(2, 50_000, 100, 6100, 0)
+    p.add_generated(2, 50_000, 100, 6200, 1)
+    p.add_generated(1, 50_000, 100, 6300, 2)
+    a = p.arrays()
+    assert a["max_host_nodes"] > 100_000
+    b = pt.Batch(a)
+    v_auto, s_auto, c_auto = b.contain()            # splits
+    v_cl, s_cl, c_cl = b.contain(path=3)            # cluster executor, unsplit
+    b.free()
+    assert (s_auto == 0).all() and (s_cl == 0).all()
+    assert v_auto.tolist() == v_cl.tolist() and v_auto[:2].all() and not v_auto[4]
+    assert c_auto["rounds"] == 1 and c_auto["work_items"] > 0
+    # foreign label in one guest: label only in the guest -> not displayed (containment.hpp:1116); the batch is not clean
+    gb = int(a["guest_node_off"][0])
+    leaf = int(np.where(a["guest_label"][gb:gb + int(a["guest_node_off"][1])] >= 0)[0][0])
+    a["guest_label"][gb + leaf] = int(a["max_labels"])     # an id no host leaf carries (still < n + nt)
+    a["max_labels"] = int(a["max_labels"]) + 1
+    b = pt.Batch(a)
+    v2, s2, _ = b.contain()
+    b.free()
+    assert (s2 == 0).all() and not v2[0] and v2[1] and v2.tolist()[1:] == v_cl.tolist()[1:]
+
+
+def test_reference_verdicts_at_n_10k(pt):
+    """the REFERENCE's verdicts on hosts of 10 099 nodes (l = 5 000, r = 50; tests/golden/tc_ref_n10k.json, generated by running the
+    reference here for minutes): equal wherever the reference terminates, through the split path and through the global-memory
+    executors (the shared-memory executor takes these too: n < 30 000)"""
+    from conftest import load_golden
+    gold = load_golden("tc_ref_n10k.json")
+    checked = 0
+    for cfg in gold["configs"]:
+        p = pt.Packer()
+        p.add_generated(cfg["count"], cfg["leaves"], cfg["reticulations"], cfg["seed"], cfg["kind"])
+        b = pt.Batch(p.arrays())
+        for path in (0, 5, 3):
+            v, s, _ = b.contain(path=path)
+            assert (s == 0).all()
+            for i, r in enumerate(cfg["reference"]):
+                if r in "01":
+                    assert int(v[i]) == int(r), (cfg["kind"], path, i)
+                    checked += 1
+        b.free()
+    assert checked >= 6
