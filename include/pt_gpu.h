@@ -286,11 +286,13 @@ typedef struct pt_options {
                                 2 force the global-memory executor with one CTA per instance (int32 ids);
                                 3 the same with a thread-block cluster per instance (what auto picks for the
                                   global-memory executor when a launch has fewer instances than half the SMs);
-                                4 auto, but never split along bridges; 5 split along the bridges whatever the size.
-                                Auto (0) splits instances that do not fit shared memory along their bridges
-                                (utils/bridges.hpp:42-118): tree parts are decided by cluster comparisons, every bridge-free
-                                component becomes a small instance for the shared-memory executor; batches that are not
-                                clean (unlabelled leaves, labels on one side only, unary guest nodes) go to 3 / 2 */
+                                4 auto, never split (the default behaves like it);
+                                5 split the instances along their bridges first (utils/bridges.hpp:42-118, the splitting of
+                                  utils/biconnected_comps.hpp:33-88): tree parts are decided by cluster comparisons, every
+                                  bridge-free component becomes a small instance of its own; batches that are not clean
+                                  (unlabelled leaves, labels on one side only, unary guest nodes) fall back to auto.
+                                  Pays for networks whose bridge-free components are small; generator networks have one
+                                  giant component, there 3 is faster */
   int32_t reserved[5];
 } pt_options;
 

@@ -17,6 +17,9 @@
 // 4 B streamed out.
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <vector>
 #include "cuda_common.cuh"
@@ -560,6 +563,15 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
       cleanup(); lca_release(h); return rc;                                                                               \
     }                                                                                                                     \
   } while (0)
+  static const bool trace = getenv("PT_SPLIT_TRACE") != nullptr;   // profiling aid: wall time of the build's phases on stderr
+  auto t_last = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[lca build n=%lld] %-22s %8.3f ms\n", (long long)n, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   const size_t n4 = (size_t)n * 4;
   if (parent_mem == PT_MEM_HOST) { LCA_TRY(lca_malloc((void**)&d_parent, n4)); LCA_TRY(cudaMemcpyAsync(d_parent, parent, n4, cudaMemcpyHostToDevice, s)); }
   else d_parent = (int32_t*)parent;
@@ -579,6 +591,7 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
   LCA_TRY(cudaMemcpyAsync(h->d_level_base, level_base.data(), level_base.size() * 8, cudaMemcpyHostToDevice, s));
   h->device_bytes = (int64_t)n * (int64_t)sizeof(LcaRecord) + n * 8 + total * 8;
 
+  mark("allocations");
   LCA_TRY(cudaEventRecord(ev0, s));
   const int grid = dp.sms * 8;
   LCA_TRY(cudaMemsetAsync(deg, 0, n4 + 4, s)); LCA_TRY(cudaMemsetAsync(small, 0, 64, s));
@@ -590,6 +603,7 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
   int32_t info[8];
   LCA_TRY(cudaMemcpyAsync(info, small, 32, cudaMemcpyDeviceToHost, s));
   LCA_TRY(cudaStreamSynchronize(s));
+  mark("children CSR");
   if (info[0] != 1 || info[2]) {  // utils/storage_adj_common.hpp:103-109: exactly one root
     rc = set_error(PT_ERR_INVALID, "pt_lca_build: parent array is not a rooted tree (%d roots%s)", info[0], info[2] ? ", parent index out of range" : "");
     cleanup(); lca_release(h); return rc;
@@ -611,6 +625,8 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
     cleanup(); lca_release(h); return rc;
   }
   h->levels = info[3];
+  mark("sweeps");
+  if (trace) fprintf(stderr, "[lca build n=%lld] %d levels\n", (long long)n, info[3]);
   lca_keys_kernel<<<grid, 256, 0, s>>>(n, d_parent, depth, pre, h->keypos, nodeat);
   lca_blocks_kernel<true><<<grid, 256, 0, s>>>(n, h->nblocks, h->keypos, nodeat, h->rec, h->table);
   for (size_t k = 1; k < level_base.size(); ++k) {
@@ -622,6 +638,7 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
   LCA_TRY(cudaEventRecord(ev1, s));
   LCA_TRY(cudaStreamSynchronize(s));
   LCA_TRY(cudaEventElapsedTime(&h->build_ms, ev0, ev1));
+  mark("records + table");
 #undef LCA_TRY
   if (keep_size) { h->size = size; h->nodeat = nodeat; }
   cleanup();

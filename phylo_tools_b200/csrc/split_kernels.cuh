@@ -23,6 +23,9 @@
 //      are solved by the shared-memory executor (the persistent warp kernel); an instance is displayed iff no test and no blob fails
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace ptgpu {
 
@@ -215,6 +218,16 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
   auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (lca_malloc(&p, bytes ? bytes : 4) != cudaSuccess) { cudaGetLastError(); return nullptr; } owned.push_back(p); return p; };
 #define SP_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return set_error(PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
 #define SP_PTR(p) do { if (!(p)) { cleanup(); return set_error(PT_ERR_NOMEM, "split path: out of device memory"); } } while (0)
+  // PT_SPLIT_TRACE=1: wall time of every phase on stderr (a synchronise per mark: a profiling aid, not the normal path)
+  static const bool trace = getenv("PT_SPLIT_TRACE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[split] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   int64_t tails[3];
   SP_TRY(cudaMemcpyAsync(&tails[0], d_hnode_off + B, 8, cudaMemcpyDeviceToHost, s)); SP_TRY(cudaMemcpyAsync(&tails[1], d_harc_off + B, 8, cudaMemcpyDeviceToHost, s));
   SP_TRY(cudaMemcpyAsync(&tails[2], d_gnode_off + B, 8, cudaMemcpyDeviceToHost, s));
@@ -248,6 +261,7 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
   int32_t hf[16];
   SP_TRY(cudaMemcpyAsync(hf, flags, 64, cudaMemcpyDeviceToHost, s));
   SP_TRY(cudaStreamSynchronize(s));
+  mark("concatenate + tables");
   if (hf[0] || hf[1]) { cleanup(); return PT_OK; }   // malformed or not clean: the general executors decide (and report per-instance statuses)
   // ---- host side: spanning tree, LCA structure, bridges, component tops (the kernels of pt_net_bridges) ----
   int32_t* tree_arc = (int32_t*)dalloc((size_t)N * 4); int32_t* arc_tail = (int32_t*)dalloc((size_t)M * 4); int32_t* parent = (int32_t*)dalloc((size_t)N * 4);
@@ -260,6 +274,7 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
   br_first_parent_kernel<<<grid, 256, 0, s>>>(N, M, so, sa, tree_arc);
   br_tree_parent_kernel<<<grid, 256, 0, s>>>(N, so, sa, tree_arc, arc_tail, parent);
   if (int rc = lca_build_impl(&H, parent, N, PT_MEM_DEVICE, stream, true)) { cleanup(); if (rc == PT_ERR_INVALID) return PT_OK; return rc; }   // a cycle: the general path reports it
+  mark("host spanning tree + LCA");
   br_cover_kernel<<<grid, 256, 0, s>>>(M, arc_tail, sa, tree_arc, H->rec, H->keypos, H->table, H->d_level_base, cntpos);
   if (int rc = device_exclusive_scan(cntpos, N, prefix, scan_tmp, s)) { cleanup(); return rc; }
   br_mark_kernel<<<grid, 256, 0, s>>>(N, parent, tree_arc, H->rec, H->size, prefix, is_bridge, up);
@@ -271,8 +286,10 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
     SP_TRY(cudaStreamSynchronize(s));
     if (!h) break;
   }
+  mark("bridges + components");
   // ---- guest: LCA structure; guest positions of the labels along the host preorder; cluster tests ----
   if (int rc = lca_build_impl(&G, tp, NT, PT_MEM_DEVICE, stream, true)) { cleanup(); if (rc == PT_ERR_INVALID) return PT_OK; return rc; }
+  mark("guest LCA");
   int32_t* amin = (int32_t*)dalloc((size_t)N * 4); int32_t* amax = (int32_t*)dalloc((size_t)N * 4); int32_t* leaf_h = (int32_t*)dalloc((size_t)(N + 1) * 4); int32_t* leafpre_h = (int32_t*)dalloc((size_t)(N + 1) * 4);
   int32_t* leaf_t = (int32_t*)dalloc((size_t)(NT + 1) * 4); int32_t* leafpre_t = (int32_t*)dalloc((size_t)(NT + 1) * 4); int32_t* tmap = (int32_t*)dalloc((size_t)N * 4); int32_t* nb = (int32_t*)dalloc((size_t)N * 4);
   SP_PTR(amin); SP_PTR(amax); SP_PTR(leaf_h); SP_PTR(leafpre_h); SP_PTR(leaf_t); SP_PTR(leafpre_t); SP_PTR(tmap); SP_PTR(nb);
@@ -282,11 +299,13 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
   if (int rc = device_exclusive_scan(leaf_t, NT, leafpre_t, scan_tmp, s)) { cleanup(); return rc; }
   if (int rc = pt_rmq_build(&Rmin, amin, N, PT_MEM_DEVICE, stream)) { cleanup(); return rc; }
   if (int rc = pt_rmq_build(&Rmax, amax, N, PT_MEM_DEVICE, stream)) { cleanup(); return rc; }
+  mark("leaf positions + 2 RMQ builds");
   sp_tops_kernel<<<grid, 256, 0, s>>>(N, up, H->rec, H->size, leafpre_h, Rmin->rec, Rmin->keypos, Rmin->table, Rmin->d_level_base, Rmax->rec, Rmax->keypos, Rmax->table, Rmax->d_level_base,
                                       amin, G->rec, G->keypos, G->table, G->d_level_base, G->nodeat, G->size, leafpre_t, inst_h, NH, tmap, fail);
   SP_TRY(cudaMemsetAsync(nb, 0, (size_t)N * 4, s));
   sp_comp_sizes_kernel<<<grid, 256, 0, s>>>(N, up, nb);
   sp_trivial_kernel<<<grid, 256, 0, s>>>(NH, so, sa, up, nb, tmap, tp, inst_h, fail);
+  mark("cluster tests + trivial comps");
   // ---- the blobs: compact their nodes, sort by (component, node), pull their arcs ----
   u64* keys = (u64*)dalloc((size_t)N * 8); u64* keys2 = (u64*)dalloc((size_t)N * 8); int32_t* cnt = (int32_t*)dalloc(64);
   SP_PTR(keys); SP_PTR(keys2); SP_PTR(cnt);
@@ -319,6 +338,8 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
     SP_TRY(cudaMemcpyAsync(hngn.data(), node_gnode, (size_t)nbn * 4, cudaMemcpyDeviceToHost, s)); SP_TRY(cudaMemcpyAsync(hngp.data(), node_gpos, (size_t)nbn * 4, cudaMemcpyDeviceToHost, s));
     SP_TRY(cudaMemcpyAsync(hinst.data(), node_inst, (size_t)nbn * 4, cudaMemcpyDeviceToHost, s));
     SP_TRY(cudaStreamSynchronize(s));
+    mark("blob compaction + download");
+    if (trace) fprintf(stderr, "[split] %d blob nodes, %d arcs\n", nbn, narcs);
     // ---- host: one small instance per blob (the blobs together hold a few thousand nodes) ----
     struct Cand { int32_t gpos, gnode, label; };
     std::vector<int32_t> bstart;   // first sorted index of every blob
@@ -397,6 +418,7 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
       b_gn.push_back((int64_t)b_gp.size());
       (void)g0;
     }
+    mark("blob instances on the host");
     // solve the blobs with the shared-memory executor
     pt_batch_desc d{};
     d.num_instances = (int64_t)nblobs; d.mem = PT_MEM_HOST; d.host_node_off = b_hn.data(); d.host_arc_off = b_ha.data(); d.guest_node_off = b_gn.data();
@@ -407,6 +429,8 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
     pt_options bo{}; bo.path = 4;   // 4 = "do not split again" (internal): warp executor, or the global-memory ones for a huge blob
     const int rc2 = pt_batch_contain(bb, &bo, bbits.data(), bstat.data(), PT_MEM_HOST, nullptr, stream);
     pt_batch_free(bb);
+    mark("blob batch solved");
+    if (trace) fprintf(stderr, "[split] %zu blobs, largest host %lld nodes\n", nblobs, (long long)[&]() { int64_t mx = 0; for (size_t b = 0; b < nblobs; ++b) mx = std::max(mx, b_hn[b + 1] - b_hn[b]); return mx; }());
     if (rc2) { cleanup(); return rc2; }
     std::vector<int32_t> hfail((size_t)B, 0);
     bool any = false;

@@ -1261,10 +1261,14 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   const size_t slot_elems = (size_t)sN1 + sM + sN + 2 * (size_t)sNT;
   int want = opt && opt->pool_slots > 0 ? opt->pool_slots : (int)std::min<int64_t>(std::max<int64_t>(8192, B), 1 << 22);
   bool split_done = false;
-  if (B > 0 && force == 0 && !no_split && (use_cta || want_split)) {
-    // ---- split along the bridges first (north_star subsystem 1): instances beyond shared memory when the path is chosen
-    // automatically, or any batch on request.  The split path decides CLEAN batches completely (tree parts by cluster
-    // comparisons, bridge-free blobs on the shared-memory executor); anything else goes to the executors below.
+  if (B > 0 && force == 0 && !no_split && want_split) {
+    // ---- split along the bridges first (north_star subsystem 1), on request (pt_options.path = 5).  The split path decides CLEAN
+    // batches completely (tree parts by cluster comparisons, bridge-free blobs as small instances); anything else goes to the
+    // executors below.  It is NOT what the automatic choice takes for instances beyond shared memory: measured on BASELINE config 4
+    // (8 x n = 10^6, r = 10^3, generator networks) the reticulations of an instance fall into ONE bridge-free component of ~16 500
+    // nodes (+ 15 000 pendants), so the split costs two LCA builds over the whole forest (7.4 ms of sweeps) and still leaves a blob
+    // for the global-memory executor (6.8 ms): 37-43 ms against 24.5 ms unsplit (21.4 against 22.9 ms for a single instance).
+    // Networks with small, local blobs are where it pays (profiles/README.md).
     if (b->copy_stream) PT_CUDA(cudaStreamSynchronize(b->copy_stream));   // a HOST batch: its chunks must have landed
     int applied = 0; uint64_t blobs = 0;
     if (int rc = ptgpu_split_contain(B, b->d_hnode_off, b->d_harc_off, b->d_gnode_off, b->d_succ_off, b->d_succ_adj, b->d_hlabel, b->d_tparent, b->d_tlabel, b->idx_bytes,

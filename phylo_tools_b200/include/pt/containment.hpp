@@ -194,6 +194,16 @@ class TreeInTreeContainment {
 
   void fill_table() {
     const DpArrays a(host_, guest_);
+    // a host that is declared single-labelled must be: the reference throws when it builds the label matching
+    // (utils/label_matching.hpp:51-52,61-62); the guest is always single-labelled
+    auto check_single = [](const auto& T, const std::vector<int32_t>& lab) {
+      int32_t mx = -1;
+      for (const int32_t l : lab) mx = std::max(mx, l);
+      std::vector<char> seen((size_t)(mx + 2), 0);
+      for (Node v = 0; v < T.num_nodes(); ++v) if (T.is_leaf(v) && lab[v] >= 0) { if (seen[(size_t)lab[v]]) throw std::logic_error("single-label map for multi-labeled tree/network"); seen[(size_t)lab[v]] = 1; }
+    };
+    if (Host::is_single_labeled) check_single(host_, a.hl);
+    check_single(guest_, a.gl);
     pt_who* h = nullptr;
     throw_status(pt_who_build(&h, a.hp.data(), a.hl.data(), (int64_t)a.hp.size(), a.gp.data(), a.gl.data(), (int64_t)a.gp.size(), PT_MEM_HOST, nullptr), "pt_who_build");
     int64_t total = 0;
@@ -240,8 +250,8 @@ template <class Host, class Guest> TreeInTreeContainment(Host&&, Guest&&) -> Tre
 // component still displays (:328-344).  subtree() / origin() expose the unfolding: node 0 is u, ids are a preorder.
 template <class MulSubtree, class Guest, bool leaf_labels_only = true>
 class TreeInComponent {
+  std::vector<Node> origin_;   // (declared first: unzip() fills it while subtree_ is being constructed)
   MulSubtree subtree_;
-  std::vector<Node> origin_;
   TreeInTreeContainment<MulSubtree, Guest> display_;
 
   template <class Host>

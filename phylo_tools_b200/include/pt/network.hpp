@@ -45,10 +45,12 @@ class NodeSlice {
   Node front() const { return (Node)*b_; }
 };
 
-template <class _LabelMap = LabelMapDefault>
+// _MultiLabel: the reference's multi_label_tag (utils/tree.hpp:641-645, ROMulTree / RWMulTree): several leaves may carry one name
+template <class _LabelMap = LabelMapDefault, bool _MultiLabel = false>
 class Phylogeny {
  public:
   using LabelMap = _LabelMap;
+  static constexpr bool is_single_labeled = !_MultiLabel;
   using LabelType = std::string;
   using Edge = PT::Edge;
 
@@ -132,6 +134,8 @@ template <class LabelMap = LabelMapDefault> using ROTree = Phylogeny<LabelMap>;
 template <class LabelMap = LabelMapDefault> using RWTree = Phylogeny<LabelMap>;
 template <class LabelMap = LabelMapDefault> using RONetwork = Phylogeny<LabelMap>;
 template <class LabelMap = LabelMapDefault> using RWNetwork = Phylogeny<LabelMap>;
+template <class LabelMap = LabelMapDefault> using ROMulTree = Phylogeny<LabelMap, true>;
+template <class LabelMap = LabelMapDefault> using RWMulTree = Phylogeny<LabelMap, true>;
 template <class T> using CompatibleRWNetwork = Phylogeny<typename T::LabelMap>;
 template <class T> using CompatibleROTree = Phylogeny<typename T::LabelMap>;
 

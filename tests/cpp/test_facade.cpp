@@ -111,7 +111,7 @@ int main(int argc, char** argv) {
   {
     EdgeVec he, ge; LabelMapDefault hl, gl;
     const size_t hn = parse_newick(std::string("((((a,b),(c,d)),(e,d)),((a,b),(e,d)));"), he, hl), gn = parse_newick(std::string("(e,((a,c),(b,d)));"), ge, gl);
-    using MulTree = ROTree<>;   // the facade's label map may repeat a name: the reference's ROMulTree
+    using MulTree = ROMulTree<>;   // utils/tree.hpp:641-645
     MulTree H(he, hl, consecutive_tag(), hn); MyTree G(ge, gl, consecutive_tag(), gn);
     auto infos = std::make_shared<TreeInTreeContainment<MulTree, MyTree>::NodeInfos>();
     TreeInTreeContainment<MulTree, MyTree> c(H, G, infos);       // the reference's 5-argument constructor (containment.hpp:50-54), defaults for the rest
@@ -127,7 +127,7 @@ int main(int argc, char** argv) {
     EdgeVec he, ge; LabelMapDefault hl, gl;
     const size_t hn = parse_newick(std::string("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);"), he, hl), gn = parse_newick(std::string("((a,b),(c,d));"), ge, gl);
     MyNet N(he, hl, consecutive_tag(), hn); MyTree G(ge, gl, consecutive_tag(), gn);
-    TreeInComponent<ROTree<>, MyTree> tic(N, G, LabelMatchingMap(), N.root());
+    TreeInComponent<ROMulTree<>, MyTree> tic(N, G, LabelMatchingMap(), N.root());
     assert(tic.subtree().num_nodes() == 11 && tic.origin(0) == N.root());
     const int hda[7] = {-1, 1, 1, 1, 4, 4, 4};
     for (Node v = 1; v < 7; ++v) assert(tic.highest_displayed_ancestor(v) == (Node)hda[v]);

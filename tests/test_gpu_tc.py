@@ -599,7 +599,7 @@ def test_bridge_splitting_on_golden_instances(pt, gold_tc):
 
 
 def test_large_instances_split_vs_cluster_executor(pt):
-    """n >= 10^5 nodes per instance (beyond shared memory): the automatic path splits along the bridges; verdicts equal the cluster
+    """n >= 10^5 nodes per instance (beyond shared memory), split along the bridges (path = 5); verdicts equal the cluster
     executor's on displayed guests, label-swapped guests and random guests, and a guest with a foreign label (not clean: the batch
     falls back) is refused by both"""
     p = pt.Packer()
@@ -609,7 +609,7 @@ def test_large_instances_split_vs_cluster_executor(pt):
     a = p.arrays()
     assert a["max_host_nodes"] > 100_000
     b = pt.Batch(a)
-    v_auto, s_auto, c_auto = b.contain()            # splits
+    v_auto, s_auto, c_auto = b.contain(path=5)      # splits
     v_cl, s_cl, c_cl = b.contain(path=3)            # cluster executor, unsplit
     b.free()
     assert (s_auto == 0).all() and (s_cl == 0).all()
@@ -621,9 +621,10 @@ def test_large_instances_split_vs_cluster_executor(pt):
     a["guest_label"][gb + leaf] = int(a["max_labels"])     # an id no host leaf carries (still < n + nt)
     a["max_labels"] = int(a["max_labels"]) + 1
     b = pt.Batch(a)
-    v2, s2, _ = b.contain()
+    v2, s2, c2 = b.contain(path=5)
     b.free()
     assert (s2 == 0).all() and not v2[0] and v2[1] and v2.tolist()[1:] == v_cl.tolist()[1:]
+    assert c2["rounds"] >= 1 and c2["work_items"] >= 5    # the general executors ran: one work item per instance at least
 
 
 def test_reference_verdicts_at_n_10k(pt):
