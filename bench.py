@@ -57,10 +57,10 @@ def bind_to_gpu_numa_node(local_rank):
 
 
 def measured_traffic(kernel, units):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r01.json), only when the
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r02.json), only when the
     launch here processes the same number of units as the captured one; else None"""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))[kernel]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))[kernel]
         return t["dram_bytes_per_launch"] if t["units_per_launch"] == units else None
     except Exception:
         return None
@@ -329,7 +329,8 @@ def lca_leg(pt, torch, leaves, queries, peak, rank=0, world=1, dist=None):
         ok = bool((o2[:2000].cpu().numpy() == lca.query(cand[:2000].cpu().numpy(), cand[1:2001].cpu().numpy())).all())
         res["adjacent"]["density_%g" % dens] = {"queries": qn, "ms": a2, "queries_per_s": qps2, "answers_ok": ok,
                                                 "roofline": {"bound": "hbm", "achieved": LCA_BYTES_PER_QUERY * qps2 / 1e9 / world, "peak": peak, "unit": "GB/s",
-                                                             "frac": LCA_BYTES_PER_QUERY * qps2 / 1e9 / world / peak, "model": "40 B/query: 4 B id in, one 32-byte record, 4 B out"}}
+                                                             "frac": LCA_BYTES_PER_QUERY * qps2 / 1e9 / world / peak, "traffic": measured_traffic("lca_adjacent_kernel", qn),
+                                                             "model": "40 B/query: 4 B id in, one 32-byte record, 4 B out"}}
     lca.free()
     if rank == 0 and world == 1:
         res["cpu_baseline"] = lca_cpu_baseline()
