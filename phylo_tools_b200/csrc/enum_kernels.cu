@@ -25,37 +25,41 @@ __host__ __device__ __forceinline__ u64 child_term(u64 v) { return mix64(v + 0xD
 __host__ __device__ __forceinline__ u64 node_hash(u64 sum_terms) { u64 h = mix64(sum_terms ^ 0xA0761D6478BD642Full); return h ? h : 1; }
 
 // node i in children-first order
-struct EnumNode { int32_t parent;      // fixed parent position, -1 root, <= -2: multi-parent, digit = -2 - parent
-                  int32_t label; };    // leaf label or -1
+struct EnumNode { int32_t parent;      // ACCUMULATOR index of the fixed parent, -1 root, <= -2: multi-parent, digit = -2 - parent
+                  int32_t label;       // leaf label or -1
+                  int32_t acc;         // accumulator index of this node (nodes with out-arcs only: a leaf never receives), else -1
+                  int32_t pad; };
 
-__global__ void __launch_bounds__(256) enum_kernel(int n, const EnumNode* __restrict__ nodes, int r, const int32_t* __restrict__ radix,
+__global__ void __launch_bounds__(256) enum_kernel(int n, int nacc, const EnumNode* __restrict__ nodes, int r, const int32_t* __restrict__ radix,
                                                    const int32_t* __restrict__ par_off, const int32_t* __restrict__ par_pos,
                                                    u64 begin, u64 end, u64 guest_hash, int stop_at_first,
                                                    u64* __restrict__ S1, u64* __restrict__ S2, uint32_t* __restrict__ cnt,
                                                    u64* __restrict__ result /* [0]=count [1]=first [2]=stop flag */) {
   extern __shared__ int32_t sm[];
   EnumNode* snode = reinterpret_cast<EnumNode*>(sm);
-  int32_t* sradix = sm + 2 * n; int32_t* soff = sradix + r; int32_t* spar = soff + r + 1;
+  int32_t* sradix = sm + 4 * n; int32_t* soff = sradix + r; int32_t* spar = soff + r + 1;
   for (int i = threadIdx.x; i < n; i += blockDim.x) snode[i] = nodes[i];
   for (int i = threadIdx.x; i < r; i += blockDim.x) sradix[i] = radix[i];
   for (int i = threadIdx.x; i <= r; i += blockDim.x) soff[i] = par_off[i];
   for (int i = threadIdx.x; i < par_off[r]; i += blockDim.x) spar[i] = par_pos[i];
   __syncthreads();
   const u64 T = (u64)gridDim.x * blockDim.x, tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int i = 0; i < n; ++i) { S1[(u64)i * T + tid] = 0; S2[(u64)i * T + tid] = 0; cnt[(u64)i * T + tid] = 0; }
+  for (int i = 0; i < nacc; ++i) { S1[(u64)i * T + tid] = 0; S2[(u64)i * T + tid] = 0; cnt[(u64)i * T + tid] = 0; }
   u64 found = 0, first = ~0ull;
   for (u64 s = begin + tid; s < end; s += T) {
     if (stop_at_first && *(volatile u64*)&result[2]) break;
     u64 val = 0;
     for (int i = 0; i < n; ++i) {
       const EnumNode nd = snode[i];
-      const u64 k = (u64)i * T + tid;
-      const uint32_t c = cnt[k];
-      if (nd.label >= 0) val = leaf_hash(nd.label);
-      else if (c == 0) val = 0;
-      else if (c == 1) val = S1[k];
-      else val = node_hash(S2[k]);
-      if (c) { S1[k] = 0; S2[k] = 0; cnt[k] = 0; }
+      if (nd.acc < 0) val = nd.label >= 0 ? leaf_hash(nd.label) : 0;   // a node without out-arcs: its leaf hash, or nothing
+      else {
+        const u64 k = (u64)nd.acc * T + tid;
+        const uint32_t c = cnt[k];
+        if (c == 0) val = 0;
+        else if (c == 1) val = S1[k];
+        else val = node_hash(S2[k]);
+        if (c) { S1[k] = 0; S2[k] = 0; cnt[k] = 0; }
+      }
       if (val && nd.parent != -1) {
         int p = nd.parent;
         if (p <= -2) {
@@ -81,7 +85,7 @@ using namespace ptgpu;
 // ---- persistent handle: everything that does not depend on the index range is done once (host preprocessing, upload,
 // accumulators); a run is then a kernel launch per chunk of the range, with the found word looked at between chunks ----------
 struct pt_enum {
-  int n = 0, r = 0, grid = 0;
+  int n = 0, nacc = 1, r = 0, grid = 0;
   uint64_t total = 1;
   int trivial = 0;            // 0 enumerate; 1 never displayed (a guest label the host lacks); 2 always displayed (<= 2 common labels)
   u64 guest_hash = 0;
@@ -179,18 +183,24 @@ int pt_enum_create(pt_enum** out, int32_t n, int32_t m, const int32_t* succ_off,
   for (int i = 0; i < r; ++i) { radix[i] = indeg[retis[i]]; par_off[i + 1] = par_off[i] + indeg[retis[i]]; }
   par_pos.assign(std::max(par_off[r], 1), 0);
   std::vector<int32_t> fill(std::max(r, 1), 0);
+  // accumulators only for nodes with out-arcs (a leaf never receives a child value): half the per-thread state of a binary network
+  std::vector<int32_t> accof(n, -1);
+  int nacc = 0;
+  for (int i = 0; i < n; ++i) { const int v = order[n - 1 - i]; if (succ_off[v + 1] > succ_off[v]) accof[v] = nacc++; }
   for (int v = 0; v < n; ++v) {
     EnumNode& nd = nodes[posof[v]];
-    nd.parent = -1;
+    nd.parent = -1; nd.pad = 0;
     const int l = host_label[v];
     nd.label = (l >= 0 && succ_off[v + 1] == succ_off[v] && l2t[l] >= 0) ? l : -1;   // host-only labels are dropped (:1117-1121)
+    nd.acc = accof[v];
     if (ridx[v] >= 0) nd.parent = -2 - ridx[v];
   }
   for (int u = 0; u < n; ++u) for (int e = succ_off[u]; e < succ_off[u + 1]; ++e) {
     const int v = succ_adj[e];
-    if (ridx[v] >= 0) par_pos[par_off[ridx[v]] + fill[ridx[v]]++] = posof[u];   // digit order = arc order, like oracle/pt_oracle.c
-    else nodes[posof[v]].parent = posof[u];
+    if (ridx[v] >= 0) par_pos[par_off[ridx[v]] + fill[ridx[v]]++] = accof[u];   // digit order = arc order, like oracle/pt_oracle.c
+    else nodes[posof[v]].parent = accof[u];
   }
+  h->nacc = std::max(nacc, 1);
   // guest canonical hash (same functions as the device)
   std::vector<std::vector<int>> tk(nt);
   for (int t = 0; t < nt; ++t) if (guest_parent[t] >= 0) tk[guest_parent[t]].push_back(t);
@@ -204,19 +214,23 @@ int pt_enum_create(pt_enum** out, int32_t n, int32_t m, const int32_t* succ_off,
   cudaStream_t s = (cudaStream_t)stream;
   DeviceProps dp;
   if (int rc = device_props(&dp)) { delete h; return rc; }
-  h->smem = (size_t)(2 * n + r + (r + 1) + par_off[r] + 4) * 4;
+  h->smem = (size_t)(4 * n + r + (r + 1) + par_off[r] + 4) * 4;
   if (h->smem > (size_t)dp.smem_optin) { const size_t need = h->smem; delete h; return set_error(PT_ERR_UNSUPPORTED, "instance too large for the enumerator (%zu bytes of shared memory)", need); }
-  // threads: at most 8 CTAs of 256 per SM, and at most ~2 GB of accumulators
-  int grid = dp.sms * 8;
-  while (grid > 1 && (uint64_t)grid * 256ull * (uint64_t)n * 20ull > (2ull << 30)) grid /= 2;
-  h->grid = std::max(grid, 1);
+  // threads: the per-thread accumulators (20 bytes per node with out-arcs) are touched for every switching.  Measured on BASELINE
+  // config 5 (2^24 switchings, 53 such nodes): 1 CTA of 256 per SM 38.2 ms, 2: 33.0, 3: 28.1, 4: 26.3, 8: 28.8 -- keeping all
+  // accumulators in L2 (1-2 CTAs: <= 80 MB) does not pay, the kernel needs the warps to hide its dependent loads
+  // (profiles/ncu_enum_r02.txt: long_scoreboard 24.5 stall cycles per issue); 4 CTAs per SM unless that takes more than 1 GB.
+  int per_sm = 4;
+  while (per_sm > 1 && (uint64_t)per_sm * (uint64_t)dp.sms * 256ull * (uint64_t)h->nacc * 20ull > (1ull << 30)) --per_sm;
+  if (const char* e = getenv("PT_ENUM_CTAS_PER_SM")) per_sm = std::max(1, std::min(8, atoi(e)));   // tuning aid
+  h->grid = std::max(dp.sms * per_sm, 1);
   const size_t T = (size_t)h->grid * 256;
   auto en_malloc = [](void** p, size_t bytes) -> cudaError_t { return dev_alloc(p, bytes) == PT_OK ? cudaSuccess : cudaErrorMemoryAllocation; };  // cached: raw cudaMalloc/cudaFree cost milliseconds
 #define EN_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cudaStreamSynchronize(s); enum_release(h); return set_error(e__ == cudaErrorMemoryAllocation ? PT_ERR_NOMEM : PT_ERR_CUDA, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); } } while (0)
   EN_TRY(cudaFuncSetAttribute(enum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   EN_TRY(en_malloc((void**)&h->d_nodes, nodes.size() * sizeof(EnumNode))); EN_TRY(en_malloc((void**)&h->d_radix, radix.size() * 4));
   EN_TRY(en_malloc((void**)&h->d_off, par_off.size() * 4)); EN_TRY(en_malloc((void**)&h->d_par, par_pos.size() * 4));
-  EN_TRY(en_malloc((void**)&h->d_S1, T * (size_t)n * 8)); EN_TRY(en_malloc((void**)&h->d_S2, T * (size_t)n * 8)); EN_TRY(en_malloc((void**)&h->d_cnt, T * (size_t)n * 4));
+  EN_TRY(en_malloc((void**)&h->d_S1, T * (size_t)h->nacc * 8)); EN_TRY(en_malloc((void**)&h->d_S2, T * (size_t)h->nacc * 8)); EN_TRY(en_malloc((void**)&h->d_cnt, T * (size_t)h->nacc * 4));
   EN_TRY(en_malloc((void**)&h->d_res, 64));
   EN_TRY(cudaMemcpyAsync(h->d_nodes, nodes.data(), nodes.size() * sizeof(EnumNode), cudaMemcpyHostToDevice, s));
   EN_TRY(cudaMemcpyAsync(h->d_radix, radix.data(), radix.size() * 4, cudaMemcpyHostToDevice, s));
@@ -264,7 +278,7 @@ int pt_enum_run(pt_enum* h, uint64_t begin, uint64_t end, int stop_at_first, pt_
       if (cudaMemcpyAsync(h->d_res, init, 32, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = set_error(PT_ERR_CUDA, "pt_enum_run: copy failed"); break; }
       const uint64_t want = (stop - pos + 255) / 256;
       const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)h->grid));
-      enum_kernel<<<grid, 256, h->smem, s>>>(h->n, h->d_nodes, h->r, h->d_radix, h->d_off, h->d_par, pos, stop, h->guest_hash, stop_at_first, h->d_S1, h->d_S2, h->d_cnt, h->d_res);
+      enum_kernel<<<grid, 256, h->smem, s>>>(h->n, h->nacc, h->d_nodes, h->r, h->d_radix, h->d_off, h->d_par, pos, stop, h->guest_hash, stop_at_first, h->d_S1, h->d_S2, h->d_cnt, h->d_res);
       if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(res, h->d_res, 32, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { rc = set_error(PT_ERR_CUDA, "pt_enum_run: launch failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
       // the witness of this chunk, confirmed exactly; a hash collision is counted out and the search goes on behind it
       while (res[1] != ~0ull) {
@@ -276,7 +290,7 @@ int pt_enum_run(pt_enum* h, uint64_t begin, uint64_t end, int stop_at_first, pt_
         if (bad + 1 < stop) {
           const u64 init2[4] = {0, ~0ull, 0, 0};
           cudaMemcpyAsync(h->d_res, init2, 32, cudaMemcpyHostToDevice, s);
-          enum_kernel<<<1, 256, h->smem, s>>>(h->n, h->d_nodes, h->r, h->d_radix, h->d_off, h->d_par, bad + 1, stop, h->guest_hash, 1, h->d_S1, h->d_S2, h->d_cnt, h->d_res);
+          enum_kernel<<<1, 256, h->smem, s>>>(h->n, h->nacc, h->d_nodes, h->r, h->d_radix, h->d_off, h->d_par, bad + 1, stop, h->guest_hash, 1, h->d_S1, h->d_S2, h->d_cnt, h->d_res);
           u64 r2[4];
           if (cudaMemcpyAsync(r2, h->d_res, 32, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { rc = set_error(PT_ERR_CUDA, "pt_enum_run: launch failed"); break; }
           res[1] = r2[1];

@@ -16,6 +16,7 @@
 // A query is therefore: 8 B of (u,v) streamed, TWO random 32-byte sector reads, two table reads that hit L2,
 // 4 B streamed out.
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -113,16 +114,20 @@ __global__ void lca_fill_children_kernel(const int32_t* __restrict__ parent, int
 
 // children lists in ascending node id: the atomic fill above leaves them in arrival order, which would make the preorder (and
 // with it the order of every who_displays list) differ from build to build; lists are short, one thread sorts one list
-__global__ void lca_sort_children_kernel(int64_t n, const int32_t* __restrict__ child_off, int32_t* __restrict__ child_adj) {
+__global__ void lca_sort_children_kernel(int64_t n, const int32_t* __restrict__ child_off, int32_t* __restrict__ child_adj, int32_t* __restrict__ long_lists) {
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
     const int32_t b = child_off[v], e = child_off[v + 1];
     if (e - b == 2) { const int32_t x = child_adj[b], y = child_adj[b + 1]; if (x > y) { child_adj[b] = y; child_adj[b + 1] = x; } continue; }
     if (e - b <= 64) { for (int32_t i = b + 1; i < e; ++i) { const int32_t x = child_adj[i]; int32_t j = i; while (j > b && child_adj[j - 1] > x) { child_adj[j] = child_adj[j - 1]; --j; } child_adj[j] = x; } continue; }
-    // long lists (stars): heap sort in place
-    const int32_t m = e - b; int32_t* a = child_adj + b;
-    for (int32_t start = m / 2 - 1; start >= 0; --start) { int32_t r = start; const int32_t val = a[r]; for (;;) { int32_t c = 2 * r + 1; if (c >= m) break; if (c + 1 < m && a[c + 1] > a[c]) ++c; if (a[c] <= val) break; a[r] = a[c]; r = c; } a[r] = val; }
-    for (int32_t end = m - 1; end > 0; --end) { const int32_t val = a[end]; a[end] = a[0]; int32_t r = 0; for (;;) { int32_t c = 2 * r + 1; if (c >= end) break; if (c + 1 < end && a[c + 1] > a[c]) ++c; if (a[c] <= val) break; a[r] = a[c]; r = c; } a[r] = val; }
+    *long_lists = 1;   // more than 64 children: left to the radix sort of (parent, child) keys below (a star of 10^6 leaves in one thread took 3 s)
   }
+}
+__global__ void lca_child_keys_kernel(int64_t n, const int32_t* __restrict__ parent, u64* __restrict__ keys) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+    keys[v] = parent[v] < 0 ? ~0ull : (((u64)(uint32_t)parent[v] << 32) | (u64)(uint32_t)v);
+}
+__global__ void lca_child_from_keys_kernel(int64_t n, const u64* __restrict__ keys, int32_t* __restrict__ child_adj) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n - 1; j += (int64_t)gridDim.x * blockDim.x) child_adj[j] = (int32_t)(keys[j] & 0xffffffffull);
 }
 
 // ---- build step 4: three level-synchronous sweeps in ONE cooperative kernel -------------------------------------
@@ -176,6 +181,97 @@ __global__ void __launch_bounds__(256) lca_sweeps_kernel(int64_t n, int32_t root
     }
     grid.sync();
   }
+}
+
+// ---- build step 4': depth / preorder / subtree size by EULER TOUR + LIST RANKING (replaces the level-synchronous sweeps above
+// in pt_lca_build: they pay three grid-wide barriers per LEVEL, so a path of 10^6 nodes took seconds and even a random tree of
+// 2*10^7 nodes spent 8 of its 13 ms waiting at barriers and on dependent loads).  The reference's lca does the same walk
+// recursively (rmq/lca.hpp:61-71: "emit node on entry and after each child").
+//   arcs: 2c = the step DOWN into node c, 2c+1 = the step UP out of c (c != root); succ[] links them into the tour
+//   ranking: every 64th arc (by a hash) is a SPLITTER; one thread walks from each splitter to the next one, summing length and
+//   (down - up) weight of its sublist; the ~n/32 splitters are ranked by pointer jumping; a second walk hands every arc its
+//   index idx and prefix weight W.   depth(c) = W(2c), preorder(c) = (idx(2c) + 1 + W(2c)) / 2, size(c) = (idx(2c+1) - idx(2c) + 1) / 2.
+// Work and traffic are O(n) whatever the shape of the tree.
+constexpr uint32_t ET_END = 0x7fffffffu;
+__device__ __forceinline__ bool et_is_splitter(uint32_t a) { return ((a * 2654435761u) >> 26) == 0u; }
+// succ word: bit 31 = "the successor is a splitter (or the end)", bits 0..30 = successor arc
+__global__ void et_next_sibling_kernel(int64_t n, const int32_t* __restrict__ parent, const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj, int32_t* __restrict__ next_sib) {
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n - 1; j += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t c = child_adj[j], p = parent[c];
+    next_sib[c] = (j + 1 < child_off[p + 1]) ? child_adj[j + 1] : -1;
+  }
+}
+__global__ void et_succ_kernel(int64_t n, int32_t root, const int32_t* __restrict__ parent, const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj,
+                               const int32_t* __restrict__ next_sib, uint32_t head, uint32_t* __restrict__ succ, int32_t* __restrict__ slot, int32_t* __restrict__ nsplit) {
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < 2 * n; a += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t c = (int32_t)(a >> 1);
+    uint32_t nx = ET_END;
+    if (c != root) {
+      if (!(a & 1)) nx = child_off[c + 1] > child_off[c] ? 2u * (uint32_t)child_adj[child_off[c]] : (uint32_t)a + 1u;
+      else { const int32_t sb = next_sib[c]; const int32_t p = parent[c]; nx = sb >= 0 ? 2u * (uint32_t)sb : (p == root ? ET_END : 2u * (uint32_t)p + 1u); }
+    }
+    const bool nsp = nx == ET_END || et_is_splitter(nx) || nx == head;
+    succ[a] = nx | (nsp ? 0x80000000u : 0u);
+    const bool me = c != root && (et_is_splitter((uint32_t)a) || (uint32_t)a == head);
+    slot[a] = me ? atomicAdd(nsplit, 1) : -1;
+  }
+}
+// first walk: sublist [a, next splitter): length and weight; next splitter's slot
+__global__ void et_walk1_kernel(int64_t n, const uint32_t* __restrict__ succ, const int32_t* __restrict__ slot, int32_t* __restrict__ sp_arc, int32_t* __restrict__ nxt,
+                                int32_t* __restrict__ len, int32_t* __restrict__ wsum) {
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < 2 * n; a += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t i = slot[a];
+    if (i < 0) continue;
+    uint32_t x = (uint32_t)a; int32_t l = 0, w = 0;
+    for (int64_t guard = 0; guard <= 2 * n; ++guard) {
+      ++l; w += (x & 1u) ? -1 : 1;
+      const uint32_t sw = succ[x];
+      x = sw & 0x7fffffffu;
+      if (sw & 0x80000000u) break;
+    }
+    sp_arc[i] = (int32_t)a; len[i] = l; wsum[i] = w;
+    nxt[i] = x == ET_END ? -1 : slot[x];
+  }
+}
+// pointer jumping over the splitters: suffix sums of (len, wsum)
+__global__ void et_jump_kernel(int32_t S, const int32_t* __restrict__ nxt_in, const int32_t* __restrict__ len_in, const int32_t* __restrict__ w_in,
+                               int32_t* __restrict__ nxt_out, int32_t* __restrict__ len_out, int32_t* __restrict__ w_out) {
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+    const int32_t j = nxt_in[i];
+    if (j < 0) { nxt_out[i] = -1; len_out[i] = len_in[i]; w_out[i] = w_in[i]; }
+    else { nxt_out[i] = nxt_in[j]; len_out[i] = len_in[i] + len_in[j]; w_out[i] = w_in[i] + w_in[j]; }
+  }
+}
+// second walk: idx and prefix weight of every arc of the sublist; idx_down -> pre[], idx_up -> size[], W(down) -> depth[]
+__global__ void et_walk2_kernel(int32_t S, int64_t n, const uint32_t* __restrict__ succ, const int32_t* __restrict__ sp_arc, const int32_t* __restrict__ nxt_final,
+                                const int32_t* __restrict__ suf_len, const int32_t* __restrict__ suf_w, int32_t head_slot, int32_t* __restrict__ depth, int32_t* __restrict__ pre, int32_t* __restrict__ size) {
+  const int32_t total = suf_len[head_slot], totw = suf_w[head_slot];
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+    if (nxt_final[i] != -1) continue;   // a splitter whose list never ends: it sits on a cycle beside the tree (the build reports it)
+    uint32_t x = (uint32_t)sp_arc[i];
+    int32_t idx = total - suf_len[i], w = totw - suf_w[i];
+    if (idx < 0) continue;
+    for (int64_t guard = 0; guard <= 2 * n; ++guard) {
+      const int32_t c = (int32_t)(x >> 1);
+      if (x & 1u) { w -= 1; size[c] = idx; } else { w += 1; pre[c] = idx; depth[c] = w; }
+      ++idx;
+      const uint32_t sw = succ[x];
+      x = sw & 0x7fffffffu;
+      if (sw & 0x80000000u) break;
+    }
+  }
+}
+__global__ void et_finish_kernel(int64_t n, int32_t root, int32_t* __restrict__ depth, int32_t* __restrict__ pre, int32_t* __restrict__ size, int32_t* __restrict__ info /* [3] levels [4] reached */) {
+  int32_t mx = 0, reached = 0;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+    if (c == root) { depth[c] = 0; pre[c] = 0; size[c] = (int32_t)n; ++reached; continue; }
+    const int32_t id = pre[c], iu = size[c], d = depth[c];
+    if (id < 0 || iu < id) { continue; }   // never visited
+    pre[c] = (id + 1 + d) / 2; size[c] = (iu - id + 1) / 2;
+    mx = max(mx, d); ++reached;
+  }
+  for (int o = 16; o; o >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); reached += __shfl_xor_sync(0xffffffffu, reached, o); }
+  if ((threadIdx.x & 31) == 0) { atomicMax(&info[3], mx + 1); atomicAdd(&info[4], reached); }
 }
 
 // ---- build step 5: keys by position ------------------------------------------------------------------------------
@@ -544,10 +640,12 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
   int32_t *d_parent = nullptr, *deg = nullptr, *child_off = nullptr, *child_adj = nullptr, *order = nullptr, *depth = nullptr, *size = nullptr, *pre = nullptr,
           *level_off = nullptr, *small = nullptr, *nodeat = nullptr;
   int64_t* scan_tmp = nullptr;
+  void* et_owned[3] = {nullptr, nullptr, nullptr};   // scratch of the Euler-tour ranking
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int rc = PT_OK;
   auto cleanup = [&]() {
     cudaStreamSynchronize(s);
+    for (void* p : et_owned) dev_free(p);
     if (parent_mem == PT_MEM_HOST) dev_free(d_parent);
     dev_free(deg); dev_free(child_off); dev_free(child_adj); dev_free(order); dev_free(depth); if (size != h->size) dev_free(size); dev_free(pre); dev_free(level_off); dev_free(small);
     if (nodeat != h->nodeat) dev_free(nodeat);
@@ -599,16 +697,29 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
   if ((rc = device_exclusive_scan(deg, n, child_off, scan_tmp, s)) != PT_OK) { cleanup(); lca_release(h); return rc; }
   LCA_TRY(cudaMemsetAsync(deg, 0, n4, s));
   lca_fill_children_kernel<<<grid, 256, 0, s>>>(d_parent, n, child_off, deg, child_adj);
-  lca_sort_children_kernel<<<grid, 256, 0, s>>>(n, child_off, child_adj);
+  lca_sort_children_kernel<<<grid, 256, 0, s>>>(n, child_off, child_adj, small + 5);
   int32_t info[8];
   LCA_TRY(cudaMemcpyAsync(info, small, 32, cudaMemcpyDeviceToHost, s));
   LCA_TRY(cudaStreamSynchronize(s));
+  if (info[5]) {   // some node has more than 64 children: the whole children array by one radix sort of (parent << 32 | child)
+    u64 *k1 = nullptr, *k2 = nullptr; void* tmp = nullptr; size_t tb = 0;
+    LCA_TRY(lca_malloc((void**)&k1, (size_t)n * 8)); et_owned[0] = k1;
+    LCA_TRY(lca_malloc((void**)&k2, (size_t)n * 8)); et_owned[1] = k2;
+    lca_child_keys_kernel<<<grid, 256, 0, s>>>(n, d_parent, k1);
+    LCA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb, k1, k2, (int)n, 0, 64, s));
+    LCA_TRY(lca_malloc(&tmp, tb)); et_owned[2] = tmp;
+    LCA_TRY(cub::DeviceRadixSort::SortKeys(tmp, tb, k1, k2, (int)n, 0, 64, s));
+    lca_child_from_keys_kernel<<<grid, 256, 0, s>>>(n, k2, child_adj);
+    LCA_TRY(cudaStreamSynchronize(s));
+    for (void*& p : et_owned) { dev_free(p); p = nullptr; }
+  }
   mark("children CSR");
   if (info[0] != 1 || info[2]) {  // utils/storage_adj_common.hpp:103-109: exactly one root
     rc = set_error(PT_ERR_INVALID, "pt_lca_build: parent array is not a rooted tree (%d roots%s)", info[0], info[2] ? ", parent index out of range" : "");
     cleanup(); lca_release(h); return rc;
   }
-  {
+  static const bool use_sweeps = getenv("PT_LCA_SWEEPS") != nullptr;   // A/B aid: the level-synchronous sweeps this build used before
+  if (use_sweeps) {
     int occ = 0;
     LCA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lca_sweeps_kernel, 256, 0));
     const int cgrid = dp.sms * std::max(1, std::min(occ, 4));
@@ -617,6 +728,54 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
     int32_t* ctr = small + 8; int32_t* inf = small;
     void* args[] = {&nn, &root, &child_off, &child_adj, &order, &depth, &size, &pre, &level_off, &ctr, &inf};
     LCA_TRY(cudaLaunchCooperativeKernel((void*)lca_sweeps_kernel, dim3(cgrid), dim3(256), args, 0, s));
+  } else if (n == 1) {
+    const int32_t one[2] = {1, 1};
+    LCA_TRY(cudaMemsetAsync(depth, 0, 4, s)); LCA_TRY(cudaMemsetAsync(pre, 0, 4, s)); LCA_TRY(cudaMemcpyAsync(size, one, 4, cudaMemcpyHostToDevice, s));
+    LCA_TRY(cudaMemcpyAsync(small + 3, one, 8, cudaMemcpyHostToDevice, s));
+  } else {
+    // Euler tour + list ranking.  Scratch: order[] and level_off[] (free in this path) hold next_sib and the splitter slots' arcs.
+    const int32_t root = info[1];
+    uint32_t* succ = nullptr; int32_t* slot = nullptr;
+    LCA_TRY(lca_malloc((void**)&succ, (size_t)n * 8)); et_owned[0] = succ;
+    LCA_TRY(lca_malloc((void**)&slot, (size_t)n * 8)); et_owned[1] = slot;
+    int32_t* next_sib = order;
+    et_next_sibling_kernel<<<grid, 256, 0, s>>>(n, d_parent, child_off, child_adj, next_sib);
+    int32_t first_child = 0;
+    {
+      int32_t ro[2] = {0, 0};
+      LCA_TRY(cudaMemcpyAsync(ro, child_off + root, 8, cudaMemcpyDeviceToHost, s));
+      LCA_TRY(cudaStreamSynchronize(s));
+      if (ro[1] == ro[0]) {   // n > 1 and nothing hangs on the root: the other nodes form cycles
+        rc = set_error(PT_ERR_INVALID, "pt_lca_build: parent array is not a tree (1 of %lld nodes reachable from the root: cycle)", (long long)n);
+        cleanup(); lca_release(h); return rc;
+      }
+      LCA_TRY(cudaMemcpyAsync(&first_child, child_adj + ro[0], 4, cudaMemcpyDeviceToHost, s));
+      LCA_TRY(cudaStreamSynchronize(s));
+    }
+    const uint32_t head = 2u * (uint32_t)first_child;
+    LCA_TRY(cudaMemsetAsync(small + 8, 0, 4, s));
+    et_succ_kernel<<<grid, 256, 0, s>>>(n, root, d_parent, child_off, child_adj, next_sib, head, succ, slot, small + 8);
+    int32_t S = 0;
+    LCA_TRY(cudaMemcpyAsync(&S, small + 8, 4, cudaMemcpyDeviceToHost, s));
+    LCA_TRY(cudaStreamSynchronize(s));
+    int32_t* sp = nullptr;   // sp_arc | nxt A/B | len A/B | w A/B : 7 arrays of S
+    LCA_TRY(lca_malloc((void**)&sp, (size_t)std::max(S, 1) * 7 * 4)); et_owned[2] = sp;
+    int32_t* sp_arc = sp; int32_t* nxtA = sp + (size_t)S; int32_t* nxtB = sp + 2 * (size_t)S; int32_t* lenA = sp + 3 * (size_t)S; int32_t* lenB = sp + 4 * (size_t)S;
+    int32_t* wA = sp + 5 * (size_t)S; int32_t* wB = sp + 6 * (size_t)S;
+    et_walk1_kernel<<<grid, 256, 0, s>>>(n, succ, slot, sp_arc, nxtA, lenA, wA);
+    int rounds = 1;
+    while (((int64_t)1 << rounds) < (int64_t)S) ++rounds;
+    const int jgrid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)S + 255) / 256));
+    for (int r = 0; r <= rounds; ++r) {
+      et_jump_kernel<<<jgrid, 256, 0, s>>>(S, nxtA, lenA, wA, nxtB, lenB, wB);
+      std::swap(nxtA, nxtB); std::swap(lenA, lenB); std::swap(wA, wB);
+    }
+    int32_t head_slot = 0;
+    LCA_TRY(cudaMemcpyAsync(&head_slot, slot + head, 4, cudaMemcpyDeviceToHost, s));
+    LCA_TRY(cudaStreamSynchronize(s));
+    LCA_TRY(cudaMemsetAsync(pre, 0xff, n4, s)); LCA_TRY(cudaMemsetAsync(size, 0xff, n4, s));
+    et_walk2_kernel<<<jgrid, 256, 0, s>>>(S, n, succ, sp_arc, nxtA, lenA, wA, head_slot, depth, pre, size);
+    et_finish_kernel<<<grid, 256, 0, s>>>(n, root, depth, pre, size, small);
   }
   LCA_TRY(cudaMemcpyAsync(info, small, 32, cudaMemcpyDeviceToHost, s));
   LCA_TRY(cudaStreamSynchronize(s));
@@ -625,7 +784,7 @@ static int lca_build_impl(pt_lca** out, const int32_t* parent, int64_t n, pt_mem
     cleanup(); lca_release(h); return rc;
   }
   h->levels = info[3];
-  mark("sweeps");
+  mark(use_sweeps ? "sweeps" : "Euler tour + ranking");
   if (trace) fprintf(stderr, "[lca build n=%lld] %d levels\n", (long long)n, info[3]);
   lca_keys_kernel<<<grid, 256, 0, s>>>(n, d_parent, depth, pre, h->keypos, nodeat);
   lca_blocks_kernel<true><<<grid, 256, 0, s>>>(n, h->nblocks, h->keypos, nodeat, h->rec, h->table);
