@@ -608,6 +608,11 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
+    # stdout carries exactly ONE line, the JSON: whatever a library prints to file descriptor 1 from here on (NCCL's version banner
+    # comes from ncclCommInitRank whatever NCCL_DEBUG_FILE says) is sent to stderr; the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3:
         args.warmup = 3
     import numpy as np
@@ -623,7 +628,8 @@ def main():
     pt.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL_DEBUG asks for goes to stderr: rank 0 prints ONE JSON line on stdout
+        os.environ.setdefault("NCCL_DEBUG", "WARN")              # no version banner: rank 0 prints ONE JSON line on stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # and whatever a caller's NCCL_DEBUG asks for goes to stderr
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def bootstrap(ident):  # the library's NCCL id travels by torch.distributed (the host program's own bootstrap)
@@ -807,7 +813,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":

@@ -23,6 +23,8 @@ struct NcclApi {
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   bool ok = false;
   char why[200] = {0};
 };
@@ -38,7 +40,9 @@ NcclApi& nccl() {
     api.CommDestroy = (int (*)(NcclComm))dlsym(h, "ncclCommDestroy");
     api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllReduce");
     api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    api.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    api.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString && api.GroupStart && api.GroupEnd;
     if (!api.ok) snprintf(api.why, sizeof(api.why), "libnccl.so.2 lacks an expected symbol");
   });
   return api;
@@ -113,21 +117,25 @@ int pt_batch_contain_sharded(pt_batch* b, pt_comm* c, const pt_options* opt, int
     return set_error(PT_ERR_INVALID, "pt_batch_contain_sharded: bad argument (the first instance of a shard must be a multiple of 32)");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t words = (total_instances + 31) / 32, w0 = first_instance / 32, wl = (local_instances + 31) / 32;
-  if (w0 > 0) PT_CUDA(cudaMemsetAsync(full_bits, 0, (size_t)w0 * 4, s));
-  if (w0 + wl < words) PT_CUDA(cudaMemsetAsync(full_bits + w0 + wl, 0, (size_t)(words - w0 - wl) * 4, s));
-  if (full_status) {
-    if (first_instance > 0) PT_CUDA(cudaMemsetAsync(full_status, 0, (size_t)first_instance, s));
-    if (first_instance + local_instances < total_instances) PT_CUDA(cudaMemsetAsync(full_status + first_instance + local_instances, 0, (size_t)(total_instances - first_instance - local_instances), s));
-  }
+  // every other rank's words / bytes are zero here (the local kernel clears and fills its own range)
+  (void)w0; (void)wl;
+  PT_CUDA(cudaMemsetAsync(full_bits, 0, (size_t)words * 4, s));
+  if (full_status) PT_CUDA(cudaMemsetAsync(full_status, 0, (size_t)((total_instances + 3) / 4 * 4), s));
   pt_counters local;
   memset(&local, 0, sizeof(local));
   if (local_instances > 0) {
     if (int rc = pt_batch_contain(b, opt, full_bits + w0, full_status ? full_status + first_instance : nullptr, PT_MEM_DEVICE, total ? &local : nullptr, stream)) return rc;
   }
-  if (int rc = pt_comm_allreduce(c, full_bits, words, 4, 0, stream)) return rc;
-  // status bytes are disjoint per rank as well: summed as 32-bit words when the total is a multiple of 4, else byte ranges would
-  // straddle -- the vector is padded by the caller to a multiple of 4 (documented in pt_gpu.h)
-  if (full_status) { if (int rc = pt_comm_allreduce(c, full_status, (total_instances + 3) / 4, 4, 0, stream)) return rc; }
+  // status bytes are disjoint per rank as well and are summed as 32-bit words (the caller pads the vector to a multiple of 4,
+  // pt_gpu.h); both all-reduces go out as ONE NCCL group (one launch)
+  if (c->nranks > 1) {
+    PT_NCCL(nccl().GroupStart());
+    int rc = pt_comm_allreduce(c, full_bits, words, 4, 0, stream);
+    if (rc == PT_OK && full_status) rc = pt_comm_allreduce(c, full_status, (total_instances + 3) / 4, 4, 0, stream);
+    const int ge = nccl().GroupEnd();
+    if (rc != PT_OK) return rc;
+    if (ge != 0) return set_error(PT_ERR_CUDA, "ncclGroupEnd failed: %d (%s)", ge, nccl().GetErrorString(ge));
+  }
   if (total) {
     static_assert(sizeof(pt_counters) == 12 * sizeof(uint64_t), "pt_counters layout");
     uint64_t h[12];

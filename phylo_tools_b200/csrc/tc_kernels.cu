@@ -864,6 +864,7 @@ struct pt_batch {
   int32_t maxN = 0, maxM = 0, maxNT = 0, maxL = 0;
   // results + scratch
   uint32_t* d_bits = nullptr; uint8_t* d_status = nullptr; uint8_t* d_branched = nullptr;
+  size_t scratch_bytes = 0;
   int32_t* d_ticket = nullptr;  // 256 bytes: the warp path's TcCtl; the global-memory executors: [0] ticket, [1] pool count A, [2] pool count B, [4..] chunk tickets
   unsigned long long* d_counters = nullptr;
   // pools of the global-memory executors (ping-pong, int32) and of the persistent warp kernel (one, element type of the batch)
@@ -932,7 +933,7 @@ static void batch_release(pt_batch* b) {
     dev_free(b->d_hnode_off); dev_free(b->d_harc_off); dev_free(b->d_gnode_off);
     dev_free(b->d_succ_off); dev_free(b->d_succ_adj); dev_free(b->d_hlabel); dev_free(b->d_tparent); dev_free(b->d_tlabel);
   }
-  dev_free(b->d_bits); dev_free(b->d_status); dev_free(b->d_branched); dev_free(b->d_ticket); dev_free(b->d_counters);
+  dev_free(b->d_bits); dev_free(b->d_status); dev_free(b->d_ticket);   // (counters and branched flags live inside d_ticket's block)
   dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); dev_free(b->d_ws); dev_free(b->d_ppool); dev_free(b->d_pready); dev_free(b->d_chunk_ready);
   for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : b->chunk_ev) if (e) cudaEventDestroy(e);
@@ -963,10 +964,14 @@ static int upload(T** dst, const T* src, int64_t count, cudaStream_t s, int64_t*
 static int batch_scratch(pt_batch* b) {
   const int64_t B = b->B;
   int rc = PT_OK;
+  // control block, counters and the "branched" flags share one allocation: pt_batch_contain clears them with one memset
+  b->scratch_bytes = 256 + 128 + (((size_t)B + 1 + 15) & ~(size_t)15);
   if ((rc = dev_alloc((void**)&b->d_bits, ((size_t)((B + 31) / 32) + 1) * 4)) || (rc = dev_alloc((void**)&b->d_status, (size_t)B + 1)) ||
-      (rc = dev_alloc((void**)&b->d_branched, (size_t)B + 1)) || (rc = dev_alloc((void**)&b->d_ticket, 256)) ||
-      (rc = dev_alloc((void**)&b->d_counters, CNT_N * sizeof(unsigned long long))))
+      (rc = dev_alloc((void**)&b->d_ticket, b->scratch_bytes)))
     return rc;
+  b->d_counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(b->d_ticket) + 256);
+  b->d_branched = reinterpret_cast<uint8_t*>(b->d_ticket) + 256 + 128;
+  static_assert(CNT_N * sizeof(unsigned long long) <= 128, "counter block");
   if (!(b->h_ctl = take_pinned_ctl())) return set_error(PT_ERR_NOMEM, "cudaHostAlloc failed");
   memset(b->h_ctl, 0, 64);
   return PT_OK;
@@ -1243,9 +1248,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   uint8_t* stat = (out_mem == PT_MEM_DEVICE && status) ? status : b->d_status;
   PT_CUDA(cudaMemsetAsync(bits, 0, words * 4, s));
   PT_CUDA(cudaMemsetAsync(stat, 0, (size_t)B, s));
-  PT_CUDA(cudaMemsetAsync(b->d_branched, 0, (size_t)B, s));
-  PT_CUDA(cudaMemsetAsync(b->d_counters, 0, CNT_N * sizeof(unsigned long long), s));
-  PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 256, s));
+  PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, b->scratch_bytes, s));   // control block + counters + branched flags
   uint64_t rounds = 0;
   // executors over the same solver: warps with the instance in shared memory (int16 ids, ONE persistent launch), or one CTA /
   // one cluster per instance with the workspace in global memory (int32 ids, one launch per branching depth) when an instance
