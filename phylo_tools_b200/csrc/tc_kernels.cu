@@ -1098,7 +1098,7 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
     // Chunks that double in size (1/32, 1/32, 1/16, ... 1/2 of the batch): the persistent kernel starts on a small first chunk
     // and the copy engine stays ahead of the solver from then on (the upload is 3-4 times faster than the solve), with few
     // API calls: their host time comes BEFORE the kernel launch and delays it.
-    b->nchunks = B >= 8192 ? 6 : 1;
+    b->nchunks = B >= 65536 ? 6 : (B >= 16384 ? 4 : (B >= 4096 ? 2 : 1));   // (a shard of 12 500 instances: 2 chunks = 12 copy calls, not 36)
     if (const char* e = getenv("PT_TC_CHUNKS")) b->nchunks = std::max(1, std::min((int)pt_batch::kMaxChunks, atoi(e)));  // tuning aid
     const int32_t* one = b->nchunks > 1 ? pinned_one() : nullptr;
     if (b->nchunks > 1 && (!one || !(b->copy_stream = take_copy_stream()))) { b->nchunks = 1; b->copy_stream = nullptr; }
