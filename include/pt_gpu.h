@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PT_GPU_ABI_VERSION 2
+#define PT_GPU_ABI_VERSION 3
 
 typedef enum pt_status {
   PT_OK = 0,

@@ -33,6 +33,12 @@ class LCAOracle {
     throw_status(pt_lca_query(h_, u.data(), v.data(), out.data(), (int64_t)u.size(), PT_MEM_HOST, nullptr), "pt_lca_query");
     return out;
   }
+  // LCAs of consecutive entries of a preorder-sorted candidate list (utils/induced_tree.hpp:128-138): out[i] = LCA(nodes[i], nodes[i+1])
+  std::vector<int32_t> query_adjacent(const std::vector<int32_t>& nodes) const {
+    std::vector<int32_t> out(nodes.size() > 1 ? nodes.size() - 1 : 0);
+    if (!out.empty()) throw_status(pt_lca_query_adjacent(h_, nodes.data(), (int64_t)nodes.size(), out.data(), PT_MEM_HOST, nullptr), "pt_lca_query_adjacent");
+    return out;
+  }
   pt_lca_info info() const { pt_lca_info i{}; throw_status(pt_lca_get_info(h_, &i), "pt_lca_get_info"); return i; }
   const pt_lca* handle() const { return h_; }
 };

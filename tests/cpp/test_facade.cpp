@@ -92,6 +92,7 @@ int main(int argc, char** argv) {
   // LCA: the tree of rmq/lca.cpp:24-43 and its four known answers
   LCAOracle L(std::vector<int32_t>{3, 3, 3, 8, 5, 7, 7, 8, -1});
   assert(L.query(8, 8) == 8 && L.query(3, 7) == 8 && L.query(0, 2) == 3 && L.query(4, 6) == 7);
+  { const std::vector<int32_t> adj = L.query_adjacent({0, 2, 3, 7, 4, 6}); assert((adj == std::vector<int32_t>{3, 3, 8, 7, 7})); }
   MyTree T2 = [] { EdgeVec e; LabelMapDefault l; const size_t n = parse_newick(std::string("((a,b),(c,(d,e)));"), e, l); return MyTree(e, l, consecutive_tag(), n); }();
   LCAOracle L2(T2);
   for (Node u = 0; u < T2.num_nodes(); ++u) assert(L2.LCA(u, T2.root()) == T2.root());

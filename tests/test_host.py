@@ -17,7 +17,7 @@ def test_exports_every_declared_symbol(pt):
     lib = C.CDLL(os.path.join(ROOT, "phylo_tools_b200", "libptgpu.so"))
     for name in declared:
         assert hasattr(lib, name), name
-    assert pt.lib().pt_abi_version() == 2
+    assert pt.lib().pt_abi_version() == 3
 
 
 def test_cpp_newick_reader_matches_reference(pt, gold_newick):
