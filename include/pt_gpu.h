@@ -125,6 +125,15 @@ int pt_tree_highest_displayed(const int32_t* guest_parent, const int32_t* who, i
  *   pt_net_tree_components : comp_root[v] (-1 = NoNode) and visible_leaf[v] (for component roots: a leaf whose comp_root is v,
  *       the largest such id; else -1) as TreeComponentInfos computes them for a fresh network, and the arcs of the component
  *       DAG as (root above << 32 | root below), duplicates included (*dag_count of them; at most dag_capacity are written).
+ *   pt_net_visible_component : VisibleComponentRule (utils/containment.hpp:603-725) as a query on a label-cleaned pair (HOST arrays):
+ *       eligibility[v] (optional, n bytes) = bit 0: component root v is "1/2-eligible" (is_half_eligible :652-687: every root below it in
+ *       the component DAG is, and the host has at most ONE path from v's tree component to each of them), bit 1: and a leaf sees it
+ *       (eligible), bit 2: and no eligible root lies below it (what get_eligible_component_root :689-704 can return).  *root = the root
+ *       the rule treats (smallest id with bit 2; want_root >= 0 overrides; -1 = the rule does not apply), *leaf = its visible leaf
+ *       (want_leaf >= 0 overrides), *guest_node = highest_displayed_ancestor of the guest leaf carrying that label in
+ *       TreeInComponent(host, guest, root) (treat_comp_root :623-644): the pair (root, guest_node) is what the reference hands to
+ *       match_nodes.  Path counts are taken once per component-DAG arc; the reference's own counters depend on the iteration order
+ *       of its hash containers (every root it calls half-eligible is half-eligible here).  unzip_cap bounds the unfolding (0 = 2^26).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pt_who pt_who;
 int pt_who_build(pt_who** out, const int32_t* host_parent, const int32_t* host_label, int64_t n, const int32_t* guest_parent,
@@ -137,6 +146,9 @@ int pt_net_unzip(int64_t n, int64_t m, const int32_t* succ_off, const int32_t* s
                  int32_t* out_parent, int32_t* out_label, int32_t* out_origin, int64_t capacity, int64_t* count, pt_mem mem, void* stream);
 int pt_net_tree_components(int64_t n, int64_t m, const int32_t* succ_off, const int32_t* succ_adj, int32_t* comp_root, int32_t* visible_leaf,
                            int64_t* dag_edges, int64_t dag_capacity, int64_t* dag_count, pt_mem mem, void* stream);
+int pt_net_visible_component(int64_t n, int64_t m, const int32_t* succ_off, const int32_t* succ_adj, const int32_t* host_label, int64_t nt,
+                             const int32_t* guest_parent, const int32_t* guest_label, int32_t want_root, int32_t want_leaf, int64_t unzip_cap,
+                             uint8_t* eligibility, int32_t* root, int32_t* leaf, int32_t* guest_node, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Network isomorphism -- replaces  make_iso_mapper(N0, N1, flags).check_isomorph()

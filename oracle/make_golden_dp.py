@@ -7,6 +7,7 @@ through oracle/_ref/ref_tc; the committed JSON travels to the GPU box).
         (TreeInComponent::unzip_retis :262-312) and highest_displayed_ancestor(v) of every guest node (:328-344), via `ref_tc hda`
   tests/golden/comps_ref.json   network -> comp_root / visible_leaf per node and the component DAG of the REFERENCE's
         TreeComponentInfos (utils/tree_components.hpp:41-234), via `ref_tc comps`
+  tests/golden/vcr_ref.json     (host network, guest tree) -> the REFERENCE's VisibleComponentRule (utils/containment.hpp:603-725), via `ref_tc vcr`
 """
 import json
 import os
@@ -188,8 +189,40 @@ def make_edgelist():
     print("edgelist_ref.json:", len(items), "texts,", sum(1 for it in items if "reference" in it), "malformed / crashed")
 
 
+def make_vcr():
+    """(host network, guest tree) -> the REFERENCE's VisibleComponentRule on the fresh pair (utils/containment.hpp:603-725, via `ref_tc vcr`):
+    the order in which it visits the component roots and their component-DAG children (its hash containers decide), is_half_eligible
+    and eligibility of every root, and for every eligible root its visible leaf and the guest node treat_comp_root would match it with"""
+    pairs = [("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));"), ("((a,(b)#H1),(#H1,c));", "(a,(b,c));"),
+             ("((((a,b),(c)#H1),(#H1,d)),((e,f),g));", "(((a,b),(c,d)),((e,f),g));"),
+             # two tree components above one root (x below a reticulation with parents in both): the reference's counters double
+             ("(((a,((x,y))#H1),b),((c,#H1),d));", "((a,b),((c,d),(x,y)));")]
+    for (l, r, cnt) in [(6, 2, 14), (8, 3, 16), (10, 4, 16), (14, 6, 14), (20, 8, 12), (30, 12, 8), (60, 20, 4)]:
+        for kind in (0, 1):
+            pairs += gen_pairs(cnt, l, r, 7700 + 100 * l + kind, kind)
+    blocks = run_lines("vcr", [x for p in pairs for x in p])[:len(pairs)]
+    items = []
+    for (h, g), b in zip(pairs, blocks):
+        if any(x in ("CRASH", "EXC", "FAIL", "UNCLEAN") for x in b) or not b or not b[0]:
+            items.append(dict(host=h, guest=g, reference="CRASH"))
+            continue
+        order = [[int(x.split(":")[0].split()[1])] + [int(y) for y in x.split(":")[1].split()] for x in b if x.startswith("O ")]
+        half = {x.split()[1]: [int(x.split()[2]), int(x.split()[3])] for x in b if x.startswith("H ")}
+        res = [[int(y) for y in x.split()[1:]] for x in b if x.startswith("R ") and "NOLABEL" not in x]
+        items.append(dict(host=h, guest=g, edgeless=any(x.startswith("EDGELESS") for x in b), order=order, half=half, treated=res))
+    crashed = sum(1 for it in items if it.get("reference") == "CRASH")
+    json.dump(dict(source="oracle/_ref/ref_tc vcr (reference VisibleComponentRule: is_half_eligible containment.hpp:652-687, get_eligible_component_root :689-704, treat_comp_root :623-644)",
+                   crashed=crashed, items=items), open(os.path.join(GOLD, "vcr_ref.json"), "w"), indent=0)
+    print("vcr_ref.json:", len(items), "pairs,", crashed, "reference crashes,", sum(len(it.get("treated", [])) for it in items), "eligible roots treated,",
+          sum(1 for it in items if it.get("half") and any(v[0] == 0 for v in it["half"].values())), "pairs with a root that is not half-eligible")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vcr":
+        make_vcr()
+        sys.exit(0)
     make_whomul()
     make_hda()
     make_comps()
     make_edgelist()
+    make_vcr()

@@ -205,6 +205,111 @@ def highest_displayed(guest_parent, who, host_root):
     return out
 
 
+def component_dag(succ_off, succ_adj):
+    """TreeComponentInfos for the component roots (utils/tree_components.hpp:68-131), restated: comp_root of every internal tree node,
+    and per non-trivial root v the multiset of component roots reached by climbing through the reticulations above v -- one entry per
+    PATH, which is what VisibleComponentRule::is_half_eligible counts (utils/containment.hpp:664-676).
+    -> (comp_root dict, arcs dict {(root above, v): number of paths}, network root)"""
+    so, sa = list(map(int, succ_off)), list(map(int, succ_adj))
+    n = len(so) - 1
+    parents = [[] for _ in range(n)]
+    for u in range(n):
+        for k in range(so[u], so[u + 1]):
+            parents[sa[k]].append(u)
+    root = [v for v in range(n) if not parents[v]][0]
+    comp = {root: root}
+
+    def comp_of(u):          # internal tree nodes only (:78-86)
+        chain = []
+        while u not in comp:
+            chain.append(u)
+            p = parents[u][0]
+            if len(parents[p]) > 1:
+                comp[u] = u
+                break
+            u = p
+        for x in reversed(chain):
+            if x not in comp:
+                comp[x] = comp[parents[x][0]]
+        return comp[chain[0]] if chain else comp[u]
+    arcs = {}
+    for v in range(n):
+        if len(parents[v]) == 1 and so[v + 1] > so[v] and len(parents[parents[v][0]]) > 1:   # non-trivial root
+            comp[v] = v
+            stack = [parents[v][0]]
+            while stack:
+                r = stack.pop()
+                for p in parents[r]:
+                    if len(parents[p]) > 1:
+                        stack.append(p)
+                    else:
+                        c = comp_of(p)
+                        arcs[(c, v)] = arcs.get((c, v), 0) + 1
+    return comp, arcs, root
+
+
+def vcr_half_eligible(succ_off, succ_adj, order=None):
+    """VisibleComponentRule::is_half_eligible (utils/containment.hpp:652-687) for the roots of the component DAG.
+    order = None: every path count taken once per component-DAG arc (the semantics the library implements) -> {root: bool}.
+    order = [[u, child, child, ...], ...] (the reference's own visiting order, printed by `ref_tc vcr`): the loop exactly as written,
+    including its shared counters -- walking the reticulations above a root v adds to num_paths[c][v] for EVERY component c above v, and
+    the walk is repeated for every component above v, so later components see doubled counts."""
+    comp, arcs, root = component_dag(succ_off, succ_adj)
+    kids = {}
+    for (c, v), k in arcs.items():
+        kids.setdefault(c, []).append(v)
+    if order is None:
+        half, paths = {}, {}
+
+        def visit(u):
+            if u in half:
+                return
+            for v in kids.get(u, []):
+                visit(v)
+            ok, acc = True, {}
+            for v in kids.get(u, []):
+                if not half[v] or arcs[(u, v)] > 1:
+                    ok = False
+                    continue
+                acc[v] = acc.get(v, 0) + 1
+                for x, k in paths[v].items():
+                    acc[x] = acc.get(x, 0) + k
+            ok = ok and all(k <= 1 for k in acc.values())
+            half[u], paths[u] = ok, (acc if ok else {})
+        for u in [root] + sorted(kids) + sorted(v for vs in kids.values() for v in vs):
+            visit(u)
+        return half
+    num_paths, half = {}, {}
+    above = {}
+    for (c, v), k in arcs.items():
+        above.setdefault(v, []).append((c, k))
+    for row in order:
+        u, children = row[0], row[1:]
+        up = num_paths.setdefault(u, {})
+        ok = True
+        for v in children:
+            if not half.get(v, False):
+                ok = False
+                break
+            for c, k in above.get(v, []):           # the walk above v registers a path for every tree node it ends in (:664-674)
+                d = num_paths.setdefault(c, {})
+                d[v] = d.get(v, 0) + k
+            if up.get(v, 0) > 1:
+                ok = False
+                break
+            bad = False
+            for x, k in list(num_paths.setdefault(v, {}).items()):
+                up[x] = up.get(x, 0) + k
+                if up[x] > 1:
+                    bad = True
+                    break
+            if bad:
+                ok = False
+                break
+        half[u] = ok
+    return half
+
+
 def tree_arrays_from_newick(host_nw, guest_nw):
     """two TREE Newick strings -> (host_parent, host_label, guest_parent, guest_label) with a shared dense label dictionary,
     node ids as the reference reader assigns them (oracle/newick.py)"""

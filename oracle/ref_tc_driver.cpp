@@ -22,6 +22,12 @@
 //        template instantiation naming the member (legal C++; nothing of the reference is modified)
 //   ref_tc comps <file> : per network line: per node "v comp_root visible_leaf" (-1 = NoNode) of TreeComponentInfos
 //        (utils/tree_components.hpp:41-234), then the arcs of its component DAG "D u v", then "--"
+//   ref_tc vcr <file> : (host network, guest tree) pairs; VisibleComponentRule (utils/containment.hpp:603-725) on a FRESH instance (no other
+//        rule applied; labels cleaned as init() does): "O u: v1 v2 .." = the component roots in the order cDAG.dfs().postorder() yields
+//        them, each with its component-DAG children in iteration order; "H u h e" = is_half_eligible(u) (called for EVERY root in that
+//        order, u joining half_eligible when true, as get_eligible_component_root does until it returns) and e = h && visible leaf;
+//        "R u leaf v" for every eligible u: its visible leaf and highest_displayed_ancestor of the matched guest leaf in
+//        TreeInComponent(host, guest, match, u) -- what treat_comp_root would hand to match_nodes(u, v)
 //   ref_tc parse_el <file> : the whole file as ONE edge list through the reference's parse_edgelist (io/edgelist.hpp:41-86): same output
 //        format as `parse` ("ERR" for MalformedEdgeVec)
 //   ref_tc parse <file> : for each line: "n m" then edges "u v" in reference edge-list order, then
@@ -129,6 +135,63 @@ static void run_hda(const std::string& l0, const std::string& l1) {
   }
   for (size_t v = 0; v < nt; ++v) if (v != (size_t)T.root()) out += std::to_string(v) + ": " + std::to_string((size_t)tic.highest_displayed_ancestor(v)) + "\n";
   fputs(out.c_str(), stdout);
+}
+
+// VisibleComponentRule outside its solver: a minimal "Containment" with the members the rule touches (containment.hpp:618-620),
+// built from the reference's own types exactly as TreeInNetContainment builds them (:975-989, :1008-1013)
+struct VcrContain {
+  using RWHost = CompatibleRWNetwork<MyNet, ComponentData>;
+  using RWGuest = CompatibleRWTree<MyTree>;
+  using LabelMatching = LabelMatchingFromNets<RWHost, RWGuest, std::vector>;
+  RWHost host; RWGuest guest; LabelMatching HG_label_match; TreeComponentInfos<RWHost> comp_info;
+  struct NoMatch { template <class... A> void match_nodes(A&&...) {} } HG_match;
+  VcrContain(const MyNet& N, const MyTree& T) : host(N), guest(T), HG_label_match(host, guest), comp_info(host) {}
+};
+static void run_vcr(const std::string& l0, const std::string& l1) {
+  std::vector<ENL> el(2);
+  parse_line(l0, el[0]); parse_line(l1, el[1]);
+  MyNet N(std::move(el[0].edges), std::move(el[0].labels), consecutive_tag());
+  MyTree T(std::move(el[1].edges), std::move(el[1].labels), consecutive_tag());
+  VcrContain c(N, T);
+  // init() :1086-1098 without the rules: labels only in the host are removed; a label only in the guest fails the instance
+  for (auto it = c.HG_label_match.begin(); it != c.HG_label_match.end();) {
+    auto& uv = it->second;
+    if (uv.first.empty()) { printf("FAIL\n"); return; }
+    if (uv.second.empty()) { printf("UNCLEAN\n"); return; }   // the golden generator only emits clean pairs; say so if one slips through
+    ++it;
+  }
+  auto& cDAG = c.comp_info.comp_DAG;
+  if (cDAG.edgeless() && !c.host.edgeless()) { const Node r = cDAG.root(); cDAG.add_child(r, c.host.root()); cDAG.remove_node(r); }
+  VisibleComponentRule<VcrContain> rule(c);
+  std::string out;
+  if (cDAG.edgeless()) { out += "EDGELESS " + std::to_string((size_t)cDAG.root()) + "\n"; }
+  typename VisibleComponentRule<VcrContain>::PathProfile num_paths;
+  HashSet<Node> half;
+  std::vector<Node> order;
+  for (const Node u : cDAG.dfs().postorder()) order.push_back(u);
+  for (const Node u : order) {
+    out += "O " + std::to_string((size_t)u) + ":";
+    for (const Node v : cDAG.children(u)) out += " " + std::to_string((size_t)v);
+    out += "\n";
+  }
+  std::vector<Node> eligible;
+  for (const Node u : order) {
+    const bool h = cDAG.edgeless() ? true : rule.is_half_eligible(u, num_paths, half);
+    const bool e = h && c.host[u].visible_leaf != NoNode;
+    if (h) half.emplace(u);
+    if (e) eligible.push_back(u);
+    out += "H " + std::to_string((size_t)u) + " " + (h ? "1" : "0") + " " + (e ? "1" : "0") + "\n";
+  }
+  fputs(out.c_str(), stdout); fflush(stdout);
+  for (const Node u : eligible) {
+    const Node leaf = c.host[u].visible_leaf;
+    const auto it = c.HG_label_match.find(c.host.label(leaf));
+    if (it == c.HG_label_match.end()) { printf("R %zu %zu NOLABEL\n", (size_t)u, (size_t)leaf); continue; }
+    const Node gleaf = it->second.second;
+    TreeInComponent<ROMulTree<>, VcrContain::RWGuest, true> tic(c.host, c.guest, c.HG_label_match, u);
+    const Node v = tic.highest_displayed_ancestor(gleaf);
+    printf("R %zu %zu %zu\n", (size_t)u, (size_t)leaf, (size_t)v); fflush(stdout);
+  }
 }
 
 static std::vector<std::string> read_lines(const char* fn) {
@@ -262,13 +325,13 @@ int main(int argc, char** argv) {
     printf("%s\n", out.c_str());
     return 0;
   }
-  if (mode == "whomul" || mode == "hda") {
+  if (mode == "whomul" || mode == "hda" || mode == "vcr") {
     for (size_t i = 0; i + 1 < L.size(); i += 2) {
       fflush(stdout);
       pid_t pid = fork();
       if (pid == 0) {
         std::cout.setstate(std::ios::badbit);
-        try { if (mode == "whomul") run_whomul(L[i], L[i + 1]); else run_hda(L[i], L[i + 1]); } catch (...) { printf("EXC\n"); }
+        try { if (mode == "whomul") run_whomul(L[i], L[i + 1]); else if (mode == "hda") run_hda(L[i], L[i + 1]); else run_vcr(L[i], L[i + 1]); } catch (...) { printf("EXC\n"); }
         fflush(stdout); _exit(0);
       }
       int st = 0; waitpid(pid, &st, 0);

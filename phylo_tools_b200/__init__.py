@@ -460,6 +460,21 @@ def net_tree_components(succ_off, succ_adj):
     return comp, vis, [(int(x >> 32), int(x & 0xFFFFFFFF)) for x in e]
 
 
+def net_visible_component(succ_off, succ_adj, host_label, guest_parent, guest_label, root=-1, leaf=-1, unzip_cap=0):
+    """pt_net_visible_component (VisibleComponentRule, utils/containment.hpp:603-725) -> (eligibility uint8[n], root, visible leaf,
+    guest node); eligibility bits: 1 half-eligible, 2 eligible, 4 eligible and lowest; -1 where the rule has no answer"""
+    so = np.ascontiguousarray(succ_off, dtype=np.int32); sa = np.ascontiguousarray(succ_adj, dtype=np.int32)
+    hl = np.ascontiguousarray(host_label, dtype=np.int32); gp = np.ascontiguousarray(guest_parent, dtype=np.int32); gl = np.ascontiguousarray(guest_label, dtype=np.int32)
+    n, m, nt = len(so) - 1, len(sa), len(gp)
+    if len(hl) != n or len(gl) != nt:
+        raise ValueError("label arrays do not match the node counts")
+    el = np.zeros(n, dtype=np.uint8)
+    r, lf, g = C.c_int32(-1), C.c_int32(-1), C.c_int32(-1)
+    _check(_L.pt_net_visible_component(n, m, so.ctypes.data, sa.ctypes.data if m else None, hl.ctypes.data, nt, gp.ctypes.data, gl.ctypes.data, int(root), int(leaf), int(unzip_cap),
+                                       el.ctypes.data, C.byref(r), C.byref(lf), C.byref(g), None), "pt_net_visible_component")
+    return el, r.value, lf.value, g.value
+
+
 def highest_displayed(guest_parent, who, host_root):
     """pt_tree_highest_displayed: int32[nt], TreeInComponent::highest_displayed_ancestor (utils/containment.hpp:328-344) of every
     guest node, from the table who_displays returned"""

@@ -671,4 +671,132 @@ int pt_net_tree_components(int64_t n, int64_t m, const int32_t* succ_off, const 
   return PT_OK;
 }
 
+// ---- VisibleComponentRule (utils/containment.hpp:603-725) as a query: which tree component the rule would treat, and what it would match it with.
+// The device does the work that grows with the network -- component roots, visible leaves and the reticulation-path walks behind the component DAG
+// (pt_net_tree_components: one arc per PATH, so the multiplicity of an arc IS the path count is_half_eligible :664-676 accumulates), the unfolding
+// below the chosen root (pt_net_unzip), the tree-in-tree DP on it and the climb (pt_who_*); the eligibility test itself runs over the component
+// DAG (at most r + 1 nodes) on the host.  Path counts are taken ONCE per arc: the reference re-walks the reticulations above a root v for every
+// component above v and adds to the same counters each time (:670), so its answer depends on the order in which its hash containers yield the
+// roots; what it calls half-eligible is always half-eligible here (counts only grow there), see tests/test_oracle.py.
+int pt_net_visible_component(int64_t n, int64_t m, const int32_t* succ_off, const int32_t* succ_adj, const int32_t* host_label, int64_t nt, const int32_t* guest_parent,
+                             const int32_t* guest_label, int32_t want_root, int32_t want_leaf, int64_t unzip_cap, uint8_t* eligibility, int32_t* root_out, int32_t* leaf_out,
+                             int32_t* guest_node_out, void* stream) {
+  if (n <= 0 || m < 0 || nt <= 0 || !succ_off || (!succ_adj && m > 0) || !host_label || !guest_parent || !guest_label || !root_out || !leaf_out || !guest_node_out ||
+      want_root >= n || want_leaf >= n)
+    return set_error(PT_ERR_INVALID, "pt_net_visible_component: bad argument");
+  *root_out = *leaf_out = *guest_node_out = -1;
+  std::vector<int32_t> comp((size_t)n), vis((size_t)n);
+  std::vector<int64_t> arcs((size_t)std::max<int64_t>(4 * m, 16));
+  int64_t cnt = 0;
+  if (int rc = pt_net_tree_components(n, m, succ_off, succ_adj, comp.data(), vis.data(), arcs.data(), (int64_t)arcs.size(), &cnt, PT_MEM_HOST, stream)) return rc;
+  if (cnt > (int64_t)arcs.size()) {
+    arcs.assign((size_t)cnt, 0);
+    if (int rc = pt_net_tree_components(n, m, succ_off, succ_adj, comp.data(), vis.data(), arcs.data(), (int64_t)arcs.size(), &cnt, PT_MEM_HOST, stream)) return rc;
+  }
+  arcs.resize((size_t)cnt);
+  std::sort(arcs.begin(), arcs.end());
+  // component DAG with multiplicities: kids[c] = (root below, number of reticulation paths from tree nodes of c to it)
+  std::vector<int32_t> indeg((size_t)n, 0);
+  for (int64_t e = 0; e < m; ++e) if (succ_adj[e] >= 0 && succ_adj[e] < n) ++indeg[(size_t)succ_adj[e]];
+  int32_t net_root = -1;
+  for (int64_t v = 0; v < n; ++v) if (indeg[(size_t)v] == 0) { net_root = (int32_t)v; break; }
+  if (net_root < 0) return set_error(PT_ERR_INVALID, "pt_net_visible_component: the network has no root");
+  std::vector<int32_t> node_of;                 // component-DAG nodes
+  std::vector<int32_t> idx((size_t)n, -1);
+  auto id_of = [&](int32_t v) { if (idx[(size_t)v] < 0) { idx[(size_t)v] = (int32_t)node_of.size(); node_of.push_back(v); } return idx[(size_t)v]; };
+  id_of(net_root);
+  std::vector<std::vector<std::pair<int32_t, int32_t>>> kids;
+  for (size_t i = 0; i < arcs.size();) {
+    size_t j = i;
+    while (j < arcs.size() && arcs[j] == arcs[i]) ++j;
+    const int32_t a = id_of((int32_t)(arcs[i] >> 32)), b = id_of((int32_t)(arcs[i] & 0xffffffffll));
+    if (kids.size() < node_of.size()) kids.resize(node_of.size());
+    kids[(size_t)a].emplace_back(b, (int32_t)(j - i));
+    i = j;
+  }
+  kids.resize(node_of.size());
+  const int K = (int)node_of.size();
+  // children first (iterative post-order over the DAG from every node), then the test of :652-687 with every count taken once
+  std::vector<int8_t> half((size_t)K, -1);
+  std::vector<uint8_t> elig_below((size_t)K, 0);
+  std::vector<std::vector<std::pair<int32_t, int32_t>>> paths((size_t)K);   // (root below, paths) for half-eligible nodes, sorted by root
+  std::vector<std::pair<int, size_t>> stack;
+  for (int start = 0; start < K; ++start) {
+    if (half[(size_t)start] >= 0) continue;
+    stack.emplace_back(start, 0);
+    half[(size_t)start] = -2;   // on the stack
+    while (!stack.empty()) {
+      const int u = stack.back().first;
+      if (stack.back().second < kids[(size_t)u].size()) {
+        const int v = kids[(size_t)u][stack.back().second++].first;
+        if (half[(size_t)v] == -1) { half[(size_t)v] = -2; stack.emplace_back(v, 0); }
+        else if (half[(size_t)v] == -2) return set_error(PT_ERR_INVALID, "pt_net_visible_component: the component DAG has a cycle");
+        continue;
+      }
+      stack.pop_back();
+      bool ok = true;
+      std::vector<std::pair<int32_t, int32_t>> acc;
+      for (const auto& vc : kids[(size_t)u]) {
+        const int v = vc.first;
+        elig_below[(size_t)u] |= elig_below[(size_t)v] | (uint8_t)(half[(size_t)v] == 1 && vis[(size_t)node_of[(size_t)v]] >= 0);
+        if (half[(size_t)v] != 1 || vc.second > 1) { ok = false; continue; }
+        acc.emplace_back(v, 1);
+        for (const auto& xp : paths[(size_t)v]) acc.push_back(xp);
+      }
+      if (ok) {
+        std::sort(acc.begin(), acc.end());
+        for (size_t i = 0; i < acc.size() && ok;) {
+          size_t j = i; int32_t c = 0;
+          while (j < acc.size() && acc[j].first == acc[i].first) c += acc[j++].second;
+          if (c > 1) ok = false;
+          paths[(size_t)u].emplace_back(acc[i].first, c);
+          i = j;
+        }
+        if (!ok) paths[(size_t)u].clear();
+      }
+      half[(size_t)u] = ok ? 1 : 0;
+    }
+  }
+  if (eligibility) {
+    memset(eligibility, 0, (size_t)n);
+    for (int k = 0; k < K; ++k) {
+      const int32_t v = node_of[(size_t)k];
+      const bool e = half[(size_t)k] == 1 && vis[(size_t)v] >= 0;
+      eligibility[(size_t)v] = (uint8_t)((half[(size_t)k] == 1 ? 1 : 0) | (e ? 2 : 0) | (e && !elig_below[(size_t)k] ? 4 : 0));
+    }
+  }
+  // the root the rule treats: the first eligible one in a post-order of the component DAG (:689-704), i.e. an eligible root without an eligible
+  // root below it -- the one with the smallest id here -- or the caller's choice
+  int32_t rt = want_root;
+  if (rt >= 0) { if (idx[(size_t)rt] < 0) return set_error(PT_ERR_INVALID, "pt_net_visible_component: node %d is not a component root", rt); }
+  else for (int k = 0; k < K; ++k) {
+    const int32_t v = node_of[(size_t)k];
+    if (half[(size_t)k] == 1 && vis[(size_t)v] >= 0 && !elig_below[(size_t)k] && (rt < 0 || v < rt)) rt = v;
+  }
+  if (rt < 0) return PT_OK;
+  *root_out = rt;
+  const int32_t leaf = want_leaf >= 0 ? want_leaf : vis[(size_t)rt];
+  *leaf_out = leaf;
+  if (leaf < 0 || host_label[(size_t)leaf] < 0) return PT_OK;
+  // treat_comp_root :623-644: the guest leaf with the visible leaf's label, then the highest ancestor still displayed below rt
+  std::vector<uint8_t> has_child((size_t)nt, 0);
+  for (int64_t t = 0; t < nt; ++t) if (guest_parent[(size_t)t] >= 0 && guest_parent[(size_t)t] < nt) has_child[(size_t)guest_parent[(size_t)t]] = 1;
+  int32_t gleaf = -1;
+  for (int64_t t = 0; t < nt; ++t) if (!has_child[(size_t)t] && guest_label[(size_t)t] == host_label[(size_t)leaf]) { gleaf = (int32_t)t; break; }
+  if (gleaf < 0) return PT_OK;
+  int64_t count = 0;
+  if (int rc = pt_net_unzip(n, m, succ_off, succ_adj, host_label, rt, nullptr, nullptr, nullptr, 0, &count, PT_MEM_HOST, stream)) return rc;
+  if (count > (unzip_cap > 0 ? unzip_cap : ((int64_t)1 << 26)))
+    return set_error(PT_ERR_UNSUPPORTED, "pt_net_visible_component: the unfolding below node %d has %lld nodes (cap %lld)", rt, (long long)count, (long long)unzip_cap);
+  std::vector<int32_t> par((size_t)count), lab((size_t)count), org((size_t)count), hda((size_t)nt);
+  if (int rc = pt_net_unzip(n, m, succ_off, succ_adj, host_label, rt, par.data(), lab.data(), org.data(), count, &count, PT_MEM_HOST, stream)) return rc;
+  pt_who* W = nullptr;
+  if (int rc = pt_who_build(&W, par.data(), lab.data(), count, guest_parent, guest_label, nt, PT_MEM_HOST, stream)) return rc;
+  const int rc = pt_who_highest_displayed(W, 0, hda.data(), PT_MEM_HOST, stream);
+  pt_who_free(W);
+  if (rc) return rc;
+  *guest_node_out = hda[(size_t)gleaf];
+  return PT_OK;
+}
+
 }  // extern "C"

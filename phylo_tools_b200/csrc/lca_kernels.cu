@@ -21,7 +21,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 #include "cuda_common.cuh"
 

@@ -322,4 +322,37 @@ class TreeComponentInfos {
   const EdgeVec& comp_DAG_edges() const { return dag_; }
 };
 
+// VisibleComponentRule (utils/containment.hpp:603-725) as a query over pt_net_visible_component: which tree component of the host the
+// rule would treat, the leaf that sees it, and the guest node treat_comp_root would match it with.  The reference applies the rule inside
+// its solver's loop; here the solver needs no such rule (the batch solver is exact without it), so this is the caller-visible answer to
+// "which part of the host displays which subtree of the guest".  Labels must be cleaned as TreeInNetContainment::init does (:1110-1125).
+template <class Host, class Guest>
+class VisibleComponentRule {
+  std::vector<uint8_t> elig_;
+  Node root_ = NoNode, leaf_ = NoNode, guest_node_ = NoNode;
+
+ public:
+  VisibleComponentRule(const Host& host, const Guest& guest, const Node want_root = NoNode, const Node want_leaf = NoNode) : elig_(host.num_nodes(), 0) {
+    std::unordered_map<std::string, int32_t> dict;
+    auto id_of = [&](const std::string& s) -> int32_t { if (s.empty()) return -1; return dict.emplace(s, (int32_t)dict.size()).first->second; };
+    std::vector<int32_t> hl(host.num_nodes(), -1), gl(guest.num_nodes(), -1);
+    for (Node v = 0; v < host.num_nodes(); ++v) if (host.is_leaf(v)) hl[v] = id_of(host.label(v));
+    for (Node v = 0; v < guest.num_nodes(); ++v) if (guest.is_leaf(v)) gl[v] = id_of(guest.label(v));
+    const std::vector<int32_t> gp = guest.parent_array();
+    int32_t r = -1, l = -1, g = -1;
+    throw_status(pt_net_visible_component((int64_t)host.num_nodes(), (int64_t)host.num_edges(), host.succ_off().data(), host.succ_adj().data(), hl.data(), (int64_t)guest.num_nodes(),
+                                          gp.data(), gl.data(), want_root == NoNode ? -1 : (int32_t)want_root, want_leaf == NoNode ? -1 : (int32_t)want_leaf, 0, elig_.data(), &r, &l, &g, nullptr),
+                 "pt_net_visible_component");
+    if (r >= 0) root_ = (Node)r;
+    if (l >= 0) leaf_ = (Node)l;
+    if (g >= 0) guest_node_ = (Node)g;
+  }
+  bool is_half_eligible(const Node u) const { return elig_.at(u) & 1; }        // :652-687
+  bool is_eligible(const Node u) const { return elig_.at(u) & 2; }
+  Node get_eligible_component_root() const { return root_; }                   // :689-704 (NoNode: the rule does not apply)
+  Node visible_leaf() const { return leaf_; }
+  Node matched_guest_node() const { return guest_node_; }                      // the v of match_nodes(u, v) in treat_comp_root :623-644
+  bool apply() const { return root_ != NoNode && guest_node_ != NoNode; }
+};
+
 }  // namespace PT

@@ -136,6 +136,18 @@ int main(int argc, char** argv) {
     for (Node v = 0; v < hn; ++v) assert(ci.comp_root(v) == 0);
     assert(ci.visible_leaf(0) != NoNode && N.is_leaf(ci.visible_leaf(0)) && ci.comp_DAG_edges().empty());
   }
+  // VisibleComponentRule (containment.hpp:603-725) on the pair `ref_tc vcr` prints as "R 9 11 2" (tests/golden/vcr_ref.json item 3): the tree
+  // component below the reticulation is 1/2-eligible and seen by leaf 11, the root (two host paths to it) is not; guest node 2 = (x,y)
+  {
+    EdgeVec he, ge; LabelMapDefault hl, gl;
+    const size_t hn = parse_newick(std::string("(((a,((x,y))#H1),b),((c,#H1),d));"), he, hl), gn = parse_newick(std::string("((a,b),((c,d),(x,y)));"), ge, gl);
+    MyNet N(he, hl, consecutive_tag(), hn); MyTree G(ge, gl, consecutive_tag(), gn);
+    VisibleComponentRule<MyNet, MyTree> vc(N, G);
+    assert(vc.apply() && vc.get_eligible_component_root() == 9 && vc.matched_guest_node() == 2 && vc.is_half_eligible(9) && !vc.is_half_eligible(0));
+    assert(N.is_leaf(vc.visible_leaf()));
+    VisibleComponentRule<MyNet, MyTree> vc2(N, G, 9, 11);
+    assert(vc2.visible_leaf() == 11 && vc2.matched_guest_node() == 2);
+  }
   // the reference's class names for LCA / RMQ (rmq/lca.hpp:79-106, rmq/rmq.hpp:63-72): lca<Tree>, sparse_rmq<It>::query / query_offset
   {
     lca<MyTree> L3(T2);

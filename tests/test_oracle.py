@@ -218,3 +218,41 @@ def test_unzip_and_hda_oracle_equal_reference(oracle):
             assert int(hda[int(v)]) == want, (it["host"], it["guest"], v, int(hda[int(v)]), want)
         checked += 1
     assert checked >= 150
+
+
+def test_visible_component_rule_restatement_equals_reference(oracle):
+    """VisibleComponentRule::is_half_eligible (utils/containment.hpp:652-687) restated in oracle/pt_oracle.py, against the reference run on
+    fresh pairs (tests/golden/vcr_ref.json, `ref_tc vcr`).  Replayed in the reference's own visiting order the loop gives the reference's
+    answer for every component root of every pair; with every path counted once (the library's semantics) a root the reference accepts is
+    always accepted, and the two differ only where a root has several components above it (the reference re-walks it and doubles its
+    counters: order-dependent).  For every eligible root the guest node the reference would match it with equals the oracle's
+    unzip + DP + climb below that root."""
+    from conftest import load_golden
+    gold = load_golden("vcr_ref.json")
+    checked = differ = treated = 0
+    for it in gold["items"]:
+        assert it.get("reference") != "CRASH"
+        off, adj, hl, gp, gl, names = _net_arrays(oracle, it["host"], it["guest"])
+        comp, arcs, root = oracle.component_dag(off, adj)
+        if not arcs:
+            continue      # one tree component: the reference's component DAG is a stub there (containment.hpp:1092-1098)
+        ref = {int(k): bool(v[0]) for k, v in it["half"].items()}
+        assert oracle.vcr_half_eligible(off, adj, order=it["order"]) == ref, it["host"]
+        once = oracle.vcr_half_eligible(off, adj)
+        assert set(once) == set(ref)
+        assert all(once[u] for u, h in ref.items() if h), it["host"]
+        differ += once != ref
+        for u, leaf, v in it["treated"]:
+            par, lab, org = oracle.unzip(off, adj, hl, u)
+            woff, wadj = oracle.mul_who_displays(par, lab, gp, gl)
+            hda = oracle.highest_displayed_lists(gp, woff, wadj, 0)
+            gleaf = [t for t in range(len(gp)) if gl[t] == hl[leaf] and t not in set(gp.tolist())][0]
+            assert int(hda[gleaf]) == v, (it["host"], it["guest"], u, leaf)
+            treated += 1
+        checked += 1
+    assert checked >= 140 and treated >= 250 and 5 <= differ <= 40
+    # hand-made: the tree component {x, y} hangs below a reticulation both of whose parents sit in the ROOT's component: two host paths
+    # from the root to it, so the root is not 1/2-eligible while the lower root trivially is
+    off, adj, hl, gp, gl, names = _net_arrays(oracle, "(((a,((x,y))#H1),b),((c,#H1),d));", "((a,b),((c,d),(x,y)));")
+    assert oracle.vcr_half_eligible(off, adj) == {9: True, 0: False}
+
