@@ -61,6 +61,7 @@ struct pt_comm {
   unsigned long long* d_cnt = nullptr;  // staging for the counters
 };
 
+extern "C" void ptgpu_batch_outputs_prezeroed(pt_batch* b);   // tc_kernels.cu
 using ptgpu::dev_alloc;
 using ptgpu::dev_free;
 using ptgpu::set_error;
@@ -124,6 +125,7 @@ int pt_batch_contain_sharded(pt_batch* b, pt_comm* c, const pt_options* opt, int
   pt_counters local;
   memset(&local, 0, sizeof(local));
   if (local_instances > 0) {
+    ptgpu_batch_outputs_prezeroed(b);
     if (int rc = pt_batch_contain(b, opt, full_bits + w0, full_status ? full_status + first_instance : nullptr, PT_MEM_DEVICE, total ? &local : nullptr, stream)) return rc;
   }
   // status bytes are disjoint per rank as well and are summed as 32-bit words (the caller pads the vector to a multiple of 4,

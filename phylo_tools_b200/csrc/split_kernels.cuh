@@ -29,6 +29,17 @@
 
 namespace ptgpu {
 
+// every instance's ranges must lie inside the arrays (their lengths are the last entries of the offset tables) and follow each other
+// without gaps or overlaps: the concatenation below writes by these offsets.  out[0..2] = the three lengths, out[3] = 1 if not
+__global__ void sp_offsets_check_kernel(int64_t B, const int64_t* __restrict__ hnode_off, const int64_t* __restrict__ harc_off, const int64_t* __restrict__ gnode_off, int64_t* __restrict__ out) {
+  const int64_t NH = hnode_off[B], MH = harc_off[B], NG = gnode_off[B];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = NH; out[1] = MH; out[2] = NG; if (hnode_off[0] != 0 || harc_off[0] != 0 || gnode_off[0] != 0 || NH < 0 || MH < 0 || NG < 0) out[3] = 1; }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+    if (hnode_off[i + 1] < hnode_off[i] || harc_off[i + 1] < harc_off[i] || gnode_off[i + 1] < gnode_off[i] || hnode_off[i] < 0 || harc_off[i] < 0 || gnode_off[i] < 0 ||
+        hnode_off[i + 1] > NH || harc_off[i + 1] > MH || gnode_off[i + 1] > NG)
+      out[3] = 1;
+}
+
 template <class S>
 __global__ void sp_concat_kernel(int64_t B, const int64_t* __restrict__ hnode_off, const int64_t* __restrict__ harc_off, const int64_t* __restrict__ gnode_off,
                                  const S* __restrict__ succ_off, const S* __restrict__ succ_adj, const S* __restrict__ hlabel, const S* __restrict__ tparent, const S* __restrict__ tlabel,
@@ -228,10 +239,14 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
     fprintf(stderr, "[split] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
     t_last = now;
   };
-  int64_t tails[3];
-  SP_TRY(cudaMemcpyAsync(&tails[0], d_hnode_off + B, 8, cudaMemcpyDeviceToHost, s)); SP_TRY(cudaMemcpyAsync(&tails[1], d_harc_off + B, 8, cudaMemcpyDeviceToHost, s));
-  SP_TRY(cudaMemcpyAsync(&tails[2], d_gnode_off + B, 8, cudaMemcpyDeviceToHost, s));
+  int64_t tails[4] = {0, 0, 0, 0};
+  int64_t* d_tails = (int64_t*)dalloc(32);
+  SP_PTR(d_tails);
+  SP_TRY(cudaMemsetAsync(d_tails, 0, 32, s));
+  sp_offsets_check_kernel<<<std::max(1, (int)std::min<int64_t>(dp.sms * 4, (B + 255) / 256)), 256, 0, s>>>(B, d_hnode_off, d_harc_off, d_gnode_off, d_tails);
+  SP_TRY(cudaMemcpyAsync(tails, d_tails, 32, cudaMemcpyDeviceToHost, s));
   SP_TRY(cudaStreamSynchronize(s));
+  if (tails[3]) { cleanup(); return PT_OK; }   // malformed offset tables: the executors report the instances concerned (PT_INST_BAD_GRAPH)
   const int64_t NH = tails[0], MH = tails[1], NG = tails[2], N = NH + 1, M = MH + B, NT = NG + 1, NL = NH + NG;
   if (N > INT32_MAX / 2 || M > INT32_MAX / 2 || NT > INT32_MAX / 2 || B > 65535) { cleanup(); return PT_OK; }
   const int grid = dp.sms * 8;

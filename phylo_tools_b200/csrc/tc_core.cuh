@@ -200,7 +200,8 @@ struct TcSolver {
   PT_NI int load(const TcInst& in) {
     ex.phase = 1;
     n = in.n; m = in.m; nt = in.nt;
-    if (n > w.capN || m > w.capM || nt > w.capNT || n < 0 || m < 0 || nt < 0) return TCS_TOO_LARGE;
+    if (n < 0 || m < 0 || nt < 0) return TCS_BAD_GRAPH;   // malformed offset tables (batch_inst)
+    if (n > w.capN || m > w.capM || nt > w.capNT) return TCS_TOO_LARGE;
     if (ex.tid() == 0) { PT_NOUNROLL for (int k = 0; k < TcWork<I>::kScalars; ++k) w.sc[k] = 0; }
     ex.sync();
     // structure checks on the CSR offsets (branch-free bodies: the loads of consecutive iterations overlap)

@@ -13,6 +13,7 @@
 #include "tc_core.cuh"
 
 #include <cooperative_groups.h>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -446,7 +447,10 @@ __device__ __forceinline__ void batch_inst(const TcSource& src, int item, TcInst
   const int64_t hb = src.hnode_off[item], ab = src.harc_off[item], gb = src.gnode_off[item];
   const int64_t nn = src.hnode_off[item + 1] - hb, mm = src.harc_off[item + 1] - ab, tt = src.gnode_off[item + 1] - gb;
   in.n = (int)min(nn, (int64_t)1 << 30); in.m = (int)min(mm, (int64_t)1 << 30); in.nt = (int)min(tt, (int64_t)1 << 30);
-  if (nn < 0 || mm < 0 || tt < 0) { in.n = in.m = in.nt = -1; }
+  // the offset tables are validated HERE, per instance (reading 2.4 MB of tables on one host core before the launch cost 0.14 ms per
+  // 10^5 instances): every range must lie inside the arrays, whose lengths are the last entries of the tables
+  const int64_t B = src.count;
+  if (nn < 0 || mm < 0 || tt < 0 || hb < 0 || ab < 0 || gb < 0 || hb + nn > src.hnode_off[B] || ab + mm > src.harc_off[B] || gb + tt > src.gnode_off[B]) { in.n = in.m = in.nt = -1; }
   // the degree layout (uint8_t) has n entries per instance in succ_off, the offset layouts n + 1
   in.succ_off = static_cast<const char*>(src.succ_off) + ((hb + (TcLayout<S>::kDegrees ? 0 : item)) << sh); in.succ_adj = static_cast<const char*>(src.succ_adj) + (ab << sh);
   in.hlabel = static_cast<const char*>(src.hlabel) + (hb << sh); in.tparent = static_cast<const char*>(src.tparent) + (gb << sh);
@@ -464,7 +468,8 @@ __device__ __forceinline__ void batch_inst(const TcSource& src, int item, TcInst
 // launch.  Every wait is bounded by a watchdog (ctl->abort), so a lost flag becomes an error instead of a hang.
 struct TcCtl {
   int32_t ticket, pool_tail, pool_head, finished, abort, overflow, done, pad;
-  unsigned long long t_first, t_batch_done, t_last;  // %globaltimer (ns): first warp in, first warp that found the ticket exhausted, last warp out
+  unsigned long long t_first, t_batch_done_inv, t_last;  // %globaltimer (ns): first warp in, ~(first warp that found the ticket exhausted) -- kept inverted so
+                                                          // that the ONE memset that zeroes the control block initialises it (atomicMax of ~t = min of t) --, last warp out
 };
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 struct TcPool {   // fixed-stride slots of element type S (see TcLayout); ready[slot] == epoch once the slot is complete
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(MAXT, 1) tc_persistent_kernel(TcSource src, Tc
           const int i = atomicAdd(&ctl->ticket, 1);
           if (i < B) { item = i; break; }
           batch_done = true;
-          atomicMin(&ctl->t_batch_done, global_ns());
+          atomicMax(&ctl->t_batch_done_inv, ~global_ns());
           continue;
         }
         // nothing to do: wait for the claimed slot or for the end of the job
@@ -567,6 +572,7 @@ __global__ void __launch_bounds__(MAXT, 1) tc_persistent_kernel(TcSource src, Tc
         code = sv.rule_loop(&st, &x);
         ex.phase = 13;
         if (code != TC_BRANCH) break;
+        if (chunks.flags & 4) { code = TC_NOT; break; }   // measuring aid: no branching at all (wrong verdicts; shows the tail without chains)
         // ---- branch on x: children 1 .. d-1 go to the pool, child 0 continues in place -------------------------------------
         const int d = sv.indeg(x);
         int base = -1;
@@ -856,6 +862,7 @@ extern "C" int pt_debug_profile(unsigned long long* out128) {
 static constexpr int kDefaultMaxWarps = 24;  // measured on config 2: 16 warps 8.5 ms, 20: 8.0, 24: 7.6, 28: 8.2 (instruction fetch, not latency, is the limit)
 
 struct pt_batch {
+  bool outputs_prezeroed = false;   // set by pt_batch_contain_sharded for the next call
   int64_t B = 0;
   bool owns_input = false;
   int64_t *d_hnode_off = nullptr, *d_harc_off = nullptr, *d_gnode_off = nullptr;
@@ -999,7 +1006,13 @@ static cudaError_t launch_persistent(int wpc, int grid, size_t smem, cudaStream_
   using I = int16_t;
   auto k768 = tc_persistent_kernel<I, S, 768>; auto k1024 = tc_persistent_kernel<I, S, 1024>;
   auto kern = wpc > 24 ? k1024 : k768;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the attribute is per function and device: set it again only when it has to grow (one process may drive several devices)
+  static std::mutex mu; static size_t have[2][64] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  cudaError_t e = cudaSuccess;
+  { std::lock_guard<std::mutex> g(mu);
+    size_t& h = have[wpc > 24 ? 1 : 0][dev & 63];
+    if (h < smem) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e == cudaSuccess) h = smem; } }
   if (e != cudaSuccess) return e;
   kern<<<grid, wpc * 32, smem, s>>>(src, pool, ch, ctl, (int)b->maxN, (int)b->maxM, (int)b->maxNT, (int)b->maxL, warp_bytes, bits, stat, b->d_branched, b->d_counters);
   return cudaGetLastError();
@@ -1053,6 +1066,14 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   if (d->index_bytes != 0 && d->index_bytes != 1 && d->index_bytes != 2 && d->index_bytes != 4) return set_error(PT_ERR_INVALID, "pt_batch_create: index_bytes must be 0, 1, 2 or 4");
   if (int rc = require_device()) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  static const bool trace = getenv("PT_CREATE_TRACE") != nullptr;   // measuring aid: host time of every phase of this call
+  auto t_prev = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[create] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
+    t_prev = t;
+  };
   pt_batch* b = new (std::nothrow) pt_batch();
   if (!b) return set_error(PT_ERR_NOMEM, "out of host memory");
   const int64_t B = b->B = d->num_instances;
@@ -1070,11 +1091,11 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   const bool need_max = !(b->maxN > 0 && b->maxNT > 0 && b->maxL > 0) && B > 0;
   if (d->mem == PT_MEM_HOST) {
     // structural sanity of the offset tables before trusting them for the copy sizes
-    for (int64_t i = 0; i < B; ++i)
-      if (d->host_node_off[i + 1] < d->host_node_off[i] || d->host_arc_off[i + 1] < d->host_arc_off[i] || d->guest_node_off[i + 1] < d->guest_node_off[i])
-        return fail(set_error(PT_ERR_INVALID, "pt_batch_create: offset tables must be non-decreasing (instance %lld)", (long long)i));
+    // only the entries that size the copies are looked at here (first, last and the chunk boundaries below); every instance's own range is
+    // checked against the array lengths by the kernel that loads it (batch_inst -> PT_INST_BAD_GRAPH)
     if (d->host_node_off[0] != 0 || d->host_arc_off[0] != 0 || d->guest_node_off[0] != 0) return fail(set_error(PT_ERR_INVALID, "pt_batch_create: offset tables must start at 0"));
     const int64_t NH = d->host_node_off[B], MH = d->host_arc_off[B], NG = d->guest_node_off[B];
+    if (NH < 0 || MH < 0 || NG < 0) return fail(set_error(PT_ERR_INVALID, "pt_batch_create: offset tables must be non-decreasing"));
     if (need_max) {
       for (int64_t i = 0; i < B; ++i) {
         b->maxN = std::max<int32_t>(b->maxN, (int32_t)std::min<int64_t>(d->host_node_off[i + 1] - d->host_node_off[i], INT32_MAX));
@@ -1087,10 +1108,12 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       b->maxL = std::max(b->maxL, ml);
     }
     b->owns_input = true;
+    mark("checks");
     // offset tables first (small), then the five data arrays chunk by chunk on the copy stream
     if ((rc = upload(&b->d_hnode_off, d->host_node_off, B + 1, s, &b->h2d_bytes)) || (rc = upload(&b->d_harc_off, d->host_arc_off, B + 1, s, &b->h2d_bytes)) ||
         (rc = upload(&b->d_gnode_off, d->guest_node_off, B + 1, s, &b->h2d_bytes)))
       return fail(rc);
+    mark("offset tables");
     if ((rc = dev_alloc(&b->d_succ_off, (size_t)std::max<int64_t>(NH + (deg ? 0 : B), 1) * esz)) || (rc = dev_alloc(&b->d_succ_adj, (size_t)std::max<int64_t>(MH, 1) * esz)) ||
         (rc = dev_alloc(&b->d_hlabel, (size_t)std::max<int64_t>(NH, 1) * esz)) || (rc = dev_alloc(&b->d_tparent, (size_t)std::max<int64_t>(NG, 1) * esz)) ||
         (rc = dev_alloc(&b->d_tlabel, (size_t)std::max<int64_t>(NG, 1) * esz)))
@@ -1098,8 +1121,10 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
     // Chunks that double in size (1/32, 1/32, 1/16, ... 1/2 of the batch): the persistent kernel starts on a small first chunk
     // and the copy engine stays ahead of the solver from then on (the upload is 3-4 times faster than the solve), with few
     // API calls: their host time comes BEFORE the kernel launch and delays it.
-    b->nchunks = B >= 65536 ? 6 : (B >= 16384 ? 4 : (B >= 4096 ? 2 : 1));   // (a shard of 12 500 instances: 2 chunks = 12 copy calls, not 36)
-    if (const char* e = getenv("PT_TC_CHUNKS")) b->nchunks = std::max(1, std::min((int)pt_batch::kMaxChunks, atoi(e)));  // tuning aid
+    // measured end to end at 12 500 instances (one rank's shard of config 2 at N = 8; profiles/chunks_sweep.sh): 1 chunk 1.49 ms, 2: 1.36, 3: 1.31, 4: 1.32, 6: 1.37
+    b->nchunks = B >= 65536 ? 6 : (B >= 4096 ? 3 : 1);
+    static const int env_chunks = [] { const char* e = getenv("PT_TC_CHUNKS"); return e ? std::max(1, std::min((int)pt_batch::kMaxChunks, atoi(e))) : 0; }();  // tuning aid
+    if (env_chunks) b->nchunks = env_chunks;
     const int32_t* one = b->nchunks > 1 ? pinned_one() : nullptr;
     if (b->nchunks > 1 && (!one || !(b->copy_stream = take_copy_stream()))) { b->nchunks = 1; b->copy_stream = nullptr; }
     cudaStream_t cs = b->nchunks > 1 ? b->copy_stream : s;
@@ -1116,6 +1141,7 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       if (e == cudaSuccess) e = cudaStreamWaitEvent(s, b->flags_zeroed, 0);
       if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: %s", cudaGetErrorString(e)));
     }
+    mark("allocations + flags");
     auto chunk_bound = [&](int k) -> int64_t {
       if (k <= 0) return 0;
       if (k >= b->nchunks) return B;
@@ -1125,6 +1151,8 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       const int64_t i0 = chunk_bound(c), i1 = chunk_bound(c + 1);
       b->chunk_end[c] = i1;
       const int64_t h0 = d->host_node_off[i0], h1 = d->host_node_off[i1], a0 = d->host_arc_off[i0], a1 = d->host_arc_off[i1], g0 = d->guest_node_off[i0], g1 = d->guest_node_off[i1];
+      if (h0 < 0 || h1 < h0 || h1 > NH || a0 < 0 || a1 < a0 || a1 > MH || g0 < 0 || g1 < g0 || g1 > NG)
+        return fail(set_error(PT_ERR_INVALID, "pt_batch_create: offset tables must be non-decreasing (around instance %lld)", (long long)i0));
       auto cp = [&](void* dst, const void* src, int64_t from, int64_t to) -> cudaError_t {
         if (to <= from) return cudaSuccess;
         b->h2d_bytes += (to - from) * (int64_t)esz;
@@ -1141,6 +1169,7 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       }
       if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: upload failed: %s", cudaGetErrorString(e)));
     }
+    mark("chunk copies");
     if (b->nchunks > 1) {  // for an executor that was not expected here (pt_options.path): everything has landed
       cudaError_t e = cudaEventCreateWithFlags(&b->upload_done, cudaEventDisableTiming);
       if (e == cudaSuccess) e = cudaEventRecord(b->upload_done, cs);
@@ -1167,6 +1196,7 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   if (b->idx_bytes == 1 && (b->maxN > 255 || b->maxNT > 255 || b->maxL > 255))
     return fail(set_error(PT_ERR_INVALID, "pt_batch_create: index_bytes = 1 needs at most 255 host nodes, guest nodes and labels per instance"));
   if ((rc = batch_scratch(b))) return fail(rc);
+  mark("scratch");
   *out = b;
   return PT_OK;
 }
@@ -1213,6 +1243,8 @@ int ptgpu_batch_adopt(pt_batch** out, int64_t B, void* const arrays[8], int inde
   return PT_OK;
 }
 int64_t pt_batch_h2d_bytes(const pt_batch* b) { return b ? b->h2d_bytes : 0; }
+// internal (comm.cu): the caller's DEVICE result words / status bytes of the next pt_batch_contain are already zero
+void ptgpu_batch_outputs_prezeroed(pt_batch* b) { if (b) b->outputs_prezeroed = true; }
 // debug / profiling aid (not part of include/pt_gpu.h): phases of the last persistent launch in microseconds --
 // out[0] = first warp in -> first warp that found the batch ticket exhausted, out[1] = from there to the last warp out (the tail),
 // out[2] = pool slots used, out[3] = items finished
@@ -1220,7 +1252,8 @@ int pt_debug_last_phases(pt_batch* b, double out[4]) {
   if (!b || !b->h_ctl) return PT_ERR_INVALID;
   if (b->used_stream_valid) cudaStreamSynchronize(b->used_stream);
   const TcCtl* c = reinterpret_cast<const TcCtl*>(b->h_ctl);
-  out[0] = (double)(c->t_batch_done - c->t_first) / 1e3; out[1] = (double)(c->t_last - c->t_batch_done) / 1e3; out[2] = c->pool_tail; out[3] = c->finished;
+  const unsigned long long t_batch_done = ~c->t_batch_done_inv;
+  out[0] = (double)(t_batch_done - c->t_first) / 1e3; out[1] = (double)(c->t_last - t_batch_done) / 1e3; out[2] = c->pool_tail; out[3] = c->finished;
   return PT_OK;
 }
 int pt_batch_round_ms(const pt_batch* bc, int round, float* ms) {
@@ -1246,8 +1279,10 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   b->used_stream = s; b->used_stream_valid = true;
   uint32_t* bits = out_mem == PT_MEM_DEVICE ? result_bits : b->d_bits;
   uint8_t* stat = (out_mem == PT_MEM_DEVICE && status) ? status : b->d_status;
-  PT_CUDA(cudaMemsetAsync(bits, 0, words * 4, s));
-  PT_CUDA(cudaMemsetAsync(stat, 0, (size_t)B, s));
+  const bool prezeroed = b->outputs_prezeroed && out_mem == PT_MEM_DEVICE;   // pt_batch_contain_sharded has just cleared the whole vectors
+  b->outputs_prezeroed = false;
+  if (!prezeroed) PT_CUDA(cudaMemsetAsync(bits, 0, words * 4, s));
+  if (!prezeroed || stat == b->d_status) PT_CUDA(cudaMemsetAsync(stat, 0, (size_t)B, s));
   PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, b->scratch_bytes, s));   // control block + counters + branched flags
   uint64_t rounds = 0;
   // executors over the same solver: warps with the instance in shared memory (int16 ids, ONE persistent launch), or one CTA /
@@ -1294,7 +1329,8 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     // occupancy: as many warps per SM as shared memory allows (warp_bytes each), in one CTA per SM; the kernel variant
     // (register budget) follows from the warp count
     int max_warps = kDefaultMaxWarps;
-    if (const char* e = getenv("PT_TC_MAX_WARPS")) max_warps = std::max(1, std::min(32, atoi(e)));  // tuning aid
+    static const int env_warps = [] { const char* e = getenv("PT_TC_MAX_WARPS"); return e ? std::max(1, std::min(32, atoi(e))) : 0; }();  // tuning aid
+    if (env_warps) max_warps = env_warps;
     const int wpc = std::max(1, (int)std::min<size_t>((size_t)max_warps, ((size_t)dp.smem_optin) / warp_bytes));
     const size_t smem = (size_t)wpc * warp_bytes;
     const size_t esz = (size_t)b->idx_bytes;
@@ -1325,13 +1361,13 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     src.first = 0; src.count = B; src.is_pool = 0; src.hnode_off = b->d_hnode_off; src.harc_off = b->d_harc_off; src.gnode_off = b->d_gnode_off;
     src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel;
     TcChunks ch{};
-    if (const char* e = getenv("PT_TC_FLAGS")) ch.flags = atoi(e);
+    static const int env_flags = [] { const char* e = getenv("PT_TC_FLAGS"); return e ? atoi(e) : 0; }();   // tuning / measuring aid
+    ch.flags = env_flags;
     if (b->nchunks > 1 && b->d_chunk_ready) { ch.n = b->nchunks; for (int c = 0; c < b->nchunks; ++c) ch.end[c] = (int32_t)b->chunk_end[c]; ch.ready = b->d_chunk_ready; }
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)dp.sms, (B + wpc - 1) / wpc));
     for (int j = 0; j < 2; ++j) if (!b->ev[j]) PT_CUDA(cudaEventCreate(&b->ev[j]));
     PT_CUDA(cudaEventRecord(b->ev[0], s));
     TcCtl* ctl = reinterpret_cast<TcCtl*>(b->d_ticket);
-    PT_CUDA(cudaMemsetAsync(&ctl->t_batch_done, 0xff, 8, s));
     cudaError_t e = b->idx_bytes == 1 ? launch_persistent<uint8_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat)
                   : b->idx_bytes == 2 ? launch_persistent<int16_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat)
                                       : launch_persistent<int32_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat);

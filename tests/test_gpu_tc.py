@@ -107,6 +107,45 @@ def test_error_statuses_do_not_poison_the_batch(pt, path):
     assert c["errors"] == 2
 
 
+@pytest.mark.parametrize("path", [0, 2, 3, 5])
+@pytest.mark.parametrize("compact", [0, 1, 2])
+def test_malformed_offset_tables_are_per_instance_errors(pt, path, compact):
+    """the offset tables are validated on the device, instance by instance (no pass over them on the host before the launch): an entry
+    that makes an instance's range negative or run past the arrays gives PT_INST_BAD_GRAPH for that instance, never an out-of-range
+    read, and the instances that do not touch the damaged entry keep their verdicts; damaged FIRST / LAST entries (they size the
+    upload) are refused by pt_batch_create"""
+    p = pt.Packer()
+    p.add_generated(40, 12, 3, 77, 0)
+    p.add_generated(24, 12, 3, 78, 1)
+    clean = p.arrays(compact=compact)
+    b = pt.Batch(clean)
+    v0, s0, _ = b.contain(path=path)
+    b.free()
+    assert (s0 == 0).all()
+    for table, k in (("host_node_off", 17), ("host_arc_off", 30), ("guest_node_off", 51)):
+        a = {key: (val.copy() if isinstance(val, np.ndarray) else val) for key, val in clean.items()}
+        a[table][k] = a[table][k + 1] + 7                    # instance k: negative size; instance k - 1: runs into its neighbours
+        b = pt.Batch(a)
+        v, s, c = b.contain(path=path)
+        b.free()
+        assert s[k] == 2, (table, k, s[k])                   # PT_INST_BAD_GRAPH
+        keep = np.ones(len(s), dtype=bool); keep[k - 1] = keep[k] = False
+        assert (s[keep] == 0).all() and (v[keep] == v0[keep]).all(), table
+        a[table][k] = 1 << 40                                 # far beyond the arrays
+        b = pt.Batch(a)
+        v, s, c = b.contain(path=path)
+        b.free()
+        assert s[k] == 2 and s[k - 1] == 2 and (s[keep] == 0).all() and (v[keep] == v0[keep]).all()
+    a = {key: (val.copy() if isinstance(val, np.ndarray) else val) for key, val in clean.items()}
+    a["host_node_off"][0] = 3
+    with pytest.raises(Exception):
+        pt.Batch(a)
+    a = {key: (val.copy() if isinstance(val, np.ndarray) else val) for key, val in clean.items()}
+    a["guest_node_off"][-1] = -5
+    with pytest.raises(Exception):
+        pt.Batch(a)
+
+
 def _layouts(p):
     """every input layout the batch fits: int32, int16, and uint8 (out-degrees) when every id fits a byte"""
     a = p.arrays()
