@@ -225,7 +225,9 @@ int pt_rmq_free(pt_rmq* h);
  * (sum(n_i) entries, instance i at host_node_off[i]) instead of n_i + 1 offsets: arc positions may exceed 255 (BASELINE
  * config 2 has m = 258) while every node id, label id and degree fits a byte -- 1 134 B per config-2 instance instead of
  * 2 294 B (int16) or 4 564 B (int32).  Needs at most 255 host nodes, guest nodes and labels per instance.
- *   host_node_off[B+1], host_arc_off[B+1], guest_node_off[B+1]   (int64 prefix sums of n_i, m_i, nt_i)
+ *   host_node_off[B+1], host_arc_off[B+1], guest_node_off[B+1]   (int64 prefix sums of n_i, m_i, nt_i; first entry 0, last entry
+ *                    = the length of the arrays below.  Every instance's range is checked against those lengths by the kernel
+ *                    that loads it: a malformed entry makes the instances it touches PT_INST_BAD_GRAPH, nothing else)
  *   host_succ_off  : sum(n_i + 1) entries; instance i starts at host_node_off[i] + i; values are LOCAL arc
  *                    positions 0..m_i  (the immutable CSR of utils/storage_adj_immutable.hpp:173-261)
  *   host_succ_adj  : sum(m_i) entries at host_arc_off[i]; LOCAL node ids (children)
