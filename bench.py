@@ -9,7 +9,8 @@ step     : one pass of the hot path over the whole batch.  With N GPUs the batch
            result words) leaves the whole verdict vector on every rank.
 value    : whole-job instances/s with the batch RESIDENT in HBM when the timed region starts (CUDA events, max over ranks)
 e2e      : the same through the public C-ABI with HOST (pinned) buffers: pt_batch_create (H2D, uint8 layout) +
-           pt_batch_contain_sharded (kernel + collective) + D2H of the result words + pt_batch_free, every step
+           pt_batch_contain_sharded (kernel + collective) + D2H of the result words + host sync + pt_batch_free, every step;
+           "value" = double-buffered (step k+1's batch is created while step k's kernel runs), "serial_value" = one step after the other
 roofline : dominant kernel = tc_persistent_kernel (the one launch of a step), timed live with CUDA events inside the library;
            algorithmic bytes = 8124 B/instance; peak = MEASURED_PEAKS.json hbm_gbs
 cpu_baseline / --impl reference : the reference's own TreeInNetContainment::displayed() (oracle/_ref/ref_tc, unmodified
@@ -732,29 +733,69 @@ def main():
     pinned_np = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in pinned.items()}
     h2d = 0
 
-    def step_e2e():
+    def time_e2e(pipelined):
+        """K timed steps, each = pt_batch_create from pinned HOST arrays (H2D) + pt_batch_contain_sharded + D2H of the result words + a
+        host wait for that read + pt_batch_free.  serial: one step after the other (the latency view).  pipelined: double-buffered --
+        the host keeps ONE step queued behind the running one: while the kernel of step k runs, step k+1's batch is created (its
+        upload overlaps the solve), its solve and result read are enqueued, and only then the host waits for step k's result and frees
+        it (two pinned input buffers, two result buffers, two handles alive).  Step 0 is issued before the clock starts (pipeline
+        fill) and the last timed iteration still issues a successor, so the timed region holds exactly K creates (K uploads), K
+        launches and K result reads."""
         nonlocal h2d
-        b = pt.Batch(pinned_np, stream=stream)
-        h2d = b.h2d_bytes()
-        comm.contain_sharded(b, first, total_B, full_bits, None, stream=stream)
-        h_bits.copy_(full_bits, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        b.free()
+        bufs = [pinned_np, pinned_np2]
+        hb = [h_bits, h_bits2]
+        state = {"k": 0, "inflight": None}
 
-    for _ in range(args.warmup):
-        step_e2e()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1000.0
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))  # host syncs inside the call: take the larger of device and wall time
-    e2e_val = total_B / (e2e_ms / args.steps / 1000.0)
-    e2e_disp = int(np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[:total_B].sum())
+        def issue(k):
+            nonlocal h2d
+            b = pt.Batch(bufs[k % 2], stream=stream)
+            h2d = b.h2d_bytes()
+            comm.contain_sharded(b, first, total_B, full_bits, None, stream=stream)
+            hb[k % 2].copy_(full_bits, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return (b, ev, k)
+
+        def retire(x):
+            b, ev, k = x
+            ev.synchronize()
+            state["disp"] = hb[k % 2]
+            b.free()
+
+        def step():
+            k = state["k"]; state["k"] = k + 1
+            if pipelined:
+                nxt = issue(k + 1)
+                retire(state["inflight"])
+                state["inflight"] = nxt
+            else:
+                retire(issue(k))
+        if pipelined:
+            state["inflight"] = issue(0)
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        wall_ms = (time.perf_counter() - t0) * 1000.0
+        barrier()
+        if pipelined:
+            retire(state["inflight"])
+        torch.cuda.synchronize()
+        ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))  # the host waits inside every step: take the larger of device and wall time
+        disp = int(np.unpackbits(state["disp"].numpy().view(np.uint8), bitorder="little")[:total_B].sum())
+        return total_B / (ms / args.steps / 1000.0), disp
+
+    h_bits2 = torch.zeros(max(words, 1), dtype=torch.int32).pin_memory()
+    pinned_np2 = {k: (torch.from_numpy(v.copy()).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in pinned_np.items()}
+    e2e_serial, disp_serial = time_e2e(False)
+    e2e_val, e2e_disp = time_e2e(True)
+    if disp_serial != e2e_disp:
+        e2e_disp = -1
     h2d_total = sum_over_ranks(h2d)
 
     out = {"metric": "tree-containment instances/s", "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -766,11 +807,13 @@ def main():
                       "parallelism": "instances sharded %d-way (contiguous ranges), one NCCL all-reduce of the packed result words issued by the library (pt_batch_contain_sharded)" % world if world > 1 else "single GPU",
                       "cpu_affinity": ("%d cores next to the GPU" % numa) if numa else "default"},
            "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": words * 4 * world,
-                   "api": "pt_batch_create(HOST pinned) + pt_batch_contain_sharded + D2H of the result words + pt_batch_free, on every rank", "displayed": e2e_disp},
+                   "api": "pt_batch_create(HOST pinned) + pt_batch_contain_sharded + D2H of the result words + host sync + pt_batch_free, on every rank, every step",
+                   "mode": "double-buffered: while step k's kernel runs the host creates step k+1's batch (its H2D overlaps the solve) and queues its solve + result read, then waits for step k's result; K creates, K launches, K result reads inside the timed region",
+                   "serial_value": e2e_serial, "serial_mode": "one step after the other (upload chunks overlap only the step's own kernel)", "displayed": e2e_disp},
            "gpu_launches": r["launches"] * world, "clocks": clocks, "roofline": roofline,
            "verdicts": {"displayed": r["displayed"], "errors": r["errors"], "expected_displayed": total_B}, "counters": r["counters"],
            "host_generation_s": t_gen}
-    del pinned, pinned_np
+    del pinned, pinned_np, pinned_np2
     # ---- extra: weak scaling, 10^5 instances per GPU ----
     if world > 1 and not args.no_weak:
         wf, wB, wp = make_shard(args.instances * world, SEED + (1 << 30))

@@ -863,6 +863,10 @@ static constexpr int kDefaultMaxWarps = 24;  // measured on config 2: 16 warps 8
 
 struct pt_batch {
   bool outputs_prezeroed = false;   // set by pt_batch_contain_sharded for the next call
+  // pt_batch_free waits for THIS handle's work only (an event recorded behind the last thing a call enqueued), not for everything the
+  // caller has queued on the stream since: a caller that keeps the next batch's solve queued behind this one must not be stalled by the free
+  cudaEvent_t last_work = nullptr;
+  bool work_recorded = false;
   int64_t B = 0;
   bool owns_input = false;
   int64_t *d_hnode_off = nullptr, *d_harc_off = nullptr, *d_gnode_off = nullptr;
@@ -934,7 +938,9 @@ static void give_copy_stream(cudaStream_t s) {
 
 static void batch_release(pt_batch* b) {
   if (!b) return;
-  if (b->used_stream_valid) cudaStreamSynchronize(b->used_stream);  // cached blocks may be handed to another handle at once
+  // cached blocks may be handed to another handle at once: everything this handle has enqueued must be over
+  if (b->work_recorded && b->last_work) cudaEventSynchronize(b->last_work);
+  else if (b->used_stream_valid) cudaStreamSynchronize(b->used_stream);
   if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); give_copy_stream(b->copy_stream); }
   if (b->owns_input) {
     dev_free(b->d_hnode_off); dev_free(b->d_harc_off); dev_free(b->d_gnode_off);
@@ -943,6 +949,7 @@ static void batch_release(pt_batch* b) {
   dev_free(b->d_bits); dev_free(b->d_status); dev_free(b->d_ticket);   // (counters and branched flags live inside d_ticket's block)
   dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); dev_free(b->d_ws); dev_free(b->d_ppool); dev_free(b->d_pready); dev_free(b->d_chunk_ready);
   for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
+  if (b->last_work) cudaEventDestroy(b->last_work);
   for (cudaEvent_t e : b->chunk_ev) if (e) cudaEventDestroy(e);
   if (b->flags_zeroed) cudaEventDestroy(b->flags_zeroed);
   if (b->upload_done) cudaEventDestroy(b->upload_done);
@@ -967,6 +974,13 @@ static int upload(T** dst, const T* src, int64_t count, cudaStream_t s, int64_t*
   return PT_OK;
 }
 
+// marks the end of what a call has enqueued for this handle on its stream (see pt_batch::last_work)
+static void batch_mark_work(pt_batch* b, cudaStream_t s) {
+  b->work_recorded = false;
+  if (!b->last_work && cudaEventCreateWithFlags(&b->last_work, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); b->last_work = nullptr; return; }
+  if (cudaEventRecord(b->last_work, s) == cudaSuccess) b->work_recorded = true; else cudaGetLastError();
+}
+
 // common scratch of a handle (result words, status, flags, counters)
 static int batch_scratch(pt_batch* b) {
   const int64_t B = b->B;
@@ -988,7 +1002,8 @@ static int batch_scratch(pt_batch* b) {
 static int batch_check_ctl(pt_batch* b) {
   if (!b->ctl_pending) return PT_OK;
   b->ctl_pending = false;
-  if (b->used_stream_valid) PT_CUDA(cudaStreamSynchronize(b->used_stream));
+  if (b->work_recorded && b->last_work) PT_CUDA(cudaEventSynchronize(b->last_work));
+  else if (b->used_stream_valid) PT_CUDA(cudaStreamSynchronize(b->used_stream));
   const TcCtl* c = reinterpret_cast<const TcCtl*>(b->h_ctl);
   if (c->abort) return set_error(PT_ERR_CUDA, "pt_batch_contain: the device watchdog fired (a wait for an upload chunk or a pool slot did not end); results are incomplete");
   return PT_OK;
@@ -1109,11 +1124,6 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
     }
     b->owns_input = true;
     mark("checks");
-    // offset tables first (small), then the five data arrays chunk by chunk on the copy stream
-    if ((rc = upload(&b->d_hnode_off, d->host_node_off, B + 1, s, &b->h2d_bytes)) || (rc = upload(&b->d_harc_off, d->host_arc_off, B + 1, s, &b->h2d_bytes)) ||
-        (rc = upload(&b->d_gnode_off, d->guest_node_off, B + 1, s, &b->h2d_bytes)))
-      return fail(rc);
-    mark("offset tables");
     if ((rc = dev_alloc(&b->d_succ_off, (size_t)std::max<int64_t>(NH + (deg ? 0 : B), 1) * esz)) || (rc = dev_alloc(&b->d_succ_adj, (size_t)std::max<int64_t>(MH, 1) * esz)) ||
         (rc = dev_alloc(&b->d_hlabel, (size_t)std::max<int64_t>(NH, 1) * esz)) || (rc = dev_alloc(&b->d_tparent, (size_t)std::max<int64_t>(NG, 1) * esz)) ||
         (rc = dev_alloc(&b->d_tlabel, (size_t)std::max<int64_t>(NG, 1) * esz)))
@@ -1142,6 +1152,13 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
       if (e != cudaSuccess) return fail(set_error(PT_ERR_CUDA, "pt_batch_create: %s", cudaGetErrorString(e)));
     }
     mark("allocations + flags");
+    // offset tables first (small), then the five data arrays chunk by chunk, all on the copy stream when there is one: the kernel looks at
+    // nothing before it has seen chunk_ready[0], which is written behind them, and the caller's stream carries no copy of ours between
+    // the previous batch's kernel and this one's
+    if ((rc = upload(&b->d_hnode_off, d->host_node_off, B + 1, cs, &b->h2d_bytes)) || (rc = upload(&b->d_harc_off, d->host_arc_off, B + 1, cs, &b->h2d_bytes)) ||
+        (rc = upload(&b->d_gnode_off, d->guest_node_off, B + 1, cs, &b->h2d_bytes)))
+      return fail(rc);
+    mark("offset tables");
     auto chunk_bound = [&](int k) -> int64_t {
       if (k <= 0) return 0;
       if (k >= b->nchunks) return B;
@@ -1196,6 +1213,7 @@ int pt_batch_create(pt_batch** out, const pt_batch_desc* d, void* stream) {
   if (b->idx_bytes == 1 && (b->maxN > 255 || b->maxNT > 255 || b->maxL > 255))
     return fail(set_error(PT_ERR_INVALID, "pt_batch_create: index_bytes = 1 needs at most 255 host nodes, guest nodes and labels per instance"));
   if ((rc = batch_scratch(b))) return fail(rc);
+  batch_mark_work(b, s);
   mark("scratch");
   *out = b;
   return PT_OK;
@@ -1275,6 +1293,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   const int64_t B = b->B;
   const size_t words = (size_t)((B + 31) / 32);
   b->last_launches = 0; b->timed_rounds = 0;
+  b->work_recorded = false;   // until the end of this call is marked, pt_batch_free falls back to a stream synchronisation
   if (b->flags_zeroed && (!b->used_stream_valid || b->used_stream != s)) PT_CUDA(cudaStreamWaitEvent(s, b->flags_zeroed, 0));
   b->used_stream = s; b->used_stream_valid = true;
   uint32_t* bits = out_mem == PT_MEM_DEVICE ? result_bits : b->d_bits;
@@ -1518,6 +1537,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
   } else if (out_mem == PT_MEM_HOST) {
     PT_CUDA(cudaStreamSynchronize(s));
   }
+  batch_mark_work(b, s);
   if (out_mem == PT_MEM_HOST || counters) return batch_check_ctl(b);  // the stream has been synchronised: report a fired watchdog now
   return PT_OK;
 }
