@@ -372,6 +372,9 @@ typedef struct pt_comm pt_comm;
 int pt_comm_unique_id(void* id128);
 int pt_comm_init(pt_comm** out, int nranks, int rank, const void* id128);
 int pt_comm_rank(const pt_comm* c);
+/* 1 if the ranks exchange result words through each other's memory (CUDA IPC mappings over NVLink peer access, set up and agreed on
+ * by all ranks in pt_comm_init), 0 if through NCCL (no peer access, more than 64 ranks, or PT_COMM_P2P=0 in the environment) */
+int pt_comm_peer_exchange(const pt_comm* c);
 int pt_comm_size(const pt_comm* c);
 int pt_comm_allreduce(pt_comm* c, void* device_words, int64_t count, int elem_bytes, int op, void* stream);
 int pt_batch_contain_sharded(pt_batch* b, pt_comm* c, const pt_options* opt, int64_t first_instance, int64_t total_instances, int64_t local_instances,

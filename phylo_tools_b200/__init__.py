@@ -299,6 +299,10 @@ class Comm:
         self._h = C.c_void_p()
         _check(_L.pt_comm_init(C.byref(self._h), self.nranks, self.rank, ident), "pt_comm_init")
 
+    def peer_exchange(self):
+        """True if the ranks exchange result words through each other's memory (NVLink peer access), False if through NCCL"""
+        return bool(_L.pt_comm_peer_exchange(self._h))
+
     def allreduce(self, words, op="sum", stream=None):
         """in place on a torch CUDA tensor of 4- or 8-byte elements"""
         _check(_L.pt_comm_allreduce(self._h, words.data_ptr(), int(words.numel()), int(words.element_size()), 0 if op == "sum" else 1, stream), "pt_comm_allreduce")

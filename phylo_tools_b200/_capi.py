@@ -109,6 +109,7 @@ def load():
         "pt_net_tree_components": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, vp, vp, C.c_int64, i64p, C.c_int, vp]),
         "pt_net_visible_component": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp, vp, vp]),
         "pt_lca_query_adjacent": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, vp]),
+        "pt_comm_peer_exchange": (C.c_int, [vp]),
         "pt_comm_unique_id": (C.c_int, [vp]),
         "pt_comm_init": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, vp]),
         "pt_comm_rank": (C.c_int, [vp]),
@@ -127,4 +128,4 @@ EXPORTED = ["pt_last_error", "pt_abi_version", "pt_device_count", "pt_set_device
             "pt_lca_node_info", "pt_lca_free", "pt_tree_who_displays", "pt_tree_highest_displayed", "pt_net_bridges", "pt_rmq_build", "pt_rmq_query", "pt_rmq_free", "pt_get_limits", "pt_batch_create",
             "pt_batch_contain", "pt_batch_contain_multi", "pt_batch_create_from_newick", "pt_batch_download", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_enum_create", "pt_enum_run", "pt_enum_free", "pt_parse_newick", "pt_parse_edgelist", "pt_packer_create",
             "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_desc_bytes", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree", "pt_iso_batch", "pt_iso_from_newick",
-            "pt_lca_query_adjacent", "pt_who_build", "pt_who_total", "pt_who_lists", "pt_who_highest_displayed", "pt_who_free", "pt_net_unzip", "pt_net_tree_components", "pt_net_visible_component", "pt_comm_unique_id", "pt_comm_init", "pt_comm_rank", "pt_comm_size", "pt_comm_allreduce", "pt_batch_contain_sharded", "pt_comm_free"]
+            "pt_lca_query_adjacent", "pt_who_build", "pt_who_total", "pt_who_lists", "pt_who_highest_displayed", "pt_who_free", "pt_net_unzip", "pt_net_tree_components", "pt_net_visible_component", "pt_comm_unique_id", "pt_comm_init", "pt_comm_rank", "pt_comm_peer_exchange", "pt_comm_size", "pt_comm_allreduce", "pt_batch_contain_sharded", "pt_comm_free"]

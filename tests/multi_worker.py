@@ -29,6 +29,9 @@ def main():
         dist.broadcast_object_list(box, src=0)
         return box[0]
     comm = pt.Comm(world, rank, bootstrap)
+    want_p2p = os.environ.get("PT_COMM_P2P", "1") != "0"
+    assert comm.peer_exchange() or not want_p2p or os.environ.get("PT_ALLOW_NO_PEER_ACCESS"), "the GPUs of this box should map each other's memory"
+    assert want_p2p or not comm.peer_exchange()
     total = 5003   # not a multiple of 32: the last rank owns a ragged tail
     kinds = [(0, 1700), (1, 1700), (2, 1603)]
     # the whole batch (every rank makes it, so that each can check the merged result against a local solve of everything)

@@ -35,13 +35,16 @@ def test_sharded_call_with_one_rank(pt):
     comm.free()
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_containment_over_nccl(pt, world):
+def test_sharded_containment_over_nccl(pt, world, exchange):
+    """both forms of the result exchange: through peer memory (CUDA IPC mappings over NVLink, the default) and through NCCL (PT_COMM_P2P=0)"""
     if pt.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
+    env = dict(os.environ, PT_COMM_P2P="1" if exchange == "peer" else "0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), os.path.join(ROOT, "tests", "multi_worker.py")], capture_output=True, text=True, timeout=600)
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "multi_worker.py")], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "MULTI_OK world=%d" % world in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
