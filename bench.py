@@ -82,28 +82,38 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.stop, self.t = index, [], False, None
+        self.index, self.rows, self.stop, self.t, self.sample = index, [], False, None, None
 
-    def _run_nvml(self):
-        """NVML in-process: a sample every 2 ms (the timed region of the default run is ~80 ms, too short for nvidia-smi's ~100 ms per call)"""
+    def _nvml_open(self):
+        """NVML in-process: a sample every 1 ms (the timed region is 13 ms at N = 8, 80 ms at N = 1: too short for nvidia-smi's ~100 ms per call).
+        Opened BEFORE the timed region starts, so that the first sample falls inside it."""
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
         mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
         get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
         bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}   # nvmlClocksEventReason*
-        while not self.stop:
+
+        def sample():
             sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
             r = get_reasons(h)
             self.rows.append([str(sm), str(mx)] + [("Active" if r & bits[n] else "Not Active") for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
-            time.sleep(0.002)
+        sample()          # (fails here, not in the thread, if NVML cannot be used)
+        self.rows.clear()
+        return sample
+
+    def _run_nvml(self):
+        while not self.stop:
+            self.sample()
+            time.sleep(0.001)
 
     def _run(self):
-        try:
-            self._run_nvml()
-            return
-        except Exception:
-            pass
+        if self.sample is not None:
+            try:
+                self._run_nvml()
+                return
+            except Exception:
+                pass
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -115,11 +125,20 @@ class ClockSampler:
             time.sleep(0.2)
 
     def __enter__(self):
+        try:
+            self.sample = self._nvml_open()
+        except Exception:
+            self.sample = None
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
         return self
 
     def __exit__(self, *a):
+        if self.sample is not None:
+            try:
+                self.sample()     # one more while the last timed step is still in flight / just over
+            except Exception:
+                pass
         self.stop = True
         self.t.join(timeout=6)
 
@@ -693,12 +712,13 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(steps):
+        for _ in range(steps):      # the steps are queued back to back: the host does not wait inside the timed region
             step()
-            launches += resident.last_launches()
-            k0.append(resident.round_ms(0))
+            launches += resident.last_launches() + (1 if comm.peer_exchange() and world > 1 else 0)   # the persistent kernel (+ the library's exchange kernel)
         e1.record()
         barrier()
+        n_l = resident.launch_count()
+        k0 = [resident.launch_ms(i) for i in range(max(n_l - steps, n_l - 64, 0), n_l)]   # every timed step's kernel, from the handle's event ring
         if ctx:
             ctx.__exit__(None, None, None)
             clocks_for.update(ctx.summary())
@@ -804,7 +824,9 @@ def main():
                       "instances": total_B, "instances_on_this_gpu": B, "leaves": L, "reticulations": R, "host_nodes": 2 * R + 2 * L - 1, "generator_seed": SEED,
                       "input_layout": {4: "int32 arrays", 2: "int16 arrays (pt_batch_desc.index_bytes = 2)", 1: "uint8 arrays, out-degrees instead of offsets (pt_batch_desc.index_bytes = 1)"}[layout],
                       "l2": "the solver's working set is shared memory; inputs are %.0f MB per step on this GPU (at N = 1 close to the 126 MB L2; they are read once per step, nothing else competes for them); no explicit flush" % (r["in_bytes"] / 1e6),
-                      "parallelism": "instances sharded %d-way (contiguous ranges), one NCCL all-reduce of the packed result words issued by the library (pt_batch_contain_sharded)" % world if world > 1 else "single GPU",
+                      "parallelism": ("instances sharded %d-way (contiguous ranges); result words exchanged by the library (pt_batch_contain_sharded) %s" %
+                                      (world, "through peer memory: every rank pushes its words into the other ranks' buffers over NVLink, no reduction" if comm.peer_exchange()
+                                       else "with one NCCL all-reduce")) if world > 1 else "single GPU",
                       "cpu_affinity": ("%d cores next to the GPU" % numa) if numa else "default"},
            "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": words * 4 * world,
                    "api": "pt_batch_create(HOST pinned) + pt_batch_contain_sharded + D2H of the result words + host sync + pt_batch_free, on every rank, every step",

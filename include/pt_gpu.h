@@ -329,6 +329,10 @@ int64_t pt_batch_last_launches(const pt_batch* b);
  * pt_batch_contain (round 0 = the launch over the original instances: the dominant kernel); PT_ERR_INVALID if that
  * round did not run */
 int pt_batch_round_ms(const pt_batch* b, int round, float* ms);
+/* Device time of the persistent launch of call number `launch` (0-based, counted per handle by pt_batch_launch_count) for the last 64
+ * calls: a caller that queues many pt_batch_contain steps without waiting in between reads every step's kernel time afterwards. */
+int64_t pt_batch_launch_count(const pt_batch* b);
+int pt_batch_launch_ms(const pt_batch* b, int64_t launch, float* ms);
 /* bytes copied host->device by pt_batch_create (0 for DEVICE input) */
 int64_t pt_batch_h2d_bytes(const pt_batch* b);
 int pt_batch_free(pt_batch* b);

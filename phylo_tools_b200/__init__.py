@@ -260,6 +260,15 @@ class Batch:
         _check(_L.pt_batch_round_ms(self._h, rnd, C.byref(ms)), "pt_batch_round_ms")
         return float(ms.value)
 
+    def launch_count(self):
+        return int(_L.pt_batch_launch_count(self._h))
+
+    def launch_ms(self, launch):
+        """device time of the persistent launch of call number `launch` of this handle (the last 64 calls are kept)"""
+        ms = C.c_float()
+        _check(_L.pt_batch_launch_ms(self._h, int(launch), C.byref(ms)), "pt_batch_launch_ms")
+        return float(ms.value)
+
     def h2d_bytes(self):
         return int(_L.pt_batch_h2d_bytes(self._h))
 

@@ -80,6 +80,8 @@ def load():
         "pt_batch_download": (C.c_int, [vp, C.c_int, vp, C.c_int64, i64p, i32p, i32p]),
         "pt_batch_last_launches": (C.c_int64, [vp]),
         "pt_batch_round_ms": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float)]),
+        "pt_batch_launch_count": (C.c_int64, [vp]),
+        "pt_batch_launch_ms": (C.c_int, [vp, C.c_int64, C.POINTER(C.c_float)]),
         "pt_batch_h2d_bytes": (C.c_int64, [vp]),
         "pt_batch_free": (C.c_int, [vp]),
         "pt_enum_switchings": (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp, vp, C.c_uint64, C.c_uint64, C.c_int, u64p, u64p, u64p, vp]),
@@ -126,6 +128,6 @@ def load():
 
 EXPORTED = ["pt_last_error", "pt_abi_version", "pt_device_count", "pt_set_device", "pt_lca_build", "pt_lca_query", "pt_lca_get_info",
             "pt_lca_node_info", "pt_lca_free", "pt_tree_who_displays", "pt_tree_highest_displayed", "pt_net_bridges", "pt_rmq_build", "pt_rmq_query", "pt_rmq_free", "pt_get_limits", "pt_batch_create",
-            "pt_batch_contain", "pt_batch_contain_multi", "pt_batch_create_from_newick", "pt_batch_download", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_enum_create", "pt_enum_run", "pt_enum_free", "pt_parse_newick", "pt_parse_edgelist", "pt_packer_create",
+            "pt_batch_contain", "pt_batch_contain_multi", "pt_batch_create_from_newick", "pt_batch_download", "pt_batch_last_launches", "pt_batch_round_ms", "pt_batch_launch_count", "pt_batch_launch_ms", "pt_batch_h2d_bytes", "pt_batch_free", "pt_enum_switchings", "pt_enum_create", "pt_enum_run", "pt_enum_free", "pt_parse_newick", "pt_parse_edgelist", "pt_packer_create",
             "pt_packer_add_newick", "pt_packer_add_newick_text", "pt_packer_add_generated", "pt_packer_desc", "pt_packer_desc_compact", "pt_packer_desc_bytes", "pt_packer_get_newick", "pt_packer_free", "pt_gen_random_tree", "pt_iso_batch", "pt_iso_from_newick",
             "pt_lca_query_adjacent", "pt_who_build", "pt_who_total", "pt_who_lists", "pt_who_highest_displayed", "pt_who_free", "pt_net_unzip", "pt_net_tree_components", "pt_net_visible_component", "pt_comm_unique_id", "pt_comm_init", "pt_comm_rank", "pt_comm_peer_exchange", "pt_comm_size", "pt_comm_allreduce", "pt_batch_contain_sharded", "pt_comm_free"]

@@ -895,6 +895,11 @@ struct pt_batch {
   int64_t h2d_bytes = 0;
   static constexpr int kMaxTimedRounds = 16;
   cudaEvent_t ev[2 * kMaxTimedRounds] = {};
+  // the persistent launches of the last kRing calls keep their own event pairs, so that a caller who queues many steps without waiting
+  // in between can read every step's kernel time afterwards (pt_batch_launch_ms)
+  static constexpr int kRing = 64;
+  cudaEvent_t ring[2 * kRing] = {};
+  int64_t launch_seq = 0;
   int timed_rounds = 0;
   cudaStream_t used_stream = nullptr; bool used_stream_valid = false;
 };
@@ -949,6 +954,7 @@ static void batch_release(pt_batch* b) {
   dev_free(b->d_bits); dev_free(b->d_status); dev_free(b->d_ticket);   // (counters and branched flags live inside d_ticket's block)
   dev_free(b->d_pool[0]); dev_free(b->d_pool[1]); dev_free(b->d_ws); dev_free(b->d_ppool); dev_free(b->d_pready); dev_free(b->d_chunk_ready);
   for (cudaEvent_t e : b->ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : b->ring) if (e) cudaEventDestroy(e);
   if (b->last_work) cudaEventDestroy(b->last_work);
   for (cudaEvent_t e : b->chunk_ev) if (e) cudaEventDestroy(e);
   if (b->flags_zeroed) cudaEventDestroy(b->flags_zeroed);
@@ -1276,10 +1282,21 @@ int pt_debug_last_phases(pt_batch* b, double out[4]) {
 }
 int pt_batch_round_ms(const pt_batch* bc, int round, float* ms) {
   pt_batch* b = const_cast<pt_batch*>(bc);
+  if (b && ms && round == 0 && b->timed_rounds == -1) return pt_batch_launch_ms(b, b->launch_seq - 1, ms);
   if (!b || !ms || round < 0 || round >= b->timed_rounds) return set_error(PT_ERR_INVALID, "pt_batch_round_ms: round %d did not run (or was not timed)", round);
   PT_CUDA(cudaEventSynchronize(b->ev[2 * round + 1]));  // pt_batch_contain with DEVICE outputs does not wait for its kernel
   PT_CUDA(cudaEventElapsedTime(ms, b->ev[2 * round], b->ev[2 * round + 1]));
   return batch_check_ctl(b);
+}
+int64_t pt_batch_launch_count(const pt_batch* b) { return b ? b->launch_seq : 0; }
+int pt_batch_launch_ms(const pt_batch* bc, int64_t launch, float* ms) {
+  pt_batch* b = const_cast<pt_batch*>(bc);
+  if (!b || !ms || launch < 0 || launch >= b->launch_seq || launch < b->launch_seq - pt_batch::kRing)
+    return set_error(PT_ERR_INVALID, "pt_batch_launch_ms: launch %lld is not among the last %d persistent launches of this handle", (long long)launch, pt_batch::kRing);
+  const int slot = (int)(launch % pt_batch::kRing);
+  PT_CUDA(cudaEventSynchronize(b->ring[2 * slot + 1]));
+  PT_CUDA(cudaEventElapsedTime(ms, b->ring[2 * slot], b->ring[2 * slot + 1]));
+  return launch == b->launch_seq - 1 ? batch_check_ctl(b) : PT_OK;
 }
 
 int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, uint8_t* status, pt_mem out_mem, pt_counters* counters, void* stream) {
@@ -1384,15 +1401,17 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     ch.flags = env_flags;
     if (b->nchunks > 1 && b->d_chunk_ready) { ch.n = b->nchunks; for (int c = 0; c < b->nchunks; ++c) ch.end[c] = (int32_t)b->chunk_end[c]; ch.ready = b->d_chunk_ready; }
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)dp.sms, (B + wpc - 1) / wpc));
-    for (int j = 0; j < 2; ++j) if (!b->ev[j]) PT_CUDA(cudaEventCreate(&b->ev[j]));
-    PT_CUDA(cudaEventRecord(b->ev[0], s));
+    const int slot = (int)(b->launch_seq % pt_batch::kRing);
+    for (int j = 0; j < 2; ++j) if (!b->ring[2 * slot + j]) PT_CUDA(cudaEventCreate(&b->ring[2 * slot + j]));
+    PT_CUDA(cudaEventRecord(b->ring[2 * slot], s));
     TcCtl* ctl = reinterpret_cast<TcCtl*>(b->d_ticket);
     cudaError_t e = b->idx_bytes == 1 ? launch_persistent<uint8_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat)
                   : b->idx_bytes == 2 ? launch_persistent<int16_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat)
                                       : launch_persistent<int32_t>(wpc, grid, smem, s, src, pool, ch, ctl, b, (int)warp_bytes, bits, stat);
     if (e != cudaSuccess) return set_error(PT_ERR_CUDA, "pt_batch_contain: launch failed: %s", cudaGetErrorString(e));
-    PT_CUDA(cudaEventRecord(b->ev[1], s));
-    b->timed_rounds = 1; b->last_launches = 1; rounds = 1;
+    PT_CUDA(cudaEventRecord(b->ring[2 * slot + 1], s));
+    ++b->launch_seq;
+    b->timed_rounds = -1; b->last_launches = 1; rounds = 1;   // (-1: round 0 is the newest ring slot)
     PT_CUDA(cudaMemcpyAsync(b->h_ctl, b->d_ticket, sizeof(TcCtl), cudaMemcpyDeviceToHost, s));
     b->ctl_pending = true;
   } else if (B > 0) {
