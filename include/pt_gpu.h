@@ -307,7 +307,11 @@ typedef struct pt_options {
                                   (unlabelled leaves, labels on one side only, unary guest nodes) fall back to auto.
                                   Pays for networks whose bridge-free components are small; generator networks have one
                                   giant component, there 3 is faster */
-  int32_t reserved[5];
+  int32_t no_small_core;     /* 0 (default): an instance on which the rules are stuck and of which at most 64 host nodes, 32 labels and
+                                512 switchings are left is decided on the spot by enumerating those switchings, one per thread, with exact
+                                32-bit cluster sets (what is left of a config-2 instance at that point has 9 ... 40 nodes); 1: always branch
+                                through the pool (keeps the branching machinery testable; slower) */
+  int32_t reserved[4];
 } pt_options;
 
 typedef struct pt_limits {

@@ -235,7 +235,7 @@ class Batch:
         out.update(index_bytes=int(ib.value), max_host_nodes=mx[0], max_host_arcs=mx[1], max_guest_nodes=mx[2], max_labels=mx[3])
         return out
 
-    def contain(self, result_bits=None, status=None, want_counters=True, stream=None, pool_slots=0, max_rounds=0, path=0):
+    def contain(self, result_bits=None, status=None, want_counters=True, stream=None, pool_slots=0, max_rounds=0, path=0, no_small_core=0):
         """returns (verdicts bool[B] or None when device outputs are given, status uint8[B] or None, counters dict or None)"""
         B = self.num_instances
         words = (B + 31) // 32
@@ -243,7 +243,7 @@ class Batch:
         if result_bits is None:
             result_bits = np.zeros(max(words, 1), dtype=np.uint32)
             status = np.zeros(max(B, 1), dtype=np.uint8)
-        opt = Options(pool_slots, max_rounds, path)
+        opt = Options(pool_slots, max_rounds, path, no_small_core)
         cnt = Counters() if want_counters else None
         _check(_L.pt_batch_contain(self._h, C.byref(opt), _ptr(result_bits), _ptr(status), PT_MEM_DEVICE if dev_out else PT_MEM_HOST,
                                    C.byref(cnt) if cnt is not None else None, stream), "pt_batch_contain")

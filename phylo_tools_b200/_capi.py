@@ -38,7 +38,7 @@ class Counters(C.Structure):
 
 
 class Options(C.Structure):
-    _fields_ = [("pool_slots", C.c_int32), ("max_rounds", C.c_int32), ("path", C.c_int32), ("reserved", C.c_int32 * 5)]
+    _fields_ = [("pool_slots", C.c_int32), ("max_rounds", C.c_int32), ("path", C.c_int32), ("no_small_core", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class Limits(C.Structure):

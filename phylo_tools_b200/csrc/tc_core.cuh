@@ -170,7 +170,7 @@ struct TcSolver {
   int n, m, nt, L;  // uniform across the group
   TcStats st;
 
-  PT_HD TcSolver(Ex& e, TcWork<I>& work) : ex(e), w(work), n(0), m(0), nt(0), L(0), missing_(0), dag_state_(0) { st.cherries = st.retcherries = st.arcs_deleted = st.passes = 0; }
+  PT_HD TcSolver(Ex& e, TcWork<I>& work) : ex(e), w(work), n(0), m(0), nt(0), L(0), core_switchings_(0), allow_core_(true), missing_(0), dag_state_(0) { st.cherries = st.retcherries = st.arcs_deleted = st.passes = 0; }
 
   enum { F_FLAG = 0, F_FAIL = 1, F_ROOT = 2, F_TROOT = 3, F_NLAB = 4, F_BEST = 5, F_STATUS = 6, F_TMP = 7, F_TMP2 = 8, F_QTAIL = 9 };
   static constexpr int TDEAD = -2;
@@ -769,6 +769,97 @@ struct TcSolver {
     return head == n;  // every node was released exactly once <=> no cycle
   }
 
+  // ---- the small core: when the rules are stuck, what is left is tiny ------------------------------------------------------
+  // Measured on BASELINE config 2 (l = 100, r = 20): an instance that needs branching has been reduced to 9 ... 40 live host nodes
+  // with 2 ... 5 multi-parent nodes by then.  Instead of handing its children to other warps (emit, reload, a full rule loop per
+  // child: ~100 us of latency per level, the tail of every launch), the group decides it on the spot from the definition: ONE
+  // SWITCHING PER THREAD -- every thread walks the live nodes children first (the Kahn order the wavefront has just left in hscr),
+  // forms the label set below every node as a 32-bit mask under its switching, and checks that the nodes with >= 2 live children
+  // carry exactly the guest's clusters.  Exact (sets, not hashes) because at most 32 labels are alive.  Applicable when
+  // <= kCoreNodes live nodes, <= 32 live labels and <= kCoreSwitchings switchings remain; otherwise -1 and the caller branches.
+  // Needs: fresh CSR, wavefront order in hscr (both hold when rule_loop has just returned TC_BRANCH: the caller tries this first and
+  // branches only on -1).  Touches scratch only.
+  static constexpr int kCoreNodes = 64, kCoreSwitchings = 512;
+  int core_switchings_;   // > 0: the last verdict came from the small core, over this many switchings
+  bool allow_core_;       // false: always branch (pt_options.no_small_core; keeps the branching machinery testable)
+  PT_NI int finish_small_core() {
+    if (!allow_core_) return -1;
+    ex.phase = 17;
+    // Set-up by ONE thread, on purpose: a dozen small parallel passes with their barriers were 10 KB of code, and this kernel pays
+    // for every KB with all its instances (instruction cache).  The loops are short: <= 64 nodes, <= 32 labels with their ancestors.
+    if (ex.tid() == 0) {
+      int K = 0, nlab = 0, P = 1, Gi = 0, ok = 1;
+      PT_NOUNROLL for (int v = 0; v < n; ++v) K += w.lvl[v] != LVL_INF;
+      if (K > kCoreNodes || K < 1) ok = 0;
+      PT_NOUNROLL for (int i = 0; i < K && ok; ++i) {   // position in the order; leaves get a bit, multi-parent nodes a digit
+        const int v = w.hscr[i], d = indeg(v);
+        w.hcnt[v] = (I)i;
+        const bool leaf = outdeg(v) == 0 && w.hlab[v] >= 0;
+        w.haux[v] = (I)(leaf ? nlab++ : -1);
+        if (d >= 2) { w.lvl[v] = (I)P; P *= d; if (P > kCoreSwitchings) ok = 0; } else w.lvl[v] = (I)0;
+        if (leaf) {   // clear the cluster words of the guest leaf's ancestors (first of two walks)
+          const int t = w.l2t[w.hlab[v]];
+          if (t < 0 || w.tpar[t] == TDEAD) { ok = 0; continue; }
+          int guard = 0;
+          PT_NOUNROLL for (int p = w.tpar[t]; p >= 0 && guard++ < nt; p = w.tpar[p]) { if (p >= w.capN * w.W) { ok = 0; break; } w.lset[p] = 0u; }
+        }
+      }
+      if (nlab > 32 || nlab < 1) ok = 0;
+      PT_NOUNROLL for (int i = 0; i < K && ok; ++i) {   // guest clusters; an inner node is listed (behind the order in hscr) when first met
+        const int v = w.hscr[i];
+        if (w.haux[v] < 0) continue;
+        const uint32_t bit = 1u << w.haux[v];
+        int guard = 0;
+        PT_NOUNROLL for (int p = w.tpar[w.l2t[w.hlab[v]]]; p >= 0 && guard++ < nt; p = w.tpar[p]) {
+          if (w.lset[p] == 0u) {
+            if (w.tdeg[p] < 2 || K + Gi > w.capN || Gi >= 31) { ok = 0; break; }   // a unary guest node: not clean, leave it to the rules
+            w.hscr[K + Gi++] = (I)p;
+          }
+          w.lset[p] |= bit;
+        }
+      }
+      w.sc[F_TMP] = ok ? (K | (nlab << 8) | (Gi << 16)) : -1;
+      w.sc[F_TMP2] = P;
+    }
+    ex.sync();
+    const int packed = ex.uniform(&w.sc[F_TMP]), P = ex.uniform(&w.sc[F_TMP2]);
+    if (ex.tid() == 0) { w.sc[F_TMP] = 0; w.sc[F_TMP2] = 0; }
+    ex.sync();
+    if (packed < 0) return -1;
+    const int K = packed & 255, nlab = (packed >> 8) & 255, Gi = packed >> 16;
+    // one switching per thread
+    ex.phase = 18;
+    const uint32_t all = nlab == 32 ? 0xffffffffu : ((1u << nlab) - 1u);
+    uint32_t cl[kCoreNodes];
+    int found = 0;
+    PT_NOUNROLL for (int base = 0; base < P && !found; base += ex.nth()) {
+      const int sidx = base + ex.tid();
+      int ok = sidx < P ? 1 : 0, real = 0;
+      PT_NOUNROLL for (int i = 0; i < K && ok; ++i) {
+        const int v = w.hscr[i], od = outdeg(v);
+        uint32_t mask = w.haux[v] >= 0 ? (1u << w.haux[v]) : 0u;
+        int kids = 0;
+        PT_NOUNROLL for (int k = 0; k < od; ++k) {
+          const int e = out_arc(v, k), c = w.ah[e], dc = indeg(c);
+          if (dc >= 2 && in_arc(c, (sidx / (int)w.lvl[c]) % dc) != e) continue;
+          const uint32_t mc = cl[w.hcnt[c]];
+          if (mc) { mask |= mc; ++kids; }
+        }
+        cl[i] = mask;
+        if (kids >= 2) {
+          ++real;
+          int hit = 0;
+          PT_NOUNROLL for (int j = 0; j < Gi; ++j) hit |= (w.lset[w.hscr[K + j]] == mask);
+          ok = hit;
+        }
+      }
+      if (ok && (real != Gi || cl[K - 1] != all)) ok = 0;
+      found = ex.reduce_or(ok);
+    }
+    core_switchings_ = P;
+    return found ? 1 : 0;
+  }
+
   // ---- branching in place: keep only in-arc `keep` of node x and go on with the same workspace (first child of a branching;
   // the siblings are emitted as compact instances before this is called) ---------------------------------------------------
   PT_NI void keep_only(int x, int keep) {
@@ -820,6 +911,9 @@ struct TcSolver {
       if (r > 0) continue;
       const int x = pick_branch_node();
       if (x < 0) { *status = TCS_BAD_GRAPH; return TC_ERROR; }  // a clean tree host always has a true cherry
+      // (the CALLER tries finish_small_core() before it branches: inlined here, inside the loop nest, the same code made every
+      // instance 7 % slower -- 7.87 -> 8.45 ms per 10^5 -- although 92 % of them never reach it, and as an out-of-line call 35 %
+      // slower: the registers live across the call get spilled all over the loop)
       *branch_node = x;
       return TC_BRANCH;
     }
@@ -827,9 +921,11 @@ struct TcSolver {
   template <class S>
   PT_HD int solve(const TcInst& in, bool trusted, int* status, int* branch_node) {
     *branch_node = -1;
-    const int c = begin<S>(in, trusted, status);
+    int c = begin<S>(in, trusted, status);
     if (c != TC_CONTINUE) return c;
-    return rule_loop(status, branch_node);
+    c = rule_loop(status, branch_node);
+    if (c == TC_BRANCH) { const int core = finish_small_core(); if (core >= 0) c = core ? TC_DISPLAYED : TC_NOT; }
+    return c;
   }
 };
 

@@ -432,6 +432,7 @@ struct TcSource {
   const void *succ_off, *succ_adj, *hlabel, *tparent, *tlabel;
   const int32_t *dims, *origin;  // pool mode
   int sN1, sM, sN, sNT;          // pool strides (elements)
+  int solver_flags;              // bit 0: never finish by enumerating the small core (pt_options.no_small_core)
 };
 struct TcSink {
   int32_t *succ_off, *succ_adj, *hlabel, *tparent, *tlabel, *dims, *origin;
@@ -484,7 +485,12 @@ constexpr long long kWatchdogCycles = 8000000000ll;  // ~4 s at 1.9 GHz: far bey
 
 // S = element type of the caller's arrays (int32_t, int16_t for index_bytes = 2, uint8_t for index_bytes = 1).  MAXT = launch
 // bound = register budget: 768 threads -> 80 registers (the default: 24 warps per SM), 1024 -> 64.
-template <class I, class S, int MAXT>
+// CORE = the variant that finishes a stuck instance by enumerating its small core (TcSolver::finish_small_core) instead of branching.
+// It is a separate instantiation because its code is not free: 6 KB more SASS made EVERY instance 4.8 % slower (7.87 -> 8.25 ms per
+// 10^5; 92 % of the instances never reach that code -- this kernel lives on its instruction cache), while what it buys is per LAUNCH
+// (no chains of children in the tail: -0.08 ms) plus 1.4 % of work.  Measured break-even: ~28 000 instances per launch; the host picks
+// the variant by the size of the batch it launches (one rank's shard of BASELINE config 2 at 8 GPUs: 12 500).
+template <class I, class S, int MAXT, bool CORE>
 __global__ void __launch_bounds__(MAXT, 1) tc_persistent_kernel(TcSource src, TcPool pool, TcChunks chunks, TcCtl* __restrict__ ctl, int capN, int capM, int capNT, int capL,
                                                                 int warp_bytes, uint32_t* __restrict__ result_bits, uint8_t* __restrict__ status,
                                                                 uint8_t* __restrict__ branched, unsigned long long* __restrict__ counters) {
@@ -565,6 +571,7 @@ __global__ void __launch_bounds__(MAXT, 1) tc_persistent_kernel(TcSource src, Tc
     }
     if (!skip) {
       TcSolver<WarpEx, I> sv(ex, w);
+      sv.allow_core_ = !(src.solver_flags & 1);
       int st = 0, x = -1;
       int code = sv.template begin<S>(in, from_pool != 0, &st);
       ++c_items;
@@ -572,6 +579,7 @@ __global__ void __launch_bounds__(MAXT, 1) tc_persistent_kernel(TcSource src, Tc
         code = sv.rule_loop(&st, &x);
         ex.phase = 13;
         if (code != TC_BRANCH) break;
+        if (CORE) { const int core = sv.finish_small_core(); if (core >= 0) { code = core ? TC_DISPLAYED : TC_NOT; break; } }   // what is left is tiny: decide it here
         if (chunks.flags & 4) { code = TC_NOT; break; }   // measuring aid: no branching at all (wrong verdicts; shows the tail without chains)
         // ---- branch on x: children 1 .. d-1 go to the pool, child 0 continues in place -------------------------------------
         const int d = sv.indeg(x);
@@ -611,6 +619,10 @@ __global__ void __launch_bounds__(MAXT, 1) tc_persistent_kernel(TcSource src, Tc
         code = TC_CONTINUE;
       }
       c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
+      if (sv.core_switchings_) {   // decided by enumerating the switchings of the small core: not "by the rules alone"
+        if (lane == 0 && !from_pool) branched[origin] = 1;
+        c_br += (unsigned long long)sv.core_switchings_;
+      }
       if (code == TC_DISPLAYED) {
         if (lane == 0) { atomicOr(&result_bits[origin >> 5], 1u << (origin & 31)); }
         ++c_disp;
@@ -689,9 +701,14 @@ __global__ void __launch_bounds__(512) tc_reduce_cta_kernel(TcSource src, TcSink
       batch_inst<S>(src, item, in);
     }
     TcSolver<CtaEx, I> sv(ex, w);
+    sv.allow_core_ = !(src.solver_flags & 1);
     int st = 0, x = -1;
     const int code = sv.template solve<S>(in, src.is_pool != 0, &st, &x);
     ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
+    if (sv.core_switchings_) {   // decided by enumerating the switchings of the small core: not "by the rules alone"
+      if (threadIdx.x == 0) branched[origin] = 1;
+      c_br += (unsigned long long)sv.core_switchings_;
+    }
     if (code == TC_DISPLAYED) {
       if (threadIdx.x == 0) atomicOr(&result_bits[origin >> 5], 1u << (origin & 31));
       ++c_disp;
@@ -772,9 +789,14 @@ __global__ void __launch_bounds__(PT_CLUSTER_THREADS, 1) tc_reduce_cluster_kerne
       batch_inst<S>(src, item, in);
     }
     TcSolver<ClusterEx, I> sv(ex, w);
+    sv.allow_core_ = !(src.solver_flags & 1);
     int st = 0, x = -1;
     const int code = sv.template solve<S>(in, src.is_pool != 0, &st, &x);
     ++c_items; c_ch += sv.st.cherries; c_ret += sv.st.retcherries; c_arc += sv.st.arcs_deleted; c_pass += sv.st.passes;
+    if (sv.core_switchings_) {   // decided by enumerating the switchings of the small core: not "by the rules alone"
+      if (leader) branched[origin] = 1;
+      c_br += (unsigned long long)sv.core_switchings_;
+    }
     if (code == TC_DISPLAYED) {
       if (leader) atomicOr(&result_bits[origin >> 5], 1u << (origin & 31));
       ++c_disp;
@@ -1021,18 +1043,22 @@ extern "C" int ptgpu_split_contain(int64_t B, const int64_t* d_hnode_off, const 
                                    const void* d_hlabel, const void* d_tparent, const void* d_tlabel, int idx_bytes, uint32_t* d_bits, uint8_t* d_status, uint64_t* blobs_solved,
                                    int* applied, void* stream);
 
+constexpr int64_t kCoreMaxBatch = 28000;
 template <class S>
 static cudaError_t launch_persistent(int wpc, int grid, size_t smem, cudaStream_t s, const TcSource& src, const TcPool& pool, const TcChunks& ch, TcCtl* ctl, const pt_batch* b,
                                      int warp_bytes, uint32_t* bits, uint8_t* stat) {
   using I = int16_t;
-  auto k768 = tc_persistent_kernel<I, S, 768>; auto k1024 = tc_persistent_kernel<I, S, 1024>;
-  auto kern = wpc > 24 ? k1024 : k768;
+  // the small-core variant for launches below the measured break-even (see the kernel), PT_TC_CORE=0 / 1 forces one (A/B aid)
+  static const int env_core = [] { const char* e = getenv("PT_TC_CORE"); return e ? atoi(e) : -1; }();
+  const bool core = !(src.solver_flags & 1) && (env_core >= 0 ? env_core != 0 : src.count <= kCoreMaxBatch);
+  auto kern = wpc > 24 ? (core ? tc_persistent_kernel<I, S, 1024, true> : tc_persistent_kernel<I, S, 1024, false>)
+                       : (core ? tc_persistent_kernel<I, S, 768, true> : tc_persistent_kernel<I, S, 768, false>);
   // the attribute is per function and device: set it again only when it has to grow (one process may drive several devices)
-  static std::mutex mu; static size_t have[2][64] = {};
+  static std::mutex mu; static size_t have[4][64] = {};
   int dev = 0; cudaGetDevice(&dev);
   cudaError_t e = cudaSuccess;
   { std::lock_guard<std::mutex> g(mu);
-    size_t& h = have[wpc > 24 ? 1 : 0][dev & 63];
+    size_t& h = have[(wpc > 24 ? 1 : 0) + (core ? 2 : 0)][dev & 63];
     if (h < smem) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e == cudaSuccess) h = smem; } }
   if (e != cudaSuccess) return e;
   kern<<<grid, wpc * 32, smem, s>>>(src, pool, ch, ctl, (int)b->maxN, (int)b->maxM, (int)b->maxNT, (int)b->maxL, warp_bytes, bits, stat, b->d_branched, b->d_counters);
@@ -1394,11 +1420,13 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       pool.ready = b->d_pready; pool.capacity = cap; pool.sN1 = sN1; pool.sM = sM; pool.sN = sN; pool.sNT = sNT; pool.epoch = b->pool_epoch;
     }
     TcSource src{};
+    src.solver_flags = (opt && opt->no_small_core) ? 1 : 0;
     src.first = 0; src.count = B; src.is_pool = 0; src.hnode_off = b->d_hnode_off; src.harc_off = b->d_harc_off; src.gnode_off = b->d_gnode_off;
     src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel;
     TcChunks ch{};
     static const int env_flags = [] { const char* e = getenv("PT_TC_FLAGS"); return e ? atoi(e) : 0; }();   // tuning / measuring aid
     ch.flags = env_flags;
+    if (env_flags & 8) src.solver_flags |= 1;   // (bit 3: never finish by the small core)
     if (b->nchunks > 1 && b->d_chunk_ready) { ch.n = b->nchunks; for (int c = 0; c < b->nchunks; ++c) ch.end[c] = (int32_t)b->chunk_end[c]; ch.ready = b->d_chunk_ready; }
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)dp.sms, (B + wpc - 1) / wpc));
     const int slot = (int)(b->launch_seq % pt_batch::kRing);
@@ -1462,6 +1490,8 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
     // only lower that bound (whatever is still pending then is REPORTED, see tc_round_limit_kernel)
     const int64_t max_rounds = opt && opt->max_rounds > 0 ? opt->max_rounds : (int64_t)b->maxN + 2;
     TcSource src{};
+    const int solver_flags = (opt && opt->no_small_core) ? 1 : 0;
+    src.solver_flags = solver_flags;
     src.count = B; src.is_pool = 0; src.hnode_off = b->d_hnode_off; src.harc_off = b->d_harc_off; src.gnode_off = b->d_gnode_off;
     src.succ_off = b->d_succ_off; src.succ_adj = b->d_succ_adj; src.hlabel = b->d_hlabel; src.tparent = b->d_tparent; src.tlabel = b->d_tlabel;
     int64_t items = B;
@@ -1526,6 +1556,7 @@ int pt_batch_contain(pt_batch* b, const pt_options* opt, uint32_t* result_bits, 
       // next round reads the pool just written; reset the ticket and the other pool's counter
       pending = sink;
       src = TcSource{};
+      src.solver_flags = solver_flags;
       src.is_pool = 1; src.count_ptr = pending.count; src.capacity = cap; src.succ_off = pending.succ_off; src.succ_adj = pending.succ_adj; src.hlabel = pending.hlabel;
       src.tparent = pending.tparent; src.tlabel = pending.tlabel; src.dims = pending.dims; src.origin = pending.origin; src.sN1 = sN1; src.sM = sM; src.sN = sN; src.sNT = sNT;
       PT_CUDA(cudaMemsetAsync(b->d_ticket, 0, 4, s));

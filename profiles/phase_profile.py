@@ -11,7 +11,7 @@ from phylo_tools_b200 import _capi
 NAMES = {0: "idle/ticket", 1: "load: arrays", 15: "load: guest checks", 16: "load: label tables", 2: "clean_guest", 3: "csr: compact arcs", 31: "csr: renumber nodes", 32: "csr: zero+count+offsets", 33: "csr: scan", 34: "csr: fill in-lists",
          71: "true cherry: collapse", 72: "true cherry: parents", 7: "true cherry: queue/overhead", 5: "check_dag", 40: "clean: detect", 41: "clean: dead ends", 43: "clean: suppress",
          44: "clean: merge chains", 46: "clean: parallel arcs", 14: "count_labels", 8: "guest cherries", 9: "ret cherry",
-         6: "wavefront", 10: "sibling", 11: "pick branch", 12: "emit child", 13: "epilogue"}
+         6: "wavefront", 17: "small core: setup", 18: "small core: switchings", 10: "sibling", 11: "pick branch", 12: "emit child", 13: "epilogue"}
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 pt.set_device(0)
 p = pt.Packer(); p.add_generated(B, 100, 20, 0xB200, 0)

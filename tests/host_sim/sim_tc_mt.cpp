@@ -81,6 +81,7 @@ static int solve_instance(const Item& root, int capN, int capM, int capNT, int c
       GroupEx ex{t, T, &sh};
       TcWork<I> w; w.carve(mem.data(), capN, capM, capNT, capL);
       TcSolver<GroupEx, I> sv(ex, w);
+      if (getenv("SIM_NO_CORE")) sv.allow_core_ = false;   // always branch (both ways of finishing are tested)
       TcInst in{it.n, it.m, it.nt, it.succ_off.data(), it.succ_adj.data(), it.hlabel.data(), it.tparent.data(), it.tlabel.data()};
       int st = 0, x = -1;
       const int code = sv.template solve<int32_t>(in, !first, &st, &x);

@@ -16,12 +16,14 @@ def _solve(pt, packer, **kw):
         b.free()
 
 
-def test_golden_instances(pt, gold_tc):
+@pytest.mark.parametrize("no_small_core", [0, 1])
+def test_golden_instances(pt, gold_tc, no_small_core):
+    """(both ways of finishing an instance on which the rules are stuck: enumerating its small core on the spot, and branching)"""
     items = gold_tc["items"]
     p = pt.Packer()
     for it in items:
         p.add_newick(it["host"], it["guest"])
-    v, s, c = _solve(pt, p)
+    v, s, c = _solve(pt, p, no_small_core=no_small_core)
     assert (s == 0).all()
     bad = [(i, it["tag"]) for i, it in enumerate(items) if int(v[i]) != it["truth"]]
     assert not bad, bad[:5]
@@ -40,11 +42,18 @@ def test_generated_vs_bruteforce(pt, oracle, l, r):
     p = pt.Packer()
     for kind in (0, 1, 2):
         p.add_generated(120, l, r, 31337 + 17 * l + kind, kind)
-    v, s, c = _solve(pt, p)
-    assert (s == 0).all()
     truth = np.array([oracle.tc_bruteforce_newick(*p.newick(i))[0] for i in range(len(p))])
-    assert (v.astype(int) == truth).all(), np.where(v.astype(int) != truth)[0][:10]
-    assert v[:120].all()  # kind 0 is displayed by construction
+    branched = []
+    for no_small_core in (0, 1):          # finish stuck instances by enumerating their small core / by branching
+        for path in (1, 2, 3):
+            v, s, c = _solve(pt, p, no_small_core=no_small_core, path=path)
+            assert (s == 0).all()
+            assert (v.astype(int) == truth).all(), (no_small_core, path, np.where(v.astype(int) != truth)[0][:10])
+            assert v[:120].all()  # kind 0 is displayed by construction
+            branched.append(c["branched"])
+            if no_small_core == 0 and c["branched"]:
+                assert c["work_items"] < len(p) + c["branched"]     # (almost) nobody needed children
+    assert len(set(branched)) == 1   # the same instances need more than the rules, however they are finished
 
 
 @pytest.mark.skipif(not os.environ.get("PT_STRESS"), reason="long randomized parity run: set PT_STRESS=<instances per (l, r, kind)>")
@@ -60,10 +69,11 @@ def test_stress_all_executors_vs_bruteforce(pt, oracle):
         for compact in (False, True):
             b = pt.Batch(p.arrays(compact=compact))
             for path in (1, 2, 3):
-                v, s, _ = b.contain(path=path)
-                assert (s == 0).all(), (l, r, compact, path)
-                bad = np.where(v.astype(int) != truth)[0]
-                assert len(bad) == 0, (l, r, compact, path, bad[:10])
+                for no_small_core in (0, 1):
+                    v, s, _ = b.contain(path=path, no_small_core=no_small_core)
+                    assert (s == 0).all(), (l, r, compact, path)
+                    bad = np.where(v.astype(int) != truth)[0]
+                    assert len(bad) == 0, (l, r, compact, path, no_small_core, bad[:10])
             b.free()
 
 
@@ -235,9 +245,9 @@ def test_round_limit_is_reported(pt, path):
     p = pt.Packer()
     p.add_generated(400, 16, 7, 777, 0)
     b = pt.Batch(p.arrays())
-    v, s, c = b.contain(path=path)
+    v, s, c = b.contain(path=path, no_small_core=1)     # (branching itself is under test: no finishing on the spot)
     assert (s == 0).all() and v.all() and c["branched"] > 4 and c["rounds"] >= 2
-    v1, s1, c1 = b.contain(path=path, max_rounds=1)
+    v1, s1, c1 = b.contain(path=path, max_rounds=1, no_small_core=1)
     b.free()
     assert ((s1 == 0) | (s1 == 5)).all() and (s1 == 5).sum() >= 1     # PT_INST_ROUND_LIMIT
     assert v1[s1 == 0].all()                                            # whoever has status 0 has its true verdict
@@ -249,9 +259,9 @@ def test_pool_overflow_is_reported(pt, oracle, path):
     p = pt.Packer()
     p.add_generated(400, 16, 7, 777, 0)
     b = pt.Batch(p.arrays())
-    v, s, c = b.contain(path=path)
+    v, s, c = b.contain(path=path, no_small_core=1)     # (branching itself is under test: no finishing on the spot)
     assert (s == 0).all() and v.all() and c["branched"] > 4
-    v2, s2, c2 = b.contain(pool_slots=2, path=path)
+    v2, s2, c2 = b.contain(pool_slots=2, path=path, no_small_core=1)
     b.free()
     assert ((s2 == 0) | (s2 == 4)).all() and (s2 == 4).sum() >= 1   # PT_INST_POOL_OVERFLOW, never a wrong verdict
     assert v2[s2 == 0].all()

@@ -14,6 +14,16 @@ _PT_HDR = os.path.join(ROOT, "phylo_tools_b200", "include", "pt")
 HOST_HEADERS = [os.path.join(ROOT, "include", "pt_gpu.h")] + [os.path.join(_PT_HDR, f) for f in sorted(os.listdir(_PT_HDR))]
 
 
+@pytest.fixture(params=["small-core", "always-branch"], autouse=True)
+def finishing_mode(request, monkeypatch):
+    """every test runs twice: with the small-core enumeration that finishes a stuck instance on the spot (the default), and with it
+    switched off, so that branching (emit_child / keep_only / the pool of children) stays under test"""
+    if request.param == "always-branch":
+        monkeypatch.setenv("SIM_NO_CORE", "1")
+    else:
+        monkeypatch.delenv("SIM_NO_CORE", raising=False)
+
+
 @pytest.fixture(scope="module")
 def sim():
     os.makedirs(os.path.dirname(SIM_BIN), exist_ok=True)
