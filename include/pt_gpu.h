@@ -339,6 +339,9 @@ int64_t pt_batch_launch_count(const pt_batch* b);
 int pt_batch_launch_ms(const pt_batch* b, int64_t launch, float* ms);
 /* bytes copied host->device by pt_batch_create (0 for DEVICE input) */
 int64_t pt_batch_h2d_bytes(const pt_batch* b);
+/* Waits for what THIS handle has enqueued (an event behind its last call), not for everything the caller has queued on the stream
+ * since: a caller may keep the next batch's pt_batch_create / pt_batch_contain queued behind this one (double buffering: the next
+ * upload overlaps this solve) and free this one as soon as its own result has arrived. */
 int pt_batch_free(pt_batch* b);
 
 /* Extended-Newick text straight to a device-resident batch, PARSED ON THE GPU: every two non-blank lines of text[0, len) are

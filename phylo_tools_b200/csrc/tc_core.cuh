@@ -905,6 +905,9 @@ struct TcSolver {
       }
       if (r < 0) return TC_NOT;
       if (progress) continue;
+#ifdef PT_AONLY   // measuring aid (make aonly): how fast is the kernel when the code behind this point does not exist?  (wrong verdicts)
+      *branch_node = 0; return TC_BRANCH;
+#endif
       if (!wavefront()) { *status = TCS_BAD_GRAPH; return TC_ERROR; }
       r = rule_sibling();
       if (r < 0) return TC_NOT;

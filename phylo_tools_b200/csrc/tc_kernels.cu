@@ -579,6 +579,9 @@ __global__ void __launch_bounds__(MAXT, 1) tc_persistent_kernel(TcSource src, Tc
         code = sv.rule_loop(&st, &x);
         ex.phase = 13;
         if (code != TC_BRANCH) break;
+#ifdef PT_AONLY
+        code = TC_NOT; ++c_err; break;
+#endif
         if (CORE) { const int core = sv.finish_small_core(); if (core >= 0) { code = core ? TC_DISPLAYED : TC_NOT; break; } }   // what is left is tiny: decide it here
         if (chunks.flags & 4) { code = TC_NOT; break; }   // measuring aid: no branching at all (wrong verdicts; shows the tail without chains)
         // ---- branch on x: children 1 .. d-1 go to the pool, child 0 continues in place -------------------------------------
