@@ -240,10 +240,26 @@ def cpu_baseline_leg(sample_seconds=15.0):
     crashed = cores * per - done
     # one core alone (no neighbours competing for the memory system): the first 100 instances
     one = _ref_json(subprocess.run([ref, "bench", files[0], "100"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True).stderr)
+    # the reference's own `tc` tool as it is (examples/tc.cpp with its unconditional printing, one process per instance): SURVEY 8(d)
+    stock, stock_rate = O.ref_binary("tc_stock"), None
+    if stock is not None:
+        lines = open(files[0]).read().split("\n")
+        n_stock, verdicts = 40, 0
+        tmp = tempfile.NamedTemporaryFile("w", suffix=".nw", delete=False)
+        tmp.close()
+        t1 = time.perf_counter()
+        for i in range(n_stock):
+            with open(tmp.name, "w") as f:
+                f.write(lines[2 * i] + "\n" + lines[2 * i + 1] + "\n")
+            r = subprocess.run([stock, tmp.name], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            tail = r.stdout.rstrip().rsplit("\n", 1)[-1] if r.stdout else ""
+            verdicts += tail in ("displayed", "not displayed")
+        stock_rate = verdicts / (time.perf_counter() - t1) if verdicts else None
+        os.unlink(tmp.name)
     for fn in files:
         os.unlink(fn)
     return {"value": done / dt, "reference_crashes_or_exceptions": crashed, "unit": "instances/s", "cores": cores, "kind": "reference",
-            "one_core_instances_per_s": one.get("inst_per_s"),
+            "one_core_instances_per_s": one.get("inst_per_s"), "stock_tc_one_core_instances_per_s": stock_rate,
             "sample": "first %d instances of the batch, %d per core, reference TreeInNetContainment::displayed() with std::cout silenced; %d/%d displayed"
                       % (cores * per, per, disp, cores * per)}
 
