@@ -744,7 +744,12 @@ def main():
         n_err = int((full_stat[:total] != 0).sum().item())
         in_bytes = sum(int(dev[k].numel()) * dev[k].element_size() for k in ("host_node_off", "host_arc_off", "guest_node_off", "host_succ_off", "host_succ_adj", "host_label", "guest_parent", "guest_label"))
         resident.free()
-        return dict(ms=ms, k0=sum(k0) / len(k0), launches=launches, counters=counters, displayed=n_disp, errors=n_err, in_bytes=in_bytes)
+        k_avg = sum(k0) / len(k0)
+        k_all = [k_avg]
+        if world > 1:      # every rank's own kernel time (the step follows the slowest rank)
+            k_all = [None] * world
+            dist.all_gather_object(k_all, (k_avg, max(k0)))
+        return dict(ms=ms, k0=k_avg, k_all=k_all, launches=launches, counters=counters, displayed=n_disp, errors=n_err, in_bytes=in_bytes)
 
     # ---- headline: ONE batch of `args.instances`, sharded over the ranks (strong scaling) ----
     total_B = args.instances
@@ -758,7 +763,7 @@ def main():
     k0 = r["k0"]
     ach = ALG_BYTES_PER_INSTANCE * B / (k0 / 1000.0) / 1e9
     roofline = {"bound": "hbm", "kernel": "tc_persistent_kernel (the one launch of a step; %d instances on this GPU)" % B, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": measured_traffic("tc_persistent_kernel", B), "kernel_ms": k0, "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
+                "traffic": measured_traffic("tc_persistent_kernel", B), "kernel_ms": k0, "kernel_ms_per_rank_avg_max": r["k_all"], "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
                 "algorithmic_bytes_per_instance": ALG_BYTES_PER_INSTANCE, "bytes_actually_read_per_instance": r["in_bytes"] / max(B, 1),
                 "note": "instance-resident shared-memory solver: bound by instruction fetch and dependent shared-memory latency, not HBM (SURVEY 8(d)); see profiles/"}
 

@@ -776,10 +776,12 @@ struct TcSolver {
   // SWITCHING PER THREAD -- every thread walks the live nodes children first (the Kahn order the wavefront has just left in hscr),
   // forms the label set below every node as a 32-bit mask under its switching, and checks that the nodes with >= 2 live children
   // carry exactly the guest's clusters.  Exact (sets, not hashes) because at most 32 labels are alive.  Applicable when
-  // <= kCoreNodes live nodes, <= 32 live labels and <= kCoreSwitchings switchings remain; otherwise -1 and the caller branches.
+  // <= kCoreNodes (64) live nodes, <= 32 live labels and <= kCoreSwitchings (64) switchings remain; otherwise -1 and the caller branches.
   // Needs: fresh CSR, wavefront order in hscr (both hold when rule_loop has just returned TC_BRANCH: the caller tries this first and
   // branches only on -1).  Touches scratch only.
-  static constexpr int kCoreNodes = 64, kCoreSwitchings = 512;
+  // (kCoreSwitchings: 89 % of the stuck states of config 2 have <= 32 switchings, 95 % <= 64; every 32 more are one more pass of
+  // ~20 us on this one warp, and a 16-pass straggler at the end of a launch costs more than a level of branching)
+  static constexpr int kCoreNodes = 64, kCoreSwitchings = 64;
   int core_switchings_;   // > 0: the last verdict came from the small core, over this many switchings
   bool allow_core_;       // false: always branch (pt_options.no_small_core; keeps the branching machinery testable)
   PT_NI int finish_small_core() {

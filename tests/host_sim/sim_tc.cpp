@@ -100,19 +100,20 @@ static int solve_instance_t(const Item& root, int capN, int capM, int capNT, int
     while (code == TC_CONTINUE) {
       code = sv.rule_loop(&st, &x);
       if (code != TC_BRANCH) break;
-      { const int core = sv.finish_small_core(); if (core >= 0) { code = core ? TC_DISPLAYED : TC_NOT; break; } }
       if (getenv("SIM_DUMP_STUCK")) {   // the state the rules could not reduce (for looking at what a further rule would have to see)
         int live_n = 0, retis = 0; std::vector<int> ind(sv.n, 0), outd(sv.n, 0);
         for (int e = 0; e < sv.m; ++e) if (w.at[e] >= 0) { ++outd[w.at[e]]; ++ind[w.ah[e]]; }
         for (int v = 0; v < sv.n; ++v) { live_n += (ind[v] + outd[v]) > 0; retis += ind[v] > 1; }
         int gl = 0; for (int t = 0; t < sv.nt; ++t) gl += w.tlab[t] >= 0 && w.tpar[t] != TcSolver<HostEx, I>::TDEAD;
-        fprintf(stderr, "STUCK items=%ld live_nodes=%d retis=%d labels=%d branch_on=%d indeg=%d\n  host:", items, live_n, retis, sv.L, x, sv.indeg(x));
+        long P = 1; for (int v = 0; v < sv.n; ++v) if (ind[v] > 1) P *= ind[v];
+        fprintf(stderr, "STUCK items=%ld live_nodes=%d retis=%d switchings=%ld labels=%d branch_on=%d indeg=%d\n  host:", items, live_n, retis, P, sv.L, x, sv.indeg(x));
         for (int e = 0; e < sv.m; ++e) if (w.at[e] >= 0) fprintf(stderr, " %d>%d", (int)w.at[e], (int)w.ah[e]);
         fprintf(stderr, "\n  hlab:"); for (int v = 0; v < sv.n; ++v) if (w.hlab[v] >= 0 && ind[v] + outd[v] > 0) fprintf(stderr, " %d=%d", v, (int)w.hlab[v]);
         fprintf(stderr, "\n  guest:"); for (int t = 0; t < sv.nt; ++t) if (w.tpar[t] != TcSolver<HostEx, I>::TDEAD) fprintf(stderr, " %d<%d", t, (int)w.tpar[t]);
         fprintf(stderr, "\n  tlab:"); for (int t = 0; t < sv.nt; ++t) if (w.tlab[t] >= 0 && w.tpar[t] != TcSolver<HostEx, I>::TDEAD) fprintf(stderr, " %d=%d", t, (int)w.tlab[t]);
         fprintf(stderr, "\n");
       }
+      { const int core = sv.finish_small_core(); if (core >= 0) { code = core ? TC_DISPLAYED : TC_NOT; break; } }
       const int d = sv.indeg(x);
       std::vector<int> arcs; for (int k = 0; k < d; ++k) arcs.push_back(sv.in_arc(x, k));
       for (int k = 1; k < d; ++k) {
