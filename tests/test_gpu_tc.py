@@ -156,6 +156,57 @@ def test_malformed_offset_tables_are_per_instance_errors(pt, path, compact):
         pt.Batch(a)
 
 
+def test_double_buffered_batches_and_launch_times(pt):
+    """the streaming pattern of INTEGRATION.md: step k+1's batch is created and its solve queued while step k's kernel runs; a handle is
+    freed as soon as ITS result has arrived (pt_batch_free waits for the handle's own work, not for the stream).  Every step's verdicts
+    are right, and the handle's event ring returns one kernel time per launch."""
+    import torch
+    packs = []
+    for k in range(2):
+        p = pt.Packer()
+        p.add_generated(3000, 30, 8, 500 + k, 0)
+        p.add_generated(1000, 30, 8, 600 + k, 1)
+        packs.append(p)
+    truth = []
+    for p in packs:
+        v, s, _ = _solve(pt, p)
+        assert (s == 0).all() and v[:3000].all()
+        truth.append(v)
+    pinned = [{k: (torch.from_numpy(v.copy()).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in p.arrays(compact=1).items()} for p in packs]
+    stream = torch.cuda.current_stream().cuda_stream
+    words = (4000 + 31) // 32
+    d_bits = [torch.zeros(words, dtype=torch.int32, device="cuda") for _ in range(2)]
+    h_bits = [torch.zeros(words, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def issue(k):
+        b = pt.Batch(pinned[k % 2], stream=stream)
+        b.contain(result_bits=d_bits[k % 2], want_counters=False, stream=stream)
+        h_bits[k % 2].copy_(d_bits[k % 2], non_blocking=True)
+        ev = torch.cuda.Event(); ev.record()
+        return b, ev
+    cur = issue(0)
+    for k in range(1, 12):
+        nxt = issue(k)
+        cur[1].synchronize()
+        got = np.unpackbits(h_bits[(k - 1) % 2].numpy().view(np.uint8), bitorder="little")[:4000].astype(bool)
+        assert (got == truth[(k - 1) % 2]).all(), k
+        assert cur[0].launch_count() == 1 and 0.0 < cur[0].launch_ms(0) < 50.0
+        cur[0].free()
+        cur = nxt
+    cur[1].synchronize()
+    cur[0].free()
+    # one handle, many queued steps: the ring keeps the last 64 launch times
+    b = pt.Batch(packs[0].arrays(compact=1))
+    for _ in range(70):
+        b.contain(result_bits=d_bits[0], want_counters=False)
+    assert b.launch_count() == 70
+    ts = [b.launch_ms(i) for i in range(6, 70)]
+    assert all(0.0 < t < 50.0 for t in ts)
+    with pytest.raises(pt.PtError):
+        b.launch_ms(5)          # fallen out of the ring
+    b.free()
+
+
 def _layouts(p):
     """every input layout the batch fits: int32, int16, and uint8 (out-degrees) when every id fits a byte"""
     a = p.arrays()
