@@ -701,6 +701,8 @@ def main():
         the batch is pt_packer_add_generated(..., seed + i, kind 0) whichever rank makes it"""
         cuts = [min(total, (total * r // world + 31) // 32 * 32) for r in range(world)] + [total]
         first, count = cuts[rank], cuts[rank + 1] - cuts[rank]
+        if count == 0:
+            first = first // 32 * 32      # an empty trailing shard of a tiny batch: any word boundary will do
         packer = pt.Packer()
         packer.add_generated(count, L, R, seed + first, 0)
         host = packer.arrays(compact=layout if layout != 4 else 0)
