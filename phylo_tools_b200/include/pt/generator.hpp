@@ -97,6 +97,17 @@ void generate_random_binary_edgelist_rl(EdgeContainer& edges, NameContainer& nam
   const uint32_t n = n_from_rl(num_retis, num_leaves);
   generate_random_binary_edgelist_trl(edges, names, n - num_retis - num_leaves, num_retis, num_leaves, rng);
 }
+// from the number of nodes and reticulations / nodes and leaves (utils/generator.hpp:247-269; like the reference, the _nl form hands
+// its second argument on as the number of RETICULATIONS -- generator.hpp:268)
+template <class EdgeContainer, class NameContainer>
+void generate_random_binary_edgelist_nr(EdgeContainer& edges, NameContainer& names, uint32_t num_nodes, uint32_t num_retis, SplitMix64& rng) {
+  const uint32_t l = l_from_nr(num_nodes, num_retis);
+  generate_random_binary_edgelist_trl(edges, names, num_nodes - num_retis - l, num_retis, l, rng);
+}
+template <class EdgeContainer, class NameContainer>
+void generate_random_binary_edgelist_nl(EdgeContainer& edges, NameContainer& names, uint32_t num_nodes, uint32_t num_leaves, SplitMix64& rng) {
+  generate_random_binary_edgelist_nr(edges, names, num_nodes, num_leaves, rng);
+}
 
 
 // utils/generator.hpp:50-92: random (not necessarily binary) tree; leaves are 0..l-1 and named, the root is the LAST node

@@ -9,6 +9,7 @@
 #include "../../phylo_tools_b200/include/pt/lca.hpp"
 #include "../../phylo_tools_b200/include/pt/bridges.hpp"
 #include "../../phylo_tools_b200/include/pt/isomorphism.hpp"
+#include "../../phylo_tools_b200/include/pt/generator.hpp"
 #include <algorithm>
 #include <fstream>
 
@@ -50,6 +51,16 @@ static int bcc_mode(const char* path) {
 
 int main(int argc, char** argv) {
   if (argc >= 3 && std::string(argv[1]) == "bcc") return bcc_mode(argv[2]);
+  // generators by (nodes, reticulations) / (reticulations, leaves) (utils/generator.hpp:247-281): BASELINE config 2 is n = 239, r = 20, l = 100
+  {
+    EdgeVec e1, e2; LabelMapDefault n1, n2; SplitMix64 r1(7), r2(7);
+    generate_random_binary_edgelist_nr(e1, n1, 239, 20, r1);
+    generate_random_binary_edgelist_rl(e2, n2, 20, 100, r2);
+    assert(e1.size() == 258 && n1.size() == 100 && e1.size() == e2.size() && n1.size() == n2.size());
+    bool threw = false;
+    try { generate_random_binary_edgelist_nr(e1, n1, 240, 20, r1); } catch (const std::logic_error&) { threw = true; }   // an even number of nodes
+    assert(threw);
+  }
   // data/test.nw of the reference: ground truth "not displayed" (the reference itself crashes on it)
   assert(!tc("((a,(((b)#H1,(c)#H2),(#H1,#H2))),d);", "((a,b),(c,d));"));
   assert(tc("((a,(b)#H1),(#H1,c));", "(a,(b,c));"));
