@@ -1,5 +1,5 @@
 """profiles/r02_driver.py -- one launch of every kernel family at its bench.py size, for `ncu --set full` captures (round 2):
-    python profiles/r02_driver.py tc | lca | who | enum | iso | bridges | text | config4
+    python profiles/r02_driver.py tc | tc_shard | lca | who | enum | iso | bridges | text | config4
 Each mode warms the library's allocator up first (the captured launches are the steady-state ones: use ncu's -s / -k)."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,6 +18,15 @@ if what == "tc":
     for _ in range(4):
         b.contain(result_bits=bits, status=stat, want_counters=False)
     torch.cuda.synchronize(); print("tc", b.round_ms(0))
+elif what == "tc_shard":      # one rank's shard of config 2 at 8 GPUs: the small-core variant of the persistent kernel
+    B = 12_512
+    p = pt.Packer(); p.add_generated(B, 100, 20, SEED, 0)
+    dev = {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in p.arrays(compact=1).items()}
+    bits = torch.zeros((B + 31) // 32, dtype=torch.int32, device="cuda"); stat = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    b = pt.Batch(dev)
+    for _ in range(4):
+        b.contain(result_bits=bits, status=stat, want_counters=False)
+    torch.cuda.synchronize(); print("tc_shard", b.round_ms(0))
 elif what == "lca":
     par0 = torch.from_numpy(pt.random_tree(10_000_000, SEED)).cuda(); n = par0.numel()
     L = pt.Lca(par0)
