@@ -12,8 +12,9 @@
 // (hash map of bitsets per induced node) and, in post-order, accepts every induced node at which u's children can be matched
 // to DISTINCT induced children (bipartite matching), discarding the ancestors of an accepted node.
 //
-// Here: a WAVEFRONT over the guest's levels, deepest first (one cooperative launch, grid.sync per level).  Lists are kept as
-// host PREORDER POSITIONS in a device arena.  One thread per guest node: the children's lists are merged (heap sort of
+// Here: DATAFLOW over the guest tree (dp_who_flow_kernel: a thread starts at every guest leaf, whoever completes the last child of a
+// node goes on with that node; no levels, no grid barrier, any guest depth).  Lists are kept as host PREORDER POSITIONS in a device
+// arena.  One thread per guest node: the children's lists are merged (heap sort of
 // (position, child) keys), the induced subtree is built by the classic stack sweep over the sorted candidates -- one LCA query
 // per consecutive pair, through the same record / table layout as pt_lca_query -- and every induced node is finished the moment
 // it is popped from the stack (its subtree is complete then): the CHILD-SET UNION it hands to its parent is one 64-bit mask
@@ -77,127 +78,145 @@ __device__ inline bool dp_perfect_matching(int d, int r, const u64* rcov, int32_
   return true;
 }
 
-// mlen[u]: -2 dead (cleaned away: no labelled leaf below), -1 not computed yet, >= 0 length of M(u); moff[u] its start in the arena
-__global__ void __launch_bounds__(256) dp_who_kernel(int64_t nt, int levels, const int32_t* __restrict__ level_off, const int32_t* __restrict__ order,
-                                                     const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj, const int32_t* __restrict__ tlabel,
-                                                     const int32_t* __restrict__ lab_off, const int32_t* __restrict__ lab_pos /* host leaf positions grouped by label, ascending */, int64_t nlab,
-                                                     const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const int32_t* __restrict__ nodeat, const u64* __restrict__ table,
-                                                     const int64_t* __restrict__ level_base, int64_t* __restrict__ moff, int32_t* __restrict__ mlen, DpArena A) {
-  cg::grid_group grid = cg::this_grid();
-  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
-  for (int l = levels - 1; l >= 0; --l) {
-    if (gtid == 0) A.tops[1] = 0;
-    grid.sync();
-    for (int64_t idx = level_off[l] + gtid; idx < level_off[l + 1]; idx += gsize) {
-      const int32_t u = order[idx];
-      const int32_t cb = child_off[u], ce = child_off[u + 1];
-      if (cb == ce) {  // guest leaf: the host leaves with its label (construct_base_cases :115-126)
-        const int32_t lab = tlabel[u];
-        if (lab < 0) { mlen[u] = -2; continue; }
-        const int32_t b = (int64_t)lab < nlab ? lab_off[lab] : 0, e = (int64_t)lab < nlab ? lab_off[lab + 1] : 0;
-        const int len = e - b;
-        const unsigned long long at = atomicAdd(&A.tops[0], (unsigned long long)len);
-        if ((int64_t)(at + len) > A.mcap) { A.flags[1] = 1; mlen[u] = 0; moff[u] = 0; continue; }
-        for (int k = 0; k < len; ++k) A.mpos[at + k] = lab_pos[b + k];
-        moff[u] = (int64_t)at; mlen[u] = len;
-        continue;
-      }
-      // live children, K = total number of candidates
-      int d = 0; int64_t K = 0; bool missing = false, single = true; int32_t only = -1;
-      for (int32_t j = cb; j < ce; ++j) {
-        const int32_t c = child_adj[j], len = mlen[c];
-        if (len == -2) continue;
-        if (len == 0) missing = true;   // merge_child_poss :180-230: an empty child list empties the parent
-        ++d; K += len; single &= len == 1; only = c;
-      }
-      if (d == 0) { mlen[u] = -2; continue; }
-      if (missing) { mlen[u] = 0; moff[u] = 0; continue; }
-      if (d == 1) { mlen[u] = mlen[only]; moff[u] = moff[only]; continue; }   // :167 -- the same list (shared, never modified)
-      if (d > DP_MAX_CHILDREN) { A.flags[0] = 1; mlen[u] = 0; moff[u] = 0; continue; }
-      if (single && d <= 8) {
-        // every child has exactly one candidate: u is displayed iff the candidates sit in d different branches of their
-        // common ancestor v, i.e. all consecutive LCAs (in preorder) are v and no candidate is v itself
-        uint32_t ps[8]; int k = 0;
-        for (int32_t j = cb; j < ce; ++j) {
-          const int32_t c = child_adj[j];
-          if (mlen[c] != 1) continue;
-          const uint32_t p = (uint32_t)A.mpos[moff[c]];
-          int a = k++;
-          while (a > 0 && ps[a - 1] > p) { ps[a] = ps[a - 1]; --a; }
-          ps[a] = p;
-        }
-        const int32_t v = lca_one(rec, keypos, table, level_base, nodeat[ps[0]], nodeat[ps[d - 1]]);
-        const uint32_t vp = rec[v].pos;
-        bool ok = true;
-        for (int a = 0; a < d && ok; ++a) ok = ps[a] != vp;
-        for (int a = 0; a + 1 < d && ok; ++a) ok = ps[a] != ps[a + 1] && lca_one(rec, keypos, table, level_base, nodeat[ps[a]], nodeat[ps[a + 1]]) == v;
-        if (!ok) { mlen[u] = 0; moff[u] = 0; continue; }
-        const unsigned long long at = atomicAdd(&A.tops[0], 1ull);
-        if ((int64_t)(at + 1) > A.mcap) { A.flags[1] = 1; mlen[u] = 0; moff[u] = 0; continue; }
-        A.mpos[at] = (int32_t)vp; moff[u] = (int64_t)at; mlen[u] = 1;
-        continue;
-      }
-      // ---- general case: scratch = keys (2K words) | per induced node (V <= 2K): pos, depth, first, next, nchild, sb | cov (2V words)
-      //      | stack V | rcov 2V | matchR V | seen V | result K
-      const int64_t V = 2 * K;
-      const int64_t need = 2 * K + 6 * V + 2 * V + V + 2 * V + V + V + K + 16;
-      const unsigned long long sat = atomicAdd(&A.tops[1], (unsigned long long)need);
-      if ((int64_t)(sat + need) > A.scap) { A.flags[2] = 1; mlen[u] = 0; moff[u] = 0; continue; }
-      int32_t* sp = A.scratch + sat + (sat & 1);   // 8-byte alignment for the 64-bit arrays
-      u64* keys = reinterpret_cast<u64*>(sp); sp += 2 * K;
-      u64* cov = reinterpret_cast<u64*>(sp); sp += 2 * V;
-      u64* rcov = reinterpret_cast<u64*>(sp); sp += 2 * V;
-      int32_t* vpos = sp; sp += V; int32_t* vdepth = sp; sp += V; int32_t* vfirst = sp; sp += V; int32_t* vnext = sp; sp += V;
-      int32_t* vnch = sp; sp += V; int32_t* vsb = sp; sp += V; int32_t* stack = sp; sp += V; int32_t* matchR = sp; sp += V; int32_t* seen = sp; sp += V;
-      int32_t* result = sp;
-      {
-        int64_t k = 0; int ci = 0;
-        for (int32_t j = cb; j < ce; ++j) {
-          const int32_t c = child_adj[j], len = mlen[c];
-          if (len == -2) continue;
-          const int64_t o = moff[c];
-          for (int t = 0; t < len; ++t) keys[k++] = ((u64)(uint32_t)A.mpos[o + t] << 8) | (u64)ci;
-          ++ci;
-        }
-      }
-      dp_heapsort(keys, (int)K);
-      int nv = 0, top = -1, nres = 0, cur = -1;
-      // a node is FINISHED when it leaves the stack: its subtree is complete, so it can be matched and handed to its parent
-      auto finish = [&](int x, int q) {
-        int succ = 0;
-        if (!vsb[x] && vnch[x] >= d) {
-          int r = 0;
-          for (int y = vfirst[x]; y >= 0; y = vnext[y]) rcov[r++] = cov[y];
-          if (dp_perfect_matching(d, r, rcov, matchR, seen)) { result[nres++] = vpos[x]; succ = 1; }   // perfect_child_matching :174-177
-        }
-        if (q >= 0) { cov[q] |= cov[x]; vsb[q] |= succ | vsb[x]; vnext[x] = vfirst[q]; vfirst[q] = x; vnch[q]++; }   // :140-149, :160
-      };
-      auto newnode = [&](uint32_t p, u64 self) { const int x = nv++; vpos[x] = (int32_t)p; vdepth[x] = (int32_t)(keypos[p] >> 32); vfirst[x] = -1; vnext[x] = -1; vnch[x] = 0; vsb[x] = 0; cov[x] = self; return x; };
-      for (int64_t j = 0; j < K; ++j) {
-        const uint32_t p = (uint32_t)(keys[j] >> 8); const u64 bit = 1ull << (keys[j] & 255);
-        if (cur >= 0 && (uint32_t)vpos[cur] == p) { cov[cur] |= bit; continue; }   // the same host node is a candidate of several children
-        const int w = newnode(p, bit);
-        cur = w;
-        if (top < 0) { stack[++top] = w; continue; }
-        const int t = stack[top];
-        const int32_t lnode = lca_one(rec, keypos, table, level_base, nodeat[vpos[t]], nodeat[p]);   // induced_tree.hpp:128-138
-        const uint32_t lp = rec[lnode].pos; const int32_t ld = (int32_t)(keypos[lp] >> 32);
-        if (lp != (uint32_t)vpos[t]) {
-          while (top >= 1 && vdepth[stack[top - 1]] >= ld) { finish(stack[top], stack[top - 1]); --top; }
-          if ((uint32_t)vpos[stack[top]] != lp) { const int Lx = newnode(lp, 0ull); finish(stack[top], Lx); stack[top] = Lx; }
-        }
-        stack[++top] = w;
-      }
-      while (top >= 1) { finish(stack[top], stack[top - 1]); --top; }
-      if (top == 0) finish(stack[0], -1);
-      if (nres == 0) { mlen[u] = 0; moff[u] = 0; continue; }
-      const unsigned long long at = atomicAdd(&A.tops[0], (unsigned long long)nres);
-      if ((int64_t)(at + nres) > A.mcap) { A.flags[1] = 1; mlen[u] = 0; moff[u] = 0; continue; }
-      for (int k = 0; k < nres; ++k) A.mpos[at + k] = result[k];
-      moff[u] = (int64_t)at; mlen[u] = nres;
-    }
-    grid.sync();
+// mlen[u]: -2 dead (cleaned away: no labelled leaf below), -1 not computed yet, >= 0 length of M(u); moff[u] its start in the arena.
+// One guest node: everything its children have left (mlen / moff / the list arena) is read through L2 -- other SMs wrote it during
+// the same launch.
+__device__ __forceinline__ void dp_node(const int32_t u, const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj, const int32_t* __restrict__ tlabel,
+                                        const int32_t* __restrict__ lab_off, const int32_t* __restrict__ lab_pos, int64_t nlab, const LcaRecord* __restrict__ rec,
+                                        const u64* __restrict__ keypos, const int32_t* __restrict__ nodeat, const u64* __restrict__ table, const int64_t* __restrict__ level_base,
+                                        int64_t* moff, int32_t* mlen, const DpArena& A) {
+  const int32_t cb = child_off[u], ce = child_off[u + 1];
+  if (cb == ce) {  // guest leaf: the host leaves with its label (construct_base_cases :115-126)
+    const int32_t lab = tlabel[u];
+    if (lab < 0) { mlen[u] = -2; return; }
+    const int32_t b = (int64_t)lab < nlab ? lab_off[lab] : 0, e = (int64_t)lab < nlab ? lab_off[lab + 1] : 0;
+    const int len = e - b;
+    const unsigned long long at = atomicAdd(&A.tops[0], (unsigned long long)len);
+    if ((int64_t)(at + len) > A.mcap) { A.flags[1] = 1; mlen[u] = 0; moff[u] = 0; return; }
+    for (int k = 0; k < len; ++k) A.mpos[at + k] = lab_pos[b + k];
+    moff[u] = (int64_t)at; mlen[u] = len;
+    return;
   }
+  // live children, K = total number of candidates
+  int d = 0; int64_t K = 0; bool missing = false, single = true; int32_t only = -1;
+  for (int32_t j = cb; j < ce; ++j) {
+    const int32_t c = child_adj[j], len = __ldcg(&mlen[c]);
+    if (len == -2) continue;
+    if (len == 0) missing = true;   // merge_child_poss :180-230: an empty child list empties the parent
+    ++d; K += len; single &= len == 1; only = c;
+  }
+  if (d == 0) { mlen[u] = -2; return; }
+  if (missing) { mlen[u] = 0; moff[u] = 0; return; }
+  if (d == 1) { mlen[u] = __ldcg(&mlen[only]); moff[u] = __ldcg(&moff[only]); return; }   // :167 -- the same list (shared, never modified)
+  if (d > DP_MAX_CHILDREN) { A.flags[0] = 1; mlen[u] = 0; moff[u] = 0; return; }
+  if (single && d <= 8) {
+    // every child has exactly one candidate: u is displayed iff the candidates sit in d different branches of their
+    // common ancestor v, i.e. all consecutive LCAs (in preorder) are v and no candidate is v itself
+    uint32_t ps[8]; int k = 0;
+    for (int32_t j = cb; j < ce; ++j) {
+      const int32_t c = child_adj[j];
+      if (__ldcg(&mlen[c]) != 1) continue;
+      const uint32_t p = (uint32_t)__ldcg(&A.mpos[__ldcg(&moff[c])]);
+      int a = k++;
+      while (a > 0 && ps[a - 1] > p) { ps[a] = ps[a - 1]; --a; }
+      ps[a] = p;
+    }
+    const int32_t v = lca_one(rec, keypos, table, level_base, nodeat[ps[0]], nodeat[ps[d - 1]]);
+    const uint32_t vp = rec[v].pos;
+    bool ok = true;
+    for (int a = 0; a < d && ok; ++a) ok = ps[a] != vp;
+    for (int a = 0; a + 1 < d && ok; ++a) ok = ps[a] != ps[a + 1] && lca_one(rec, keypos, table, level_base, nodeat[ps[a]], nodeat[ps[a + 1]]) == v;
+    if (!ok) { mlen[u] = 0; moff[u] = 0; return; }
+    const unsigned long long at = atomicAdd(&A.tops[0], 1ull);
+    if ((int64_t)(at + 1) > A.mcap) { A.flags[1] = 1; mlen[u] = 0; moff[u] = 0; return; }
+    A.mpos[at] = (int32_t)vp; moff[u] = (int64_t)at; mlen[u] = 1;
+    return;
+  }
+  // ---- general case: scratch = keys (2K words) | per induced node (V <= 2K): pos, depth, first, next, nchild, sb | cov (2V words)
+  //      | stack V | rcov 2V | matchR V | seen V | result K
+  const int64_t V = 2 * K;
+  const int64_t need = 2 * K + 6 * V + 2 * V + V + 2 * V + V + V + K + 16;
+  const unsigned long long sat = atomicAdd(&A.tops[1], (unsigned long long)need);
+  if ((int64_t)(sat + need) > A.scap) { A.flags[2] = 1; mlen[u] = 0; moff[u] = 0; return; }
+  int32_t* sp = A.scratch + sat + (sat & 1);   // 8-byte alignment for the 64-bit arrays
+  u64* keys = reinterpret_cast<u64*>(sp); sp += 2 * K;
+  u64* cov = reinterpret_cast<u64*>(sp); sp += 2 * V;
+  u64* rcov = reinterpret_cast<u64*>(sp); sp += 2 * V;
+  int32_t* vpos = sp; sp += V; int32_t* vdepth = sp; sp += V; int32_t* vfirst = sp; sp += V; int32_t* vnext = sp; sp += V;
+  int32_t* vnch = sp; sp += V; int32_t* vsb = sp; sp += V; int32_t* stack = sp; sp += V; int32_t* matchR = sp; sp += V; int32_t* seen = sp; sp += V;
+  int32_t* result = sp;
+  {
+    int64_t k = 0; int ci = 0;
+    for (int32_t j = cb; j < ce; ++j) {
+      const int32_t c = child_adj[j], len = __ldcg(&mlen[c]);
+      if (len == -2) continue;
+      const int64_t o = __ldcg(&moff[c]);
+      for (int t = 0; t < len; ++t) keys[k++] = ((u64)(uint32_t)__ldcg(&A.mpos[o + t]) << 8) | (u64)ci;
+      ++ci;
+    }
+  }
+  dp_heapsort(keys, (int)K);
+  int nv = 0, top = -1, nres = 0, cur = -1;
+  // a node is FINISHED when it leaves the stack: its subtree is complete, so it can be matched and handed to its parent
+  auto finish = [&](int x, int q) {
+    int succ = 0;
+    if (!vsb[x] && vnch[x] >= d) {
+      int r = 0;
+      for (int y = vfirst[x]; y >= 0; y = vnext[y]) rcov[r++] = cov[y];
+      if (dp_perfect_matching(d, r, rcov, matchR, seen)) { result[nres++] = vpos[x]; succ = 1; }   // perfect_child_matching :174-177
+    }
+    if (q >= 0) { cov[q] |= cov[x]; vsb[q] |= succ | vsb[x]; vnext[x] = vfirst[q]; vfirst[q] = x; vnch[q]++; }   // :140-149, :160
+  };
+  auto newnode = [&](uint32_t p, u64 self) { const int x = nv++; vpos[x] = (int32_t)p; vdepth[x] = (int32_t)(keypos[p] >> 32); vfirst[x] = -1; vnext[x] = -1; vnch[x] = 0; vsb[x] = 0; cov[x] = self; return x; };
+  for (int64_t j = 0; j < K; ++j) {
+    const uint32_t p = (uint32_t)(keys[j] >> 8); const u64 bit = 1ull << (keys[j] & 255);
+    if (cur >= 0 && (uint32_t)vpos[cur] == p) { cov[cur] |= bit; continue; }   // the same host node is a candidate of several children
+    const int w = newnode(p, bit);
+    cur = w;
+    if (top < 0) { stack[++top] = w; continue; }
+    const int t = stack[top];
+    const int32_t lnode = lca_one(rec, keypos, table, level_base, nodeat[vpos[t]], nodeat[p]);   // induced_tree.hpp:128-138
+    const uint32_t lp = rec[lnode].pos; const int32_t ld = (int32_t)(keypos[lp] >> 32);
+    if (lp != (uint32_t)vpos[t]) {
+      while (top >= 1 && vdepth[stack[top - 1]] >= ld) { finish(stack[top], stack[top - 1]); --top; }
+      if ((uint32_t)vpos[stack[top]] != lp) { const int Lx = newnode(lp, 0ull); finish(stack[top], Lx); stack[top] = Lx; }
+    }
+    stack[++top] = w;
+  }
+  while (top >= 1) { finish(stack[top], stack[top - 1]); --top; }
+  if (top == 0) finish(stack[0], -1);
+  if (nres == 0) { mlen[u] = 0; moff[u] = 0; return; }
+  const unsigned long long at = atomicAdd(&A.tops[0], (unsigned long long)nres);
+  if ((int64_t)(at + nres) > A.mcap) { A.flags[1] = 1; mlen[u] = 0; moff[u] = 0; return; }
+  for (int k = 0; k < nres; ++k) A.mpos[at + k] = result[k];
+  moff[u] = (int64_t)at; mlen[u] = nres;
+}
+
+// DATAFLOW over the guest tree, no levels and no grid barrier: one thread starts at every guest leaf; whoever completes the LAST
+// child of a node (a counter per node, decremented behind a fence) goes on with that node at once, everybody else is done.  The
+// level-synchronous version this replaces spent 204 stall cycles per issued instruction at its grid barrier (62 levels for a
+// random guest of 10^6 leaves, most of them nearly empty) and paid one barrier per level of a deep guest.
+__global__ void __launch_bounds__(256) dp_who_flow_kernel(int64_t nt, const int32_t* __restrict__ gparent, int32_t* __restrict__ pending, const int32_t* __restrict__ child_off,
+                                                          const int32_t* __restrict__ child_adj, const int32_t* __restrict__ tlabel, const int32_t* __restrict__ lab_off,
+                                                          const int32_t* __restrict__ lab_pos, int64_t nlab, const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos,
+                                                          const int32_t* __restrict__ nodeat, const u64* __restrict__ table, const int64_t* __restrict__ level_base,
+                                                          int64_t* moff, int32_t* mlen, DpArena A) {
+  unsigned long long done = 0;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < nt; idx += (int64_t)gridDim.x * blockDim.x) {
+    int32_t u = (int32_t)idx;
+    if (child_off[u] != child_off[u + 1]) continue;   // start at the leaves
+    for (;;) {
+      dp_node(u, child_off, child_adj, tlabel, lab_off, lab_pos, nlab, rec, keypos, nodeat, table, level_base, moff, mlen, A);
+      ++done;
+      const int32_t p = gparent[u];
+      if (p < 0 || p >= nt) break;
+      __threadfence();                                 // my list is out before my parent can count me
+      if (atomicSub(&pending[p], 1) != 1) break;       // somebody else will complete p
+      __threadfence();
+      u = p;
+    }
+  }
+  if (done) atomicAdd(&A.tops[2], done);   // nodes processed: all of them unless the parent array has a cycle
 }
 
 // host leaves grouped by label: count, then fill with POSITIONS; every group is sorted afterwards (small groups: insertion sort)
@@ -427,11 +446,10 @@ int pt_who_build(pt_who** out, const int32_t* host_parent, const int32_t* host_l
   const int64_t nlab = n + nt;
   int32_t* hdeg = (int32_t*)dalloc((size_t)n * 4 + 4); int32_t* small = (int32_t*)dalloc(256); int32_t* lcnt = (int32_t*)dalloc((size_t)nlab * 4 + 4); int32_t* loff = (int32_t*)dalloc((size_t)nlab * 4 + 4);
   int32_t* tdeg = (int32_t*)dalloc((size_t)nt * 4 + 4); int32_t* toff = (int32_t*)dalloc((size_t)nt * 4 + 4); int32_t* tadj = (int32_t*)dalloc((size_t)nt * 4);
-  int32_t* order = (int32_t*)dalloc((size_t)nt * 4); int32_t* depth = (int32_t*)dalloc((size_t)nt * 4); int32_t* size = (int32_t*)dalloc((size_t)nt * 4);
-  int32_t* pre = (int32_t*)dalloc((size_t)nt * 4); int32_t* level_off = (int32_t*)dalloc((size_t)nt * 4 + 8); int32_t* mlen = (int32_t*)dalloc((size_t)nt * 4);
+  int32_t* mlen = (int32_t*)dalloc((size_t)nt * 4);
   int64_t* moff = (int64_t*)dalloc((size_t)nt * 8); int32_t* lpos = (int32_t*)dalloc((size_t)n * 4);
   int64_t* scan_tmp = (int64_t*)dalloc(((size_t)((std::max(nlab, nt) + SCAN_TILE - 1) / SCAN_TILE) + 1) * 8);
-  DP_PTR(hdeg); DP_PTR(small); DP_PTR(lcnt); DP_PTR(loff); DP_PTR(tdeg); DP_PTR(toff); DP_PTR(tadj); DP_PTR(order); DP_PTR(depth); DP_PTR(size); DP_PTR(pre); DP_PTR(level_off);
+  DP_PTR(hdeg); DP_PTR(small); DP_PTR(lcnt); DP_PTR(loff); DP_PTR(tdeg); DP_PTR(toff); DP_PTR(tadj);
   DP_PTR(mlen); DP_PTR(moff); DP_PTR(lpos); DP_PTR(scan_tmp);
   DP_TRY(cudaMemsetAsync(hdeg, 0, (size_t)n * 4 + 4, s)); DP_TRY(cudaMemsetAsync(tdeg, 0, (size_t)nt * 4 + 4, s)); DP_TRY(cudaMemsetAsync(small, 0, 256, s));
   DP_TRY(cudaMemsetAsync(lcnt, 0, (size_t)nlab * 4 + 4, s));
@@ -450,21 +468,11 @@ int pt_who_build(pt_who** out, const int32_t* host_parent, const int32_t* host_l
   DP_TRY(cudaStreamSynchronize(s));
   if (info[8] != 1 || info[10]) return fail(set_error(PT_ERR_INVALID, "pt_who_build: guest is not a rooted tree (%d roots)", info[8]));
   if (info[19]) return fail(set_error(PT_ERR_INVALID, "pt_who_build: label id out of range (must be < n + nt)"));
-  int occ = 0;
-  DP_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lca_sweeps_kernel, 256, 0));
-  {
-    const int cgrid = dp.sms * std::max(1, std::min(occ, 4));
-    int32_t root = info[9]; int64_t nn = nt; int32_t* ctr = small + 24; int32_t* inf = small + 8;
-    void* args[] = {&nn, &root, &toff, &tadj, &order, &depth, &size, &pre, &level_off, &ctr, &inf};
-    DP_TRY(cudaLaunchCooperativeKernel((void*)lca_sweeps_kernel, dim3(cgrid), dim3(256), args, 0, s));
-  }
-  DP_TRY(cudaMemcpyAsync(info, small, 256, cudaMemcpyDeviceToHost, s));
-  DP_TRY(cudaStreamSynchronize(s));
-  if (info[12] != (int32_t)nt) return fail(set_error(PT_ERR_INVALID, "pt_who_build: guest parent array has a cycle"));
-  const int levels = info[11];
-  // arenas: the lists of one guest level are disjoint sets of candidates over disjoint label sets, so a level holds at most one
-  // entry per labelled host leaf; the total over all levels is unknown in advance -> grow and repeat on overflow
+  // arenas: the lists of the nodes of one guest level are disjoint sets of candidates over disjoint label sets, so a level holds at most
+  // one entry per labelled host leaf; the total over all levels (and the scratch of the nodes that need the general case: ~17 words per
+  // merged candidate, never reused -- there are no levels to reuse it between) is unknown in advance -> grow and repeat on overflow
   int64_t mcap = 2 * (n + nt) + 1024, scap = 48 * (n + 64) + 64 * 1024;
+  int32_t* pending = (int32_t*)dalloc((size_t)nt * 4 + 4); DP_PTR(pending);
   for (int attempt = 0;; ++attempt) {
     int32_t* mpos = nullptr; int32_t* scratch = nullptr; unsigned long long* tops = nullptr;
     DP_TRY(lca_malloc((void**)&mpos, (size_t)mcap * 4)); owned.push_back(mpos);
@@ -472,16 +480,16 @@ int pt_who_build(pt_who** out, const int32_t* host_parent, const int32_t* host_l
     DP_TRY(lca_malloc((void**)&tops, 64)); owned.push_back(tops);
     DP_TRY(cudaMemsetAsync(tops, 0, 64, s)); DP_TRY(cudaMemsetAsync(small + 32, 0, 64, s));
     DP_TRY(cudaMemsetAsync(mlen, 0xff, (size_t)nt * 4, s));
+    DP_TRY(cudaMemcpyAsync(pending, tdeg, (size_t)nt * 4, cudaMemcpyDeviceToDevice, s));   // children still to come, per guest node
     DpArena A{mpos, mcap, scratch, scap, tops, small + 32};
-    DP_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_who_kernel, 256, 0));
-    const int cgrid = (int)std::min<int64_t>((int64_t)dp.sms * std::max(1, std::min(occ, 4)), (nt + 255) / 256);
-    int64_t nn = nt, nl = nlab; int lv = levels;
-    const LcaRecord* rec = H->rec; const u64* keypos = H->keypos; const int32_t* nodeat = H->nodeat; const u64* table = H->table; const int64_t* lb = H->d_level_base;
-    const int32_t* lo = level_off; const int32_t* ord = order; const int32_t* co = toff; const int32_t* ca = tadj; const int32_t* lo2 = loff; const int32_t* lp2 = lpos;
-    void* args[] = {&nn, &lv, &lo, &ord, &co, &ca, &gl, &lo2, &lp2, &nl, &rec, &keypos, &nodeat, &table, &lb, &moff, &mlen, &A};
-    DP_TRY(cudaLaunchCooperativeKernel((void*)dp_who_kernel, dim3(std::max(cgrid, 1)), dim3(256), args, 0, s));
+    dp_who_flow_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)dp.sms * 16, (nt + 255) / 256)), 256, 0, s>>>(
+        nt, gp, pending, toff, tadj, gl, loff, lpos, nlab, H->rec, H->keypos, H->nodeat, H->table, H->d_level_base, moff, mlen, A);
+    DP_TRY(cudaGetLastError());
+    unsigned long long processed = 0;
     DP_TRY(cudaMemcpyAsync(info, small, 256, cudaMemcpyDeviceToHost, s));
+    DP_TRY(cudaMemcpyAsync(&processed, tops + 2, 8, cudaMemcpyDeviceToHost, s));
     DP_TRY(cudaStreamSynchronize(s));
+    if (processed != (unsigned long long)nt) return fail(set_error(PT_ERR_INVALID, "pt_who_build: guest parent array has a cycle"));
     if (info[32]) return fail(set_error(PT_ERR_UNSUPPORTED, "pt_who_build: a guest node has more than %d children", DP_MAX_CHILDREN));
     if (!info[33] && !info[34]) {
       // compact into CSR order by guest node, positions -> host node ids

@@ -534,55 +534,61 @@ __device__ __forceinline__ int32_t lca_one(const LcaRecord* __restrict__ rec, co
 // possibilities are merged in host preorder, the induced subtree is built from the LCAs of consecutive candidates
 // (utils/induced_tree.hpp:128-138) and a bipartite matching assigns children to distinct branches.  With a single-labelled
 // host every list has at most one entry, the induced subtree of k candidates needs exactly the k-1 consecutive LCAs, and
-// the matching degenerates to "all consecutive LCAs are the same node v and no candidate is v itself".  One wavefront over
-// the guest's levels, deepest first; each guest node = (small sort of its children's images by host preorder) + k-1 LCA queries.
+// the matching degenerates to "all consecutive LCAs are the same node v and no candidate is v itself".  Each guest node = (small
+// sort of its children's images by host preorder) + k-1 LCA queries.
 constexpr int WD_MAX_CHILDREN = 64;
-__global__ void __launch_bounds__(256) who_displays_kernel(int64_t nt, int levels, const int32_t* __restrict__ level_off, const int32_t* __restrict__ order,
-                                                           const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj,
-                                                           const int32_t* __restrict__ tlabel, const int32_t* __restrict__ l2h, int64_t nlab,
-                                                           const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table,
-                                                           const int64_t* __restrict__ level_base, int32_t* __restrict__ disp /* -2 dead, -1 not displayed, >= 0 host node */,
-                                                           int32_t* __restrict__ flags /* [0] too many children */) {
-  cg::grid_group grid = cg::this_grid();
-  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsize = (int64_t)gridDim.x * blockDim.x;
-  for (int l = levels - 1; l >= 0; --l) {
-    for (int64_t i = level_off[l] + gtid; i < level_off[l + 1]; i += gsize) {
-      const int32_t u = order[i];
-      const int32_t cb = child_off[u], ce = child_off[u + 1];
-      int32_t d;
-      if (cb == ce) {  // guest leaf: base case construct_base_cases :115-126
-        const int32_t lab = tlabel[u];
-        d = lab < 0 ? -2 : ((int64_t)lab < nlab ? l2h[lab] : -1);
-      } else {
-        int32_t img[WD_MAX_CHILDREN]; uint32_t ps[WD_MAX_CHILDREN];
-        int k = 0; bool missing = false, overflow = false;
-        for (int32_t j = cb; j < ce; ++j) {
-          const int32_t c = disp[child_adj[j]];
-          if (c == -2) continue;               // unlabelled dangling subtree: cleaned away
-          if (c == -1) { missing = true; break; }  // merge_child_poss :180-230: an empty child list empties the parent
-          if (k == WD_MAX_CHILDREN) { overflow = true; break; }
-          // insertion sort by host preorder position (sort_by_order :108-111)
-          const uint32_t p = rec[c].pos;
-          int a = k++;
-          while (a > 0 && ps[a - 1] > p) { ps[a] = ps[a - 1]; img[a] = img[a - 1]; --a; }
-          ps[a] = p; img[a] = c;
-        }
-        if (overflow) { flags[0] = 1; d = -1; }
-        else if (missing) d = -1;
-        else if (k == 0) d = -2;
-        else if (k == 1) d = img[0];             // :167: a node with one child maps where the child maps
-        else {
-          const int32_t v = lca_one(rec, keypos, table, level_base, img[0], img[k - 1]);
-          bool ok = true;
-          for (int a = 0; a < k && ok; ++a) ok = img[a] != v;
-          for (int a = 0; a + 1 < k && ok; ++a) ok = lca_one(rec, keypos, table, level_base, img[a], img[a + 1]) == v;
-          d = ok ? v : -1;
-        }
-      }
-      disp[u] = d;
-    }
-    grid.sync();
+__device__ __forceinline__ int32_t wd_node(const int32_t u, const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj, const int32_t* __restrict__ tlabel,
+                                           const int32_t* __restrict__ l2h, int64_t nlab, const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos,
+                                           const u64* __restrict__ table, const int64_t* __restrict__ level_base, const int32_t* disp, int32_t* __restrict__ flags) {
+  const int32_t cb = child_off[u], ce = child_off[u + 1];
+  if (cb == ce) {  // guest leaf: base case construct_base_cases :115-126
+    const int32_t lab = tlabel[u];
+    return lab < 0 ? -2 : ((int64_t)lab < nlab ? l2h[lab] : -1);
   }
+  int32_t img[WD_MAX_CHILDREN]; uint32_t ps[WD_MAX_CHILDREN];
+  int k = 0;
+  for (int32_t j = cb; j < ce; ++j) {
+    const int32_t c = __ldcg(&disp[child_adj[j]]);   // (written by another SM during the same launch: through L2)
+    if (c == -2) continue;               // unlabelled dangling subtree: cleaned away
+    if (c == -1) return -1;              // merge_child_poss :180-230: an empty child list empties the parent
+    if (k == WD_MAX_CHILDREN) { flags[0] = 1; return -1; }
+    // insertion sort by host preorder position (sort_by_order :108-111)
+    const uint32_t p = rec[c].pos;
+    int a = k++;
+    while (a > 0 && ps[a - 1] > p) { ps[a] = ps[a - 1]; img[a] = img[a - 1]; --a; }
+    ps[a] = p; img[a] = c;
+  }
+  if (k == 0) return -2;
+  if (k == 1) return img[0];             // :167: a node with one child maps where the child maps
+  const int32_t v = lca_one(rec, keypos, table, level_base, img[0], img[k - 1]);
+  bool ok = true;
+  for (int a = 0; a < k && ok; ++a) ok = img[a] != v;
+  for (int a = 0; a + 1 < k && ok; ++a) ok = lca_one(rec, keypos, table, level_base, img[a], img[a + 1]) == v;
+  return ok ? v : -1;
+}
+// DATAFLOW over the guest tree (no levels, no grid barrier: see dp_who_flow_kernel): a thread starts at every guest leaf; whoever
+// completes the last child of a node goes on with that node
+__global__ void __launch_bounds__(256) who_displays_kernel(int64_t nt, const int32_t* __restrict__ gparent, int32_t* __restrict__ pending, const int32_t* __restrict__ child_off,
+                                                           const int32_t* __restrict__ child_adj, const int32_t* __restrict__ tlabel, const int32_t* __restrict__ l2h, int64_t nlab,
+                                                           const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table,
+                                                           const int64_t* __restrict__ level_base, int32_t* disp /* -2 dead, -1 not displayed, >= 0 host node */,
+                                                           int32_t* __restrict__ flags /* [0] too many children */, unsigned long long* __restrict__ processed) {
+  unsigned long long done = 0;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < nt; idx += (int64_t)gridDim.x * blockDim.x) {
+    int32_t u = (int32_t)idx;
+    if (child_off[u] != child_off[u + 1]) continue;
+    for (;;) {
+      disp[u] = wd_node(u, child_off, child_adj, tlabel, l2h, nlab, rec, keypos, table, level_base, disp, flags);
+      ++done;
+      const int32_t p = gparent[u];
+      if (p < 0 || p >= nt) break;
+      __threadfence();
+      if (atomicSub(&pending[p], 1) != 1) break;
+      __threadfence();
+      u = p;
+    }
+  }
+  if (done) atomicAdd(processed, done);
 }
 
 __global__ void wd_label_map_kernel(int64_t n, const int32_t* __restrict__ deg, const int32_t* __restrict__ hlabel, int64_t nlab, int32_t* __restrict__ l2h, int32_t* __restrict__ flags) {
@@ -1002,10 +1008,9 @@ extern "C" int pt_tree_who_displays(const int32_t* host_parent, const int32_t* h
   const int64_t nlab = n + nt;
   int32_t* hdeg = (int32_t*)dalloc((size_t)n * 4 + 4); int32_t* small = (int32_t*)dalloc(128); int32_t* l2h = (int32_t*)dalloc((size_t)nlab * 4);
   int32_t* tdeg = (int32_t*)dalloc((size_t)nt * 4 + 4); int32_t* toff = (int32_t*)dalloc((size_t)nt * 4 + 4); int32_t* tadj = (int32_t*)dalloc((size_t)nt * 4);
-  int32_t* order = (int32_t*)dalloc((size_t)nt * 4); int32_t* depth = (int32_t*)dalloc((size_t)nt * 4); int32_t* size = (int32_t*)dalloc((size_t)nt * 4);
-  int32_t* pre = (int32_t*)dalloc((size_t)nt * 4); int32_t* level_off = (int32_t*)dalloc((size_t)nt * 4 + 8); int32_t* disp = (int32_t*)dalloc((size_t)nt * 4);
+  int32_t* disp = (int32_t*)dalloc((size_t)nt * 4);
   int64_t* scan_tmp = (int64_t*)dalloc(((size_t)((std::max(n, nt) + SCAN_TILE - 1) / SCAN_TILE) + 1) * 8);
-  WD_PTR(hdeg); WD_PTR(small); WD_PTR(l2h); WD_PTR(tdeg); WD_PTR(toff); WD_PTR(tadj); WD_PTR(order); WD_PTR(depth); WD_PTR(size); WD_PTR(pre); WD_PTR(level_off); WD_PTR(disp); WD_PTR(scan_tmp);
+  WD_PTR(hdeg); WD_PTR(small); WD_PTR(l2h); WD_PTR(tdeg); WD_PTR(toff); WD_PTR(tadj); WD_PTR(disp); WD_PTR(scan_tmp);
   WD_TRY(cudaMemsetAsync(hdeg, 0, (size_t)n * 4 + 4, s)); WD_TRY(cudaMemsetAsync(tdeg, 0, (size_t)nt * 4 + 4, s)); WD_TRY(cudaMemsetAsync(small, 0, 128, s));
   WD_TRY(cudaMemsetAsync(l2h, 0xff, (size_t)nlab * 4, s));
   lca_count_kernel<<<grid, 256, 0, s>>>(hp, n, hdeg, small);           // host out-degrees (leaf test); host validity was checked by pt_lca_build
@@ -1020,26 +1025,18 @@ extern "C" int pt_tree_who_displays(const int32_t* host_parent, const int32_t* h
   if (info[8] != 1 || info[10]) { cleanup(); return set_error(PT_ERR_INVALID, "pt_tree_who_displays: guest is not a rooted tree (%d roots)", info[8]); }
   if (info[17]) { cleanup(); return set_error(PT_ERR_INVALID, "single-label map for multi-labeled tree/network"); }  // label_matching.hpp:51-52
   if (info[18]) { cleanup(); return set_error(PT_ERR_INVALID, "pt_tree_who_displays: label id out of range (must be < n + nt)"); }
-  int occ = 0;
-  WD_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lca_sweeps_kernel, 256, 0));
   {
-    const int cgrid = dp.sms * std::max(1, std::min(occ, 4));
-    int32_t root = info[9]; int64_t nn = nt; int32_t* ctr = small + 24; int32_t* inf = small + 8;
-    void* args[] = {&nn, &root, &toff, &tadj, &order, &depth, &size, &pre, &level_off, &ctr, &inf};
-    WD_TRY(cudaLaunchCooperativeKernel((void*)lca_sweeps_kernel, dim3(cgrid), dim3(256), args, 0, s));
-  }
-  WD_TRY(cudaMemcpyAsync(info, small, 128, cudaMemcpyDeviceToHost, s));
-  WD_TRY(cudaStreamSynchronize(s));
-  if (info[12] != (int32_t)nt) { cleanup(); return set_error(PT_ERR_INVALID, "pt_tree_who_displays: guest parent array has a cycle"); }
-  {
-    int levels = info[11];
-    WD_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, who_displays_kernel, 256, 0));
-    const int cgrid = (int)std::min<int64_t>((int64_t)dp.sms * std::max(1, std::min(occ, 4)), (nt + 255) / 256);
-    int64_t nn = nt, nl = nlab; int32_t* flags = small + 16;
-    const LcaRecord* rec = H->rec; const u64* keypos = H->keypos; const u64* table = H->table; const int64_t* lb = H->d_level_base;
-    const int32_t* gl2 = gl; const int32_t* l2hc = l2h; const int32_t* lo = level_off; const int32_t* ord = order; const int32_t* co = toff; const int32_t* ca = tadj;
-    void* args[] = {&nn, &levels, &lo, &ord, &co, &ca, &gl2, &l2hc, &nl, &rec, &keypos, &table, &lb, &disp, &flags};
-    WD_TRY(cudaLaunchCooperativeKernel((void*)who_displays_kernel, dim3(std::max(cgrid, 1)), dim3(256), args, 0, s));
+    int32_t* pending = (int32_t*)dalloc((size_t)nt * 4 + 4); unsigned long long* processed = (unsigned long long*)dalloc(8);
+    WD_PTR(pending); WD_PTR(processed);
+    WD_TRY(cudaMemcpyAsync(pending, tdeg, (size_t)nt * 4, cudaMemcpyDeviceToDevice, s));   // children still to come, per guest node
+    WD_TRY(cudaMemsetAsync(processed, 0, 8, s));
+    who_displays_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)dp.sms * 16, (nt + 255) / 256)), 256, 0, s>>>(
+        nt, gp, pending, toff, tadj, gl, l2h, nlab, H->rec, H->keypos, H->table, H->d_level_base, disp, small + 16, processed);
+    WD_TRY(cudaGetLastError());
+    unsigned long long hp2 = 0;
+    WD_TRY(cudaMemcpyAsync(&hp2, processed, 8, cudaMemcpyDeviceToHost, s));
+    WD_TRY(cudaStreamSynchronize(s));
+    if (hp2 != (unsigned long long)nt) { cleanup(); return set_error(PT_ERR_INVALID, "pt_tree_who_displays: guest parent array has a cycle"); }
   }
   wd_finish_kernel<<<grid, 256, 0, s>>>(nt, disp);
   WD_TRY(cudaMemcpyAsync(info, small, 128, cudaMemcpyDeviceToHost, s));
