@@ -25,40 +25,34 @@
 
 namespace ptgpu {
 
-constexpr int DP_MAX_CHILDREN = 64;
+constexpr int DP_CHILD_BITS = 20;             // low bits of a merge key: which child of u the candidate belongs to
+constexpr int DP_MAX_CHILDREN = 1024;         // general case (some child has several candidates): child sets are W = ceil(d / 64) words per induced node and the
+                                              // matching is serial in one thread; guest nodes whose children all have ONE candidate (every node over a
+                                              // single-labelled host) take the closed form below for ANY number of children
 
 struct DpArena {
   int32_t* mpos;       // list arena: host preorder positions
   int64_t mcap;
-  int32_t* scratch;    // per-level scratch, bump-allocated, reset every level
+  int32_t* scratch;    // scratch of the nodes that need the general case (or a sort of many children), bump-allocated
   int64_t scap;
-  unsigned long long* tops;  // [0] list arena top  [1] scratch top
+  unsigned long long* tops;  // [0] list arena top  [1] scratch top  [2] nodes processed
   int32_t* flags;      // [0] too many children  [1] list arena overflow  [2] scratch overflow
 };
 
-// in-place heap sort of 64-bit keys (small n; one thread)
-__device__ inline void dp_heapsort(u64* a, int n) {
-  for (int start = n / 2 - 1; start >= 0; --start) {
-    int r = start; const u64 v = a[r];
-    for (;;) { int c = 2 * r + 1; if (c >= n) break; if (c + 1 < n && a[c + 1] > a[c]) ++c; if (a[c] <= v) break; a[r] = a[c]; r = c; }
-    a[r] = v;
-  }
-  for (int end = n - 1; end > 0; --end) {
-    const u64 v = a[end]; a[end] = a[0];
-    int r = 0;
-    for (;;) { int c = 2 * r + 1; if (c >= end) break; if (c + 1 < end && a[c + 1] > a[c]) ++c; if (a[c] <= v) break; a[r] = a[c]; r = c; }
-    a[r] = v;
-  }
-}
+// (dp_heapsort: lca_kernels.cu, next to who_displays_kernel)
 
-// maximum matching saturating all d left nodes?  right node y is adjacent to left i iff bit i of rcov[y]
-__device__ inline bool dp_perfect_matching(int d, int r, const u64* rcov, int32_t* matchR, int32_t* seen) {
+// maximum matching saturating all d left nodes (the guest children)?  Right node y (an induced child) is adjacent to left i iff bit i of the
+// W-word child set cov[ridx[y] * W ...].  Kuhn's augmenting paths, iterative; L / it / chosen: d ints each
+__device__ inline bool dp_perfect_matching(int d, int r, int W, const u64* cov, const int32_t* ridx, int32_t* matchR, int32_t* seen, int32_t* L, int32_t* it, int32_t* chosen) {
   if (r < d) return false;
-  u64 all = 0;
-  for (int y = 0; y < r; ++y) { all |= rcov[y]; matchR[y] = -1; }
-  const u64 full = d == 64 ? ~0ull : ((1ull << d) - 1ull);
-  if ((all & full) != full) return false;
-  int L[DP_MAX_CHILDREN], it[DP_MAX_CHILDREN], chosen[DP_MAX_CHILDREN];
+  for (int w = 0; w < W; ++w) {
+    u64 all = 0;
+    for (int y = 0; y < r; ++y) all |= cov[(int64_t)ridx[y] * W + w];
+    const int bits = d - 64 * w;
+    const u64 full = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+    if ((all & full) != full) return false;
+  }
+  for (int y = 0; y < r; ++y) matchR[y] = -1;
   for (int i = 0; i < d; ++i) {
     for (int y = 0; y < r; ++y) seen[y] = 0;
     int depth = 0; L[0] = i; it[0] = 0;
@@ -66,11 +60,11 @@ __device__ inline bool dp_perfect_matching(int d, int r, const u64* rcov, int32_
     while (depth >= 0) {
       const int l = L[depth];
       int found = -1;
-      while (it[depth] < r) { const int y = it[depth]++; if (((rcov[y] >> l) & 1ull) && !seen[y]) { seen[y] = 1; found = y; break; } }
+      while (it[depth] < r) { const int y = it[depth]++; if (((cov[(int64_t)ridx[y] * W + (l >> 6)] >> (l & 63)) & 1ull) && !seen[y]) { seen[y] = 1; found = y; break; } }
       if (found < 0) { --depth; continue; }
       chosen[depth] = found;
       if (matchR[found] < 0) { for (int k = 0; k <= depth; ++k) matchR[chosen[k]] = L[k]; ok = true; break; }
-      if (depth + 1 >= DP_MAX_CHILDREN) break;
+      if (depth + 1 >= d) break;   // (cannot happen: the left nodes of an alternating path are distinct)
       L[depth + 1] = matchR[found]; it[depth + 1] = 0; ++depth;
     }
     if (!ok) return false;

@@ -536,22 +536,65 @@ __device__ __forceinline__ int32_t lca_one(const LcaRecord* __restrict__ rec, co
 // host every list has at most one entry, the induced subtree of k candidates needs exactly the k-1 consecutive LCAs, and
 // the matching degenerates to "all consecutive LCAs are the same node v and no candidate is v itself".  Each guest node = (small
 // sort of its children's images by host preorder) + k-1 LCA queries.
-constexpr int WD_MAX_CHILDREN = 64;
+constexpr int WD_MAX_CHILDREN = 64;   // up to here the images are sorted in registers / local memory; beyond, in a global scratch span
+
+// in-place heap sort of 32- or 64-bit keys (one thread)
+template <typename K>
+__device__ inline void dp_heapsort(K* a, int64_t n) {
+  for (int64_t start = n / 2 - 1; start >= 0; --start) {
+    int64_t r = start; const K v = a[r];
+    for (;;) { int64_t c = 2 * r + 1; if (c >= n) break; if (c + 1 < n && a[c + 1] > a[c]) ++c; if (a[c] <= v) break; a[r] = a[c]; r = c; }
+    a[r] = v;
+  }
+  for (int64_t end = n - 1; end > 0; --end) {
+    const K v = a[end]; a[end] = a[0];
+    int64_t r = 0;
+    for (;;) { int64_t c = 2 * r + 1; if (c >= end) break; if (c + 1 < end && a[c + 1] > a[c]) ++c; if (a[c] <= v) break; a[r] = a[c]; r = c; }
+    a[r] = v;
+  }
+}
+
+// a guest node with more than WD_MAX_CHILDREN children (a star, a wide multifurcation): the same test over (position, node) keys
+// sorted in a span of `big` -- every guest node is the child of one parent, so all spans together need at most nt keys
+__device__ __noinline__ int32_t wd_node_big(const int32_t cb, const int32_t ce, const int32_t* __restrict__ child_adj, const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos,
+                                            const u64* __restrict__ table, const int64_t* __restrict__ level_base, const int32_t* disp, u64* __restrict__ big, unsigned long long* __restrict__ big_top) {
+  int64_t k = 0;
+  for (int32_t j = cb; j < ce; ++j) {
+    const int32_t c = __ldcg(&disp[child_adj[j]]);
+    if (c == -2) continue;
+    if (c == -1) return -1;
+    ++k;
+  }
+  if (k == 0) return -2;
+  u64* keys = big + atomicAdd(big_top, (unsigned long long)k);
+  int64_t i = 0;
+  for (int32_t j = cb; j < ce; ++j) {
+    const int32_t c = __ldcg(&disp[child_adj[j]]);
+    if (c >= 0) keys[i++] = ((u64)rec[c].pos << 32) | (u64)(uint32_t)c;
+  }
+  if (k == 1) return (int32_t)(uint32_t)keys[0];
+  dp_heapsort(keys, k);
+  const int32_t v = lca_one(rec, keypos, table, level_base, (int32_t)(uint32_t)keys[0], (int32_t)(uint32_t)keys[k - 1]);
+  for (int64_t a = 0; a < k; ++a) if ((int32_t)(uint32_t)keys[a] == v) return -1;
+  for (int64_t a = 0; a + 1 < k; ++a)   // (two children with the same image have that image as their LCA, which is not v)
+    if (lca_one(rec, keypos, table, level_base, (int32_t)(uint32_t)keys[a], (int32_t)(uint32_t)keys[a + 1]) != v) return -1;
+  return v;
+}
 __device__ __forceinline__ int32_t wd_node(const int32_t u, const int32_t* __restrict__ child_off, const int32_t* __restrict__ child_adj, const int32_t* __restrict__ tlabel,
                                            const int32_t* __restrict__ l2h, int64_t nlab, const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos,
-                                           const u64* __restrict__ table, const int64_t* __restrict__ level_base, const int32_t* disp, int32_t* __restrict__ flags) {
+                                           const u64* __restrict__ table, const int64_t* __restrict__ level_base, const int32_t* disp, u64* __restrict__ big, unsigned long long* __restrict__ big_top) {
   const int32_t cb = child_off[u], ce = child_off[u + 1];
   if (cb == ce) {  // guest leaf: base case construct_base_cases :115-126
     const int32_t lab = tlabel[u];
     return lab < 0 ? -2 : ((int64_t)lab < nlab ? l2h[lab] : -1);
   }
+  if (ce - cb > WD_MAX_CHILDREN) return wd_node_big(cb, ce, child_adj, rec, keypos, table, level_base, disp, big, big_top);
   int32_t img[WD_MAX_CHILDREN]; uint32_t ps[WD_MAX_CHILDREN];
   int k = 0;
   for (int32_t j = cb; j < ce; ++j) {
     const int32_t c = __ldcg(&disp[child_adj[j]]);   // (written by another SM during the same launch: through L2)
     if (c == -2) continue;               // unlabelled dangling subtree: cleaned away
     if (c == -1) return -1;              // merge_child_poss :180-230: an empty child list empties the parent
-    if (k == WD_MAX_CHILDREN) { flags[0] = 1; return -1; }
     // insertion sort by host preorder position (sort_by_order :108-111)
     const uint32_t p = rec[c].pos;
     int a = k++;
@@ -572,13 +615,13 @@ __global__ void __launch_bounds__(256) who_displays_kernel(int64_t nt, const int
                                                            const int32_t* __restrict__ child_adj, const int32_t* __restrict__ tlabel, const int32_t* __restrict__ l2h, int64_t nlab,
                                                            const LcaRecord* __restrict__ rec, const u64* __restrict__ keypos, const u64* __restrict__ table,
                                                            const int64_t* __restrict__ level_base, int32_t* disp /* -2 dead, -1 not displayed, >= 0 host node */,
-                                                           int32_t* __restrict__ flags /* [0] too many children */, unsigned long long* __restrict__ processed) {
+                                                           u64* __restrict__ big /* nt keys: sort space of the nodes with many children */, unsigned long long* __restrict__ processed /* [1]: top of big */) {
   unsigned long long done = 0;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < nt; idx += (int64_t)gridDim.x * blockDim.x) {
     int32_t u = (int32_t)idx;
     if (child_off[u] != child_off[u + 1]) continue;
     for (;;) {
-      disp[u] = wd_node(u, child_off, child_adj, tlabel, l2h, nlab, rec, keypos, table, level_base, disp, flags);
+      disp[u] = wd_node(u, child_off, child_adj, tlabel, l2h, nlab, rec, keypos, table, level_base, disp, big, processed + 1);
       ++done;
       const int32_t p = gparent[u];
       if (p < 0 || p >= nt) break;
@@ -1026,12 +1069,13 @@ extern "C" int pt_tree_who_displays(const int32_t* host_parent, const int32_t* h
   if (info[17]) { cleanup(); return set_error(PT_ERR_INVALID, "single-label map for multi-labeled tree/network"); }  // label_matching.hpp:51-52
   if (info[18]) { cleanup(); return set_error(PT_ERR_INVALID, "pt_tree_who_displays: label id out of range (must be < n + nt)"); }
   {
-    int32_t* pending = (int32_t*)dalloc((size_t)nt * 4 + 4); unsigned long long* processed = (unsigned long long*)dalloc(8);
-    WD_PTR(pending); WD_PTR(processed);
+    int32_t* pending = (int32_t*)dalloc((size_t)nt * 4 + 4); unsigned long long* processed = (unsigned long long*)dalloc(16);
+    u64* big = (u64*)dalloc((size_t)nt * 8);   // sort space of the guest nodes with more than WD_MAX_CHILDREN children
+    WD_PTR(pending); WD_PTR(processed); WD_PTR(big);
     WD_TRY(cudaMemcpyAsync(pending, tdeg, (size_t)nt * 4, cudaMemcpyDeviceToDevice, s));   // children still to come, per guest node
-    WD_TRY(cudaMemsetAsync(processed, 0, 8, s));
+    WD_TRY(cudaMemsetAsync(processed, 0, 16, s));
     who_displays_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)dp.sms * 16, (nt + 255) / 256)), 256, 0, s>>>(
-        nt, gp, pending, toff, tadj, gl, l2h, nlab, H->rec, H->keypos, H->table, H->d_level_base, disp, small + 16, processed);
+        nt, gp, pending, toff, tadj, gl, l2h, nlab, H->rec, H->keypos, H->table, H->d_level_base, disp, big, processed);
     WD_TRY(cudaGetLastError());
     unsigned long long hp2 = 0;
     WD_TRY(cudaMemcpyAsync(&hp2, processed, 8, cudaMemcpyDeviceToHost, s));
@@ -1046,7 +1090,6 @@ extern "C" int pt_tree_who_displays(const int32_t* host_parent, const int32_t* h
 #undef WD_TRY
 #undef WD_PTR
   cleanup();
-  if (info[16]) return set_error(PT_ERR_UNSUPPORTED, "pt_tree_who_displays: a guest node has more than %d children", WD_MAX_CHILDREN);
   return PT_OK;
 }
 
