@@ -89,9 +89,10 @@ int pt_lca_free(pt_lca* h);
  * for a SINGLE-LABELLED TREE host: out_host_node[u] = the host node that minimally displays the guest subtree below u
  * (the one entry of the reference's list), or -1 if none does.  The guest is displayed iff out_host_node[guest root] >= 0
  * (containment.hpp:83).  Internally the induced-subtree step of the reference (k-1 LCAs of consecutive candidates,
- * utils/induced_tree.hpp:128-138) runs as one wavefront over the guest's levels on top of pt_lca.
+ * utils/induced_tree.hpp:128-138) runs as a dataflow over the guest tree (leaves first, a node as soon as its last child is done)
+ * on top of pt_lca.  Any number of children per guest node (more than 64: sorted in device scratch by the one thread that owns the node).
  * Labels: dense ids < n + nt shared by both trees, -1 = unlabelled; only labels on leaves count.  Multi-labelled hosts
- * (the reference's MUL-trees) return PT_ERR_INVALID; more than 64 children on one guest node PT_ERR_UNSUPPORTED.
+ * (the reference's MUL-trees) return PT_ERR_INVALID: use pt_who_build.
  * ---------------------------------------------------------------------------------------------- */
 int pt_tree_who_displays(const int32_t* host_parent, const int32_t* host_label, int64_t n, const int32_t* guest_parent,
                          const int32_t* guest_label, int64_t nt, int32_t* out_host_node, pt_mem mem, void* stream);
@@ -110,10 +111,12 @@ int pt_tree_highest_displayed(const int32_t* guest_parent, const int32_t* who, i
  *     TreeInComponent::unzip_retis / highest_displayed_ancestor            utils/containment.hpp:262-312, 328-344
  *     TreeComponentInfos (comp_root, visible_leaf, component DAG)           utils/tree_components.hpp:41-234
  * The host tree may be MULTI-LABELLED (the reference's ROMulTree: a leaf label may occur several times); the guest is a
- * single-labelled tree.  pt_who_build runs the whole DP (a wavefront over the guest's levels on top of pt_lca) and keeps, per
+ * single-labelled tree.  pt_who_build runs the whole DP (a dataflow over the guest tree on top of pt_lca) and keeps, per
  * guest node u, the list of host nodes that MINIMALLY display the guest subtree below u, ascending in host preorder -- what
- * who_displays(u) returns.  The guest is displayed iff the list of its root is not empty (:83).  Guest nodes with more than 64
- * children: PT_ERR_UNSUPPORTED.  Labels: dense ids < n + nt shared by both trees, -1 = none; only leaf labels count.
+ * who_displays(u) returns.  The guest is displayed iff the list of its root is not empty (:83).  A guest node whose
+ * children all have ONE candidate (always, over a single-labelled host) may have any number of children; one whose children have several
+ * candidates each is matched over ceil(d / 64)-word child sets by one thread and is limited to 1024 children (more: PT_ERR_UNSUPPORTED).
+ * Labels: dense ids < n + nt shared by both trees, -1 = none; only leaf labels count.
  *   pt_who_total : number of entries over all lists;  pt_who_lists : off[nt + 1] and the concatenated lists (HOST or DEVICE)
  *   pt_who_highest_displayed : highest_displayed_ancestor of EVERY guest node over those lists ("displayed by the host root
  *       alone" = the list is exactly { host_root }, :340); out[guest root] = guest root

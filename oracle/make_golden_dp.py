@@ -3,6 +3,8 @@ through oracle/_ref/ref_tc; the committed JSON travels to the GPU box).
 
   tests/golden/whomul_ref.json  (multi-labelled host tree, guest tree) -> who_displays(u) of the REFERENCE for every guest node
         (TreeInTreeContainment<ROMulTree<>, ROTree<>>, utils/containment.hpp:27-233, via `ref_tc whomul`); data/test_tree.nw first
+  tests/golden/whowide_ref.json the same for guests (and hosts) with WIDE nodes: 65 ... 300 children on one node (stars, wide multifurcations,
+        single- and multi-labelled hosts) -- beyond one 64-bit child-set word
   tests/golden/hda_ref.json     (host network, guest tree) -> the MUL-tree the REFERENCE unzips below the host's root
         (TreeInComponent::unzip_retis :262-312) and highest_displayed_ancestor(v) of every guest node (:328-344), via `ref_tc hda`
   tests/golden/comps_ref.json   network -> comp_root / visible_leaf per node and the component DAG of the REFERENCE's
@@ -107,6 +109,67 @@ def make_whomul():
               open(os.path.join(GOLD, "whomul_ref.json"), "w"), indent=0)
     disp = sum(1 for it in items if it["reference"] != "CRASH" and it["reference"][0])
     print("whomul_ref.json:", len(items), "pairs,", crashed, "reference crashes,", disp, "with a displayed guest root")
+
+
+def wide_tree(rng, leaves, wide, max_deg):
+    """random tree over `leaves` in which one join takes `wide` subtrees at once (a node with `wide` children)"""
+    nodes = list(leaves)
+    rng.shuffle(nodes)
+    done_wide = False
+    while len(nodes) > 1:
+        if not done_wide and len(nodes) >= wide and rng.integers(0, 3) == 0 or (not done_wide and len(nodes) == wide):
+            k = wide; done_wide = True
+        else:
+            k = int(min(len(nodes), rng.integers(2, max_deg + 1)))
+            if not done_wide and len(nodes) - k + 1 < wide:
+                k = wide if len(nodes) >= wide else k; done_wide = done_wide or k == wide
+        idx = sorted(rng.choice(len(nodes), k, replace=False).tolist(), reverse=True)
+        kids = [nodes.pop(i) for i in idx]
+        nodes.insert(int(rng.integers(0, len(nodes) + 1)), "(" + ",".join(kids) + ")")
+    return nodes[0] + ";"
+
+
+def make_whowide():
+    rng = np.random.default_rng(20261021)
+    pairs = []
+    for trial in range(36):
+        wide = int(rng.choice([65, 66, 70, 100, 128, 129, 200, 300]))
+        l = wide + int(rng.integers(0, 40))
+        labs = [name(i) for i in range(l)]
+        kind = trial % 6
+        if kind == 0:      # star guest in a star host (displayed), or in a host whose root is wider still
+            host = "(" + ",".join(rng.permutation(labs).tolist()) + ");"
+            guest = "(" + ",".join(rng.permutation(labs[:wide]).tolist()) + ");"
+        elif kind == 1:    # wide guest = the host itself, children shuffled (displayed)
+            host = wide_tree(rng, labs, wide, 3)
+            guest = host
+        elif kind == 2:    # wide guest against a binary host (not displayed at the wide node)
+            host = rand_tree(rng, labs, 2)
+            guest = wide_tree(rng, labs, wide, 3)
+        elif kind == 3:    # multi-labelled host with a wide node, guest = one leaf per label
+            host_leaves = labs + [labs[int(rng.integers(0, l))] for _ in range(int(rng.integers(1, l // 2)))]
+            host = wide_tree(rng, host_leaves, wide + 20, 3)
+            guest = restricted(rng, host)
+        elif kind == 4:    # multi-labelled host, independent wide guest
+            host_leaves = labs + [labs[int(rng.integers(0, l))] for _ in range(int(rng.integers(1, l // 2)))]
+            host = wide_tree(rng, host_leaves, wide + 20, 4)
+            guest = wide_tree(rng, labs, wide, 4)
+        else:              # star host with every label twice, star guest: the matching has to choose
+            host = "(" + ",".join(rng.permutation(labs + labs).tolist()) + ");"
+            guest = "(" + ",".join(rng.permutation(labs).tolist()) + ");"
+        pairs.append((host, guest))
+    blocks = run_lines("whomul", [x for p in pairs for x in p])[:len(pairs)]
+    items = []
+    for (h, g), b in zip(pairs, blocks):
+        if any(x in ("CRASH", "EXC") for x in b):
+            items.append(dict(host=h, guest=g, reference="CRASH"))
+            continue
+        items.append(dict(host=h, guest=g, reference=[[int(x) for x in line.split(":")[1].split()] for line in b if ":" in line]))
+    crashed = sum(1 for it in items if it["reference"] == "CRASH")
+    json.dump(dict(source="oracle/_ref/ref_tc whomul on pairs with a node of 65 ... 320 children (reference TreeInTreeContainment::who_displays, containment.hpp:72-230)", crashed=crashed, items=items),
+              open(os.path.join(GOLD, "whowide_ref.json"), "w"), indent=0)
+    disp = sum(1 for it in items if it["reference"] != "CRASH" and it["reference"][0])
+    print("whowide_ref.json:", len(items), "pairs,", crashed, "reference crashes,", disp, "with a displayed guest root")
 
 
 def gen_pairs(count, l, r, seed, kind):
@@ -221,7 +284,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "vcr":
         make_vcr()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "whowide":
+        make_whowide()
+        sys.exit(0)
     make_whomul()
+    make_whowide()
     make_hda()
     make_comps()
     make_edgelist()

@@ -305,10 +305,11 @@ int orc_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, int n
  * to distinct children y of x, y in A(child); A(u) = ancestors-or-self of A'(u); the answer M(u) = the minimal nodes of A'(u).
  * Every host node is tried, no induced tree, no LCA.  Unlabelled guest leaves are cleaned away (as everywhere in this repo).
  * out_off[nt+1] / out_adj: M(u) in ascending node id (the reference sorts by ITS preorder: compare as sets).
- * returns the total number of entries, or -1 if out_adj (capacity cap) is too small, -3 on more than 64 guest children. */
-typedef struct { int nl, nr; const uint64_t* adj; int matchR[4096]; uint8_t seen[4096]; } orc_match_ctx;
+ * returns the total number of entries, or -1 if out_adj (capacity cap) is too small, -3 on more than 4096 guest or host children.
+ * (adjacency of the matching: adj[y * words + i / 64] bit i % 64 = "guest child i can be displayed below host child y") */
+typedef struct { int nl, nr, words; const uint64_t* adj; int matchR[4096]; uint8_t seen[4096]; } orc_match_ctx;
 static int orc_try_match(orc_match_ctx* c, int i) {
-  for (int y = 0; y < c->nr; ++y) if (((c->adj[y] >> i) & 1ull) && !c->seen[y]) {
+  for (int y = 0; y < c->nr; ++y) if (((c->adj[(size_t)y * c->words + (i >> 6)] >> (i & 63)) & 1ull) && !c->seen[y]) {
     c->seen[y] = 1;
     if (c->matchR[y] < 0 || orc_try_match(c, c->matchR[y])) { c->matchR[y] = i; return 1; }
   }
@@ -330,16 +331,17 @@ int orc_mul_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, i
   uint8_t* A = (uint8_t*)calloc((size_t)nt * (size_t)n, 1); uint8_t* M = (uint8_t*)calloc((size_t)nt * (size_t)n, 1); uint8_t* dead = (uint8_t*)calloc((size_t)nt, 1);
   int rc = 0;
   orc_match_ctx* mc = (orc_match_ctx*)malloc(sizeof(orc_match_ctx));
-  uint64_t* adj = (uint64_t*)malloc(4096 * 8);
+  uint64_t* adj = (uint64_t*)malloc((size_t)4096 * 64 * 8);
+  int* kids = (int*)malloc((size_t)4096 * sizeof(int));
   for (int d = maxtd; d >= 0 && rc == 0; --d) for (int u = 0; u < nt && rc == 0; ++u) if (tdepth[u] == d) {
     uint8_t* Au = A + (size_t)u * n; uint8_t* Mu = M + (size_t)u * n;
     if (tdeg[u] == 0) {
       if (tlabel[u] < 0) { dead[u] = 1; continue; }
       for (int v = 0; v < n; ++v) if (hdeg[v] == 0 && hlabel[v] == tlabel[u]) Mu[v] = 1;
     } else {
-      int kids[64], nk = 0, empty = 0;
+      int nk = 0, empty = 0;
       for (int c = 0; c < nt; ++c) if (tparent[c] == u && !dead[c]) {
-        if (nk == 64) { rc = -3; break; }
+        if (nk == 4096) { rc = -3; break; }
         kids[nk++] = c;
         int any = 0; for (int v = 0; v < n; ++v) any |= M[(size_t)c * n + v];
         if (!any) empty = 1;
@@ -353,8 +355,10 @@ int orc_mul_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, i
         for (int x = 0; x < n; ++x) {
           const int r = hoff[x + 1] - hoff[x];
           if (r < nk || r > 4096) continue;
-          for (int k = 0; k < r; ++k) { const int y = hadj[hoff[x] + k]; uint64_t m = 0; for (int i = 0; i < nk; ++i) if (A[(size_t)kids[i] * n + y]) m |= 1ull << i; adj[k] = m; }
-          mc->nl = nk; mc->nr = r; mc->adj = adj;
+          const int words = (nk + 63) / 64;
+          memset(adj, 0, (size_t)r * words * 8);
+          for (int k = 0; k < r; ++k) { const int y = hadj[hoff[x] + k]; for (int i = 0; i < nk; ++i) if (A[(size_t)kids[i] * n + y]) adj[(size_t)k * words + (i >> 6)] |= 1ull << (i & 63); }
+          mc->nl = nk; mc->nr = r; mc->words = words; mc->adj = adj;
           for (int k = 0; k < r; ++k) mc->matchR[k] = -1;
           int ok = 1;
           for (int i = 0; i < nk && ok; ++i) { memset(mc->seen, 0, (size_t)r); ok = orc_try_match(mc, i); }
@@ -381,7 +385,7 @@ int orc_mul_who_displays(int n, const int32_t* hparent, const int32_t* hlabel, i
     }
     out_off[nt] = total;
   }
-  free(hdeg); free(tdeg); free(tdepth); free(hoff); free(hadj); free(A); free(M); free(dead); free(mc); free(adj);
+  free(hdeg); free(tdeg); free(tdepth); free(hoff); free(hadj); free(A); free(M); free(dead); free(mc); free(adj); free(kids);
   return rc ? rc : total;
 }
 

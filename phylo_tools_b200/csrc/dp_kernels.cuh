@@ -102,19 +102,27 @@ __device__ __forceinline__ void dp_node(const int32_t u, const int32_t* __restri
   if (d == 0) { mlen[u] = -2; return; }
   if (missing) { mlen[u] = 0; moff[u] = 0; return; }
   if (d == 1) { mlen[u] = __ldcg(&mlen[only]); moff[u] = __ldcg(&moff[only]); return; }   // :167 -- the same list (shared, never modified)
-  if (d > DP_MAX_CHILDREN) { A.flags[0] = 1; mlen[u] = 0; moff[u] = 0; return; }
-  if (single && d <= 8) {
+  if (single) {
     // every child has exactly one candidate: u is displayed iff the candidates sit in d different branches of their
     // common ancestor v, i.e. all consecutive LCAs (in preorder) are v and no candidate is v itself
-    uint32_t ps[8]; int k = 0;
+    uint32_t few[8]; uint32_t* ps = few;
+    if (d > 8) {   // many children (a star, a wide multifurcation): sorted in a scratch span instead of registers
+      const int64_t need = d + 2;
+      const unsigned long long sat = atomicAdd(&A.tops[1], (unsigned long long)need);
+      if ((int64_t)(sat + need) > A.scap) { A.flags[2] = 1; mlen[u] = 0; moff[u] = 0; return; }
+      ps = reinterpret_cast<uint32_t*>(A.scratch + sat);
+    }
+    int k = 0;
     for (int32_t j = cb; j < ce; ++j) {
       const int32_t c = child_adj[j];
       if (__ldcg(&mlen[c]) != 1) continue;
       const uint32_t p = (uint32_t)__ldcg(&A.mpos[__ldcg(&moff[c])]);
+      if (d > 8) { ps[k++] = p; continue; }
       int a = k++;
       while (a > 0 && ps[a - 1] > p) { ps[a] = ps[a - 1]; --a; }
       ps[a] = p;
     }
+    if (d > 8) dp_heapsort(ps, (int64_t)d);
     const int32_t v = lca_one(rec, keypos, table, level_base, nodeat[ps[0]], nodeat[ps[d - 1]]);
     const uint32_t vp = rec[v].pos;
     bool ok = true;
@@ -126,46 +134,56 @@ __device__ __forceinline__ void dp_node(const int32_t u, const int32_t* __restri
     A.mpos[at] = (int32_t)vp; moff[u] = (int64_t)at; mlen[u] = 1;
     return;
   }
-  // ---- general case: scratch = keys (2K words) | per induced node (V <= 2K): pos, depth, first, next, nchild, sb | cov (2V words)
-  //      | stack V | rcov 2V | matchR V | seen V | result K
+  if (d > DP_MAX_CHILDREN) { A.flags[0] = 1; mlen[u] = 0; moff[u] = 0; return; }
+  // ---- general case: W = ceil(d / 64) words per child set.  scratch = keys (2K words) | cov (2VW words) | per induced node (V <= 2K): pos, depth,
+  //      first, next, nchild, sb | stack V | ridx V | matchR V | seen V | result K | L, it, chosen (d each)
+  const int W = (d + 63) >> 6;
   const int64_t V = 2 * K;
-  const int64_t need = 2 * K + 6 * V + 2 * V + V + 2 * V + V + V + K + 16;
+  const int64_t need = 2 * K + 2 * V * W + 6 * V + 4 * V + K + 3 * (int64_t)d + 16;
   const unsigned long long sat = atomicAdd(&A.tops[1], (unsigned long long)need);
   if ((int64_t)(sat + need) > A.scap) { A.flags[2] = 1; mlen[u] = 0; moff[u] = 0; return; }
   int32_t* sp = A.scratch + sat + (sat & 1);   // 8-byte alignment for the 64-bit arrays
   u64* keys = reinterpret_cast<u64*>(sp); sp += 2 * K;
-  u64* cov = reinterpret_cast<u64*>(sp); sp += 2 * V;
-  u64* rcov = reinterpret_cast<u64*>(sp); sp += 2 * V;
+  u64* cov = reinterpret_cast<u64*>(sp); sp += 2 * V * W;
   int32_t* vpos = sp; sp += V; int32_t* vdepth = sp; sp += V; int32_t* vfirst = sp; sp += V; int32_t* vnext = sp; sp += V;
-  int32_t* vnch = sp; sp += V; int32_t* vsb = sp; sp += V; int32_t* stack = sp; sp += V; int32_t* matchR = sp; sp += V; int32_t* seen = sp; sp += V;
-  int32_t* result = sp;
+  int32_t* vnch = sp; sp += V; int32_t* vsb = sp; sp += V; int32_t* stack = sp; sp += V; int32_t* ridx = sp; sp += V; int32_t* matchR = sp; sp += V; int32_t* seen = sp; sp += V;
+  int32_t* result = sp; sp += K;
+  int32_t* mL = sp; sp += d; int32_t* mit = sp; sp += d; int32_t* mchosen = sp;
   {
     int64_t k = 0; int ci = 0;
     for (int32_t j = cb; j < ce; ++j) {
       const int32_t c = child_adj[j], len = __ldcg(&mlen[c]);
       if (len == -2) continue;
       const int64_t o = __ldcg(&moff[c]);
-      for (int t = 0; t < len; ++t) keys[k++] = ((u64)(uint32_t)__ldcg(&A.mpos[o + t]) << 8) | (u64)ci;
+      for (int t = 0; t < len; ++t) keys[k++] = ((u64)(uint32_t)__ldcg(&A.mpos[o + t]) << DP_CHILD_BITS) | (u64)ci;
       ++ci;
     }
   }
-  dp_heapsort(keys, (int)K);
+  dp_heapsort(keys, K);
   int nv = 0, top = -1, nres = 0, cur = -1;
   // a node is FINISHED when it leaves the stack: its subtree is complete, so it can be matched and handed to its parent
   auto finish = [&](int x, int q) {
     int succ = 0;
     if (!vsb[x] && vnch[x] >= d) {
       int r = 0;
-      for (int y = vfirst[x]; y >= 0; y = vnext[y]) rcov[r++] = cov[y];
-      if (dp_perfect_matching(d, r, rcov, matchR, seen)) { result[nres++] = vpos[x]; succ = 1; }   // perfect_child_matching :174-177
+      for (int y = vfirst[x]; y >= 0; y = vnext[y]) ridx[r++] = y;
+      if (dp_perfect_matching(d, r, W, cov, ridx, matchR, seen, mL, mit, mchosen)) { result[nres++] = vpos[x]; succ = 1; }   // perfect_child_matching :174-177
     }
-    if (q >= 0) { cov[q] |= cov[x]; vsb[q] |= succ | vsb[x]; vnext[x] = vfirst[q]; vfirst[q] = x; vnch[q]++; }   // :140-149, :160
+    if (q >= 0) {   // :140-149, :160
+      for (int w = 0; w < W; ++w) cov[(int64_t)q * W + w] |= cov[(int64_t)x * W + w];
+      vsb[q] |= succ | vsb[x]; vnext[x] = vfirst[q]; vfirst[q] = x; vnch[q]++;
+    }
   };
-  auto newnode = [&](uint32_t p, u64 self) { const int x = nv++; vpos[x] = (int32_t)p; vdepth[x] = (int32_t)(keypos[p] >> 32); vfirst[x] = -1; vnext[x] = -1; vnch[x] = 0; vsb[x] = 0; cov[x] = self; return x; };
+  auto newnode = [&](uint32_t p) {
+    const int x = nv++; vpos[x] = (int32_t)p; vdepth[x] = (int32_t)(keypos[p] >> 32); vfirst[x] = -1; vnext[x] = -1; vnch[x] = 0; vsb[x] = 0;
+    for (int w = 0; w < W; ++w) cov[(int64_t)x * W + w] = 0ull;
+    return x;
+  };
   for (int64_t j = 0; j < K; ++j) {
-    const uint32_t p = (uint32_t)(keys[j] >> 8); const u64 bit = 1ull << (keys[j] & 255);
-    if (cur >= 0 && (uint32_t)vpos[cur] == p) { cov[cur] |= bit; continue; }   // the same host node is a candidate of several children
-    const int w = newnode(p, bit);
+    const uint32_t p = (uint32_t)(keys[j] >> DP_CHILD_BITS); const int ci = (int)(keys[j] & ((1u << DP_CHILD_BITS) - 1u));
+    if (cur >= 0 && (uint32_t)vpos[cur] == p) { cov[(int64_t)cur * W + (ci >> 6)] |= 1ull << (ci & 63); continue; }   // the same host node is a candidate of several children
+    const int w = newnode(p);
+    cov[(int64_t)w * W + (ci >> 6)] |= 1ull << (ci & 63);
     cur = w;
     if (top < 0) { stack[++top] = w; continue; }
     const int t = stack[top];
@@ -173,7 +191,7 @@ __device__ __forceinline__ void dp_node(const int32_t u, const int32_t* __restri
     const uint32_t lp = rec[lnode].pos; const int32_t ld = (int32_t)(keypos[lp] >> 32);
     if (lp != (uint32_t)vpos[t]) {
       while (top >= 1 && vdepth[stack[top - 1]] >= ld) { finish(stack[top], stack[top - 1]); --top; }
-      if ((uint32_t)vpos[stack[top]] != lp) { const int Lx = newnode(lp, 0ull); finish(stack[top], Lx); stack[top] = Lx; }
+      if ((uint32_t)vpos[stack[top]] != lp) { const int Lx = newnode(lp); finish(stack[top], Lx); stack[top] = Lx; }
     }
     stack[++top] = w;
   }
@@ -484,7 +502,7 @@ int pt_who_build(pt_who** out, const int32_t* host_parent, const int32_t* host_l
     DP_TRY(cudaMemcpyAsync(&processed, tops + 2, 8, cudaMemcpyDeviceToHost, s));
     DP_TRY(cudaStreamSynchronize(s));
     if (processed != (unsigned long long)nt) return fail(set_error(PT_ERR_INVALID, "pt_who_build: guest parent array has a cycle"));
-    if (info[32]) return fail(set_error(PT_ERR_UNSUPPORTED, "pt_who_build: a guest node has more than %d children", DP_MAX_CHILDREN));
+    if (info[32]) return fail(set_error(PT_ERR_UNSUPPORTED, "pt_who_build: a guest node whose children have several candidates each has more than %d children", DP_MAX_CHILDREN));
     if (!info[33] && !info[34]) {
       // compact into CSR order by guest node, positions -> host node ids
       int32_t* len = (int32_t*)dalloc((size_t)nt * 4 + 4); DP_PTR(len);

@@ -180,6 +180,25 @@ def _canon(parent, label):
     return rec(root)
 
 
+def test_mul_who_displays_oracle_equals_reference_on_wide_nodes(oracle):
+    """the same beyond one 64-bit child-set word: guests / hosts with a node of 65 ... 320 children (tests/golden/whowide_ref.json)"""
+    from conftest import load_golden
+    gold = load_golden("whowide_ref.json")
+    checked = multi = wide = 0
+    for it in gold["items"]:
+        hp, hl, gp, gl = oracle.tree_arrays_from_newick(it["host"], it["guest"])
+        gp_ = np.asarray(gp)
+        wide += int(np.bincount(gp_[gp_ >= 0]).max() > 64)
+        if it["reference"] == "CRASH":
+            continue
+        off, adj = oracle.mul_who_displays(hp, hl, gp, gl)
+        for u, ref in enumerate(it["reference"]):
+            assert sorted(adj[off[u]:off[u + 1]].tolist()) == sorted(ref), (it["host"], it["guest"], u)
+            multi += len(ref) > 1
+        checked += 1
+    assert checked >= 28 and multi >= 500 and wide == len(gold["items"])
+
+
 def test_mul_who_displays_oracle_equals_reference(oracle):
     """the definition-based restatement (orc_mul_who_displays) against the reference's own lists on multi-labelled hosts
     (tests/golden/whomul_ref.json, data/test_tree.nw first); the reference sorts by its own preorder: compared as sets"""
