@@ -67,6 +67,15 @@ def measured_traffic(kernel, units):
         return None
 
 
+def measured_ncu(kernel):
+    """what the committed ncu --set full capture of `kernel` says beside the bytes: L2 hit rate, warp execution efficiency (active threads
+    per instruction), achieved occupancy, issue-slot utilisation, top stall reasons (profiles/traffic_r02.json; static, from the capture)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))[kernel].get("ncu")
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -821,7 +830,7 @@ def main():
     ach = ALG_BYTES_PER_INSTANCE * B / (k0 / 1000.0) / 1e9
     roofline = {"bound": "hbm", "kernel": "tc_persistent_kernel (the one launch of a step; %d instances on this GPU)" % B, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": measured_traffic("tc_persistent_kernel", B), "kernel_ms": k0, "kernel_ms_per_rank_avg_max": r["k_all"], "kernel_share_of_step": k0 / ms_per_step, "peak_source": peak_src,
-                "algorithmic_bytes_per_instance": ALG_BYTES_PER_INSTANCE, "bytes_actually_read_per_instance": r["in_bytes"] / max(B, 1),
+                "algorithmic_bytes_per_instance": ALG_BYTES_PER_INSTANCE, "bytes_actually_read_per_instance": r["in_bytes"] / max(B, 1), "ncu": measured_ncu("tc_persistent_kernel"),
                 "note": "instance-resident shared-memory solver: bound by instruction fetch and dependent shared-memory latency, not HBM (SURVEY 8(d)); see profiles/"}
 
     # ---- end to end: HOST (pinned) buffers -> pt_batch_create (H2D) -> pt_batch_contain_sharded -> D2H of the result words -> free ----
