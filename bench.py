@@ -334,7 +334,7 @@ def lca_leg(pt, torch, leaves, queries, peak, rank=0, world=1, dist=None):
            "resident_bytes": info["device_bytes"], "checksum": checksum,
            "roofline": {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak, "traffic": measured_traffic("lca_query_kernel", queries),
                         "model": "40 B/query (SURVEY 8(d)); uniform pairs need 2 random records per query and B200 moves a 128-byte line per random read (profiles/micro_gather.cu): 254 B/query measured, "
-                                 "i.e. the kernel moves 5.3 TB/s of DRAM lines = 0.81 of the measured peak; bound for uniform pairs with this layout = peak / 254 B = 25.7 G queries/s"}}
+                                 "i.e. the kernel moves 5.3 TB/s of DRAM lines = 0.81 of the measured peak; bound for uniform pairs with this layout = peak / (2 x 128-byte lines + 12 B streamed) = 24.4 G queries/s (DESIGN.md section 3)"}}
     if rank == 0:
         # end to end: queries in pinned host memory in, answers in pinned host memory out (H2D 8 B + D2H 4 B per query inside the call)
         q2 = min(queries, 20_000_000)
